@@ -1,0 +1,439 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: batched u32 lower_bound over an S+-tree of 2^28 keys.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...             # the reference's CPU path (oracle restatement)
+
+A "step" is one pass of the hot path over one batch of 10^8 synthetic queries per GPU.
+Own arm: one process per GPU (torchrun), index replicated, queries sharded, no collective on the
+data path; `value` is whole-job queries/s with inputs resident in HBM, timed with CUDA events on
+the launching stream between barriers, max over ranks.  `e2e` is the same metric through the
+public host-buffer API (sst_query: pinned host -> H2D -> kernel -> D2H).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "suffix-array-searching_b200"))
+
+MAX = 0x7FFFFFFF
+METRIC = "u32 lower_bound queries/s (2^28 keys)"
+UNIT = "queries/s"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def shard_range(total: int, rank: int, world: int):
+    """Contiguous shard rule of static-search-tree/src/bin/bench.rs:558-573: chunk = ceil(total / world)."""
+    chunk = -(-total // world)
+    s = min(total, rank * chunk)
+    e = min(total, (rank + 1) * chunk)
+    return s, e
+
+
+def hbm_levels(layer_nodes, l2_bytes):
+    """a level is HBM-resident iff the cumulative size root..level exceeds L2."""
+    cum, h = 0, 0
+    for nodes in layer_nodes:
+        cum += nodes * 64
+        if cum > l2_bytes:
+            h += 1
+    return h
+
+
+def layer_nodes_for(n, B=16):
+    def prev_keys(x):
+        return -(-(-(-x // B)) // (B + 1)) * B
+
+    sizes = [n]
+    while sizes[-1] > B:
+        sizes.append(prev_keys(sizes[-1]))
+    return [-(-s // B) for s in reversed(sizes)]
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (profiling recipe's clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu),
+                 "-f", self.path], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            sm, mx, reasons = [], [], set()
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            if sm:
+                out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        except Exception:
+            pass
+        finally:
+            try:
+                os.unlink(self.path)
+            except Exception:
+                pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the path (oracle restatement of
+# batched(STree16::batch_final::<128>) on new_params(vals, true, false, false), bench_binsearch.rs:239-252)
+# ------------------------------------------------------------------------------------------------
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def gen_keys_host(n, seed):
+    rng = np.random.default_rng(seed)
+    v = rng.integers(0, MAX, n, dtype=np.uint32)
+    v[0] = MAX
+    v.sort()
+    return v
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as O
+
+    O.build()
+    threads = host_threads()
+    n = args.n_keys
+    t0 = time.time()
+    keys = gen_keys_host(n, args.seed)
+    tree = O.Tree.stree(keys, left_max=True)
+    build_s = time.time() - t0
+    sample = args.ref_sample
+    rng = np.random.default_rng(args.seed + 1)
+    batches = [rng.integers(0, MAX, sample, dtype=np.uint32) for _ in range(2)]
+    for w in range(max(args.warmup, 1)):
+        tree.batch_final(batches[w % 2], threads)
+    secs = []
+    for k in range(args.steps):
+        _, s = tree.batch_final(batches[k % 2], threads)
+        secs.append(s)
+    total = sum(secs)
+    value = sample * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": f"stree16 left_max lower_bound, {n} sorted uniform u32 keys; CPU batch_final<128> (s_tree.rs:303-326)",
+                   "n_keys": n, "queries_per_step": sample, "host_build_s": round(build_s, 2)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} uniform queries per step over the full {n}-key tree, {threads} host threads, AVX2={bool(O.lib().orc_has_avx2())}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# own arm
+# ------------------------------------------------------------------------------------------------
+def run_own(args):
+    import ctypes as C
+
+    import torch
+
+    import sst_b200 as sst
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if sst.device_count() < 1:
+        raise RuntimeError("no sm_100 device: sst_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n, nq = args.n_keys, args.queries
+    L = sst.lib()
+    # ---- index: replicated (same seed on every rank), built by the GPU layout builder ----
+    g = torch.Generator(device=dev).manual_seed(args.seed)
+    keys = torch.randint(0, MAX, (n,), dtype=torch.int32, device=dev, generator=g)
+    keys[0] = MAX
+    keys = torch.sort(keys).values.contiguous()
+    t0 = time.time()
+    tree = sst.STree16.new_params(keys, True, False, False)
+    torch.cuda.synchronize()
+    build_s = time.time() - t0
+    # ---- queries: this rank's contiguous shard of a global batch of world*nq (weak scaling) ----
+    s, e = shard_range(world * nq, rank, world)
+    gq = torch.Generator(device=dev).manual_seed(args.seed + 1000 + rank)
+    batches = [torch.randint(0, MAX, (e - s,), dtype=torch.int32, device=dev, generator=gq) for _ in range(2)]
+    out_v = torch.empty(e - s, dtype=torch.int32, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def step(k):
+        rc = L.sst_query_device(tree._h, C.c_void_p(batches[k % 2].data_ptr()), e - s, C.c_void_p(out_v.data_ptr()), None,
+                                args.scheme, stream)
+        if rc != 0:
+            raise RuntimeError(L.sst_last_error().decode())
+
+    for w in range(args.warmup):
+        step(w)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for k in range(args.steps):
+        step(k)
+        ev[k + 1].record()
+    barrier()
+    per_step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[args.steps])
+    if rank == 0:
+        time.sleep(0.15)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * nq * args.steps / (total_ms_max * 1e-3)
+
+    # ---- spot check of the timed output (device-side properties; parity proper lives in tests/) ----
+    q_last = batches[(args.steps - 1) % 2]
+    ok = bool((out_v >= q_last).all())
+    i2 = torch.searchsorted(keys, q_last[:1_000_000])
+    ok = ok and bool((keys[i2.clamp(max=n - 1)] == out_v[:1_000_000]).all())
+
+    # ---- roofline of the dominant (only) kernel: algorithmic bytes per launch / mean launch time ----
+    layer_nodes = layer_nodes_for(n)
+    l2_bytes = torch.cuda.get_device_properties(dev).L2_cache_size
+    H_hbm = hbm_levels(layer_nodes, l2_bytes)
+    bytes_per_query = 64 * H_hbm + 4 + 4  # 64*H_hbm + query in + value out
+    kern_ms = statistics.mean(per_step_ms)
+    achieved = bytes_per_query * (e - s) / (kern_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "bytes_per_query": bytes_per_query, "hbm_levels": H_hbm,
+                "kernel": "stree_search_fast", "kernel_ms": kern_ms}
+    tf = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tf):
+        try:
+            roofline["traffic"] = json.load(open(tf)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- e2e: the public host-buffer call (pinned host memory -> H2D -> kernel -> D2H) ----
+    e2e = None
+    if not args.no_e2e:
+        hq = torch.empty(e - s, dtype=torch.int32).pin_memory()
+        hv = torch.empty(e - s, dtype=torch.int32).pin_memory()
+        hq.copy_(batches[0])
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            rc = L.sst_query(tree._h, C.c_void_p(hq.data_ptr()), e - s, C.c_void_p(hv.data_ptr()), None, args.scheme)
+            if rc != 0:
+                raise RuntimeError(L.sst_last_error().decode())
+
+        e2e_step()
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t1
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ok = ok and bool((hv.to(dev) == tree.query(batches[0])).all())
+        e2e = {"value": world * nq * args.e2e_steps / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": 4 * (e - s),
+               "d2h_bytes_per_step": 4 * (e - s), "steps": args.e2e_steps}
+
+    # ---- CPU baseline on the box's host cores (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle as O  # allowed: bench.py's cpu_baseline leg
+
+        O.build()
+        threads = host_threads()
+        hk = keys.cpu().numpy().view(np.uint32)
+        ot = O.Tree.stree(hk, left_max=True)
+        sample = min(nq, args.cpu_sample)
+        hs = batches[0][:sample].cpu().numpy().view(np.uint32)
+        ot.batch_final(hs[: min(sample, 1 << 20)], threads)  # warm-up (also builds the hugepage copy)
+        cv, secs = ot.batch_final(hs, threads)
+        gv = tree.query(batches[0][:sample]).cpu().numpy().view(np.uint32)
+        ok = ok and bool((cv == gv).all())
+        cpu = {"value": sample / secs, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"first {sample} queries of the step's batch over the full {n}-key tree; oracle batch_final<128> (AVX2={bool(O.lib().orc_has_avx2())}) on {threads} threads; results equal the GPU's"}
+        del ot
+
+    # ---- optional secondary metric: suffix-array patterns/s (config C3) ----
+    sa_info = None
+    if rank == 0 and world == 1 and args.sa_text > 0:
+        try:
+            sa_info = bench_sa(args, sst, torch, dev)
+        except Exception as ex:  # the headline line must still print
+            sa_info = {"error": repr(ex)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {
+                "workload": f"stree16 left_max lower_bound: {n} sorted uniform u32 keys (S+-tree B=16, {len(layer_nodes)} levels), {nq} uniform u32 queries per GPU per step",
+                "n_keys": n, "queries_per_gpu": nq, "global_queries": world * nq, "parallelism": f"replicated index, query-sharded x{world}",
+                "scheme": args.scheme, "index_build_s": round(build_s, 3),
+                "l2_policy": "inputs larger than L2: 1 GiB leaf level + 0.8 GB query/result streams per step, two alternating query batches",
+            },
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * L.sst_query_launches(tree._h, args.scheme),
+            "clocks": clocks, "results_ok": ok,
+        }
+        if sa_info is not None:
+            line["sa"] = sa_info
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0 if ok else 1
+
+
+def bench_sa(args, sst, torch, dev):
+    """Config C3: random DNA text, 32-mer patterns, plain vs LCP-accelerated binary search."""
+    import ctypes as C
+
+    L = sst.lib()
+    n, npat, plen = args.sa_text, args.sa_patterns, 32
+    g = torch.Generator(device=dev).manual_seed(args.seed + 5)
+    text = torch.randint(0, 4, (n,), dtype=torch.uint8, device=dev, generator=g)
+    t0 = time.time()
+    sa = sst.SaNaive.build(text)
+    torch.cuda.synchronize()
+    build_s = time.time() - t0
+    starts = torch.randint(0, n - 200, (npat,), device=dev, generator=g)
+    pats = text[(starts[:, None] + torch.arange(plen, device=dev)[None, :]).reshape(-1)].contiguous()
+    off = (torch.arange(npat + 1, device=dev, dtype=torch.int64) * plen).contiguous()
+    lo = torch.empty(npat, dtype=torch.int32, device=dev)
+    hi = torch.empty(npat, dtype=torch.int32, device=dev)
+    pos = torch.empty(npat, dtype=torch.int32, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    out = {"text_bytes": n, "patterns": npat, "pattern_len": plen, "sa_build_s": round(build_s, 3), "unit": "patterns/s"}
+    ref_lo = None
+    for name, mode in (("binary", sst.SA_BINARY), ("mlr", sst.SA_MLR)):
+        def run():
+            rc = L.sst_sa_search_device(sa._h, C.c_void_p(pats.data_ptr()), C.c_void_p(off.data_ptr()), npat, mode,
+                                        C.c_void_p(lo.data_ptr()), C.c_void_p(hi.data_ptr()), C.c_void_p(pos.data_ptr()), stream)
+            if rc != 0:
+                raise RuntimeError(L.sst_last_error().decode())
+        run()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            run()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 3
+        out[name + "_patterns_per_s"] = npat / (ms * 1e-3)
+        # property: the pattern occurs at the returned position
+        got = text[(pos.long()[:100000, None] + torch.arange(plen, device=dev)[None, :])]
+        out[name + "_ok"] = bool((got == pats.view(npat, plen)[:100000]).all()) and bool((hi > lo).all())
+        if ref_lo is None:
+            ref_lo = lo.clone()
+        else:
+            out["mlr_equals_binary"] = bool((lo == ref_lo).all())
+    out["sa_check_violations"] = sa.check()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--n-keys", type=int, default=1 << 28)
+    ap.add_argument("--queries", type=int, default=100_000_000, help="queries per GPU per step")
+    ap.add_argument("--scheme", type=int, default=0)
+    ap.add_argument("--seed", type=int, default=20251018)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=100_000_000)
+    ap.add_argument("--ref-sample", type=int, default=20_000_000, help="queries per step of the reference arm")
+    ap.add_argument("--sa-text", type=int, default=100_000_000, help="0 disables the secondary SA metric")
+    ap.add_argument("--sa-patterns", type=int, default=10_000_000)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "own":
+        args.warmup = 3  # timing rule: W >= 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_own(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

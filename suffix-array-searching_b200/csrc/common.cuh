@@ -1,0 +1,99 @@
+// common.cuh -- internal declarations shared by the translation units of libsst_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "sst_b200.h"
+
+namespace sst {
+
+constexpr int kMaxLevels = 12;
+constexpr uint32_t kMax = SST_MAX;   // static-search-tree/src/node.rs:5
+constexpr int kNodeSlots = 16;       // BTreeNode<16>, 64 bytes (node.rs:7-11)
+
+void set_error(int status, const std::string& msg);
+void clear_error();
+bool cuda_ok(cudaError_t e, const char* what, const char* file, int line);
+
+#define SST_CUDA_OK(call) ::sst::cuda_ok((call), #call, __FILE__, __LINE__)
+
+// Selects `device` for the current host thread for the lifetime of the guard.
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int device);
+    ~DeviceGuard();
+};
+
+// One non-blocking stream per (host thread, device); created lazily, never destroyed.
+cudaStream_t thread_stream(int device);
+// Two extra per-thread streams used by the chunked host-buffer pipeline.
+cudaStream_t thread_copy_stream(int device, int which);
+
+int sm_count(int device);
+size_t max_smem_optin(int device);
+bool device_usable(int device);
+
+inline size_t div_ceil(size_t a, size_t b) { return (a + b - 1) / b; }
+
+}  // namespace sst
+
+// What the search kernels need to know about an index.  Passed by value (__grid_constant__).
+// All positions are in u32 "slots" (4 bytes); a node is 16 slots.
+struct SstTreeView {
+    const uint32_t* tree;                          // device base of the node array
+    unsigned long long level_slot[sst::kMaxLevels]; // first slot of each level (within a part for COMPACT)
+    uint32_t mult[sst::kMaxLevels];                // s' = s * mult[h] + 16 * count after level h
+    int levels;                                    // offsets.len()
+    int variant;                                   // SST_PLAIN .. SST_MAP
+    uint32_t node_b;                               // B: 16 or 15
+    uint32_t shift;                                // part = q >> shift
+    unsigned long long parts;
+    uint32_t start_mul;                            // first slot = part * start_mul (SIMPLE/L1: 16, OVERLAPPING: 16 - overlap)
+    unsigned long long part_stride;                // COMPACT: slots per part (bpp * 16)
+    const uint32_t* prefix_map;                    // MAP
+    unsigned long long leaf_slots;                 // slots of the leaf level (per part for COMPACT)
+    unsigned long long n;                          // number of keys
+    // sorted-array index of record for the partitioned layouts
+    const uint32_t* part_start;                    // [parts + 1] index of each part's first key
+    const unsigned long long* part_pos;            // [parts] leaf slot of each part's first key
+};
+
+struct sst_index {
+    int device = 0;
+    int variant = SST_PLAIN;
+    uint32_t node_b = 16;
+    uint32_t flags = 0;
+    size_t n = 0;
+    size_t n_blocks = 0;          // nodes in the image; one MAX guard node follows on the device
+    uint32_t* d_tree = nullptr;
+    int levels = 0;
+    size_t offsets[sst::kMaxLevels] = {};      // node offsets, as the reference's `offsets`
+    size_t layer_sizes[sst::kMaxLevels] = {};  // nodes per level (per part where the reference says so)
+    size_t layer_blocks[sst::kMaxLevels] = {}; // nodes actually allocated per level
+    // partition parameters (partitioned_s_tree.rs:19-32)
+    size_t shift = 0, parts = 1, bpp = 0, l1 = 0, overlap = 0, max_bucket = 0;
+    bool has_overlap = false;
+    uint32_t* d_prefix_map = nullptr;
+    size_t prefix_map_len = 0;
+    uint32_t* d_part_start = nullptr;             // [parts + 1]
+    unsigned long long* d_part_pos = nullptr;     // [parts]
+    size_t l1_field = 0;                          // the `l1` struct field (max(l1,16) for OL)
+    SstTreeView view{};
+};
+
+namespace sst {
+// builders (stree_build.cu)
+sst_index* build_plain(const uint32_t* d_sorted, bool sorted_is_owned_leaf, size_t n, uint32_t node_b, uint32_t flags, int device);
+sst_index* build_partitioned(const uint32_t* d_sorted, size_t n, uint32_t b, int variant, int device);
+void finalize_view(sst_index* idx);
+// search (stree_search.cu)
+int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx,
+                 int scheme, cudaStream_t stream);
+int query_launch_count(const sst_index* idx, int scheme);
+}  // namespace sst

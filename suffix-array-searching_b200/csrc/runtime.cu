@@ -1,0 +1,93 @@
+// runtime.cu -- error state, device selection and per-thread streams.
+#include <cstdio>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace sst {
+
+namespace {
+thread_local std::string g_err;
+thread_local int g_status = SST_OK;
+constexpr int kMaxDevices = 64;
+thread_local cudaStream_t g_streams[kMaxDevices][3] = {};
+}  // namespace
+
+void set_error(int status, const std::string& msg) {
+    g_status = status;
+    g_err = msg;
+}
+void clear_error() {
+    g_status = SST_OK;
+    g_err.clear();
+}
+
+bool cuda_ok(cudaError_t e, const char* what, const char* file, int line) {
+    if (e == cudaSuccess) return true;
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+    set_error(SST_ERR_CUDA, buf);
+    (void)cudaGetLastError();
+    return false;
+}
+
+DeviceGuard::DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = SST_CUDA_OK(cudaSetDevice(device));
+}
+DeviceGuard::~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+}
+
+static cudaStream_t get_stream(int device, int which) {
+    if (device < 0 || device >= kMaxDevices) return nullptr;
+    cudaStream_t& s = g_streams[device][which];
+    if (!s) {
+        DeviceGuard g(device);
+        if (!g.ok) return nullptr;
+        if (!SST_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking))) s = nullptr;
+    }
+    return s;
+}
+cudaStream_t thread_stream(int device) { return get_stream(device, 0); }
+cudaStream_t thread_copy_stream(int device, int which) { return get_stream(device, 1 + (which & 1)); }
+
+int sm_count(int device) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
+    return v;
+}
+size_t max_smem_optin(int device) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) return 0;
+    return (size_t)v;
+}
+bool device_usable(int device) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return major == 10;  // the library is built for sm_100a only
+}
+
+}  // namespace sst
+
+extern "C" {
+
+const char* sst_last_error(void) { return sst::g_err.c_str(); }
+int sst_last_status(void) { return sst::g_status; }
+const char* sst_version(void) { return "sst_b200 0.1 (sm_100a)"; }
+
+int sst_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    int usable = 0;
+    for (int d = 0; d < n; d++) usable += sst::device_usable(d) ? 1 : 0;
+    return usable;
+}
+
+}  // extern "C"

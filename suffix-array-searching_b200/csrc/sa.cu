@@ -1,0 +1,435 @@
+// sa.cu -- suffix array construction, validation and pattern search on the GPU.
+//
+// Replaces (reference paths relative to suffix-array-searching/src):
+//   SaNaive::build / SA::build        sa_search.rs:30-57, experiments.rs:19-38
+//     (the libsais call at sa_search.rs:33 / experiments.rs:26 and the strict-order assertion
+//      at sa_search.rs:36-38)
+//   binary_search                      sa_search.rs:98-112, experiments.rs:51-64
+//   cmp (16-byte SIMD compare)         sa_search.rs:346-374
+//   the LCP-accelerated search that the reference only sketches (TODO at sa_search.rs:344-345)
+//
+// Search mapping: a sub-warp of PL lanes serves one pattern; every probe loads sa[m] once
+// (broadcast within the group) and compares 4*PL-byte windows of text and pattern, each lane
+// one (unaligned) 4-byte word, with __ballot_sync + ffs to find the first mismatching lane.
+// PL = 32 is the warp-per-pattern mapping; smaller groups put more patterns (more independent
+// dependent-miss chains) in flight per SM.  The `mlr` mode carries lcp(q, suffix(l-1)) and
+// lcp(q, suffix(r)) and starts each comparison at their minimum.
+//
+// Construction: prefix doubling.  Suffixes are ranked by their first 7 symbols (9 bits each,
+// 0 = past the end, so that a proper prefix sorts first exactly as Rust's slice ordering),
+// then by (rank[i], rank[i+h]) pairs with h = 7, 14, 28, ... until all ranks are distinct.
+// The pair sort uses cub::DeviceRadixSort (a sort primitive, like the reference's use of
+// libsais); everything else is hand-written.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+
+struct sst_sa {
+    int device = 0;
+    size_t n = 0;
+    uint8_t* d_text = nullptr;  // n bytes (+ allocation slack)
+    uint32_t* d_sa = nullptr;   // n entries
+};
+
+namespace sst {
+namespace {
+
+constexpr int kThreads = 256;
+
+inline unsigned grid_for(size_t work) { return (unsigned)std::min<size_t>(div_ceil(work, (size_t)kThreads), 148 * 32); }
+
+// ---- construction --------------------------------------------------------------------------
+__global__ void sa_init_keys(const uint8_t* __restrict__ t, size_t n, unsigned long long* __restrict__ keys,
+                             uint32_t* __restrict__ vals) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned long long k = 0;
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            const size_t p = i + j;
+            const unsigned long long sym = p < n ? (unsigned long long)t[p] + 1ull : 0ull;
+            k = (k << 9) | sym;
+        }
+        keys[i] = k;
+        vals[i] = (uint32_t)i;
+    }
+}
+
+// flags[j] = 1 when sorted key j starts a new group.
+__global__ void sa_flag_heads(const unsigned long long* __restrict__ keys, size_t n, uint32_t* __restrict__ flags) {
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x)
+        flags[j] = (j == 0 || keys[j] != keys[j - 1]) ? 1u : 0u;
+}
+
+// rank[sa[j]] = (number of group heads up to j) - 1
+__global__ void sa_scatter_rank(const uint32_t* __restrict__ sa, const uint32_t* __restrict__ scan, size_t n,
+                                uint32_t* __restrict__ rank) {
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x)
+        rank[sa[j]] = scan[j] - 1u;
+}
+
+// key for suffix i after knowing ranks by the first h symbols: (rank[i], rank[i+h] + 1 | 0)
+__global__ void sa_pair_keys(const uint32_t* __restrict__ rank, size_t n, size_t h, unsigned long long* __restrict__ keys,
+                             uint32_t* __restrict__ vals) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned long long hi = rank[i];
+        const unsigned long long lo = i + h < n ? (unsigned long long)rank[i + h] + 1ull : 0ull;
+        keys[i] = (hi << 32) | lo;
+        vals[i] = (uint32_t)i;
+    }
+}
+
+int bits_needed(unsigned long long max_value) {
+    int b = 1;
+    while (b < 64 && (max_value >> b)) b++;
+    return b;
+}
+
+bool build_sa_device(const uint8_t* d_text, size_t n, uint32_t* d_sa, int device) {
+    cudaStream_t st = thread_stream(device);
+    unsigned long long *k0 = nullptr, *k1 = nullptr;
+    uint32_t *v0 = nullptr, *v1 = nullptr, *rank = nullptr, *flags = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0, scan_bytes = 0;
+    bool ok = SST_CUDA_OK(cudaMalloc(&k0, n * 8)) && SST_CUDA_OK(cudaMalloc(&k1, n * 8)) && SST_CUDA_OK(cudaMalloc(&v0, n * 4)) &&
+              SST_CUDA_OK(cudaMalloc(&v1, n * 4)) && SST_CUDA_OK(cudaMalloc(&rank, n * 4)) && SST_CUDA_OK(cudaMalloc(&flags, n * 4));
+    if (ok) {
+        cub::DoubleBuffer<unsigned long long> dk(k0, k1);
+        cub::DoubleBuffer<uint32_t> dv(v0, v1);
+        ok = SST_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (unsigned long long)n, 0, 64, st)) &&
+             SST_CUDA_OK(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, flags, flags, (unsigned long long)n, st));
+        tmp_bytes = std::max(tmp_bytes, scan_bytes);
+        ok = ok && SST_CUDA_OK(cudaMalloc(&tmp, tmp_bytes));
+    }
+    if (ok) {
+        sa_init_keys<<<grid_for(n), kThreads, 0, st>>>(d_text, n, k0, v0);
+        int end_bit = 63;
+        size_t h = 7;
+        for (int round = 0; ok; round++) {
+            cub::DoubleBuffer<unsigned long long> dk(k0, k1);
+            cub::DoubleBuffer<uint32_t> dv(v0, v1);
+            size_t tb = tmp_bytes;
+            ok = SST_CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, (unsigned long long)n, 0, end_bit, st));
+            if (!ok) break;
+            const unsigned long long* sk = dk.Current();
+            const uint32_t* sv = dv.Current();
+            sa_flag_heads<<<grid_for(n), kThreads, 0, st>>>(sk, n, flags);
+            tb = tmp_bytes;
+            ok = SST_CUDA_OK(cub::DeviceScan::InclusiveSum(tmp, tb, flags, flags, (unsigned long long)n, st));
+            if (!ok) break;
+            uint32_t groups = 0;
+            ok = SST_CUDA_OK(cudaMemcpyAsync(&groups, flags + (n - 1), 4, cudaMemcpyDeviceToHost, st)) && SST_CUDA_OK(cudaStreamSynchronize(st));
+            if (!ok) break;
+            if (groups == n || h >= n) {
+                ok = SST_CUDA_OK(cudaMemcpyAsync(d_sa, sv, n * 4, cudaMemcpyDeviceToDevice, st));
+                break;
+            }
+            sa_scatter_rank<<<grid_for(n), kThreads, 0, st>>>(sv, flags, n, rank);
+            sa_pair_keys<<<grid_for(n), kThreads, 0, st>>>(rank, n, h, k0, v0);
+            end_bit = 32 + bits_needed(groups);
+            h *= 2;
+        }
+        ok = ok && SST_CUDA_OK(cudaGetLastError()) && SST_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(rank); cudaFree(flags); cudaFree(tmp);
+    return ok;
+}
+
+// ---- strict-order check: sa_search.rs:36-38 --------------------------------------------------
+__global__ void sa_check_kernel(const uint8_t* __restrict__ t, size_t n, const uint32_t* __restrict__ sa,
+                                unsigned long long* __restrict__ bad) {
+    unsigned long long local = 0;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x + 1; j < n; j += (size_t)gridDim.x * blockDim.x) {
+        const size_t x = sa[j - 1], y = sa[j];
+        if (x >= n || y >= n) { local++; continue; }
+        const size_t lx = n - x, ly = n - y, m = lx < ly ? lx : ly;
+        size_t i = 0;
+        while (i < m && t[x + i] == t[y + i]) i++;
+        const bool less = i < m ? t[x + i] < t[y + i] : lx < ly;
+        if (!less) local++;
+    }
+    if (local) atomicAdd(bad, local);
+}
+
+// ---- search ----------------------------------------------------------------------------------
+// 4 bytes starting at byte address base+pos (little endian), built from aligned words; words at
+// or beyond `end` read as zero, so nothing outside [base_aligned, end) is touched.
+__device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t* __restrict__ base, unsigned long long pos,
+                                                       unsigned long long end) {
+    const unsigned long long a = pos & ~3ull;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(base + a);
+    const uint32_t w0 = a < end ? __ldg(w) : 0u;
+    const unsigned sh = (unsigned)(pos & 3ull);
+    if (sh == 0) return w0;
+    const uint32_t w1 = a + 4 < end ? __ldg(w + 1) : 0u;
+    return __funnelshift_r(w0, w1, sh * 8);
+}
+
+struct SaParams {
+    const uint8_t* text;
+    const uint32_t* sa;
+    unsigned long long n;
+    const uint8_t* pats;
+    const unsigned long long* pat_off;
+    unsigned long long pats_bytes;  // pat_off[npat]
+    unsigned long long npat;
+    uint32_t* out_lo;
+    uint32_t* out_hi;
+    uint32_t* out_pos;
+};
+
+// Compares suffix(spos) with the pattern from byte `start` on.  Returns lcp (group-uniform) and
+// sets less = suffix < pattern under Rust slice ordering (proper prefix is smaller).
+template <int PL>
+__device__ __forceinline__ uint32_t group_compare(const SaParams& p, unsigned long long spos, const uint8_t* pat_base,
+                                                  unsigned long long pat_pos, uint32_t ql, uint32_t start, unsigned sub,
+                                                  unsigned gbase, unsigned gmask, bool& less) {
+    const unsigned long long sl64 = p.n - spos;
+    const uint32_t sl = sl64 > 0xffffffffull ? 0xffffffffu : (uint32_t)sl64;
+    const uint32_t lim = sl < ql ? sl : ql;
+    uint32_t off = start;
+    while (true) {
+        if (off >= lim) { less = sl < ql; return lim; }
+        const uint32_t my = off + 4u * sub;
+        uint32_t diff = 0, tw = 0, pw = 0;
+        if (my < lim) {
+            tw = load_u32_unaligned(p.text, spos + my, p.n);
+            pw = load_u32_unaligned(pat_base, pat_pos + my, p.pats_bytes);
+            diff = tw ^ pw;
+            const uint32_t v = lim - my;
+            if (v < 4u) diff &= (1u << (8u * v)) - 1u;
+        }
+        const unsigned b = (__ballot_sync(gmask, diff != 0u) >> gbase) & (PL == 32 ? 0xffffffffu : ((1u << PL) - 1u));
+        if (b) {
+            const unsigned f = __ffs(b) - 1;
+            const unsigned bytepos = (__ffs(diff) - 1) >> 3;  // meaningful on lane f only
+            const uint32_t my_lcp = my + bytepos;
+            const int my_less = ((tw >> (8u * bytepos)) & 0xffu) < ((pw >> (8u * bytepos)) & 0xffu);
+            const uint32_t lcp = __shfl_sync(gmask, my_lcp, gbase + f);
+            less = __shfl_sync(gmask, my_less, gbase + f) != 0;
+            return lcp;
+        }
+        off += 4u * PL;
+    }
+}
+
+template <int PL, bool MLR>
+__global__ void __launch_bounds__(kThreads)
+sa_search_kernel(const __grid_constant__ SaParams p) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned sub = lane & (PL - 1), gbase = lane & ~(unsigned)(PL - 1);
+    const unsigned gmask = PL == 32 ? 0xffffffffu : (((1u << PL) - 1u) << gbase);
+    const unsigned long long groups_per_block = kThreads / PL;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * groups_per_block + threadIdx.x / PL; i < p.npat;
+         i += (unsigned long long)gridDim.x * groups_per_block) {
+        const unsigned long long po = p.pat_off[i];
+        const uint32_t ql = (uint32_t)(p.pat_off[i + 1] - po);
+        // ---- lower bound: sa_search.rs:98-112 ----
+        unsigned long long l = 0, r = p.n;
+        uint32_t lcp_l = 0, lcp_r = 0;
+        while (l < r) {
+            const unsigned long long m = (l + r) >> 1;
+            const unsigned long long spos = __ldg(p.sa + m);
+            bool less;
+            const uint32_t start = MLR ? (lcp_l < lcp_r ? lcp_l : lcp_r) : 0u;
+            const uint32_t lcp = group_compare<PL>(p, spos, p.pats, po, ql, start, sub, gbase, gmask, less);
+            if (less) { l = m + 1; lcp_l = lcp; } else { r = m; lcp_r = lcp; }
+        }
+        const unsigned long long lo = l;
+        // ---- hi: first index >= lo whose suffix does not start with the pattern (gallop + bisect) ----
+        unsigned long long hi = lo;
+        if (p.out_hi) {
+            // Suffixes starting with q are contiguous from lo: gallop to bracket the end, then bisect.
+            unsigned long long a = lo, b = p.n, step = 1;  // invariant: all of [lo, a) start with q
+            while (true) {
+                const unsigned long long pr = a + step - 1;
+                if (pr >= p.n) break;
+                bool less;
+                const uint32_t lcp = group_compare<PL>(p, __ldg(p.sa + pr), p.pats, po, ql, 0u, sub, gbase, gmask, less);
+                if (lcp >= ql) { a = pr + 1; step <<= 1; } else { b = pr; break; }
+            }
+            // bisect in [a, b): everything before a matches, b does not (or b == n)
+            while (a < b) {
+                const unsigned long long m = (a + b) >> 1;
+                bool less;
+                const uint32_t lcp = group_compare<PL>(p, __ldg(p.sa + m), p.pats, po, ql, 0u, sub, gbase, gmask, less);
+                if (lcp >= ql) a = m + 1; else b = m;
+            }
+            hi = a;
+        }
+        if (sub == 0) {
+            p.out_lo[i] = (uint32_t)lo;
+            if (p.out_hi) p.out_hi[i] = (uint32_t)hi;
+            if (p.out_pos) p.out_pos[i] = lo < p.n ? __ldg(p.sa + lo) : 0xffffffffu;
+        }
+    }
+}
+
+int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+template <int PL>
+void launch_search(const SaParams& p, int mode, cudaStream_t st, int device) {
+    const unsigned long long gpb = kThreads / PL;
+    const unsigned grid = (unsigned)std::min<unsigned long long>((p.npat + gpb - 1) / gpb, (unsigned long long)sm_count(device) * 8);
+    if (mode == SST_SA_MLR) sa_search_kernel<PL, true><<<grid, kThreads, 0, st>>>(p);
+    else sa_search_kernel<PL, false><<<grid, kThreads, 0, st>>>(p);
+}
+
+}  // namespace
+}  // namespace sst
+
+using namespace sst;
+
+extern "C" {
+
+sst_sa_t* sst_sa_build_device(const uint8_t* d_text, size_t n, int device) {
+    clear_error();
+    if (n == 0 || !d_text) { set_error(SST_ERR_ARG, "empty text"); return nullptr; }
+    if (n >= 0xfffffff0ull) { set_error(SST_ERR_UNSUPPORTED, "text must be shorter than 2^32 - 16 (u32 suffix array, sa_search.rs:35)"); return nullptr; }
+    if (!device_usable(device)) { set_error(SST_ERR_CUDA, "device is not an sm_100 GPU (no CPU fallback)"); return nullptr; }
+    DeviceGuard g(device);
+    if (!g.ok) return nullptr;
+    auto* s = new sst_sa();
+    s->device = device;
+    s->n = n;
+    bool ok = SST_CUDA_OK(cudaMalloc(&s->d_text, n + 64)) && SST_CUDA_OK(cudaMalloc(&s->d_sa, n * 4));
+    cudaStream_t st = thread_stream(device);
+    ok = ok && SST_CUDA_OK(cudaMemsetAsync(s->d_text + n, 0, 64, st)) &&
+         SST_CUDA_OK(cudaMemcpyAsync(s->d_text, d_text, n, cudaMemcpyDeviceToDevice, st));
+    ok = ok && build_sa_device(s->d_text, n, s->d_sa, device);
+    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); delete s; return nullptr; }
+    return s;
+}
+
+sst_sa_t* sst_sa_build(const uint8_t* text, size_t n, int device) {
+    clear_error();
+    if (n == 0 || !text) { set_error(SST_ERR_ARG, "empty text"); return nullptr; }
+    if (!device_usable(device)) { set_error(SST_ERR_CUDA, "device is not an sm_100 GPU (no CPU fallback)"); return nullptr; }
+    DeviceGuard g(device);
+    if (!g.ok) return nullptr;
+    uint8_t* d = nullptr;
+    if (!SST_CUDA_OK(cudaMalloc(&d, n)) || !SST_CUDA_OK(cudaMemcpy(d, text, n, cudaMemcpyHostToDevice))) { cudaFree(d); return nullptr; }
+    sst_sa_t* s = sst_sa_build_device(d, n, device);
+    cudaFree(d);
+    return s;
+}
+
+sst_sa_t* sst_sa_from_parts(const uint8_t* text, size_t n, const uint32_t* sa, int device) {
+    clear_error();
+    if (n == 0 || !text || !sa) { set_error(SST_ERR_ARG, "empty text"); return nullptr; }
+    if (n >= 0xfffffff0ull) { set_error(SST_ERR_UNSUPPORTED, "text too long for a u32 suffix array"); return nullptr; }
+    if (!device_usable(device)) { set_error(SST_ERR_CUDA, "device is not an sm_100 GPU (no CPU fallback)"); return nullptr; }
+    DeviceGuard g(device);
+    if (!g.ok) return nullptr;
+    auto* s = new sst_sa();
+    s->device = device;
+    s->n = n;
+    bool ok = SST_CUDA_OK(cudaMalloc(&s->d_text, n + 64)) && SST_CUDA_OK(cudaMalloc(&s->d_sa, n * 4)) &&
+              SST_CUDA_OK(cudaMemset(s->d_text + n, 0, 64)) && SST_CUDA_OK(cudaMemcpy(s->d_text, text, n, cudaMemcpyHostToDevice)) &&
+              SST_CUDA_OK(cudaMemcpy(s->d_sa, sa, n * 4, cudaMemcpyHostToDevice));
+    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); delete s; return nullptr; }
+    return s;
+}
+
+void sst_sa_free(sst_sa_t* s) {
+    if (!s) return;
+    DeviceGuard g(s->device);
+    cudaFree(s->d_text);
+    cudaFree(s->d_sa);
+    delete s;
+}
+
+size_t sst_sa_len(const sst_sa_t* s) { return s ? s->n : 0; }
+
+int sst_sa_get(const sst_sa_t* s, uint32_t* out_sa) {
+    clear_error();
+    if (!s || !out_sa) { set_error(SST_ERR_ARG, "null argument"); return SST_ERR_ARG; }
+    DeviceGuard g(s->device);
+    if (!g.ok) return SST_ERR_CUDA;
+    return SST_CUDA_OK(cudaMemcpy(out_sa, s->d_sa, s->n * 4, cudaMemcpyDeviceToHost)) ? SST_OK : SST_ERR_CUDA;
+}
+
+int sst_sa_check(const sst_sa_t* s, uint64_t* out_violations) {
+    clear_error();
+    if (!s || !out_violations) { set_error(SST_ERR_ARG, "null argument"); return SST_ERR_ARG; }
+    DeviceGuard g(s->device);
+    if (!g.ok) return SST_ERR_CUDA;
+    cudaStream_t st = thread_stream(s->device);
+    unsigned long long* d_bad = nullptr;
+    if (!SST_CUDA_OK(cudaMalloc(&d_bad, 8))) return SST_ERR_CUDA;
+    unsigned long long bad = 0;
+    bool ok = SST_CUDA_OK(cudaMemsetAsync(d_bad, 0, 8, st));
+    if (ok) {
+        sa_check_kernel<<<grid_for(s->n), kThreads, 0, st>>>(s->d_text, s->n, s->d_sa, d_bad);
+        ok = SST_CUDA_OK(cudaGetLastError()) && SST_CUDA_OK(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, st)) &&
+             SST_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    cudaFree(d_bad);
+    *out_violations = bad;
+    return ok ? SST_OK : SST_ERR_CUDA;
+}
+
+int sst_sa_search_device(const sst_sa_t* s, const uint8_t* d_pats, const uint64_t* d_pat_off, size_t npat, int mode,
+                         uint32_t* d_out_lo, uint32_t* d_out_hi, uint32_t* d_out_pos, void* stream) {
+    clear_error();
+    if (!s || (npat && (!d_pat_off || !d_out_lo))) { set_error(SST_ERR_ARG, "null argument"); return SST_ERR_ARG; }
+    if (mode != SST_SA_BINARY && mode != SST_SA_MLR) { set_error(SST_ERR_ARG, "unknown SA search mode"); return SST_ERR_ARG; }
+    if (npat == 0) return SST_OK;
+    DeviceGuard g(s->device);
+    if (!g.ok) return SST_ERR_CUDA;
+    cudaStream_t st = stream ? (cudaStream_t)stream : thread_stream(s->device);
+    SaParams p{};
+    p.text = s->d_text; p.sa = s->d_sa; p.n = s->n;
+    p.pats = d_pats; p.pat_off = (const unsigned long long*)d_pat_off; p.npat = npat;
+    p.out_lo = d_out_lo; p.out_hi = d_out_hi; p.out_pos = d_out_pos;
+    // total pattern bytes (bounds the aligned word loads); read back once
+    unsigned long long total = 0;
+    if (!SST_CUDA_OK(cudaMemcpyAsync(&total, d_pat_off + npat, 8, cudaMemcpyDeviceToHost, st)) || !SST_CUDA_OK(cudaStreamSynchronize(st)))
+        return SST_ERR_CUDA;
+    p.pats_bytes = total;
+    switch (env_int("SST_SA_LANES", 8)) {
+        case 32: launch_search<32>(p, mode, st, s->device); break;
+        case 16: launch_search<16>(p, mode, st, s->device); break;
+        case 4: launch_search<4>(p, mode, st, s->device); break;
+        case 2: launch_search<2>(p, mode, st, s->device); break;
+        default: launch_search<8>(p, mode, st, s->device); break;
+    }
+    return SST_CUDA_OK(cudaGetLastError()) ? SST_OK : SST_ERR_CUDA;
+}
+
+int sst_sa_search(const sst_sa_t* s, const uint8_t* pats, const uint64_t* pat_off, size_t npat, int mode, uint32_t* out_lo,
+                  uint32_t* out_hi, uint32_t* out_pos) {
+    clear_error();
+    if (!s || (npat && (!pat_off || !out_lo))) { set_error(SST_ERR_ARG, "null argument"); return SST_ERR_ARG; }
+    if (npat == 0) return SST_OK;
+    DeviceGuard g(s->device);
+    if (!g.ok) return SST_ERR_CUDA;
+    cudaStream_t st = thread_stream(s->device);
+    const size_t bytes = pat_off[npat];
+    uint8_t* d_p = nullptr;
+    uint64_t* d_o = nullptr;
+    uint32_t *d_lo = nullptr, *d_hi = nullptr, *d_pos = nullptr;
+    bool ok = SST_CUDA_OK(cudaMalloc(&d_p, bytes + 16)) && SST_CUDA_OK(cudaMalloc(&d_o, (npat + 1) * 8)) &&
+              SST_CUDA_OK(cudaMalloc(&d_lo, npat * 4)) && (!out_hi || SST_CUDA_OK(cudaMalloc(&d_hi, npat * 4))) &&
+              (!out_pos || SST_CUDA_OK(cudaMalloc(&d_pos, npat * 4)));
+    ok = ok && (bytes == 0 || SST_CUDA_OK(cudaMemcpyAsync(d_p, pats, bytes, cudaMemcpyHostToDevice, st))) &&
+         SST_CUDA_OK(cudaMemcpyAsync(d_o, pat_off, (npat + 1) * 8, cudaMemcpyHostToDevice, st));
+    int rc = ok ? sst_sa_search_device(s, d_p, d_o, npat, mode, d_lo, d_hi, d_pos, st) : SST_ERR_CUDA;
+    if (rc == SST_OK) {
+        ok = SST_CUDA_OK(cudaMemcpyAsync(out_lo, d_lo, npat * 4, cudaMemcpyDeviceToHost, st)) &&
+             (!out_hi || SST_CUDA_OK(cudaMemcpyAsync(out_hi, d_hi, npat * 4, cudaMemcpyDeviceToHost, st))) &&
+             (!out_pos || SST_CUDA_OK(cudaMemcpyAsync(out_pos, d_pos, npat * 4, cudaMemcpyDeviceToHost, st))) &&
+             SST_CUDA_OK(cudaStreamSynchronize(st));
+        rc = ok ? SST_OK : SST_ERR_CUDA;
+    }
+    cudaFree(d_p); cudaFree(d_o); cudaFree(d_lo); cudaFree(d_hi); cudaFree(d_pos);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,633 @@
+// stree_search.cu -- batched lower_bound kernels over the S+-tree image (the hot path).
+//
+// Replaces (reference paths relative to static-search-tree/src):
+//   BTreeNode::find_popcnt / find_splat / find_splat64    node.rs:93-138
+//   STree::search, batch_*, batch_final, batch_interleave_*   s_tree.rs:196-832
+//   PartitionedSTree::<..>::search (all five layouts)     partitioned_s_tree.rs:654-880
+//
+// The reference hides DRAM latency by keeping 128 queries in flight per CPU thread with
+// software prefetch.  On B200 the same descent is mapped as follows:
+//   * A node (64 B = 2 sectors) is fetched by a G-lane subgroup in ONE load instruction so that
+//     the L1TEX tag stage sees one line per query per level: G=4 lanes x 16 B (LDG.128),
+//     G=2 lanes x 32 B (LDG.256, new on sm_100) or G=16 lanes x 4 B (the ballot/popc mapping).
+//   * Each lane group keeps G*T independent descents in flight (ILP); with 32 resident warps per
+//     SM that is >= 1000 outstanding 64-B requests per SM, enough for HBM latency.
+//   * The top levels of the tree are staged into shared memory once per CTA by 1-D TMA bulk
+//     copies (cp.async.bulk + mbarrier); a level that does not fit completely is staged as a
+//     prefix and the remainder is read from L1/L2.
+//   * Lower internal levels are loaded with an L2 evict_last policy, the leaf level (the only
+//     HBM-resident one at 2^28 keys) with evict_first and no L1 allocation, so that leaf
+//     traffic does not push the last internal level out of the 126 MB L2.
+//   * Queries and results move as one coalesced 128-B line per warp.
+// All arithmetic is integer; results are bit-exact with the reference (signed compares as in
+// node.rs:91-108, flat leaf read that may spill into the next node as in s_tree.rs:322-325).
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace sst {
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    unsigned done = 0;
+    const uint32_t addr = smem_u32(bar);
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+// 1-D TMA bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+// Per-lane slice of a node: W = 16 / G consecutive keys.
+template <int W>
+struct Keys {
+    uint32_t k[W];
+};
+
+template <int W, bool NO_L1>
+__device__ __forceinline__ Keys<W> ldg_keys(const uint32_t* p, uint64_t pol) {
+    Keys<W> r;
+    if constexpr (W == 1) {
+        if constexpr (NO_L1)
+            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r.k[0]) : "l"(p), "l"(pol));
+        else
+            asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r.k[0]) : "l"(p), "l"(pol));
+    } else if constexpr (W == 2) {
+        if constexpr (NO_L1)
+            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.k[0]), "=r"(r.k[1]) : "l"(p), "l"(pol));
+        else
+            asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.k[0]), "=r"(r.k[1]) : "l"(p), "l"(pol));
+    } else if constexpr (W == 4) {
+        if constexpr (NO_L1)
+            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                         : "=r"(r.k[0]), "=r"(r.k[1]), "=r"(r.k[2]), "=r"(r.k[3]) : "l"(p), "l"(pol));
+        else
+            asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                         : "=r"(r.k[0]), "=r"(r.k[1]), "=r"(r.k[2]), "=r"(r.k[3]) : "l"(p), "l"(pol));
+    } else {
+        static_assert(W == 8, "unsupported slice width");
+        if constexpr (NO_L1)
+            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                         : "=r"(r.k[0]), "=r"(r.k[1]), "=r"(r.k[2]), "=r"(r.k[3]), "=r"(r.k[4]), "=r"(r.k[5]), "=r"(r.k[6]), "=r"(r.k[7])
+                         : "l"(p), "l"(pol));
+        else
+            asm volatile("ld.global.nc.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                         : "=r"(r.k[0]), "=r"(r.k[1]), "=r"(r.k[2]), "=r"(r.k[3]), "=r"(r.k[4]), "=r"(r.k[5]), "=r"(r.k[6]), "=r"(r.k[7])
+                         : "l"(p), "l"(pol));
+    }
+    return r;
+}
+
+template <int W>
+__device__ __forceinline__ Keys<W> lds_keys(const uint32_t* p) {
+    Keys<W> r;
+    if constexpr (W == 1) r.k[0] = *p;
+    else if constexpr (W == 2) { uint2 v = *reinterpret_cast<const uint2*>(p); r.k[0] = v.x; r.k[1] = v.y; }
+    else if constexpr (W == 4) { uint4 v = *reinterpret_cast<const uint4*>(p); r.k[0] = v.x; r.k[1] = v.y; r.k[2] = v.z; r.k[3] = v.w; }
+    else {
+        uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 4);
+        r.k[0] = a.x; r.k[1] = a.y; r.k[2] = a.z; r.k[3] = a.w; r.k[4] = b.x; r.k[5] = b.y; r.k[6] = b.z; r.k[7] = b.w;
+    }
+    return r;
+}
+
+// node.rs:93-109: number of keys < q (signed), reduced over the G lanes of the group.
+template <int G>
+__device__ __forceinline__ unsigned group_count(const Keys<16 / G>& ks, uint32_t q, unsigned gshift) {
+    constexpr int W = 16 / G;
+    if constexpr (G == 16) {
+        const unsigned b = __ballot_sync(kFull, (int)ks.k[0] < (int)q);
+        return __popc((b >> gshift) & 0xffffu);
+    } else {
+        unsigned c = 0;
+#pragma unroll
+        for (int i = 0; i < W; i++) c += ((int)ks.k[i] < (int)q) ? 1u : 0u;
+#pragma unroll
+        for (int m = 1; m < G; m <<= 1) c += __shfl_xor_sync(kFull, c, m);
+        return c;
+    }
+}
+
+// Key at position e (0..W-1) of this lane's slice, without dynamic register indexing.
+template <int W>
+__device__ __forceinline__ uint32_t pick(const Keys<W>& ks, unsigned e) {
+    uint32_t v = ks.k[0];
+#pragma unroll
+    for (int i = 1; i < W; i++) v = (e == (unsigned)i) ? ks.k[i] : v;
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast kernel: plain S+-tree with B = 16 (any of left_max / reverse_storage / full_array).
+// ------------------------------------------------------------------------------------------------
+struct FastParams {
+    const uint32_t* tree;
+    unsigned long long level_slot[kMaxLevels];
+    unsigned smem_slot[kMaxLevels];   // first slot of level h inside shared memory
+    unsigned smem_nodes[kMaxLevels];  // nodes of level h staged in shared memory (prefix of the level)
+    int levels;
+    int smem_levels;                  // levels [0, smem_levels) have smem_nodes > 0
+    unsigned long long leaf_slots;
+    unsigned long long n;
+    int hints;                        // bit0: L2 evict_last on inner levels, bit1: evict_first on leaf
+};
+
+template <int G, int T>
+__global__ void __launch_bounds__(1024, 1)
+stree_search_fast(const __grid_constant__ FastParams p, const uint32_t* __restrict__ qs, size_t nq,
+                  uint32_t* __restrict__ out_vals, unsigned long long* __restrict__ out_idx) {
+    constexpr int W = 16 / G;   // keys per lane
+    constexpr int D = G * T;    // descents in flight per lane group
+    extern __shared__ __align__(128) uint32_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+
+    // ---- stage the top levels: one elected thread issues 1-D TMA bulk copies ----
+    if (p.smem_levels > 0) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned total = 0;
+            for (int h = 0; h < p.smem_levels; h++) total += p.smem_nodes[h] * 64u;
+            mbar_expect_tx(&bar, total);
+            for (int h = 0; h < p.smem_levels; h++) {
+                unsigned bytes = p.smem_nodes[h] * 64u, off = 0;
+                while (bytes) {  // keep each bulk copy <= 64 KiB
+                    const unsigned chunk = bytes < 65536u ? bytes : 65536u;
+                    tma_bulk_g2s(smem + p.smem_slot[h] + off / 4, p.tree + p.level_slot[h] + off / 4, chunk, &bar);
+                    off += chunk;
+                    bytes -= chunk;
+                }
+            }
+        }
+        mbar_wait(&bar, 0);
+    }
+
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const unsigned sub = lane & (G - 1), gbase = lane & ~(unsigned)(G - 1);
+    const uint64_t pol_inner = (p.hints & 1) ? policy_evict_last() : policy_evict_normal();
+    const uint64_t pol_leaf = (p.hints & 2) ? policy_evict_first() : policy_evict_normal();
+    const int L = p.levels;
+
+    for (size_t base = ((size_t)blockIdx.x * warps + warp) * (32 * T); base < nq; base += (size_t)gridDim.x * warps * (32 * T)) {
+        // one coalesced line of queries per tile; lane l owns query base + t*32 + l
+        uint32_t qown[T];
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            const size_t i = base + (size_t)t * 32 + lane;
+            qown[t] = i < nq ? __ldcs(qs + i) : 0u;
+        }
+        uint32_t q[D], k[D];
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            q[d] = __shfl_sync(kFull, qown[d / G], gbase + (d % G));
+            k[d] = 0;
+        }
+        // ---- internal levels ----
+        for (int h = 0; h + 1 < L; h++) {
+            Keys<W> ks[D];
+            if (h < p.smem_levels) {
+                const uint32_t* sl = smem + p.smem_slot[h] + sub * W;
+                const uint32_t* gl = p.tree + p.level_slot[h] + sub * W;
+                const unsigned staged = p.smem_nodes[h];
+#pragma unroll
+                for (int d = 0; d < D; d++) {
+                    if (k[d] < staged) ks[d] = lds_keys<W>(sl + k[d] * 16u);
+                    else ks[d] = ldg_keys<W, false>(gl + (size_t)k[d] * 16u, pol_inner);
+                }
+            } else {
+                const uint32_t* gl = p.tree + p.level_slot[h] + sub * W;
+                if (h + 2 < L) {
+#pragma unroll
+                    for (int d = 0; d < D; d++) ks[d] = ldg_keys<W, false>(gl + (size_t)k[d] * 16u, pol_inner);
+                } else {  // last internal level: larger than L1, keep it out
+#pragma unroll
+                    for (int d = 0; d < D; d++) ks[d] = ldg_keys<W, true>(gl + (size_t)k[d] * 16u, pol_inner);
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < D; d++) k[d] = k[d] * 17u + group_count<G>(ks[d], q[d], gbase);
+        }
+        // ---- leaf level: s_tree.rs:322-325 ----
+        {
+            const uint32_t* gl = p.tree + p.level_slot[L - 1];
+            Keys<W> ks[D];
+#pragma unroll
+            for (int d = 0; d < D; d++) ks[d] = ldg_keys<W, true>(gl + (size_t)k[d] * 16u + sub * W, pol_leaf);
+            uint32_t myval[T];
+            unsigned long long myidx[T];
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                const unsigned c = group_count<G>(ks[d], q[d], gbase);  // 0..16, uniform in the group
+                // the answer sits in lane c / W of the group, element c % W
+                const uint32_t cand = pick<W>(ks[d], c % W);
+                uint32_t v = __shfl_sync(kFull, cand, gbase + (c < 16u ? c / W : 0u));
+                const unsigned long long pos = (unsigned long long)k[d] * 16ull + c;
+                if (c == 16u) v = pos < p.leaf_slots ? __ldg(gl + pos) : kMax;  // flat read spills into the next node
+                if (sub == (unsigned)(d % G)) {
+                    myval[d / G] = v;
+                    myidx[d / G] = pos < p.n ? pos : p.n;
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < T; t++) {
+                const size_t i = base + (size_t)t * 32 + lane;
+                if (i < nq) {
+                    __stcs(out_vals + i, myval[t]);
+                    if (out_idx) __stcs(out_idx + i, myidx[t]);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic kernel: one thread per query, any layout (all partitioned variants, B = 15, ...).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned count16(const uint32_t* __restrict__ p, uint32_t q) {
+    unsigned c = 0;
+    if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + i);
+            c += ((int)v.x < (int)q) + ((int)v.y < (int)q) + ((int)v.z < (int)q) + ((int)v.w < (int)q);
+        }
+    } else {  // unaligned window: partitioned_s_tree.rs:807,857,876 read_unaligned
+#pragma unroll
+        for (int i = 0; i < 16; i++) c += ((int)__ldg(p + i) < (int)q);
+    }
+    return c;
+}
+
+__global__ void __launch_bounds__(256)
+stree_search_generic(const __grid_constant__ SstTreeView v, const uint32_t* __restrict__ qs, size_t nq,
+                     uint32_t* __restrict__ out_vals, unsigned long long* __restrict__ out_idx) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t q = qs[i];
+        const unsigned long long part = (unsigned long long)(q >> v.shift);
+        uint32_t val = kMax;
+        unsigned long long index = v.n;
+        if (v.variant == SST_PLAIN || part < v.parts) {
+            unsigned long long s = 0, pb = 0;
+            switch (v.variant) {
+                case SST_COMPACT: pb = part * v.part_stride; break;
+                case SST_MAP: s = v.prefix_map[part]; break;
+                case SST_PLAIN: break;
+                default: s = part * v.start_mul; break;
+            }
+            const int L = v.levels;
+            for (int h = 0; h + 1 < L; h++) {
+                const unsigned c = count16(v.tree + v.level_slot[h] + pb + s, q);
+                s = s * v.mult[h] + 16ull * c;
+            }
+            const uint32_t* leaf = v.tree + v.level_slot[L - 1] + pb;
+            const unsigned c = count16(leaf + s, q);
+            const unsigned long long pos = s + c;  // flat slot inside the leaf level (of this part for COMPACT)
+            // The read below may spill into the next node (idx == 16, s_tree.rs:322-325).  Past the
+            // leaf level the reference reads allocation slack; defined as MAX.
+            val = pos < v.leaf_slots ? __ldg(leaf + pos) : kMax;
+            switch (v.variant) {
+                case SST_PLAIN: index = (s >> 4) * v.node_b + c; break;
+                case SST_MAP: index = pos; break;
+                case SST_COMPACT: {
+                    const unsigned long long st = v.part_start[part], cnt = v.part_start[part + 1] - st;
+                    index = st + (pos < cnt ? pos : cnt);
+                    break;
+                }
+                default: {
+                    const unsigned long long st = v.part_start[part], cnt = v.part_start[part + 1] - st, pp = v.part_pos[part];
+                    const unsigned long long off = pos > pp ? pos - pp : 0;
+                    index = st + (off < cnt ? off : cnt);
+                    break;
+                }
+            }
+            if (index > v.n) index = v.n;
+        }
+        out_vals[i] = val;
+        if (out_idx) out_idx[i] = index;
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Random 64-byte gather probe: the access pattern of ONE tree level without the dependent chain.
+// Gives the practical ceiling of "one random node per query" on this GPU for each lane mapping.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+
+template <int G, int D>
+__global__ void __launch_bounds__(1024, 1)
+gather_probe_kernel(const uint32_t* __restrict__ buf, unsigned long long nodes, size_t n_gathers, uint32_t* __restrict__ sink,
+                    unsigned long long seed) {
+    constexpr int W = 16 / G;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const unsigned sub = lane & (G - 1), grp = lane / G;
+    constexpr unsigned GROUPS = 32 / G;
+    const uint64_t pol = policy_evict_first();
+    unsigned acc = 0;
+    const size_t per_warp = (size_t)GROUPS * D;
+    for (size_t base = ((size_t)blockIdx.x * warps + warp) * per_warp; base < n_gathers; base += (size_t)gridDim.x * warps * per_warp) {
+        Keys<W> ks[D];
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            const uint64_t id = mix64(seed + base + (size_t)grp * D + d) % nodes;
+            ks[d] = ldg_keys<W, true>(buf + id * 16 + sub * W, pol);
+        }
+#pragma unroll
+        for (int d = 0; d < D; d++)
+#pragma unroll
+            for (int i = 0; i < W; i++) acc += ks[d].k[i] < 0x40000000u;
+    }
+    if (acc == 0xffffffffu) sink[0] = acc;  // never true; keeps the loads alive
+}
+
+// ------------------------------------------------------------------------------------------------
+// Launch planning
+// ------------------------------------------------------------------------------------------------
+int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+struct Plan {
+    FastParams fp;
+    size_t smem_bytes;
+    int threads;
+    int grid;
+};
+
+bool fast_eligible(const sst_index* idx) { return idx->variant == SST_PLAIN && idx->node_b == 16; }
+
+Plan make_plan(const sst_index* idx, size_t nq, int T) {
+    Plan pl{};
+    FastParams& fp = pl.fp;
+    fp.tree = idx->d_tree;
+    fp.levels = idx->levels;
+    fp.leaf_slots = (unsigned long long)idx->layer_sizes[idx->levels - 1] * 16;
+    fp.n = idx->n;
+    fp.hints = env_int("SST_HINTS", 3);
+    for (int h = 0; h < idx->levels; h++) fp.level_slot[h] = (unsigned long long)idx->offsets[h] * 16;
+    const size_t cap_total = max_smem_optin(idx->device);
+    // Staging the top of the tree costs every CTA one pass over it; only worth it for big batches.
+    size_t budget = (size_t)env_int("SST_SMEM_KB", nq >= ((size_t)1 << 20) ? 224 : (nq >= (1 << 16) ? 16 : 0)) * 1024;
+    budget = std::min(budget, cap_total > 2048 ? cap_total - 2048 : 0);
+    size_t used = 0;
+    int sl = 0;
+    for (int h = 0; h + 1 < idx->levels; h++) {
+        const size_t nodes = std::min(idx->layer_sizes[h], (budget - used) / 64);
+        if (nodes == 0) break;
+        fp.smem_slot[h] = (unsigned)(used / 4);
+        fp.smem_nodes[h] = (unsigned)nodes;
+        used += nodes * 64;
+        sl = h + 1;
+        if (nodes < idx->layer_sizes[h]) break;
+    }
+    fp.smem_levels = sl;
+    pl.smem_bytes = used;
+    pl.threads = env_int("SST_THREADS", 1024);
+    const int sms = sm_count(idx->device);
+    const size_t per_cta = (size_t)(pl.threads / 32) * 32 * T;
+    const size_t ctas_needed = div_ceil(nq, per_cta);
+    int ctas_per_sm = 1;
+    if (used <= 100 * 1024 && pl.threads <= 512) ctas_per_sm = 2;
+    pl.grid = (int)std::min<size_t>(ctas_needed, (size_t)sms * ctas_per_sm * (size_t)env_int("SST_WAVES", 1));
+    if (pl.grid < 1) pl.grid = 1;
+    return pl;
+}
+
+template <int G, int T>
+int launch_fast(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx,
+                cudaStream_t st) {
+    Plan pl = make_plan(idx, nq, T);
+    auto kern = stree_search_fast<G, T>;
+    if (pl.smem_bytes > 48 * 1024 &&
+        !SST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes)))
+        return SST_ERR_CUDA;
+    kern<<<pl.grid, pl.threads, pl.smem_bytes, st>>>(pl.fp, d_qs, nq, d_vals, d_idx);
+    return SST_CUDA_OK(cudaGetLastError()) ? SST_OK : SST_ERR_CUDA;
+}
+
+}  // namespace
+
+int query_launch_count(const sst_index*, int) { return 1; }
+
+int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx,
+                 int scheme, cudaStream_t st) {
+    if (nq == 0) return SST_OK;
+    if (scheme == SST_SCHEME_AUTO) scheme = fast_eligible(idx) ? env_int("SST_SCHEME", SST_SCHEME_GROUP4) : SST_SCHEME_GENERIC;
+    if (scheme != SST_SCHEME_GENERIC && !fast_eligible(idx)) {
+        set_error(SST_ERR_UNSUPPORTED, "the group kernels serve the plain B=16 tree; use SST_SCHEME_AUTO or SST_SCHEME_GENERIC");
+        return SST_ERR_UNSUPPORTED;
+    }
+    const int T = env_int("SST_T", 2);
+    switch (scheme) {
+        case SST_SCHEME_GROUP4:
+            if (T == 1) return launch_fast<4, 1>(idx, d_qs, nq, d_vals, d_idx, st);
+            return launch_fast<4, 2>(idx, d_qs, nq, d_vals, d_idx, st);
+        case SST_SCHEME_GROUP16:
+            return launch_fast<16, 1>(idx, d_qs, nq, d_vals, d_idx, st);
+        case SST_SCHEME_GROUP2:
+            if (T == 1) return launch_fast<2, 1>(idx, d_qs, nq, d_vals, d_idx, st);
+            return launch_fast<2, 2>(idx, d_qs, nq, d_vals, d_idx, st);
+        case SST_SCHEME_GENERIC: {
+            const int sms = sm_count(idx->device);
+            const int grid = (int)std::min<size_t>(div_ceil(nq, 256), (size_t)sms * 32);
+            stree_search_generic<<<grid, 256, 0, st>>>(idx->view, d_qs, nq, d_vals, d_idx);
+            return SST_CUDA_OK(cudaGetLastError()) ? SST_OK : SST_ERR_CUDA;
+        }
+        default:
+            set_error(SST_ERR_ARG, "unknown scheme");
+            return SST_ERR_ARG;
+    }
+}
+
+}  // namespace sst
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace sst;
+
+extern "C" {
+
+int sst_query_launches(const sst_index_t* idx, int scheme) { return idx ? query_launch_count(idx, scheme) : 0; }
+
+int sst_query_device(const sst_index_t* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_out_vals, uint64_t* d_out_idx,
+                     int scheme, void* stream) {
+    clear_error();
+    if (!idx || (nq && (!d_qs || !d_out_vals))) { set_error(SST_ERR_ARG, "null argument"); return SST_ERR_ARG; }
+    DeviceGuard g(idx->device);
+    if (!g.ok) return SST_ERR_CUDA;
+    cudaStream_t st = stream ? (cudaStream_t)stream : thread_stream(idx->device);
+    return launch_query(idx, d_qs, nq, d_out_vals, (unsigned long long*)d_out_idx, scheme, st);
+}
+
+// Host buffers: chunked three-stage pipeline (H2D | kernel | D2H) over two copy streams and the
+// compute stream, so that PCIe traffic in both directions overlaps the kernel.
+int sst_query(const sst_index_t* idx, const uint32_t* qs, size_t nq, uint32_t* out_vals, uint64_t* out_idx, int scheme) {
+    clear_error();
+    if (!idx || (nq && (!qs || !out_vals))) { set_error(SST_ERR_ARG, "null argument"); return SST_ERR_ARG; }
+    if (nq == 0) return SST_OK;
+    DeviceGuard g(idx->device);
+    if (!g.ok) return SST_ERR_CUDA;
+    const int dev = idx->device;
+    cudaStream_t s_in = thread_copy_stream(dev, 0), s_k = thread_stream(dev), s_out = thread_copy_stream(dev, 1);
+    if (!s_in || !s_k || !s_out) return SST_ERR_CUDA;
+    const size_t chunk = std::max<size_t>((size_t)env_int("SST_CHUNK", 1 << 24), 1024);
+    const size_t nchunks = div_ceil(nq, chunk);
+    const int NB = nchunks > 1 ? 3 : 1;  // device-side ring
+    const size_t cap = std::min(chunk, nq);
+    uint32_t* d_q[3] = {};
+    uint32_t* d_v[3] = {};
+    unsigned long long* d_i[3] = {};
+    cudaEvent_t e_in[3] = {}, e_k[3] = {}, e_out[3] = {};
+    int rc = SST_OK;
+    for (int b = 0; b < NB && rc == SST_OK; b++) {
+        if (!SST_CUDA_OK(cudaMalloc(&d_q[b], cap * 4)) || !SST_CUDA_OK(cudaMalloc(&d_v[b], cap * 4)) ||
+            (out_idx && !SST_CUDA_OK(cudaMalloc(&d_i[b], cap * 8))) ||
+            !SST_CUDA_OK(cudaEventCreateWithFlags(&e_in[b], cudaEventDisableTiming)) ||
+            !SST_CUDA_OK(cudaEventCreateWithFlags(&e_k[b], cudaEventDisableTiming)) ||
+            !SST_CUDA_OK(cudaEventCreateWithFlags(&e_out[b], cudaEventDisableTiming)))
+            rc = SST_ERR_CUDA;
+    }
+    for (size_t c = 0; c < nchunks && rc == SST_OK; c++) {
+        const int b = (int)(c % NB);
+        const size_t off = c * chunk, cnt = std::min(chunk, nq - off);
+        // buffer b is free once the D2H of chunk c-NB has finished
+        if (c >= (size_t)NB && !SST_CUDA_OK(cudaStreamWaitEvent(s_in, e_out[b], 0))) { rc = SST_ERR_CUDA; break; }
+        if (!SST_CUDA_OK(cudaMemcpyAsync(d_q[b], qs + off, cnt * 4, cudaMemcpyHostToDevice, s_in)) ||
+            !SST_CUDA_OK(cudaEventRecord(e_in[b], s_in)) || !SST_CUDA_OK(cudaStreamWaitEvent(s_k, e_in[b], 0))) { rc = SST_ERR_CUDA; break; }
+        rc = launch_query(idx, d_q[b], cnt, d_v[b], d_i[b], scheme, s_k);
+        if (rc != SST_OK) break;
+        if (!SST_CUDA_OK(cudaEventRecord(e_k[b], s_k)) || !SST_CUDA_OK(cudaStreamWaitEvent(s_out, e_k[b], 0)) ||
+            !SST_CUDA_OK(cudaMemcpyAsync(out_vals + off, d_v[b], cnt * 4, cudaMemcpyDeviceToHost, s_out)) ||
+            (out_idx && !SST_CUDA_OK(cudaMemcpyAsync(out_idx + off, d_i[b], cnt * 8, cudaMemcpyDeviceToHost, s_out))) ||
+            !SST_CUDA_OK(cudaEventRecord(e_out[b], s_out))) { rc = SST_ERR_CUDA; break; }
+    }
+    if (!SST_CUDA_OK(cudaStreamSynchronize(s_in)) || !SST_CUDA_OK(cudaStreamSynchronize(s_k)) ||
+        !SST_CUDA_OK(cudaStreamSynchronize(s_out)))
+        rc = rc == SST_OK ? SST_ERR_CUDA : rc;
+    for (int b = 0; b < NB; b++) {
+        cudaFree(d_q[b]); cudaFree(d_v[b]); cudaFree(d_i[b]);
+        if (e_in[b]) cudaEventDestroy(e_in[b]);
+        if (e_k[b]) cudaEventDestroy(e_k[b]);
+        if (e_out[b]) cudaEventDestroy(e_out[b]);
+    }
+    return rc;
+}
+
+double sst_time_query_device(const sst_index_t* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_out_vals,
+                             uint64_t* d_out_idx, int scheme, int warmup, int iters) {
+    clear_error();
+    if (!idx || iters < 1) { set_error(SST_ERR_ARG, "bad argument"); return -1.0; }
+    DeviceGuard g(idx->device);
+    if (!g.ok) return -1.0;
+    cudaStream_t st = thread_stream(idx->device);
+    cudaEvent_t a, b;
+    if (!SST_CUDA_OK(cudaEventCreate(&a)) || !SST_CUDA_OK(cudaEventCreate(&b))) return -1.0;
+    for (int i = 0; i < warmup; i++)
+        if (launch_query(idx, d_qs, nq, d_out_vals, (unsigned long long*)d_out_idx, scheme, st) != SST_OK) return -1.0;
+    cudaEventRecord(a, st);
+    for (int i = 0; i < iters; i++)
+        if (launch_query(idx, d_qs, nq, d_out_vals, (unsigned long long*)d_out_idx, scheme, st) != SST_OK) return -1.0;
+    cudaEventRecord(b, st);
+    float ms = 0;
+    bool ok = SST_CUDA_OK(cudaEventSynchronize(b)) && SST_CUDA_OK(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    return ok ? (double)ms / iters : -1.0;
+}
+
+double sst_probe_gather64(int device, size_t bytes, size_t n_gathers, int lanes_per_node, int iters) {
+    clear_error();
+    if (!device_usable(device)) { set_error(SST_ERR_CUDA, "device is not an sm_100 GPU"); return -1.0; }
+    if (bytes < 64 || iters < 1) { set_error(SST_ERR_ARG, "bad argument"); return -1.0; }
+    DeviceGuard g(device);
+    if (!g.ok) return -1.0;
+    cudaStream_t st = thread_stream(device);
+    uint32_t *buf = nullptr, *sink = nullptr;
+    const unsigned long long nodes = bytes / 64;
+    if (!SST_CUDA_OK(cudaMalloc(&buf, nodes * 64)) || !SST_CUDA_OK(cudaMalloc(&sink, 64))) { cudaFree(buf); return -1.0; }
+    cudaMemsetAsync(buf, 0x55, nodes * 64, st);
+    const int grid = sm_count(device), threads = 1024;
+    auto launch = [&](unsigned long long seed) {
+        switch (lanes_per_node) {
+            case 16: gather_probe_kernel<16, 16><<<grid, threads, 0, st>>>(buf, nodes, n_gathers, sink, seed); break;
+            case 8: gather_probe_kernel<8, 8><<<grid, threads, 0, st>>>(buf, nodes, n_gathers, sink, seed); break;
+            case 4: gather_probe_kernel<4, 8><<<grid, threads, 0, st>>>(buf, nodes, n_gathers, sink, seed); break;
+            case 2: gather_probe_kernel<2, 4><<<grid, threads, 0, st>>>(buf, nodes, n_gathers, sink, seed); break;
+            default: return false;
+        }
+        return true;
+    };
+    double result = -1.0;
+    if (!launch(1)) set_error(SST_ERR_ARG, "lanes_per_node must be 2, 4, 8 or 16");
+    else {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, st);
+        for (int i = 0; i < iters; i++) launch(1000003ull * (i + 2));
+        cudaEventRecord(b, st);
+        float ms = 0;
+        if (SST_CUDA_OK(cudaEventSynchronize(b)) && SST_CUDA_OK(cudaEventElapsedTime(&ms, a, b)) && SST_CUDA_OK(cudaGetLastError()))
+            result = (double)n_gathers * 64.0 * iters / (ms * 1e-3) / 1e9;
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+    }
+    cudaFree(buf);
+    cudaFree(sink);
+    return result;
+}
+
+}  // extern "C"

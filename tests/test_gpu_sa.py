@@ -1,0 +1,97 @@
+"""GPU parity tests (-m gpu): suffix array construction and pattern search vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from util import random_patterns, random_text
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_search(sst, oracle, sa_obj, text, sa, pats):
+    flat, off = sst.pack_patterns(pats)
+    oflat, ooff = oracle.pack_patterns(pats)
+    elo, ehi, epos, _ = oracle.sa_search(text, sa, oflat, ooff)
+    for mode in (sst.SA_BINARY, sst.SA_MLR):
+        lo, hi, pos = sa_obj.search(flat, off, mode)
+        assert np.array_equal(lo, elo), mode
+        assert np.array_equal(hi, ehi), mode
+        assert np.array_equal(pos, epos), mode
+    lo, hi, pos = sa_obj.search(flat, off, sst.SA_BINARY, want_hi=False)
+    assert hi is None and np.array_equal(lo, elo) and np.array_equal(pos, epos)
+
+
+@pytest.mark.parametrize("n,sigma", [(1, 4), (2, 4), (7, 4), (8, 2), (100, 4), (5000, 4), (60_000, 4), (60_000, 256), (30_000, 1), (40_000, 2)])
+def test_sa_build_matches_oracle(gpu, oracle, n, sigma):
+    """The suffix array is unique: GPU prefix doubling == oracle sort; strict order holds (sa_search.rs:36-38)."""
+    sst = gpu
+    text = random_text(n, seed=n + sigma, sigma=sigma)
+    s = sst.SaNaive.build(text)
+    sa = s.sa
+    assert np.array_equal(sa, oracle.sa_build(text))
+    assert s.check() == 0 and oracle.sa_check(text, sa) == 0
+
+
+def test_sa_build_repetitive(gpu, oracle):
+    sst = gpu
+    unit = random_text(37, seed=1)
+    text = np.concatenate([np.tile(unit, 300), random_text(500, seed=2), np.tile(unit, 100)])
+    s = sst.SaNaive.build(text)
+    assert np.array_equal(s.sa, oracle.sa_build(text))
+    assert s.check() == 0
+
+
+def test_sa_check_detects_corruption(gpu, oracle):
+    sst = gpu
+    text = random_text(10_000, seed=4)
+    sa = oracle.sa_build(text)
+    bad = sa.copy()
+    bad[[100, 101]] = bad[[101, 100]]
+    assert sst.SaNaive.from_parts(text, sa).check() == 0
+    assert sst.SaNaive.from_parts(text, bad).check() > 0
+
+
+@pytest.mark.parametrize("lanes", ["32", "8", "4"])
+def test_sa_search_parity(gpu, oracle, lanes, monkeypatch):
+    sst = gpu
+    monkeypatch.setenv("SST_SA_LANES", lanes)
+    text = random_text(200_000, seed=11)
+    s = sst.SaNaive.build(text)
+    sa = s.sa
+    rng = np.random.default_rng(12)
+    pats = random_patterns(text, 3000, seed=13)                      # util.rs:18-26
+    pats += [text[i : i + 32].tobytes() for i in rng.integers(0, text.size - 200, 500)]  # config C3: 32-mers
+    pats += [bytes(rng.integers(0, 4, int(l), dtype=np.uint8)) for l in rng.integers(1, 40, 500)]  # mostly absent
+    pats += [b"", bytes([3] * 64), bytes([0] * 64), bytes([0]), bytes([3]), bytes([4]), bytes([255] * 3),
+             text[-1:].tobytes(), text[-7:].tobytes(), text[-40:].tobytes(), text[-40:].tobytes() + b"\x00",
+             text[:150].tobytes(), text.tobytes()[:1000]]
+    _check_search(sst, oracle, s, text, sa, pats)
+
+
+def test_sa_search_repetitive_text(gpu, oracle):
+    """Long LCPs: all-equal text and tandem repeats (many occurrences -> hi - lo large)."""
+    sst = gpu
+    for text in (np.zeros(5000, np.uint8), np.tile(random_text(13, seed=5), 700)):
+        s = sst.SaNaive.build(text)
+        sa = s.sa
+        assert np.array_equal(sa, oracle.sa_build(text))
+        pats = [text[i : i + l].tobytes() for i, l in [(0, 1), (0, 13), (5, 64), (100, 300), (4000, 999), (4990, 10), (4990, 11)]]
+        pats += [bytes([1]), bytes([0] * 6000)]
+        _check_search(sst, oracle, s, text, sa, pats)
+
+
+def test_sa_byte_alphabet(gpu, oracle):
+    sst = gpu
+    text = random_text(50_000, seed=21, sigma=256)
+    s = sst.SaNaive.build(text)
+    pats = random_patterns(text, 2000, seed=22, lo=1, hi=20) + [bytes([255, 255]), bytes([0, 0]), bytes([128])]
+    _check_search(sst, oracle, s, text, s.sa, pats)
+
+
+def test_sa_reference_return_value(gpu, oracle):
+    """binary_search returns sa[l] (sa_search.rs:111): the text position of the lower-bound suffix."""
+    sst = gpu
+    text = random_text(100_000, seed=31)
+    s = sst.SaNaive.build(text)
+    q = text[5000:5040].tobytes()
+    pos = s.binary_search(q)
+    assert text[pos : pos + 40].tobytes() == q
