@@ -11,7 +11,8 @@
  *
  * Conventions
  *   - plain pointers and sizes only; no CUDA or torch types in any signature (streams are
- *     passed as `void*` holding a cudaStream_t, NULL = the library's own per-thread stream).
+ *     passed as `void*` holding a cudaStream_t; NULL is the CUDA legacy default stream, which is
+ *     also what torch.cuda.current_stream().cuda_stream returns for torch's default stream).
  *   - the caller owns every input/output buffer; a handle owns its device memory.
  *   - functions returning int return 0 on success, non-zero on failure; pointer-returning
  *     builders return NULL on failure.  sst_last_error() gives the message (thread-local).
@@ -57,10 +58,11 @@ enum { SST_PLAIN = 0, SST_SIMPLE = 1, SST_COMPACT = 2, SST_L1 = 3, SST_OVERLAPPI
  * SearchScheme closures over one index (sst/bin/bench.rs:93-96).  All return identical results. */
 enum {
     SST_SCHEME_AUTO = 0,     /* best measured kernel for the index */
-    SST_SCHEME_GROUP4 = 1,   /* 4 lanes x 16 B per node, top levels in shared memory */
+    SST_SCHEME_GROUP4 = 1,   /* 4 lanes x 16 B per node (LDG.128), every level from L1/L2 */
     SST_SCHEME_GROUP16 = 2,  /* 16 lanes x 4 B per node + ballot/popc (north-star baseline) */
     SST_SCHEME_GROUP2 = 3,   /* 2 lanes x 32 B per node (LDG.256) */
-    SST_SCHEME_GENERIC = 4   /* one thread per query, any layout */
+    SST_SCHEME_GENERIC = 4,  /* one thread per query, any layout */
+    SST_SCHEME_TABLE = 5     /* top levels answered by a shared-memory rank table (TMA-staged), rest as GROUP2 */
 };
 
 /* SA search modes */

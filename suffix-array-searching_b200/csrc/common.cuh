@@ -35,6 +35,7 @@ cudaStream_t thread_stream(int device);
 // Two extra per-thread streams used by the chunked host-buffer pipeline.
 cudaStream_t thread_copy_stream(int device, int which);
 
+void configure_l2_fetch(int device);  // must run with `device` current
 int sm_count(int device);
 size_t max_smem_optin(int device);
 bool device_usable(int device);
@@ -84,6 +85,13 @@ struct sst_index {
     uint32_t* d_part_start = nullptr;             // [parts + 1]
     unsigned long long* d_part_pos = nullptr;     // [parts]
     size_t l1_field = 0;                          // the `l1` struct field (max(l1,16) for OL)
+    // shared-memory rank table replacing levels [0, top_level) of the plain B=16 tree
+    int top_level = 0;
+    size_t top_nbound = 0;
+    uint16_t* d_top_table = nullptr;              // [2^15 + 1] separators-before-bucket counts
+    uint16_t* d_top_low = nullptr;                // [top_nbound] low 16 bits of each separator
+    bool persist_ok = false;                      // persisting-L2 carve-out configured on this device
+    size_t persist_window_max = 0;
     SstTreeView view{};
 };
 
@@ -92,6 +100,7 @@ namespace sst {
 sst_index* build_plain(const uint32_t* d_sorted, bool sorted_is_owned_leaf, size_t n, uint32_t node_b, uint32_t flags, int device);
 sst_index* build_partitioned(const uint32_t* d_sorted, size_t n, uint32_t b, int variant, int device);
 void finalize_view(sst_index* idx);
+bool build_top_table(sst_index* idx, const uint32_t* d_sorted);
 // search (stree_search.cu)
 int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx,
                  int scheme, cudaStream_t stream);

@@ -1,5 +1,6 @@
 // runtime.cu -- error state, device selection and per-thread streams.
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -51,6 +52,24 @@ static cudaStream_t get_stream(int device, int which) {
 }
 cudaStream_t thread_stream(int device) { return get_stream(device, 0); }
 cudaStream_t thread_copy_stream(int device, int which) { return get_stream(device, 1 + (which & 1)); }
+
+// L2 fetch granularity (cudaLimitMaxL2FetchGranularity).  The hot path reads isolated 64-byte
+// nodes; with the default 128-byte granularity every leaf miss moves twice the bytes it needs
+// (measured: dram__bytes_read = 2x algorithmic, profiles/).  SST_L2_FETCH overrides (0 = leave).
+void configure_l2_fetch(int device) {
+    static thread_local bool done[kMaxDevices] = {};
+    if (device < 0 || device >= kMaxDevices || done[device]) return;
+    done[device] = true;
+    const char* e = getenv("SST_L2_FETCH");
+    const int want = e && *e ? atoi(e) : 64;
+    if (want <= 0) return;
+    size_t before = 0, after = 0;
+    cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
+    const cudaError_t rc = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)want);
+    cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
+    if (rc != cudaSuccess) (void)cudaGetLastError();
+    if (getenv("SST_DEBUG")) fprintf(stderr, "[sst] L2 fetch granularity: before=%zu want=%d rc=%d after=%zu\n", before, want, (int)rc, after);
+}
 
 int sm_count(int device) {
     int v = 0;

@@ -294,7 +294,7 @@ sst_sa_t* sst_sa_build_device(const uint8_t* d_text, size_t n, int device) {
     if (n >= 0xfffffff0ull) { set_error(SST_ERR_UNSUPPORTED, "text must be shorter than 2^32 - 16 (u32 suffix array, sa_search.rs:35)"); return nullptr; }
     if (!device_usable(device)) { set_error(SST_ERR_CUDA, "device is not an sm_100 GPU (no CPU fallback)"); return nullptr; }
     DeviceGuard g(device);
-    if (!g.ok) return nullptr;
+    if (!g.ok || !SST_CUDA_OK(cudaDeviceSynchronize())) return nullptr;  // the text may come from another stream
     auto* s = new sst_sa();
     s->device = device;
     s->n = n;
@@ -383,7 +383,7 @@ int sst_sa_search_device(const sst_sa_t* s, const uint8_t* d_pats, const uint64_
     if (npat == 0) return SST_OK;
     DeviceGuard g(s->device);
     if (!g.ok) return SST_ERR_CUDA;
-    cudaStream_t st = stream ? (cudaStream_t)stream : thread_stream(s->device);
+    cudaStream_t st = (cudaStream_t)stream;  // NULL == the CUDA legacy default stream
     SaParams p{};
     p.text = s->d_text; p.sa = s->d_sa; p.n = s->n;
     p.pats = d_pats; p.pat_off = (const unsigned long long*)d_pat_off; p.npat = npat;

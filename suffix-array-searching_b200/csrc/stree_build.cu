@@ -15,6 +15,8 @@
 //     the already-written leaf layer (partitioned layouts, whose separators include fill keys).
 // The image is bit-identical to the reference's (tests compare it against the oracle).
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -79,7 +81,9 @@ __global__ void plain_leaf_kernel(const uint32_t* __restrict__ vals, uint32_t* _
         const unsigned long long i = s < B ? j * B + s : (j + 1) * B;  // slot B of a B<16 node: next leaf's first key (:137-139)
         uint32_t v;
         if (i < n) v = vals[i];
-        else v = (j == n / B && s >= n % B) ? kMax : (zero_tail ? 0u : kMax);  // :142-145; other nodes stay zero (hugepages)
+        else if (j == n / B && s >= n % B) v = kMax;  // :142-145
+        else if (s >= B && n % B == 0 && j + 1 == n / B) v = kMax;  // deviation: reference leaves a stray 0 here
+        else v = zero_tail ? 0u : kMax;  // other nodes stay zero (hugepages)
         tree[base + t] = v;
     }
 }
@@ -111,6 +115,32 @@ __global__ void fill_kernel(uint32_t* __restrict__ p, unsigned long long count, 
         p[t] = value;
 }
 
+
+// ---- shared-memory rank table for the top of the plain tree (see stree_search.cu) --------------
+// Separator before node c (c >= 1) of level t: the key the builder formula of s_tree.rs:156-172
+// places between the subtrees of nodes c-1 and c, i.e. vals[f*16 - 1] (left_max) or vals[f*16]
+// with f = c * 17^(H-1-t) the first leaf below node c.
+__global__ void top_bounds_kernel(const uint32_t* __restrict__ vals, unsigned nbound, unsigned long long leaf_stride, int left_max,
+                                  uint32_t* __restrict__ bkeys, uint16_t* __restrict__ low) {
+    for (unsigned c = blockIdx.x * blockDim.x + threadIdx.x; c < nbound; c += gridDim.x * blockDim.x) {
+        const unsigned long long i = (unsigned long long)(c + 1) * leaf_stride * 16ull;
+        const uint32_t key = left_max ? vals[i - 1] : vals[i];
+        bkeys[c] = key;
+        low[c] = (uint16_t)(key & 0xffffu);
+    }
+}
+// table[b] = number of separators whose key >> 16 is < b, b in [0, 2^15]
+__global__ void top_table_kernel(const uint32_t* __restrict__ bkeys, unsigned nbound, uint16_t* __restrict__ table) {
+    for (unsigned b = blockIdx.x * blockDim.x + threadIdx.x; b <= (1u << 15); b += gridDim.x * blockDim.x) {
+        unsigned lo = 0, hi = nbound;
+        while (lo < hi) {
+            const unsigned m = (lo + hi) >> 1;
+            if ((bkeys[m] >> 16) < b) lo = m + 1; else hi = m;
+        }
+        table[b] = (uint16_t)lo;
+    }
+}
+
 bool validate_keys(const uint32_t* d_sorted, size_t n, int device) {
     unsigned* d_flags = nullptr;
     if (!SST_CUDA_OK(cudaMalloc(&d_flags, sizeof(unsigned)))) return false;
@@ -128,6 +158,26 @@ bool validate_keys(const uint32_t* d_sorted, size_t n, int device) {
     if (flags & 1u) { set_error(SST_ERR_ARG, "key larger than i32::MAX (reference: assert!(v <= MAX), s_tree.rs:87-89)"); return false; }
     if (flags & 2u) { set_error(SST_ERR_ARG, "keys are not sorted"); return false; }
     return true;
+}
+
+// Optional persisting-L2 carve-out (SST_PERSIST != 0): lets a per-launch access-policy window pin
+// the last internal level.  Device-wide limit, so only touched when asked for.
+void configure_persisting_l2(sst_index* idx) {
+    const char* e = getenv("SST_PERSIST");
+    if (!e || atoi(e) == 0) return;
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, idx->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, idx->device);
+    if (max_persist <= 0 || max_window <= 0) return;
+    const cudaError_t rc = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+    if (getenv("SST_DEBUG")) {
+        size_t got = 0;
+        cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize);
+        fprintf(stderr, "[sst] persisting L2: max=%d window_max=%d set rc=%d limit now=%zu\n", max_persist, max_window, (int)rc, got);
+    }
+    if (rc != cudaSuccess) { (void)cudaGetLastError(); return; }
+    idx->persist_ok = true;
+    idx->persist_window_max = (size_t)max_window;
 }
 
 }  // namespace
@@ -148,6 +198,7 @@ sst_index* build_plain(const uint32_t* d_sorted, bool, size_t n, uint32_t node_b
     if (!device_usable(device)) { set_error(SST_ERR_CUDA, "device is not an sm_100 GPU (no CPU fallback)"); return nullptr; }
     DeviceGuard guard(device);
     if (!guard.ok) return nullptr;
+    configure_l2_fetch(device);
     if (!validate_keys(d_sorted, n, device)) return nullptr;
 
     const size_t B = node_b;
@@ -197,6 +248,12 @@ sst_index* build_plain(const uint32_t* d_sorted, bool, size_t n, uint32_t node_b
         delete idx;
         return nullptr;
     }
+    if (!build_top_table(idx, d_sorted)) {
+        cudaFree(idx->d_tree);
+        delete idx;
+        return nullptr;
+    }
+    configure_persisting_l2(idx);
     finalize_view(idx);
     return idx;
 }
@@ -395,10 +452,54 @@ void free_index(sst_index* idx) {
     cudaFree(idx->d_prefix_map);
     cudaFree(idx->d_part_start);
     cudaFree(idx->d_part_pos);
+    cudaFree(idx->d_top_table);
+    cudaFree(idx->d_top_low);
     delete idx;
 }
 
 }  // namespace
+
+// Chooses the deepest level t whose node count fits 16-bit ranks and shared memory, and builds
+// the rank table for it.  Plain B=16 trees only; a tree of height 1 has no table.
+bool build_top_table(sst_index* idx, const uint32_t* d_sorted) {
+    if (idx->variant != SST_PLAIN || idx->node_b != 16 || idx->levels < 2) return true;
+    const size_t H = idx->levels, n = idx->n;
+    const size_t smem_cap = max_smem_optin(idx->device);
+    const size_t table_bytes = (((size_t)(1u << 15) + 1) * 2 + 15) & ~(size_t)15;
+    int t = 0;
+    size_t nb = 0;
+    for (size_t lvl = 1; lvl < H; lvl++) {
+        const size_t real_nodes = div_ceil(tb_layer_size(n, lvl, H, 16), 16);  // full_array has more slots, not more nodes
+        if (real_nodes < 2) continue;
+        const size_t bounds = real_nodes - 1;
+        if (bounds > 65535) break;
+        if (table_bytes + ((bounds * 2 + 15) & ~(size_t)15) + 4096 > smem_cap) break;
+        t = (int)lvl;
+        nb = bounds;
+    }
+    if (t == 0) return true;
+    cudaStream_t st = thread_stream(idx->device);
+    uint32_t* d_bkeys = nullptr;
+    const size_t low_bytes = (nb * 2 + 15) & ~(size_t)15;
+    bool ok = SST_CUDA_OK(cudaMalloc(&d_bkeys, nb * 4)) && SST_CUDA_OK(cudaMalloc(&idx->d_top_table, table_bytes)) &&
+              SST_CUDA_OK(cudaMalloc(&idx->d_top_low, low_bytes)) && SST_CUDA_OK(cudaMemsetAsync(idx->d_top_table, 0, table_bytes, st)) &&
+              SST_CUDA_OK(cudaMemsetAsync(idx->d_top_low, 0, low_bytes, st));
+    if (ok) {
+        top_bounds_kernel<<<std::min<unsigned>(grid_for(nb), 148 * 8), kBuildThreads, 0, st>>>(
+            d_sorted, (unsigned)nb, ipow(17, H - 1 - t), (idx->flags & SST_LEFT_MAX) ? 1 : 0, d_bkeys, idx->d_top_low);
+        top_table_kernel<<<std::min<unsigned>(grid_for((1u << 15) + 1), 148 * 8), kBuildThreads, 0, st>>>(d_bkeys, (unsigned)nb, idx->d_top_table);
+        ok = SST_CUDA_OK(cudaGetLastError()) && SST_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    cudaFree(d_bkeys);
+    if (!ok) {
+        cudaFree(idx->d_top_table); cudaFree(idx->d_top_low);
+        idx->d_top_table = nullptr; idx->d_top_low = nullptr;
+        return false;
+    }
+    idx->top_level = t;
+    idx->top_nbound = nb;
+    return true;
+}
 
 sst_index* build_partitioned(const uint32_t* d_sorted, size_t n, uint32_t b, int variant, int device) {
     clear_error();
@@ -408,6 +509,7 @@ sst_index* build_partitioned(const uint32_t* d_sorted, size_t n, uint32_t b, int
     if (!device_usable(device)) { set_error(SST_ERR_CUDA, "device is not an sm_100 GPU (no CPU fallback)"); return nullptr; }
     DeviceGuard guard(device);
     if (!guard.ok) return nullptr;
+    configure_l2_fetch(device);
     if (!validate_keys(d_sorted, n, device)) return nullptr;
     cudaStream_t st = thread_stream(device);
     const size_t B = 16;
@@ -648,7 +750,17 @@ using namespace sst;
 
 extern "C" {
 
+// The keys may have been produced on any stream of the caller (e.g. a sort on torch's stream):
+// builders are not on the hot path, so they simply wait for the whole device first.
+static bool sync_device(int device) {
+    if (!device_usable(device)) { set_error(SST_ERR_CUDA, "device is not an sm_100 GPU (no CPU fallback)"); return false; }
+    DeviceGuard g(device);
+    return g.ok && SST_CUDA_OK(cudaDeviceSynchronize());
+}
+
 sst_index_t* sst_stree_build_device(const uint32_t* d_sorted, size_t n, uint32_t node_b, uint32_t flags, int device) {
+    clear_error();
+    if (!sync_device(device)) return nullptr;
     return build_plain(d_sorted, false, n, node_b, flags, device);
 }
 
@@ -673,6 +785,8 @@ sst_index_t* sst_stree_build(const uint32_t* sorted, size_t n, uint32_t node_b, 
 }
 
 sst_index_t* sst_pstree_build_device(const uint32_t* d_sorted, size_t n, uint32_t b, int variant, int device) {
+    clear_error();
+    if (!sync_device(device)) return nullptr;
     return build_partitioned(d_sorted, n, b, variant, device);
 }
 

@@ -22,6 +22,7 @@
 // All arithmetic is integer; results are bit-exact with the reference (signed compares as in
 // node.rs:91-108, flat leaf read that may spill into the next node as in s_tree.rs:322-325).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -162,48 +163,73 @@ __device__ __forceinline__ uint32_t pick(const Keys<W>& ks, unsigned e) {
 
 // ------------------------------------------------------------------------------------------------
 // Fast kernel: plain S+-tree with B = 16 (any of left_max / reverse_storage / full_array).
+//
+// TOP = true replaces the walk through levels [0, top_level) by a rank query in shared memory.
+// The in-order sequence of all keys stored in levels [0, top_level) is exactly the sorted list of
+// separators between consecutive nodes of level `top_level`, and the node the reference's
+// descent (s_tree.rs:196-203) reaches at that level is the number of separators < q.  The
+// builder stores, per index, a bucket table over the top 15 key bits (`top_table[b]` = number of
+// separators with key >> 16 < b) and the low 16 bits of every separator (`top_low`); both are
+// staged into shared memory once per CTA by 1-D TMA bulk copies.  One lane answers one rank
+// query with 2 + ~2 two-byte shared loads, which costs ~0.1 L1 data-pipe wavefronts per load
+// instead of the 1 wavefront per 64-byte node of the node walk (ncu: the node walk ran at 84 %
+// of the L1TEX data-pipe peak, profiles/r1_*).
 // ------------------------------------------------------------------------------------------------
 struct FastParams {
     const uint32_t* tree;
     unsigned long long level_slot[kMaxLevels];
-    unsigned smem_slot[kMaxLevels];   // first slot of level h inside shared memory
-    unsigned smem_nodes[kMaxLevels];  // nodes of level h staged in shared memory (prefix of the level)
     int levels;
-    int smem_levels;                  // levels [0, smem_levels) have smem_nodes > 0
+    int top_level;                    // first level read from global memory (0 without TOP)
+    const uint16_t* top_table;        // [2^15 + 1] (+ padding to 16 B)
+    const uint16_t* top_low;          // [top_nbound] (+ padding to 16 B)
+    unsigned top_nbound;
     unsigned long long leaf_slots;
     unsigned long long n;
     int hints;                        // bit0: L2 evict_last on inner levels, bit1: evict_first on leaf
 };
 
-template <int G, int T>
+constexpr unsigned kTopBuckets = 1u << 15;
+constexpr unsigned kTopTableBytes = ((kTopBuckets + 1) * 2 + 15) & ~15u;
+
+__device__ __forceinline__ unsigned top_rank(const uint16_t* __restrict__ tab, const uint16_t* __restrict__ low, uint32_t q) {
+    if (q > kMax) return 0;  // signed compare of node.rs:91-108: such a q is below every key
+    const unsigned b = q >> 16, ql = q & 0xffffu;
+    unsigned lo = tab[b], hi = tab[b + 1];
+    if (hi - lo > 8u) {  // skewed keys: many separators share the bucket
+        while (lo < hi) {
+            const unsigned m = (lo + hi) >> 1;
+            if (low[m] < ql) lo = m + 1; else hi = m;
+        }
+    } else {
+        while (lo < hi && low[lo] < ql) lo++;
+    }
+    return lo;
+}
+
+template <int G, int T, bool TOP>
 __global__ void __launch_bounds__(1024, 1)
 stree_search_fast(const __grid_constant__ FastParams p, const uint32_t* __restrict__ qs, size_t nq,
                   uint32_t* __restrict__ out_vals, unsigned long long* __restrict__ out_idx) {
     constexpr int W = 16 / G;   // keys per lane
     constexpr int D = G * T;    // descents in flight per lane group
-    extern __shared__ __align__(128) uint32_t smem[];
+    extern __shared__ __align__(128) uint16_t smem16[];
     __shared__ __align__(8) uint64_t bar;
+    const uint16_t* s_tab = smem16;
+    const uint16_t* s_low = smem16 + kTopTableBytes / 2;
 
-    // ---- stage the top levels: one elected thread issues 1-D TMA bulk copies ----
-    if (p.smem_levels > 0) {
+    if constexpr (TOP) {  // stage the rank table: one elected thread issues 1-D TMA bulk copies
         if (threadIdx.x == 0) {
             mbar_init(&bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            unsigned total = 0;
-            for (int h = 0; h < p.smem_levels; h++) total += p.smem_nodes[h] * 64u;
-            mbar_expect_tx(&bar, total);
-            for (int h = 0; h < p.smem_levels; h++) {
-                unsigned bytes = p.smem_nodes[h] * 64u, off = 0;
-                while (bytes) {  // keep each bulk copy <= 64 KiB
-                    const unsigned chunk = bytes < 65536u ? bytes : 65536u;
-                    tma_bulk_g2s(smem + p.smem_slot[h] + off / 4, p.tree + p.level_slot[h] + off / 4, chunk, &bar);
-                    off += chunk;
-                    bytes -= chunk;
-                }
-            }
+            const unsigned low_bytes = (p.top_nbound * 2u + 15u) & ~15u;
+            mbar_expect_tx(&bar, kTopTableBytes + low_bytes);
+            for (unsigned off = 0; off < kTopTableBytes; off += 32768u)
+                tma_bulk_g2s((char*)smem16 + off, (const char*)p.top_table + off, min(32768u, kTopTableBytes - off), &bar);
+            for (unsigned off = 0; off < low_bytes; off += 32768u)
+                tma_bulk_g2s((char*)smem16 + kTopTableBytes + off, (const char*)p.top_low + off, min(32768u, low_bytes - off), &bar);
         }
         mbar_wait(&bar, 0);
     }
@@ -213,42 +239,33 @@ stree_search_fast(const __grid_constant__ FastParams p, const uint32_t* __restri
     const uint64_t pol_inner = (p.hints & 1) ? policy_evict_last() : policy_evict_normal();
     const uint64_t pol_leaf = (p.hints & 2) ? policy_evict_first() : policy_evict_normal();
     const int L = p.levels;
+    const int h0 = TOP ? p.top_level : 0;
 
     for (size_t base = ((size_t)blockIdx.x * warps + warp) * (32 * T); base < nq; base += (size_t)gridDim.x * warps * (32 * T)) {
         // one coalesced line of queries per tile; lane l owns query base + t*32 + l
-        uint32_t qown[T];
+        uint32_t qown[T], kown[T];
 #pragma unroll
         for (int t = 0; t < T; t++) {
             const size_t i = base + (size_t)t * 32 + lane;
             qown[t] = i < nq ? __ldcs(qs + i) : 0u;
+            kown[t] = TOP ? top_rank(s_tab, s_low, qown[t]) : 0u;
         }
         uint32_t q[D], k[D];
 #pragma unroll
         for (int d = 0; d < D; d++) {
             q[d] = __shfl_sync(kFull, qown[d / G], gbase + (d % G));
-            k[d] = 0;
+            k[d] = TOP ? __shfl_sync(kFull, kown[d / G], gbase + (d % G)) : 0u;
         }
-        // ---- internal levels ----
-        for (int h = 0; h + 1 < L; h++) {
+        // ---- internal levels read from L1/L2 ----
+        for (int h = h0; h + 1 < L; h++) {
             Keys<W> ks[D];
-            if (h < p.smem_levels) {
-                const uint32_t* sl = smem + p.smem_slot[h] + sub * W;
-                const uint32_t* gl = p.tree + p.level_slot[h] + sub * W;
-                const unsigned staged = p.smem_nodes[h];
+            const uint32_t* gl = p.tree + p.level_slot[h] + sub * W;
+            if (h + 2 < L) {
 #pragma unroll
-                for (int d = 0; d < D; d++) {
-                    if (k[d] < staged) ks[d] = lds_keys<W>(sl + k[d] * 16u);
-                    else ks[d] = ldg_keys<W, false>(gl + (size_t)k[d] * 16u, pol_inner);
-                }
-            } else {
-                const uint32_t* gl = p.tree + p.level_slot[h] + sub * W;
-                if (h + 2 < L) {
+                for (int d = 0; d < D; d++) ks[d] = ldg_keys<W, false>(gl + (size_t)k[d] * 16u, pol_inner);
+            } else {  // last internal level: larger than L1, keep it out
 #pragma unroll
-                    for (int d = 0; d < D; d++) ks[d] = ldg_keys<W, false>(gl + (size_t)k[d] * 16u, pol_inner);
-                } else {  // last internal level: larger than L1, keep it out
-#pragma unroll
-                    for (int d = 0; d < D; d++) ks[d] = ldg_keys<W, true>(gl + (size_t)k[d] * 16u, pol_inner);
-                }
+                for (int d = 0; d < D; d++) ks[d] = ldg_keys<W, true>(gl + (size_t)k[d] * 16u, pol_inner);
             }
 #pragma unroll
             for (int d = 0; d < D; d++) k[d] = k[d] * 17u + group_count<G>(ks[d], q[d], gbase);
@@ -380,7 +397,7 @@ gather_probe_kernel(const uint32_t* __restrict__ buf, unsigned long long nodes, 
         Keys<W> ks[D];
 #pragma unroll
         for (int d = 0; d < D; d++) {
-            const uint64_t id = mix64(seed + base + (size_t)grp * D + d) % nodes;
+            const uint64_t id = ((mix64(seed + base + (size_t)grp * D + d) >> 32) * nodes) >> 32;  // multiply-shift range reduction
             ks[d] = ldg_keys<W, true>(buf + id * 16 + sub * W, pol);
         }
 #pragma unroll
@@ -399,62 +416,76 @@ int env_int(const char* name, int dflt) {
     return (s && *s) ? atoi(s) : dflt;
 }
 
-struct Plan {
-    FastParams fp;
-    size_t smem_bytes;
-    int threads;
-    int grid;
-};
-
 bool fast_eligible(const sst_index* idx) { return idx->variant == SST_PLAIN && idx->node_b == 16; }
+bool top_eligible(const sst_index* idx) { return fast_eligible(idx) && idx->d_top_table != nullptr; }
 
-Plan make_plan(const sst_index* idx, size_t nq, int T) {
-    Plan pl{};
-    FastParams& fp = pl.fp;
+template <int G, int T, bool TOP>
+int launch_fast(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx,
+                cudaStream_t st) {
+    FastParams fp{};
     fp.tree = idx->d_tree;
     fp.levels = idx->levels;
     fp.leaf_slots = (unsigned long long)idx->layer_sizes[idx->levels - 1] * 16;
     fp.n = idx->n;
     fp.hints = env_int("SST_HINTS", 3);
     for (int h = 0; h < idx->levels; h++) fp.level_slot[h] = (unsigned long long)idx->offsets[h] * 16;
-    const size_t cap_total = max_smem_optin(idx->device);
-    // Staging the top of the tree costs every CTA one pass over it; only worth it for big batches.
-    size_t budget = (size_t)env_int("SST_SMEM_KB", nq >= ((size_t)1 << 20) ? 224 : (nq >= (1 << 16) ? 16 : 0)) * 1024;
-    budget = std::min(budget, cap_total > 2048 ? cap_total - 2048 : 0);
-    size_t used = 0;
-    int sl = 0;
-    for (int h = 0; h + 1 < idx->levels; h++) {
-        const size_t nodes = std::min(idx->layer_sizes[h], (budget - used) / 64);
-        if (nodes == 0) break;
-        fp.smem_slot[h] = (unsigned)(used / 4);
-        fp.smem_nodes[h] = (unsigned)nodes;
-        used += nodes * 64;
-        sl = h + 1;
-        if (nodes < idx->layer_sizes[h]) break;
+    size_t smem_bytes = 0;
+    if (TOP) {
+        fp.top_level = idx->top_level;
+        fp.top_table = idx->d_top_table;
+        fp.top_low = idx->d_top_low;
+        fp.top_nbound = (unsigned)idx->top_nbound;
+        smem_bytes = kTopTableBytes + ((idx->top_nbound * 2 + 15) & ~(size_t)15);
     }
-    fp.smem_levels = sl;
-    pl.smem_bytes = used;
-    pl.threads = env_int("SST_THREADS", 1024);
+    const int threads = env_int("SST_THREADS", 1024);
     const int sms = sm_count(idx->device);
-    const size_t per_cta = (size_t)(pl.threads / 32) * 32 * T;
-    const size_t ctas_needed = div_ceil(nq, per_cta);
-    int ctas_per_sm = 1;
-    if (used <= 100 * 1024 && pl.threads <= 512) ctas_per_sm = 2;
-    pl.grid = (int)std::min<size_t>(ctas_needed, (size_t)sms * ctas_per_sm * (size_t)env_int("SST_WAVES", 1));
-    if (pl.grid < 1) pl.grid = 1;
-    return pl;
+    const size_t per_cta = (size_t)(threads / 32) * 32 * T;
+    int grid = (int)std::min<size_t>(div_ceil(nq, per_cta), (size_t)sms * (size_t)env_int("SST_WAVES", 1));
+    if (grid < 1) grid = 1;
+    auto kern = stree_search_fast<G, T, TOP>;
+    if (smem_bytes > 48 * 1024 &&
+        !SST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)))
+        return SST_ERR_CUDA;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    int nattr = 0;
+    // Optional: pin the last internal level (the one that just fits L2) with a persisting
+    // access-policy window for this launch only; the leaf level streams through.
+    const int persist = env_int("SST_PERSIST", 0);
+    if (persist && idx->levels >= 2 && idx->persist_ok) {
+        const int h = idx->levels - 2;
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = (void*)(idx->d_tree + idx->offsets[h] * 16);
+        attr[0].val.accessPolicyWindow.num_bytes = std::min<size_t>(idx->layer_sizes[h] * 64, idx->persist_window_max);
+        attr[0].val.accessPolicyWindow.hitRatio = persist >= 100 ? 1.0f : persist / 100.0f;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        nattr = 1;
+        if (persist >= 200) {  // experiment: set it on the stream instead of the launch
+            cudaStreamAttrValue sv{};
+            sv.accessPolicyWindow = attr[0].val.accessPolicyWindow;
+            sv.accessPolicyWindow.hitRatio = 1.0f;
+            if (!SST_CUDA_OK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &sv))) return SST_ERR_CUDA;
+            nattr = 0;
+        }
+        if (getenv("SST_DEBUG"))
+            fprintf(stderr, "[sst] access window base=%p bytes=%zu hit=%.2f mode=%s\n", attr[0].val.accessPolicyWindow.base_ptr,
+                    (size_t)attr[0].val.accessPolicyWindow.num_bytes, attr[0].val.accessPolicyWindow.hitRatio, nattr ? "launch" : "stream");
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = nattr;
+    return SST_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, fp, d_qs, nq, d_vals, d_idx)) ? SST_OK : SST_ERR_CUDA;
 }
 
 template <int G, int T>
-int launch_fast(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx,
-                cudaStream_t st) {
-    Plan pl = make_plan(idx, nq, T);
-    auto kern = stree_search_fast<G, T>;
-    if (pl.smem_bytes > 48 * 1024 &&
-        !SST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes)))
-        return SST_ERR_CUDA;
-    kern<<<pl.grid, pl.threads, pl.smem_bytes, st>>>(pl.fp, d_qs, nq, d_vals, d_idx);
-    return SST_CUDA_OK(cudaGetLastError()) ? SST_OK : SST_ERR_CUDA;
+int launch_fast_top(const sst_index* idx, bool top, const uint32_t* d_qs, size_t nq, uint32_t* d_vals,
+                    unsigned long long* d_idx, cudaStream_t st) {
+    if (top) return launch_fast<G, T, true>(idx, d_qs, nq, d_vals, d_idx, st);
+    return launch_fast<G, T, false>(idx, d_qs, nq, d_vals, d_idx, st);
 }
 
 }  // namespace
@@ -464,21 +495,33 @@ int query_launch_count(const sst_index*, int) { return 1; }
 int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx,
                  int scheme, cudaStream_t st) {
     if (nq == 0) return SST_OK;
-    if (scheme == SST_SCHEME_AUTO) scheme = fast_eligible(idx) ? env_int("SST_SCHEME", SST_SCHEME_GROUP4) : SST_SCHEME_GENERIC;
+    if (scheme == SST_SCHEME_AUTO) {
+        if (!fast_eligible(idx)) scheme = SST_SCHEME_GENERIC;
+        else scheme = env_int("SST_SCHEME", (top_eligible(idx) && nq >= (size_t)env_int("SST_TABLE_MIN_NQ", 1 << 18)) ? SST_SCHEME_TABLE : SST_SCHEME_GROUP2);
+    }
     if (scheme != SST_SCHEME_GENERIC && !fast_eligible(idx)) {
-        set_error(SST_ERR_UNSUPPORTED, "the group kernels serve the plain B=16 tree; use SST_SCHEME_AUTO or SST_SCHEME_GENERIC");
+        set_error(SST_ERR_UNSUPPORTED, "the group/table kernels serve the plain B=16 tree; use SST_SCHEME_AUTO or SST_SCHEME_GENERIC");
         return SST_ERR_UNSUPPORTED;
     }
     const int T = env_int("SST_T", 2);
     switch (scheme) {
+        case SST_SCHEME_TABLE: {
+            const bool top = top_eligible(idx);  // trees of height 1 have nothing above the leaf
+            if (env_int("SST_TABLE_G", 2) == 4) {
+                if (T == 1) return launch_fast_top<4, 1>(idx, top, d_qs, nq, d_vals, d_idx, st);
+                return launch_fast_top<4, 2>(idx, top, d_qs, nq, d_vals, d_idx, st);
+            }
+            if (T == 1) return launch_fast_top<2, 1>(idx, top, d_qs, nq, d_vals, d_idx, st);
+            return launch_fast_top<2, 2>(idx, top, d_qs, nq, d_vals, d_idx, st);
+        }
         case SST_SCHEME_GROUP4:
-            if (T == 1) return launch_fast<4, 1>(idx, d_qs, nq, d_vals, d_idx, st);
-            return launch_fast<4, 2>(idx, d_qs, nq, d_vals, d_idx, st);
+            if (T == 1) return launch_fast<4, 1, false>(idx, d_qs, nq, d_vals, d_idx, st);
+            return launch_fast<4, 2, false>(idx, d_qs, nq, d_vals, d_idx, st);
         case SST_SCHEME_GROUP16:
-            return launch_fast<16, 1>(idx, d_qs, nq, d_vals, d_idx, st);
+            return launch_fast<16, 1, false>(idx, d_qs, nq, d_vals, d_idx, st);
         case SST_SCHEME_GROUP2:
-            if (T == 1) return launch_fast<2, 1>(idx, d_qs, nq, d_vals, d_idx, st);
-            return launch_fast<2, 2>(idx, d_qs, nq, d_vals, d_idx, st);
+            if (T == 1) return launch_fast<2, 1, false>(idx, d_qs, nq, d_vals, d_idx, st);
+            return launch_fast<2, 2, false>(idx, d_qs, nq, d_vals, d_idx, st);
         case SST_SCHEME_GENERIC: {
             const int sms = sm_count(idx->device);
             const int grid = (int)std::min<size_t>(div_ceil(nq, 256), (size_t)sms * 32);
@@ -508,7 +551,7 @@ int sst_query_device(const sst_index_t* idx, const uint32_t* d_qs, size_t nq, ui
     if (!idx || (nq && (!d_qs || !d_out_vals))) { set_error(SST_ERR_ARG, "null argument"); return SST_ERR_ARG; }
     DeviceGuard g(idx->device);
     if (!g.ok) return SST_ERR_CUDA;
-    cudaStream_t st = stream ? (cudaStream_t)stream : thread_stream(idx->device);
+    cudaStream_t st = (cudaStream_t)stream;  // NULL == the CUDA legacy default stream
     return launch_query(idx, d_qs, nq, d_out_vals, (unsigned long long*)d_out_idx, scheme, st);
 }
 
@@ -573,6 +616,7 @@ double sst_time_query_device(const sst_index_t* idx, const uint32_t* d_qs, size_
     DeviceGuard g(idx->device);
     if (!g.ok) return -1.0;
     cudaStream_t st = thread_stream(idx->device);
+    if (!SST_CUDA_OK(cudaDeviceSynchronize())) return -1.0;  // inputs may come from another stream
     cudaEvent_t a, b;
     if (!SST_CUDA_OK(cudaEventCreate(&a)) || !SST_CUDA_OK(cudaEventCreate(&b))) return -1.0;
     for (int i = 0; i < warmup; i++)
@@ -594,9 +638,10 @@ double sst_probe_gather64(int device, size_t bytes, size_t n_gathers, int lanes_
     if (bytes < 64 || iters < 1) { set_error(SST_ERR_ARG, "bad argument"); return -1.0; }
     DeviceGuard g(device);
     if (!g.ok) return -1.0;
+    configure_l2_fetch(device);
     cudaStream_t st = thread_stream(device);
     uint32_t *buf = nullptr, *sink = nullptr;
-    const unsigned long long nodes = bytes / 64;
+    const unsigned long long nodes = bytes / 64;  // < 2^32 nodes (256 GiB)
     if (!SST_CUDA_OK(cudaMalloc(&buf, nodes * 64)) || !SST_CUDA_OK(cudaMalloc(&sink, 64))) { cudaFree(buf); return -1.0; }
     cudaMemsetAsync(buf, 0x55, nodes * 64, st);
     const int grid = sm_count(device), threads = 1024;

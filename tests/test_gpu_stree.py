@@ -13,7 +13,7 @@ FLAG_SETS = [(0, 0, 0), (1, 0, 0), (1, 0, 1), (0, 1, 0), (1, 1, 0), (0, 0, 1)]
 
 
 def schemes(sst):
-    return [sst.SCHEME_AUTO, sst.SCHEME_GROUP4, sst.SCHEME_GROUP16, sst.SCHEME_GROUP2, sst.SCHEME_GENERIC]
+    return [sst.SCHEME_AUTO, sst.SCHEME_GROUP4, sst.SCHEME_GROUP16, sst.SCHEME_GROUP2, sst.SCHEME_GENERIC, sst.SCHEME_TABLE]
 
 
 def test_kats(gpu, oracle):
@@ -134,6 +134,24 @@ def test_edge_batches_and_out_of_range(gpu, oracle):
         assert np.array_equal(t.query(big, s), ot.search(big))
 
 
+def test_table_kernel_skewed_keys(gpu, oracle):
+    """Rank table with crowded buckets (keys packed into few 2^16 ranges) and with every flag set."""
+    sst = gpu
+    rng = np.random.default_rng(17)
+    vals = np.sort(np.concatenate([rng.integers(5 << 16, (5 << 16) + 3000, 400_000), rng.integers(0, MAX, 5000),
+                                   rng.integers(0x7FFF0000, MAX, 100_000), [MAX]]).astype(np.uint32))
+    qs = np.concatenate([rng.integers(5 << 16, (5 << 16) + 3100, 20000), rng.integers(0x7FFE0000, MAX, 20000),
+                         gen_queries(20001, seed=5, vals=vals)]).astype(np.uint32)
+    ev, ei = oracle.lower_bound(vals, qs)
+    for lm, rev, full in FLAG_SETS:
+        t = sst.STree16.new_params(vals, bool(lm), bool(rev), bool(full))
+        for g in ("2", "4"):
+            os.environ["SST_TABLE_G"] = g
+            v, i = t.query(qs, sst.SCHEME_TABLE, want_index=True)
+            assert np.array_equal(v, ev) and np.array_equal(i, ei), (lm, rev, full, g)
+    os.environ.pop("SST_TABLE_G", None)
+
+
 def test_duplicates_and_tiny(gpu, oracle):
     sst = gpu
     for vals in ([MAX], [0, MAX], [5] * 40 + [MAX], list(range(16)), list(range(17)), [7] * 16 + [9] * 16 + [MAX] * 3,
@@ -239,7 +257,7 @@ def test_full_size_properties(gpu):
     t = sst.STree16.new_params(keys, True, False, False)
     assert t.layers() == 7
     ref_v = None
-    for s in (sst.SCHEME_GROUP4, sst.SCHEME_GROUP16, sst.SCHEME_GROUP2, sst.SCHEME_GENERIC):
+    for s in (sst.SCHEME_TABLE, sst.SCHEME_GROUP4, sst.SCHEME_GROUP16, sst.SCHEME_GROUP2, sst.SCHEME_GENERIC):
         v, i = t.query(qs, s, want_index=True)
         torch.cuda.synchronize()
         assert bool((v >= qs).all())

@@ -34,8 +34,9 @@ def main():
     nq = int(os.environ.get("SWEEP_NQ", "100000000"))
     dev = torch.device("cuda", 0)
     if what in ("all", "probe"):
-        for bytes_ in (64 << 20, 1 << 30, 8 << 30):
-            for lanes in (16, 8, 4, 2):
+        sizes = [m << 20 for m in (16, 32, 48, 56, 64, 72, 80, 96, 112, 128, 160, 192, 256, 384, 512, 768, 1024, 2048, 4096, 8192, 16384)]
+        for bytes_ in sizes:
+            for lanes in (2,):
                 gbs = L.sst_probe_gather64(0, bytes_, 200_000_000, lanes, 3)
                 emit(kind="probe", bytes=bytes_, lanes=lanes, gbs=gbs, gnodes_per_s=gbs / 64)
     if what in ("all", "tree"):
@@ -44,23 +45,44 @@ def main():
         keys = torch.randint(0, MAX, (n,), dtype=torch.int32, device=dev, generator=g)
         keys[0] = MAX
         keys = torch.sort(keys).values.contiguous()
+        os.environ['SST_PERSIST'] = '100'  # configure the persisting-L2 carve-out at build time
         tree = sst.STree16.new_params(keys, True, False, False)
         qs = torch.randint(0, MAX, (nq,), dtype=torch.int32, device=dev, generator=g)
         out = torch.empty_like(qs)
         configs = []
-        for scheme, T in ((1, 1), (1, 2), (2, 1), (3, 1), (3, 2), (4, 1)):
-            for smem in (0, 16, 224):
-                for hints in (3, 0):
-                    for threads in (1024, 512):
-                        if scheme == 4 and (smem or hints != 3 or threads != 1024):
-                            continue
-                        configs.append((scheme, T, smem, hints, threads))
-        for scheme, T, smem, hints, threads in configs:
-            os.environ.update(SST_T=str(T), SST_SMEM_KB=str(smem), SST_HINTS=str(hints), SST_THREADS=str(threads))
+        for scheme, G, T in ((3, 2, 2), (5, 2, 1), (5, 2, 2), (5, 4, 1), (5, 4, 2)):
+            for hints in (3, 0, 1, 2):
+                for persist in (0, 100, 60):
+                    configs.append((scheme, G, T, hints, persist))
+        for scheme, G, T, hints, persist in configs:
+            os.environ.update(SST_T=str(T), SST_TABLE_G=str(G), SST_HINTS=str(hints), SST_PERSIST=str(persist))
             ms = L.sst_time_query_device(tree._h, C.c_void_p(qs.data_ptr()), nq, C.c_void_p(out.data_ptr()), None, scheme, 2, 5)
-            emit(kind="tree", logn=logn, nq=nq, scheme=scheme, T=T, smem_kb=smem, hints=hints, threads=threads, ms=ms,
+            emit(kind="tree", logn=logn, nq=nq, scheme=scheme, G=G, T=T, hints=hints, persist=persist, ms=ms,
                  gqps=nq / ms / 1e6 if ms > 0 else None, err=L.sst_last_error().decode() if ms < 0 else "")
 
 
+def ncu_mode():
+    """Launch a few configurations once each (run under `ncu -k regex:stree_search_fast`)."""
+    L = sst.lib()
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(1)
+    n, nq = 1 << 28, 100_000_000
+    keys = torch.randint(0, MAX, (n,), dtype=torch.int32, device=dev, generator=g)
+    keys[0] = MAX
+    keys = torch.sort(keys).values.contiguous()
+    os.environ["SST_PERSIST"] = "100"
+    tree = sst.STree16.new_params(keys, True, False, False)
+    qs = torch.randint(0, MAX, (nq,), dtype=torch.int32, device=dev, generator=g)
+    out = torch.empty_like(qs)
+    for scheme, hints, persist in ((5, 3, 0), (5, 3, 100), (5, 2, 100), (5, 0, 100), (5, 3, 200), (5, 2, 200)):
+        os.environ.update(SST_T="2", SST_TABLE_G="2", SST_HINTS=str(hints), SST_PERSIST=str(persist))
+        for _ in range(2):
+            ms = L.sst_time_query_device(tree._h, C.c_void_p(qs.data_ptr()), nq, C.c_void_p(out.data_ptr()), None, scheme, 0, 1)
+        emit(kind="ncu_cfg", scheme=scheme, hints=hints, persist=persist, ms=ms)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "ncu":
+        ncu_mode()
+        sys.exit(0)
     main()
