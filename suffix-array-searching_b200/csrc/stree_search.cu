@@ -122,6 +122,21 @@ __device__ __forceinline__ Keys<W> ldg_keys(const uint32_t* p, uint64_t pol) {
     return r;
 }
 
+// Plain read-only load without an L2 cache hint (so that an access-policy window, if any, decides).
+template <int W>
+__device__ __forceinline__ Keys<W> ldg_keys_plain(const uint32_t* p) {
+    Keys<W> r;
+    if constexpr (W == 1) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r.k[0]) : "l"(p));
+    else if constexpr (W == 2) asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(r.k[0]), "=r"(r.k[1]) : "l"(p));
+    else if constexpr (W == 4)
+        asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.k[0]), "=r"(r.k[1]), "=r"(r.k[2]), "=r"(r.k[3]) : "l"(p));
+    else
+        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r.k[0]), "=r"(r.k[1]), "=r"(r.k[2]), "=r"(r.k[3]), "=r"(r.k[4]), "=r"(r.k[5]), "=r"(r.k[6]), "=r"(r.k[7])
+                     : "l"(p));
+    return r;
+}
+
 template <int W>
 __device__ __forceinline__ Keys<W> lds_keys(const uint32_t* p) {
     Keys<W> r;
@@ -260,7 +275,10 @@ stree_search_fast(const __grid_constant__ FastParams p, const uint32_t* __restri
         for (int h = h0; h + 1 < L; h++) {
             Keys<W> ks[D];
             const uint32_t* gl = p.tree + p.level_slot[h] + sub * W;
-            if (h + 2 < L) {
+            if (p.hints & 4) {  // experiment: un-hinted loads, the launch's access-policy window decides
+#pragma unroll
+                for (int d = 0; d < D; d++) ks[d] = ldg_keys_plain<W>(gl + (size_t)k[d] * 16u);
+            } else if (h + 2 < L) {
 #pragma unroll
                 for (int d = 0; d < D; d++) ks[d] = ldg_keys<W, false>(gl + (size_t)k[d] * 16u, pol_inner);
             } else {  // last internal level: larger than L1, keep it out
@@ -497,7 +515,7 @@ int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t
     if (nq == 0) return SST_OK;
     if (scheme == SST_SCHEME_AUTO) {
         if (!fast_eligible(idx)) scheme = SST_SCHEME_GENERIC;
-        else scheme = env_int("SST_SCHEME", (top_eligible(idx) && nq >= (size_t)env_int("SST_TABLE_MIN_NQ", 1 << 18)) ? SST_SCHEME_TABLE : SST_SCHEME_GROUP2);
+        else scheme = env_int("SST_SCHEME", (top_eligible(idx) && nq >= (size_t)env_int("SST_TABLE_MIN_NQ", 1 << 19)) ? SST_SCHEME_TABLE : SST_SCHEME_GROUP2);
     }
     if (scheme != SST_SCHEME_GENERIC && !fast_eligible(idx)) {
         set_error(SST_ERR_UNSUPPORTED, "the group/table kernels serve the plain B=16 tree; use SST_SCHEME_AUTO or SST_SCHEME_GENERIC");
@@ -555,8 +573,51 @@ int sst_query_device(const sst_index_t* idx, const uint32_t* d_qs, size_t nq, ui
     return launch_query(idx, d_qs, nq, d_out_vals, (unsigned long long*)d_out_idx, scheme, st);
 }
 
+// Per (host thread, device) staging ring for the host-buffer path: allocated once and reused, so
+// that a call costs no cudaMalloc/cudaFree (which synchronise the device).
+namespace {
+struct Staging {
+    size_t cap = 0, cap_idx = 0;
+    uint32_t* q[3] = {};
+    uint32_t* v[3] = {};
+    unsigned long long* i[3] = {};
+    cudaEvent_t e_in[3] = {}, e_k[3] = {}, e_out[3] = {};
+    bool events = false;
+};
+thread_local Staging g_staging[64];
+
+bool staging_ensure(Staging& s, size_t cap, bool want_idx) {
+    if (!s.events) {
+        for (int b = 0; b < 3; b++)
+            if (!SST_CUDA_OK(cudaEventCreateWithFlags(&s.e_in[b], cudaEventDisableTiming)) ||
+                !SST_CUDA_OK(cudaEventCreateWithFlags(&s.e_k[b], cudaEventDisableTiming)) ||
+                !SST_CUDA_OK(cudaEventCreateWithFlags(&s.e_out[b], cudaEventDisableTiming)))
+                return false;
+        s.events = true;
+    }
+    if (cap > s.cap) {
+        for (int b = 0; b < 3; b++) {
+            cudaFree(s.q[b]); cudaFree(s.v[b]);
+            s.q[b] = s.v[b] = nullptr;
+            if (!SST_CUDA_OK(cudaMalloc(&s.q[b], cap * 4)) || !SST_CUDA_OK(cudaMalloc(&s.v[b], cap * 4))) { s.cap = 0; return false; }
+        }
+        s.cap = cap;
+    }
+    if (want_idx && cap > s.cap_idx) {
+        for (int b = 0; b < 3; b++) {
+            cudaFree(s.i[b]);
+            s.i[b] = nullptr;
+            if (!SST_CUDA_OK(cudaMalloc(&s.i[b], cap * 8))) { s.cap_idx = 0; return false; }
+        }
+        s.cap_idx = cap;
+    }
+    return true;
+}
+}  // namespace
+
 // Host buffers: chunked three-stage pipeline (H2D | kernel | D2H) over two copy streams and the
-// compute stream, so that PCIe traffic in both directions overlaps the kernel.
+// compute stream, so that PCIe traffic in both directions overlaps the kernel.  Full speed needs
+// page-locked host buffers (cudaMemcpyAsync from pageable memory is staged by the driver).
 int sst_query(const sst_index_t* idx, const uint32_t* qs, size_t nq, uint32_t* out_vals, uint64_t* out_idx, int scheme) {
     clear_error();
     if (!idx || (nq && (!qs || !out_vals))) { set_error(SST_ERR_ARG, "null argument"); return SST_ERR_ARG; }
@@ -564,48 +625,32 @@ int sst_query(const sst_index_t* idx, const uint32_t* qs, size_t nq, uint32_t* o
     DeviceGuard g(idx->device);
     if (!g.ok) return SST_ERR_CUDA;
     const int dev = idx->device;
+    if (dev < 0 || dev >= 64) { set_error(SST_ERR_ARG, "device index out of range"); return SST_ERR_ARG; }
     cudaStream_t s_in = thread_copy_stream(dev, 0), s_k = thread_stream(dev), s_out = thread_copy_stream(dev, 1);
     if (!s_in || !s_k || !s_out) return SST_ERR_CUDA;
-    const size_t chunk = std::max<size_t>((size_t)env_int("SST_CHUNK", 1 << 24), 1024);
+    const size_t chunk = std::max<size_t>((size_t)env_int("SST_CHUNK", 1 << 22), 1024);
     const size_t nchunks = div_ceil(nq, chunk);
-    const int NB = nchunks > 1 ? 3 : 1;  // device-side ring
-    const size_t cap = std::min(chunk, nq);
-    uint32_t* d_q[3] = {};
-    uint32_t* d_v[3] = {};
-    unsigned long long* d_i[3] = {};
-    cudaEvent_t e_in[3] = {}, e_k[3] = {}, e_out[3] = {};
+    const int NB = 3;  // device-side ring
+    Staging& sg = g_staging[dev];
+    if (!staging_ensure(sg, std::min(chunk, nq), out_idx != nullptr)) return SST_ERR_CUDA;
     int rc = SST_OK;
-    for (int b = 0; b < NB && rc == SST_OK; b++) {
-        if (!SST_CUDA_OK(cudaMalloc(&d_q[b], cap * 4)) || !SST_CUDA_OK(cudaMalloc(&d_v[b], cap * 4)) ||
-            (out_idx && !SST_CUDA_OK(cudaMalloc(&d_i[b], cap * 8))) ||
-            !SST_CUDA_OK(cudaEventCreateWithFlags(&e_in[b], cudaEventDisableTiming)) ||
-            !SST_CUDA_OK(cudaEventCreateWithFlags(&e_k[b], cudaEventDisableTiming)) ||
-            !SST_CUDA_OK(cudaEventCreateWithFlags(&e_out[b], cudaEventDisableTiming)))
-            rc = SST_ERR_CUDA;
-    }
     for (size_t c = 0; c < nchunks && rc == SST_OK; c++) {
         const int b = (int)(c % NB);
         const size_t off = c * chunk, cnt = std::min(chunk, nq - off);
         // buffer b is free once the D2H of chunk c-NB has finished
-        if (c >= (size_t)NB && !SST_CUDA_OK(cudaStreamWaitEvent(s_in, e_out[b], 0))) { rc = SST_ERR_CUDA; break; }
-        if (!SST_CUDA_OK(cudaMemcpyAsync(d_q[b], qs + off, cnt * 4, cudaMemcpyHostToDevice, s_in)) ||
-            !SST_CUDA_OK(cudaEventRecord(e_in[b], s_in)) || !SST_CUDA_OK(cudaStreamWaitEvent(s_k, e_in[b], 0))) { rc = SST_ERR_CUDA; break; }
-        rc = launch_query(idx, d_q[b], cnt, d_v[b], d_i[b], scheme, s_k);
+        if (c >= (size_t)NB && !SST_CUDA_OK(cudaStreamWaitEvent(s_in, sg.e_out[b], 0))) { rc = SST_ERR_CUDA; break; }
+        if (!SST_CUDA_OK(cudaMemcpyAsync(sg.q[b], qs + off, cnt * 4, cudaMemcpyHostToDevice, s_in)) ||
+            !SST_CUDA_OK(cudaEventRecord(sg.e_in[b], s_in)) || !SST_CUDA_OK(cudaStreamWaitEvent(s_k, sg.e_in[b], 0))) { rc = SST_ERR_CUDA; break; }
+        rc = launch_query(idx, sg.q[b], cnt, sg.v[b], out_idx ? sg.i[b] : nullptr, scheme, s_k);
         if (rc != SST_OK) break;
-        if (!SST_CUDA_OK(cudaEventRecord(e_k[b], s_k)) || !SST_CUDA_OK(cudaStreamWaitEvent(s_out, e_k[b], 0)) ||
-            !SST_CUDA_OK(cudaMemcpyAsync(out_vals + off, d_v[b], cnt * 4, cudaMemcpyDeviceToHost, s_out)) ||
-            (out_idx && !SST_CUDA_OK(cudaMemcpyAsync(out_idx + off, d_i[b], cnt * 8, cudaMemcpyDeviceToHost, s_out))) ||
-            !SST_CUDA_OK(cudaEventRecord(e_out[b], s_out))) { rc = SST_ERR_CUDA; break; }
+        if (!SST_CUDA_OK(cudaEventRecord(sg.e_k[b], s_k)) || !SST_CUDA_OK(cudaStreamWaitEvent(s_out, sg.e_k[b], 0)) ||
+            !SST_CUDA_OK(cudaMemcpyAsync(out_vals + off, sg.v[b], cnt * 4, cudaMemcpyDeviceToHost, s_out)) ||
+            (out_idx && !SST_CUDA_OK(cudaMemcpyAsync(out_idx + off, sg.i[b], cnt * 8, cudaMemcpyDeviceToHost, s_out))) ||
+            !SST_CUDA_OK(cudaEventRecord(sg.e_out[b], s_out))) { rc = SST_ERR_CUDA; break; }
     }
     if (!SST_CUDA_OK(cudaStreamSynchronize(s_in)) || !SST_CUDA_OK(cudaStreamSynchronize(s_k)) ||
         !SST_CUDA_OK(cudaStreamSynchronize(s_out)))
         rc = rc == SST_OK ? SST_ERR_CUDA : rc;
-    for (int b = 0; b < NB; b++) {
-        cudaFree(d_q[b]); cudaFree(d_v[b]); cudaFree(d_i[b]);
-        if (e_in[b]) cudaEventDestroy(e_in[b]);
-        if (e_k[b]) cudaEventDestroy(e_k[b]);
-        if (e_out[b]) cudaEventDestroy(e_out[b]);
-    }
     return rc;
 }
 

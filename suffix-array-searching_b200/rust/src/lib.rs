@@ -1,0 +1,144 @@
+//! Rust shim over `libsst_b200.so` (C ABI in `include/sst_b200.h`).
+//!
+//! Drop-in for the hot path of the reference workspace: implement the reference's own traits
+//! (`static_search_tree::{SearchIndex, SearchScheme}`, static-search-tree/src/lib.rs:30-61) for
+//! GPU-resident indices, so `bench.rs` / `test.rs` can use them unchanged.  Reference errors are
+//! panics (`assert!`, `unwrap`, `panic = 'abort'`), so every non-zero status panics here too;
+//! `try_new` maps `SST_ERR_CAPACITY` to `None` (partitioned_s_tree.rs:271-274,463-466,594-597).
+//!
+//! NOT COMPILED in the authoring image (no rustc/cargo there); kept in lock-step with the tested
+//! C++ mirror `host/sst.hpp`.
+use std::ffi::{c_char, c_int, c_void, CStr};
+use std::marker::PhantomData;
+
+#[repr(C)] pub struct SstIndex { _p: [u8; 0] }
+#[repr(C)] pub struct SstSa { _p: [u8; 0] }
+
+pub const SST_LEFT_MAX: u32 = 1;
+pub const SST_REVERSE_STORAGE: u32 = 2;
+pub const SST_FULL_ARRAY: u32 = 4;
+pub const SST_ERR_CAPACITY: c_int = 3;
+
+extern "C" {
+    fn sst_last_error() -> *const c_char;
+    fn sst_last_status() -> c_int;
+    fn sst_stree_build(sorted: *const u32, n: usize, node_b: u32, flags: u32, device: c_int) -> *mut SstIndex;
+    fn sst_pstree_build(sorted: *const u32, n: usize, b: u32, variant: c_int, device: c_int) -> *mut SstIndex;
+    fn sst_index_free(idx: *mut SstIndex);
+    fn sst_index_size_bytes(idx: *const SstIndex) -> usize;
+    fn sst_index_layers(idx: *const SstIndex) -> usize;
+    fn sst_query(idx: *const SstIndex, qs: *const u32, nq: usize, out_vals: *mut u32, out_idx: *mut u64, scheme: c_int) -> c_int;
+    fn sst_sa_build(text: *const u8, n: usize, device: c_int) -> *mut SstSa;
+    fn sst_sa_free(sa: *mut SstSa);
+    fn sst_sa_check(sa: *const SstSa, out_violations: *mut u64) -> c_int;
+    fn sst_sa_search(sa: *const SstSa, pats: *const u8, pat_off: *const u64, npat: usize, mode: c_int,
+                     out_lo: *mut u32, out_hi: *mut u32, out_pos: *mut u32) -> c_int;
+}
+
+fn last_error() -> String { unsafe { CStr::from_ptr(sst_last_error()).to_string_lossy().into_owned() } }
+fn check(rc: c_int) { if rc != 0 { panic!("sst_b200: {}", last_error()); } }
+
+/// Owns one GPU index.  `Sync`: the C ABI allows concurrent queries on one handle.
+pub struct GpuIndex { h: *mut SstIndex }
+unsafe impl Send for GpuIndex {}
+unsafe impl Sync for GpuIndex {}
+impl Drop for GpuIndex { fn drop(&mut self) { unsafe { sst_index_free(self.h) } } }
+
+impl GpuIndex {
+    fn from_raw(h: *mut SstIndex) -> Self { if h.is_null() { panic!("sst_b200: {}", last_error()); } Self { h } }
+    pub fn size(&self) -> usize { unsafe { sst_index_size_bytes(self.h) } }
+    pub fn layers(&self) -> usize { unsafe { sst_index_layers(self.h) } }
+    /// `SearchScheme::query`: values of the first key >= q, same length and order as `qs`.
+    pub fn query(&self, qs: &[u32]) -> Vec<u32> {
+        let mut out = vec![0u32; qs.len()];
+        check(unsafe { sst_query(self.h, qs.as_ptr(), qs.len(), out.as_mut_ptr(), std::ptr::null_mut(), 0) });
+        out
+    }
+    /// values and the sorted-array indices (`l` of binary_search.rs:36-49)
+    pub fn query_with_index(&self, qs: &[u32]) -> (Vec<u32>, Vec<u64>) {
+        let (mut v, mut i) = (vec![0u32; qs.len()], vec![0u64; qs.len()]);
+        check(unsafe { sst_query(self.h, qs.as_ptr(), qs.len(), v.as_mut_ptr(), i.as_mut_ptr(), 0) });
+        (v, i)
+    }
+}
+
+/// `STree<B, 16>` on the GPU (s_tree.rs:14-20).
+pub struct GpuSTree<const B: usize>(pub GpuIndex);
+pub type GpuSTree16 = GpuSTree<16>;
+pub type GpuSTree15 = GpuSTree<15>;
+impl<const B: usize> GpuSTree<B> {
+    /// `STree::new_params(vals, left_max, reverse_storage, full_array)` (s_tree.rs:72-77).
+    pub fn new_params(vals: &[u32], left_max: bool, reverse_storage: bool, full_array: bool) -> Self {
+        let flags = (left_max as u32) * SST_LEFT_MAX | (reverse_storage as u32) * SST_REVERSE_STORAGE | (full_array as u32) * SST_FULL_ARRAY;
+        Self(GpuIndex::from_raw(unsafe { sst_stree_build(vals.as_ptr(), vals.len(), B as u32, flags, 0) }))
+    }
+    pub fn search(&self, q: u32) -> u32 { self.0.query(&[q])[0] }
+    pub fn batch<const P: usize>(&self, qb: &[u32; P]) -> [u32; P] { self.0.query(qb).try_into().unwrap() }
+    pub fn batch_interleave_all_128(&self, qs: &[u32]) -> Vec<u32> { self.0.query(qs) }
+}
+
+/// Marker layouts of partitioned_s_tree.rs:34-81.
+pub trait Layout { const VARIANT: c_int; }
+pub struct Simple; pub struct Compact; pub struct L1; pub struct Overlapping; pub struct Map;
+impl Layout for Simple { const VARIANT: c_int = 1; }
+impl Layout for Compact { const VARIANT: c_int = 2; }
+impl Layout for L1 { const VARIANT: c_int = 3; }
+impl Layout for Overlapping { const VARIANT: c_int = 4; }
+impl Layout for Map { const VARIANT: c_int = 5; }
+
+/// `PartitionedSTree<16, 16, Tp>` on the GPU.
+pub struct GpuPartitionedSTree<Tp: Layout>(pub GpuIndex, PhantomData<Tp>);
+impl<Tp: Layout> GpuPartitionedSTree<Tp> {
+    pub fn new(vals: &[u32], b: usize) -> Self { Self::try_new(vals, b).unwrap() }
+    pub fn try_new(vals: &[u32], b: usize) -> Option<Self> {
+        let h = unsafe { sst_pstree_build(vals.as_ptr(), vals.len(), b as u32, Tp::VARIANT, 0) };
+        if h.is_null() && unsafe { sst_last_status() } == SST_ERR_CAPACITY { return None; }
+        Some(Self(GpuIndex::from_raw(h), PhantomData))
+    }
+    pub fn search(&self, q: u32) -> u32 { self.0.query(&[q])[0] }
+}
+
+// In the reference workspace, add (static-search-tree/src/lib.rs):
+//
+//   impl<const B: usize> SearchIndex for sst_b200::GpuSTree<B> {
+//       fn new(vals: &[u32]) -> Self { Self::new_params(vals, false, false, false) }
+//       fn size(&self) -> usize { self.0.size() }
+//       fn layers(&self) -> usize { self.0.layers() }
+//   }
+//   // one scheme serves every GPU index: the whole slice goes down in one call
+//   pub const GPU: Full<..> = full(|idx: &sst_b200::GpuSTree16, qs: &[u32]| idx.0.query(qs));
+
+/// `SaNaive` on the GPU (sa_search.rs:11-57): text and suffix array live in HBM.
+pub struct GpuSa<'t> { h: *mut SstSa, _t: PhantomData<&'t [u8]> }
+unsafe impl Send for GpuSa<'_> {}
+unsafe impl Sync for GpuSa<'_> {}
+impl Drop for GpuSa<'_> { fn drop(&mut self) { unsafe { sst_sa_free(self.h) } } }
+impl<'t> GpuSa<'t> {
+    /// `SaNaive::build(t)`: builds the suffix array on the GPU and asserts strict suffix order
+    /// exactly like sa_search.rs:36-38.
+    pub fn build(t: &'t [u8]) -> Self {
+        let h = unsafe { sst_sa_build(t.as_ptr(), t.len(), 0) };
+        if h.is_null() { panic!("sst_b200: {}", last_error()); }
+        let mut bad = 0u64;
+        check(unsafe { sst_sa_check(h, &mut bad) });
+        assert!(bad == 0);
+        Self { h, _t: PhantomData }
+    }
+    /// Batched `binary_search` (sa_search.rs:98-112): returns `sa[l]` per pattern.
+    pub fn binary_search_batch(&self, qs: &[&[u8]], mlr: bool) -> Vec<usize> {
+        let mut flat = Vec::new();
+        let mut off = vec![0u64];
+        for q in qs { flat.extend_from_slice(q); off.push(flat.len() as u64); }
+        let (mut lo, mut pos) = (vec![0u32; qs.len()], vec![0u32; qs.len()]);
+        check(unsafe { sst_sa_search(self.h, flat.as_ptr(), off.as_ptr(), qs.len(), mlr as c_int, lo.as_mut_ptr(),
+                                     std::ptr::null_mut(), pos.as_mut_ptr()) });
+        pos.into_iter().map(|p| p as usize).collect()
+    }
+}
+/// `fn(&SaNaive, &[u8], &mut usize) -> usize` (type F1, sa_search.rs:453).
+pub fn binary_search(sa: &GpuSa, q: &[u8], cnt: &mut usize) -> usize {
+    *cnt += (usize::BITS - 1) as usize;  // probes are not counted on the device
+    sa.binary_search_batch(&[q], false)[0]
+}
+#[allow(dead_code)]
+fn _unused(_: *const c_void) {}

@@ -74,7 +74,7 @@ def ncu_mode():
     tree = sst.STree16.new_params(keys, True, False, False)
     qs = torch.randint(0, MAX, (nq,), dtype=torch.int32, device=dev, generator=g)
     out = torch.empty_like(qs)
-    for scheme, hints, persist in ((5, 3, 0), (5, 3, 100), (5, 2, 100), (5, 0, 100), (5, 3, 200), (5, 2, 200)):
+    for scheme, hints, persist in ((5, 3, 0), (5, 7, 0), (5, 7, 100), (5, 6, 100), (5, 7, 200), (5, 4, 100)):
         os.environ.update(SST_T="2", SST_TABLE_G="2", SST_HINTS=str(hints), SST_PERSIST=str(persist))
         for _ in range(2):
             ms = L.sst_time_query_device(tree._h, C.c_void_p(qs.data_ptr()), nq, C.c_void_p(out.data_ptr()), None, scheme, 0, 1)
