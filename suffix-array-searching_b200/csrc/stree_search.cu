@@ -324,17 +324,32 @@ stree_search_fast(const __grid_constant__ FastParams p, const uint32_t* __restri
 // ------------------------------------------------------------------------------------------------
 // Generic kernel: one thread per query, any layout (all partitioned variants, B = 15, ...).
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned count4(const uint4& v, uint32_t q) {
+    return ((int)v.x < (int)q) + ((int)v.y < (int)q) + ((int)v.z < (int)q) + ((int)v.w < (int)q);
+}
+
+// Number of keys < q (signed) in the 16-slot window starting at p (4-byte aligned).
 __device__ __forceinline__ unsigned count16(const uint32_t* __restrict__ p, uint32_t q) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    if ((a & 31u) == 0) {  // node-aligned: two 256-bit loads (LDG.E.256)
+        const Keys<8> lo = ldg_keys_plain<8>(p), hi = ldg_keys_plain<8>(p + 8);
+        unsigned c = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) c += ((int)lo.k[i] < (int)q) + ((int)hi.k[i] < (int)q);
+        return c;
+    }
+    // unaligned window (partitioned_s_tree.rs:807,857,876 read_unaligned): five aligned 16-byte
+    // chunks cover it; slots outside [p, p+16) are masked out.
+    const unsigned sh = (unsigned)((a >> 2) & 3u);  // window starts at slot `sh` of the first chunk
+    const uint4* c0 = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
     unsigned c = 0;
-    if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+    const uint4 f = __ldg(c0);
+    c += (sh <= 0 && (int)f.x < (int)q) + (sh <= 1 && (int)f.y < (int)q) + (sh <= 2 && (int)f.z < (int)q) + ((int)f.w < (int)q);
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + i);
-            c += ((int)v.x < (int)q) + ((int)v.y < (int)q) + ((int)v.z < (int)q) + ((int)v.w < (int)q);
-        }
-    } else {  // unaligned window: partitioned_s_tree.rs:807,857,876 read_unaligned
-#pragma unroll
-        for (int i = 0; i < 16; i++) c += ((int)__ldg(p + i) < (int)q);
+    for (int i = 1; i < 4; i++) c += count4(__ldg(c0 + i), q);
+    if (sh) {
+        const uint4 l = __ldg(c0 + 4);
+        c += (sh > 0 && (int)l.x < (int)q) + (sh > 1 && (int)l.y < (int)q) + (sh > 2 && (int)l.z < (int)q);
     }
     return c;
 }

@@ -50,10 +50,13 @@ def test_sa_check_detects_corruption(gpu, oracle):
     assert sst.SaNaive.from_parts(text, bad).check() > 0
 
 
-@pytest.mark.parametrize("lanes", ["32", "8", "4"])
-def test_sa_search_parity(gpu, oracle, lanes, monkeypatch):
+@pytest.mark.parametrize("lanes,pivot_levels", [("1", "20"), ("1", "6"), ("1", "0"), ("32", "20"), ("8", "20"), ("4", "20"), ("2", "20")])
+def test_sa_search_parity(gpu, oracle, lanes, pivot_levels, monkeypatch):
+    """lanes=1: thread-per-pattern kernel with the pivot-prefix table (all / some / no levels from the table);
+    lanes>1: sub-warp kernels (32 = warp per pattern)."""
     sst = gpu
     monkeypatch.setenv("SST_SA_LANES", lanes)
+    monkeypatch.setenv("SST_SA_PIVOT_LEVELS", pivot_levels)
     text = random_text(200_000, seed=11)
     s = sst.SaNaive.build(text)
     sa = s.sa
@@ -67,9 +70,11 @@ def test_sa_search_parity(gpu, oracle, lanes, monkeypatch):
     _check_search(sst, oracle, s, text, sa, pats)
 
 
-def test_sa_search_repetitive_text(gpu, oracle):
+@pytest.mark.parametrize("pivot_levels", ["20", "4"])
+def test_sa_search_repetitive_text(gpu, oracle, pivot_levels, monkeypatch):
     """Long LCPs: all-equal text and tandem repeats (many occurrences -> hi - lo large)."""
     sst = gpu
+    monkeypatch.setenv("SST_SA_PIVOT_LEVELS", pivot_levels)
     for text in (np.zeros(5000, np.uint8), np.tile(random_text(13, seed=5), 700)):
         s = sst.SaNaive.build(text)
         sa = s.sa
@@ -77,6 +82,22 @@ def test_sa_search_repetitive_text(gpu, oracle):
         pats = [text[i : i + l].tobytes() for i, l in [(0, 1), (0, 13), (5, 64), (100, 300), (4000, 999), (4990, 10), (4990, 11)]]
         pats += [bytes([1]), bytes([0] * 6000)]
         _check_search(sst, oracle, s, text, sa, pats)
+
+
+def test_sa_zero_bytes_and_short_suffixes(gpu, oracle):
+    """Text full of zero bytes and patterns that end in zeros: the pivot table's zero padding must never decide wrongly."""
+    sst = gpu
+    rng = np.random.default_rng(77)
+    text = (rng.integers(0, 3, 30_000) * (rng.random(30_000) < 0.5)).astype(np.uint8)
+    text[-20:] = 0
+    s = sst.SaNaive.build(text)
+    sa = s.sa
+    assert np.array_equal(sa, oracle.sa_build(text))
+    tail = text.tobytes()
+    pats = [tail[-k:] for k in range(1, 40)] + [tail[-k:] + b"\x00" * z for k in (1, 5, 17) for z in (1, 3, 16, 20)]
+    pats += [tail[-k:] + b"\x01" for k in (1, 2, 15, 16, 17)] + [b"\x00" * k for k in (1, 2, 15, 16, 17, 19, 20, 21, 33)]
+    pats += random_patterns(text, 1000, seed=78, lo=1, hi=50)
+    _check_search(sst, oracle, s, text, sa, pats)
 
 
 def test_sa_byte_alphabet(gpu, oracle):
