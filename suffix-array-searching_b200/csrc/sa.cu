@@ -501,7 +501,9 @@ sst_sa_t* sst_sa_build(const uint8_t* text, size_t n, int device) {
     DeviceGuard g(device);
     if (!g.ok) return nullptr;
     uint8_t* d = nullptr;
-    if (!SST_CUDA_OK(cudaMalloc(&d, n)) || !SST_CUDA_OK(cudaMemcpy(d, text, n, cudaMemcpyHostToDevice))) { cudaFree(d); return nullptr; }
+    cudaStream_t st = thread_stream(device);
+    if (!SST_CUDA_OK(cudaMalloc(&d, n)) || !SST_CUDA_OK(cudaMemcpyAsync(d, text, n, cudaMemcpyHostToDevice, st)) ||
+        !SST_CUDA_OK(cudaStreamSynchronize(st))) { cudaFree(d); return nullptr; }
     sst_sa_t* s = sst_sa_build_device(d, n, device);
     cudaFree(d);
     return s;
@@ -517,9 +519,10 @@ sst_sa_t* sst_sa_from_parts(const uint8_t* text, size_t n, const uint32_t* sa, i
     auto* s = new sst_sa();
     s->device = device;
     s->n = n;
+    cudaStream_t st = thread_stream(device);  // stream-ordered with build_pivots (see upload_keys in stree_build.cu)
     bool ok = SST_CUDA_OK(cudaMalloc(&s->d_text, n + 64)) && SST_CUDA_OK(cudaMalloc(&s->d_sa, n * 4)) &&
-              SST_CUDA_OK(cudaMemset(s->d_text + n, 0, 64)) && SST_CUDA_OK(cudaMemcpy(s->d_text, text, n, cudaMemcpyHostToDevice)) &&
-              SST_CUDA_OK(cudaMemcpy(s->d_sa, sa, n * 4, cudaMemcpyHostToDevice));
+              SST_CUDA_OK(cudaMemsetAsync(s->d_text + n, 0, 64, st)) && SST_CUDA_OK(cudaMemcpyAsync(s->d_text, text, n, cudaMemcpyHostToDevice, st)) &&
+              SST_CUDA_OK(cudaMemcpyAsync(s->d_sa, sa, n * 4, cudaMemcpyHostToDevice, st)) && SST_CUDA_OK(cudaStreamSynchronize(st));
     ok = ok && build_pivots(s);
     if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); delete s; return nullptr; }
     return s;

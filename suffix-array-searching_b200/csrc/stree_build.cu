@@ -770,7 +770,13 @@ static uint32_t* upload_keys(const uint32_t* sorted, size_t n, int device) {
     if (!guard.ok) return nullptr;
     uint32_t* d = nullptr;
     if (!SST_CUDA_OK(cudaMalloc(&d, std::max<size_t>(n, 1) * 4))) return nullptr;
-    if (n && !SST_CUDA_OK(cudaMemcpy(d, sorted, n * 4, cudaMemcpyHostToDevice))) { cudaFree(d); return nullptr; }
+    // Stream-ordered with the builder's kernels (same per-thread stream).  A plain cudaMemcpy from
+    // pageable memory may return before the DMA has landed and would not order against that stream.
+    cudaStream_t st = thread_stream(device);
+    if (n && (!SST_CUDA_OK(cudaMemcpyAsync(d, sorted, n * 4, cudaMemcpyHostToDevice, st)) || !SST_CUDA_OK(cudaStreamSynchronize(st)))) {
+        cudaFree(d);
+        return nullptr;
+    }
     return d;
 }
 

@@ -201,6 +201,7 @@ struct FastParams {
     unsigned long long leaf_slots;
     unsigned long long n;
     int hints;                        // bit0: L2 evict_last on inner levels, bit1: evict_first on leaf
+    unsigned l1_levels;               // bit h set: level h is small enough to live in L1 (allocate there)
 };
 
 constexpr unsigned kTopBuckets = 1u << 15;
@@ -278,10 +279,10 @@ stree_search_fast(const __grid_constant__ FastParams p, const uint32_t* __restri
             if (p.hints & 4) {  // experiment: un-hinted loads, the launch's access-policy window decides
 #pragma unroll
                 for (int d = 0; d < D; d++) ks[d] = ldg_keys_plain<W>(gl + (size_t)k[d] * 16u);
-            } else if (h + 2 < L) {
+            } else if ((p.l1_levels >> h) & 1u) {
 #pragma unroll
                 for (int d = 0; d < D; d++) ks[d] = ldg_keys<W, false>(gl + (size_t)k[d] * 16u, pol_inner);
-            } else {  // last internal level: larger than L1, keep it out
+            } else {  // larger than L1: do not allocate there
 #pragma unroll
                 for (int d = 0; d < D; d++) ks[d] = ldg_keys<W, true>(gl + (size_t)k[d] * 16u, pol_inner);
             }
@@ -292,8 +293,13 @@ stree_search_fast(const __grid_constant__ FastParams p, const uint32_t* __restri
         {
             const uint32_t* gl = p.tree + p.level_slot[L - 1];
             Keys<W> ks[D];
+            if ((p.l1_levels >> (L - 1)) & 1u) {  // small tree: the leaf level itself is L1-resident
 #pragma unroll
-            for (int d = 0; d < D; d++) ks[d] = ldg_keys<W, true>(gl + (size_t)k[d] * 16u + sub * W, pol_leaf);
+                for (int d = 0; d < D; d++) ks[d] = ldg_keys<W, false>(gl + (size_t)k[d] * 16u + sub * W, pol_inner);
+            } else {
+#pragma unroll
+                for (int d = 0; d < D; d++) ks[d] = ldg_keys<W, true>(gl + (size_t)k[d] * 16u + sub * W, pol_leaf);
+            }
             uint32_t myval[T];
             unsigned long long myidx[T];
 #pragma unroll
@@ -381,7 +387,7 @@ stree_search_generic(const __grid_constant__ SstTreeView v, const uint32_t* __re
             // The read below may spill into the next node (idx == 16, s_tree.rs:322-325).  Past the
             // leaf level the reference reads allocation slack; defined as MAX.
             val = pos < v.leaf_slots ? __ldg(leaf + pos) : kMax;
-            switch (v.variant) {
+            if (out_idx) switch (v.variant) {
                 case SST_PLAIN: index = (s >> 4) * v.node_b + c; break;
                 case SST_MAP: index = pos; break;
                 case SST_COMPACT: {
@@ -461,7 +467,10 @@ int launch_fast(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t*
     fp.leaf_slots = (unsigned long long)idx->layer_sizes[idx->levels - 1] * 16;
     fp.n = idx->n;
     fp.hints = env_int("SST_HINTS", 3);
-    for (int h = 0; h < idx->levels; h++) fp.level_slot[h] = (unsigned long long)idx->offsets[h] * 16;
+    for (int h = 0; h < idx->levels; h++) {
+        fp.level_slot[h] = (unsigned long long)idx->offsets[h] * 16;
+        if (idx->layer_sizes[h] * 64 <= (size_t)env_int("SST_L1_LEVEL_KB", 256) * 1024) fp.l1_levels |= 1u << h;
+    }
     size_t smem_bytes = 0;
     if (TOP) {
         fp.top_level = idx->top_level;

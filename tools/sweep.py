@@ -81,7 +81,44 @@ def ncu_mode():
         emit(kind="ncu_cfg", scheme=scheme, hints=hints, persist=persist, ms=ms)
 
 
+def sizes_mode():
+    """Config C2: size sweep 2^10..2^30 keys, 10^8 queries, plain left-max tree (AUTO kernel) and the
+    partitioned layouts through the generic kernel."""
+    L = sst.lib()
+    dev = torch.device("cuda", 0)
+    nq = int(os.environ.get("SWEEP_NQ", "100000000"))
+    g = torch.Generator(device=dev).manual_seed(3)
+    qs = torch.randint(0, MAX, (nq,), dtype=torch.int32, device=dev, generator=g)
+    out = torch.empty_like(qs)
+    lo, hi = int(os.environ.get("SWEEP_LO", "10")), int(os.environ.get("SWEEP_HI", "30"))
+    for logn in range(lo, hi + 1, 2):
+        n = 1 << logn
+        keys = torch.randint(0, MAX, (n,), dtype=torch.int32, device=dev, generator=g)
+        keys[0] = MAX
+        keys = torch.sort(keys).values.contiguous()
+        tree = sst.STree16.new_params(keys, True, False, False)
+        for scheme, name in ((0, "auto"), (3, "group2"), (4, "generic")):
+            ms = L.sst_time_query_device(tree._h, C.c_void_p(qs.data_ptr()), nq, C.c_void_p(out.data_ptr()), None, scheme, 2, 5)
+            emit(kind="size", logn=logn, layout="stree16_left_max", layers=tree.layers(), kernel=name, ms=ms, gqps=nq / ms / 1e6 if ms > 0 else None)
+        del tree
+        if logn >= 20:
+            for cls, name in ((sst.PartitionedSTree16M, "map"), (sst.PartitionedSTree16C, "compact"), (sst.PartitionedSTree16L, "l1"),
+                              (sst.PartitionedSTree16O, "overlap"), (sst.PartitionedSTree16, "simple")):
+                t = cls.try_new(keys, 20)
+                if t is None:
+                    emit(kind="size", logn=logn, layout=name, none=True)
+                    continue
+                ms = L.sst_time_query_device(t._h, C.c_void_p(qs.data_ptr()), nq, C.c_void_p(out.data_ptr()), None, 0, 1, 3)
+                emit(kind="size", logn=logn, layout=name, layers=t.layers(), size_mb=t.size() / 2**20, params=t.params, kernel="generic",
+                     ms=ms, gqps=nq / ms / 1e6 if ms > 0 else None)
+                del t
+        del keys
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "sizes":
+        sizes_mode()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ncu":
         ncu_mode()
         sys.exit(0)
