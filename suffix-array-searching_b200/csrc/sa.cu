@@ -362,6 +362,7 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
         const W4 p0 = load16_unaligned(pat, pend), p1 = load16_unaligned(pat + 16, pend);
         unsigned long long l = 0, r = p.n;
         uint32_t lcp_l = 0, lcp_r = 0;
+        bool lcp_r_exact = false;  // lcp_r == lcp(q, suffix(r)) exactly (not a conservative bound)
         // ---- table levels: one 16-byte load per probe ----
         {
             const uint32_t c = ql < 16u ? ql : 16u;
@@ -373,16 +374,18 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
                 ew.w[0] = e.x; ew.w[1] = e.y; ew.w[2] = e.z; ew.w[3] = e.w;
                 unsigned tb, pb;
                 const unsigned mp = first_mismatch16(ew, p0, tb, pb);
-                bool less;
+                bool less, exact;
                 uint32_t lcp;
                 if (mp < c) {
                     less = tb < pb;
-                    lcp = tb == 0u ? 0u : mp;  // a zero may be end-of-text padding: keep the lcp bound conservative
+                    exact = tb != 0u;          // a zero may be end-of-text padding: keep the lcp bound conservative
+                    lcp = exact ? mp : 0u;
                 } else {  // tie on the stored prefix: decide on the text
                     const uint32_t start = MLR ? ((lcp_l < lcp_r ? lcp_l : lcp_r) & ~15u) : 0u;
                     lcp = thread_compare(p, __ldg(p.sa + m), p0, p1, pat, ql, start, less);
+                    exact = true;
                 }
-                if (less) { l = m + 1; lcp_l = lcp; j = 2 * j + 1; } else { r = m; lcp_r = lcp; j = 2 * j; }
+                if (less) { l = m + 1; lcp_l = lcp; j = 2 * j + 1; } else { r = m; lcp_r = lcp; lcp_r_exact = exact; j = 2 * j; }
             }
         }
         // ---- remaining levels: sa[m] then text ----
@@ -391,7 +394,7 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
             const uint32_t start = MLR ? ((lcp_l < lcp_r ? lcp_l : lcp_r) & ~15u) : 0u;
             bool less;
             const uint32_t lcp = thread_compare(p, __ldg(p.sa + m), p0, p1, pat, ql, start, less);
-            if (less) { l = m + 1; lcp_l = lcp; } else { r = m; lcp_r = lcp; }
+            if (less) { l = m + 1; lcp_l = lcp; } else { r = m; lcp_r = lcp; lcp_r_exact = true; }
         }
         const unsigned long long lo = l;
         p.out_lo[i] = (uint32_t)lo;
@@ -399,7 +402,12 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
         if (p.out_hi) {
             // Suffixes starting with q are contiguous from lo: gallop to bracket the end, then bisect.
             unsigned long long a = lo, b = p.n, step = 1;
-            while (true) {
+            // The lower-bound search ended with r == lo; if r moved at all, lcp_r is lcp(q, suffix(lo))
+            // and the first probe of the gallop is already answered.
+            if (lo < p.n && r == lo && lcp_r_exact) {
+                if (lcp_r >= ql) { a = lo + 1; step = 2; } else { b = lo; step = 0; }
+            }
+            while (step) {
                 const unsigned long long pr = a + step - 1;
                 if (pr >= p.n) break;
                 bool less;
@@ -441,11 +449,14 @@ __global__ void sa_pivot_kernel(const uint8_t* __restrict__ t, const uint32_t* _
 
 bool build_pivots(sst_sa* s) {
     const char* e = getenv("SST_SA_PIVOT_LEVELS");
-    int levels = e && *e ? atoi(e) : 22;  // 64 MB: still L2-resident on B200 (measured 3.74 vs 3.43 Gpat/s at 20)
     int need = 1;
     while ((1ull << need) < s->n + 1) need++;
+    // Default: 22 levels (64 MB, L2-resident on B200: measured 3.74 vs 3.43 Gpat/s at 20 for a 10^8 text);
+    // longer texts get need-6 levels: a table probe below L2 still costs one 128-B DRAM fill where
+    // the plain probe (sa[m], then the text) costs two.  2^26 entries = 1 GiB at most.
+    int levels = e && *e ? atoi(e) : std::min(26, std::max(22, need - 6));
     if (levels > need) levels = need;
-    if (levels > 24) levels = 24;
+    if (levels > 26) levels = 26;
     if (levels < 1) { s->pivot_levels = 0; return true; }
     cudaStream_t st = thread_stream(s->device);
     if (!SST_CUDA_OK(cudaMalloc(&s->d_pivots, (sizeof(uint4)) << levels))) return false;
