@@ -411,6 +411,115 @@ stree_search_generic(const __grid_constant__ SstTreeView v, const uint32_t* __re
 
 
 // ------------------------------------------------------------------------------------------------
+// Lane-group kernel for the partitioned layouts (Simple, Compact, L1, Overlapping, Map; B = 16):
+// the descent of partitioned_s_tree.rs:654-880 with 2 lanes x 32 B per node like the fast kernel.
+// Positions are kept in slots (4 B) so that the unaligned root windows of Overlapping / Map
+// (read_unaligned, :807,857,876) fit the same loop: s' = s * mult[h] + 16 * count.
+// ------------------------------------------------------------------------------------------------
+// 8 consecutive keys starting at p (4-byte aligned): one LDG.256 when 32-byte aligned, otherwise three
+// aligned 16-byte chunks and a word-select network.
+__device__ __forceinline__ Keys<8> ldg_window8(const uint32_t* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    if ((a & 31u) == 0) return ldg_keys_plain<8>(p);
+    const uint4* c = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+    const uint4 A = __ldg(c), B = __ldg(c + 1);
+    const unsigned w = (unsigned)((a >> 2) & 3u);
+    uint4 Cc = make_uint4(0, 0, 0, 0);
+    if (w) Cc = __ldg(c + 2);
+    const bool s2 = (w & 2u) != 0, s1 = (w & 1u) != 0;
+    const uint32_t W0 = A.x, W1 = A.y, W2 = A.z, W3 = A.w, W4 = B.x, W5 = B.y, W6 = B.z, W7 = B.w, W8 = Cc.x, W9 = Cc.y, W10 = Cc.z;
+    const uint32_t u0 = s2 ? W2 : W0, u1 = s2 ? W3 : W1, u2 = s2 ? W4 : W2, u3 = s2 ? W5 : W3, u4 = s2 ? W6 : W4, u5 = s2 ? W7 : W5,
+                   u6 = s2 ? W8 : W6, u7 = s2 ? W9 : W7, u8 = s2 ? W10 : W8;
+    Keys<8> r;
+    r.k[0] = s1 ? u1 : u0; r.k[1] = s1 ? u2 : u1; r.k[2] = s1 ? u3 : u2; r.k[3] = s1 ? u4 : u3;
+    r.k[4] = s1 ? u5 : u4; r.k[5] = s1 ? u6 : u5; r.k[6] = s1 ? u7 : u6; r.k[7] = s1 ? u8 : u7;
+    return r;
+}
+
+template <int T>
+__global__ void __launch_bounds__(512, 2)
+pstree_search_group(const __grid_constant__ SstTreeView v, const uint32_t* __restrict__ qs, size_t nq,
+                    uint32_t* __restrict__ out_vals, unsigned long long* __restrict__ out_idx) {
+    constexpr int G = 2, W = 8, D = G * T;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const unsigned sub = lane & 1u, gbase = lane & ~1u;
+    const int L = v.levels;
+    for (size_t base = ((size_t)blockIdx.x * warps + warp) * (32 * T); base < nq; base += (size_t)gridDim.x * warps * (32 * T)) {
+        uint32_t qown[T];
+        unsigned long long sown[T];  // first slot; ~0 marks "prefix beyond the last part"
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            const size_t i = base + (size_t)t * 32 + lane;
+            const uint32_t q = i < nq ? __ldcs(qs + i) : 0u;
+            qown[t] = q;
+            const unsigned long long part = (unsigned long long)(q >> v.shift);
+            unsigned long long s0;
+            if (part >= v.parts) s0 = ~0ull;
+            else if (v.variant == SST_MAP) s0 = __ldg(v.prefix_map + part);
+            else if (v.variant == SST_COMPACT) s0 = 0;
+            else s0 = part * v.start_mul;
+            sown[t] = s0;
+        }
+        uint32_t q[D];
+        unsigned long long s[D], pb[D];
+        bool live[D];
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            q[d] = __shfl_sync(kFull, qown[d / G], gbase + (d % G));
+            const unsigned long long s0 = __shfl_sync(kFull, sown[d / G], gbase + (d % G));
+            live[d] = s0 != ~0ull;
+            s[d] = live[d] ? s0 : 0ull;
+            pb[d] = (v.variant == SST_COMPACT && live[d]) ? (unsigned long long)(q[d] >> v.shift) * v.part_stride : 0ull;
+        }
+        for (int h = 0; h + 1 < L; h++) {
+            Keys<W> ks[D];
+            const uint32_t* gl = v.tree + v.level_slot[h] + sub * W;
+#pragma unroll
+            for (int d = 0; d < D; d++) ks[d] = ldg_window8(gl + pb[d] + s[d]);
+#pragma unroll
+            for (int d = 0; d < D; d++) s[d] = s[d] * v.mult[h] + 16ull * group_count<G>(ks[d], q[d], gbase);
+        }
+        const uint32_t* gl = v.tree + v.level_slot[L - 1];
+        Keys<W> ks[D];
+#pragma unroll
+        for (int d = 0; d < D; d++) ks[d] = ldg_window8(gl + pb[d] + s[d] + sub * W);
+        uint32_t myval[T];
+        unsigned long long mypos[T];
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            const unsigned c = group_count<G>(ks[d], q[d], gbase);
+            const uint32_t cand = pick<W>(ks[d], c % W);
+            uint32_t val = __shfl_sync(kFull, cand, gbase + (c < 16u ? c / W : 0u));
+            const unsigned long long pos = s[d] + c;  // flat slot in the leaf level (of this part for Compact)
+            if (c == 16u) val = pos < v.leaf_slots ? __ldg(gl + pb[d] + pos) : kMax;
+            if (!live[d]) val = kMax;
+            if (sub == (unsigned)(d % G)) { myval[d / G] = val; mypos[d / G] = pos; }
+        }
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            const size_t i = base + (size_t)t * 32 + lane;
+            if (i >= nq) continue;
+            __stcs(out_vals + i, myval[t]);
+            if (out_idx) {  // sorted-array index of record through the per-part tables
+                unsigned long long index = v.n;
+                const unsigned long long part = (unsigned long long)(qown[t] >> v.shift), pos = mypos[t];
+                if (part < v.parts) {
+                    if (v.variant == SST_MAP) index = pos;
+                    else {
+                        const unsigned long long st = v.part_start[part], cnt = v.part_start[part + 1] - st;
+                        const unsigned long long pp = v.variant == SST_COMPACT ? 0ull : v.part_pos[part];
+                        const unsigned long long off = pos > pp ? pos - pp : 0ull;
+                        index = st + (off < cnt ? off : cnt);
+                    }
+                    if (index > v.n) index = v.n;
+                }
+                __stcs(out_idx + i, index);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Random 64-byte gather probe: the access pattern of ONE tree level without the dependent chain.
 // Gives the practical ceiling of "one random node per query" on this GPU for each lane mapping.
 // ------------------------------------------------------------------------------------------------
@@ -537,6 +646,14 @@ int query_launch_count(const sst_index*, int) { return 1; }
 int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx,
                  int scheme, cudaStream_t st) {
     if (nq == 0) return SST_OK;
+    if (scheme == SST_SCHEME_AUTO && idx->variant != SST_PLAIN && idx->node_b == 16 && env_int("SST_PGROUP", 1)) {
+        const int sms = sm_count(idx->device);
+        const int T = env_int("SST_PT", 1);  // measured: T=1 27.7 vs T=2 23.9 Gq/s (Simple, 2^28 keys)
+        const int grid = (int)std::min<size_t>(div_ceil(nq, (size_t)16 * 32 * T), (size_t)sms * 2);
+        if (T == 1) pstree_search_group<1><<<grid, 512, 0, st>>>(idx->view, d_qs, nq, d_vals, d_idx);
+        else pstree_search_group<2><<<grid, 512, 0, st>>>(idx->view, d_qs, nq, d_vals, d_idx);
+        return SST_CUDA_OK(cudaGetLastError()) ? SST_OK : SST_ERR_CUDA;
+    }
     if (scheme == SST_SCHEME_AUTO) {
         if (!fast_eligible(idx)) scheme = SST_SCHEME_GENERIC;
         else scheme = env_int("SST_SCHEME", (top_eligible(idx) && nq >= (size_t)env_int("SST_TABLE_MIN_NQ", 1 << 19)) ? SST_SCHEME_TABLE : SST_SCHEME_GROUP2);

@@ -87,10 +87,12 @@ def test_partitioned_matrix(gpu, oracle, n, var):
         assert np.array_equal(t.image(), ot.image()), ("image", var, n, b)
         if var == "map":
             assert np.array_equal(t.prefix_map, ot.prefix_map)
-        v, i = t.query(qs, want_index=True)
-        assert np.array_equal(v, ot.search(qs)), (var, n, b)
-        assert np.array_equal(v, ev), (var, n, b)
-        assert np.array_equal(i, ei), (var, n, b)
+        for scheme in (sst.SCHEME_AUTO, sst.SCHEME_GENERIC):  # lane-group kernel / thread-per-query kernel
+            v, i = t.query(qs, scheme, want_index=True)
+            assert np.array_equal(v, ot.search(qs)), (var, n, b, scheme)
+            assert np.array_equal(v, ev), (var, n, b, scheme)
+            assert np.array_equal(i, ei), (var, n, b, scheme)
+        assert np.array_equal(t.query(qs), ev)
 
 
 def test_skewed_keys_partitioned(gpu, oracle):
@@ -112,8 +114,9 @@ def test_skewed_keys_partitioned(gpu, oracle):
                 continue
             assert t.params == ot.params
             assert np.array_equal(t.image(), ot.image()), (var, b)
-            v, i = t.query(qs, want_index=True)
-            assert np.array_equal(v, ev) and np.array_equal(i, ei), (var, b)
+            for scheme in (sst.SCHEME_AUTO, sst.SCHEME_GENERIC):
+                v, i = t.query(qs, scheme, want_index=True)
+                assert np.array_equal(v, ev) and np.array_equal(i, ei), (var, b, scheme)
 
 
 def test_edge_batches_and_out_of_range(gpu, oracle):
