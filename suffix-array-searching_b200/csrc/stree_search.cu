@@ -12,9 +12,10 @@
 //     G=2 lanes x 32 B (LDG.256, new on sm_100) or G=16 lanes x 4 B (the ballot/popc mapping).
 //   * Each lane group keeps G*T independent descents in flight (ILP); with 32 resident warps per
 //     SM that is >= 1000 outstanding 64-B requests per SM, enough for HBM latency.
-//   * The top levels of the tree are staged into shared memory once per CTA by 1-D TMA bulk
-//     copies (cp.async.bulk + mbarrier); a level that does not fit completely is staged as a
-//     prefix and the remainder is read from L1/L2.
+//   * The top levels of the plain tree are replaced by a rank table (bucket table over the top 15
+//     key bits + low 16 bits of every separator of the first global level), staged into shared
+//     memory once per CTA by 1-D TMA bulk copies (cp.async.bulk + mbarrier).  Copying the top
+//     NODES into shared memory instead was measured slower (profiles/r1_tree_sweep1.log).
 //   * Lower internal levels are loaded with an L2 evict_last policy, the leaf level (the only
 //     HBM-resident one at 2^28 keys) with evict_first and no L1 allocation, so that leaf
 //     traffic does not push the last internal level out of the 126 MB L2.
@@ -134,19 +135,6 @@ __device__ __forceinline__ Keys<W> ldg_keys_plain(const uint32_t* p) {
         asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=r"(r.k[0]), "=r"(r.k[1]), "=r"(r.k[2]), "=r"(r.k[3]), "=r"(r.k[4]), "=r"(r.k[5]), "=r"(r.k[6]), "=r"(r.k[7])
                      : "l"(p));
-    return r;
-}
-
-template <int W>
-__device__ __forceinline__ Keys<W> lds_keys(const uint32_t* p) {
-    Keys<W> r;
-    if constexpr (W == 1) r.k[0] = *p;
-    else if constexpr (W == 2) { uint2 v = *reinterpret_cast<const uint2*>(p); r.k[0] = v.x; r.k[1] = v.y; }
-    else if constexpr (W == 4) { uint4 v = *reinterpret_cast<const uint4*>(p); r.k[0] = v.x; r.k[1] = v.y; r.k[2] = v.z; r.k[3] = v.w; }
-    else {
-        uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 4);
-        r.k[0] = a.x; r.k[1] = a.y; r.k[2] = a.z; r.k[3] = a.w; r.k[4] = b.x; r.k[5] = b.y; r.k[6] = b.z; r.k[7] = b.w;
-    }
     return r;
 }
 
