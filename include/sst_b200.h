@@ -62,7 +62,8 @@ enum {
     SST_SCHEME_GROUP16 = 2,  /* 16 lanes x 4 B per node + ballot/popc (north-star baseline) */
     SST_SCHEME_GROUP2 = 3,   /* 2 lanes x 32 B per node (LDG.256) */
     SST_SCHEME_GENERIC = 4,  /* one thread per query, any layout */
-    SST_SCHEME_TABLE = 5     /* top levels answered by a shared-memory rank table (TMA-staged), rest as GROUP2 */
+    SST_SCHEME_TABLE = 5,    /* top levels answered by a shared-memory rank table (TMA-staged), rest as GROUP2 */
+    SST_SCHEME_BINSEARCH = 6 /* baseline: SortedVec::binary_search (sst/binary_search.rs:36-49) over the leaf level */
 };
 
 /* SA search modes */

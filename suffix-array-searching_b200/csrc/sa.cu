@@ -279,13 +279,30 @@ sa_search_kernel(const __grid_constant__ SaParams p) {
 // Thread-per-pattern search with a pivot-prefix table (default).
 //
 // The binary search of sa_search.rs:98-112 visits a fixed implicit tree of midpoints.  For its top
-// `pivot_levels` levels the first 16 bytes of every pivot suffix are stored in heap order, so a
-// probe there is ONE 16-byte load (L2-resident, 64 MB for 22 levels) instead of the two dependent
-// misses sa[m] -> text[sa[m]..]; only a tie on those bytes falls back to the text.  Below the
-// table every probe loads sa[m] and compares 16-byte windows (two aligned LDG.128 + funnel
-// shifts).  One thread per pattern maximises the number of independent miss chains per SM, which
+// `pivot_levels` levels the first 16 bytes of every pivot suffix are stored in 128-byte blocks of
+// three levels each (pivot_entry), so a probe there is ONE 16-byte load, three probes share one
+// L2/DRAM fill, and the two dependent misses sa[m] -> text[sa[m]..] are only paid on a 16-byte tie.
+// By default the table covers the whole search when it fits the memory budget (16 B per suffix,
+// 2.4 GB for a 10^8 text).  Below the table every probe loads sa[m] and compares 16-byte windows
+// (two aligned LDG.128 + funnel shifts).  One thread per pattern maximises the number of independent miss chains per SM, which
 // is what bounds this path (measured: 8 lanes/pattern 0.57, 4: 0.82, 2: 1.04 Gpat/s).
 // ------------------------------------------------------------------------------------------------
+// Blocked pivot table: three consecutive levels of the implicit search tree (1 + 2 + 4 pivots, 16 B each)
+// share one 128-byte block, so one L2/DRAM fill serves three probes.  Node j (heap index, root = 1) at
+// depth d lives in triple t = d / 3; its block is rooted at j >> (d % 3); blocks of triple t start at
+// entry 8 * (8^t - 1) / 7.  Entry 0 of every block is unused.
+__host__ __device__ __forceinline__ unsigned long long pivot_entry(unsigned long long j, int d) {
+    const int t = d / 3, e = d - 3 * t;
+    const unsigned long long root = j >> e;                          // heap index of the block's root
+    const unsigned long long block = root - (1ull << (3 * t));       // ordinal within the triple
+    const unsigned long long base = ((1ull << (3 * t)) - 1ull) / 7ull;  // blocks in earlier triples
+    const unsigned long long within = (1ull << e) | (j & ((1ull << e) - 1ull));
+    return (base + block) * 8ull + within;
+}
+__host__ __device__ __forceinline__ unsigned long long pivot_table_entries(int levels) {  // levels is a multiple of 3
+    return (((1ull << levels) - 1ull) / 7ull) * 8ull;
+}
+
 struct W4 { uint32_t w[4]; };
 
 // 16 bytes starting at byte address `addr` (little endian words); aligned 16-byte chunks starting
@@ -369,7 +386,7 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
             unsigned long long j = 1;
             for (int d = 0; d < p.pivot_levels && l < r; d++) {
                 const unsigned long long m = (l + r) >> 1;
-                const uint4 e = __ldg(p.pivots + j);
+                const uint4 e = __ldg(p.pivots + pivot_entry(j, d));
                 W4 ew;
                 ew.w[0] = e.x; ew.w[1] = e.y; ew.w[2] = e.z; ew.w[3] = e.w;
                 unsigned tb, pb;
@@ -443,7 +460,7 @@ __global__ void sa_pivot_kernel(const uint8_t* __restrict__ t, const uint32_t* _
             for (int k = 0; k < 16; k++)
                 if (pos + k < n) w[k >> 2] |= (uint32_t)t[pos + k] << (8 * (k & 3));
         }
-        table[j] = make_uint4(w[0], w[1], w[2], w[3]);
+        table[pivot_entry(j, depth)] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
@@ -451,16 +468,24 @@ bool build_pivots(sst_sa* s) {
     const char* e = getenv("SST_SA_PIVOT_LEVELS");
     int need = 1;
     while ((1ull << need) < s->n + 1) need++;
-    // Default: 22 levels (64 MB, L2-resident on B200: measured 3.74 vs 3.43 Gpat/s at 20 for a 10^8 text);
-    // longer texts get need-6 levels: a table probe below L2 still costs one 128-B DRAM fill where
-    // the plain probe (sa[m], then the text) costs two.  2^26 entries = 1 GiB at most.
-    int levels = e && *e ? atoi(e) : std::min(26, std::max(22, need - 6));
-    if (levels > need) levels = need;
-    if (levels > 26) levels = 26;
-    if (levels < 1) { s->pivot_levels = 0; return true; }
+    // Default: all but the last ~3 levels of the search (measured on a 10^8 text: 24 levels 4.16,
+    // 27 = full depth 3.74, 21 levels 3.97 Gpat/s: at the bottom every pattern ties with its own
+    // suffix and needs sa[lo] anyway), within the memory budget (16 B per heap slot * 8/7).  The
+    // levels below the table are plain probes (sa[m], then the text: two fills each).
+    int levels = e && *e ? atoi(e) : 3 * ((need - 2) / 3);  // 10^8 text: 24 of 27; 3x10^9 text: 30 of 32 (1.98 vs 1.76 Gpat/s at 27)
+    levels = 3 * (levels / 3);
+    if (levels > 3 * ((need + 2) / 3)) levels = 3 * ((need + 2) / 3);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const char* ge = getenv("SST_SA_TABLE_GB");
+    const double budget = ge && *ge ? atof(ge) * 1e9 : std::min(0.5 * (double)free_b, 64e9);
+    while (levels >= 3 && (double)pivot_table_entries(levels) * 16.0 > budget) levels -= 3;
+    if (levels < 3) { s->pivot_levels = 0; return true; }
     cudaStream_t st = thread_stream(s->device);
-    if (!SST_CUDA_OK(cudaMalloc(&s->d_pivots, (sizeof(uint4)) << levels))) return false;
-    sa_pivot_kernel<<<grid_for((size_t)1 << levels), kThreads, 0, st>>>(s->d_text, s->d_sa, s->n, levels, s->d_pivots);
+    const unsigned long long entries = pivot_table_entries(levels);
+    if (!SST_CUDA_OK(cudaMalloc(&s->d_pivots, entries * sizeof(uint4)))) return false;
+    if (!SST_CUDA_OK(cudaMemsetAsync(s->d_pivots, 0, entries * sizeof(uint4), st))) return false;
+    sa_pivot_kernel<<<grid_for((size_t)1 << std::min(levels, 30)), kThreads, 0, st>>>(s->d_text, s->d_sa, s->n, levels, s->d_pivots);
     if (!SST_CUDA_OK(cudaGetLastError()) || !SST_CUDA_OK(cudaStreamSynchronize(st))) return false;
     s->pivot_levels = levels;
     return true;

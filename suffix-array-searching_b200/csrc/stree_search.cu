@@ -399,6 +399,26 @@ stree_search_generic(const __grid_constant__ SstTreeView v, const uint32_t* __re
 
 
 // ------------------------------------------------------------------------------------------------
+// Baseline: SortedVec::binary_search (binary_search.rs:36-49) on the GPU, one thread per query over
+// the leaf level of a plain B=16 tree (which is the sorted array itself).  This is the comparison
+// the reference's headline is about ("S-tree vs binary search"); not a production path.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+binary_search_kernel(const uint32_t* __restrict__ vals, unsigned long long n, const uint32_t* __restrict__ qs, size_t nq,
+                     uint32_t* __restrict__ out_vals, unsigned long long* __restrict__ out_idx) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t q = qs[i];
+        unsigned long long l = 0, r = n;
+        while (l < r) {
+            const unsigned long long m = (l + r) >> 1;
+            if (__ldg(vals + m) < q) l = m + 1; else r = m;
+        }
+        out_vals[i] = l < n ? __ldg(vals + l) : kMax;
+        if (out_idx) out_idx[i] = l;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Lane-group kernel for the partitioned layouts (Simple, Compact, L1, Overlapping, Map; B = 16):
 // the descent of partitioned_s_tree.rs:654-880 with 2 lanes x 32 B per node like the fast kernel.
 // Positions are kept in slots (4 B) so that the unaligned root windows of Overlapping / Map
@@ -646,7 +666,7 @@ int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t
         if (!fast_eligible(idx)) scheme = SST_SCHEME_GENERIC;
         else scheme = env_int("SST_SCHEME", (top_eligible(idx) && nq >= (size_t)env_int("SST_TABLE_MIN_NQ", 1 << 19)) ? SST_SCHEME_TABLE : SST_SCHEME_GROUP2);
     }
-    if (scheme != SST_SCHEME_GENERIC && !fast_eligible(idx)) {
+    if (scheme != SST_SCHEME_GENERIC && !fast_eligible(idx)) {  // (BINSEARCH included: plain B=16 only)
         set_error(SST_ERR_UNSUPPORTED, "the group/table kernels serve the plain B=16 tree; use SST_SCHEME_AUTO or SST_SCHEME_GENERIC");
         return SST_ERR_UNSUPPORTED;
     }
@@ -669,6 +689,13 @@ int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t
         case SST_SCHEME_GROUP2:
             if (T == 1) return launch_fast<2, 1, false>(idx, d_qs, nq, d_vals, d_idx, st);
             return launch_fast<2, 2, false>(idx, d_qs, nq, d_vals, d_idx, st);
+        case SST_SCHEME_BINSEARCH: {
+            // every plain B=16 layout stores the sorted keys verbatim at the start of its leaf level
+            const int sms = sm_count(idx->device);
+            const int grid = (int)std::min<size_t>(div_ceil(nq, 256), (size_t)sms * 8);
+            binary_search_kernel<<<grid, 256, 0, st>>>(idx->d_tree + idx->offsets[idx->levels - 1] * 16, idx->n, d_qs, nq, d_vals, d_idx);
+            return SST_CUDA_OK(cudaGetLastError()) ? SST_OK : SST_ERR_CUDA;
+        }
         case SST_SCHEME_GENERIC: {
             const int sms = sm_count(idx->device);
             const int grid = (int)std::min<size_t>(div_ceil(nq, 256), (size_t)sms * 32);

@@ -155,6 +155,20 @@ def test_table_kernel_skewed_keys(gpu, oracle):
     os.environ.pop("SST_TABLE_G", None)
 
 
+def test_binary_search_baseline(gpu, oracle):
+    """SortedVec::binary_search (binary_search.rs:36-49) as a GPU baseline kernel."""
+    sst = gpu
+    vals = gen_vals(300_001, seed=3)
+    qs = gen_queries(10_007, seed=4, vals=vals)
+    ev, ei = oracle.lower_bound(vals, qs)
+    for lm, rev, full in FLAG_SETS:
+        t = sst.STree16.new_params(vals, bool(lm), bool(rev), bool(full))
+        v, i = t.query(qs, sst.SCHEME_BINSEARCH, want_index=True)
+        assert np.array_equal(v, ev) and np.array_equal(i, ei)
+    with pytest.raises(sst.SstError):  # plain B=16 trees only
+        sst.PartitionedSTree16.new(vals, 4).query(qs, sst.SCHEME_BINSEARCH)
+
+
 def test_duplicates_and_tiny(gpu, oracle):
     sst = gpu
     for vals in ([MAX], [0, MAX], [5] * 40 + [MAX], list(range(16)), list(range(17)), [7] * 16 + [9] * 16 + [MAX] * 3,
