@@ -180,7 +180,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     return 0
 
 
@@ -332,6 +332,22 @@ def run_own(args):
                "sample": f"first {sample} queries of the step's batch over the full {n}-key tree; oracle batch_final<128> (AVX2={bool(O.lib().orc_has_avx2())}) on {threads} threads; results equal the GPU's"}
         del ot
 
+    # ---- GPU baseline the reference's headline is about: plain binary search on the same device ----
+    baselines = None
+    if rank == 0:
+        nb = min(e - s, 20_000_000)
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for it in range(2):
+            if it == 1:
+                a_.record()
+            rc = L.sst_query_device(tree._h, C.c_void_p(batches[0].data_ptr()), nb, C.c_void_p(out_v.data_ptr()), None, sst.SCHEME_BINSEARCH, stream)
+            if rc != 0:
+                raise RuntimeError(L.sst_last_error().decode())
+        b_.record()
+        torch.cuda.synchronize()
+        baselines = {"gpu_binary_search_queries_per_s": nb / (a_.elapsed_time(b_) * 1e-3),
+                     "note": "SortedVec::binary_search (binary_search.rs:36-49) as a thread-per-query kernel on the same B200"}
+
     # ---- optional secondary metric: suffix-array patterns/s (config C3) ----
     sa_info = None
     if rank == 0 and world == 1 and args.sa_text > 0:
@@ -354,9 +370,11 @@ def run_own(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * L.sst_query_launches(tree._h, args.scheme),
             "clocks": clocks, "results_ok": ok,
         }
+        if baselines is not None:
+            line["baselines"] = baselines
         if sa_info is not None:
             line["sa"] = sa_info
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0 if ok else 1
@@ -407,7 +425,46 @@ def bench_sa(args, sst, torch, dev):
         else:
             out["mlr_equals_binary"] = bool((lo == ref_lo).all())
     out["sa_check_violations"] = sa.check()
+    # bytes/pattern = 96*max(0, I-T) + 96 + |q| + 8 with I = ceil(log2(n+1)), T = floor(log2(L2/96))
+    import math
+    I = math.ceil(math.log2(n + 1))
+    T = math.floor(math.log2(torch.cuda.get_device_properties(dev).L2_cache_size / 96))
+    bpp = 96 * max(0, I - T) + 96 + plen + 8
+    peak, _ = measured_peak()
+    out["algorithmic_bytes_per_pattern"] = bpp
+    out["roofline_frac_binary"] = out["binary_patterns_per_s"] * bpp / 1e9 / peak
     return out
+
+
+class _QuietStdout:
+    """Library chatter (e.g. NCCL's version banner) goes to stdout; the contract is ONE JSON line there.
+    Route fd 1 to stderr for the duration of the run and hand back a writer for the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text: str):
+        os.write(self.saved, (text.rstrip("\n") + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+_OUT = None
+
+
+def emit_line(obj):
+    text = json.dumps(obj)
+    if _OUT is not None:
+        _OUT.emit(text)
+    else:
+        print(text, flush=True)
 
 
 def main():
@@ -430,9 +487,13 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "own":
         args.warmup = 3  # timing rule: W >= 3
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_own(args)
+    global _OUT
+    with _QuietStdout() as q:
+        _OUT = q
+        try:
+            return run_reference(args) if args.impl == "reference" else run_own(args)
+        finally:
+            _OUT = None
 
 
 if __name__ == "__main__":
