@@ -77,6 +77,10 @@ typedef struct sst_multi sst_multi_t; /* replicas of one index on several device
 const char* sst_last_error(void);
 int sst_last_status(void);
 int sst_device_count(void);          /* number of usable sm_100 devices, 0 if none */
+/* Page-locked host memory for query/result buffers: sst_query overlaps H2D, kernel and D2H only when the
+ * host buffers are pinned (pageable memory is staged by the driver).  NULL on failure. */
+void* sst_host_alloc(size_t bytes);
+void sst_host_free(void* p);
 const char* sst_version(void);
 
 /* ---- S+-tree: replaces STree::<B,16>::new_params (sst/s_tree.rs:72-176) ------------------- */

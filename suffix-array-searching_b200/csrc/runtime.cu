@@ -98,6 +98,17 @@ const char* sst_last_error(void) { return sst::g_err.c_str(); }
 int sst_last_status(void) { return sst::g_status; }
 const char* sst_version(void) { return "sst_b200 0.1 (sm_100a)"; }
 
+// Page-locked host buffers for full-speed sst_query / sst_sa_search (PCIe DMA without a staging copy).
+void* sst_host_alloc(size_t bytes) {
+    sst::clear_error();
+    void* p = nullptr;
+    if (!SST_CUDA_OK(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable))) return nullptr;
+    return p;
+}
+void sst_host_free(void* p) {
+    if (p) (void)cudaFreeHost(p);
+}
+
 int sst_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) {

@@ -739,6 +739,18 @@ struct Staging {
     unsigned long long* i[3] = {};
     cudaEvent_t e_in[3] = {}, e_k[3] = {}, e_out[3] = {};
     bool events = false;
+    int device = -1;
+    ~Staging() {  // host thread exits: give the device memory back (errors at process teardown are ignored)
+        if (device < 0 || (!cap && !cap_idx && !events)) return;
+        int prev = -1;
+        if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) { (void)cudaGetLastError(); return; }
+        for (int b = 0; b < 3; b++) {
+            cudaFree(q[b]); cudaFree(v[b]); cudaFree(i[b]);
+            if (events) { cudaEventDestroy(e_in[b]); cudaEventDestroy(e_k[b]); cudaEventDestroy(e_out[b]); }
+        }
+        (void)cudaGetLastError();
+        if (prev >= 0) cudaSetDevice(prev);
+    }
 };
 thread_local Staging g_staging[64];
 
@@ -788,6 +800,7 @@ int sst_query(const sst_index_t* idx, const uint32_t* qs, size_t nq, uint32_t* o
     const size_t nchunks = div_ceil(nq, chunk);
     const int NB = 3;  // device-side ring
     Staging& sg = g_staging[dev];
+    sg.device = dev;
     if (!staging_ensure(sg, std::min(chunk, nq), out_idx != nullptr)) return SST_ERR_CUDA;
     int rc = SST_OK;
     for (size_t c = 0; c < nchunks && rc == SST_OK; c++) {

@@ -56,6 +56,8 @@ def lib() -> C.CDLL:
         "sst_last_status": (i32, []),
         "sst_device_count": (i32, []),
         "sst_version": (C.c_char_p, []),
+        "sst_host_alloc": (vp, [sz]),
+        "sst_host_free": (None, [vp]),
         "sst_stree_build": (vp, [vp, sz, u32, u32, i32]),
         "sst_stree_build_device": (vp, [vp, sz, u32, u32, i32]),
         "sst_pstree_build": (vp, [vp, sz, u32, i32, i32]),
@@ -115,6 +117,24 @@ def _check(rc: int):
 
 def device_count() -> int:
     return lib().sst_device_count()
+
+
+class PinnedArray:
+    """numpy view over page-locked host memory from sst_host_alloc (full-speed host path)."""
+
+    def __init__(self, n: int, dtype=np.uint32):
+        self.nbytes = int(n) * np.dtype(dtype).itemsize
+        self._p = lib().sst_host_alloc(self.nbytes)
+        if not self._p:
+            _raise()
+        buf = (C.c_char * max(self.nbytes, 1)).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(n))
+
+    def __del__(self):
+        if getattr(self, "_p", None) and _lib is not None:
+            self.array = None
+            _lib.sst_host_free(C.c_void_p(self._p))
+            self._p = None
 
 
 def _is_torch(x) -> bool:

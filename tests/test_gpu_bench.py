@@ -1,0 +1,33 @@
+"""GPU test: bench.py's JSON contract on a small configuration (keys the driver reads)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+def test_bench_line_contract(gpu):
+    out = subprocess.run(
+        [sys.executable, os.path.join(ROOT, "bench.py"), "--n-keys", str(1 << 22), "--queries", str(1 << 22), "--steps", "3", "--warmup", "3",
+         "--cpu-sample", str(1 << 20), "--sa-text", "400000", "--sa-patterns", "20000", "--e2e-steps", "2"],
+        capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, "exactly one JSON line on stdout"
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["unit"] == "queries/s" and d["dtype"] == "u32" and d["data"] == "synthetic" and d["vs_baseline"] is None
+    assert d["steps"] == 3 and d["gpu_launches"] == 3 and d["results_ok"] is True
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == 4 * (1 << 22) and e["d2h_bytes_per_step"] == 4 * (1 << 22) and e["value"] > 0
+    assert d["sa"]["binary_ok"] and d["sa"]["mlr_ok"] and d["sa"]["mlr_equals_binary"] and d["sa"]["sa_check_violations"] == 0
+    assert "workload" in d["config"]

@@ -259,6 +259,40 @@ def test_multi_replicas_shard_queries(gpu, oracle):
     assert np.array_equal(v, ev) and np.array_equal(i, ei)
 
 
+def test_multi_repeated_calls_reuse_buffers(gpu, oracle):
+    """sst_multi_query keeps one worker thread (with its staging ring) per replica: no growth per call."""
+    import torch
+
+    sst = gpu
+    vals = gen_vals(500_000, seed=21)
+    qs = gen_queries(3_000_000, seed=22, vals=vals)
+    ev, _ = oracle.lower_bound(vals, qs[:50_000])
+    m = sst.MultiIndex.stree(vals, [0, 0], left_max=True)
+    assert np.array_equal(m.query(qs)[:50_000], ev)
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(8):
+        out = m.query(qs)
+    assert np.array_equal(out[:50_000], ev)
+    assert free0 - torch.cuda.mem_get_info()[0] < 32 << 20
+
+
+def test_pinned_host_buffers(gpu, oracle):
+    """sst_host_alloc: page-locked buffers through the host path."""
+    sst = gpu
+    vals = gen_vals(1 << 18, seed=31)
+    n = 5_000_003
+    q = sst.PinnedArray(n)
+    q.array[:] = gen_queries(n, seed=32, vals=vals)
+    out = sst.PinnedArray(n)
+    t = sst.STree16.new_params(vals, True, False, False)
+    import ctypes as C
+    rc = sst.lib().sst_query(t._h, q.array.ctypes.data_as(C.c_void_p), n, out.array.ctypes.data_as(C.c_void_p), None, 0)
+    assert rc == 0
+    ev, _ = oracle.lower_bound(vals, q.array[:100_000])
+    assert np.array_equal(out.array[:100_000], ev)
+    assert np.array_equal(out.array, t.query(q.array))
+
+
 def test_full_size_properties(gpu):
     """BASELINE size (2^28 keys, 10^8 queries): size-independent properties checked on the device:
     value >= q, keys[idx] == value, keys[idx-1] < q, and every kernel agrees with every other."""
