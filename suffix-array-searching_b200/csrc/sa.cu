@@ -8,12 +8,16 @@
 //   cmp (16-byte SIMD compare)         sa_search.rs:346-374
 //   the LCP-accelerated search that the reference only sketches (TODO at sa_search.rs:344-345)
 //
-// Search mapping: a sub-warp of PL lanes serves one pattern; every probe loads sa[m] once
-// (broadcast within the group) and compares 4*PL-byte windows of text and pattern, each lane
-// one (unaligned) 4-byte word, with __ballot_sync + ffs to find the first mismatching lane.
-// PL = 32 is the warp-per-pattern mapping; smaller groups put more patterns (more independent
-// dependent-miss chains) in flight per SM.  The `mlr` mode carries lcp(q, suffix(l-1)) and
-// lcp(q, suffix(r)) and starts each comparison at their minimum.
+// Search, two mappings (both bit-identical to the reference's binary_search):
+//   * sa_search_thread_kernel (default): one thread per pattern plus a pivot-prefix table that
+//     answers all but the last levels of the search with one 16-byte load per probe (see below);
+//   * sa_search_kernel<PL>: a sub-warp of PL lanes per pattern; every probe loads sa[m] once
+//     (broadcast within the group) and compares 4*PL-byte windows, each lane one (unaligned)
+//     4-byte word, with __ballot_sync + ffs to find the first mismatching lane.  PL = 32 is the
+//     warp-per-pattern mapping of the north star; it is the slowest one measured, because this
+//     path is bound by the number of independent miss chains in flight, not by compare width.
+// The `mlr` mode carries lcp(q, suffix(l-1)) and lcp(q, suffix(r)) and starts each comparison at
+// their minimum.
 //
 // Construction: prefix doubling.  Suffixes are ranked by their first 7 symbols (9 bits each,
 // 0 = past the end, so that a proper prefix sorts first exactly as Rust's slice ordering),

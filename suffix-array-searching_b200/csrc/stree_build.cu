@@ -169,7 +169,10 @@ void configure_persisting_l2(sst_index* idx) {
     cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, idx->device);
     cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, idx->device);
     if (max_persist <= 0 || max_window <= 0) return;
-    const cudaError_t rc = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+    const char* mb = getenv("SST_PERSIST_MB");
+    size_t want = (size_t)max_persist;
+    if (mb && *mb) want = std::min<size_t>((size_t)atoi(mb) << 20, (size_t)max_persist);
+    const cudaError_t rc = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
     if (getenv("SST_DEBUG")) {
         size_t got = 0;
         cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize);
