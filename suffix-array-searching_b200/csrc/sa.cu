@@ -311,12 +311,13 @@ struct W4 { uint32_t w[4]; };
 
 // 16 bytes starting at byte address `addr` (little endian words); aligned 16-byte chunks starting
 // at or beyond `end` read as zero.
+template <bool GUARD>
 __device__ __forceinline__ W4 load16_unaligned(const uint8_t* addr, const uint8_t* end) {
     const uintptr_t a = reinterpret_cast<uintptr_t>(addr) & ~(uintptr_t)15;
     const uint4* c = reinterpret_cast<const uint4*>(a);
     uint4 A = make_uint4(0, 0, 0, 0), B = make_uint4(0, 0, 0, 0);
-    if (reinterpret_cast<const uint8_t*>(c) < end) A = __ldg(c);
-    if (reinterpret_cast<const uint8_t*>(c + 1) < end) B = __ldg(c + 1);
+    if (!GUARD || reinterpret_cast<const uint8_t*>(c) < end) A = __ldg(c);
+    if (!GUARD || reinterpret_cast<const uint8_t*>(c + 1) < end) B = __ldg(c + 1);
     const unsigned s = (unsigned)(reinterpret_cast<uintptr_t>(addr) & 15u);
     const bool s2 = (s & 8u) != 0, s1 = (s & 4u) != 0;
     const unsigned bs = (s & 3u) * 8u;
@@ -332,20 +333,18 @@ __device__ __forceinline__ W4 load16_unaligned(const uint8_t* addr, const uint8_
 }
 
 // First mismatching byte (0..15, or 16 if none) between two 16-byte windows; tb/pb = the bytes there.
+// Branch-free: a select chain picks the first differing word.
 __device__ __forceinline__ unsigned first_mismatch16(const W4& t, const W4& q, unsigned& tb, unsigned& pb) {
-    unsigned mp = 16;
-    tb = pb = 0;
-#pragma unroll
-    for (int i = 3; i >= 0; i--) {
-        const uint32_t x = t.w[i] ^ q.w[i];
-        if (x) {
-            const unsigned byte = (__ffs(x) - 1) >> 3;
-            mp = 4u * i + byte;
-            tb = (t.w[i] >> (8u * byte)) & 0xffu;
-            pb = (q.w[i] >> (8u * byte)) & 0xffu;
-        }
-    }
-    return mp;
+    const uint32_t x0 = t.w[0] ^ q.w[0], x1 = t.w[1] ^ q.w[1], x2 = t.w[2] ^ q.w[2], x3 = t.w[3] ^ q.w[3];
+    const bool n0 = x0 != 0, n1 = x1 != 0, n2 = x2 != 0;
+    const uint32_t x = n0 ? x0 : n1 ? x1 : n2 ? x2 : x3;
+    const uint32_t tw = n0 ? t.w[0] : n1 ? t.w[1] : n2 ? t.w[2] : t.w[3];
+    const uint32_t pw = n0 ? q.w[0] : n1 ? q.w[1] : n2 ? q.w[2] : q.w[3];
+    const unsigned wi = n0 ? 0u : n1 ? 1u : n2 ? 2u : 3u;
+    const unsigned sh = (__ffs(x) - 1) & 24u;  // bit offset of the first differing byte (x == 0 -> 24, masked below)
+    tb = (tw >> sh) & 0xffu;
+    pb = (pw >> sh) & 0xffu;
+    return x ? 4u * wi + (sh >> 3) : 16u;
 }
 
 // suffix(spos) vs pattern from byte `start` (a multiple of 16) on; returns lcp, sets less.
@@ -359,11 +358,11 @@ __device__ __forceinline__ uint32_t thread_compare(const SaParams& p, unsigned l
     const uint8_t* pend = p.pats + p.pats_bytes;
     for (uint32_t off = start;; off += 16u) {
         if (off >= lim) { less = sl < ql; return lim; }
-        const W4 tw = load16_unaligned(tbase + off, tend);
+        const W4 tw = load16_unaligned<false>(tbase + off, tend);  // the text has 64 bytes of zero padding
         W4 pw;
         if (off == 0u) pw = p0;
         else if (off == 16u) pw = p1;
-        else pw = load16_unaligned(pat + off, pend);
+        else pw = load16_unaligned<true>(pat + off, pend);
         unsigned tb, pb;
         const unsigned mp = first_mismatch16(tw, pw, tb, pb);
         const uint32_t valid = lim - off;  // >= 1
@@ -380,17 +379,24 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
         const uint32_t ql = (uint32_t)(p.pat_off[i + 1] - po);
         const uint8_t* pat = p.pats + po;
         const uint8_t* pend = p.pats + p.pats_bytes;
-        const W4 p0 = load16_unaligned(pat, pend), p1 = load16_unaligned(pat + 16, pend);
-        unsigned long long l = 0, r = p.n;
+        const W4 p0 = load16_unaligned<true>(pat, pend), p1 = load16_unaligned<true>(pat + 16, pend);
+        uint32_t l = 0, r = (uint32_t)p.n;  // n < 2^32 - 16: all search state fits 32 bits
         uint32_t lcp_l = 0, lcp_r = 0;
         bool lcp_r_exact = false;  // lcp_r == lcp(q, suffix(r)) exactly (not a conservative bound)
         // ---- table levels: one 16-byte load per probe ----
         {
             const uint32_t c = ql < 16u ? ql : 16u;
-            unsigned long long j = 1;
+            // Incremental form of pivot_entry(j, d): the block of triple t rooted at heap node `root`
+            // is number root + off_t with off_0 = -1, off_{t+1} = 8 * off_t + 1 (<= 30 levels: 32-bit).
+            uint32_t j = 1, block8 = 0;
+            int off_t = -1;
+            unsigned e3 = 0;  // depth within the current triple
             for (int d = 0; d < p.pivot_levels && l < r; d++) {
-                const unsigned long long m = (l + r) >> 1;
-                const uint4 e = __ldg(p.pivots + pivot_entry(j, d));
+                const uint32_t m = l + ((r - l) >> 1);
+                if (e3 == 0) block8 = (uint32_t)((int)j + off_t) * 8u;
+                const uint32_t entry = block8 + ((1u << e3) | (j & ((1u << e3) - 1u)));
+                if (++e3 == 3) { e3 = 0; off_t = off_t * 8 + 1; }
+                const uint4 e = __ldg(p.pivots + entry);
                 W4 ew;
                 ew.w[0] = e.x; ew.w[1] = e.y; ew.w[2] = e.z; ew.w[3] = e.w;
                 unsigned tb, pb;
@@ -411,7 +417,7 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
         }
         // ---- remaining levels: sa[m] then text ----
         while (l < r) {
-            const unsigned long long m = (l + r) >> 1;
+            const uint32_t m = l + ((r - l) >> 1);
             const uint32_t start = MLR ? ((lcp_l < lcp_r ? lcp_l : lcp_r) & ~15u) : 0u;
             bool less;
             const uint32_t lcp = thread_compare(p, __ldg(p.sa + m), p0, p1, pat, ql, start, less);
@@ -483,6 +489,7 @@ bool build_pivots(sst_sa* s) {
     cudaMemGetInfo(&free_b, &total_b);
     const char* ge = getenv("SST_SA_TABLE_GB");
     const double budget = ge && *ge ? atof(ge) * 1e9 : std::min(0.5 * (double)free_b, 64e9);
+    if (levels > 30) levels = 30;  // the search kernel keeps heap indices and table offsets in 32 bits
     while (levels >= 3 && (double)pivot_table_entries(levels) * 16.0 > budget) levels -= 3;
     if (levels < 3) { s->pivot_levels = 0; return true; }
     cudaStream_t st = thread_stream(s->device);
