@@ -614,24 +614,13 @@ int sst_sa_check(const sst_sa_t* s, uint64_t* out_violations) {
     return ok ? SST_OK : SST_ERR_CUDA;
 }
 
-int sst_sa_search_device(const sst_sa_t* s, const uint8_t* d_pats, const uint64_t* d_pat_off, size_t npat, int mode,
-                         uint32_t* d_out_lo, uint32_t* d_out_hi, uint32_t* d_out_pos, void* stream) {
-    clear_error();
-    if (!s || (npat && (!d_pat_off || !d_out_lo))) { set_error(SST_ERR_ARG, "null argument"); return SST_ERR_ARG; }
-    if (mode != SST_SA_BINARY && mode != SST_SA_MLR) { set_error(SST_ERR_ARG, "unknown SA search mode"); return SST_ERR_ARG; }
-    if (npat == 0) return SST_OK;
-    DeviceGuard g(s->device);
-    if (!g.ok) return SST_ERR_CUDA;
-    cudaStream_t st = (cudaStream_t)stream;  // NULL == the CUDA legacy default stream
+static int sa_search_launch(const sst_sa_t* s, const uint8_t* d_pats, const uint64_t* d_pat_off, unsigned long long pats_end,
+                            size_t npat, int mode, uint32_t* d_out_lo, uint32_t* d_out_hi, uint32_t* d_out_pos, cudaStream_t st) {
     SaParams p{};
     p.text = s->d_text; p.sa = s->d_sa; p.n = s->n;
     p.pats = d_pats; p.pat_off = (const unsigned long long*)d_pat_off; p.npat = npat;
     p.out_lo = d_out_lo; p.out_hi = d_out_hi; p.out_pos = d_out_pos;
-    // total pattern bytes (bounds the aligned word loads); read back once
-    unsigned long long total = 0;
-    if (!SST_CUDA_OK(cudaMemcpyAsync(&total, d_pat_off + npat, 8, cudaMemcpyDeviceToHost, st)) || !SST_CUDA_OK(cudaStreamSynchronize(st)))
-        return SST_ERR_CUDA;
-    p.pats_bytes = total;
+    p.pats_bytes = pats_end;  // end offset of the packed patterns (bounds the aligned 16-byte loads)
     p.pivots = s->d_pivots;
     p.pivot_levels = s->d_pivots ? std::min(s->pivot_levels, env_int("SST_SA_USE_LEVELS", 64)) : 0;
     const int lanes = env_int("SST_SA_LANES", 1);
@@ -651,32 +640,120 @@ int sst_sa_search_device(const sst_sa_t* s, const uint8_t* d_pats, const uint64_
     return SST_CUDA_OK(cudaGetLastError()) ? SST_OK : SST_ERR_CUDA;
 }
 
+int sst_sa_search_device(const sst_sa_t* s, const uint8_t* d_pats, const uint64_t* d_pat_off, size_t npat, int mode,
+                         uint32_t* d_out_lo, uint32_t* d_out_hi, uint32_t* d_out_pos, void* stream) {
+    clear_error();
+    if (!s || (npat && (!d_pat_off || !d_out_lo))) { set_error(SST_ERR_ARG, "null argument"); return SST_ERR_ARG; }
+    if (mode != SST_SA_BINARY && mode != SST_SA_MLR) { set_error(SST_ERR_ARG, "unknown SA search mode"); return SST_ERR_ARG; }
+    if (npat == 0) return SST_OK;
+    DeviceGuard g(s->device);
+    if (!g.ok) return SST_ERR_CUDA;
+    cudaStream_t st = (cudaStream_t)stream;  // NULL == the CUDA legacy default stream
+    // total pattern bytes (bounds the aligned loads); one small read-back on the caller's stream
+    unsigned long long total = 0;
+    if (!SST_CUDA_OK(cudaMemcpyAsync(&total, d_pat_off + npat, 8, cudaMemcpyDeviceToHost, st)) || !SST_CUDA_OK(cudaStreamSynchronize(st)))
+        return SST_ERR_CUDA;
+    return sa_search_launch(s, d_pats, d_pat_off, total, npat, mode, d_out_lo, d_out_hi, d_out_pos, st);
+}
+
+// Per (host thread, device) staging ring for the host-buffer SA path (see Staging in stree_search.cu).
+namespace {
+struct SaStaging {
+    size_t cap_pat = 0, cap_bytes = 0;
+    uint8_t* p[3] = {};
+    uint64_t* o[3] = {};
+    uint32_t *lo[3] = {}, *hi[3] = {}, *pos[3] = {};
+    cudaEvent_t e_in[3] = {}, e_k[3] = {}, e_out[3] = {};
+    bool events = false;
+    int device = -1;
+    ~SaStaging() {
+        if (device < 0) return;
+        int prev = -1;
+        if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) { (void)cudaGetLastError(); return; }
+        for (int b = 0; b < 3; b++) {
+            cudaFree(p[b]); cudaFree(o[b]); cudaFree(lo[b]); cudaFree(hi[b]); cudaFree(pos[b]);
+            if (events) { cudaEventDestroy(e_in[b]); cudaEventDestroy(e_k[b]); cudaEventDestroy(e_out[b]); }
+        }
+        (void)cudaGetLastError();
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    bool ensure(size_t npat, size_t bytes) {
+        if (!events) {
+            for (int b = 0; b < 3; b++)
+                if (!SST_CUDA_OK(cudaEventCreateWithFlags(&e_in[b], cudaEventDisableTiming)) ||
+                    !SST_CUDA_OK(cudaEventCreateWithFlags(&e_k[b], cudaEventDisableTiming)) ||
+                    !SST_CUDA_OK(cudaEventCreateWithFlags(&e_out[b], cudaEventDisableTiming)))
+                    return false;
+            events = true;
+        }
+        if (npat > cap_pat) {
+            for (int b = 0; b < 3; b++) {
+                cudaFree(o[b]); cudaFree(lo[b]); cudaFree(hi[b]); cudaFree(pos[b]);
+                o[b] = nullptr; lo[b] = hi[b] = pos[b] = nullptr;
+                if (!SST_CUDA_OK(cudaMalloc(&o[b], (npat + 1) * 8)) || !SST_CUDA_OK(cudaMalloc(&lo[b], npat * 4)) ||
+                    !SST_CUDA_OK(cudaMalloc(&hi[b], npat * 4)) || !SST_CUDA_OK(cudaMalloc(&pos[b], npat * 4))) { cap_pat = 0; return false; }
+            }
+            cap_pat = npat;
+        }
+        if (bytes > cap_bytes) {
+            const size_t want = bytes + bytes / 4;
+            for (int b = 0; b < 3; b++) {
+                cudaFree(p[b]);
+                p[b] = nullptr;
+                if (!SST_CUDA_OK(cudaMalloc(&p[b], want + 64))) { cap_bytes = 0; return false; }
+            }
+            cap_bytes = want;
+        }
+        return true;
+    }
+};
+thread_local SaStaging g_sa_staging[64];
+}  // namespace
+
+// Host buffers: patterns go down in chunks through a three-buffer ring (H2D | kernel | D2H on three
+// streams).  Offsets stay absolute: the kernel is given a pattern base shifted by the chunk's first offset.
 int sst_sa_search(const sst_sa_t* s, const uint8_t* pats, const uint64_t* pat_off, size_t npat, int mode, uint32_t* out_lo,
                   uint32_t* out_hi, uint32_t* out_pos) {
     clear_error();
     if (!s || (npat && (!pat_off || !out_lo))) { set_error(SST_ERR_ARG, "null argument"); return SST_ERR_ARG; }
+    if (mode != SST_SA_BINARY && mode != SST_SA_MLR) { set_error(SST_ERR_ARG, "unknown SA search mode"); return SST_ERR_ARG; }
     if (npat == 0) return SST_OK;
-    DeviceGuard g(s->device);
+    const int dev = s->device;
+    if (dev < 0 || dev >= 64) { set_error(SST_ERR_ARG, "device index out of range"); return SST_ERR_ARG; }
+    DeviceGuard g(dev);
     if (!g.ok) return SST_ERR_CUDA;
-    cudaStream_t st = thread_stream(s->device);
-    const size_t bytes = pat_off[npat];
-    uint8_t* d_p = nullptr;
-    uint64_t* d_o = nullptr;
-    uint32_t *d_lo = nullptr, *d_hi = nullptr, *d_pos = nullptr;
-    bool ok = SST_CUDA_OK(cudaMalloc(&d_p, bytes + 64)) && SST_CUDA_OK(cudaMalloc(&d_o, (npat + 1) * 8)) &&
-              SST_CUDA_OK(cudaMalloc(&d_lo, npat * 4)) && (!out_hi || SST_CUDA_OK(cudaMalloc(&d_hi, npat * 4))) &&
-              (!out_pos || SST_CUDA_OK(cudaMalloc(&d_pos, npat * 4)));
-    ok = ok && (bytes == 0 || SST_CUDA_OK(cudaMemcpyAsync(d_p, pats, bytes, cudaMemcpyHostToDevice, st))) &&
-         SST_CUDA_OK(cudaMemcpyAsync(d_o, pat_off, (npat + 1) * 8, cudaMemcpyHostToDevice, st));
-    int rc = ok ? sst_sa_search_device(s, d_p, d_o, npat, mode, d_lo, d_hi, d_pos, st) : SST_ERR_CUDA;
-    if (rc == SST_OK) {
-        ok = SST_CUDA_OK(cudaMemcpyAsync(out_lo, d_lo, npat * 4, cudaMemcpyDeviceToHost, st)) &&
-             (!out_hi || SST_CUDA_OK(cudaMemcpyAsync(out_hi, d_hi, npat * 4, cudaMemcpyDeviceToHost, st))) &&
-             (!out_pos || SST_CUDA_OK(cudaMemcpyAsync(out_pos, d_pos, npat * 4, cudaMemcpyDeviceToHost, st))) &&
-             SST_CUDA_OK(cudaStreamSynchronize(st));
-        rc = ok ? SST_OK : SST_ERR_CUDA;
+    cudaStream_t s_in = thread_copy_stream(dev, 0), s_k = thread_stream(dev), s_out = thread_copy_stream(dev, 1);
+    if (!s_in || !s_k || !s_out) return SST_ERR_CUDA;
+    const size_t chunk = std::max<size_t>((size_t)env_int("SST_SA_CHUNK", 1 << 20), 16);
+    const size_t nchunks = div_ceil(npat, chunk);
+    size_t max_bytes = 0;
+    for (size_t c = 0; c < nchunks; c++) {
+        const size_t a = c * chunk, b = std::min(npat, a + chunk);
+        max_bytes = std::max<size_t>(max_bytes, pat_off[b] - pat_off[a]);
     }
-    cudaFree(d_p); cudaFree(d_o); cudaFree(d_lo); cudaFree(d_hi); cudaFree(d_pos);
+    SaStaging& sg = g_sa_staging[dev];
+    sg.device = dev;
+    if (!sg.ensure(std::min(chunk, npat), max_bytes)) return SST_ERR_CUDA;
+    int rc = SST_OK;
+    for (size_t c = 0; c < nchunks && rc == SST_OK; c++) {
+        const int b = (int)(c % 3);
+        const size_t a = c * chunk, e = std::min(npat, a + chunk), cnt = e - a;
+        const size_t byte0 = pat_off[a], bytes = pat_off[e] - byte0;
+        if (c >= 3 && !SST_CUDA_OK(cudaStreamWaitEvent(s_in, sg.e_out[b], 0))) { rc = SST_ERR_CUDA; break; }
+        if ((bytes && !SST_CUDA_OK(cudaMemcpyAsync(sg.p[b], pats + byte0, bytes, cudaMemcpyHostToDevice, s_in))) ||
+            !SST_CUDA_OK(cudaMemcpyAsync(sg.o[b], pat_off + a, (cnt + 1) * 8, cudaMemcpyHostToDevice, s_in)) ||
+            !SST_CUDA_OK(cudaEventRecord(sg.e_in[b], s_in)) || !SST_CUDA_OK(cudaStreamWaitEvent(s_k, sg.e_in[b], 0))) { rc = SST_ERR_CUDA; break; }
+        rc = sa_search_launch(s, sg.p[b] - byte0, sg.o[b], pat_off[e], cnt, mode, sg.lo[b], out_hi ? sg.hi[b] : nullptr,
+                              out_pos ? sg.pos[b] : nullptr, s_k);
+        if (rc != SST_OK) break;
+        if (!SST_CUDA_OK(cudaEventRecord(sg.e_k[b], s_k)) || !SST_CUDA_OK(cudaStreamWaitEvent(s_out, sg.e_k[b], 0)) ||
+            !SST_CUDA_OK(cudaMemcpyAsync(out_lo + a, sg.lo[b], cnt * 4, cudaMemcpyDeviceToHost, s_out)) ||
+            (out_hi && !SST_CUDA_OK(cudaMemcpyAsync(out_hi + a, sg.hi[b], cnt * 4, cudaMemcpyDeviceToHost, s_out))) ||
+            (out_pos && !SST_CUDA_OK(cudaMemcpyAsync(out_pos + a, sg.pos[b], cnt * 4, cudaMemcpyDeviceToHost, s_out))) ||
+            !SST_CUDA_OK(cudaEventRecord(sg.e_out[b], s_out))) { rc = SST_ERR_CUDA; break; }
+    }
+    if (!SST_CUDA_OK(cudaStreamSynchronize(s_in)) || !SST_CUDA_OK(cudaStreamSynchronize(s_k)) || !SST_CUDA_OK(cudaStreamSynchronize(s_out)))
+        rc = rc == SST_OK ? SST_ERR_CUDA : rc;
     return rc;
 }
 

@@ -100,6 +100,18 @@ def test_sa_zero_bytes_and_short_suffixes(gpu, oracle):
     _check_search(sst, oracle, s, text, sa, pats)
 
 
+def test_sa_host_pipeline_chunks(gpu, oracle, monkeypatch):
+    """Host path in many small chunks (ring of three staging buffers, shifted pattern base per chunk)."""
+    sst = gpu
+    monkeypatch.setenv("SST_SA_CHUNK", "37")
+    text = random_text(80_000, seed=41)
+    s = sst.SaNaive.build(text)
+    pats = random_patterns(text, 1000, seed=42, lo=1, hi=90) + [b"", b"", text[-3:].tobytes()]
+    _check_search(sst, oracle, s, text, s.sa, pats)
+    monkeypatch.setenv("SST_SA_CHUNK", "1000000")
+    _check_search(sst, oracle, s, text, s.sa, pats)
+
+
 def test_sa_byte_alphabet(gpu, oracle):
     sst = gpu
     text = random_text(50_000, seed=21, sigma=256)
