@@ -280,9 +280,14 @@ def run_own(args):
                 "traffic": None, "peak_source": peak_src, "bytes_per_query": bytes_per_query, "hbm_levels": H_hbm,
                 "kernel": "stree_search_fast", "kernel_ms": kern_ms}
     tf = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tf):
+    if os.path.exists(tf) and n == (1 << 28) and (e - s) == 100_000_000:  # the capture is of exactly this launch shape
         try:
             roofline["traffic"] = json.load(open(tf)).get("dram_bytes_per_launch")
+            # what the DRAM actually moved (ncu) over the live launch time: B200 fills L2 in 128-B units,
+            # so a random 64-B node costs two sectors more than it needs (profiles/r1_ncu_probe.csv)
+            roofline["traffic_gbs"] = roofline["traffic"] / (kern_ms * 1e-3) / 1e9
+            roofline["traffic_frac"] = roofline["traffic_gbs"] / peak
+            roofline["random_fill_ceiling_gbs"] = 5000.0  # probe: 42.5 G random 64-B gathers/s x 117 B of DRAM read each
         except Exception:
             pass
 
