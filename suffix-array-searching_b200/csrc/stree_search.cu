@@ -426,9 +426,10 @@ binary_search_kernel(const uint32_t* __restrict__ vals, unsigned long long n, co
 // ------------------------------------------------------------------------------------------------
 // 8 consecutive keys starting at p (4-byte aligned): one LDG.256 when 32-byte aligned, otherwise three
 // aligned 16-byte chunks and a word-select network.
-__device__ __forceinline__ Keys<8> ldg_window8(const uint32_t* p) {
+template <bool LEAF>
+__device__ __forceinline__ Keys<8> ldg_window8(const uint32_t* p, uint64_t pol) {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    if ((a & 31u) == 0) return ldg_keys_plain<8>(p);
+    if ((a & 31u) == 0) return ldg_keys<8, LEAF>(p, pol);  // same L2 policies as the fast kernel
     const uint4* c = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
     const uint4 A = __ldg(c), B = __ldg(c + 1);
     const unsigned w = (unsigned)((a >> 2) & 3u);
@@ -452,6 +453,7 @@ pstree_search_group(const __grid_constant__ SstTreeView v, const uint32_t* __res
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
     const unsigned sub = lane & 1u, gbase = lane & ~1u;
     const int L = v.levels;
+    const uint64_t pol_inner = policy_evict_last(), pol_leaf = policy_evict_first();
     for (size_t base = ((size_t)blockIdx.x * warps + warp) * (32 * T); base < nq; base += (size_t)gridDim.x * warps * (32 * T)) {
         uint32_t qown[T];
         unsigned long long sown[T];  // first slot; ~0 marks "prefix beyond the last part"
@@ -483,14 +485,14 @@ pstree_search_group(const __grid_constant__ SstTreeView v, const uint32_t* __res
             Keys<W> ks[D];
             const uint32_t* gl = v.tree + v.level_slot[h] + sub * W;
 #pragma unroll
-            for (int d = 0; d < D; d++) ks[d] = ldg_window8(gl + pb[d] + s[d]);
+            for (int d = 0; d < D; d++) ks[d] = ldg_window8<false>(gl + pb[d] + s[d], pol_inner);
 #pragma unroll
             for (int d = 0; d < D; d++) s[d] = s[d] * v.mult[h] + 16ull * group_count<G>(ks[d], q[d], gbase);
         }
         const uint32_t* gl = v.tree + v.level_slot[L - 1];
         Keys<W> ks[D];
 #pragma unroll
-        for (int d = 0; d < D; d++) ks[d] = ldg_window8(gl + pb[d] + s[d] + sub * W);
+        for (int d = 0; d < D; d++) ks[d] = ldg_window8<true>(gl + pb[d] + s[d] + sub * W, pol_leaf);
         uint32_t myval[T];
         unsigned long long mypos[T];
 #pragma unroll
