@@ -283,11 +283,13 @@ def run_own(args):
     if os.path.exists(tf) and n == (1 << 28) and (e - s) == 100_000_000:  # the capture is of exactly this launch shape
         try:
             roofline["traffic"] = json.load(open(tf)).get("dram_bytes_per_launch")
-            # what the DRAM actually moved (ncu) over the live launch time: B200 fills L2 in 128-B units,
-            # so a random 64-B node costs two sectors more than it needs (profiles/r1_ncu_probe.csv)
+            # what the DRAM actually moved (ncu) over the live launch time
             roofline["traffic_gbs"] = roofline["traffic"] / (kern_ms * 1e-3) / 1e9
             roofline["traffic_frac"] = roofline["traffic_gbs"] / peak
-            roofline["random_fill_ceiling_gbs"] = 5000.0  # probe: 42.5 G random 64-B gathers/s x 117 B of DRAM read each
+            # the binding limit is the random-access RATE, not bytes: a gather probe tops out at 43 G random
+            # 64-B accesses/s whether L2 is filled in 64-B or 128-B units (profiles/r1_ncu_probe_pf.csv)
+            roofline["random_access_ceiling_per_s"] = 43.0e9
+            roofline["dram_accesses_per_s"] = roofline["traffic"] / 64 / (kern_ms * 1e-3)
         except Exception:
             pass
 

@@ -90,6 +90,9 @@ struct sst_index {
     size_t top_nbound = 0;
     uint16_t* d_top_table = nullptr;              // [2^15 + 1] separators-before-bucket counts
     uint16_t* d_top_low = nullptr;                // [top_nbound] low 16 bits of each separator
+    // 16-bit compressed copy of the last internal level (plain B=16 trees whose level is HBM/L2 sized)
+    uint16_t* d_c5 = nullptr;                     // [nodes * 16] separators minus the node's base
+    uint32_t* d_h5 = nullptr;                     // [nodes] base (first separator), 0xffffffff = use the exact node
     bool persist_ok = false;                      // persisting-L2 carve-out configured on this device
     size_t persist_window_max = 0;
     SstTreeView view{};
@@ -101,6 +104,7 @@ sst_index* build_plain(const uint32_t* d_sorted, bool sorted_is_owned_leaf, size
 sst_index* build_partitioned(const uint32_t* d_sorted, size_t n, uint32_t b, int variant, int device);
 void finalize_view(sst_index* idx);
 bool build_top_table(sst_index* idx, const uint32_t* d_sorted);
+bool build_compressed_level(sst_index* idx);
 // search (stree_search.cu)
 int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx,
                  int scheme, cudaStream_t stream);

@@ -26,6 +26,8 @@ namespace {
 
 constexpr int kBuildThreads = 256;
 
+void free_index(sst_index* idx);  // defined below
+
 inline unsigned grid_for(size_t work, int threads = kBuildThreads) {
     size_t b = div_ceil(work, (size_t)threads);
     return (unsigned)std::min<size_t>(b, (size_t)1 << 30);
@@ -251,9 +253,8 @@ sst_index* build_plain(const uint32_t* d_sorted, bool, size_t n, uint32_t node_b
         delete idx;
         return nullptr;
     }
-    if (!build_top_table(idx, d_sorted)) {
-        cudaFree(idx->d_tree);
-        delete idx;
+    if (!build_top_table(idx, d_sorted) || !build_compressed_level(idx)) {
+        free_index(idx);
         return nullptr;
     }
     configure_persisting_l2(idx);
@@ -457,10 +458,57 @@ void free_index(sst_index* idx) {
     cudaFree(idx->d_part_pos);
     cudaFree(idx->d_top_table);
     cudaFree(idx->d_top_low);
+    cudaFree(idx->d_c5);
+    cudaFree(idx->d_h5);
     delete idx;
 }
 
 }  // namespace
+
+// 16-bit copy of the last internal level: node -> (base = first separator, 16 deltas).  Halves the L2
+// footprint of the one level that competes with leaf traffic for the cache (63 -> 33+4 MB at 2^28 keys).
+// A node whose separators span 2^16 or more (sparse keys, MAX padding) is flagged and read exactly.
+__global__ void compress_level_kernel(const uint32_t* __restrict__ level, unsigned long long nodes, uint16_t* __restrict__ low,
+                                      uint32_t* __restrict__ high) {
+    for (unsigned long long nd = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; nd < nodes;
+         nd += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint4* src = reinterpret_cast<const uint4*>(level + nd * 16);
+        uint32_t k[16];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const uint4 v = src[i]; k[4 * i] = v.x; k[4 * i + 1] = v.y; k[4 * i + 2] = v.z; k[4 * i + 3] = v.w; }
+        const uint32_t h = k[0];
+        bool uniform = h != 0xffffffffu;
+#pragma unroll
+        for (int i = 1; i < 16; i++) uniform = uniform && k[i] >= h && (k[i] - h) < 65536u;
+        high[nd] = uniform ? h : 0xffffffffu;
+        uint4* dst = reinterpret_cast<uint4*>(low + nd * 16);
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) w[i] = uniform ? (((k[2 * i] - h) & 0xffffu) | ((k[2 * i + 1] - h) << 16)) : 0u;
+        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+}
+
+bool build_compressed_level(sst_index* idx) {
+    if (idx->variant != SST_PLAIN || idx->node_b != 16 || idx->levels < 3) return true;
+    // Opt-in experiment (SST_C5=1): measured at 2^28 keys it cuts DRAM reads by 15 % (7.99 -> 6.77 GB per
+    // 10^8 queries, L2 hit 47 -> 54 %) but the extra load and instructions cost 8 % of run time.
+    const char* e = getenv("SST_C5");
+    if (!e || atoi(e) == 0) return true;
+    const int h = idx->levels - 2;
+    const size_t nodes = idx->layer_sizes[h];
+    if (idx->top_level > h) return true;
+    cudaStream_t st = thread_stream(idx->device);
+    bool ok = SST_CUDA_OK(cudaMalloc(&idx->d_c5, nodes * 32)) && SST_CUDA_OK(cudaMalloc(&idx->d_h5, nodes * 4));
+    if (ok) {
+        compress_level_kernel<<<std::min<unsigned>(grid_for(nodes), 148 * 16), kBuildThreads, 0, st>>>(
+            idx->d_tree + idx->offsets[h] * 16, nodes, idx->d_c5, idx->d_h5);
+        ok = SST_CUDA_OK(cudaGetLastError()) && SST_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    if (!ok) { cudaFree(idx->d_c5); cudaFree(idx->d_h5); idx->d_c5 = nullptr; idx->d_h5 = nullptr; }
+    return ok;
+}
 
 // Chooses the deepest level t whose node count fits 16-bit ranks and shared memory, and builds
 // the rank table for it.  Plain B=16 trees only; a tree of height 1 has no table.

@@ -89,37 +89,56 @@ struct Keys {
     uint32_t k[W];
 };
 
+// Node loads carry the L2::64B prefetch-size qualifier (SASS ...LTC64B): without it B200 fills L2 from
+// HBM in 128-byte units, i.e. every random 64-byte node drags its neighbour along (measured with the
+// gather probe: 11.7 GB vs 6.1 GB of DRAM reads per 10^8 gathers, profiles/r1_ncu_probe_pf.csv).
 template <int W, bool NO_L1>
 __device__ __forceinline__ Keys<W> ldg_keys(const uint32_t* p, uint64_t pol) {
     Keys<W> r;
     if constexpr (W == 1) {
         if constexpr (NO_L1)
-            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r.k[0]) : "l"(p), "l"(pol));
+            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.L2::64B.u32 %0, [%1], %2;" : "=r"(r.k[0]) : "l"(p), "l"(pol));
         else
-            asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r.k[0]) : "l"(p), "l"(pol));
+            asm volatile("ld.global.nc.L2::cache_hint.L2::64B.u32 %0, [%1], %2;" : "=r"(r.k[0]) : "l"(p), "l"(pol));
     } else if constexpr (W == 2) {
         if constexpr (NO_L1)
-            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.k[0]), "=r"(r.k[1]) : "l"(p), "l"(pol));
+            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.L2::64B.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.k[0]), "=r"(r.k[1]) : "l"(p), "l"(pol));
         else
-            asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.k[0]), "=r"(r.k[1]) : "l"(p), "l"(pol));
+            asm volatile("ld.global.nc.L2::cache_hint.L2::64B.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.k[0]), "=r"(r.k[1]) : "l"(p), "l"(pol));
     } else if constexpr (W == 4) {
         if constexpr (NO_L1)
-            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
                          : "=r"(r.k[0]), "=r"(r.k[1]), "=r"(r.k[2]), "=r"(r.k[3]) : "l"(p), "l"(pol));
         else
-            asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+            asm volatile("ld.global.nc.L2::cache_hint.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
                          : "=r"(r.k[0]), "=r"(r.k[1]), "=r"(r.k[2]), "=r"(r.k[3]) : "l"(p), "l"(pol));
     } else {
         static_assert(W == 8, "unsupported slice width");
         if constexpr (NO_L1)
-            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.L2::64B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
                          : "=r"(r.k[0]), "=r"(r.k[1]), "=r"(r.k[2]), "=r"(r.k[3]), "=r"(r.k[4]), "=r"(r.k[5]), "=r"(r.k[6]), "=r"(r.k[7])
                          : "l"(p), "l"(pol));
         else
-            asm volatile("ld.global.nc.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+            asm volatile("ld.global.nc.L2::cache_hint.L2::64B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
                          : "=r"(r.k[0]), "=r"(r.k[1]), "=r"(r.k[2]), "=r"(r.k[3]), "=r"(r.k[4]), "=r"(r.k[5]), "=r"(r.k[6]), "=r"(r.k[7])
                          : "l"(p), "l"(pol));
     }
+    return r;
+}
+
+// 32-byte load with an explicit L2 prefetch-size qualifier (SASS: LDG.E...LTC64B/LTC128B/LTC256B).
+template <int PF>
+__device__ __forceinline__ Keys<8> ldg_keys8_pf(const uint32_t* p, uint64_t pol) {
+    Keys<8> r;
+#define SST_LD8(Q)                                                                                                                        \
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint" Q ".v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"                          \
+                 : "=r"(r.k[0]), "=r"(r.k[1]), "=r"(r.k[2]), "=r"(r.k[3]), "=r"(r.k[4]), "=r"(r.k[5]), "=r"(r.k[6]), "=r"(r.k[7])       \
+                 : "l"(p), "l"(pol))
+    if constexpr (PF == 64) SST_LD8(".L2::64B");
+    else if constexpr (PF == 128) SST_LD8(".L2::128B");
+    else if constexpr (PF == 256) SST_LD8(".L2::256B");
+    else SST_LD8("");
+#undef SST_LD8
     return r;
 }
 
@@ -190,6 +209,8 @@ struct FastParams {
     unsigned long long n;
     int hints;                        // bit0: L2 evict_last on inner levels, bit1: evict_first on leaf
     unsigned l1_levels;               // bit h set: level h is small enough to live in L1 (allocate there)
+    const uint16_t* c5;               // 16-bit compressed copy of level `levels - 2` (or null)
+    const uint32_t* h5;               // per node: base (first separator), 0xffffffff = read the exact node
 };
 
 constexpr unsigned kTopBuckets = 1u << 15;
@@ -262,6 +283,43 @@ stree_search_fast(const __grid_constant__ FastParams p, const uint32_t* __restri
         }
         // ---- internal levels read from L1/L2 ----
         for (int h = h0; h + 1 < L; h++) {
+            if constexpr (G == 2) {
+                if (p.c5 != nullptr && h + 2 == L) {
+                    // Last internal level through its 16-bit copy: 32 B per node instead of 64, so the
+                    // level stays L2-resident next to the leaf stream (separator = base + 16-bit delta).
+                    // Nodes spanning >= 2^16 in value (and q >= 2^31) take the exact node.
+                    uint4 cw[D];
+                    unsigned hh[D];
+#pragma unroll
+                    for (int d = 0; d < D; d++) {
+                        hh[d] = __ldg(p.h5 + k[d]);
+                        const uint4* cp = reinterpret_cast<const uint4*>(p.c5 + (size_t)k[d] * 16u) + sub;
+                        asm volatile("ld.global.nc.L2::cache_hint.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                                     : "=r"(cw[d].x), "=r"(cw[d].y), "=r"(cw[d].z), "=r"(cw[d].w) : "l"(cp), "l"(pol_inner));
+                    }
+#pragma unroll
+                    for (int d = 0; d < D; d++) {
+                        unsigned c;
+                        if (hh[d] == 0xffffffffu || q[d] > kMax) {  // group-uniform, rare
+                            const unsigned gm = 3u << gbase;
+                            const Keys<W> ex = ldg_keys<W, true>(p.tree + p.level_slot[h] + sub * W + (size_t)k[d] * 16u, pol_inner);
+                            c = 0;
+#pragma unroll
+                            for (int i = 0; i < W; i++) c += ((int)ex.k[i] < (int)q[d]) ? 1u : 0u;
+                            c += __shfl_xor_sync(gm, c, 1);
+                        } else {
+                            // separator_i < q  <=>  delta_i < q - base  (0 deltas qualify when q <= base, all when q - base > 0xffff)
+                            const uint32_t x = q[d] > hh[d] ? min(q[d] - hh[d], 0x10000u) : 0u;
+                            const uint32_t w0 = cw[d].x, w1 = cw[d].y, w2 = cw[d].z, w3 = cw[d].w;
+                            const unsigned cnt = ((w0 & 0xffffu) < x) + ((w0 >> 16) < x) + ((w1 & 0xffffu) < x) + ((w1 >> 16) < x) +
+                                                 ((w2 & 0xffffu) < x) + ((w2 >> 16) < x) + ((w3 & 0xffffu) < x) + ((w3 >> 16) < x);
+                            c = cnt + __shfl_xor_sync(3u << gbase, cnt, 1);
+                        }
+                        k[d] = k[d] * 17u + c;
+                    }
+                    continue;
+                }
+            }
             Keys<W> ks[D];
             const uint32_t* gl = p.tree + p.level_slot[h] + sub * W;
             if (p.hints & 4) {  // experiment: un-hinted loads, the launch's access-policy window decides
@@ -540,6 +598,31 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
     return x ^ (x >> 31);
 }
 
+template <int PF>
+__global__ void __launch_bounds__(1024, 1)
+gather_probe_pf_kernel(const uint32_t* __restrict__ buf, unsigned long long nodes, size_t n_gathers, uint32_t* __restrict__ sink,
+                       unsigned long long seed) {
+    constexpr int D = 4;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const unsigned sub = lane & 1u, grp = lane / 2;
+    const uint64_t pol = policy_evict_first();
+    unsigned acc = 0;
+    const size_t per_warp = 16 * D;
+    for (size_t base = ((size_t)blockIdx.x * warps + warp) * per_warp; base < n_gathers; base += (size_t)gridDim.x * warps * per_warp) {
+        Keys<8> ks[D];
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            const uint64_t id = ((mix64(seed + base + (size_t)grp * D + d) >> 32) * nodes) >> 32;
+            ks[d] = ldg_keys8_pf<PF>(buf + id * 16 + sub * 8, pol);
+        }
+#pragma unroll
+        for (int d = 0; d < D; d++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc += ks[d].k[i] < 0x40000000u;
+    }
+    if (acc == 0xffffffffu) sink[0] = acc;
+}
+
 template <int G, int D>
 __global__ void __launch_bounds__(1024, 1)
 gather_probe_kernel(const uint32_t* __restrict__ buf, unsigned long long nodes, size_t n_gathers, uint32_t* __restrict__ sink,
@@ -590,6 +673,7 @@ int launch_fast(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t*
         fp.level_slot[h] = (unsigned long long)idx->offsets[h] * 16;
         if (idx->layer_sizes[h] * 64 <= (size_t)env_int("SST_L1_LEVEL_KB", 256) * 1024) fp.l1_levels |= 1u << h;
     }
+    if (G == 2 && TOP && idx->d_c5 && env_int("SST_USE_C5", 1)) { fp.c5 = idx->d_c5; fp.h5 = idx->d_h5; }
     size_t smem_bytes = 0;
     if (TOP) {
         fp.top_level = idx->top_level;
@@ -867,6 +951,10 @@ double sst_probe_gather64(int device, size_t bytes, size_t n_gathers, int lanes_
             case 8: gather_probe_kernel<8, 8><<<grid, threads, 0, st>>>(buf, nodes, n_gathers, sink, seed); break;
             case 4: gather_probe_kernel<4, 8><<<grid, threads, 0, st>>>(buf, nodes, n_gathers, sink, seed); break;
             case 2: gather_probe_kernel<2, 4><<<grid, threads, 0, st>>>(buf, nodes, n_gathers, sink, seed); break;
+            case 1064: gather_probe_pf_kernel<64><<<grid, threads, 0, st>>>(buf, nodes, n_gathers, sink, seed); break;   // experiment:
+            case 1128: gather_probe_pf_kernel<128><<<grid, threads, 0, st>>>(buf, nodes, n_gathers, sink, seed); break;  // explicit L2
+            case 1256: gather_probe_pf_kernel<256><<<grid, threads, 0, st>>>(buf, nodes, n_gathers, sink, seed); break;  // prefetch size
+            case 1000: gather_probe_pf_kernel<0><<<grid, threads, 0, st>>>(buf, nodes, n_gathers, sink, seed); break;
             default: return false;
         }
         return true;

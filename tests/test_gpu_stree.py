@@ -155,6 +155,27 @@ def test_table_kernel_skewed_keys(gpu, oracle):
     os.environ.pop("SST_TABLE_G", None)
 
 
+def test_compressed_last_level(gpu, oracle, monkeypatch):
+    """16-bit copy of the last internal level (forced on for a small tree): dense keys (compressed path),
+    sparse keys (every node falls back to the exact node) and a mix, all flag combinations."""
+    sst = gpu
+    monkeypatch.setenv("SST_C5", "1")  # build it regardless of the level's size
+    rng = np.random.default_rng(91)
+    dense = np.sort(rng.integers(1 << 20, (1 << 20) + (1 << 22), 600_000).astype(np.uint32))
+    sparse = gen_vals(300_000, seed=92)
+    mix = np.sort(np.concatenate([dense[:200_000], sparse[:100_000], [MAX]]).astype(np.uint32))
+    for vals in (dense, sparse, mix):
+        qs = np.concatenate([gen_queries(600_000, seed=93, vals=vals), rng.integers(1 << 20, (1 << 20) + (1 << 22), 600_000).astype(np.uint32),
+                             np.array([0x80000000, 0xFFFFFFFF, 0, MAX], np.uint32)])
+        ev, ei = oracle.lower_bound(vals, qs)
+        for lm, rev, full in FLAG_SETS:
+            ot = oracle.Tree.stree(vals, left_max=lm, reverse=rev, full=full)
+            t = sst.STree16.new_params(vals, bool(lm), bool(rev), bool(full))
+            v, i = t.query(qs, sst.SCHEME_TABLE, want_index=True)
+            assert np.array_equal(v, ot.search(qs)), (lm, rev, full)   # incl. the signed-compare quirk for q >= 2^31
+            assert np.array_equal(v[:-4], ev[:-4]) and np.array_equal(i[:-4], ei[:-4]), (lm, rev, full)
+
+
 def test_binary_search_baseline(gpu, oracle):
     """SortedVec::binary_search (binary_search.rs:36-49) as a GPU baseline kernel."""
     sst = gpu

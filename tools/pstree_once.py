@@ -15,5 +15,5 @@ cls = {"map": sst.PartitionedSTree16M, "compact": sst.PartitionedSTree16C, "l1":
 for name in os.environ.get("LAYOUT", "compact,simple").split(","):
     t = cls[name].new(keys, 20)
     ms = L.sst_time_query_device(t._h, C.c_void_p(qs.data_ptr()), nq, C.c_void_p(out.data_ptr()), None, 0, 1, 2)
-    print(name, t.params, t.layers(), round(t.size() / 2**20), "MB", round(nq / ms / 1e6, 2), "Gq/s", flush=True)
+    print(name, round(nq / ms / 1e6, 2), "Gq/s", t.layers(), "layers", round(t.size() / 2**20), "MB", flush=True)
     del t
