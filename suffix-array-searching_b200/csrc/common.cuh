@@ -63,6 +63,11 @@ struct SstTreeView {
     // sorted-array index of record for the partitioned layouts
     const uint32_t* part_start;                    // [parts + 1] index of each part's first key
     const unsigned long long* part_pos;            // [parts] leaf slot of each part's first key
+    // COMPACT only: dense copy of every part's non-leaf nodes (part p at upper + p * upper_stride slots).
+    // The image interleaves them with the leaves over the whole allocation, which costs a TLB miss per
+    // level (measured: 13.9 vs 28 Gq/s for the same DRAM traffic); the copy keeps them in a few pages.
+    const uint32_t* upper;
+    unsigned long long upper_stride;
 };
 
 struct sst_index {
@@ -84,6 +89,7 @@ struct sst_index {
     size_t prefix_map_len = 0;
     uint32_t* d_part_start = nullptr;             // [parts + 1]
     unsigned long long* d_part_pos = nullptr;     // [parts]
+    uint32_t* d_upper = nullptr;                  // COMPACT: dense copy of the non-leaf nodes of every part
     size_t l1_field = 0;                          // the `l1` struct field (max(l1,16) for OL)
     // shared-memory rank table replacing levels [0, top_level) of the plain B=16 tree
     int top_level = 0;

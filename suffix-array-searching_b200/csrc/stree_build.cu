@@ -421,6 +421,19 @@ __global__ void ps_prefix_map_kernel(const uint32_t* __restrict__ tree, PartShap
     }
 }
 
+// COMPACT: gather the first `upper_nodes` nodes (all non-leaf levels) of every part into a dense array.
+__global__ void compact_upper_kernel(const uint32_t* __restrict__ tree, unsigned long long parts, unsigned long long bpp,
+                                     unsigned long long upper_nodes, uint32_t* __restrict__ upper) {
+    const unsigned long long total = parts * upper_nodes * 4;  // in 16-byte chunks
+    const uint4* src = reinterpret_cast<const uint4*>(tree);
+    uint4* dst = reinterpret_cast<uint4*>(upper);
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long part = t / (upper_nodes * 4), r = t % (upper_nodes * 4);
+        dst[t] = src[part * bpp * 4 + r];
+    }
+}
+
 // partitioned_s_tree.rs:200-227
 bool max_overlap(const std::vector<size_t>& buckets, size_t subtree_size, size_t* out) {
     if (buckets.size() == 1) {
@@ -456,6 +469,7 @@ void free_index(sst_index* idx) {
     cudaFree(idx->d_prefix_map);
     cudaFree(idx->d_part_start);
     cudaFree(idx->d_part_pos);
+    cudaFree(idx->d_upper);
     cudaFree(idx->d_top_table);
     cudaFree(idx->d_top_low);
     cudaFree(idx->d_c5);
@@ -751,6 +765,12 @@ sst_index* build_partitioned(const uint32_t* d_sorted, size_t n, uint32_t b, int
             }
         }
         if (ok) fill_kernel<<<1, 16, 0, st>>>(idx->d_tree + n_blocks * 16, 16, kMax);
+        if (ok && COMPACT && H > 1) {
+            const size_t upper_nodes = idx->offsets[H - 1];
+            ok = SST_CUDA_OK(cudaMalloc(&idx->d_upper, parts * upper_nodes * 64));
+            if (ok) compact_upper_kernel<<<std::min(grid_for(parts * upper_nodes * 4), maxgrid), kBuildThreads, 0, st>>>(
+                        idx->d_tree, parts, idx->bpp, upper_nodes, idx->d_upper);
+        }
         ok = ok && SST_CUDA_OK(cudaGetLastError()) && SST_CUDA_OK(cudaStreamSynchronize(st));
     }
     cudaFree(d_ne_pos); cudaFree(d_ne_start); cudaFree(d_ne_cnt);
@@ -785,6 +805,8 @@ void finalize_view(sst_index* idx) {
             v.start_mul = 0;
             v.part_stride = (unsigned long long)idx->bpp * 16;
             v.leaf_slots = (unsigned long long)idx->layer_sizes[H - 1] * 16;
+            v.upper = idx->d_upper;
+            v.upper_stride = (unsigned long long)idx->offsets[H - 1] * 16;
             break;
         case SST_L1: v.start_mul = 16; v.mult[0] = (uint32_t)idx->l1_field; break;       // :745-759
         case SST_OVERLAPPING: v.start_mul = (uint32_t)(16 - idx->overlap); v.mult[0] = (uint32_t)idx->l1_field; break;  // :795-810

@@ -423,8 +423,10 @@ stree_search_generic(const __grid_constant__ SstTreeView v, const uint32_t* __re
                 default: s = part * v.start_mul; break;
             }
             const int L = v.levels;
+            const bool dense_upper = v.variant == SST_COMPACT && v.upper != nullptr;
+            const uint32_t* ub = dense_upper ? v.upper + part * v.upper_stride : v.tree + pb;
             for (int h = 0; h + 1 < L; h++) {
-                const unsigned c = count16(v.tree + v.level_slot[h] + pb + s, q);
+                const unsigned c = count16(ub + v.level_slot[h] + s, q);
                 s = s * v.mult[h] + 16ull * c;
             }
             const uint32_t* leaf = v.tree + v.level_slot[L - 1] + pb;
@@ -528,8 +530,8 @@ pstree_search_group(const __grid_constant__ SstTreeView v, const uint32_t* __res
             else s0 = part * v.start_mul;
             sown[t] = s0;
         }
-        uint32_t q[D];
-        unsigned long long s[D], pb[D];
+        uint32_t q[D], cpart[D];  // cpart: part index for COMPACT (0 otherwise)
+        unsigned long long s[D];
         bool live[D];
 #pragma unroll
         for (int d = 0; d < D; d++) {
@@ -537,20 +539,23 @@ pstree_search_group(const __grid_constant__ SstTreeView v, const uint32_t* __res
             const unsigned long long s0 = __shfl_sync(kFull, sown[d / G], gbase + (d % G));
             live[d] = s0 != ~0ull;
             s[d] = live[d] ? s0 : 0ull;
-            pb[d] = (v.variant == SST_COMPACT && live[d]) ? (unsigned long long)(q[d] >> v.shift) * v.part_stride : 0ull;
+            cpart[d] = (v.variant == SST_COMPACT && live[d]) ? (q[d] >> v.shift) : 0u;
         }
+        // COMPACT reads its non-leaf levels from the dense copy (a few pages instead of one page per part)
+        const bool dense_upper = v.variant == SST_COMPACT && v.upper != nullptr;
+        const unsigned long long ustride = dense_upper ? v.upper_stride : v.part_stride;
         for (int h = 0; h + 1 < L; h++) {
             Keys<W> ks[D];
-            const uint32_t* gl = v.tree + v.level_slot[h] + sub * W;
+            const uint32_t* gl = (dense_upper ? v.upper : v.tree) + v.level_slot[h] + sub * W;
 #pragma unroll
-            for (int d = 0; d < D; d++) ks[d] = ldg_window8<false>(gl + pb[d] + s[d], pol_inner);
+            for (int d = 0; d < D; d++) ks[d] = ldg_window8<false>(gl + (unsigned long long)cpart[d] * ustride + s[d], pol_inner);
 #pragma unroll
             for (int d = 0; d < D; d++) s[d] = s[d] * v.mult[h] + 16ull * group_count<G>(ks[d], q[d], gbase);
         }
         const uint32_t* gl = v.tree + v.level_slot[L - 1];
         Keys<W> ks[D];
 #pragma unroll
-        for (int d = 0; d < D; d++) ks[d] = ldg_window8<true>(gl + pb[d] + s[d] + sub * W, pol_leaf);
+        for (int d = 0; d < D; d++) ks[d] = ldg_window8<true>(gl + (unsigned long long)cpart[d] * v.part_stride + s[d] + sub * W, pol_leaf);
         uint32_t myval[T];
         unsigned long long mypos[T];
 #pragma unroll
@@ -559,7 +564,7 @@ pstree_search_group(const __grid_constant__ SstTreeView v, const uint32_t* __res
             const uint32_t cand = pick<W>(ks[d], c % W);
             uint32_t val = __shfl_sync(kFull, cand, gbase + (c < 16u ? c / W : 0u));
             const unsigned long long pos = s[d] + c;  // flat slot in the leaf level (of this part for Compact)
-            if (c == 16u) val = pos < v.leaf_slots ? __ldg(gl + pb[d] + pos) : kMax;
+            if (c == 16u) val = pos < v.leaf_slots ? __ldg(gl + (unsigned long long)cpart[d] * v.part_stride + pos) : kMax;
             if (!live[d]) val = kMax;
             if (sub == (unsigned)(d % G)) { myval[d / G] = val; mypos[d / G] = pos; }
         }
