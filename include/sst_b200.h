@@ -148,6 +148,21 @@ int sst_sa_search(const sst_sa_t* sa, const uint8_t* pats, const uint64_t* pat_o
 int sst_sa_search_device(const sst_sa_t* sa, const uint8_t* d_pats, const uint64_t* d_pat_off, size_t npat, int mode,
                          uint32_t* d_out_lo, uint32_t* d_out_hi, uint32_t* d_out_pos, void* stream);
 
+/* ---- input data formats (the callers' side of the path) --------------------------------------
+ * sst_fasta_encode: FASTA text -> one byte per base in 0..3, replaces read_fasta_file
+ *   (sas/util.rs:144-169: headers dropped, line ends stripped, A/C/G/T in either case -> 0..3, every
+ *   other byte -> 0).  out_codes needs room for `len` bytes; *out_len receives the number of bases.
+ * sst_kmer_keys: the `--human` key mode of the bench harness (sst/bin/bench.rs:60-76): key i is the
+ *   2-bit pack of codes[i..i+k) (first base most significant) masked to 31 bits, key 0 is SST_MAX;
+ *   count = min(n - k + 1, max_keys).  sort != 0 also sorts them (bench.rs:89) so that they can go
+ *   straight into sst_stree_build_device. */
+int sst_fasta_encode(const char* fasta, size_t len, uint8_t* out_codes, size_t* out_len, int device);
+int sst_fasta_encode_device(const char* d_fasta, size_t len, uint8_t* d_out_codes, size_t* out_len, int device);
+int sst_kmer_keys(const uint8_t* codes, size_t n, uint32_t k, size_t max_keys, uint32_t* out_keys, size_t* out_count, int sort,
+                  int device);
+int sst_kmer_keys_device(const uint8_t* d_codes, size_t n, uint32_t k, size_t max_keys, uint32_t* d_out_keys, size_t* out_count,
+                         int sort, int device);
+
 /* ---- multi-GPU: index replicated per device, query batch sharded contiguously
  *      (chunk = ceil(nq / G), the rule of sst/bin/bench.rs:558-573), one host thread and one
  *      stream per device, no collective. */

@@ -265,3 +265,46 @@ def sa_search_batch32(text, sa, flat, off, threads=1):
     pos = np.empty(npat, np.uint32)
     secs = lib().orc_sa_search_batch32(_p(text), text.size, _p(sa), _p(flat), _p(off), npat, _p(lo), _p(pos), threads)
     return lo, pos, secs
+
+
+# ----------------------------------------------------------------------------------------------
+# input formats (pure Python / numpy restatements)
+# ----------------------------------------------------------------------------------------------
+def read_fasta(data: bytes) -> np.ndarray:
+    """suffix-array-searching/src/util.rs:144-169 read_fasta_file: needletail FASTA records (a header line
+    starts with '>', sequence lines are concatenated with line ends stripped); map[] sends A/C/G/T in either
+    case to 0..3 and every other byte to 0."""
+    m = np.zeros(256, np.uint8)
+    for ch, v in ((b"A", 0), (b"C", 1), (b"G", 2), (b"T", 3), (b"a", 0), (b"c", 1), (b"g", 2), (b"t", 3)):
+        m[ch[0]] = v
+    out = []
+    for line in data.split(b"\n"):
+        if line.startswith(b">"):
+            continue
+        line = line.replace(b"\r", b"")
+        if line:
+            out.append(m[np.frombuffer(line, np.uint8)])
+    return np.concatenate(out) if out else np.zeros(0, np.uint8)
+
+
+def kmer_keys(codes, k=16, max_keys=None, sort=True) -> np.ndarray:
+    """static-search-tree/src/bin/bench.rs:60-76 (--human): rolling 2-bit pack of k bases masked to 2k bits
+    and to i32::MAX; vals[0] = MAX; then bench.rs:89 sorts."""
+    codes = np.asarray(codes, np.uint8)
+    n = codes.size
+    if n < k:
+        return np.zeros(0, np.uint32)
+    count = n - k + 1 if max_keys is None else min(n - k + 1, max_keys)
+    vals = np.empty(count, np.uint32)
+    key = 0
+    for i in range(k - 1):
+        key = (key << 2) | int(codes[i])
+    mask = (1 << (2 * k)) - 1
+    for i in range(k - 1, k - 1 + count):
+        key = ((key << 2) | int(codes[i])) & mask
+        vals[i - (k - 1)] = key & MAX
+    if count:
+        vals[0] = MAX
+    if sort:
+        vals.sort()
+    return vals

@@ -86,6 +86,10 @@ def lib() -> C.CDLL:
         "sst_sa_check": (i32, [vp, vp]),
         "sst_sa_search": (i32, [vp, vp, vp, sz, i32, vp, vp, vp]),
         "sst_sa_search_device": (i32, [vp, vp, vp, sz, i32, vp, vp, vp, vp]),
+        "sst_fasta_encode": (i32, [vp, sz, vp, vp, i32]),
+        "sst_fasta_encode_device": (i32, [vp, sz, vp, vp, i32]),
+        "sst_kmer_keys": (i32, [vp, sz, u32, sz, vp, vp, i32, i32]),
+        "sst_kmer_keys_device": (i32, [vp, sz, u32, sz, vp, vp, i32, i32]),
         "sst_multi_stree_build": (vp, [vp, sz, u32, u32, vp, i32]),
         "sst_multi_pstree_build": (vp, [vp, sz, u32, i32, vp, i32]),
         "sst_multi_query": (i32, [vp, vp, sz, vp, vp, i32]),
@@ -332,6 +336,33 @@ class PartitionedSTree16O(PartitionedSTree):
 
 class PartitionedSTree16M(PartitionedSTree):
     VARIANT = MAP
+
+
+# ----------------------------------------------------------------------------------------------
+# input formats: read_fasta_file (sas/util.rs:144-169) and the --human k-mer keys (sst/bin/bench.rs:60-76)
+# ----------------------------------------------------------------------------------------------
+def read_fasta(data: bytes, device=0) -> np.ndarray:
+    """FASTA text -> uint8 codes 0..3 (headers dropped, line ends stripped, non-ACGT -> 0)."""
+    buf = np.frombuffer(data, np.uint8)
+    out = np.empty(max(buf.size, 1), np.uint8)
+    n = C.c_size_t(0)
+    _check(lib().sst_fasta_encode(_ptr(buf) if buf.size else None, buf.size, _ptr(out), C.byref(n), device))
+    return out[: n.value].copy()
+
+
+def read_fasta_file(path, device=0) -> np.ndarray:
+    with open(path, "rb") as f:
+        return read_fasta(f.read(), device)
+
+
+def kmer_keys(codes, k=16, max_keys=None, sort=True, device=0) -> np.ndarray:
+    """bench.rs:60-76: 31-bit k-mer keys of a 2-bit coded sequence, keys[0] = MAX, optionally sorted."""
+    c = np.ascontiguousarray(codes, np.uint8)
+    cap = max(c.size - k + 1, 0) if max_keys is None else min(max(c.size - k + 1, 0), max_keys)
+    out = np.empty(max(cap, 1), np.uint32)
+    n = C.c_size_t(0)
+    _check(lib().sst_kmer_keys(_ptr(c), c.size, k, cap if max_keys is None else max_keys, _ptr(out), C.byref(n), int(sort), device))
+    return out[: n.value].copy()
 
 
 # ----------------------------------------------------------------------------------------------

@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--range", action="store_true")
     ap.add_argument("--positive", action="store_true")
     ap.add_argument("--dense", action="store_true")
+    ap.add_argument("--human", metavar="FASTA", help="keys = 16-mers of this FASTA file (bench.rs:60-76) instead of random keys")
     ap.add_argument("--out", default=os.path.join(ROOT, "results", "gpu-results.json"))
     a = ap.parse_args()
     L = sst.lib()
@@ -48,8 +49,17 @@ def main():
     for run in range(a.runs):
         g = torch.Generator(device=dev).manual_seed(100 + run)
         big = sizes(a.lo, a.hi, a.dense)[-1] // 4
-        vals_all = torch.randint(0, MAX, (big,), dtype=torch.int32, device=dev, generator=g)  # util.rs:31-42
-        vals_all[0] = MAX
+        if a.human:  # bench.rs:60-76: rolling 16-mers of the genome, unsorted here (each size sorts its prefix)
+            import numpy as np
+
+            codes = sst.read_fasta_file(a.human)
+            keys = sst.kmer_keys(codes, k=16, max_keys=big, sort=False)
+            if keys.size < big:
+                raise SystemExit(f"{a.human}: only {keys.size} k-mers, need {big} for --to {a.hi}")
+            vals_all = torch.from_numpy(keys.view(np.int32)).to(dev)
+        else:
+            vals_all = torch.randint(0, MAX, (big,), dtype=torch.int32, device=dev, generator=g)  # util.rs:31-42
+            vals_all[0] = MAX
         for size in sizes(a.lo, a.hi, a.dense):
             n = size // 4
             vals = torch.sort(vals_all[:n]).values.contiguous()
