@@ -353,7 +353,21 @@ def run_own(args):
         b_.record()
         torch.cuda.synchronize()
         baselines = {"gpu_binary_search_queries_per_s": nb / (a_.elapsed_time(b_) * 1e-3),
-                     "note": "SortedVec::binary_search (binary_search.rs:36-49) as a thread-per-query kernel on the same B200"}
+                     "note": "SortedVec::binary_search (binary_search.rs:36-49) and Eytzinger::search (eytzinger.rs:82-89) as thread-per-query kernels on the same B200"}
+        try:
+            ey = sst.Eytzinger.new(keys)
+            for it in range(2):
+                if it == 1:
+                    a_.record()
+                rc = L.sst_query_device(ey._h, C.c_void_p(batches[0].data_ptr()), nb, C.c_void_p(out_v.data_ptr()), None, 0, stream)
+                if rc != 0:
+                    raise RuntimeError(L.sst_last_error().decode())
+            b_.record()
+            torch.cuda.synchronize()
+            baselines["gpu_eytzinger_queries_per_s"] = nb / (a_.elapsed_time(b_) * 1e-3)
+            del ey
+        except Exception as ex:
+            baselines["gpu_eytzinger_error"] = repr(ex)
 
     # ---- optional secondary metric: suffix-array patterns/s (config C3) ----
     sa_info = None

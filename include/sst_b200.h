@@ -52,7 +52,8 @@ enum {
 enum { SST_LEFT_MAX = 1, SST_REVERSE_STORAGE = 2, SST_FULL_ARRAY = 4 };
 
 /* PartitionedSTree layouts (sst/partitioned_s_tree.rs:34-98) */
-enum { SST_PLAIN = 0, SST_SIMPLE = 1, SST_COMPACT = 2, SST_L1 = 3, SST_OVERLAPPING = 4, SST_MAP = 5 };
+enum { SST_PLAIN = 0, SST_SIMPLE = 1, SST_COMPACT = 2, SST_L1 = 3, SST_OVERLAPPING = 4, SST_MAP = 5,
+       SST_EYTZINGER = 6 /* baseline layout of sst/eytzinger.rs, built by sst_eytzinger_build */ };
 
 /* search schemes (kernel variants) selectable per query call, like the reference's many
  * SearchScheme closures over one index (sst/bin/bench.rs:93-96).  All return identical results. */
@@ -97,6 +98,12 @@ sst_index_t* sst_stree_build_device(const uint32_t* d_sorted, size_t n, uint32_t
 sst_index_t* sst_pstree_build(const uint32_t* sorted, size_t n, uint32_t b, int variant, int device);
 sst_index_t* sst_pstree_build_device(const uint32_t* d_sorted, size_t n, uint32_t b, int variant, int device);
 
+/* ---- Eytzinger baseline: replaces Eytzinger::new + search (sst/eytzinger.rs:37-89).  One-based BFS layout of
+ *      the sorted keys with element 0 = u32::MAX; UNSIGNED compares; a query above every key returns
+ *      0xffffffff (eytzinger.rs:222-229) and index n.  Image = n + 1 words (sst_index_image_words). */
+sst_index_t* sst_eytzinger_build(const uint32_t* sorted, size_t n, int device);
+sst_index_t* sst_eytzinger_build_device(const uint32_t* d_sorted, size_t n, int device);
+
 void sst_index_free(sst_index_t* idx);
 
 /* SearchIndex::size (bytes) and ::layers (sst/lib.rs:35-40; s_tree.rs:52-58; partitioned_s_tree.rs:100-107) */
@@ -111,7 +118,8 @@ int sst_index_variant(const sst_index_t* idx);
 size_t sst_index_nodes(const sst_index_t* idx);                  /* tree.len() */
 size_t sst_index_levels(const sst_index_t* idx);                 /* offsets.len() */
 int sst_index_offsets(const sst_index_t* idx, uint64_t* out);     /* out[levels], node units */
-int sst_index_image(const sst_index_t* idx, uint32_t* out);       /* out[nodes*16], device -> host */
+size_t sst_index_image_words(const sst_index_t* idx);             /* u32 words in the image: nodes*16, or n+1 for Eytzinger */
+int sst_index_image(const sst_index_t* idx, uint32_t* out);       /* out[image_words], device -> host */
 /* out[8] = shift, parts, bpp, l1, overlap, has_overlap, max_bucket, prefix_map_len */
 int sst_index_params(const sst_index_t* idx, uint64_t* out);
 int sst_index_prefix_map(const sst_index_t* idx, uint32_t* out);

@@ -72,6 +72,10 @@ def lib() -> C.CDLL:
         L.orc_sa_search_mlr.argtypes = [vp, sz, vp, vp, vp, sz, vp, vp]
         L.orc_sa_search_batch32.restype = C.c_double
         L.orc_sa_search_batch32.argtypes = [vp, sz, vp, vp, vp, sz, vp, vp, C.c_int]
+        L.orc_eytzinger_build.restype = None
+        L.orc_eytzinger_build.argtypes = [vp, sz, vp]
+        L.orc_eytzinger_search.restype = None
+        L.orc_eytzinger_search.argtypes = [vp, sz, vp, sz, vp]
         L.orc_has_avx2.restype = C.c_int
         _lib = L
     return _lib
@@ -195,6 +199,22 @@ class Tree:
         if secs < 0:
             raise RuntimeError("batch_final needs a plain B=16 tree")
         return ov, secs
+
+
+def eytzinger_build(vals) -> np.ndarray:
+    """sst/src/eytzinger.rs:37-63: one-based BFS layout, element 0 is u32::MAX."""
+    vals = _u32(vals)
+    out = np.empty(vals.size + 1, np.uint32)
+    lib().orc_eytzinger_build(_p(vals), vals.size, _p(out))
+    return out
+
+
+def eytzinger_search(e, qs) -> np.ndarray:
+    """sst/src/eytzinger.rs:82-89."""
+    e, qs = _u32(e), _u32(qs)
+    out = np.empty(qs.size, np.uint32)
+    lib().orc_eytzinger_search(_p(e), e.size, _p(qs), qs.size, _p(out))
+    return out
 
 
 # ----------------------------------------------------------------------------------------------

@@ -42,6 +42,35 @@ bool device_usable(int device);
 
 inline size_t div_ceil(size_t a, size_t b) { return (a + b - 1) / b; }
 
+// Eytzinger layout helpers (shared by the builder and the search kernel): in-order rank of BFS slot k.
+__host__ __device__ inline unsigned long long eytz_subtree_size(unsigned long long k, int depth, unsigned long long n, int H) {
+    // nodes of the subtree rooted at BFS slot k (depth `depth`, root = 0) in a tree of n slots whose last level H is filled from the left
+    if (k > n) return 0;
+    const int below = H - depth;                       // levels below k down to level H
+    const unsigned long long full = (1ull << below) - 1ull;   // k's level .. H-1
+    const unsigned long long first = k << below;       // first slot of k's span on level H
+    unsigned long long last_level = 0;
+    if (first <= n) { last_level = n + 1 - first; const unsigned long long cap = 1ull << below; if (last_level > cap) last_level = cap; }
+    return full + last_level;
+}
+__host__ __device__ inline unsigned long long eytz_rank(unsigned long long k, unsigned long long n, int H) {
+#ifdef __CUDA_ARCH__
+    const int depth = 63 - __clzll((long long)k);
+#else
+    const int depth = 63 - __builtin_clzll(k);
+#endif
+    unsigned long long base = 0, c = 1;
+    for (int b = depth - 1; b >= 0; b--) {
+        const unsigned bit = (unsigned)((k >> b) & 1ull);
+        const int d = depth - 1 - b;                   // depth of c
+        if (bit) base += eytz_subtree_size(2 * c, d + 1, n, H) + 1;
+        c = 2 * c + bit;
+    }
+    return base + eytz_subtree_size(2 * k, depth + 1, n, H);
+}
+
+
+
 }  // namespace sst
 
 // What the search kernels need to know about an index.  Passed by value (__grid_constant__).
@@ -91,6 +120,8 @@ struct sst_index {
     unsigned long long* d_part_pos = nullptr;     // [parts]
     uint32_t* d_upper = nullptr;                  // COMPACT: dense copy of the non-leaf nodes of every part
     size_t l1_field = 0;                          // the `l1` struct field (max(l1,16) for OL)
+    size_t eytz_words = 0;                        // SST_EYTZINGER: n + 1 array entries (entry 0 = u32::MAX)
+    int eytz_h = 0;                               // SST_EYTZINGER: depth of the last level
     // shared-memory rank table replacing levels [0, top_level) of the plain B=16 tree
     int top_level = 0;
     size_t top_nbound = 0;
@@ -108,6 +139,7 @@ namespace sst {
 // builders (stree_build.cu)
 sst_index* build_plain(const uint32_t* d_sorted, bool sorted_is_owned_leaf, size_t n, uint32_t node_b, uint32_t flags, int device);
 sst_index* build_partitioned(const uint32_t* d_sorted, size_t n, uint32_t b, int variant, int device);
+sst_index* build_eytzinger(const uint32_t* d_sorted, size_t n, int device);
 void finalize_view(sst_index* idx);
 bool build_top_table(sst_index* idx, const uint32_t* d_sorted);
 bool build_compressed_level(sst_index* idx);

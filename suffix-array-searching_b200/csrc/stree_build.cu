@@ -779,6 +779,57 @@ sst_index* build_partitioned(const uint32_t* d_sorted, size_t n, uint32_t b, int
     return idx;
 }
 
+// =================================================================================================
+// Eytzinger baseline (eytzinger.rs:37-63).  The reference fills the array by an in-order recursion;
+// here slot k (BFS index) computes its in-order rank in closed form: walk from the root to k and add,
+// at every right turn, the size of the left subtree + 1; finally add the size of k's own left subtree.
+// =================================================================================================
+namespace {
+__global__ void eytzinger_build_kernel(const uint32_t* __restrict__ vals, unsigned long long n, int H, uint32_t* __restrict__ out) {
+    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k <= n; k += (unsigned long long)gridDim.x * blockDim.x)
+        out[k] = k == 0 ? 0xffffffffu : vals[eytz_rank(k, n, H)];
+}
+__global__ void check_sorted_kernel(const uint32_t* __restrict__ v, size_t n, unsigned* __restrict__ flags) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n; i += (size_t)gridDim.x * blockDim.x)
+        if (v[i + 1] < v[i]) atomicOr(flags, 2u);
+}
+}  // namespace
+
+sst_index* build_eytzinger(const uint32_t* d_sorted, size_t n, int device) {
+    clear_error();
+    if (n == 0) { set_error(SST_ERR_ARG, "empty input"); return nullptr; }
+    if (n >= ((size_t)1 << 32) - 1) { set_error(SST_ERR_UNSUPPORTED, "n must be < 2^32 - 1"); return nullptr; }
+    if (!device_usable(device)) { set_error(SST_ERR_CUDA, "device is not an sm_100 GPU (no CPU fallback)"); return nullptr; }
+    DeviceGuard guard(device);
+    if (!guard.ok) return nullptr;
+    cudaStream_t st = thread_stream(device);
+    unsigned* d_flags = nullptr;
+    unsigned flags = 0;
+    bool ok = SST_CUDA_OK(cudaMalloc(&d_flags, 4)) && SST_CUDA_OK(cudaMemsetAsync(d_flags, 0, 4, st));
+    if (ok) {
+        check_sorted_kernel<<<std::min<unsigned>(grid_for(n), 148 * 16), kBuildThreads, 0, st>>>(d_sorted, n, d_flags);
+        ok = SST_CUDA_OK(cudaMemcpyAsync(&flags, d_flags, 4, cudaMemcpyDeviceToHost, st)) && SST_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    cudaFree(d_flags);
+    if (!ok) return nullptr;
+    if (flags) { set_error(SST_ERR_ARG, "keys are not sorted"); return nullptr; }
+    auto* idx = new sst_index();
+    idx->device = device; idx->variant = SST_EYTZINGER; idx->node_b = 16; idx->n = n;
+    int H = 0;
+    while ((2ull << H) <= n) H++;                       // depth of the last level: floor(log2 n)
+    int lg = 0;
+    while ((2ull << lg) <= n + 1) lg++;
+    idx->levels = lg + 1;                               // layers() = (n + 1).ilog2() + 1 (eytzinger.rs:72-74)
+    idx->n_blocks = div_ceil(n + 1, 16);
+    idx->eytz_words = n + 1;
+    if (!SST_CUDA_OK(cudaMalloc(&idx->d_tree, (idx->n_blocks + 1) * 64))) { delete idx; return nullptr; }
+    eytzinger_build_kernel<<<std::min<unsigned>(grid_for(n + 1), 148 * 32), kBuildThreads, 0, st>>>(d_sorted, n, H, idx->d_tree);
+    if (!SST_CUDA_OK(cudaGetLastError()) || !SST_CUDA_OK(cudaStreamSynchronize(st))) { cudaFree(idx->d_tree); delete idx; return nullptr; }
+    idx->eytz_h = H;
+    finalize_view(idx);
+    return idx;
+}
+
 void finalize_view(sst_index* idx) {
     SstTreeView& v = idx->view;
     v = SstTreeView{};
@@ -793,11 +844,18 @@ void finalize_view(sst_index* idx) {
     v.part_start = idx->d_part_start;
     v.part_pos = idx->d_part_pos;
     const int H = idx->levels;
-    for (int h = 0; h < H; h++) {
-        v.level_slot[h] = (unsigned long long)idx->offsets[h] * 16;
-        v.mult[h] = idx->node_b + 1;
+    if (idx->variant != SST_EYTZINGER) {
+        for (int h = 0; h < H; h++) {
+            v.level_slot[h] = (unsigned long long)idx->offsets[h] * 16;
+            v.mult[h] = idx->node_b + 1;
+        }
+        v.leaf_slots = (unsigned long long)idx->layer_blocks[H - 1] * 16;
     }
-    v.leaf_slots = (unsigned long long)idx->layer_blocks[H - 1] * 16;
+    if (idx->variant == SST_EYTZINGER) {  // not a node tree: the view only carries the array
+        v.levels = 1;
+        v.leaf_slots = idx->eytz_words;
+        return;
+    }
     switch (idx->variant) {
         case SST_PLAIN: v.start_mul = 0; break;
         case SST_SIMPLE: v.start_mul = 16; break;                                       // partitioned_s_tree.rs:664-665
@@ -879,6 +937,22 @@ sst_index_t* sst_pstree_build(const uint32_t* sorted, size_t n, uint32_t b, int 
     return idx;
 }
 
+sst_index_t* sst_eytzinger_build_device(const uint32_t* d_sorted, size_t n, int device) {
+    clear_error();
+    if (!sync_device(device)) return nullptr;
+    return build_eytzinger(d_sorted, n, device);
+}
+
+sst_index_t* sst_eytzinger_build(const uint32_t* sorted, size_t n, int device) {
+    clear_error();
+    if (n == 0 || !sorted) { set_error(SST_ERR_ARG, "empty input"); return nullptr; }
+    uint32_t* d = upload_keys(sorted, n, device);
+    if (!d) return nullptr;
+    sst_index* idx = build_eytzinger(d, n, device);
+    { DeviceGuard g(device); cudaFree(d); }
+    return idx;
+}
+
 void sst_index_free(sst_index_t* idx) {
     if (!idx) return;
     DeviceGuard g(idx->device);
@@ -886,7 +960,15 @@ void sst_index_free(sst_index_t* idx) {
 }
 
 // SearchIndex::size: s_tree.rs:56-58, partitioned_s_tree.rs:101-103
-size_t sst_index_size_bytes(const sst_index_t* idx) { return idx ? idx->n_blocks * 64 + idx->prefix_map_len * 4 : 0; }
+size_t sst_index_size_bytes(const sst_index_t* idx) {
+    if (!idx) return 0;
+    if (idx->variant == SST_EYTZINGER) return idx->eytz_words * 4;  // eytzinger.rs:76-78
+    return idx->n_blocks * 64 + idx->prefix_map_len * 4;
+}
+size_t sst_index_image_words(const sst_index_t* idx) {
+    if (!idx) return 0;
+    return idx->variant == SST_EYTZINGER ? idx->eytz_words : idx->n_blocks * 16;
+}
 // SearchIndex::layers: s_tree.rs:52-54, partitioned_s_tree.rs:105-107
 size_t sst_index_layers(const sst_index_t* idx) { return idx ? (size_t)idx->levels + (idx->variant == SST_MAP ? 1 : 0) : 0; }
 size_t sst_index_len(const sst_index_t* idx) { return idx ? idx->n : 0; }
@@ -905,7 +987,7 @@ int sst_index_image(const sst_index_t* idx, uint32_t* out) {
     if (!idx || !out) { set_error(SST_ERR_ARG, "null argument"); return SST_ERR_ARG; }
     DeviceGuard g(idx->device);
     if (!g.ok) return SST_ERR_CUDA;
-    return SST_CUDA_OK(cudaMemcpy(out, idx->d_tree, idx->n_blocks * 64, cudaMemcpyDeviceToHost)) ? SST_OK : SST_ERR_CUDA;
+    return SST_CUDA_OK(cudaMemcpy(out, idx->d_tree, sst_index_image_words(idx) * 4, cudaMemcpyDeviceToHost)) ? SST_OK : SST_ERR_CUDA;
 }
 
 int sst_index_params(const sst_index_t* idx, uint64_t* out) {

@@ -479,6 +479,22 @@ binary_search_kernel(const uint32_t* __restrict__ vals, unsigned long long n, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// Baseline: Eytzinger::search (eytzinger.rs:82-89), one thread per query, unsigned compares.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+eytzinger_search_kernel(const uint32_t* __restrict__ e, unsigned long long len, int H, const uint32_t* __restrict__ qs, size_t nq,
+                        uint32_t* __restrict__ out_vals, unsigned long long* __restrict__ out_idx) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t q = qs[i];
+        unsigned long long idx = 1;
+        while (idx < len) idx = 2 * idx + (q > __ldg(e + idx) ? 1ull : 0ull);
+        idx >>= (__ffsll(~(long long)idx));  // search_result_to_index: drop the trailing ones and one more bit
+        out_vals[i] = __ldg(e + idx);
+        if (out_idx) out_idx[i] = idx ? eytz_rank(idx, len - 1, H) : len - 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Lane-group kernel for the partitioned layouts (Simple, Compact, L1, Overlapping, Map; B = 16):
 // the descent of partitioned_s_tree.rs:654-880 with 2 lanes x 32 B per node like the fast kernel.
 // Positions are kept in slots (4 B) so that the unaligned root windows of Overlapping / Map
@@ -745,6 +761,15 @@ int query_launch_count(const sst_index*, int) { return 1; }
 int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx,
                  int scheme, cudaStream_t st) {
     if (nq == 0) return SST_OK;
+    if (idx->variant == SST_EYTZINGER) {
+        if (scheme != SST_SCHEME_AUTO && scheme != SST_SCHEME_GENERIC) {
+            set_error(SST_ERR_UNSUPPORTED, "the Eytzinger baseline has one kernel; use SST_SCHEME_AUTO");
+            return SST_ERR_UNSUPPORTED;
+        }
+        const int grid = (int)std::min<size_t>(div_ceil(nq, 256), (size_t)sm_count(idx->device) * 8);
+        eytzinger_search_kernel<<<grid, 256, 0, st>>>(idx->d_tree, idx->eytz_words, idx->eytz_h, d_qs, nq, d_vals, d_idx);
+        return SST_CUDA_OK(cudaGetLastError()) ? SST_OK : SST_ERR_CUDA;
+    }
     if (scheme == SST_SCHEME_AUTO && idx->variant != SST_PLAIN && idx->node_b == 16 && env_int("SST_PGROUP", 1)) {
         const int sms = sm_count(idx->device);
         const int T = env_int("SST_PT", 1);  // measured: T=1 27.7 vs T=2 23.9 Gq/s (Simple, 2^28 keys)

@@ -24,7 +24,7 @@ import numpy as np
 MAX = 0x7FFFFFFF
 
 LEFT_MAX, REVERSE_STORAGE, FULL_ARRAY = 1, 2, 4
-PLAIN, SIMPLE, COMPACT, L1, OVERLAPPING, MAP = 0, 1, 2, 3, 4, 5
+PLAIN, SIMPLE, COMPACT, L1, OVERLAPPING, MAP, EYTZINGER = 0, 1, 2, 3, 4, 5, 6
 SCHEME_AUTO, SCHEME_GROUP4, SCHEME_GROUP16, SCHEME_GROUP2, SCHEME_GENERIC, SCHEME_TABLE, SCHEME_BINSEARCH = 0, 1, 2, 3, 4, 5, 6
 SA_BINARY, SA_MLR = 0, 1
 ERR_CUDA, ERR_ARG, ERR_CAPACITY, ERR_UNSUPPORTED = 1, 2, 3, 4
@@ -62,6 +62,9 @@ def lib() -> C.CDLL:
         "sst_stree_build_device": (vp, [vp, sz, u32, u32, i32]),
         "sst_pstree_build": (vp, [vp, sz, u32, i32, i32]),
         "sst_pstree_build_device": (vp, [vp, sz, u32, i32, i32]),
+        "sst_eytzinger_build": (vp, [vp, sz, i32]),
+        "sst_eytzinger_build_device": (vp, [vp, sz, i32]),
+        "sst_index_image_words": (sz, [vp]),
         "sst_index_free": (None, [vp]),
         "sst_index_size_bytes": (sz, [vp]),
         "sst_index_layers": (sz, [vp]),
@@ -202,7 +205,7 @@ class SearchIndex:
         return out
 
     def image(self) -> np.ndarray:
-        out = np.empty(lib().sst_index_nodes(self._h) * 16, np.uint32)
+        out = np.empty(lib().sst_index_image_words(self._h), np.uint32)
         _check(lib().sst_index_image(self._h, _ptr(out)))
         return out
 
@@ -292,6 +295,18 @@ class STree16(STree):
 
 class STree15(STree):
     B = 15
+
+
+class Eytzinger(SearchIndex):
+    """Eytzinger (static-search-tree/src/eytzinger.rs:9-78): baseline layout, unsigned compares,
+    a query above every key returns 0xffffffff."""
+
+    def __init__(self, vals, device=0):
+        super().__init__(_build("sst_eytzinger_build", "sst_eytzinger_build_device", vals, device=device))
+
+    @classmethod
+    def new(cls, vals, device=0):
+        return cls(vals, device=device)
 
 
 class PartitionedSTree(SearchIndex):
