@@ -107,6 +107,36 @@ using PartitionedSTree16L = PartitionedSTree<SST_L1>;
 using PartitionedSTree16O = PartitionedSTree<SST_OVERLAPPING>;
 using PartitionedSTree16M = PartitionedSTree<SST_MAP>;
 
+/// Eytzinger (eytzinger.rs:9-89): baseline layout; unsigned compares; 0xffffffff when q is above every key
+class Eytzinger : public SearchIndex {
+  public:
+    static Eytzinger new_(const std::vector<uint32_t>& vals, int device = 0) { return Eytzinger(sst_eytzinger_build(vals.data(), vals.size(), device)); }
+    std::vector<uint32_t> vals() const {  // the `vals` field: n + 1 entries, entry 0 = u32::MAX
+        std::vector<uint32_t> out(sst_index_image_words(h_.get()));
+        check(sst_index_image(h_.get(), out.data()));
+        return out;
+    }
+
+  private:
+    explicit Eytzinger(sst_index_t* h) : SearchIndex(h) {}
+};
+
+/// read_fasta_file's decoding (sas/util.rs:144-169) and the --human k-mer keys (sst/bin/bench.rs:60-76)
+inline std::vector<uint8_t> read_fasta(const std::string& fasta, int device = 0) {
+    std::vector<uint8_t> out(fasta.size() ? fasta.size() : 1);
+    size_t n = 0;
+    check(sst_fasta_encode(fasta.data(), fasta.size(), out.data(), &n, device));
+    out.resize(n);
+    return out;
+}
+inline std::vector<uint32_t> kmer_keys(const std::vector<uint8_t>& codes, uint32_t k = 16, bool sort = true, int device = 0) {
+    std::vector<uint32_t> out(codes.size() >= k ? codes.size() - k + 1 : 1);
+    size_t n = 0;
+    check(sst_kmer_keys(codes.data(), codes.size(), k, out.size(), out.data(), &n, sort ? 1 : 0, device));
+    out.resize(n);
+    return out;
+}
+
 /// trait SearchScheme<I> + adapters (lib.rs:51-107)
 template <class I>
 struct SearchScheme {

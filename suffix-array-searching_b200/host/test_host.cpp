@@ -79,6 +79,23 @@ int main() {
         for (int k = 1; k < 4; k++) EXPECT(outs[k] == outs[0]);
         EXPECT(MultiIndex::stree(vals, {0, 0}, true).query(qs) == outs[0]);
     }
+    {   // eytzinger.rs:199-229 golden vectors
+        std::vector<uint32_t> in15, in10;
+        for (uint32_t i = 1; i <= 15; i++) in15.push_back(i);
+        for (uint32_t i = 0; i < 10; i++) in10.push_back(i);
+        const uint32_t M = 0xffffffffu;
+        EXPECT((Eytzinger::new_(in15).vals() == std::vector<uint32_t>{M, 8, 4, 12, 2, 6, 10, 14, 1, 3, 5, 7, 9, 11, 13, 15}));
+        auto e = Eytzinger::new_(in10);
+        EXPECT((e.vals() == std::vector<uint32_t>{M, 6, 3, 8, 1, 5, 7, 9, 0, 2, 4}));
+        EXPECT(e.search(3) == 3 && e.search(12) == M);
+    }
+    {   // read_fasta_file + --human keys feeding the tree
+        auto codes = read_fasta(">r1 x\nACGT\nacgtN\n>r2\nTT\n");
+        EXPECT((codes == std::vector<uint8_t>{0, 1, 2, 3, 0, 1, 2, 3, 0, 3, 3}));
+        auto keys = kmer_keys(codes, 3, true);
+        EXPECT(keys.size() == 9 && std::is_sorted(keys.begin(), keys.end()) && keys.back() == MAX);
+        EXPECT(STree16::new_(keys).search(0) == keys[0]);
+    }
     {   // panics of the reference become exceptions
         bool threw = false;
         try { STree16::new_({3, 2, 1}); } catch (const Panic&) { threw = true; }
