@@ -446,6 +446,25 @@ def bench_sa(args, sst, torch, dev):
         else:
             out["mlr_equals_binary"] = bool((lo == ref_lo).all())
     out["sa_check_violations"] = sa.check()
+    # CPU baseline for the same path on this box: oracle port of binary_search_batch::<32> (sa_search.rs:157-196)
+    # on all host threads over a bounded sample of the same patterns; results must equal the GPU's.
+    if not args.no_cpu:
+        try:
+            from oracle import oracle as O
+
+            threads = host_threads()
+            sample = min(npat, args.sa_cpu_sample)
+            h_text = text.cpu().numpy()
+            h_sa = sa.sa
+            h_pats = np.concatenate([pats[: sample * plen].cpu().numpy(), np.zeros(64, np.uint8)])
+            h_off = (np.arange(sample + 1, dtype=np.uint64) * plen)
+            O.sa_search_batch32(h_text, h_sa, h_pats, h_off[: min(sample, 1 << 14) + 1], threads)  # warm-up
+            clo, cpos, secs = O.sa_search_batch32(h_text, h_sa, h_pats, h_off, threads)
+            out["cpu_baseline"] = {"value": sample / secs, "unit": "patterns/s", "cores": threads, "kind": "port",
+                                   "sample": f"first {sample} patterns; oracle binary_search_batch<32> on {threads} threads",
+                                   "equals_gpu": bool((clo == ref_lo[:sample].cpu().numpy().view(np.uint32)).all())}
+        except Exception as ex:
+            out["cpu_baseline"] = {"error": repr(ex)}
     # bytes/pattern = 96*max(0, I-T) + 96 + |q| + 8 with I = ceil(log2(n+1)), T = floor(log2(L2/96))
     import math
     I = math.ceil(math.log2(n + 1))
@@ -505,6 +524,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=20_000_000, help="queries per step of the reference arm")
     ap.add_argument("--sa-text", type=int, default=100_000_000, help="0 disables the secondary SA metric")
     ap.add_argument("--sa-patterns", type=int, default=10_000_000)
+    ap.add_argument("--sa-cpu-sample", type=int, default=2_000_000, help="patterns of the CPU SA baseline sample")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "own":
         args.warmup = 3  # timing rule: W >= 3

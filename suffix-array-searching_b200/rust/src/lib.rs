@@ -28,6 +28,12 @@ extern "C" {
     fn sst_index_size_bytes(idx: *const SstIndex) -> usize;
     fn sst_index_layers(idx: *const SstIndex) -> usize;
     fn sst_query(idx: *const SstIndex, qs: *const u32, nq: usize, out_vals: *mut u32, out_idx: *mut u64, scheme: c_int) -> c_int;
+    fn sst_eytzinger_build(sorted: *const u32, n: usize, device: c_int) -> *mut SstIndex;
+    fn sst_host_alloc(bytes: usize) -> *mut c_void;
+    fn sst_host_free(p: *mut c_void);
+    fn sst_fasta_encode(fasta: *const c_char, len: usize, out_codes: *mut u8, out_len: *mut usize, device: c_int) -> c_int;
+    fn sst_kmer_keys(codes: *const u8, n: usize, k: u32, max_keys: usize, out_keys: *mut u32, out_count: *mut usize,
+                     sort: c_int, device: c_int) -> c_int;
     fn sst_sa_build(text: *const u8, n: usize, device: c_int) -> *mut SstSa;
     fn sst_sa_free(sa: *mut SstSa);
     fn sst_sa_check(sa: *const SstSa, out_violations: *mut u64) -> c_int;
@@ -75,6 +81,52 @@ impl<const B: usize> GpuSTree<B> {
     pub fn search(&self, q: u32) -> u32 { self.0.query(&[q])[0] }
     pub fn batch<const P: usize>(&self, qb: &[u32; P]) -> [u32; P] { self.0.query(qb).try_into().unwrap() }
     pub fn batch_interleave_all_128(&self, qs: &[u32]) -> Vec<u32> { self.0.query(qs) }
+}
+
+/// `Eytzinger` on the GPU (eytzinger.rs:9-89): baseline layout, unsigned compares.
+pub struct GpuEytzinger(pub GpuIndex);
+impl GpuEytzinger {
+    pub fn new(vals: &[u32]) -> Self { Self(GpuIndex::from_raw(unsafe { sst_eytzinger_build(vals.as_ptr(), vals.len(), 0) })) }
+    pub fn search(&self, q: u32) -> u32 { self.0.query(&[q])[0] }
+}
+
+/// Page-locked `u32` buffer (`sst_host_alloc`): lets `GpuIndex::query_into` overlap H2D, kernel and D2H.
+pub struct PinnedU32 { p: *mut u32, len: usize }
+unsafe impl Send for PinnedU32 {}
+impl PinnedU32 {
+    pub fn new(len: usize) -> Self {
+        let p = unsafe { sst_host_alloc(len * 4) } as *mut u32;
+        if p.is_null() { panic!("sst_b200: {}", last_error()); }
+        Self { p, len }
+    }
+    pub fn as_slice(&self) -> &[u32] { unsafe { std::slice::from_raw_parts(self.p, self.len) } }
+    pub fn as_mut_slice(&mut self) -> &mut [u32] { unsafe { std::slice::from_raw_parts_mut(self.p, self.len) } }
+}
+impl Drop for PinnedU32 { fn drop(&mut self) { unsafe { sst_host_free(self.p as *mut c_void) } } }
+impl GpuIndex {
+    /// Like `query`, writing into a caller-provided (ideally pinned) buffer.
+    pub fn query_into(&self, qs: &[u32], out: &mut [u32]) {
+        assert_eq!(qs.len(), out.len());
+        check(unsafe { sst_query(self.h, qs.as_ptr(), qs.len(), out.as_mut_ptr(), std::ptr::null_mut(), 0) });
+    }
+}
+
+/// `read_fasta_file`'s decoding (suffix-array-searching/src/util.rs:144-169) on the GPU.
+pub fn read_fasta(fasta: &[u8]) -> Vec<u8> {
+    let mut out = vec![0u8; fasta.len().max(1)];
+    let mut n = 0usize;
+    check(unsafe { sst_fasta_encode(fasta.as_ptr() as *const c_char, fasta.len(), out.as_mut_ptr(), &mut n, 0) });
+    out.truncate(n);
+    out
+}
+/// The `--human` key mode of bench.rs:60-76 (+ the sort of :89).
+pub fn kmer_keys(codes: &[u8], k: u32, sort: bool) -> Vec<u32> {
+    let cap = codes.len().saturating_sub(k as usize - 1);
+    let mut out = vec![0u32; cap.max(1)];
+    let mut n = 0usize;
+    check(unsafe { sst_kmer_keys(codes.as_ptr(), codes.len(), k, cap, out.as_mut_ptr(), &mut n, sort as c_int, 0) });
+    out.truncate(n);
+    out
 }
 
 /// Marker layouts of partitioned_s_tree.rs:34-81.
@@ -140,5 +192,3 @@ pub fn binary_search(sa: &GpuSa, q: &[u8], cnt: &mut usize) -> usize {
     *cnt += (usize::BITS - 1) as usize;  // probes are not counted on the device
     sa.binary_search_batch(&[q], false)[0]
 }
-#[allow(dead_code)]
-fn _unused(_: *const c_void) {}
