@@ -14,7 +14,7 @@ fn main() {
               "-Xcompiler", "-fPIC", "-shared", "-o"])
         .arg(&lib)
         .arg(format!("-I{}", include.display()));
-    for f in ["runtime.cu", "stree_build.cu", "stree_search.cu", "sa.cu", "multi.cu"] {
+    for f in ["runtime.cu", "stree_build.cu", "stree_search.cu", "sa.cu", "multi.cu", "formats.cu"] {
         cmd.arg(csrc.join(f));
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
