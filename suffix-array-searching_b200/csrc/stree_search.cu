@@ -779,8 +779,12 @@ int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t
         return SST_CUDA_OK(cudaGetLastError()) ? SST_OK : SST_ERR_CUDA;
     }
     if (scheme == SST_SCHEME_AUTO) {
+        // Measured at 2^28 keys (tools/batch_sweep.py): the thread-per-query kernel has the shortest latency
+        // (6-10 us up to 2^16 queries), the rank-table kernel the highest throughput from 2^17 queries up
+        // (16.8 Gq/s at 2^18, 34 Gq/s at 2^26); the table-less group kernel never wins.
         if (!fast_eligible(idx)) scheme = SST_SCHEME_GENERIC;
-        else scheme = env_int("SST_SCHEME", (top_eligible(idx) && nq >= (size_t)env_int("SST_TABLE_MIN_NQ", 1 << 19)) ? SST_SCHEME_TABLE : SST_SCHEME_GROUP2);
+        else if (nq < (size_t)env_int("SST_TABLE_MIN_NQ", 1 << 17)) scheme = env_int("SST_SCHEME", SST_SCHEME_GENERIC);
+        else scheme = env_int("SST_SCHEME", top_eligible(idx) ? SST_SCHEME_TABLE : SST_SCHEME_GROUP2);
     }
     if (scheme != SST_SCHEME_GENERIC && !fast_eligible(idx)) {  // (BINSEARCH included: plain B=16 only)
         set_error(SST_ERR_UNSUPPORTED, "the group/table kernels serve the plain B=16 tree; use SST_SCHEME_AUTO or SST_SCHEME_GENERIC");
