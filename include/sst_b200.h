@@ -64,7 +64,9 @@ enum {
     SST_SCHEME_GROUP2 = 3,   /* 2 lanes x 32 B per node (LDG.256) */
     SST_SCHEME_GENERIC = 4,  /* one thread per query, any layout */
     SST_SCHEME_TABLE = 5,    /* top levels answered by a shared-memory rank table (TMA-staged), rest as GROUP2 */
-    SST_SCHEME_BINSEARCH = 6 /* baseline: SortedVec::binary_search (sst/binary_search.rs:36-49) over the leaf level */
+    SST_SCHEME_BINSEARCH = 6, /* baseline: SortedVec::binary_search (sst/binary_search.rs:36-49) over the leaf level */
+    SST_SCHEME_BUCKETED = 7   /* reordered batch: queries partitioned by key range, each bucket answered from shared memory
+                                 + one leaf sector, results un-permuted (plain B=16 trees of 2^22..2^28 keys, large batches) */
 };
 
 /* SA search modes */

@@ -1,0 +1,710 @@
+// bucketed.cu -- reordered-batch lower_bound: partition the query batch by key range, answer each bucket
+// from shared memory + one leaf sector, un-permute the results.  Same results as every other scheme.
+//
+// Replaces (static-search-tree/src): the batched/interleaved searches of s_tree.rs:208-832 for LARGE
+// batches over LARGE trees.  The reference keeps 128 independent queries in flight and lets each one
+// miss the cache once per level (s_tree.rs:303-326); on B200 that design is bound by the number of
+// random DRAM accesses per second (~43 G/s), one per query for the leaf level.
+// Here the batch is first reordered so that all queries that fall into the same 512 KB window of the
+// leaf level are answered together by one CTA:
+//
+//   rank    (bk_rank_kernel)    per 16384-query tile: bucket id per query (table over the top 12 key bits +
+//                               splitter scan), stable rank inside the tile by per-warp counters and
+//                               ballot-matching (no atomics), tile x bucket counts, 16-bit local position
+//   plan    (bk_colsum/plan/offsets) exclusive scan of the count matrix -> global offset of every
+//                               (tile, bucket) run, bucket starts, work items (bucket, 16384-query chunk)
+//   scatter (bk_move_kernel<0>) tile -> shared memory in bucket order -> coalesced runs in HBM
+//   search  (bk_search_kernel)  per work item: the bucket's separators (last key of every 8-key half
+//                               node, 64 KB) and its jump table (16 KB) are staged into shared memory
+//                               by 1-D TMA bulk copies; a query is ranked among them with 2 + ~2 shared
+//                               loads and finished with ONE 32-byte leaf load (8 keys, LDG.256)
+//   gather  (bk_move_kernel<1>) results back into the caller's order through shared memory
+//
+// DRAM traffic per 10^8 queries over 2^28 keys: the leaf level once (1 GiB, instead of 6.4-12.8 GB of
+// random sectors), 128 MB of separators, and ~3 GB of query/result/position streams.  The tree image is
+// untouched: the leaf level is read in place and the separators are a GPU-only auxiliary array like
+// the rank table of stree_search.cu.  Plain B = 16 trees (any new_params flags) up to 2^28 keys.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace sst {
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kTile = 16384;                 // queries per partition tile (64 KB of shared memory)
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+constexpr int kItems = kTile / kThreads;     // 32 queries per thread
+constexpr int kCells = 8192;                 // jump-table cells per bucket
+constexpr int kJumpStride = kCells + 8;      // u16 entries per bucket (multiple of 16 bytes)
+constexpr int kBtShift = 19;                 // bucket table over the top 12 bits of a 31-bit key
+constexpr int kBtCells = 1 << (31 - kBtShift);
+constexpr int kBtStride = kBtCells + 8;
+constexpr unsigned kChunk = 16384;           // queries per search work item
+constexpr int kTilesPerGroup = 64;
+constexpr size_t kSubBatch = (size_t)1 << 27;  // queries per pipeline run (bounds the scratch buffers)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    unsigned done = 0;
+    const uint32_t addr = smem_u32(bar);
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Exclusive prefix sum of one value per thread over the CTA (blockDim.x = 32 * nwarps <= 1024).
+// s_warp needs nwarps + 1 entries; the caller synchronises before reusing it.
+__device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned* s_warp, unsigned* total) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    unsigned x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned y = __shfl_up_sync(kFull, x, o);
+        if (lane >= (unsigned)o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned w = lane < nwarps ? s_warp[lane] : 0u;
+        unsigned ws = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(kFull, ws, o);
+            if (lane >= (unsigned)o) ws += y;
+        }
+        if (lane < nwarps) s_warp[lane] = ws - w;
+        if (lane == 31) s_warp[nwarps] = ws;
+    }
+    __syncthreads();
+    *total = s_warp[nwarps];
+    return s_warp[warp] + x - v;
+}
+
+// Signed node compare of node.rs:91-108: a query above MAX is below every key, i.e. behaves like 0.
+__device__ __forceinline__ uint32_t canonical(uint32_t q) { return q > kMax ? 0u : q; }
+
+// bucket(q) = number of splitters < q; split[i], i in [1, nb), are the splitters (split[0] = 0, split[nb] = MAX).
+// bt[c] = number of splitters whose top 12 bits are < c.
+__device__ __forceinline__ unsigned bk_bucket(const uint16_t* __restrict__ bt, const uint32_t* __restrict__ split, uint32_t q) {
+    const unsigned c = q >> kBtShift;
+    unsigned lo = bt[c], hi = bt[c + 1];
+    if (hi - lo > 8u) {  // skewed keys: many splitters share the prefix
+        while (lo < hi) {
+            const unsigned m = (lo + hi) >> 1;
+            if (split[m + 1] < q) lo = m + 1; else hi = m;
+        }
+    } else {
+        while (lo < hi && split[lo + 1] < q) lo++;
+    }
+    return lo;
+}
+
+struct BkView {
+    const uint16_t* bt;
+    const uint32_t* split;
+    unsigned nb, nbp, bpt;  // buckets, padded to a multiple of kThreads, buckets per thread
+};
+
+// ------------------------------------------------------------------------------------------------
+// rank: bucket id, stable tile-local position and tile x bucket counts
+// ------------------------------------------------------------------------------------------------
+template <int BITS>
+__global__ void __launch_bounds__(kThreads, 2)
+bk_rank_kernel(const BkView v, const uint32_t* __restrict__ qs, size_t nq, unsigned ntiles, uint32_t* __restrict__ counts,
+               uint16_t* __restrict__ lpos16) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint16_t* cnt = reinterpret_cast<uint16_t*>(smem_raw);                       // [kWarps][nbp]
+    uint16_t* s_start = cnt + (size_t)kWarps * v.nbp;                             // [nbp]
+    uint16_t* s_bt = s_start + v.nbp;                                             // [kBtStride]
+    uint32_t* s_split = reinterpret_cast<uint32_t*>(s_bt + kBtStride);            // [nbp + 1]
+    __shared__ unsigned s_warp[kWarps + 1];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (unsigned i = tid; i < (unsigned)kBtStride; i += kThreads) s_bt[i] = i <= (unsigned)kBtCells ? v.bt[i] : 0;
+    for (unsigned i = tid; i <= v.nbp; i += kThreads) s_split[i] = i <= v.nb ? v.split[i] : kMax;
+    uint16_t* cntw = cnt + (size_t)warp * v.nbp;
+
+    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        {   // zero the per-warp counters
+            uint4* c4 = reinterpret_cast<uint4*>(cnt);
+            const unsigned n16 = kWarps * v.nbp / 8;
+            for (unsigned i = tid; i < n16; i += kThreads) c4[i] = make_uint4(0, 0, 0, 0);
+        }
+        const size_t tile_base = (size_t)tile * kTile;
+        const unsigned tile_n = (unsigned)min((size_t)kTile, nq - tile_base);
+        __syncthreads();  // tables + zeroed counters visible
+        uint32_t pk[kItems];  // bucket | rank << 16; 0xffffffff = no query
+#pragma unroll
+        for (int r = 0; r < kItems; r++) {
+            const unsigned i = warp * (kItems * 32) + r * 32 + lane;
+            pk[r] = i < tile_n ? __ldcs(qs + tile_base + i) : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < kItems; r++) {
+            const unsigned i = warp * (kItems * 32) + r * 32 + lane;
+            pk[r] = i < tile_n ? bk_bucket(s_bt, s_split, canonical(pk[r])) : 0xffffffffu;
+        }
+        // stable rank inside the warp's 1024 queries: lanes with the same bucket find each other by
+        // ballots over the bucket bits; the lowest of them bumps the warp's private counter
+#pragma unroll
+        for (int r = 0; r < kItems; r++) {
+            const bool valid = pk[r] != 0xffffffffu;
+            const unsigned b = valid ? pk[r] : 0u;
+            unsigned peers = __ballot_sync(kFull, valid);
+#pragma unroll
+            for (int bit = 0; bit < BITS; bit++) {
+                const bool one = (b >> bit) & 1u;
+                const unsigned vote = __ballot_sync(kFull, one);
+                peers &= one ? vote : ~vote;
+            }
+            const unsigned before = peers & lt_mask;
+            const unsigned old = valid ? cntw[b] : 0u;
+            __syncwarp();
+            if (valid && before == 0u) cntw[b] = (uint16_t)(old + __popc(peers));
+            __syncwarp();
+            if (valid) pk[r] = b | ((old + __popc(before)) << 16);
+        }
+        __syncthreads();
+        // per bucket: exclusive scan over the warps, total to the count matrix, start inside the tile
+        unsigned tot[4], sum = 0;
+#pragma unroll
+        for (unsigned k = 0; k < 4; k++) {
+            tot[k] = 0;
+            if (k < v.bpt) {
+                const unsigned b = tid * v.bpt + k;
+                unsigned run = 0;
+#pragma unroll
+                for (int w = 0; w < kWarps; w++) {
+                    const unsigned c = cnt[(size_t)w * v.nbp + b];
+                    cnt[(size_t)w * v.nbp + b] = (uint16_t)run;
+                    run += c;
+                }
+                tot[k] = run;
+                sum += run;
+                counts[(size_t)tile * v.nbp + b] = run;
+            }
+        }
+        unsigned total;
+        unsigned base = block_excl_scan(sum, s_warp, &total);
+#pragma unroll
+        for (unsigned k = 0; k < 4; k++)
+            if (k < v.bpt) { s_start[tid * v.bpt + k] = (uint16_t)base; base += tot[k]; }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kItems; r++) {
+            const unsigned i = warp * (kItems * 32) + r * 32 + lane;
+            if (i < tile_n) {
+                const unsigned b = pk[r] & 0xffffu;
+                lpos16[tile_base + i] = (uint16_t)(s_start[b] + cntw[b] + (pk[r] >> 16));
+            }
+        }
+        __syncthreads();  // counters are zeroed again at the top
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan: scan of the count matrix (tiles x buckets) and the work-item list of the search kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bk_colsum_kernel(const uint32_t* __restrict__ counts, unsigned ntiles, unsigned nbp, uint32_t* __restrict__ gsum) {
+    const unsigned b = blockIdx.x * 256 + threadIdx.x, g = blockIdx.y;
+    const unsigned t0 = g * kTilesPerGroup, t1 = min(t0 + kTilesPerGroup, ntiles);
+    unsigned s = 0;
+    for (unsigned t = t0; t < t1; t++) s += counts[(size_t)t * nbp + b];
+    gsum[(size_t)g * nbp + b] = s;
+}
+
+// ctrl[0] = work counter of the search kernel, ctrl[1] = number of work items
+__global__ void __launch_bounds__(1024)
+bk_plan_kernel(uint32_t* __restrict__ gsum, unsigned ngroups, unsigned nbp, uint32_t* __restrict__ bstart, uint2* __restrict__ items,
+               unsigned* __restrict__ ctrl) {
+    __shared__ unsigned s_warp[33];
+    const unsigned tid = threadIdx.x;
+    unsigned tot[2] = {0, 0};
+#pragma unroll
+    for (unsigned k = 0; k < 2; k++) {
+        const unsigned b = tid * 2 + k;
+        if (b < nbp) {
+            unsigned run = 0;
+            for (unsigned g = 0; g < ngroups; g++) {
+                const unsigned c = gsum[(size_t)g * nbp + b];
+                gsum[(size_t)g * nbp + b] = run;
+                run += c;
+            }
+            tot[k] = run;
+        }
+    }
+    unsigned total;
+    unsigned base = block_excl_scan(tot[0] + tot[1], s_warp, &total);
+    if (tid * 2 < nbp) bstart[tid * 2] = base;
+    if (tid * 2 + 1 < nbp) bstart[tid * 2 + 1] = base + tot[0];
+    if (tid == 0) bstart[nbp] = total;
+    __syncthreads();
+    const unsigned ni0 = (tot[0] + kChunk - 1) / kChunk, ni1 = (tot[1] + kChunk - 1) / kChunk;
+    unsigned nitems;
+    unsigned ib = block_excl_scan(ni0 + ni1, s_warp, &nitems);
+    for (unsigned c = 0; c < ni0; c++) items[ib + c] = make_uint2(tid * 2, c);
+    for (unsigned c = 0; c < ni1; c++) items[ib + ni0 + c] = make_uint2(tid * 2 + 1, c);
+    if (tid == 0) { ctrl[0] = 0; ctrl[1] = nitems; }
+}
+
+__global__ void __launch_bounds__(256)
+bk_offsets_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ gsum, const uint32_t* __restrict__ bstart,
+                  unsigned ntiles, unsigned nbp, uint32_t* __restrict__ offs) {
+    const unsigned b = blockIdx.x * 256 + threadIdx.x, g = blockIdx.y;
+    const unsigned t0 = g * kTilesPerGroup, t1 = min(t0 + kTilesPerGroup, ntiles);
+    unsigned run = gsum[(size_t)g * nbp + b] + bstart[b];
+    for (unsigned t = t0; t < t1; t++) {
+        const unsigned c = counts[(size_t)t * nbp + b];
+        offs[(size_t)t * nbp + b] = run;
+        run += c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// scatter (GATHER = false): queries of a tile -> bucket order; gather (GATHER = true): results back
+// ------------------------------------------------------------------------------------------------
+template <bool GATHER, typename OutT>
+__global__ void __launch_bounds__(kThreads, 2)
+bk_move_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offs, const uint16_t* __restrict__ lpos16,
+               unsigned nbp, unsigned bpt, unsigned ntiles, size_t nq, const uint32_t* __restrict__ src, OutT* __restrict__ dst) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t* s_tile = reinterpret_cast<uint32_t*>(smem_raw);        // [kTile] in bucket order
+    uint32_t* s_delta = s_tile + kTile;                                // [nbp] global offset - local start
+    uint16_t* s_map = reinterpret_cast<uint16_t*>(s_delta + nbp);      // [kTile] bucket of each local position
+    __shared__ unsigned s_warp[kWarps + 1];
+    const unsigned tid = threadIdx.x;
+    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const size_t tile_base = (size_t)tile * kTile;
+        const unsigned tile_n = (unsigned)min((size_t)kTile, nq - tile_base);
+        unsigned c[4], o[4], sum = 0;
+#pragma unroll
+        for (unsigned k = 0; k < 4; k++) {
+            c[k] = 0; o[k] = 0;
+            if (k < bpt) {
+                c[k] = counts[(size_t)tile * nbp + tid * bpt + k];
+                o[k] = offs[(size_t)tile * nbp + tid * bpt + k];
+                sum += c[k];
+            }
+        }
+        unsigned total;
+        unsigned base = block_excl_scan(sum, s_warp, &total);
+#pragma unroll
+        for (unsigned k = 0; k < 4; k++)
+            if (k < bpt) {
+                const unsigned b = tid * bpt + k;
+                s_delta[b] = o[k] - base;
+                for (unsigned j = 0; j < c[k]; j++) s_map[base + j] = (uint16_t)b;
+                base += c[k];
+            }
+        __syncthreads();
+        if constexpr (!GATHER) {
+#pragma unroll 8
+            for (int r = 0; r < kItems; r++) {
+                const unsigned i = r * kThreads + tid;
+                if (i < tile_n) s_tile[lpos16[tile_base + i]] = canonical(__ldcs(src + tile_base + i));
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int r = 0; r < kItems; r++) {
+                const unsigned i = r * kThreads + tid;
+                if (i < tile_n) dst[s_delta[s_map[i]] + i] = (OutT)s_tile[i];
+            }
+        } else {
+#pragma unroll 8
+            for (int r = 0; r < kItems; r++) {
+                const unsigned i = r * kThreads + tid;
+                if (i < tile_n) s_tile[i] = __ldcs(src + (s_delta[s_map[i]] + i));
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int r = 0; r < kItems; r++) {
+                const unsigned i = r * kThreads + tid;
+                if (i < tile_n) __stcs(dst + tile_base + i, (OutT)s_tile[lpos16[tile_base + i]]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// search: one work item = (bucket, chunk of its queries)
+// ------------------------------------------------------------------------------------------------
+struct BkSearchParams {
+    const uint32_t* sep;     // [nb * r]
+    const uint16_t* jump;    // [nb][kJumpStride]
+    const uint2* meta;       // [nb] {lo, shift}
+    const uint32_t* leaf;    // sorted keys (leaf level of the image, MAX-padded)
+    unsigned r;              // half nodes (separators) per bucket
+    unsigned long long m8;   // half nodes that hold keys
+    unsigned long long n;
+};
+
+__device__ __forceinline__ void ldg256(const uint32_t* p, uint32_t (&k)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(k[0]), "=r"(k[1]), "=r"(k[2]), "=r"(k[3]), "=r"(k[4]), "=r"(k[5]), "=r"(k[6]), "=r"(k[7])
+                 : "l"(p));
+}
+
+template <bool WANT_IDX>
+__global__ void __launch_bounds__(kThreads, 2)
+bk_search_kernel(const BkSearchParams p, const uint32_t* __restrict__ qb, const uint32_t* __restrict__ bstart,
+                 const uint2* __restrict__ items, unsigned* __restrict__ ctrl, uint32_t* __restrict__ rb, uint32_t* __restrict__ ib) {
+    constexpr int U = 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t* s_sep = reinterpret_cast<uint32_t*>(smem_raw);                 // [r]
+    uint16_t* s_jump = reinterpret_cast<uint16_t*>(s_sep + p.r);              // [kJumpStride]
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ unsigned s_item;
+    const unsigned tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    unsigned phase = 0, cur_b = 0xffffffffu;
+    const unsigned nitems = ctrl[1];
+    while (true) {
+        __syncthreads();  // previous item finished: s_item, s_sep, s_jump may be overwritten
+        if (tid == 0) s_item = atomicAdd(&ctrl[0], 1u);
+        __syncthreads();
+        const unsigned item = s_item;
+        if (item >= nitems) break;
+        const uint2 it = items[item];
+        const unsigned b = it.x;
+        if (b != cur_b) {  // stage the bucket: 1-D TMA bulk copies (SASS UBLKCP), completion on the mbarrier
+            if (tid == 0) {
+                const unsigned sep_bytes = p.r * 4u, jump_bytes = kJumpStride * 2u;
+                mbar_expect_tx(&bar, sep_bytes + jump_bytes);
+                for (unsigned off = 0; off < sep_bytes; off += 32768u)
+                    tma_bulk_g2s((char*)s_sep + off, (const char*)(p.sep + (size_t)b * p.r) + off, min(32768u, sep_bytes - off), &bar);
+                tma_bulk_g2s(s_jump, p.jump + (size_t)b * kJumpStride, jump_bytes, &bar);
+            }
+            mbar_wait(&bar, phase);
+            phase ^= 1u;
+            cur_b = b;
+        }
+        const uint2 mt = p.meta[b];
+        const uint32_t lo = mt.x;
+        const unsigned sh = mt.y;
+        const unsigned qbeg = bstart[b] + it.y * kChunk, qend = min(qbeg + kChunk, bstart[b + 1]);
+        const unsigned long long hbase = (unsigned long long)b * p.r;
+        for (unsigned i0 = qbeg + tid; i0 < qend; i0 += kThreads * U) {
+            uint32_t q[U];
+            unsigned a[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const unsigned i = i0 + u * kThreads;
+                q[u] = i < qend ? __ldcs(qb + i) : lo;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {  // rank among the bucket's separators
+                const unsigned x = (q[u] - lo) >> sh;
+                unsigned l = s_jump[x], h = s_jump[x + 1];
+                if (h - l > 8u) {
+                    while (l < h) {
+                        const unsigned m = (l + h) >> 1;
+                        if (s_sep[m] < q[u]) l = m + 1; else h = m;
+                    }
+                } else {
+                    while (l < h && s_sep[l] < q[u]) l++;
+                }
+                a[u] = l;
+            }
+            uint32_t ks[U][8];
+            unsigned long long hn[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {  // the half node that holds the answer: one 32-byte sector
+                hn[u] = hbase + a[u];
+                const unsigned long long hc = hn[u] < p.m8 ? hn[u] : p.m8 - 1;
+                ldg256(p.leaf + hc * 8ull, ks[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const unsigned i = i0 + u * kThreads;
+                unsigned c = 0;
+#pragma unroll
+                for (int e = 0; e < 8; e++) c += ks[u][e] < q[u] ? 1u : 0u;
+                uint32_t val = ks[u][0];
+#pragma unroll
+                for (int e = 1; e < 8; e++) val = c == (unsigned)e ? ks[u][e] : val;
+                unsigned long long pos = hn[u] * 8ull + c;
+                if (hn[u] >= p.m8 || c == 8u) { val = kMax; pos = p.n; }  // above every key (c == 8 cannot happen below m8)
+                if (pos > p.n) pos = p.n;
+                if (i < qend) {
+                    __stcs(rb + i, val);
+                    if constexpr (WANT_IDX) __stcs(ib + i, (uint32_t)pos);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// auxiliary arrays (index build time)
+// ------------------------------------------------------------------------------------------------
+// sep[m] = last key of half node m (leaf slot 8m + 7) for m < m8, 0xffffffff beyond
+__global__ void bk_sep_kernel(const uint32_t* __restrict__ leaf, unsigned long long m8, unsigned long long total, uint32_t* __restrict__ sep) {
+    for (unsigned long long m = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; m < total;
+         m += (unsigned long long)gridDim.x * blockDim.x)
+        sep[m] = m < m8 ? leaf[m * 8ull + 7ull] : 0xffffffffu;
+}
+// split[0] = 0, split[b] = sep[b*r - 1] (last key before bucket b), split[nb] = MAX
+__global__ void bk_split_kernel(const uint32_t* __restrict__ sep, unsigned nb, unsigned r, uint32_t* __restrict__ split) {
+    for (unsigned b = blockIdx.x * blockDim.x + threadIdx.x; b <= nb; b += gridDim.x * blockDim.x)
+        split[b] = b == 0 ? 0u : (b == nb ? kMax : sep[(size_t)b * r - 1]);
+}
+// bt[c] = number of splitters split[1..nb-1] whose top bits are < c, c in [0, kBtCells]
+__global__ void bk_bt_kernel(const uint32_t* __restrict__ split, unsigned nb, uint16_t* __restrict__ bt) {
+    for (unsigned c = blockIdx.x * blockDim.x + threadIdx.x; c < (unsigned)kBtStride; c += gridDim.x * blockDim.x) {
+        unsigned l = 0, h = nb - 1;  // count over i in [1, nb): index i = l + 1
+        while (l < h) {
+            const unsigned m = (l + h) >> 1;
+            if ((split[m + 1] >> kBtShift) < c) l = m + 1; else h = m;
+        }
+        bt[c] = c <= (unsigned)kBtCells ? (uint16_t)l : 0;
+    }
+}
+// Per bucket: lo = split[b], shift = smallest s with (split[b+1] - lo) >> s < kCells, and
+// jump[x] = number of the bucket's separators with (sep - lo) >> s < x, x in [0, kCells].
+__global__ void __launch_bounds__(256)
+bk_jump_kernel(const uint32_t* __restrict__ sep, const uint32_t* __restrict__ split, unsigned r, unsigned long long m8,
+               uint16_t* __restrict__ jump, uint2* __restrict__ meta) {
+    const unsigned b = blockIdx.x;
+    const uint32_t lo = split[b], hi = split[b + 1];
+    unsigned s = 0;
+    while (((hi - lo) >> s) >= (unsigned)kCells) s++;
+    if (threadIdx.x == 0) meta[b] = make_uint2(lo, s);
+    const uint32_t* sb = sep + (size_t)b * r;
+    const unsigned long long first = (unsigned long long)b * r;
+    const unsigned valid = (unsigned)min((unsigned long long)r, m8 > first ? m8 - first : 0ull);
+    for (unsigned x = threadIdx.x; x < (unsigned)kJumpStride; x += blockDim.x) {
+        unsigned l = 0, h = valid;
+        while (l < h) {
+            const unsigned m = (l + h) >> 1;
+            if (((sb[m] - lo) >> s) < x) l = m + 1; else h = m;
+        }
+        jump[(size_t)b * kJumpStride + x] = x <= (unsigned)kCells ? (uint16_t)l : 0;
+    }
+}
+
+int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scratch buffers: one set per (host thread, device), grown on demand, released when the thread exits
+// ------------------------------------------------------------------------------------------------
+struct Scratch {
+    int device = -1;
+    size_t cap_q = 0, cap_idx = 0, cap_mat = 0, cap_items = 0;
+    uint32_t *qb = nullptr, *rb = nullptr, *ib = nullptr, *counts = nullptr, *offs = nullptr, *gsum = nullptr, *bstart = nullptr;
+    uint16_t* lpos = nullptr;
+    uint2* items = nullptr;
+    unsigned* ctrl = nullptr;
+    cudaEvent_t done = nullptr;  // last pipeline run (another stream of this thread must wait for it)
+    ~Scratch() {
+        if (device < 0) return;
+        int prev = -1;
+        if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) { (void)cudaGetLastError(); return; }
+        cudaFree(qb); cudaFree(rb); cudaFree(ib); cudaFree(counts); cudaFree(offs); cudaFree(gsum); cudaFree(bstart);
+        cudaFree(lpos); cudaFree(items); cudaFree(ctrl);
+        if (done) cudaEventDestroy(done);
+        (void)cudaGetLastError();
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+thread_local Scratch g_scratch[64];
+
+template <typename T>
+bool regrow(T*& p, size_t count) {
+    cudaFree(p);
+    p = nullptr;
+    return SST_CUDA_OK(cudaMalloc(&p, count * sizeof(T)));
+}
+
+bool scratch_ensure(Scratch& s, int device, size_t nq, bool want_idx, unsigned nbp) {
+    s.device = device;
+    if (!s.done && !SST_CUDA_OK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming))) return false;
+    if (!s.ctrl && (!regrow(s.ctrl, 4) || !regrow(s.bstart, 2048 + 8))) return false;
+    if (nq > s.cap_q) {
+        s.cap_q = 0;
+        if (!regrow(s.qb, nq) || !regrow(s.rb, nq) || !regrow(s.lpos, nq)) return false;
+        s.cap_q = nq;
+    }
+    if (want_idx && nq > s.cap_idx) {
+        s.cap_idx = 0;
+        if (!regrow(s.ib, nq)) return false;
+        s.cap_idx = nq;
+    }
+    const size_t ntiles = div_ceil(nq, (size_t)kTile);
+    const size_t mat = ntiles * nbp;
+    if (mat > s.cap_mat) {
+        s.cap_mat = 0;
+        if (!regrow(s.counts, mat) || !regrow(s.offs, mat) || !regrow(s.gsum, mat / kTilesPerGroup + 4096)) return false;
+        s.cap_mat = mat;
+    }
+    const size_t items = 2048 + nq / kChunk + 2;
+    if (items > s.cap_items) {
+        s.cap_items = 0;
+        if (!regrow(s.items, items)) return false;
+        s.cap_items = items;
+    }
+    return true;
+}
+
+template <int BITS>
+void launch_rank(const BkView& v, int grid, size_t smem, cudaStream_t st, const uint32_t* qs, size_t nq, unsigned ntiles, uint32_t* counts,
+                 uint16_t* lpos) {
+    auto kern = bk_rank_kernel<BITS>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, kThreads, smem, st>>>(v, qs, nq, ntiles, counts, lpos);
+}
+
+template <bool GATHER, typename OutT>
+void launch_move(int grid, size_t smem, cudaStream_t st, const Scratch& s, unsigned nbp, unsigned bpt, unsigned ntiles, size_t nq,
+                 const uint32_t* src, OutT* dst) {
+    auto kern = bk_move_kernel<GATHER, OutT>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, kThreads, smem, st>>>(s.counts, s.offs, s.lpos, nbp, bpt, ntiles, nq, src, dst);
+}
+
+}  // namespace
+
+void free_bucket_aux(sst_index* idx) {
+    cudaFree(idx->bk.d_sep); cudaFree(idx->bk.d_split); cudaFree(idx->bk.d_bt); cudaFree(idx->bk.d_jump); cudaFree(idx->bk.d_meta);
+    idx->bk = BkAux{};
+}
+
+// Builds the auxiliary arrays of the reordered-batch pipeline for a plain B=16 tree.  Returns false only
+// on a CUDA error; an index the pipeline does not serve simply has bk.nb == 0.
+bool build_bucket_aux(sst_index* idx) {
+    if (idx->variant != SST_PLAIN || idx->node_b != 16) return true;
+    if (idx->n < (size_t)env_int("SST_BK_MIN_N", 1 << 22)) return true;  // small trees are L2-resident: nothing to gain
+    unsigned r = (unsigned)env_int("SST_BK_R", 16384);
+    if (r < 64 || r > 16384 || (r & (r - 1))) r = 16384;
+    const unsigned long long m8 = div_ceil(idx->n, (size_t)8);
+    const unsigned long long nb64 = div_ceil((size_t)m8, (size_t)r);
+    if (nb64 > 2048) return true;  // > 2^28 keys: served by the rank-table kernel
+    BkAux& a = idx->bk;
+    const unsigned nb = (unsigned)nb64;
+    const unsigned nbp = (unsigned)(div_ceil((size_t)nb, (size_t)kThreads) * kThreads);
+    unsigned bits = 0;
+    while ((1u << bits) < nb) bits++;
+    cudaStream_t st = thread_stream(idx->device);
+    const uint32_t* leaf = idx->d_tree + idx->offsets[idx->levels - 1] * 16;
+    const unsigned long long total = (unsigned long long)nb * r;
+    bool ok = SST_CUDA_OK(cudaMalloc(&a.d_sep, total * 4)) && SST_CUDA_OK(cudaMalloc(&a.d_split, ((size_t)nb + 1) * 4)) &&
+              SST_CUDA_OK(cudaMalloc(&a.d_bt, (size_t)kBtStride * 2)) && SST_CUDA_OK(cudaMalloc(&a.d_jump, (size_t)nb * kJumpStride * 2)) &&
+              SST_CUDA_OK(cudaMalloc(&a.d_meta, (size_t)nb * sizeof(uint2)));
+    if (ok) {
+        bk_sep_kernel<<<(unsigned)std::min<size_t>(div_ceil((size_t)total, (size_t)256), 148 * 16), 256, 0, st>>>(leaf, m8, total, a.d_sep);
+        bk_split_kernel<<<(unsigned)div_ceil((size_t)nb + 1, (size_t)256), 256, 0, st>>>(a.d_sep, nb, r, a.d_split);
+        bk_bt_kernel<<<(unsigned)div_ceil((size_t)kBtStride, (size_t)256), 256, 0, st>>>(a.d_split, nb, a.d_bt);
+        bk_jump_kernel<<<nb, 256, 0, st>>>(a.d_sep, a.d_split, r, m8, a.d_jump, a.d_meta);
+        ok = SST_CUDA_OK(cudaGetLastError()) && SST_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    if (!ok) { free_bucket_aux(idx); return false; }
+    a.nb = nb; a.nbp = nbp; a.r = r; a.bits = bits; a.m8 = m8;
+    return true;
+}
+
+bool bucketed_eligible(const sst_index* idx) { return idx->bk.nb != 0; }
+
+int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx, cudaStream_t st) {
+    const BkAux& a = idx->bk;
+    if (!a.nb) { set_error(SST_ERR_UNSUPPORTED, "the reordered-batch pipeline serves plain B=16 trees of 2^22..2^28 keys"); return SST_ERR_UNSUPPORTED; }
+    const int dev = idx->device;
+    if (dev < 0 || dev >= 64) { set_error(SST_ERR_ARG, "device index out of range"); return SST_ERR_ARG; }
+    Scratch& s = g_scratch[dev];
+    const size_t sub = std::min(nq, kSubBatch);
+    if (!scratch_ensure(s, dev, sub, d_idx != nullptr, a.nbp)) return SST_ERR_CUDA;
+    if (!SST_CUDA_OK(cudaStreamWaitEvent(st, s.done, 0))) return SST_ERR_CUDA;  // scratch reuse across this thread's streams
+    const int sms = sm_count(dev);
+    const unsigned bpt = a.nbp / kThreads;
+    BkView v{a.d_bt, a.d_split, a.nb, a.nbp, bpt};
+    const size_t smem_rank = (size_t)kWarps * a.nbp * 2 + (size_t)a.nbp * 2 + (size_t)kBtStride * 2 + ((size_t)a.nbp + 1) * 4 + 16;
+    const size_t smem_move = (size_t)kTile * 4 + (size_t)a.nbp * 4 + (size_t)kTile * 2;
+    const size_t smem_search = (size_t)a.r * 4 + (size_t)kJumpStride * 2;
+    BkSearchParams sp{a.d_sep, a.d_jump, a.d_meta, idx->d_tree + idx->offsets[idx->levels - 1] * 16, a.r, a.m8, (unsigned long long)idx->n};
+    // SST_BK_TIMING=1 (debug): per-stage CUDA-event times on stderr; synchronises the stream
+    const bool timing = env_int("SST_BK_TIMING", 0) != 0;
+    cudaEvent_t ev[8] = {};
+    int nev = 0;
+    auto mark = [&]() {
+        if (!timing || nev >= 8) return;
+        cudaEventCreate(&ev[nev]);
+        cudaEventRecord(ev[nev++], st);
+    };
+    for (size_t off = 0; off < nq; off += sub) {
+        const size_t cnt = std::min(sub, nq - off);
+        const unsigned ntiles = (unsigned)div_ceil(cnt, (size_t)kTile), ngroups = (unsigned)div_ceil((size_t)ntiles, (size_t)kTilesPerGroup);
+        const int grid = (int)std::min<size_t>(ntiles, (size_t)sms * 2);
+        const uint32_t* qs = d_qs + off;
+        nev = 0;
+        mark();
+        switch (a.bits) {
+#define SST_BK_RANK(B) case B: launch_rank<B>(v, grid, smem_rank, st, qs, cnt, ntiles, s.counts, s.lpos); break;
+            SST_BK_RANK(0) SST_BK_RANK(1) SST_BK_RANK(2) SST_BK_RANK(3) SST_BK_RANK(4) SST_BK_RANK(5)
+            SST_BK_RANK(6) SST_BK_RANK(7) SST_BK_RANK(8) SST_BK_RANK(9) SST_BK_RANK(10) SST_BK_RANK(11)
+#undef SST_BK_RANK
+            default: set_error(SST_ERR_UNSUPPORTED, "too many buckets"); return SST_ERR_UNSUPPORTED;
+        }
+        mark();
+        const dim3 mgrid(a.nbp / 256, ngroups);
+        bk_colsum_kernel<<<mgrid, 256, 0, st>>>(s.counts, ntiles, a.nbp, s.gsum);
+        bk_plan_kernel<<<1, 1024, 0, st>>>(s.gsum, ngroups, a.nbp, s.bstart, s.items, s.ctrl);
+        bk_offsets_kernel<<<mgrid, 256, 0, st>>>(s.counts, s.gsum, s.bstart, ntiles, a.nbp, s.offs);
+        mark();
+        launch_move<false, uint32_t>(grid, smem_move, st, s, a.nbp, bpt, ntiles, cnt, qs, s.qb);
+        mark();
+        if (d_idx) {
+            auto kern = bk_search_kernel<true>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_search);
+            kern<<<sms * 2, kThreads, smem_search, st>>>(sp, s.qb, s.bstart, s.items, s.ctrl, s.rb, s.ib);
+        } else {
+            auto kern = bk_search_kernel<false>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_search);
+            kern<<<sms * 2, kThreads, smem_search, st>>>(sp, s.qb, s.bstart, s.items, s.ctrl, s.rb, s.ib);
+        }
+        mark();
+        launch_move<true, uint32_t>(grid, smem_move, st, s, a.nbp, bpt, ntiles, cnt, s.rb, d_vals + off);
+        if (d_idx) launch_move<true, unsigned long long>(grid, smem_move, st, s, a.nbp, bpt, ntiles, cnt, s.ib, d_idx + off);
+        mark();
+        if (timing && nev == 6 && cudaEventSynchronize(ev[5]) == cudaSuccess) {
+            float t[5];
+            for (int i = 0; i < 5; i++) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
+            fprintf(stderr, "[sst] bucketed nq=%zu nb=%u: rank %.3f plan %.3f scatter %.3f search %.3f gather %.3f ms\n", cnt, a.nb, t[0], t[1],
+                    t[2], t[3], t[4]);
+        }
+        for (int i = 0; i < nev; i++) cudaEventDestroy(ev[i]);
+    }
+    if (!SST_CUDA_OK(cudaGetLastError()) || !SST_CUDA_OK(cudaEventRecord(s.done, st))) return SST_ERR_CUDA;
+    return SST_OK;
+}
+
+}  // namespace sst

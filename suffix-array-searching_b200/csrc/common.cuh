@@ -99,6 +99,17 @@ struct SstTreeView {
     unsigned long long upper_stride;
 };
 
+// Auxiliary arrays of the reordered-batch pipeline (bucketed.cu); nb == 0: not built for this index.
+struct BkAux {
+    uint32_t* d_sep = nullptr;    // [nb * r] last key of every 8-key half node of the leaf level, 0xffffffff beyond the keys
+    uint32_t* d_split = nullptr;  // [nb + 1] split[0] = 0, split[b] = last key before bucket b, split[nb] = MAX
+    uint16_t* d_bt = nullptr;     // bucket table over the top 12 key bits
+    uint16_t* d_jump = nullptr;   // [nb][8200] per-bucket jump table into its separators
+    uint2* d_meta = nullptr;      // [nb] {lo, shift} of the jump table
+    unsigned nb = 0, nbp = 0, r = 0, bits = 0;
+    unsigned long long m8 = 0;    // half nodes that hold keys
+};
+
 struct sst_index {
     int device = 0;
     int variant = SST_PLAIN;
@@ -130,6 +141,7 @@ struct sst_index {
     // 16-bit compressed copy of the last internal level (plain B=16 trees whose level is HBM/L2 sized)
     uint16_t* d_c5 = nullptr;                     // [nodes * 16] separators minus the node's base
     uint32_t* d_h5 = nullptr;                     // [nodes] base (first separator), 0xffffffff = use the exact node
+    BkAux bk;                                     // reordered-batch pipeline (plain B=16 trees, 2^22..2^28 keys)
     bool persist_ok = false;                      // persisting-L2 carve-out configured on this device
     size_t persist_window_max = 0;
     SstTreeView view{};
@@ -147,4 +159,10 @@ bool build_compressed_level(sst_index* idx);
 int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx,
                  int scheme, cudaStream_t stream);
 int query_launch_count(const sst_index* idx, int scheme);
+// reordered-batch pipeline (bucketed.cu)
+bool build_bucket_aux(sst_index* idx);
+void free_bucket_aux(sst_index* idx);
+bool bucketed_eligible(const sst_index* idx);
+int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx,
+                    cudaStream_t stream);
 }  // namespace sst

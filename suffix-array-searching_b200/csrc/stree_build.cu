@@ -253,7 +253,7 @@ sst_index* build_plain(const uint32_t* d_sorted, bool, size_t n, uint32_t node_b
         delete idx;
         return nullptr;
     }
-    if (!build_top_table(idx, d_sorted) || !build_compressed_level(idx)) {
+    if (!build_top_table(idx, d_sorted) || !build_compressed_level(idx) || !build_bucket_aux(idx)) {
         free_index(idx);
         return nullptr;
     }
@@ -474,6 +474,7 @@ void free_index(sst_index* idx) {
     cudaFree(idx->d_top_low);
     cudaFree(idx->d_c5);
     cudaFree(idx->d_h5);
+    free_bucket_aux(idx);
     delete idx;
 }
 

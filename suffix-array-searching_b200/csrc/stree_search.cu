@@ -756,7 +756,9 @@ int launch_fast_top(const sst_index* idx, bool top, const uint32_t* d_qs, size_t
 
 }  // namespace
 
-int query_launch_count(const sst_index*, int) { return 1; }
+// Kernel launches per sst_query_device call (per 2^27-query sub-batch for the reordered-batch pipeline: rank,
+// column sums, plan, offsets, scatter, search, gather; one more gather when the index output is requested).
+int query_launch_count(const sst_index*, int scheme) { return scheme == SST_SCHEME_BUCKETED ? 7 : 1; }
 
 int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx,
                  int scheme, cudaStream_t st) {
@@ -792,6 +794,8 @@ int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t
     }
     const int T = env_int("SST_T", 2);
     switch (scheme) {
+        case SST_SCHEME_BUCKETED:
+            return launch_bucketed(idx, d_qs, nq, d_vals, d_idx, st);
         case SST_SCHEME_TABLE: {
             const bool top = top_eligible(idx);  // trees of height 1 have nothing above the leaf
             if (env_int("SST_TABLE_G", 2) == 4) {

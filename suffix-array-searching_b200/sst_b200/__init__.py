@@ -25,7 +25,7 @@ MAX = 0x7FFFFFFF
 
 LEFT_MAX, REVERSE_STORAGE, FULL_ARRAY = 1, 2, 4
 PLAIN, SIMPLE, COMPACT, L1, OVERLAPPING, MAP, EYTZINGER = 0, 1, 2, 3, 4, 5, 6
-SCHEME_AUTO, SCHEME_GROUP4, SCHEME_GROUP16, SCHEME_GROUP2, SCHEME_GENERIC, SCHEME_TABLE, SCHEME_BINSEARCH = 0, 1, 2, 3, 4, 5, 6
+SCHEME_AUTO, SCHEME_GROUP4, SCHEME_GROUP16, SCHEME_GROUP2, SCHEME_GENERIC, SCHEME_TABLE, SCHEME_BINSEARCH, SCHEME_BUCKETED = 0, 1, 2, 3, 4, 5, 6, 7
 SA_BINARY, SA_MLR = 0, 1
 ERR_CUDA, ERR_ARG, ERR_CAPACITY, ERR_UNSUPPORTED = 1, 2, 3, 4
 

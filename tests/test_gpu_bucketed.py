@@ -1,0 +1,112 @@
+"""GPU parity tests (-m gpu) of the reordered-batch pipeline (SCHEME_BUCKETED, csrc/bucketed.cu): partition ->
+search from shared memory -> un-permute must give exactly the oracle's values and indices.  Small separator
+windows (SST_BK_R) force many buckets on small trees; the full-size run is in test_gpu_stree.py."""
+import numpy as np
+import pytest
+
+from test_fuzz import KINDS, make_keys, make_queries
+from util import MAX, gen_queries, gen_vals
+
+pytestmark = pytest.mark.gpu
+
+FLAG_SETS = [(0, 0, 0), (1, 0, 0), (1, 0, 1), (0, 1, 0), (1, 1, 0)]
+
+
+def _check(sst, oracle, vals, qs, flags=FLAG_SETS):
+    ev, ei = oracle.lower_bound(vals, qs)
+    for lm, rev, full in flags:
+        t = sst.STree16.new_params(vals, bool(lm), bool(rev), bool(full))
+        v, i = t.query(qs, sst.SCHEME_BUCKETED, want_index=True)
+        assert np.array_equal(v, ev), (len(vals), len(qs), lm, rev, full, np.flatnonzero(v != ev)[:5])
+        assert np.array_equal(i, ei), (len(vals), len(qs), lm, rev, full, np.flatnonzero(i != ei)[:5])
+        assert np.array_equal(t.query(qs, sst.SCHEME_BUCKETED), ev)  # values only (no index pass)
+
+
+@pytest.mark.parametrize("r,n,nq", [(64, 5000, 40_000), (64, 100_000, 100_001), (64, 1_000_000, 70_000), (256, 1 << 20, 300_000),
+                                    (1024, 2_000_003, 50_000), (16384, (1 << 22) + 12345, 1_000_003), (64, 17, 33), (64, 600, 1)])
+def test_bucketed_uniform(gpu, oracle, monkeypatch, r, n, nq):
+    monkeypatch.setenv("SST_BK_MIN_N", "0")
+    monkeypatch.setenv("SST_BK_R", str(r))
+    vals = gen_vals(n, seed=n + r)
+    _check(gpu, oracle, vals, gen_queries(nq, seed=n + 1, vals=vals))
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_bucketed_fuzz(gpu, oracle, monkeypatch, seed):
+    """Adversarial key distributions (clusters, duplicate runs longer than a bucket, tiny ranges): crowded bucket-table
+    cells, empty buckets, all queries in one bucket, jump-table cells with many separators."""
+    rng = np.random.default_rng(5000 + seed)
+    monkeypatch.setenv("SST_BK_MIN_N", "0")
+    monkeypatch.setenv("SST_BK_R", str(int(rng.choice([64, 128, 1024]))))
+    n = int(rng.integers(1, 900_000))
+    vals = make_keys(rng, n, KINDS[seed % len(KINDS)])
+    nq = int(rng.integers(1, 200_000))
+    qs = make_queries(rng, vals, max(nq, 3))
+    if seed % 2:  # every query in a narrow range -> one or two buckets, many chunks
+        qs = np.clip(qs.astype(np.int64) % 5000 + int(vals[len(vals) // 2]), 0, MAX).astype(np.uint32)
+    _check(gpu, oracle, vals, qs, flags=[(1, 0, 0), (0, 1, 0)])
+
+
+def test_bucketed_edges(gpu, oracle, monkeypatch):
+    sst = gpu
+    monkeypatch.setenv("SST_BK_MIN_N", "0")
+    monkeypatch.setenv("SST_BK_R", "64")
+    vals = np.sort(np.random.default_rng(3).integers(0, 1 << 20, 50_000).astype(np.uint32))  # MAX is not a key
+    for nq in (1, 31, 33, 16383, 16384, 16385, 32768 + 7):
+        _check(sst, oracle, vals, gen_queries(nq, seed=nq, vals=vals), flags=[(1, 0, 0)])
+    for keys in ([MAX], [0, MAX], [5] * 4000 + [MAX], [3] * 1000, list(range(16)), [7] * 16 + [9] * 16 + [MAX] * 3):
+        keys = np.array(keys, np.uint32)
+        _check(sst, oracle, keys, np.array([0, 1, 3, 4, 5, 6, 7, 8, 9, 10, 15, 16, 17, MAX], np.uint32), flags=[(0, 0, 0), (1, 0, 0)])
+    # signed-compare quirk of node.rs:91-108: q >= 2^31 compares as negative -> first key, like every other kernel
+    t = sst.STree16.new_params(vals, True, False, False)
+    big = np.array([0x80000000, 0xFFFFFFFF, 0x80000001, 5, MAX], np.uint32)
+    v, i = t.query(big, sst.SCHEME_BUCKETED, want_index=True)
+    v2, i2 = t.query(big, sst.SCHEME_GROUP2, want_index=True)
+    assert np.array_equal(v, v2) and np.array_equal(i, i2)
+    assert t.query(np.zeros(0, np.uint32), sst.SCHEME_BUCKETED).size == 0
+
+
+def test_bucketed_unsupported_is_loud(gpu, monkeypatch):
+    sst = gpu
+    vals = gen_vals(100_000, seed=9)
+    qs = gen_queries(100, seed=1, vals=vals)
+    t = sst.STree16.new_params(vals, True, False, False)  # default: trees below 2^22 keys have no bucket index
+    with pytest.raises(sst.SstError):
+        t.query(qs, sst.SCHEME_BUCKETED)
+    monkeypatch.setenv("SST_BK_MIN_N", "0")
+    monkeypatch.setenv("SST_BK_R", "64")
+    big = gen_vals(64 * 8 * 2048 + 9, seed=10)  # one bucket too many for the 2048-bucket partition
+    with pytest.raises(sst.SstError):
+        sst.STree16.new_params(big, True, False, False).query(qs, sst.SCHEME_BUCKETED)
+    with pytest.raises(sst.SstError):
+        sst.STree15.new_params(vals, True, False, False).query(qs, sst.SCHEME_BUCKETED)
+    with pytest.raises(sst.SstError):
+        sst.PartitionedSTree16.new(vals, 4).query(qs, sst.SCHEME_BUCKETED)
+
+
+def test_bucketed_streams_and_repeats(gpu, oracle, monkeypatch):
+    """Scratch buffers are per host thread: back-to-back calls on two torch streams must not trample each other."""
+    import torch
+
+    sst = gpu
+    monkeypatch.setenv("SST_BK_MIN_N", "0")
+    monkeypatch.setenv("SST_BK_R", "256")
+    vals = gen_vals(1 << 19, seed=5)
+    t = sst.STree16.new_params(vals, True, False, False)
+    qa = gen_queries(400_000, seed=6, vals=vals)
+    qb = gen_queries(123_457, seed=7, vals=vals)
+    ea, _ = oracle.lower_bound(vals, qa)
+    eb, _ = oracle.lower_bound(vals, qb)
+    da, db = torch.from_numpy(qa.view(np.int32)).cuda(), torch.from_numpy(qb.view(np.int32)).cuda()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            va = t.query(da, sst.SCHEME_BUCKETED)
+        with torch.cuda.stream(s2):
+            vb = t.query(db, sst.SCHEME_BUCKETED)
+        outs.append((va, vb))
+    torch.cuda.synchronize()
+    for va, vb in outs:
+        assert np.array_equal(va.cpu().numpy().view(np.uint32), ea)
+        assert np.array_equal(vb.cpu().numpy().view(np.uint32), eb)

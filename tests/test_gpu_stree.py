@@ -329,7 +329,7 @@ def test_full_size_properties(gpu):
     t = sst.STree16.new_params(keys, True, False, False)
     assert t.layers() == 7
     ref_v = None
-    for s in (sst.SCHEME_TABLE, sst.SCHEME_GROUP4, sst.SCHEME_GROUP16, sst.SCHEME_GROUP2, sst.SCHEME_GENERIC):
+    for s in (sst.SCHEME_TABLE, sst.SCHEME_BUCKETED, sst.SCHEME_GROUP4, sst.SCHEME_GROUP16, sst.SCHEME_GROUP2, sst.SCHEME_GENERIC):
         v, i = t.query(qs, s, want_index=True)
         torch.cuda.synchronize()
         assert bool((v >= qs).all())
