@@ -40,7 +40,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kItems = kTile / kThreads;     // 32 queries per thread
 constexpr int kCells = 8192;                 // jump-table cells per bucket
 constexpr int kJumpStride = kCells + 8;      // u16 entries per bucket (multiple of 16 bytes)
-constexpr int kBtShift = 19;                 // bucket table over the top 12 bits of a 31-bit key
+constexpr int kBtShift = 18;                 // bucket table over the top 13 bits of a 31-bit key
 constexpr int kBtCells = 1 << (31 - kBtShift);
 constexpr int kBtStride = kBtCells + 8;
 constexpr unsigned kChunk = 16384;           // queries per search work item
@@ -108,19 +108,22 @@ __device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned* s_warp
 __device__ __forceinline__ uint32_t canonical(uint32_t q) { return q > kMax ? 0u : q; }
 
 // bucket(q) = number of splitters < q; split[i], i in [1, nb), are the splitters (split[0] = 0, split[nb] = MAX).
-// bt[c] = number of splitters whose top 12 bits are < c.
+// bt[c] & 0x7fff = number of splitters whose top 13 bits are < c; bit 15 is set when two or more splitters share
+// the prefix c (skewed keys), otherwise one compare against the next splitter settles it: a splitter in a later
+// cell is above q anyway.
 __device__ __forceinline__ unsigned bk_bucket(const uint16_t* __restrict__ bt, const uint32_t* __restrict__ split, uint32_t q) {
     const unsigned c = q >> kBtShift;
-    unsigned lo = bt[c], hi = bt[c + 1];
-    if (hi - lo > 8u) {  // skewed keys: many splitters share the prefix
+    const unsigned e = bt[c];
+    unsigned lo = e & 0x7fffu;
+    if (e & 0x8000u) {
+        unsigned hi = bt[c + 1] & 0x7fffu;
         while (lo < hi) {
             const unsigned m = (lo + hi) >> 1;
             if (split[m + 1] < q) lo = m + 1; else hi = m;
         }
-    } else {
-        while (lo < hi && split[lo + 1] < q) lo++;
+        return lo;
     }
-    return lo;
+    return lo + (split[lo + 1] < q ? 1u : 0u);
 }
 
 struct BkView {
@@ -132,14 +135,37 @@ struct BkView {
 // ------------------------------------------------------------------------------------------------
 // rank: bucket id, stable tile-local position and tile x bucket counts
 // ------------------------------------------------------------------------------------------------
-template <int BITS>
+// peers &= (bit BIT of b set) ? ballot(bit set) : ~ballot(bit set), for BIT in [BIT, BITS): the lanes whose bucket id
+// equals this lane's.  Spelled out in PTX so that a bit costs 4 instructions (LOP3->P, VOTE, SEL, LOP3).
+template <int BIT, int BITS>
+__device__ __forceinline__ void ballot_bits(unsigned& peers, unsigned b) {
+    if constexpr (BIT < BITS) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            ".reg .b32 t, v, m;\n"
+            "and.b32 t, %1, %2;\n"
+            "setp.ne.u32 p, t, 0;\n"
+            "vote.sync.ballot.b32 v, p, 0xffffffff;\n"
+            "selp.b32 m, 0, 0xffffffff, p;\n"
+            "lop3.b32 %0, %0, v, m, 0x60;\n"  // a & (b ^ c)
+            "}\n"
+            : "+r"(peers)
+            : "r"(b), "n"(1u << BIT));
+        ballot_bits<BIT + 1, BITS>(peers, b);
+    }
+}
+
+// FULL: every tile in [tile_begin, tile_end) holds kTile queries (the partial last tile gets its own launch).
+// BITS < 0: instead of ballots the lanes CLAIM their bucket's counter: everyone writes count + 1 tagged with its
+// lane id (5 tag bits above the 11 count bits), the lane whose tag sticks takes rank = count, the others retry.
+template <int BITS, bool FULL>
 __global__ void __launch_bounds__(kThreads, 2)
-bk_rank_kernel(const BkView v, const uint32_t* __restrict__ qs, size_t nq, unsigned ntiles, uint32_t* __restrict__ counts,
-               uint16_t* __restrict__ lpos16) {
+bk_rank_kernel(const BkView v, const uint32_t* __restrict__ qs, size_t nq, unsigned tile_begin, unsigned tile_end,
+               uint32_t* __restrict__ counts, uint16_t* __restrict__ lpos16) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint16_t* cnt = reinterpret_cast<uint16_t*>(smem_raw);                       // [kWarps][nbp]
-    uint16_t* s_start = cnt + (size_t)kWarps * v.nbp;                             // [nbp]
-    uint16_t* s_bt = s_start + v.nbp;                                             // [kBtStride]
+    uint16_t* s_bt = cnt + (size_t)kWarps * v.nbp;                                // [kBtStride]
     uint32_t* s_split = reinterpret_cast<uint32_t*>(s_bt + kBtStride);            // [nbp + 1]
     __shared__ unsigned s_warp[kWarps + 1];
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -148,80 +174,110 @@ bk_rank_kernel(const BkView v, const uint32_t* __restrict__ qs, size_t nq, unsig
     for (unsigned i = tid; i <= v.nbp; i += kThreads) s_split[i] = i <= v.nb ? v.split[i] : kMax;
     uint16_t* cntw = cnt + (size_t)warp * v.nbp;
 
-    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (unsigned tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
         {   // zero the per-warp counters
             uint4* c4 = reinterpret_cast<uint4*>(cnt);
             const unsigned n16 = kWarps * v.nbp / 8;
             for (unsigned i = tid; i < n16; i += kThreads) c4[i] = make_uint4(0, 0, 0, 0);
         }
         const size_t tile_base = (size_t)tile * kTile;
-        const unsigned tile_n = (unsigned)min((size_t)kTile, nq - tile_base);
+        const unsigned tile_n = FULL ? (unsigned)kTile : (unsigned)min((size_t)kTile, nq - tile_base);
+        const uint32_t* tq = qs + tile_base + warp * (kItems * 32) + lane;
+        const unsigned i0 = warp * (kItems * 32) + lane;
         __syncthreads();  // tables + zeroed counters visible
         uint32_t pk[kItems];  // bucket | rank << 16; 0xffffffff = no query
 #pragma unroll
-        for (int r = 0; r < kItems; r++) {
-            const unsigned i = warp * (kItems * 32) + r * 32 + lane;
-            pk[r] = i < tile_n ? __ldcs(qs + tile_base + i) : 0u;
-        }
+        for (int r = 0; r < kItems; r++) pk[r] = (FULL || i0 + r * 32 < tile_n) ? __ldcs(tq + r * 32) : 0u;
+#pragma unroll
+        for (int r = 0; r < kItems; r++)
+            pk[r] = (FULL || i0 + r * 32 < tile_n) ? bk_bucket(s_bt, s_split, canonical(pk[r])) : 0xffffffffu;
+        // rank inside the warp's 1024 queries: lanes with the same bucket find each other by ballots over
+        // the bucket bits; the lowest of them bumps the warp's private counter
 #pragma unroll
         for (int r = 0; r < kItems; r++) {
-            const unsigned i = warp * (kItems * 32) + r * 32 + lane;
-            pk[r] = i < tile_n ? bk_bucket(s_bt, s_split, canonical(pk[r])) : 0xffffffffu;
-        }
-        // stable rank inside the warp's 1024 queries: lanes with the same bucket find each other by
-        // ballots over the bucket bits; the lowest of them bumps the warp's private counter
-#pragma unroll
-        for (int r = 0; r < kItems; r++) {
-            const bool valid = pk[r] != 0xffffffffu;
+            const bool valid = FULL || pk[r] != 0xffffffffu;
             const unsigned b = valid ? pk[r] : 0u;
-            unsigned peers = __ballot_sync(kFull, valid);
-#pragma unroll
-            for (int bit = 0; bit < BITS; bit++) {
-                const bool one = (b >> bit) & 1u;
-                const unsigned vote = __ballot_sync(kFull, one);
-                peers &= one ? vote : ~vote;
+            if constexpr (BITS < 0) {
+                bool done = !valid;
+                unsigned w = 0, rank = 0;
+                do {
+                    if (!done) w = cntw[b];
+                    __syncwarp();
+                    if (!done) cntw[b] = (uint16_t)(((w & 0x7ffu) + 1u) | (lane << 11));
+                    __syncwarp();
+                    if (!done && (unsigned)(cntw[b] >> 11) == lane) { rank = w & 0x7ffu; done = true; }
+                } while (!__all_sync(kFull, done));
+                if (valid) pk[r] = b | (rank << 16);
+            } else {
+                unsigned peers = FULL ? kFull : __ballot_sync(kFull, valid);
+                ballot_bits<0, BITS>(peers, b);
+                const unsigned before = peers & lt_mask;
+                const unsigned old = valid ? cntw[b] : 0u;
+                __syncwarp();
+                if (valid && before == 0u) cntw[b] = (uint16_t)(old + __popc(peers));
+                __syncwarp();
+                if (valid) pk[r] = b | ((old + __popc(before)) << 16);
             }
-            const unsigned before = peers & lt_mask;
-            const unsigned old = valid ? cntw[b] : 0u;
-            __syncwarp();
-            if (valid && before == 0u) cntw[b] = (uint16_t)(old + __popc(peers));
-            __syncwarp();
-            if (valid) pk[r] = b | ((old + __popc(before)) << 16);
         }
         __syncthreads();
         // per bucket: exclusive scan over the warps, total to the count matrix, start inside the tile
-        unsigned tot[4], sum = 0;
+        unsigned tot[4] = {0, 0, 0, 0}, sum = 0;
+        if (v.bpt == 4) {  // 2048 buckets: four consecutive 16-bit counters per thread and warp in one 8-byte access
+            uint2* c2 = reinterpret_cast<uint2*>(cnt) + tid;
 #pragma unroll
-        for (unsigned k = 0; k < 4; k++) {
-            tot[k] = 0;
-            if (k < v.bpt) {
-                const unsigned b = tid * v.bpt + k;
-                unsigned run = 0;
-#pragma unroll
-                for (int w = 0; w < kWarps; w++) {
-                    const unsigned c = cnt[(size_t)w * v.nbp + b];
-                    cnt[(size_t)w * v.nbp + b] = (uint16_t)run;
-                    run += c;
-                }
-                tot[k] = run;
-                sum += run;
-                counts[(size_t)tile * v.nbp + b] = run;
+            for (int w = 0; w < kWarps; w++) {
+                const uint2 c = c2[(size_t)w * (v.nbp / 4)];
+                c2[(size_t)w * (v.nbp / 4)] = make_uint2(tot[0] | (tot[1] << 16), tot[2] | (tot[3] << 16));
+                tot[0] += c.x & 0x7ffu; tot[1] += (c.x >> 16) & 0x7ffu; tot[2] += c.y & 0x7ffu; tot[3] += (c.y >> 16) & 0x7ffu;  // (claim tags masked off)
             }
+            sum = tot[0] + tot[1] + tot[2] + tot[3];
+            *reinterpret_cast<uint4*>(counts + (size_t)tile * v.nbp + tid * 4) = make_uint4(tot[0], tot[1], tot[2], tot[3]);
+        } else {
+#pragma unroll
+            for (unsigned k = 0; k < 4; k++)
+                if (k < v.bpt) {
+                    const unsigned b = tid * v.bpt + k;
+                    unsigned run = 0;
+#pragma unroll
+                    for (int w = 0; w < kWarps; w++) {
+                        const unsigned c = cnt[(size_t)w * v.nbp + b] & 0x7ffu;
+                        cnt[(size_t)w * v.nbp + b] = (uint16_t)run;
+                        run += c;
+                    }
+                    tot[k] = run;
+                    sum += run;
+                    counts[(size_t)tile * v.nbp + b] = run;
+                }
         }
         unsigned total;
-        unsigned base = block_excl_scan(sum, s_warp, &total);
+        const unsigned base = block_excl_scan(sum, s_warp, &total);
+        // fold the bucket's start inside the tile into the per-warp bases
+        if (v.bpt == 4) {
+            const unsigned s0 = base, s1 = s0 + tot[0], s2 = s1 + tot[1], s3 = s2 + tot[2];
+            const uint2 add = make_uint2(s0 | (s1 << 16), s2 | (s3 << 16));
+            uint2* c2 = reinterpret_cast<uint2*>(cnt) + tid;
 #pragma unroll
-        for (unsigned k = 0; k < 4; k++)
-            if (k < v.bpt) { s_start[tid * v.bpt + k] = (uint16_t)base; base += tot[k]; }
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < kItems; r++) {
-            const unsigned i = warp * (kItems * 32) + r * 32 + lane;
-            if (i < tile_n) {
-                const unsigned b = pk[r] & 0xffffu;
-                lpos16[tile_base + i] = (uint16_t)(s_start[b] + cntw[b] + (pk[r] >> 16));
+            for (int w = 0; w < kWarps; w++) {
+                uint2 c = c2[(size_t)w * (v.nbp / 4)];
+                c.x += add.x; c.y += add.y;  // 16-bit lanes cannot carry: every sum is < kTile
+                c2[(size_t)w * (v.nbp / 4)] = c;
             }
+        } else {
+            unsigned st = base;
+#pragma unroll
+            for (unsigned k = 0; k < 4; k++)
+                if (k < v.bpt) {
+                    const unsigned b = tid * v.bpt + k;
+#pragma unroll
+                    for (int w = 0; w < kWarps; w++) cnt[(size_t)w * v.nbp + b] += (uint16_t)st;
+                    st += tot[k];
+                }
         }
+        __syncthreads();
+        uint16_t* tl = lpos16 + tile_base + warp * (kItems * 32) + lane;
+#pragma unroll
+        for (int r = 0; r < kItems; r++)
+            if (FULL || i0 + r * 32 < tile_n) tl[r * 32] = (uint16_t)(cntw[pk[r] & 0xffffu] + (pk[r] >> 16));
         __syncthreads();  // counters are zeroed again at the top
     }
 }
@@ -477,15 +533,19 @@ __global__ void bk_split_kernel(const uint32_t* __restrict__ sep, unsigned nb, u
     for (unsigned b = blockIdx.x * blockDim.x + threadIdx.x; b <= nb; b += gridDim.x * blockDim.x)
         split[b] = b == 0 ? 0u : (b == nb ? kMax : sep[(size_t)b * r - 1]);
 }
-// bt[c] = number of splitters split[1..nb-1] whose top bits are < c, c in [0, kBtCells]
+// bt[c] = number of splitters split[1..nb-1] whose top bits are < c, c in [0, kBtCells]; bit 15: >= 2 splitters in cell c
 __global__ void bk_bt_kernel(const uint32_t* __restrict__ split, unsigned nb, uint16_t* __restrict__ bt) {
     for (unsigned c = blockIdx.x * blockDim.x + threadIdx.x; c < (unsigned)kBtStride; c += gridDim.x * blockDim.x) {
-        unsigned l = 0, h = nb - 1;  // count over i in [1, nb): index i = l + 1
-        while (l < h) {
-            const unsigned m = (l + h) >> 1;
-            if ((split[m + 1] >> kBtShift) < c) l = m + 1; else h = m;
+        unsigned cnt[2];
+        for (int k = 0; k < 2; k++) {
+            unsigned l = 0, h = nb - 1;  // count over i in [1, nb): index i = l + 1
+            while (l < h) {
+                const unsigned m = (l + h) >> 1;
+                if ((split[m + 1] >> kBtShift) < c + k) l = m + 1; else h = m;
+            }
+            cnt[k] = l;
         }
-        bt[c] = c <= (unsigned)kBtCells ? (uint16_t)l : 0;
+        bt[c] = c <= (unsigned)kBtCells ? (uint16_t)(cnt[0] | (cnt[1] - cnt[0] >= 2u ? 0x8000u : 0u)) : 0;
     }
 }
 // Per bucket: lo = split[b], shift = smallest s with (split[b+1] - lo) >> s < kCells, and
@@ -578,11 +638,19 @@ bool scratch_ensure(Scratch& s, int device, size_t nq, bool want_idx, unsigned n
 }
 
 template <int BITS>
-void launch_rank(const BkView& v, int grid, size_t smem, cudaStream_t st, const uint32_t* qs, size_t nq, unsigned ntiles, uint32_t* counts,
+void launch_rank(const BkView& v, int sms, size_t smem, cudaStream_t st, const uint32_t* qs, size_t nq, unsigned ntiles, uint32_t* counts,
                  uint16_t* lpos) {
-    auto kern = bk_rank_kernel<BITS>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, kThreads, smem, st>>>(v, qs, nq, ntiles, counts, lpos);
+    const unsigned full = (unsigned)(nq / kTile);  // tiles with kTile queries; a partial last tile gets the checked variant
+    if (full) {
+        auto kern = bk_rank_kernel<BITS, true>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<(unsigned)std::min<size_t>(full, (size_t)sms * 2), kThreads, smem, st>>>(v, qs, nq, 0, full, counts, lpos);
+    }
+    if (full < ntiles) {
+        auto kern = bk_rank_kernel<BITS, false>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<ntiles - full, kThreads, smem, st>>>(v, qs, nq, full, ntiles, counts, lpos);
+    }
 }
 
 template <bool GATHER, typename OutT>
@@ -647,7 +715,7 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
     const int sms = sm_count(dev);
     const unsigned bpt = a.nbp / kThreads;
     BkView v{a.d_bt, a.d_split, a.nb, a.nbp, bpt};
-    const size_t smem_rank = (size_t)kWarps * a.nbp * 2 + (size_t)a.nbp * 2 + (size_t)kBtStride * 2 + ((size_t)a.nbp + 1) * 4 + 16;
+    const size_t smem_rank = (size_t)kWarps * a.nbp * 2 + (size_t)kBtStride * 2 + ((size_t)a.nbp + 1) * 4 + 16;
     const size_t smem_move = (size_t)kTile * 4 + (size_t)a.nbp * 4 + (size_t)kTile * 2;
     const size_t smem_search = (size_t)a.r * 4 + (size_t)kJumpStride * 2;
     BkSearchParams sp{a.d_sep, a.d_jump, a.d_meta, idx->d_tree + idx->offsets[idx->levels - 1] * 16, a.r, a.m8, (unsigned long long)idx->n};
@@ -667,8 +735,9 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
         const uint32_t* qs = d_qs + off;
         nev = 0;
         mark();
-        switch (a.bits) {
-#define SST_BK_RANK(B) case B: launch_rank<B>(v, grid, smem_rank, st, qs, cnt, ntiles, s.counts, s.lpos); break;
+        switch (env_int("SST_BK_CLAIM", 0) ? -1 : (int)a.bits) {
+            case -1: launch_rank<-1>(v, sms, smem_rank, st, qs, cnt, ntiles, s.counts, s.lpos); break;
+#define SST_BK_RANK(B) case B: launch_rank<B>(v, sms, smem_rank, st, qs, cnt, ntiles, s.counts, s.lpos); break;
             SST_BK_RANK(0) SST_BK_RANK(1) SST_BK_RANK(2) SST_BK_RANK(3) SST_BK_RANK(4) SST_BK_RANK(5)
             SST_BK_RANK(6) SST_BK_RANK(7) SST_BK_RANK(8) SST_BK_RANK(9) SST_BK_RANK(10) SST_BK_RANK(11)
 #undef SST_BK_RANK
