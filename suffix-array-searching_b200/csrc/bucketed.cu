@@ -38,7 +38,7 @@ constexpr int kTile = 16384;                 // queries per partition tile (64 K
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kItems = kTile / kThreads;     // 32 queries per thread
-constexpr int kCells = 8192;                 // jump-table cells per bucket
+constexpr int kCells = 16384;                // jump-table cells per bucket (about one separator per cell)
 constexpr int kJumpStride = kCells + 8;      // u16 entries per bucket (multiple of 16 bytes)
 constexpr int kBtShift = 18;                 // bucket table over the top 13 bits of a 31-bit key
 constexpr int kBtCells = 1 << (31 - kBtShift);
@@ -160,21 +160,13 @@ __device__ __forceinline__ void ballot_bits(unsigned& peers, unsigned b) {
 // BITS < 0: instead of ballots the lanes CLAIM their bucket's counter: everyone writes count + 1 tagged with its
 // lane id (5 tag bits above the 11 count bits), the lane whose tag sticks takes rank = count, the others retry.
 template <int BITS, bool FULL>
-__global__ void __launch_bounds__(kThreads, 2)
-bk_rank_kernel(const BkView v, const uint32_t* __restrict__ qs, size_t nq, unsigned tile_begin, unsigned tile_end,
-               uint32_t* __restrict__ counts, uint16_t* __restrict__ lpos16) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint16_t* cnt = reinterpret_cast<uint16_t*>(smem_raw);                       // [kWarps][nbp]
-    uint16_t* s_bt = cnt + (size_t)kWarps * v.nbp;                                // [kBtStride]
-    uint32_t* s_split = reinterpret_cast<uint32_t*>(s_bt + kBtStride);            // [nbp + 1]
-    __shared__ unsigned s_warp[kWarps + 1];
+__device__ __forceinline__ void rank_tile(const BkView& v, const uint32_t* __restrict__ qs, size_t nq, unsigned tile, uint32_t* __restrict__ counts,
+                                          uint16_t* __restrict__ lpos16, uint16_t* cnt, const uint16_t* s_bt, const uint32_t* s_split,
+                                          unsigned* s_warp) {
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    for (unsigned i = tid; i < (unsigned)kBtStride; i += kThreads) s_bt[i] = i <= (unsigned)kBtCells ? v.bt[i] : 0;
-    for (unsigned i = tid; i <= v.nbp; i += kThreads) s_split[i] = i <= v.nb ? v.split[i] : kMax;
     uint16_t* cntw = cnt + (size_t)warp * v.nbp;
-
-    for (unsigned tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+    {
         {   // zero the per-warp counters
             uint4* c4 = reinterpret_cast<uint4*>(cnt);
             const unsigned n16 = kWarps * v.nbp / 8;
@@ -282,6 +274,24 @@ bk_rank_kernel(const BkView v, const uint32_t* __restrict__ qs, size_t nq, unsig
     }
 }
 
+template <int BITS>
+__global__ void __launch_bounds__(kThreads, 2)
+bk_rank_kernel(const BkView v, const uint32_t* __restrict__ qs, size_t nq, unsigned ntiles, uint32_t* __restrict__ counts,
+               uint16_t* __restrict__ lpos16) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint16_t* cnt = reinterpret_cast<uint16_t*>(smem_raw);                       // [kWarps][nbp]
+    uint16_t* s_bt = cnt + (size_t)kWarps * v.nbp;                                // [kBtStride]
+    uint32_t* s_split = reinterpret_cast<uint32_t*>(s_bt + kBtStride);            // [nbp + 1]
+    __shared__ unsigned s_warp[kWarps + 1];
+    const unsigned tid = threadIdx.x;
+    for (unsigned i = tid; i < (unsigned)kBtStride; i += kThreads) s_bt[i] = i <= (unsigned)kBtCells ? v.bt[i] : 0;
+    for (unsigned i = tid; i <= v.nbp; i += kThreads) s_split[i] = i <= v.nb ? v.split[i] : kMax;
+    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if ((size_t)(tile + 1) * kTile <= nq) rank_tile<BITS, true>(v, qs, nq, tile, counts, lpos16, cnt, s_bt, s_split, s_warp);
+        else rank_tile<BITS, false>(v, qs, nq, tile, counts, lpos16, cnt, s_bt, s_split, s_warp);  // partial last tile
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // plan: scan of the count matrix (tiles x buckets) and the work-item list of the search kernel
 // ------------------------------------------------------------------------------------------------
@@ -306,10 +316,13 @@ bk_plan_kernel(uint32_t* __restrict__ gsum, unsigned ngroups, unsigned nbp, uint
         const unsigned b = tid * 2 + k;
         if (b < nbp) {
             unsigned run = 0;
-            for (unsigned g = 0; g < ngroups; g++) {
-                const unsigned c = gsum[(size_t)g * nbp + b];
-                gsum[(size_t)g * nbp + b] = run;
-                run += c;
+            for (unsigned g0 = 0; g0 < ngroups; g0 += 16) {  // 16 independent loads in flight, then the running sums
+                unsigned c[16];
+#pragma unroll
+                for (unsigned j = 0; j < 16; j++) c[j] = g0 + j < ngroups ? gsum[(size_t)(g0 + j) * nbp + b] : 0u;
+#pragma unroll
+                for (unsigned j = 0; j < 16; j++)
+                    if (g0 + j < ngroups) { gsum[(size_t)(g0 + j) * nbp + b] = run; run += c[j]; }
             }
             tot[k] = run;
         }
@@ -342,33 +355,49 @@ bk_offsets_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// scatter (GATHER = false): queries of a tile -> bucket order; gather (GATHER = true): results back
+// scatter (GATHER = false): queries of a tile -> bucket order; gather (GATHER = true): results back.
+// A full tile with 16-byte aligned buffers takes the vector path: four queries per load (LDG.128 + LDG.64 of the
+// positions), run elements fetched by 4-byte cp.async (LDGSTS) straight into shared memory so that all 32 per
+// thread are in flight at once; a partial last tile or an odd pointer takes the checked scalar path.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
 template <bool GATHER, typename OutT>
 __global__ void __launch_bounds__(kThreads, 2)
 bk_move_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offs, const uint16_t* __restrict__ lpos16,
-               unsigned nbp, unsigned bpt, unsigned ntiles, size_t nq, const uint32_t* __restrict__ src, OutT* __restrict__ dst) {
+               unsigned nbp, unsigned bpt, unsigned ntiles, size_t nq, int aligned, const uint32_t* __restrict__ src,
+               OutT* __restrict__ dst) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t* s_tile = reinterpret_cast<uint32_t*>(smem_raw);        // [kTile] in bucket order
     uint32_t* s_delta = s_tile + kTile;                                // [nbp] global offset - local start
     uint16_t* s_map = reinterpret_cast<uint16_t*>(s_delta + nbp);      // [kTile] bucket of each local position
     __shared__ unsigned s_warp[kWarps + 1];
     const unsigned tid = threadIdx.x;
+    constexpr int kVec = kItems / 4;  // 8 groups of 4 consecutive queries per thread
+    unsigned c[4] = {0, 0, 0, 0}, o[4] = {0, 0, 0, 0};
+    auto load_row = [&](unsigned tile) {  // this thread's buckets of the count / offset rows of `tile`
+        if (bpt == 4) {
+            const uint4 c4 = *reinterpret_cast<const uint4*>(counts + (size_t)tile * nbp + tid * 4);
+            const uint4 o4 = *reinterpret_cast<const uint4*>(offs + (size_t)tile * nbp + tid * 4);
+            c[0] = c4.x; c[1] = c4.y; c[2] = c4.z; c[3] = c4.w;
+            o[0] = o4.x; o[1] = o4.y; o[2] = o4.z; o[3] = o4.w;
+        } else {
+#pragma unroll
+            for (unsigned k = 0; k < 4; k++)
+                if (k < bpt) { c[k] = counts[(size_t)tile * nbp + tid * bpt + k]; o[k] = offs[(size_t)tile * nbp + tid * bpt + k]; }
+        }
+    };
+    if (blockIdx.x < ntiles) load_row(blockIdx.x);
     for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const size_t tile_base = (size_t)tile * kTile;
         const unsigned tile_n = (unsigned)min((size_t)kTile, nq - tile_base);
-        unsigned c[4], o[4], sum = 0;
-#pragma unroll
-        for (unsigned k = 0; k < 4; k++) {
-            c[k] = 0; o[k] = 0;
-            if (k < bpt) {
-                c[k] = counts[(size_t)tile * nbp + tid * bpt + k];
-                o[k] = offs[(size_t)tile * nbp + tid * bpt + k];
-                sum += c[k];
-            }
-        }
         unsigned total;
-        unsigned base = block_excl_scan(sum, s_warp, &total);
+        unsigned base = block_excl_scan(c[0] + c[1] + c[2] + c[3], s_warp, &total);
 #pragma unroll
         for (unsigned k = 0; k < 4; k++)
             if (k < bpt) {
@@ -377,8 +406,51 @@ bk_move_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__
                 for (unsigned j = 0; j < c[k]; j++) s_map[base + j] = (uint16_t)b;
                 base += c[k];
             }
+        if (tile + gridDim.x < ntiles) load_row(tile + gridDim.x);  // next tile's rows: in flight during this tile
         __syncthreads();
-        if constexpr (!GATHER) {
+        if (aligned && tile_n == (unsigned)kTile) {
+            const uint2* l2 = reinterpret_cast<const uint2*>(lpos16 + tile_base);
+            if constexpr (!GATHER) {
+                const uint4* q4 = reinterpret_cast<const uint4*>(src + tile_base);
+                uint4 q[kVec];
+                uint2 l[kVec];
+#pragma unroll
+                for (int r = 0; r < kVec; r++) { q[r] = __ldcs(q4 + r * kThreads + tid); l[r] = __ldcs(l2 + r * kThreads + tid); }
+#pragma unroll
+                for (int r = 0; r < kVec; r++) {
+                    s_tile[l[r].x & 0xffffu] = canonical(q[r].x); s_tile[l[r].x >> 16] = canonical(q[r].y);
+                    s_tile[l[r].y & 0xffffu] = canonical(q[r].z); s_tile[l[r].y >> 16] = canonical(q[r].w);
+                }
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < kItems; r++) {  // runs: consecutive lanes write consecutive words
+                    const unsigned i = r * kThreads + tid;
+                    dst[s_delta[s_map[i]] + i] = (OutT)s_tile[i];
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < kItems; r++) {
+                    const unsigned i = r * kThreads + tid;
+                    cp_async4(s_tile + i, src + (s_delta[s_map[i]] + i));
+                }
+                uint2 l[kVec];
+#pragma unroll
+                for (int r = 0; r < kVec; r++) l[r] = __ldcs(l2 + r * kThreads + tid);
+                cp_async_wait_all();
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < kVec; r++) {
+                    const uint32_t v0 = s_tile[l[r].x & 0xffffu], v1 = s_tile[l[r].x >> 16], v2 = s_tile[l[r].y & 0xffffu], v3 = s_tile[l[r].y >> 16];
+                    OutT* d = dst + tile_base + (size_t)(r * kThreads + tid) * 4;
+                    if constexpr (sizeof(OutT) == 4) {
+                        __stcs(reinterpret_cast<uint4*>(d), make_uint4(v0, v1, v2, v3));
+                    } else {
+                        __stcs(reinterpret_cast<ulonglong2*>(d), make_ulonglong2(v0, v1));
+                        __stcs(reinterpret_cast<ulonglong2*>(d) + 1, make_ulonglong2(v2, v3));
+                    }
+                }
+            }
+        } else if constexpr (!GATHER) {
 #pragma unroll 8
             for (int r = 0; r < kItems; r++) {
                 const unsigned i = r * kThreads + tid;
@@ -468,27 +540,55 @@ bk_search_kernel(const BkSearchParams p, const uint32_t* __restrict__ qb, const 
         const unsigned sh = mt.y;
         const unsigned qbeg = bstart[b] + it.y * kChunk, qend = min(qbeg + kChunk, bstart[b + 1]);
         const unsigned long long hbase = (unsigned long long)b * p.r;
+        uint32_t qn[U];  // queries of the next round: their loads stay in flight while this round is answered
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const unsigned i = qbeg + tid + u * kThreads;
+            qn[u] = i < qend ? __ldcs(qb + i) : lo;
+        }
         for (unsigned i0 = qbeg + tid; i0 < qend; i0 += kThreads * U) {
             uint32_t q[U];
             unsigned a[U];
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                const unsigned i = i0 + u * kThreads;
-                q[u] = i < qend ? __ldcs(qb + i) : lo;
+                q[u] = qn[u];
+                const unsigned i = i0 + (U + u) * kThreads;
+                qn[u] = i < qend ? __ldcs(qb + i) : lo;
+            }
+            // rank among the bucket's separators: jump-table cell, then three unconditional probes (independent
+            // shared loads for all U queries); a cell with more separators below q continues in a loop (rare)
+            unsigned l[U], h[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const unsigned x = (q[u] - lo) >> sh;
+                l[u] = s_jump[x];
+                h[u] = s_jump[x + 1];
+            }
+            uint32_t s0[U], s1[U], s2[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                s0[u] = s_sep[min(l[u], p.r - 1u)];
+                s1[u] = s_sep[min(l[u] + 1u, p.r - 1u)];
+                s2[u] = s_sep[min(l[u] + 2u, p.r - 1u)];
             }
 #pragma unroll
-            for (int u = 0; u < U; u++) {  // rank among the bucket's separators
-                const unsigned x = (q[u] - lo) >> sh;
-                unsigned l = s_jump[x], h = s_jump[x + 1];
-                if (h - l > 8u) {
-                    while (l < h) {
-                        const unsigned m = (l + h) >> 1;
-                        if (s_sep[m] < q[u]) l = m + 1; else h = m;
+            for (int u = 0; u < U; u++) {
+                const bool c0 = l[u] < h[u] && s0[u] < q[u];
+                const bool c1 = c0 && l[u] + 1u < h[u] && s1[u] < q[u];
+                const bool c2 = c1 && l[u] + 2u < h[u] && s2[u] < q[u];
+                unsigned pos = l[u] + (c0 ? 1u : 0u) + (c1 ? 1u : 0u) + (c2 ? 1u : 0u);
+                if (c2) {
+                    unsigned hh = h[u];
+                    if (hh - pos > 8u) {
+                        while (pos < hh) {
+                            const unsigned m = (pos + hh) >> 1;
+                            if (s_sep[m] < q[u]) pos = m + 1; else hh = m;
+                        }
+                    } else {
+                        while (pos < hh && s_sep[pos] < q[u]) pos++;
                     }
-                } else {
-                    while (l < h && s_sep[l] < q[u]) l++;
                 }
-                a[u] = l;
+                a[u] = pos;
             }
             uint32_t ks[U][8];
             unsigned long long hn[U];
@@ -640,25 +740,18 @@ bool scratch_ensure(Scratch& s, int device, size_t nq, bool want_idx, unsigned n
 template <int BITS>
 void launch_rank(const BkView& v, int sms, size_t smem, cudaStream_t st, const uint32_t* qs, size_t nq, unsigned ntiles, uint32_t* counts,
                  uint16_t* lpos) {
-    const unsigned full = (unsigned)(nq / kTile);  // tiles with kTile queries; a partial last tile gets the checked variant
-    if (full) {
-        auto kern = bk_rank_kernel<BITS, true>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<(unsigned)std::min<size_t>(full, (size_t)sms * 2), kThreads, smem, st>>>(v, qs, nq, 0, full, counts, lpos);
-    }
-    if (full < ntiles) {
-        auto kern = bk_rank_kernel<BITS, false>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<ntiles - full, kThreads, smem, st>>>(v, qs, nq, full, ntiles, counts, lpos);
-    }
+    auto kern = bk_rank_kernel<BITS>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<(unsigned)std::min<size_t>(ntiles, (size_t)sms * 2), kThreads, smem, st>>>(v, qs, nq, ntiles, counts, lpos);
 }
 
 template <bool GATHER, typename OutT>
-void launch_move(int grid, size_t smem, cudaStream_t st, const Scratch& s, unsigned nbp, unsigned bpt, unsigned ntiles, size_t nq,
+void launch_move(int sms, size_t smem, cudaStream_t st, const Scratch& s, unsigned nbp, unsigned bpt, unsigned ntiles, size_t nq,
                  const uint32_t* src, OutT* dst) {
+    const int aligned = (((uintptr_t)src | (uintptr_t)dst) & 15u) == 0 && env_int("SST_BK_VEC", 1);
     auto kern = bk_move_kernel<GATHER, OutT>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, kThreads, smem, st>>>(s.counts, s.offs, s.lpos, nbp, bpt, ntiles, nq, src, dst);
+    kern<<<(unsigned)std::min<size_t>(ntiles, (size_t)sms * 2), kThreads, smem, st>>>(s.counts, s.offs, s.lpos, nbp, bpt, ntiles, nq, aligned, src, dst);
 }
 
 }  // namespace
@@ -735,7 +828,7 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
         const uint32_t* qs = d_qs + off;
         nev = 0;
         mark();
-        switch (env_int("SST_BK_CLAIM", 0) ? -1 : (int)a.bits) {
+        switch (env_int("SST_BK_CLAIM", 1) ? -1 : (int)a.bits) {
             case -1: launch_rank<-1>(v, sms, smem_rank, st, qs, cnt, ntiles, s.counts, s.lpos); break;
 #define SST_BK_RANK(B) case B: launch_rank<B>(v, sms, smem_rank, st, qs, cnt, ntiles, s.counts, s.lpos); break;
             SST_BK_RANK(0) SST_BK_RANK(1) SST_BK_RANK(2) SST_BK_RANK(3) SST_BK_RANK(4) SST_BK_RANK(5)
@@ -749,7 +842,7 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
         bk_plan_kernel<<<1, 1024, 0, st>>>(s.gsum, ngroups, a.nbp, s.bstart, s.items, s.ctrl);
         bk_offsets_kernel<<<mgrid, 256, 0, st>>>(s.counts, s.gsum, s.bstart, ntiles, a.nbp, s.offs);
         mark();
-        launch_move<false, uint32_t>(grid, smem_move, st, s, a.nbp, bpt, ntiles, cnt, qs, s.qb);
+        launch_move<false, uint32_t>(sms, smem_move, st, s, a.nbp, bpt, ntiles, cnt, qs, s.qb);
         mark();
         if (d_idx) {
             auto kern = bk_search_kernel<true>;
@@ -761,8 +854,8 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
             kern<<<sms * 2, kThreads, smem_search, st>>>(sp, s.qb, s.bstart, s.items, s.ctrl, s.rb, s.ib);
         }
         mark();
-        launch_move<true, uint32_t>(grid, smem_move, st, s, a.nbp, bpt, ntiles, cnt, s.rb, d_vals + off);
-        if (d_idx) launch_move<true, unsigned long long>(grid, smem_move, st, s, a.nbp, bpt, ntiles, cnt, s.ib, d_idx + off);
+        launch_move<true, uint32_t>(sms, smem_move, st, s, a.nbp, bpt, ntiles, cnt, s.rb, d_vals + off);
+        if (d_idx) launch_move<true, unsigned long long>(sms, smem_move, st, s, a.nbp, bpt, ntiles, cnt, s.ib, d_idx + off);
         mark();
         if (timing && nev == 6 && cudaEventSynchronize(ev[5]) == cudaSuccess) {
             float t[5];

@@ -110,3 +110,20 @@ def test_bucketed_streams_and_repeats(gpu, oracle, monkeypatch):
     for va, vb in outs:
         assert np.array_equal(va.cpu().numpy().view(np.uint32), ea)
         assert np.array_equal(vb.cpu().numpy().view(np.uint32), eb)
+
+
+def test_bucketed_unaligned_device_buffers(gpu, oracle, monkeypatch):
+    """The vector move kernels need 16-byte aligned buffers; a sliced tensor takes the checked scalar kernels."""
+    import torch
+
+    sst = gpu
+    monkeypatch.setenv("SST_BK_MIN_N", "0")
+    monkeypatch.setenv("SST_BK_R", "128")
+    vals = gen_vals(300_000, seed=15)
+    t = sst.STree16.new_params(vals, True, False, False)
+    qs = gen_queries(100_000, seed=16, vals=vals)
+    ev, ei = oracle.lower_bound(vals, qs)
+    d = torch.from_numpy(qs.view(np.int32)).cuda()
+    for k in (1, 2, 3, 4):
+        v, i = t.query(d[k:], sst.SCHEME_BUCKETED, want_index=True)
+        assert np.array_equal(v.cpu().numpy().view(np.uint32), ev[k:]) and np.array_equal(i.cpu().numpy().astype(np.uint64), ei[k:]), k
