@@ -159,7 +159,7 @@ __device__ __forceinline__ void ballot_bits(unsigned& peers, unsigned b) {
 // FULL: every tile in [tile_begin, tile_end) holds kTile queries (the partial last tile gets its own launch).
 // BITS < 0: instead of ballots the lanes CLAIM their bucket's counter: everyone writes count + 1 tagged with its
 // lane id (5 tag bits above the 11 count bits), the lane whose tag sticks takes rank = count, the others retry.
-template <int BITS, bool FULL>
+template <int BITS, bool FULL, bool HYBRID>
 __device__ __forceinline__ void rank_tile(const BkView& v, const uint32_t* __restrict__ qs, size_t nq, unsigned tile, uint32_t* __restrict__ counts,
                                           uint16_t* __restrict__ lpos16, uint16_t* cnt, const uint16_t* s_bt, const uint32_t* s_split,
                                           unsigned* s_warp) {
@@ -189,7 +189,14 @@ __device__ __forceinline__ void rank_tile(const BkView& v, const uint32_t* __res
         for (int r = 0; r < kItems; r++) {
             const bool valid = FULL || pk[r] != 0xffffffffu;
             const unsigned b = valid ? pk[r] : 0u;
-            if constexpr (BITS < 0) {
+            // Two ways to rank, used on alternating steps so that the work is split between the ALU pipe (ballots) and
+            // the shared-memory pipe (claims) -- each alone is bound by its pipe (0.61 / 0.55 ms per 10^8 queries):
+            //  claim:   every lane writes count + 1 tagged with its lane id (5 tag bits above the 11 count bits); the lane
+            //           whose tag sticks takes rank = count, the others retry
+            //  ballots: lanes with the same bucket find each other by ballots over the bucket bits; the lowest of them
+            //           bumps the counter by the group size
+            const bool claim_step = BITS < 0 || (HYBRID && (r & 1));
+            if (claim_step) {
                 bool done = !valid;
                 unsigned w = 0, rank = 0;
                 do {
@@ -202,9 +209,9 @@ __device__ __forceinline__ void rank_tile(const BkView& v, const uint32_t* __res
                 if (valid) pk[r] = b | (rank << 16);
             } else {
                 unsigned peers = FULL ? kFull : __ballot_sync(kFull, valid);
-                ballot_bits<0, BITS>(peers, b);
+                ballot_bits<0, (BITS < 0 ? 0 : BITS)>(peers, b);
                 const unsigned before = peers & lt_mask;
-                const unsigned old = valid ? cntw[b] : 0u;
+                const unsigned old = valid ? (cntw[b] & 0x7ffu) : 0u;
                 __syncwarp();
                 if (valid && before == 0u) cntw[b] = (uint16_t)(old + __popc(peers));
                 __syncwarp();
@@ -274,11 +281,13 @@ __device__ __forceinline__ void rank_tile(const BkView& v, const uint32_t* __res
     }
 }
 
-template <int BITS>
+template <int BITS, bool HYBRID>
 __global__ void __launch_bounds__(kThreads, 2)
 bk_rank_kernel(const BkView v, const uint32_t* __restrict__ qs, size_t nq, unsigned ntiles, uint32_t* __restrict__ counts,
-               uint16_t* __restrict__ lpos16) {
+               uint16_t* __restrict__ lpos16, uint32_t* __restrict__ tot) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (blockIdx.x == 0)  // bucket totals accumulated by bk_colsum_kernel, which runs after this kernel
+        for (unsigned i = threadIdx.x; i < v.nbp; i += kThreads) tot[i] = 0;
     uint16_t* cnt = reinterpret_cast<uint16_t*>(smem_raw);                       // [kWarps][nbp]
     uint16_t* s_bt = cnt + (size_t)kWarps * v.nbp;                                // [kBtStride]
     uint32_t* s_split = reinterpret_cast<uint32_t*>(s_bt + kBtStride);            // [nbp + 1]
@@ -287,46 +296,33 @@ bk_rank_kernel(const BkView v, const uint32_t* __restrict__ qs, size_t nq, unsig
     for (unsigned i = tid; i < (unsigned)kBtStride; i += kThreads) s_bt[i] = i <= (unsigned)kBtCells ? v.bt[i] : 0;
     for (unsigned i = tid; i <= v.nbp; i += kThreads) s_split[i] = i <= v.nb ? v.split[i] : kMax;
     for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        if ((size_t)(tile + 1) * kTile <= nq) rank_tile<BITS, true>(v, qs, nq, tile, counts, lpos16, cnt, s_bt, s_split, s_warp);
-        else rank_tile<BITS, false>(v, qs, nq, tile, counts, lpos16, cnt, s_bt, s_split, s_warp);  // partial last tile
+        if ((size_t)(tile + 1) * kTile <= nq) rank_tile<BITS, true, HYBRID>(v, qs, nq, tile, counts, lpos16, cnt, s_bt, s_split, s_warp);
+        else rank_tile<BITS, false, HYBRID>(v, qs, nq, tile, counts, lpos16, cnt, s_bt, s_split, s_warp);  // partial last tile
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // plan: scan of the count matrix (tiles x buckets) and the work-item list of the search kernel
 // ------------------------------------------------------------------------------------------------
+// gsum[g][b] = queries of bucket b in the tiles of group g; tot[b] += the same (zeroed by the rank kernel)
 __global__ void __launch_bounds__(256)
-bk_colsum_kernel(const uint32_t* __restrict__ counts, unsigned ntiles, unsigned nbp, uint32_t* __restrict__ gsum) {
+bk_colsum_kernel(const uint32_t* __restrict__ counts, unsigned ntiles, unsigned nbp, uint32_t* __restrict__ gsum, uint32_t* __restrict__ tot) {
     const unsigned b = blockIdx.x * 256 + threadIdx.x, g = blockIdx.y;
     const unsigned t0 = g * kTilesPerGroup, t1 = min(t0 + kTilesPerGroup, ntiles);
     unsigned s = 0;
     for (unsigned t = t0; t < t1; t++) s += counts[(size_t)t * nbp + b];
     gsum[(size_t)g * nbp + b] = s;
+    if (s) atomicAdd(tot + b, s);
 }
 
-// ctrl[0] = work counter of the search kernel, ctrl[1] = number of work items
+// bucket starts, work items of the search kernel; ctrl[0] = work counter, ctrl[1] = number of work items
 __global__ void __launch_bounds__(1024)
-bk_plan_kernel(uint32_t* __restrict__ gsum, unsigned ngroups, unsigned nbp, uint32_t* __restrict__ bstart, uint2* __restrict__ items,
+bk_plan_kernel(const uint32_t* __restrict__ tot_in, unsigned nbp, uint32_t* __restrict__ bstart, uint2* __restrict__ items,
                unsigned* __restrict__ ctrl) {
     __shared__ unsigned s_warp[33];
     const unsigned tid = threadIdx.x;
     unsigned tot[2] = {0, 0};
-#pragma unroll
-    for (unsigned k = 0; k < 2; k++) {
-        const unsigned b = tid * 2 + k;
-        if (b < nbp) {
-            unsigned run = 0;
-            for (unsigned g0 = 0; g0 < ngroups; g0 += 16) {  // 16 independent loads in flight, then the running sums
-                unsigned c[16];
-#pragma unroll
-                for (unsigned j = 0; j < 16; j++) c[j] = g0 + j < ngroups ? gsum[(size_t)(g0 + j) * nbp + b] : 0u;
-#pragma unroll
-                for (unsigned j = 0; j < 16; j++)
-                    if (g0 + j < ngroups) { gsum[(size_t)(g0 + j) * nbp + b] = run; run += c[j]; }
-            }
-            tot[k] = run;
-        }
-    }
+    if (tid * 2 < nbp) { const uint2 t2 = *reinterpret_cast<const uint2*>(tot_in + tid * 2); tot[0] = t2.x; tot[1] = t2.y; }
     unsigned total;
     unsigned base = block_excl_scan(tot[0] + tot[1], s_warp, &total);
     if (tid * 2 < nbp) bstart[tid * 2] = base;
@@ -341,12 +337,20 @@ bk_plan_kernel(uint32_t* __restrict__ gsum, unsigned ngroups, unsigned nbp, uint
     if (tid == 0) { ctrl[0] = 0; ctrl[1] = nitems; }
 }
 
+// offs[t][b] = position in the bucketed array of the first query of (tile t, bucket b)
 __global__ void __launch_bounds__(256)
 bk_offsets_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ gsum, const uint32_t* __restrict__ bstart,
                   unsigned ntiles, unsigned nbp, uint32_t* __restrict__ offs) {
     const unsigned b = blockIdx.x * 256 + threadIdx.x, g = blockIdx.y;
     const unsigned t0 = g * kTilesPerGroup, t1 = min(t0 + kTilesPerGroup, ntiles);
-    unsigned run = gsum[(size_t)g * nbp + b] + bstart[b];
+    unsigned run = bstart[b];
+    for (unsigned g0 = 0; g0 < g; g0 += 16) {  // queries of the bucket in earlier tile groups (16 loads in flight)
+        unsigned c[16];
+#pragma unroll
+        for (unsigned j = 0; j < 16; j++) c[j] = g0 + j < g ? gsum[(size_t)(g0 + j) * nbp + b] : 0u;
+#pragma unroll
+        for (unsigned j = 0; j < 16; j++) run += c[j];
+    }
     for (unsigned t = t0; t < t1; t++) {
         const unsigned c = counts[(size_t)t * nbp + b];
         offs[(size_t)t * nbp + b] = run;
@@ -403,8 +407,11 @@ bk_move_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__
             if (k < bpt) {
                 const unsigned b = tid * bpt + k;
                 s_delta[b] = o[k] - base;
-                for (unsigned j = 0; j < c[k]; j++) s_map[base + j] = (uint16_t)b;
-                base += c[k];
+                unsigned j = base, e = base + c[k];  // fill [j, e) with b: 32-bit stores over the aligned middle
+                if (j < e && (j & 1u)) s_map[j++] = (uint16_t)b;
+                for (; j + 2 <= e; j += 2) *reinterpret_cast<uint32_t*>(s_map + j) = b | (b << 16);
+                if (j < e) s_map[j] = (uint16_t)b;
+                base = e;
             }
         if (tile + gridDim.x < ntiles) load_row(tile + gridDim.x);  // next tile's rows: in flight during this tile
         __syncthreads();
@@ -682,7 +689,7 @@ int env_int(const char* name, int dflt) {
 struct Scratch {
     int device = -1;
     size_t cap_q = 0, cap_idx = 0, cap_mat = 0, cap_items = 0;
-    uint32_t *qb = nullptr, *rb = nullptr, *ib = nullptr, *counts = nullptr, *offs = nullptr, *gsum = nullptr, *bstart = nullptr;
+    uint32_t *qb = nullptr, *rb = nullptr, *ib = nullptr, *counts = nullptr, *offs = nullptr, *gsum = nullptr, *bstart = nullptr, *tot = nullptr;
     uint16_t* lpos = nullptr;
     uint2* items = nullptr;
     unsigned* ctrl = nullptr;
@@ -691,7 +698,7 @@ struct Scratch {
         if (device < 0) return;
         int prev = -1;
         if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) { (void)cudaGetLastError(); return; }
-        cudaFree(qb); cudaFree(rb); cudaFree(ib); cudaFree(counts); cudaFree(offs); cudaFree(gsum); cudaFree(bstart);
+        cudaFree(qb); cudaFree(rb); cudaFree(ib); cudaFree(counts); cudaFree(offs); cudaFree(gsum); cudaFree(bstart); cudaFree(tot);
         cudaFree(lpos); cudaFree(items); cudaFree(ctrl);
         if (done) cudaEventDestroy(done);
         (void)cudaGetLastError();
@@ -710,7 +717,7 @@ bool regrow(T*& p, size_t count) {
 bool scratch_ensure(Scratch& s, int device, size_t nq, bool want_idx, unsigned nbp) {
     s.device = device;
     if (!s.done && !SST_CUDA_OK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming))) return false;
-    if (!s.ctrl && (!regrow(s.ctrl, 4) || !regrow(s.bstart, 2048 + 8))) return false;
+    if (!s.ctrl && (!regrow(s.ctrl, 4) || !regrow(s.bstart, 2048 + 8) || !regrow(s.tot, 2048))) return false;
     if (nq > s.cap_q) {
         s.cap_q = 0;
         if (!regrow(s.qb, nq) || !regrow(s.rb, nq) || !regrow(s.lpos, nq)) return false;
@@ -739,10 +746,17 @@ bool scratch_ensure(Scratch& s, int device, size_t nq, bool want_idx, unsigned n
 
 template <int BITS>
 void launch_rank(const BkView& v, int sms, size_t smem, cudaStream_t st, const uint32_t* qs, size_t nq, unsigned ntiles, uint32_t* counts,
-                 uint16_t* lpos) {
-    auto kern = bk_rank_kernel<BITS>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<(unsigned)std::min<size_t>(ntiles, (size_t)sms * 2), kThreads, smem, st>>>(v, qs, nq, ntiles, counts, lpos);
+                 uint16_t* lpos, uint32_t* tot) {
+    const unsigned grid = (unsigned)std::min<size_t>(ntiles, (size_t)sms * 2);
+    if (BITS > 0 && env_int("SST_BK_HYBRID", 1)) {
+        auto kern = bk_rank_kernel<BITS, true>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, kThreads, smem, st>>>(v, qs, nq, ntiles, counts, lpos, tot);
+    } else {
+        auto kern = bk_rank_kernel<BITS, false>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, kThreads, smem, st>>>(v, qs, nq, ntiles, counts, lpos, tot);
+    }
 }
 
 template <bool GATHER, typename OutT>
@@ -828,9 +842,9 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
         const uint32_t* qs = d_qs + off;
         nev = 0;
         mark();
-        switch (env_int("SST_BK_CLAIM", 1) ? -1 : (int)a.bits) {
-            case -1: launch_rank<-1>(v, sms, smem_rank, st, qs, cnt, ntiles, s.counts, s.lpos); break;
-#define SST_BK_RANK(B) case B: launch_rank<B>(v, sms, smem_rank, st, qs, cnt, ntiles, s.counts, s.lpos); break;
+        switch (env_int("SST_BK_CLAIM", 0) ? -1 : (int)a.bits) {
+            case -1: launch_rank<-1>(v, sms, smem_rank, st, qs, cnt, ntiles, s.counts, s.lpos, s.tot); break;
+#define SST_BK_RANK(B) case B: launch_rank<B>(v, sms, smem_rank, st, qs, cnt, ntiles, s.counts, s.lpos, s.tot); break;
             SST_BK_RANK(0) SST_BK_RANK(1) SST_BK_RANK(2) SST_BK_RANK(3) SST_BK_RANK(4) SST_BK_RANK(5)
             SST_BK_RANK(6) SST_BK_RANK(7) SST_BK_RANK(8) SST_BK_RANK(9) SST_BK_RANK(10) SST_BK_RANK(11)
 #undef SST_BK_RANK
@@ -838,8 +852,8 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
         }
         mark();
         const dim3 mgrid(a.nbp / 256, ngroups);
-        bk_colsum_kernel<<<mgrid, 256, 0, st>>>(s.counts, ntiles, a.nbp, s.gsum);
-        bk_plan_kernel<<<1, 1024, 0, st>>>(s.gsum, ngroups, a.nbp, s.bstart, s.items, s.ctrl);
+        bk_colsum_kernel<<<mgrid, 256, 0, st>>>(s.counts, ntiles, a.nbp, s.gsum, s.tot);
+        bk_plan_kernel<<<1, 1024, 0, st>>>(s.tot, a.nbp, s.bstart, s.items, s.ctrl);
         bk_offsets_kernel<<<mgrid, 256, 0, st>>>(s.counts, s.gsum, s.bstart, ntiles, a.nbp, s.offs);
         mark();
         launch_move<false, uint32_t>(sms, smem_move, st, s, a.nbp, bpt, ntiles, cnt, qs, s.qb);
