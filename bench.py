@@ -268,7 +268,8 @@ def run_own(args):
     i2 = torch.searchsorted(keys, q_last[:1_000_000])
     ok = ok and bool((keys[i2.clamp(max=n - 1)] == out_v[:1_000_000]).all())
 
-    # ---- roofline of the dominant (only) kernel: algorithmic bytes per launch / mean launch time ----
+    # ---- roofline of the step's kernels: algorithmic bytes per step / mean step time ----
+    # (one kernel for the direct schemes; the reordered-batch pipeline is 7 dependent kernels, timed as a whole)
     layer_nodes = layer_nodes_for(n)
     l2_bytes = torch.cuda.get_device_properties(dev).L2_cache_size
     H_hbm = hbm_levels(layer_nodes, l2_bytes)
@@ -276,20 +277,37 @@ def run_own(args):
     kern_ms = statistics.mean(per_step_ms)
     achieved = bytes_per_query * (e - s) / (kern_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
+    res_scheme, res_launches = C.c_int(0), C.c_int(0)
+    L.sst_query_plan(tree._h, e - s, args.scheme, 0, C.byref(res_scheme), C.byref(res_launches))
+    scheme_names = {0: "auto", 1: "group4", 2: "group16", 3: "group2", 4: "generic", 5: "table", 6: "binsearch", 7: "bucketed"}
+    bucketed = res_scheme.value == sst.SCHEME_BUCKETED
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "bytes_per_query": bytes_per_query, "hbm_levels": H_hbm,
-                "kernel": "stree_search_fast", "kernel_ms": kern_ms}
+                "kernel": ("reordered-batch pipeline: bk_rank + bk_colsum + bk_plan + bk_offsets + bk_move<scatter> + bk_search + bk_move<gather>"
+                           if bucketed else "stree_search_fast"),
+                "kernel_ms": kern_ms, "launches_per_step": res_launches.value}
+    if bucketed:  # one extra untimed step with per-stage CUDA events (synchronises between stages, so it is not a bench value)
+        os.environ["SST_BK_TIMING"] = "1"
+        step(0)
+        torch.cuda.synchronize()
+        os.environ.pop("SST_BK_TIMING", None)
+        st_ms = (C.c_double * 5)()
+        if L.sst_last_stage_ms(st_ms, 5) == 5:
+            roofline["stage_ms"] = dict(zip(["rank", "plan", "scatter", "search", "gather"], [round(float(x), 4) for x in st_ms]))
     tf = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tf) and n == (1 << 28) and (e - s) == 100_000_000:  # the capture is of exactly this launch shape
+    if os.path.exists(tf) and n == (1 << 28) and (e - s) == 100_000_000:  # the capture is of exactly this step shape
         try:
-            roofline["traffic"] = json.load(open(tf)).get("dram_bytes_per_launch")
-            # what the DRAM actually moved (ncu) over the live launch time
-            roofline["traffic_gbs"] = roofline["traffic"] / (kern_ms * 1e-3) / 1e9
-            roofline["traffic_frac"] = roofline["traffic_gbs"] / peak
-            # the binding limit is the random-access RATE, not bytes: a gather probe tops out at 43 G random
-            # 64-B accesses/s whether L2 is filled in 64-B or 128-B units (profiles/r1_ncu_probe_pf.csv)
-            roofline["random_access_ceiling_per_s"] = 43.0e9
-            roofline["dram_accesses_per_s"] = roofline["traffic"] / 64 / (kern_ms * 1e-3)
+            tj = json.load(open(tf))
+            if tj.get("scheme") == res_scheme.value:
+                roofline["traffic"] = tj.get("dram_bytes_per_launch")
+                # what the DRAM actually moved (ncu, all kernels of the step) over the live step time
+                roofline["traffic_gbs"] = roofline["traffic"] / (kern_ms * 1e-3) / 1e9
+                roofline["traffic_frac"] = roofline["traffic_gbs"] / peak
+                if not bucketed:
+                    # the direct kernel is bound by the random-access RATE, not bytes: a gather probe tops out at 43 G
+                    # random 64-B accesses/s whether L2 is filled in 64-B or 128-B units (profiles/r1_ncu_probe_pf.csv)
+                    roofline["random_access_ceiling_per_s"] = 43.0e9
+                    roofline["dram_accesses_per_s"] = roofline["traffic"] / 64 / (kern_ms * 1e-3)
         except Exception:
             pass
 
@@ -385,10 +403,10 @@ def run_own(args):
             "config": {
                 "workload": f"stree16 left_max lower_bound: {n} sorted uniform u32 keys (S+-tree B=16, {len(layer_nodes)} levels), {nq} uniform u32 queries per GPU per step",
                 "n_keys": n, "queries_per_gpu": nq, "global_queries": world * nq, "parallelism": f"replicated index, query-sharded x{world}",
-                "scheme": args.scheme, "index_build_s": round(build_s, 3),
+                "scheme": scheme_names.get(res_scheme.value, str(res_scheme.value)), "index_build_s": round(build_s, 3),
                 "l2_policy": "inputs larger than L2: 1 GiB leaf level + 0.8 GB query/result streams per step, two alternating query batches",
             },
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * L.sst_query_launches(tree._h, args.scheme),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * res_launches.value,
             "clocks": clocks, "results_ok": ok,
         }
         if baselines is not None:

@@ -137,6 +137,9 @@ int sst_query_device(const sst_index_t* idx, const uint32_t* d_qs, size_t nq, ui
                      uint64_t* d_out_idx, int scheme, void* stream); /* DEVICE buffers, asynchronous on `stream` */
 /* Number of kernel launches sst_query_device issues for this index/scheme (for launch accounting). */
 int sst_query_launches(const sst_index_t* idx, int scheme);
+/* The kernel SST_SCHEME_AUTO resolves to for a batch of nq queries on this index (*out_scheme; partitioned layouts
+ * report SST_SCHEME_AUTO = their lane-group kernel) and the number of kernel launches the call issues (*out_launches). */
+int sst_query_plan(const sst_index_t* idx, size_t nq, int scheme, int want_index, int* out_scheme, int* out_launches);
 
 /* ---- suffix arrays: replaces SaNaive::build / SA::build (sas/sa_search.rs:30-57,
  *      sas/experiments.rs:19-38; the libsais call at sa_search.rs:33) and binary_search
@@ -193,6 +196,10 @@ double sst_time_query_device(const sst_index_t* idx, const uint32_t* d_qs, size_
 /* Random 64-byte gather probe over `bytes` of device memory: the practical ceiling of the
  * access pattern of one tree level.  Returns GB/s (<0 on error). lanes_per_node in {1,2,4,8,16}. */
 double sst_probe_gather64(int device, size_t bytes, size_t n_gathers, int lanes_per_node, int iters);
+/* With SST_BK_TIMING=1 in the environment the reordered-batch pipeline times its stages with CUDA events (and
+ * synchronises the stream); this returns the calling thread's last {rank, plan, scatter, search, gather} times in ms
+ * (0 = nothing recorded). */
+int sst_last_stage_ms(double* out, int n);
 
 #ifdef __cplusplus
 }

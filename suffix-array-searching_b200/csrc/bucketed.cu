@@ -38,8 +38,7 @@ constexpr int kTile = 16384;                 // queries per partition tile (64 K
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kItems = kTile / kThreads;     // 32 queries per thread
-constexpr int kCells = 16384;                // jump-table cells per bucket (about one separator per cell)
-constexpr int kJumpStride = kCells + 8;      // u16 entries per bucket (multiple of 16 bytes)
+// jump table: one cell per separator of a bucket (cells = r), r + 8 u16 entries per bucket (a multiple of 16 bytes)
 constexpr int kBtShift = 18;                 // bucket table over the top 13 bits of a 31-bit key
 constexpr int kBtCells = 1 << (31 - kBtShift);
 constexpr int kBtStride = kBtCells + 8;
@@ -231,6 +230,16 @@ __device__ __forceinline__ void rank_tile(const BkView& v, const uint32_t* __res
             }
             sum = tot[0] + tot[1] + tot[2] + tot[3];
             *reinterpret_cast<uint4*>(counts + (size_t)tile * v.nbp + tid * 4) = make_uint4(tot[0], tot[1], tot[2], tot[3]);
+        } else if (v.bpt == 2) {  // 1024 buckets: two counters per 4-byte access
+            uint32_t* c1 = reinterpret_cast<uint32_t*>(cnt) + tid;
+#pragma unroll
+            for (int w = 0; w < kWarps; w++) {
+                const uint32_t c = c1[(size_t)w * (v.nbp / 2)];
+                c1[(size_t)w * (v.nbp / 2)] = tot[0] | (tot[1] << 16);
+                tot[0] += c & 0x7ffu; tot[1] += (c >> 16) & 0x7ffu;
+            }
+            sum = tot[0] + tot[1];
+            *reinterpret_cast<uint2*>(counts + (size_t)tile * v.nbp + tid * 2) = make_uint2(tot[0], tot[1]);
         } else {
 #pragma unroll
             for (unsigned k = 0; k < 4; k++)
@@ -261,6 +270,11 @@ __device__ __forceinline__ void rank_tile(const BkView& v, const uint32_t* __res
                 c.x += add.x; c.y += add.y;  // 16-bit lanes cannot carry: every sum is < kTile
                 c2[(size_t)w * (v.nbp / 4)] = c;
             }
+        } else if (v.bpt == 2) {
+            const uint32_t add = base | ((base + tot[0]) << 16);
+            uint32_t* c1 = reinterpret_cast<uint32_t*>(cnt) + tid;
+#pragma unroll
+            for (int w = 0; w < kWarps; w++) c1[(size_t)w * (v.nbp / 2)] += add;
         } else {
             unsigned st = base;
 #pragma unroll
@@ -491,7 +505,7 @@ bk_move_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__
 // ------------------------------------------------------------------------------------------------
 struct BkSearchParams {
     const uint32_t* sep;     // [nb * r]
-    const uint16_t* jump;    // [nb][kJumpStride]
+    const uint16_t* jump;    // [nb][r + 8]
     const uint2* meta;       // [nb] {lo, shift}
     const uint32_t* leaf;    // sorted keys (leaf level of the image, MAX-padded)
     unsigned r;              // half nodes (separators) per bucket
@@ -506,16 +520,16 @@ __device__ __forceinline__ void ldg256(const uint32_t* p, uint32_t (&k)[8]) {
 }
 
 template <bool WANT_IDX>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(1024, 1)
 bk_search_kernel(const BkSearchParams p, const uint32_t* __restrict__ qb, const uint32_t* __restrict__ bstart,
                  const uint2* __restrict__ items, unsigned* __restrict__ ctrl, uint32_t* __restrict__ rb, uint32_t* __restrict__ ib) {
     constexpr int U = 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t* s_sep = reinterpret_cast<uint32_t*>(smem_raw);                 // [r]
-    uint16_t* s_jump = reinterpret_cast<uint16_t*>(s_sep + p.r);              // [kJumpStride]
+    uint16_t* s_jump = reinterpret_cast<uint16_t*>(s_sep + p.r);              // [r + 8]
     __shared__ __align__(8) uint64_t bar;
     __shared__ unsigned s_item;
-    const unsigned tid = threadIdx.x;
+    const unsigned tid = threadIdx.x, nthr = blockDim.x;
     if (tid == 0) {
         mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -532,11 +546,12 @@ bk_search_kernel(const BkSearchParams p, const uint32_t* __restrict__ qb, const 
         const unsigned b = it.x;
         if (b != cur_b) {  // stage the bucket: 1-D TMA bulk copies (SASS UBLKCP), completion on the mbarrier
             if (tid == 0) {
-                const unsigned sep_bytes = p.r * 4u, jump_bytes = kJumpStride * 2u;
+                const unsigned sep_bytes = p.r * 4u, jump_bytes = (p.r + 8u) * 2u;
                 mbar_expect_tx(&bar, sep_bytes + jump_bytes);
                 for (unsigned off = 0; off < sep_bytes; off += 32768u)
                     tma_bulk_g2s((char*)s_sep + off, (const char*)(p.sep + (size_t)b * p.r) + off, min(32768u, sep_bytes - off), &bar);
-                tma_bulk_g2s(s_jump, p.jump + (size_t)b * kJumpStride, jump_bytes, &bar);
+                for (unsigned off = 0; off < jump_bytes; off += 32768u)
+                    tma_bulk_g2s((char*)s_jump + off, (const char*)(p.jump + (size_t)b * (p.r + 8u)) + off, min(32768u, jump_bytes - off), &bar);
             }
             mbar_wait(&bar, phase);
             phase ^= 1u;
@@ -550,16 +565,16 @@ bk_search_kernel(const BkSearchParams p, const uint32_t* __restrict__ qb, const 
         uint32_t qn[U];  // queries of the next round: their loads stay in flight while this round is answered
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const unsigned i = qbeg + tid + u * kThreads;
+            const unsigned i = qbeg + tid + u * nthr;
             qn[u] = i < qend ? __ldcs(qb + i) : lo;
         }
-        for (unsigned i0 = qbeg + tid; i0 < qend; i0 += kThreads * U) {
+        for (unsigned i0 = qbeg + tid; i0 < qend; i0 += nthr * U) {
             uint32_t q[U];
             unsigned a[U];
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 q[u] = qn[u];
-                const unsigned i = i0 + (U + u) * kThreads;
+                const unsigned i = i0 + (U + u) * nthr;
                 qn[u] = i < qend ? __ldcs(qb + i) : lo;
             }
             // rank among the bucket's separators: jump-table cell, then three unconditional probes (independent
@@ -607,7 +622,7 @@ bk_search_kernel(const BkSearchParams p, const uint32_t* __restrict__ qb, const 
             }
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                const unsigned i = i0 + u * kThreads;
+                const unsigned i = i0 + u * nthr;
                 unsigned c = 0;
 #pragma unroll
                 for (int e = 0; e < 8; e++) c += ks[u][e] < q[u] ? 1u : 0u;
@@ -655,26 +670,26 @@ __global__ void bk_bt_kernel(const uint32_t* __restrict__ split, unsigned nb, ui
         bt[c] = c <= (unsigned)kBtCells ? (uint16_t)(cnt[0] | (cnt[1] - cnt[0] >= 2u ? 0x8000u : 0u)) : 0;
     }
 }
-// Per bucket: lo = split[b], shift = smallest s with (split[b+1] - lo) >> s < kCells, and
-// jump[x] = number of the bucket's separators with (sep - lo) >> s < x, x in [0, kCells].
+// Per bucket: lo = split[b], shift = smallest s with (split[b+1] - lo) >> s < r, and
+// jump[x] = number of the bucket's separators with (sep - lo) >> s < x, x in [0, r].
 __global__ void __launch_bounds__(256)
 bk_jump_kernel(const uint32_t* __restrict__ sep, const uint32_t* __restrict__ split, unsigned r, unsigned long long m8,
                uint16_t* __restrict__ jump, uint2* __restrict__ meta) {
     const unsigned b = blockIdx.x;
     const uint32_t lo = split[b], hi = split[b + 1];
     unsigned s = 0;
-    while (((hi - lo) >> s) >= (unsigned)kCells) s++;
+    while (((hi - lo) >> s) >= r) s++;
     if (threadIdx.x == 0) meta[b] = make_uint2(lo, s);
     const uint32_t* sb = sep + (size_t)b * r;
     const unsigned long long first = (unsigned long long)b * r;
     const unsigned valid = (unsigned)min((unsigned long long)r, m8 > first ? m8 - first : 0ull);
-    for (unsigned x = threadIdx.x; x < (unsigned)kJumpStride; x += blockDim.x) {
+    for (unsigned x = threadIdx.x; x < r + 8u; x += blockDim.x) {
         unsigned l = 0, h = valid;
         while (l < h) {
             const unsigned m = (l + h) >> 1;
             if (((sb[m] - lo) >> s) < x) l = m + 1; else h = m;
         }
-        jump[(size_t)b * kJumpStride + x] = x <= (unsigned)kCells ? (uint16_t)l : 0;
+        jump[(size_t)b * (r + 8u) + x] = x <= r ? (uint16_t)l : 0;
     }
 }
 
@@ -706,6 +721,7 @@ struct Scratch {
     }
 };
 thread_local Scratch g_scratch[64];
+thread_local double g_stage_ms[5] = {-1, -1, -1, -1, -1};
 
 template <typename T>
 bool regrow(T*& p, size_t count) {
@@ -765,7 +781,7 @@ void launch_move(int sms, size_t smem, cudaStream_t st, const Scratch& s, unsign
     const int aligned = (((uintptr_t)src | (uintptr_t)dst) & 15u) == 0 && env_int("SST_BK_VEC", 1);
     auto kern = bk_move_kernel<GATHER, OutT>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<(unsigned)std::min<size_t>(ntiles, (size_t)sms * 2), kThreads, smem, st>>>(s.counts, s.offs, s.lpos, nbp, bpt, ntiles, nq, aligned, src, dst);
+    kern<<<(unsigned)std::min<size_t>(ntiles, (size_t)sms * env_int("SST_BK_MOVE_CTAS", 2)), kThreads, smem, st>>>(s.counts, s.offs, s.lpos, nbp, bpt, ntiles, nq, aligned, src, dst);
 }
 
 }  // namespace
@@ -780,11 +796,13 @@ void free_bucket_aux(sst_index* idx) {
 bool build_bucket_aux(sst_index* idx) {
     if (idx->variant != SST_PLAIN || idx->node_b != 16) return true;
     if (idx->n < (size_t)env_int("SST_BK_MIN_N", 1 << 22)) return true;  // small trees are L2-resident: nothing to gain
-    unsigned r = (unsigned)env_int("SST_BK_R", 16384);
-    if (r < 64 || r > 16384 || (r & (r - 1))) r = 16384;
+    // separators per bucket: 16384 (two search CTAs per SM) up to 2^27 keys, 32768 (one 1024-thread CTA) above, so that the
+    // partition has at most 1024 buckets up to 2^28 keys -- fewer buckets = longer runs and fewer ballot bits
     const unsigned long long m8 = div_ceil(idx->n, (size_t)8);
+    unsigned r = (unsigned)env_int("SST_BK_R", m8 > 16384ull * 1024ull ? 32768 : 16384);
+    if (r < 64 || r > 32768 || (r & (r - 1))) r = 16384;
     const unsigned long long nb64 = div_ceil((size_t)m8, (size_t)r);
-    if (nb64 > 2048) return true;  // > 2^28 keys: served by the rank-table kernel
+    if (nb64 > 2048) return true;  // > 2^29 keys: served by the rank-table kernel
     BkAux& a = idx->bk;
     const unsigned nb = (unsigned)nb64;
     const unsigned nbp = (unsigned)(div_ceil((size_t)nb, (size_t)kThreads) * kThreads);
@@ -794,7 +812,7 @@ bool build_bucket_aux(sst_index* idx) {
     const uint32_t* leaf = idx->d_tree + idx->offsets[idx->levels - 1] * 16;
     const unsigned long long total = (unsigned long long)nb * r;
     bool ok = SST_CUDA_OK(cudaMalloc(&a.d_sep, total * 4)) && SST_CUDA_OK(cudaMalloc(&a.d_split, ((size_t)nb + 1) * 4)) &&
-              SST_CUDA_OK(cudaMalloc(&a.d_bt, (size_t)kBtStride * 2)) && SST_CUDA_OK(cudaMalloc(&a.d_jump, (size_t)nb * kJumpStride * 2)) &&
+              SST_CUDA_OK(cudaMalloc(&a.d_bt, (size_t)kBtStride * 2)) && SST_CUDA_OK(cudaMalloc(&a.d_jump, (size_t)nb * (r + 8) * 2)) &&
               SST_CUDA_OK(cudaMalloc(&a.d_meta, (size_t)nb * sizeof(uint2)));
     if (ok) {
         bk_sep_kernel<<<(unsigned)std::min<size_t>(div_ceil((size_t)total, (size_t)256), 148 * 16), 256, 0, st>>>(leaf, m8, total, a.d_sep);
@@ -810,6 +828,13 @@ bool build_bucket_aux(sst_index* idx) {
 
 bool bucketed_eligible(const sst_index* idx) { return idx->bk.nb != 0; }
 
+// rank, plan, scatter, search, gather (ms) of this thread's last pipeline run under SST_BK_TIMING; returns the count
+int last_stage_ms(double* out, int n) {
+    int k = 0;
+    for (; k < n && k < 5; k++) out[k] = g_stage_ms[k];
+    return g_stage_ms[0] < 0 ? 0 : k;
+}
+
 int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx, cudaStream_t st) {
     const BkAux& a = idx->bk;
     if (!a.nb) { set_error(SST_ERR_UNSUPPORTED, "the reordered-batch pipeline serves plain B=16 trees of 2^22..2^28 keys"); return SST_ERR_UNSUPPORTED; }
@@ -824,7 +849,9 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
     BkView v{a.d_bt, a.d_split, a.nb, a.nbp, bpt};
     const size_t smem_rank = (size_t)kWarps * a.nbp * 2 + (size_t)kBtStride * 2 + ((size_t)a.nbp + 1) * 4 + 16;
     const size_t smem_move = (size_t)kTile * 4 + (size_t)a.nbp * 4 + (size_t)kTile * 2;
-    const size_t smem_search = (size_t)a.r * 4 + (size_t)kJumpStride * 2;
+    const size_t smem_search = (size_t)a.r * 4 + ((size_t)a.r + 8) * 2;
+    // two CTAs of 512 threads per SM while two buckets fit shared memory, else one CTA of 1024 threads
+    const int search_threads = smem_search * 2 + 4096 <= max_smem_optin(dev) ? kThreads : 1024, search_ctas = search_threads == kThreads ? 2 : 1;
     BkSearchParams sp{a.d_sep, a.d_jump, a.d_meta, idx->d_tree + idx->offsets[idx->levels - 1] * 16, a.r, a.m8, (unsigned long long)idx->n};
     // SST_BK_TIMING=1 (debug): per-stage CUDA-event times on stderr; synchronises the stream
     const bool timing = env_int("SST_BK_TIMING", 0) != 0;
@@ -861,11 +888,11 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
         if (d_idx) {
             auto kern = bk_search_kernel<true>;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_search);
-            kern<<<sms * 2, kThreads, smem_search, st>>>(sp, s.qb, s.bstart, s.items, s.ctrl, s.rb, s.ib);
+            kern<<<sms * search_ctas, search_threads, smem_search, st>>>(sp, s.qb, s.bstart, s.items, s.ctrl, s.rb, s.ib);
         } else {
             auto kern = bk_search_kernel<false>;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_search);
-            kern<<<sms * 2, kThreads, smem_search, st>>>(sp, s.qb, s.bstart, s.items, s.ctrl, s.rb, s.ib);
+            kern<<<sms * search_ctas, search_threads, smem_search, st>>>(sp, s.qb, s.bstart, s.items, s.ctrl, s.rb, s.ib);
         }
         mark();
         launch_move<true, uint32_t>(sms, smem_move, st, s, a.nbp, bpt, ntiles, cnt, s.rb, d_vals + off);
@@ -874,7 +901,8 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
         if (timing && nev == 6 && cudaEventSynchronize(ev[5]) == cudaSuccess) {
             float t[5];
             for (int i = 0; i < 5; i++) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
-            fprintf(stderr, "[sst] bucketed nq=%zu nb=%u: rank %.3f plan %.3f scatter %.3f search %.3f gather %.3f ms\n", cnt, a.nb, t[0], t[1],
+            for (int i = 0; i < 5; i++) g_stage_ms[i] = t[i];
+            if (env_int("SST_BK_TIMING", 0) > 1) fprintf(stderr, "[sst] bucketed nq=%zu nb=%u: rank %.3f plan %.3f scatter %.3f search %.3f gather %.3f ms\n", cnt, a.nb, t[0], t[1],
                     t[2], t[3], t[4]);
         }
         for (int i = 0; i < nev; i++) cudaEventDestroy(ev[i]);

@@ -158,11 +158,12 @@ bool build_compressed_level(sst_index* idx);
 // search (stree_search.cu)
 int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx,
                  int scheme, cudaStream_t stream);
-int query_launch_count(const sst_index* idx, int scheme);
+int query_launch_count(const sst_index* idx, int scheme, size_t nq, bool want_idx);
 // reordered-batch pipeline (bucketed.cu)
 bool build_bucket_aux(sst_index* idx);
 void free_bucket_aux(sst_index* idx);
 bool bucketed_eligible(const sst_index* idx);
+int last_stage_ms(double* out, int n);  // stage times of this thread's last pipeline run under SST_BK_TIMING=1
 int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx,
                     cudaStream_t stream);
 }  // namespace sst

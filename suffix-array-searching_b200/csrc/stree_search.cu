@@ -754,11 +754,32 @@ int launch_fast_top(const sst_index* idx, bool top, const uint32_t* d_qs, size_t
     return launch_fast<G, T, false>(idx, d_qs, nq, d_vals, d_idx, st);
 }
 
+
+// The kernel AUTO picks for this index and batch size.  Measured on B200 (tools/batch_sweep.py, tools/bucketed_once.py):
+// the thread-per-query kernel has the shortest latency (6-10 us up to 2^16 queries), the rank-table kernel wins from 2^17
+// queries, and from 2^24 queries over >= 2^25 keys the reordered-batch pipeline does (59.7 vs 52.8 Gq/s at 2^25 keys,
+// 50 vs 34 Gq/s at 2^28 keys for 10^8 queries); the table-less group kernel never wins.
+int resolve_scheme(const sst_index* idx, int scheme, size_t nq) {
+    if (scheme != SST_SCHEME_AUTO) return scheme;
+    if (idx->variant == SST_EYTZINGER) return SST_SCHEME_GENERIC;
+    if (idx->variant != SST_PLAIN && idx->node_b == 16 && env_int("SST_PGROUP", 1)) return SST_SCHEME_AUTO;  // lane-group kernel
+    if (!fast_eligible(idx)) return SST_SCHEME_GENERIC;
+    if (nq < (size_t)env_int("SST_TABLE_MIN_NQ", 1 << 17)) return env_int("SST_SCHEME", SST_SCHEME_GENERIC);
+    if (bucketed_eligible(idx) && idx->n >= (size_t)env_int("SST_BK_AUTO_MIN_N", 1 << 25) &&
+        nq >= (size_t)env_int("SST_BK_AUTO_MIN_NQ", 1 << 24))
+        return env_int("SST_SCHEME", SST_SCHEME_BUCKETED);
+    return env_int("SST_SCHEME", top_eligible(idx) ? SST_SCHEME_TABLE : SST_SCHEME_GROUP2);
+}
+
 }  // namespace
 
-// Kernel launches per sst_query_device call (per 2^27-query sub-batch for the reordered-batch pipeline: rank,
-// column sums, plan, offsets, scatter, search, gather; one more gather when the index output is requested).
-int query_launch_count(const sst_index*, int scheme) { return scheme == SST_SCHEME_BUCKETED ? 7 : 1; }
+// Kernel launches of one sst_query_device call.  The reordered-batch pipeline runs 7 kernels per 2^27-query
+// sub-batch (rank, column sums, plan, offsets, scatter, search, gather) and one more gather for the index output.
+int query_launch_count(const sst_index* idx, int scheme, size_t nq, bool want_idx) {
+    if (nq == 0) return 0;
+    if (resolve_scheme(idx, scheme, nq) != SST_SCHEME_BUCKETED) return 1;
+    return (int)(div_ceil(nq, (size_t)1 << 27) * (want_idx ? 8 : 7));
+}
 
 int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx,
                  int scheme, cudaStream_t st) {
@@ -780,14 +801,7 @@ int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t
         else pstree_search_group<2><<<grid, 512, 0, st>>>(idx->view, d_qs, nq, d_vals, d_idx);
         return SST_CUDA_OK(cudaGetLastError()) ? SST_OK : SST_ERR_CUDA;
     }
-    if (scheme == SST_SCHEME_AUTO) {
-        // Measured at 2^28 keys (tools/batch_sweep.py): the thread-per-query kernel has the shortest latency
-        // (6-10 us up to 2^16 queries), the rank-table kernel the highest throughput from 2^17 queries up
-        // (16.8 Gq/s at 2^18, 34 Gq/s at 2^26); the table-less group kernel never wins.
-        if (!fast_eligible(idx)) scheme = SST_SCHEME_GENERIC;
-        else if (nq < (size_t)env_int("SST_TABLE_MIN_NQ", 1 << 17)) scheme = env_int("SST_SCHEME", SST_SCHEME_GENERIC);
-        else scheme = env_int("SST_SCHEME", top_eligible(idx) ? SST_SCHEME_TABLE : SST_SCHEME_GROUP2);
-    }
+    scheme = resolve_scheme(idx, scheme, nq);
     if (scheme != SST_SCHEME_GENERIC && !fast_eligible(idx)) {  // (BINSEARCH included: plain B=16 only)
         set_error(SST_ERR_UNSUPPORTED, "the group/table kernels serve the plain B=16 tree; use SST_SCHEME_AUTO or SST_SCHEME_GENERIC");
         return SST_ERR_UNSUPPORTED;
@@ -841,7 +855,17 @@ using namespace sst;
 
 extern "C" {
 
-int sst_query_launches(const sst_index_t* idx, int scheme) { return idx ? query_launch_count(idx, scheme) : 0; }
+int sst_query_launches(const sst_index_t* idx, int scheme) { return idx ? query_launch_count(idx, scheme, 1, false) : 0; }
+
+int sst_query_plan(const sst_index_t* idx, size_t nq, int scheme, int want_index, int* out_scheme, int* out_launches) {
+    clear_error();
+    if (!idx) { set_error(SST_ERR_ARG, "null argument"); return SST_ERR_ARG; }
+    if (out_scheme) *out_scheme = resolve_scheme(idx, scheme, nq);
+    if (out_launches) *out_launches = query_launch_count(idx, scheme, nq, want_index != 0);
+    return SST_OK;
+}
+
+int sst_last_stage_ms(double* out, int n) { return last_stage_ms(out, n); }
 
 int sst_query_device(const sst_index_t* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_out_vals, uint64_t* d_out_idx,
                      int scheme, void* stream) {

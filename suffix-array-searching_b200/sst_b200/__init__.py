@@ -80,6 +80,8 @@ def lib() -> C.CDLL:
         "sst_query": (i32, [vp, vp, sz, vp, vp, i32]),
         "sst_query_device": (i32, [vp, vp, sz, vp, vp, i32, vp]),
         "sst_query_launches": (i32, [vp, i32]),
+        "sst_query_plan": (i32, [vp, sz, i32, i32, vp, vp]),
+        "sst_last_stage_ms": (i32, [vp, i32]),
         "sst_sa_build": (vp, [vp, sz, i32]),
         "sst_sa_build_device": (vp, [vp, sz, i32]),
         "sst_sa_from_parts": (vp, [vp, sz, vp, i32]),

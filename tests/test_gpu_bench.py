@@ -31,3 +31,16 @@ def test_bench_line_contract(gpu):
     assert e["h2d_bytes_per_step"] == 4 * (1 << 22) and e["d2h_bytes_per_step"] == 4 * (1 << 22) and e["value"] > 0
     assert d["sa"]["binary_ok"] and d["sa"]["mlr_ok"] and d["sa"]["mlr_equals_binary"] and d["sa"]["sa_check_violations"] == 0
     assert "workload" in d["config"]
+
+
+@pytest.mark.gpu
+def test_bench_line_bucketed(gpu):
+    """A configuration large enough for SCHEME_AUTO to take the reordered-batch pipeline: 7 launches per step, stage times."""
+    out = subprocess.run(
+        [sys.executable, os.path.join(ROOT, "bench.py"), "--n-keys", str(1 << 25), "--queries", str(1 << 24), "--steps", "2", "--warmup", "3",
+         "--no-cpu", "--sa-text", "0", "--e2e-steps", "1"],
+        capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.strip()][-1])
+    assert d["config"]["scheme"] == "bucketed" and d["gpu_launches"] == 2 * 7 and d["results_ok"] is True
+    assert set(d["roofline"]["stage_ms"]) == {"rank", "plan", "scatter", "search", "gather"}

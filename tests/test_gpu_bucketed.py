@@ -23,7 +23,7 @@ def _check(sst, oracle, vals, qs, flags=FLAG_SETS):
 
 
 @pytest.mark.parametrize("r,n,nq", [(64, 5000, 40_000), (64, 100_000, 100_001), (64, 1_000_000, 70_000), (256, 1 << 20, 300_000),
-                                    (1024, 2_000_003, 50_000), (16384, (1 << 22) + 12345, 1_000_003), (64, 17, 33), (64, 600, 1)])
+                                    (1024, 2_000_003, 50_000), (16384, (1 << 22) + 12345, 1_000_003), (32768, 3_000_000, 500_000), (64, 17, 33), (64, 600, 1)])
 def test_bucketed_uniform(gpu, oracle, monkeypatch, r, n, nq):
     monkeypatch.setenv("SST_BK_MIN_N", "0")
     monkeypatch.setenv("SST_BK_R", str(r))
@@ -127,3 +127,33 @@ def test_bucketed_unaligned_device_buffers(gpu, oracle, monkeypatch):
     for k in (1, 2, 3, 4):
         v, i = t.query(d[k:], sst.SCHEME_BUCKETED, want_index=True)
         assert np.array_equal(v.cpu().numpy().view(np.uint32), ev[k:]) and np.array_equal(i.cpu().numpy().astype(np.uint64), ei[k:]), k
+
+
+def test_auto_picks_the_pipeline_for_large_batches(gpu, oracle):
+    """SCHEME_AUTO: reordered-batch pipeline from 2^24 queries over >= 2^25 keys, the rank-table kernel below; sst_query_plan
+    reports the choice and the launch count."""
+    import ctypes as C
+
+    import torch
+
+    sst = gpu
+    n = (1 << 25) + 77
+    g = torch.Generator(device="cuda").manual_seed(7)
+    keys = torch.randint(0, MAX, (n,), dtype=torch.int32, device="cuda", generator=g)
+    keys[0] = MAX
+    keys = torch.sort(keys).values.contiguous()
+    t = sst.STree16.new_params(keys, True, False, False)
+    sch, launches = C.c_int(0), C.c_int(0)
+    L = sst.lib()
+    assert L.sst_query_plan(t._h, 1 << 24, 0, 0, C.byref(sch), C.byref(launches)) == 0
+    assert sch.value == sst.SCHEME_BUCKETED and launches.value == 7
+    assert L.sst_query_plan(t._h, 1 << 24, 0, 1, C.byref(sch), C.byref(launches)) == 0 and launches.value == 8
+    assert L.sst_query_plan(t._h, 1 << 20, 0, 0, C.byref(sch), C.byref(launches)) == 0
+    assert sch.value == sst.SCHEME_TABLE and launches.value == 1
+    qs = torch.randint(0, MAX, ((1 << 24) + 5,), dtype=torch.int32, device="cuda", generator=g)
+    v, i = t.query(qs, sst.SCHEME_AUTO, want_index=True)
+    v2, i2 = t.query(qs, sst.SCHEME_TABLE, want_index=True)
+    assert bool((v == v2).all()) and bool((i == i2).all())
+    hk, hq = keys.cpu().numpy().view(np.uint32), qs[:200_000].cpu().numpy().view(np.uint32)
+    ev, ei = oracle.lower_bound(hk, hq)
+    assert np.array_equal(v[:200_000].cpu().numpy().view(np.uint32), ev) and np.array_equal(i[:200_000].cpu().numpy().astype(np.uint64), ei)

@@ -1,5 +1,5 @@
 """Reordered-batch pipeline (SCHEME_BUCKETED) vs the rank-table kernel at LOGN keys / NQ queries: equality of
-results and CUDA-event times; SST_BK_TIMING=1 prints the per-stage split."""
+results and CUDA-event times; SST_BK_TIMING=2 prints the per-stage split."""
 import ctypes as C, os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "suffix-array-searching_b200"))
