@@ -781,7 +781,9 @@ void launch_move(int sms, size_t smem, cudaStream_t st, const Scratch& s, unsign
     const int aligned = (((uintptr_t)src | (uintptr_t)dst) & 15u) == 0 && env_int("SST_BK_VEC", 1);
     auto kern = bk_move_kernel<GATHER, OutT>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<(unsigned)std::min<size_t>(ntiles, (size_t)sms * env_int("SST_BK_MOVE_CTAS", 2)), kThreads, smem, st>>>(s.counts, s.offs, s.lpos, nbp, bpt, ntiles, nq, aligned, src, dst);
+    // scatter: one CTA per SM is faster than two (0.317 vs 0.355 ms per 10^8 queries): two 104 KB tiles leave ~20 KB of L1,
+    // too little for the loads in flight (LG-throttle stalls in ncu); gather: two (0.43 vs 0.49 ms)
+    kern<<<(unsigned)std::min<size_t>(ntiles, (size_t)sms * env_int("SST_BK_MOVE_CTAS", GATHER ? 2 : 1)), kThreads, smem, st>>>(s.counts, s.offs, s.lpos, nbp, bpt, ntiles, nq, aligned, src, dst);
 }
 
 }  // namespace

@@ -128,3 +128,21 @@ def test_sa_reference_return_value(gpu, oracle):
     q = text[5000:5040].tobytes()
     pos = s.binary_search(q)
     assert text[pos : pos + 40].tobytes() == q
+
+
+@pytest.mark.parametrize("levels", ["3", "9", "18"])
+def test_sa_search_sorted_order(gpu, oracle, levels, monkeypatch):
+    """Opt-in reordered batch (SST_SA_SORT_MIN): coarse pass -> radix sort -> search in sorted order; identical outputs,
+    including duplicate patterns, absent patterns and patterns of very different lengths."""
+    sst = gpu
+    monkeypatch.setenv("SST_SA_SORT_MIN", "1")
+    monkeypatch.setenv("SST_SA_SORT_LEVELS", levels)
+    text = random_text(300_000, seed=21)
+    sa = oracle.sa_build(text)
+    s = sst.SaNaive.from_parts(text, sa)
+    pats = random_patterns(text, 5000, seed=22, lo=1, hi=120)
+    rng = np.random.default_rng(23)
+    pats += [rng.integers(0, 4, int(rng.integers(1, 60)), dtype=np.uint8).tobytes() for _ in range(1500)]  # mostly absent
+    pats += pats[:700]  # duplicates
+    pats += [bytes([3] * 40), bytes([0]), bytes([3]), text[-5:].tobytes(), text[:50].tobytes()]
+    _check_search(sst, oracle, s, text, sa, pats)

@@ -90,7 +90,15 @@ def c5(n=3_000_000_000, npat=100_000_000):
     hi = torch.empty(npat, dtype=torch.int32, device=dev)
     pos = torch.empty(npat, dtype=torch.int32, device=dev)
     ref_lo = None
-    for name, mode in (("binary", sst.SA_BINARY), ("mlr", sst.SA_MLR)):
+    variants = [("binary", sst.SA_BINARY, None), ("mlr", sst.SA_MLR, None)]
+    for lv in [x for x in os.environ.get("C5_SORT_LEVELS", "").split(",") if x]:  # sorted-order search at these coarse depths
+        variants.append((f"binary_sorted{lv}", sst.SA_BINARY, lv))
+    for name, mode, sort_lv in variants:
+        if sort_lv is None:
+            os.environ["SST_SA_SORT_MIN"] = str(1 << 62)
+        else:
+            os.environ["SST_SA_SORT_MIN"] = "1"
+            os.environ["SST_SA_SORT_LEVELS"] = sort_lv
         def run():
             rc = L.sst_sa_search_device(sa._h, C.c_void_p(pats.data_ptr()), C.c_void_p(off.data_ptr()), npat, mode,
                                         C.c_void_p(lo.data_ptr()), C.c_void_p(hi.data_ptr()), C.c_void_p(pos.data_ptr()), None)
