@@ -509,7 +509,7 @@ struct BkSearchParams {
     const uint2* meta;       // [nb] {lo, shift}
     const uint32_t* leaf;    // sorted keys (leaf level of the image, MAX-padded)
     unsigned r;              // half nodes (separators) per bucket
-    unsigned long long m8;   // half nodes that hold keys
+    unsigned long long m8;   // blocks of G keys (half nodes / nodes) that hold keys
     unsigned long long n;
 };
 
@@ -519,11 +519,12 @@ __device__ __forceinline__ void ldg256(const uint32_t* p, uint32_t (&k)[8]) {
                  : "l"(p));
 }
 
-template <bool WANT_IDX>
+// G = keys per separator: 8 (half node, one 32-byte sector per query) up to 2^29 keys, 16 (whole node, two sectors) above
+template <bool WANT_IDX, int G>
 __global__ void __launch_bounds__(1024, 1)
 bk_search_kernel(const BkSearchParams p, const uint32_t* __restrict__ qb, const uint32_t* __restrict__ bstart,
                  const uint2* __restrict__ items, unsigned* __restrict__ ctrl, uint32_t* __restrict__ rb, uint32_t* __restrict__ ib) {
-    constexpr int U = 4;
+    constexpr int U = G == 8 ? 4 : 2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t* s_sep = reinterpret_cast<uint32_t*>(smem_raw);                 // [r]
     uint16_t* s_jump = reinterpret_cast<uint16_t*>(s_sep + p.r);              // [r + 8]
@@ -612,25 +613,26 @@ bk_search_kernel(const BkSearchParams p, const uint32_t* __restrict__ qb, const 
                 }
                 a[u] = pos;
             }
-            uint32_t ks[U][8];
+            uint32_t ks[U][G];
             unsigned long long hn[U];
 #pragma unroll
             for (int u = 0; u < U; u++) {  // the half node that holds the answer: one 32-byte sector
                 hn[u] = hbase + a[u];
                 const unsigned long long hc = hn[u] < p.m8 ? hn[u] : p.m8 - 1;
-                ldg256(p.leaf + hc * 8ull, ks[u]);
+                ldg256(p.leaf + hc * (unsigned long long)G, reinterpret_cast<uint32_t(&)[8]>(ks[u][0]));
+                if constexpr (G == 16) ldg256(p.leaf + hc * 16ull + 8ull, reinterpret_cast<uint32_t(&)[8]>(ks[u][8]));
             }
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 const unsigned i = i0 + u * nthr;
                 unsigned c = 0;
 #pragma unroll
-                for (int e = 0; e < 8; e++) c += ks[u][e] < q[u] ? 1u : 0u;
+                for (int e = 0; e < G; e++) c += ks[u][e] < q[u] ? 1u : 0u;
                 uint32_t val = ks[u][0];
 #pragma unroll
-                for (int e = 1; e < 8; e++) val = c == (unsigned)e ? ks[u][e] : val;
-                unsigned long long pos = hn[u] * 8ull + c;
-                if (hn[u] >= p.m8 || c == 8u) { val = kMax; pos = p.n; }  // above every key (c == 8 cannot happen below m8)
+                for (int e = 1; e < G; e++) val = c == (unsigned)e ? ks[u][e] : val;
+                unsigned long long pos = hn[u] * (unsigned long long)G + c;
+                if (hn[u] >= p.m8 || c == (unsigned)G) { val = kMax; pos = p.n; }  // above every key (c == G cannot happen below m8)
                 if (pos > p.n) pos = p.n;
                 if (i < qend) {
                     __stcs(rb + i, val);
@@ -644,11 +646,12 @@ bk_search_kernel(const BkSearchParams p, const uint32_t* __restrict__ qb, const 
 // ------------------------------------------------------------------------------------------------
 // auxiliary arrays (index build time)
 // ------------------------------------------------------------------------------------------------
-// sep[m] = last key of half node m (leaf slot 8m + 7) for m < m8, 0xffffffff beyond
-__global__ void bk_sep_kernel(const uint32_t* __restrict__ leaf, unsigned long long m8, unsigned long long total, uint32_t* __restrict__ sep) {
+// sep[m] = last key of block m of g keys (leaf slot g*m + g - 1) for m < m8, 0xffffffff beyond
+__global__ void bk_sep_kernel(const uint32_t* __restrict__ leaf, unsigned long long m8, unsigned long long total, unsigned g,
+                              uint32_t* __restrict__ sep) {
     for (unsigned long long m = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; m < total;
          m += (unsigned long long)gridDim.x * blockDim.x)
-        sep[m] = m < m8 ? leaf[m * 8ull + 7ull] : 0xffffffffu;
+        sep[m] = m < m8 ? leaf[m * g + g - 1] : 0xffffffffu;
 }
 // split[0] = 0, split[b] = sep[b*r - 1] (last key before bucket b), split[nb] = MAX
 __global__ void bk_split_kernel(const uint32_t* __restrict__ sep, unsigned nb, unsigned r, uint32_t* __restrict__ split) {
@@ -800,11 +803,14 @@ bool build_bucket_aux(sst_index* idx) {
     if (idx->n < (size_t)env_int("SST_BK_MIN_N", 1 << 22)) return true;  // small trees are L2-resident: nothing to gain
     // separators per bucket: 16384 (two search CTAs per SM) up to 2^27 keys, 32768 (one 1024-thread CTA) above, so that the
     // partition has at most 1024 buckets up to 2^28 keys -- fewer buckets = longer runs and fewer ballot bits
-    const unsigned long long m8 = div_ceil(idx->n, (size_t)8);
+    // keys per separator: 8 (one leaf sector per query) up to 2^29 keys, 16 (a whole node) up to 2^30
+    unsigned g = (unsigned)env_int("SST_BK_G", div_ceil(idx->n, (size_t)8) > 32768ull * 2048ull ? 16 : 8);
+    if (g != 8 && g != 16) g = 8;
+    const unsigned long long m8 = div_ceil(idx->n, (size_t)g);
     unsigned r = (unsigned)env_int("SST_BK_R", m8 > 16384ull * 1024ull ? 32768 : 16384);
     if (r < 64 || r > 32768 || (r & (r - 1))) r = 16384;
     const unsigned long long nb64 = div_ceil((size_t)m8, (size_t)r);
-    if (nb64 > 2048) return true;  // > 2^29 keys: served by the rank-table kernel
+    if (nb64 > 2048) return true;  // > 2^30 keys: served by the rank-table kernel
     BkAux& a = idx->bk;
     const unsigned nb = (unsigned)nb64;
     const unsigned nbp = (unsigned)(div_ceil((size_t)nb, (size_t)kThreads) * kThreads);
@@ -817,14 +823,14 @@ bool build_bucket_aux(sst_index* idx) {
               SST_CUDA_OK(cudaMalloc(&a.d_bt, (size_t)kBtStride * 2)) && SST_CUDA_OK(cudaMalloc(&a.d_jump, (size_t)nb * (r + 8) * 2)) &&
               SST_CUDA_OK(cudaMalloc(&a.d_meta, (size_t)nb * sizeof(uint2)));
     if (ok) {
-        bk_sep_kernel<<<(unsigned)std::min<size_t>(div_ceil((size_t)total, (size_t)256), 148 * 16), 256, 0, st>>>(leaf, m8, total, a.d_sep);
+        bk_sep_kernel<<<(unsigned)std::min<size_t>(div_ceil((size_t)total, (size_t)256), 148 * 16), 256, 0, st>>>(leaf, m8, total, g, a.d_sep);
         bk_split_kernel<<<(unsigned)div_ceil((size_t)nb + 1, (size_t)256), 256, 0, st>>>(a.d_sep, nb, r, a.d_split);
         bk_bt_kernel<<<(unsigned)div_ceil((size_t)kBtStride, (size_t)256), 256, 0, st>>>(a.d_split, nb, a.d_bt);
         bk_jump_kernel<<<nb, 256, 0, st>>>(a.d_sep, a.d_split, r, m8, a.d_jump, a.d_meta);
         ok = SST_CUDA_OK(cudaGetLastError()) && SST_CUDA_OK(cudaStreamSynchronize(st));
     }
     if (!ok) { free_bucket_aux(idx); return false; }
-    a.nb = nb; a.nbp = nbp; a.r = r; a.bits = bits; a.m8 = m8;
+    a.nb = nb; a.nbp = nbp; a.r = r; a.bits = bits; a.m8 = m8; a.g = g;
     return true;
 }
 
@@ -887,12 +893,9 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
         mark();
         launch_move<false, uint32_t>(sms, smem_move, st, s, a.nbp, bpt, ntiles, cnt, qs, s.qb);
         mark();
-        if (d_idx) {
-            auto kern = bk_search_kernel<true>;
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_search);
-            kern<<<sms * search_ctas, search_threads, smem_search, st>>>(sp, s.qb, s.bstart, s.items, s.ctrl, s.rb, s.ib);
-        } else {
-            auto kern = bk_search_kernel<false>;
+        {
+            void (*kern)(const BkSearchParams, const uint32_t*, const uint32_t*, const uint2*, unsigned*, uint32_t*, uint32_t*) =
+                a.g == 16 ? (d_idx ? bk_search_kernel<true, 16> : bk_search_kernel<false, 16>) : (d_idx ? bk_search_kernel<true, 8> : bk_search_kernel<false, 8>);
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_search);
             kern<<<sms * search_ctas, search_threads, smem_search, st>>>(sp, s.qb, s.bstart, s.items, s.ctrl, s.rb, s.ib);
         }

@@ -101,13 +101,14 @@ struct SstTreeView {
 
 // Auxiliary arrays of the reordered-batch pipeline (bucketed.cu); nb == 0: not built for this index.
 struct BkAux {
-    uint32_t* d_sep = nullptr;    // [nb * r] last key of every 8-key half node of the leaf level, 0xffffffff beyond the keys
+    uint32_t* d_sep = nullptr;    // [nb * r] last key of every g-key block of the leaf level, 0xffffffff beyond the keys
     uint32_t* d_split = nullptr;  // [nb + 1] split[0] = 0, split[b] = last key before bucket b, split[nb] = MAX
     uint16_t* d_bt = nullptr;     // bucket table over the top 12 key bits
     uint16_t* d_jump = nullptr;   // [nb][8200] per-bucket jump table into its separators
     uint2* d_meta = nullptr;      // [nb] {lo, shift} of the jump table
     unsigned nb = 0, nbp = 0, r = 0, bits = 0;
-    unsigned long long m8 = 0;    // half nodes that hold keys
+    unsigned g = 8;               // keys per separator: 8 (half node) or 16 (node)
+    unsigned long long m8 = 0;    // blocks of g keys that hold keys
 };
 
 struct sst_index {

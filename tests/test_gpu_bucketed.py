@@ -31,6 +31,20 @@ def test_bucketed_uniform(gpu, oracle, monkeypatch, r, n, nq):
     _check(gpu, oracle, vals, gen_queries(nq, seed=n + 1, vals=vals))
 
 
+@pytest.mark.parametrize("r,n,nq", [(64, 5000, 40_000), (64, 1_000_000, 70_000), (256, (1 << 20) + 5, 300_000), (32768, 3_000_000, 500_000), (64, 16, 33),
+                                    (64, 17, 5)])
+def test_bucketed_node_granularity(gpu, oracle, monkeypatch, r, n, nq):
+    """SST_BK_G=16: one separator per 16-key node (the layout used above 2^29 keys), two leaf sectors per query."""
+    monkeypatch.setenv("SST_BK_MIN_N", "0")
+    monkeypatch.setenv("SST_BK_R", str(r))
+    monkeypatch.setenv("SST_BK_G", "16")
+    vals = gen_vals(n, seed=n + r + 1)
+    _check(gpu, oracle, vals, gen_queries(nq, seed=n + 2, vals=vals))
+    rng = np.random.default_rng(n)
+    skew = make_keys(rng, n, "dupes")
+    _check(gpu, oracle, skew, make_queries(rng, skew, max(nq // 4, 3)), flags=[(1, 0, 0), (0, 1, 0)])
+
+
 @pytest.mark.parametrize("seed", range(10))
 def test_bucketed_fuzz(gpu, oracle, monkeypatch, seed):
     """Adversarial key distributions (clusters, duplicate runs longer than a bucket, tiny ranges): crowded bucket-table
