@@ -44,6 +44,7 @@ constexpr int kBtCells = 1 << (31 - kBtShift);
 constexpr int kBtStride = kBtCells + 8;
 constexpr unsigned kChunk = 16384;           // queries per search work item
 constexpr int kTilesPerGroup = 64;
+constexpr unsigned kLongRun = 128;           // map runs longer than this are filled cooperatively
 constexpr size_t kSubBatch = (size_t)1 << 27;  // queries per pipeline run (bounds the scratch buffers)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -156,8 +157,6 @@ __device__ __forceinline__ void ballot_bits(unsigned& peers, unsigned b) {
 }
 
 // FULL: every tile in [tile_begin, tile_end) holds kTile queries (the partial last tile gets its own launch).
-// BITS < 0: instead of ballots the lanes CLAIM their bucket's counter: everyone writes count + 1 tagged with its
-// lane id (5 tag bits above the 11 count bits), the lane whose tag sticks takes rank = count, the others retry.
 template <int BITS, bool FULL, bool HYBRID>
 __device__ __forceinline__ void rank_tile(const BkView& v, const uint32_t* __restrict__ qs, size_t nq, unsigned tile, uint32_t* __restrict__ counts,
                                           uint16_t* __restrict__ lpos16, uint16_t* cnt, const uint16_t* s_bt, const uint32_t* s_split,
@@ -191,24 +190,33 @@ __device__ __forceinline__ void rank_tile(const BkView& v, const uint32_t* __res
             // Two ways to rank, used on alternating steps so that the work is split between the ALU pipe (ballots) and
             // the shared-memory pipe (claims) -- each alone is bound by its pipe (0.61 / 0.55 ms per 10^8 queries):
             //  claim:   every lane writes count + 1 tagged with its lane id (5 tag bits above the 11 count bits); the lane
-            //           whose tag sticks takes rank = count, the others retry
+            //           whose tag sticks takes rank = count; if any lane lost (two queries of one bucket in the same step,
+            //           ~1 step in 5 for uniform queries) the losers are settled by ballots, so the cost stays bounded
+            //           when every query hits the same bucket
             //  ballots: lanes with the same bucket find each other by ballots over the bucket bits; the lowest of them
             //           bumps the counter by the group size
-            const bool claim_step = BITS < 0 || (HYBRID && (r & 1));
+            const bool claim_step = HYBRID && (r & 1);
             if (claim_step) {
-                bool done = !valid;
-                unsigned w = 0, rank = 0;
-                do {
-                    if (!done) w = cntw[b];
+                const unsigned w = valid ? cntw[b] : 0u;
+                __syncwarp();
+                if (valid) cntw[b] = (uint16_t)(((w & 0x7ffu) + 1u) | (lane << 11));
+                __syncwarp();
+                const bool lost = valid && (unsigned)(cntw[b] >> 11) != lane;
+                unsigned rank = w & 0x7ffu;
+                unsigned peers = __ballot_sync(kFull, lost);
+                if (peers) {  // (warp-uniform, ~1 step in 5) lanes that share a bucket with a winner: settle them by ballots
+                    ballot_bits<0, BITS>(peers, b);
+                    const unsigned before = peers & lt_mask;
+                    const unsigned old = lost ? (cntw[b] & 0x7ffu) : 0u;  // includes the winner's +1
                     __syncwarp();
-                    if (!done) cntw[b] = (uint16_t)(((w & 0x7ffu) + 1u) | (lane << 11));
+                    if (lost && before == 0u) cntw[b] = (uint16_t)(old + __popc(peers));
                     __syncwarp();
-                    if (!done && (unsigned)(cntw[b] >> 11) == lane) { rank = w & 0x7ffu; done = true; }
-                } while (!__all_sync(kFull, done));
+                    if (lost) rank = old + __popc(before);
+                }
                 if (valid) pk[r] = b | (rank << 16);
             } else {
                 unsigned peers = FULL ? kFull : __ballot_sync(kFull, valid);
-                ballot_bits<0, (BITS < 0 ? 0 : BITS)>(peers, b);
+                ballot_bits<0, BITS>(peers, b);
                 const unsigned before = peers & lt_mask;
                 const unsigned old = valid ? (cntw[b] & 0x7ffu) : 0u;
                 __syncwarp();
@@ -395,7 +403,11 @@ bk_move_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__
     uint32_t* s_delta = s_tile + kTile;                                // [nbp] global offset - local start
     uint16_t* s_map = reinterpret_cast<uint16_t*>(s_delta + nbp);      // [kTile] bucket of each local position
     __shared__ unsigned s_warp[kWarps + 1];
+    __shared__ uint4 s_long[kTile / kLongRun];  // runs longer than kLongRun: {begin, end, bucket}
+    __shared__ unsigned s_nlong;
     const unsigned tid = threadIdx.x;
+    if (tid == 0) s_nlong = 0;
+    __syncthreads();
     constexpr int kVec = kItems / 4;  // 8 groups of 4 consecutive queries per thread
     unsigned c[4] = {0, 0, 0, 0}, o[4] = {0, 0, 0, 0};
     auto load_row = [&](unsigned tile) {  // this thread's buckets of the count / offset rows of `tile`
@@ -422,13 +434,27 @@ bk_move_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__
                 const unsigned b = tid * bpt + k;
                 s_delta[b] = o[k] - base;
                 unsigned j = base, e = base + c[k];  // fill [j, e) with b: 32-bit stores over the aligned middle
-                if (j < e && (j & 1u)) s_map[j++] = (uint16_t)b;
-                for (; j + 2 <= e; j += 2) *reinterpret_cast<uint32_t*>(s_map + j) = b | (b << 16);
-                if (j < e) s_map[j] = (uint16_t)b;
+                if (c[k] > kLongRun) {  // skewed batch: a long run is filled by the whole CTA below, not by one thread
+                    const unsigned slot = atomicAdd(&s_nlong, 1u);
+                    s_long[slot] = make_uint4(j, e, b, 0);
+                } else {
+                    if (j < e && (j & 1u)) s_map[j++] = (uint16_t)b;
+                    for (; j + 2 <= e; j += 2) *reinterpret_cast<uint32_t*>(s_map + j) = b | (b << 16);
+                    if (j < e) s_map[j] = (uint16_t)b;
+                }
                 base = e;
             }
         if (tile + gridDim.x < ntiles) load_row(tile + gridDim.x);  // next tile's rows: in flight during this tile
         __syncthreads();
+        if (s_nlong) {  // (block-uniform)
+            const unsigned nl = s_nlong;
+            for (unsigned q = 0; q < nl; q++) {
+                const uint4 lr = s_long[q];
+                for (unsigned j = lr.x + tid; j < lr.y; j += kThreads) s_map[j] = (uint16_t)lr.z;
+            }
+            __syncthreads();
+            if (tid == 0) s_nlong = 0;
+        }
         if (aligned && tile_n == (unsigned)kTile) {
             const uint2* l2 = reinterpret_cast<const uint2*>(lpos16 + tile_base);
             if constexpr (!GATHER) {
@@ -877,8 +903,7 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
         const uint32_t* qs = d_qs + off;
         nev = 0;
         mark();
-        switch (env_int("SST_BK_CLAIM", 0) ? -1 : (int)a.bits) {
-            case -1: launch_rank<-1>(v, sms, smem_rank, st, qs, cnt, ntiles, s.counts, s.lpos, s.tot); break;
+        switch (a.bits) {
 #define SST_BK_RANK(B) case B: launch_rank<B>(v, sms, smem_rank, st, qs, cnt, ntiles, s.counts, s.lpos, s.tot); break;
             SST_BK_RANK(0) SST_BK_RANK(1) SST_BK_RANK(2) SST_BK_RANK(3) SST_BK_RANK(4) SST_BK_RANK(5)
             SST_BK_RANK(6) SST_BK_RANK(7) SST_BK_RANK(8) SST_BK_RANK(9) SST_BK_RANK(10) SST_BK_RANK(11)

@@ -171,3 +171,15 @@ def test_auto_picks_the_pipeline_for_large_batches(gpu, oracle):
     hk, hq = keys.cpu().numpy().view(np.uint32), qs[:200_000].cpu().numpy().view(np.uint32)
     ev, ei = oracle.lower_bound(hk, hq)
     assert np.array_equal(v[:200_000].cpu().numpy().view(np.uint32), ev) and np.array_equal(i[:200_000].cpu().numpy().astype(np.uint64), ei)
+
+
+def test_bucketed_degenerate_batches(gpu, oracle, monkeypatch):
+    """Every query in one bucket / one key (all lanes of a warp collide in the ranking step), sorted and reverse-sorted batches."""
+    sst = gpu
+    monkeypatch.setenv("SST_BK_MIN_N", "0")
+    monkeypatch.setenv("SST_BK_R", "256")
+    vals = gen_vals(700_000, seed=33)
+    for qs in (np.full(300_001, vals[123_456], np.uint32), np.full(50_000, 0, np.uint32), np.full(50_000, MAX, np.uint32),
+               np.sort(gen_queries(200_000, seed=34, vals=vals)), np.sort(gen_queries(200_000, seed=35, vals=vals))[::-1].copy(),
+               (vals[100_000] + (np.arange(150_000) % 7)).astype(np.uint32)):
+        _check(sst, oracle, vals, qs, flags=[(1, 0, 0)])

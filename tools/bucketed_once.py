@@ -13,6 +13,12 @@ keys = torch.randint(0, sst.MAX, (n,), dtype=torch.int32, device=dev, generator=
 keys = torch.sort(keys).values.contiguous()
 t = sst.STree16.new_params(keys, True, False, False)
 qs = torch.randint(0, sst.MAX, (nq,), dtype=torch.int32, device=dev, generator=g)
+if os.environ.get("SKEW") == "equal":      # every query the same key: one bucket, every lane of a warp collides
+    qs[:] = int(keys[n // 3])
+elif os.environ.get("SKEW") == "narrow":   # all queries inside one bucket
+    qs = (int(keys[n // 3]) + (qs % 100_000)).to(torch.int32).contiguous()
+elif os.environ.get("SKEW") == "sorted":
+    qs = torch.sort(qs).values.contiguous()
 v1, i1 = t.query(qs, sst.SCHEME_TABLE, want_index=True)
 v2, i2 = t.query(qs, sst.SCHEME_BUCKETED, want_index=True)
 torch.cuda.synchronize()
