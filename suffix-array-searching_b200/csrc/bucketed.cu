@@ -42,7 +42,7 @@ constexpr int kItems = kTile / kThreads;     // 32 queries per thread
 constexpr int kBtShift = 18;                 // bucket table over the top 13 bits of a 31-bit key
 constexpr int kBtCells = 1 << (31 - kBtShift);
 constexpr int kBtStride = kBtCells + 8;
-constexpr unsigned kChunk = 16384;           // queries per search work item
+constexpr unsigned kMinChunk = 16384;        // queries per search work item: at least this many (scratch sizing)
 constexpr int kTilesPerGroup = 64;
 constexpr unsigned kLongRun = 128;           // map runs longer than this are filled cooperatively
 constexpr size_t kSubBatch = (size_t)1 << 27;  // queries per pipeline run (bounds the scratch buffers)
@@ -339,7 +339,7 @@ bk_colsum_kernel(const uint32_t* __restrict__ counts, unsigned ntiles, unsigned 
 
 // bucket starts, work items of the search kernel; ctrl[0] = work counter, ctrl[1] = number of work items
 __global__ void __launch_bounds__(1024)
-bk_plan_kernel(const uint32_t* __restrict__ tot_in, unsigned nbp, uint32_t* __restrict__ bstart, uint2* __restrict__ items,
+bk_plan_kernel(const uint32_t* __restrict__ tot_in, unsigned nbp, unsigned chunk, uint32_t* __restrict__ bstart, uint2* __restrict__ items,
                unsigned* __restrict__ ctrl) {
     __shared__ unsigned s_warp[33];
     const unsigned tid = threadIdx.x;
@@ -351,12 +351,12 @@ bk_plan_kernel(const uint32_t* __restrict__ tot_in, unsigned nbp, uint32_t* __re
     if (tid * 2 + 1 < nbp) bstart[tid * 2 + 1] = base + tot[0];
     if (tid == 0) bstart[nbp] = total;
     __syncthreads();
-    const unsigned ni0 = (tot[0] + kChunk - 1) / kChunk, ni1 = (tot[1] + kChunk - 1) / kChunk;
+    const unsigned ni0 = (tot[0] + chunk - 1) / chunk, ni1 = (tot[1] + chunk - 1) / chunk;
     unsigned nitems;
     unsigned ib = block_excl_scan(ni0 + ni1, s_warp, &nitems);
     for (unsigned c = 0; c < ni0; c++) items[ib + c] = make_uint2(tid * 2, c);
     for (unsigned c = 0; c < ni1; c++) items[ib + ni0 + c] = make_uint2(tid * 2 + 1, c);
-    if (tid == 0) { ctrl[0] = 0; ctrl[1] = nitems; }
+    if (tid == 0) { ctrl[0] = 0; ctrl[1] = nitems; ctrl[2] = chunk; }
 }
 
 // offs[t][b] = position in the bucketed array of the first query of (tile t, bucket b)
@@ -562,7 +562,7 @@ bk_search_kernel(const BkSearchParams p, const uint32_t* __restrict__ qb, const 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     unsigned phase = 0, cur_b = 0xffffffffu;
-    const unsigned nitems = ctrl[1];
+    const unsigned nitems = ctrl[1], chunk = ctrl[2];
     while (true) {
         __syncthreads();  // previous item finished: s_item, s_sep, s_jump may be overwritten
         if (tid == 0) s_item = atomicAdd(&ctrl[0], 1u);
@@ -587,7 +587,7 @@ bk_search_kernel(const BkSearchParams p, const uint32_t* __restrict__ qb, const 
         const uint2 mt = p.meta[b];
         const uint32_t lo = mt.x;
         const unsigned sh = mt.y;
-        const unsigned qbeg = bstart[b] + it.y * kChunk, qend = min(qbeg + kChunk, bstart[b + 1]);
+        const unsigned qbeg = bstart[b] + it.y * chunk, qend = min(qbeg + chunk, bstart[b + 1]);
         const unsigned long long hbase = (unsigned long long)b * p.r;
         uint32_t qn[U];  // queries of the next round: their loads stay in flight while this round is answered
 #pragma unroll
@@ -780,7 +780,7 @@ bool scratch_ensure(Scratch& s, int device, size_t nq, bool want_idx, unsigned n
         if (!regrow(s.counts, mat) || !regrow(s.offs, mat) || !regrow(s.gsum, mat / kTilesPerGroup + 4096)) return false;
         s.cap_mat = mat;
     }
-    const size_t items = 2048 + nq / kChunk + 2;
+    const size_t items = 2048 + nq / kMinChunk + 2;
     if (items > s.cap_items) {
         s.cap_items = 0;
         if (!regrow(s.items, items)) return false;
@@ -886,6 +886,9 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
     const size_t smem_search = (size_t)a.r * 4 + ((size_t)a.r + 8) * 2;
     // two CTAs of 512 threads per SM while two buckets fit shared memory, else one CTA of 1024 threads
     const int search_threads = smem_search * 2 + 4096 <= max_smem_optin(dev) ? kThreads : 1024, search_ctas = search_threads == kThreads ? 2 : 1;
+    // queries per search work item: every item stages its bucket (r * 6 bytes) again, so larger is cheaper, but a bucket
+    // should still split into a few items for load balance
+    const unsigned chunk = (unsigned)std::max(env_int("SST_BK_CHUNK", 32768), (int)kMinChunk);
     BkSearchParams sp{a.d_sep, a.d_jump, a.d_meta, idx->d_tree + idx->offsets[idx->levels - 1] * 16, a.r, a.m8, (unsigned long long)idx->n};
     // SST_BK_TIMING=1 (debug): per-stage CUDA-event times on stderr; synchronises the stream
     const bool timing = env_int("SST_BK_TIMING", 0) != 0;
@@ -913,7 +916,7 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
         mark();
         const dim3 mgrid(a.nbp / 256, ngroups);
         bk_colsum_kernel<<<mgrid, 256, 0, st>>>(s.counts, ntiles, a.nbp, s.gsum, s.tot);
-        bk_plan_kernel<<<1, 1024, 0, st>>>(s.tot, a.nbp, s.bstart, s.items, s.ctrl);
+        bk_plan_kernel<<<1, 1024, 0, st>>>(s.tot, a.nbp, chunk, s.bstart, s.items, s.ctrl);
         bk_offsets_kernel<<<mgrid, 256, 0, st>>>(s.counts, s.gsum, s.bstart, ntiles, a.nbp, s.offs);
         mark();
         launch_move<false, uint32_t>(sms, smem_move, st, s, a.nbp, bpt, ntiles, cnt, qs, s.qb);
