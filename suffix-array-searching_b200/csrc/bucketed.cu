@@ -876,7 +876,10 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
     if (dev < 0 || dev >= 64) { set_error(SST_ERR_ARG, "device index out of range"); return SST_ERR_ARG; }
     Scratch& s = g_scratch[dev];
     const size_t sub = std::min(nq, kSubBatch);
-    if (!scratch_ensure(s, dev, sub, d_idx != nullptr, a.nbp)) return SST_ERR_CUDA;
+    if (!scratch_ensure(s, dev, sub, d_idx != nullptr, a.nbp)) {  // out of device memory for the scratch buffers
+        set_error(SST_ERR_CAPACITY, "not enough device memory for the reordered-batch scratch buffers (10-14 bytes per query)");
+        return SST_ERR_CAPACITY;
+    }
     if (!SST_CUDA_OK(cudaStreamWaitEvent(st, s.done, 0))) return SST_ERR_CUDA;  // scratch reuse across this thread's streams
     const int sms = sm_count(dev);
     const unsigned bpt = a.nbp / kThreads;

@@ -801,7 +801,15 @@ int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t
         else pstree_search_group<2><<<grid, 512, 0, st>>>(idx->view, d_qs, nq, d_vals, d_idx);
         return SST_CUDA_OK(cudaGetLastError()) ? SST_OK : SST_ERR_CUDA;
     }
+    const bool was_auto = scheme == SST_SCHEME_AUTO;
     scheme = resolve_scheme(idx, scheme, nq);
+    if (was_auto && scheme == SST_SCHEME_BUCKETED) {
+        // the pipeline needs ~10-14 bytes of device scratch per query: when that cannot be had, AUTO falls back to the direct kernel
+        const int rc = launch_bucketed(idx, d_qs, nq, d_vals, d_idx, st);
+        if (rc != SST_ERR_CAPACITY) return rc;
+        clear_error();
+        scheme = top_eligible(idx) ? SST_SCHEME_TABLE : SST_SCHEME_GROUP2;
+    }
     if (scheme != SST_SCHEME_GENERIC && !fast_eligible(idx)) {  // (BINSEARCH included: plain B=16 only)
         set_error(SST_ERR_UNSUPPORTED, "the group/table kernels serve the plain B=16 tree; use SST_SCHEME_AUTO or SST_SCHEME_GENERIC");
         return SST_ERR_UNSUPPORTED;
