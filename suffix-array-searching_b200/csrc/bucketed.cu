@@ -393,8 +393,9 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
-template <bool GATHER, typename OutT>
-__global__ void __launch_bounds__(kThreads, 2)
+// THREADS = 512 (two CTAs per SM) or 1024 (one CTA per SM: the same shared memory, i.e. ~120 KB of L1 left for loads in flight)
+template <bool GATHER, typename OutT, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 bk_move_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offs, const uint16_t* __restrict__ lpos16,
                unsigned nbp, unsigned bpt, unsigned ntiles, size_t nq, int aligned, const uint32_t* __restrict__ src,
                OutT* __restrict__ dst) {
@@ -402,13 +403,14 @@ bk_move_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__
     uint32_t* s_tile = reinterpret_cast<uint32_t*>(smem_raw);        // [kTile] in bucket order
     uint32_t* s_delta = s_tile + kTile;                                // [nbp] global offset - local start
     uint16_t* s_map = reinterpret_cast<uint16_t*>(s_delta + nbp);      // [kTile] bucket of each local position
-    __shared__ unsigned s_warp[kWarps + 1];
+    __shared__ unsigned s_warp[THREADS / 32 + 1];
     __shared__ uint4 s_long[kTile / kLongRun];  // runs longer than kLongRun: {begin, end, bucket}
     __shared__ unsigned s_nlong;
     const unsigned tid = threadIdx.x;
     if (tid == 0) s_nlong = 0;
     __syncthreads();
-    constexpr int kVec = kItems / 4;  // 8 groups of 4 consecutive queries per thread
+    constexpr int kIt = kTile / THREADS;  // queries per thread
+    constexpr int kVec = kIt / 4;         // groups of 4 consecutive queries per thread
     unsigned c[4] = {0, 0, 0, 0}, o[4] = {0, 0, 0, 0};
     auto load_row = [&](unsigned tile) {  // this thread's buckets of the count / offset rows of `tile`
         if (bpt == 4) {
@@ -450,7 +452,7 @@ bk_move_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__
             const unsigned nl = s_nlong;
             for (unsigned q = 0; q < nl; q++) {
                 const uint4 lr = s_long[q];
-                for (unsigned j = lr.x + tid; j < lr.y; j += kThreads) s_map[j] = (uint16_t)lr.z;
+                for (unsigned j = lr.x + tid; j < lr.y; j += THREADS) s_map[j] = (uint16_t)lr.z;
             }
             __syncthreads();
             if (tid == 0) s_nlong = 0;
@@ -462,7 +464,7 @@ bk_move_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__
                 uint4 q[kVec];
                 uint2 l[kVec];
 #pragma unroll
-                for (int r = 0; r < kVec; r++) { q[r] = __ldcs(q4 + r * kThreads + tid); l[r] = __ldcs(l2 + r * kThreads + tid); }
+                for (int r = 0; r < kVec; r++) { q[r] = __ldcs(q4 + r * THREADS + tid); l[r] = __ldcs(l2 + r * THREADS + tid); }
 #pragma unroll
                 for (int r = 0; r < kVec; r++) {
                     s_tile[l[r].x & 0xffffu] = canonical(q[r].x); s_tile[l[r].x >> 16] = canonical(q[r].y);
@@ -470,25 +472,25 @@ bk_move_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__
                 }
                 __syncthreads();
 #pragma unroll
-                for (int r = 0; r < kItems; r++) {  // runs: consecutive lanes write consecutive words
-                    const unsigned i = r * kThreads + tid;
+                for (int r = 0; r < kIt; r++) {  // runs: consecutive lanes write consecutive words
+                    const unsigned i = r * THREADS + tid;
                     dst[s_delta[s_map[i]] + i] = (OutT)s_tile[i];
                 }
             } else {
 #pragma unroll
-                for (int r = 0; r < kItems; r++) {
-                    const unsigned i = r * kThreads + tid;
+                for (int r = 0; r < kIt; r++) {
+                    const unsigned i = r * THREADS + tid;
                     cp_async4(s_tile + i, src + (s_delta[s_map[i]] + i));
                 }
                 uint2 l[kVec];
 #pragma unroll
-                for (int r = 0; r < kVec; r++) l[r] = __ldcs(l2 + r * kThreads + tid);
+                for (int r = 0; r < kVec; r++) l[r] = __ldcs(l2 + r * THREADS + tid);
                 cp_async_wait_all();
                 __syncthreads();
 #pragma unroll
                 for (int r = 0; r < kVec; r++) {
                     const uint32_t v0 = s_tile[l[r].x & 0xffffu], v1 = s_tile[l[r].x >> 16], v2 = s_tile[l[r].y & 0xffffu], v3 = s_tile[l[r].y >> 16];
-                    OutT* d = dst + tile_base + (size_t)(r * kThreads + tid) * 4;
+                    OutT* d = dst + tile_base + (size_t)(r * THREADS + tid) * 4;
                     if constexpr (sizeof(OutT) == 4) {
                         __stcs(reinterpret_cast<uint4*>(d), make_uint4(v0, v1, v2, v3));
                     } else {
@@ -499,26 +501,26 @@ bk_move_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__
             }
         } else if constexpr (!GATHER) {
 #pragma unroll 8
-            for (int r = 0; r < kItems; r++) {
-                const unsigned i = r * kThreads + tid;
+            for (int r = 0; r < kIt; r++) {
+                const unsigned i = r * THREADS + tid;
                 if (i < tile_n) s_tile[lpos16[tile_base + i]] = canonical(__ldcs(src + tile_base + i));
             }
             __syncthreads();
 #pragma unroll 8
-            for (int r = 0; r < kItems; r++) {
-                const unsigned i = r * kThreads + tid;
+            for (int r = 0; r < kIt; r++) {
+                const unsigned i = r * THREADS + tid;
                 if (i < tile_n) dst[s_delta[s_map[i]] + i] = (OutT)s_tile[i];
             }
         } else {
 #pragma unroll 8
-            for (int r = 0; r < kItems; r++) {
-                const unsigned i = r * kThreads + tid;
+            for (int r = 0; r < kIt; r++) {
+                const unsigned i = r * THREADS + tid;
                 if (i < tile_n) s_tile[i] = __ldcs(src + (s_delta[s_map[i]] + i));
             }
             __syncthreads();
 #pragma unroll 8
-            for (int r = 0; r < kItems; r++) {
-                const unsigned i = r * kThreads + tid;
+            for (int r = 0; r < kIt; r++) {
+                const unsigned i = r * THREADS + tid;
                 if (i < tile_n) __stcs(dst + tile_base + i, (OutT)s_tile[lpos16[tile_base + i]]);
             }
         }
@@ -805,14 +807,23 @@ void launch_rank(const BkView& v, int sms, size_t smem, cudaStream_t st, const u
 }
 
 template <bool GATHER, typename OutT>
-void launch_move(int sms, size_t smem, cudaStream_t st, const Scratch& s, unsigned nbp, unsigned bpt, unsigned ntiles, size_t nq,
-                 const uint32_t* src, OutT* dst) {
+void launch_move(int sms, size_t smem, cudaStream_t st, const Scratch& s, unsigned nbp, unsigned ntiles, size_t nq, const uint32_t* src, OutT* dst) {
     const int aligned = (((uintptr_t)src | (uintptr_t)dst) & 15u) == 0 && env_int("SST_BK_VEC", 1);
-    auto kern = bk_move_kernel<GATHER, OutT>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    // scatter: one CTA per SM is faster than two (0.317 vs 0.355 ms per 10^8 queries): two 104 KB tiles leave ~20 KB of L1,
-    // too little for the loads in flight (LG-throttle stalls in ncu); gather: two (0.43 vs 0.49 ms)
-    kern<<<(unsigned)std::min<size_t>(ntiles, (size_t)sms * env_int("SST_BK_MOVE_CTAS", GATHER ? 2 : 1)), kThreads, smem, st>>>(s.counts, s.offs, s.lpos, nbp, bpt, ntiles, nq, aligned, src, dst);
+    // Two 104 KB tiles per SM leave ~20 KB of L1, too little for the loads in flight (ncu: LG-throttle stalls): with 512
+    // threads the scatter is faster on ONE CTA per SM (0.32 vs 0.36 ms per 10^8 queries).  Default where the bucket count
+    // allows: one CTA of 1024 threads per SM (gather 0.32 vs 0.37 ms, scatter 0.31); SST_BK_MOVE_THREADS=512 for the old shape.
+    const int threads = (nbp % 1024 == 0 && env_int("SST_BK_MOVE_THREADS", 1024) == 1024) ? 1024 : kThreads;
+    const unsigned bpt = nbp / threads;
+    if (threads == 1024) {
+        auto kern = bk_move_kernel<GATHER, OutT, 1024>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<(unsigned)std::min<size_t>(ntiles, (size_t)sms), 1024, smem, st>>>(s.counts, s.offs, s.lpos, nbp, bpt, ntiles, nq, aligned, src, dst);
+    } else {
+        auto kern = bk_move_kernel<GATHER, OutT, kThreads>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<(unsigned)std::min<size_t>(ntiles, (size_t)sms * env_int("SST_BK_MOVE_CTAS", GATHER ? 2 : 1)), kThreads, smem, st>>>(
+            s.counts, s.offs, s.lpos, nbp, bpt, ntiles, nq, aligned, src, dst);
+    }
 }
 
 }  // namespace
@@ -922,7 +933,7 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
         bk_plan_kernel<<<1, 1024, 0, st>>>(s.tot, a.nbp, chunk, s.bstart, s.items, s.ctrl);
         bk_offsets_kernel<<<mgrid, 256, 0, st>>>(s.counts, s.gsum, s.bstart, ntiles, a.nbp, s.offs);
         mark();
-        launch_move<false, uint32_t>(sms, smem_move, st, s, a.nbp, bpt, ntiles, cnt, qs, s.qb);
+        launch_move<false, uint32_t>(sms, smem_move, st, s, a.nbp, ntiles, cnt, qs, s.qb);
         mark();
         {
             void (*kern)(const BkSearchParams, const uint32_t*, const uint32_t*, const uint2*, unsigned*, uint32_t*, uint32_t*) =
@@ -931,8 +942,8 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
             kern<<<sms * search_ctas, search_threads, smem_search, st>>>(sp, s.qb, s.bstart, s.items, s.ctrl, s.rb, s.ib);
         }
         mark();
-        launch_move<true, uint32_t>(sms, smem_move, st, s, a.nbp, bpt, ntiles, cnt, s.rb, d_vals + off);
-        if (d_idx) launch_move<true, unsigned long long>(sms, smem_move, st, s, a.nbp, bpt, ntiles, cnt, s.ib, d_idx + off);
+        launch_move<true, uint32_t>(sms, smem_move, st, s, a.nbp, ntiles, cnt, s.rb, d_vals + off);
+        if (d_idx) launch_move<true, unsigned long long>(sms, smem_move, st, s, a.nbp, ntiles, cnt, s.ib, d_idx + off);
         mark();
         if (timing && nev == 6 && cudaEventSynchronize(ev[5]) == cudaSuccess) {
             float t[5];
