@@ -157,7 +157,7 @@ __device__ __forceinline__ void ballot_bits(unsigned& peers, unsigned b) {
 }
 
 // FULL: every tile in [tile_begin, tile_end) holds kTile queries (the partial last tile gets its own launch).
-template <int BITS, bool FULL, bool HYBRID>
+template <int BITS, bool FULL, int HYBRID>
 __device__ __forceinline__ void rank_tile(const BkView& v, const uint32_t* __restrict__ qs, size_t nq, unsigned tile, uint32_t* __restrict__ counts,
                                           uint16_t* __restrict__ lpos16, uint16_t* cnt, const uint16_t* s_bt, const uint32_t* s_split,
                                           unsigned* s_warp) {
@@ -187,7 +187,7 @@ __device__ __forceinline__ void rank_tile(const BkView& v, const uint32_t* __res
         for (int r = 0; r < kItems; r++) {
             const bool valid = FULL || pk[r] != 0xffffffffu;
             const unsigned b = valid ? pk[r] : 0u;
-            // Two ways to rank, used on alternating steps so that the work is split between the ALU pipe (ballots) and
+            // Two ways to rank, mixed step by step so that the work is split between the ALU pipe (ballots) and
             // the shared-memory pipe (claims) -- each alone is bound by its pipe (0.61 / 0.55 ms per 10^8 queries):
             //  claim:   every lane writes count + 1 tagged with its lane id (5 tag bits above the 11 count bits); the lane
             //           whose tag sticks takes rank = count; if any lane lost (two queries of one bucket in the same step,
@@ -195,7 +195,8 @@ __device__ __forceinline__ void rank_tile(const BkView& v, const uint32_t* __res
             //           when every query hits the same bucket
             //  ballots: lanes with the same bucket find each other by ballots over the bucket bits; the lowest of them
             //           bumps the counter by the group size
-            const bool claim_step = HYBRID && (r & 1);
+            // HYBRID = 0: ballots only; k > 0: claim on every step with r % k != 0 (2: every other step); k < 0: claim on r % -k == 0
+            const bool claim_step = HYBRID > 0 ? (r % (HYBRID > 0 ? HYBRID : 1)) != 0 : HYBRID < 0 ? (r % (HYBRID < 0 ? -HYBRID : 1)) == 0 : false;
             if (claim_step) {
                 const unsigned w = valid ? cntw[b] : 0u;
                 __syncwarp();
@@ -303,7 +304,7 @@ __device__ __forceinline__ void rank_tile(const BkView& v, const uint32_t* __res
     }
 }
 
-template <int BITS, bool HYBRID>
+template <int BITS, int HYBRID>
 __global__ void __launch_bounds__(kThreads, 2)
 bk_rank_kernel(const BkView v, const uint32_t* __restrict__ qs, size_t nq, unsigned ntiles, uint32_t* __restrict__ counts,
                uint16_t* __restrict__ lpos16, uint32_t* __restrict__ tot) {
@@ -795,15 +796,18 @@ template <int BITS>
 void launch_rank(const BkView& v, int sms, size_t smem, cudaStream_t st, const uint32_t* qs, size_t nq, unsigned ntiles, uint32_t* counts,
                  uint16_t* lpos, uint32_t* tot) {
     const unsigned grid = (unsigned)std::min<size_t>(ntiles, (size_t)sms * 2);
-    if (BITS > 0 && env_int("SST_BK_HYBRID", 1)) {
-        auto kern = bk_rank_kernel<BITS, true>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<grid, kThreads, smem, st>>>(v, qs, nq, ntiles, counts, lpos, tot);
-    } else {
-        auto kern = bk_rank_kernel<BITS, false>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<grid, kThreads, smem, st>>>(v, qs, nq, ntiles, counts, lpos, tot);
+    const int hyb = BITS > 0 ? env_int("SST_BK_HYBRID", 1) : 0;
+#define SST_BK_LAUNCH_RANK(H)                                                                       \
+    {                                                                                               \
+        auto kern = bk_rank_kernel<BITS, H>;                                                        \
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+        kern<<<grid, kThreads, smem, st>>>(v, qs, nq, ntiles, counts, lpos, tot);                   \
     }
+    // claim : ballot ratio measured at 10 bits (rank stage, ms per 10^8 queries): ballots only 0.494, 1:2 0.472, 1:1 0.452,
+    // 2:1 0.446, 3:1 0.442 -> three claim steps per ballot step
+    if (hyb != 0) SST_BK_LAUNCH_RANK(4)
+    else SST_BK_LAUNCH_RANK(0)
+#undef SST_BK_LAUNCH_RANK
 }
 
 template <bool GATHER, typename OutT>
