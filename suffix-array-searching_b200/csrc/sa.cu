@@ -47,6 +47,9 @@ namespace sst {
 namespace {
 
 constexpr int kThreads = 256;
+#ifndef SST_SA_MIN_BLOCKS
+#define SST_SA_MIN_BLOCKS 5
+#endif
 
 inline unsigned grid_for(size_t work) { return (unsigned)std::min<size_t>(div_ceil(work, (size_t)kThreads), 148 * 32); }
 
@@ -381,7 +384,7 @@ __device__ __forceinline__ uint32_t thread_compare(const SaParams& p, unsigned l
 // order of `perm`, i.e. sorted by that key: the lanes of a warp then walk (almost) the same path, so their table and
 // suffix-array loads fall into the same lines instead of 32 different ones.
 template <bool MLR, int PHASE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, SST_SA_MIN_BLOCKS)
 sa_search_thread_kernel(const __grid_constant__ SaParams p) {
     for (unsigned long long slot = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; slot < p.npat;
          slot += (unsigned long long)gridDim.x * blockDim.x) {
@@ -684,9 +687,9 @@ static int sa_search_launch(const sst_sa_t* s, const uint8_t* d_pats, const uint
         const unsigned grid = (unsigned)std::min<unsigned long long>((npat + kThreads - 1) / kThreads, (unsigned long long)sm_count(s->device) * 8);
         // Opt-in (SST_SA_SORT_MIN=<patterns>): search in sorted order (see PHASE above): coarse pass over the cache-resident
         // top of the table, radix sort of (lower bound so far, index) on the bits the coarse pass has decided, main pass
-        // through perm.  Measured: C3 3.45 vs 3.23 Gpat/s, C5 2.12 vs 2.03 Gpat/s at 12 coarse levels, slower from 18 levels
-        // up -- the DRAM fills are the text/SA probes of the last levels and of `hi` (777 B per pattern with or without the
-        // sort, ncu), not the table, so reordering buys little; it stays off by default.
+        // through perm.  Measured: C3 3.28 vs 4.61 Gpat/s (a loss), C5 2.12 vs 2.03 Gpat/s at 12 coarse levels, worse with
+        // more levels -- the DRAM fills are the text/SA probes of the last levels and of `hi` (777 B per pattern with or
+        // without the sort, ncu), not the table, so reordering cannot pay for its two extra passes; off by default.
         const int coarse = std::min(p.pivot_levels, 3 * (env_int("SST_SA_SORT_LEVELS", 12) / 3));
         const char* smin = getenv("SST_SA_SORT_MIN");
         const unsigned long long sort_min = smin && *smin ? strtoull(smin, nullptr, 10) : ~0ull;
