@@ -294,6 +294,9 @@ def run_own(args):
         st_ms = (C.c_double * 5)()
         if L.sst_last_stage_ms(st_ms, 5) == 5:
             roofline["stage_ms"] = dict(zip(["rank", "plan", "scatter", "search", "gather"], [round(float(x), 4) for x in st_ms]))
+            tot_st = sum(float(x) for x in st_ms)
+            # the dominant kernel of the step and its share (to be compared with the ncu launch list in profiles/)
+            roofline["dominant_kernel"] = {"name": "bk_search_kernel", "ms": round(float(st_ms[3]), 4), "share_of_step": round(float(st_ms[3]) / tot_st, 3)}
     tf = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tf) and n == (1 << 28) and (e - s) == 100_000_000:  # the capture is of exactly this step shape
         try:
