@@ -757,17 +757,20 @@ int launch_fast_top(const sst_index* idx, bool top, const uint32_t* d_qs, size_t
 
 // The kernel AUTO picks for this index and batch size.  Measured on B200 (tools/batch_sweep.py, tools/bucketed_once.py):
 // the thread-per-query kernel has the shortest latency (6-10 us up to 2^16 queries), the rank-table kernel wins from 2^17
-// queries, and from 2^24 queries over >= 2^25 keys the reordered-batch pipeline does (59.7 vs 52.8 Gq/s at 2^25 keys,
-// 50 vs 34 Gq/s at 2^28 keys for 10^8 queries); the table-less group kernel never wins.
+// queries, and for large batches over >= 2^25 keys the reordered-batch pipeline does (59.7 vs 52.8 Gq/s at 2^25 keys,
+// 55 vs 34 Gq/s at 2^28 keys for 10^8 queries); the table-less group kernel never wins.
 int resolve_scheme(const sst_index* idx, int scheme, size_t nq) {
     if (scheme != SST_SCHEME_AUTO) return scheme;
     if (idx->variant == SST_EYTZINGER) return SST_SCHEME_GENERIC;
     if (idx->variant != SST_PLAIN && idx->node_b == 16 && env_int("SST_PGROUP", 1)) return SST_SCHEME_AUTO;  // lane-group kernel
     if (!fast_eligible(idx)) return SST_SCHEME_GENERIC;
     if (nq < (size_t)env_int("SST_TABLE_MIN_NQ", 1 << 17)) return env_int("SST_SCHEME", SST_SCHEME_GENERIC);
-    if (bucketed_eligible(idx) && idx->n >= (size_t)env_int("SST_BK_AUTO_MIN_N", 1 << 25) &&
-        nq >= (size_t)env_int("SST_BK_AUTO_MIN_NQ", 1 << 24))
-        return env_int("SST_SCHEME", SST_SCHEME_BUCKETED);
+    if (bucketed_eligible(idx) && idx->n >= (size_t)env_int("SST_BK_AUTO_MIN_N", 1 << 25)) {
+        // measured crossovers (tools/bucketed_once.py): 2^28 keys ~1.2x10^7 queries, 2^26 keys ~4x10^7, 2^25 keys ~6x10^7;
+        // at 2^24 keys and below the tree is L2-resident and the direct kernel always wins (65.7 vs 45.5 Gq/s)
+        const size_t min_nq = idx->n >= ((size_t)1 << 27) ? (size_t)1 << 24 : idx->n >= ((size_t)1 << 26) ? (size_t)3 << 24 : (size_t)1 << 26;
+        if (nq >= (size_t)env_int("SST_BK_AUTO_MIN_NQ", (int)min_nq)) return env_int("SST_SCHEME", SST_SCHEME_BUCKETED);
+    }
     return env_int("SST_SCHEME", top_eligible(idx) ? SST_SCHEME_TABLE : SST_SCHEME_GROUP2);
 }
 

@@ -37,7 +37,7 @@ def test_bench_line_contract(gpu):
 def test_bench_line_bucketed(gpu):
     """A configuration large enough for SCHEME_AUTO to take the reordered-batch pipeline: 7 launches per step, stage times."""
     out = subprocess.run(
-        [sys.executable, os.path.join(ROOT, "bench.py"), "--n-keys", str(1 << 25), "--queries", str(1 << 24), "--steps", "2", "--warmup", "3",
+        [sys.executable, os.path.join(ROOT, "bench.py"), "--n-keys", str(1 << 27), "--queries", str(1 << 24), "--steps", "2", "--warmup", "3",
          "--no-cpu", "--sa-text", "0", "--e2e-steps", "1"],
         capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-3000:]

@@ -144,8 +144,8 @@ def test_bucketed_unaligned_device_buffers(gpu, oracle, monkeypatch):
 
 
 def test_auto_picks_the_pipeline_for_large_batches(gpu, oracle):
-    """SCHEME_AUTO: reordered-batch pipeline from 2^24 queries over >= 2^25 keys, the rank-table kernel below; sst_query_plan
-    reports the choice and the launch count."""
+    """SCHEME_AUTO: reordered-batch pipeline for large batches over >= 2^25 keys (from 2^26 queries at 2^25 keys, from 2^24 at
+    2^27 keys and up), the rank-table kernel below; sst_query_plan reports the choice and the launch count."""
     import ctypes as C
 
     import torch
@@ -159,12 +159,14 @@ def test_auto_picks_the_pipeline_for_large_batches(gpu, oracle):
     t = sst.STree16.new_params(keys, True, False, False)
     sch, launches = C.c_int(0), C.c_int(0)
     L = sst.lib()
-    assert L.sst_query_plan(t._h, 1 << 24, 0, 0, C.byref(sch), C.byref(launches)) == 0
+    assert L.sst_query_plan(t._h, 1 << 26, 0, 0, C.byref(sch), C.byref(launches)) == 0
     assert sch.value == sst.SCHEME_BUCKETED and launches.value == 7
-    assert L.sst_query_plan(t._h, 1 << 24, 0, 1, C.byref(sch), C.byref(launches)) == 0 and launches.value == 8
+    assert L.sst_query_plan(t._h, 1 << 26, 0, 1, C.byref(sch), C.byref(launches)) == 0 and launches.value == 8
+    assert L.sst_query_plan(t._h, (1 << 28) + 1, 0, 0, C.byref(sch), C.byref(launches)) == 0 and launches.value == 21  # three sub-batches
+    assert L.sst_query_plan(t._h, 1 << 24, 0, 0, C.byref(sch), C.byref(launches)) == 0 and sch.value == sst.SCHEME_TABLE
     assert L.sst_query_plan(t._h, 1 << 20, 0, 0, C.byref(sch), C.byref(launches)) == 0
     assert sch.value == sst.SCHEME_TABLE and launches.value == 1
-    qs = torch.randint(0, MAX, ((1 << 24) + 5,), dtype=torch.int32, device="cuda", generator=g)
+    qs = torch.randint(0, MAX, ((1 << 26) + 5,), dtype=torch.int32, device="cuda", generator=g)
     v, i = t.query(qs, sst.SCHEME_AUTO, want_index=True)
     v2, i2 = t.query(qs, sst.SCHEME_TABLE, want_index=True)
     assert bool((v == v2).all()) and bool((i == i2).all())
