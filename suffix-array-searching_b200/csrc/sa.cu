@@ -41,6 +41,12 @@ struct sst_sa {
     // [0, n) holds the first 16 bytes (zero padded) of suffix(sa[m_j]).  GPU-only auxiliary.
     uint4* d_pivots = nullptr;
     int pivot_levels = 0;
+    // k-mer table (texts over {0,1,2,3} only): kmer[x] = lower bound in the suffix array of the k-base string with 2-bit
+    // code x, x in [0, 4^k]; the search of a pattern starts in [kmer[x], kmer[x+1]) instead of [0, n).  The reference has
+    // the same idea as SaNaive's prefix `table` (sa_search.rs:59-85, hard-wired to p = 0 there) and packs bases with
+    // string_value (util.rs:76-117).  GPU-only auxiliary.
+    uint32_t* d_kmer = nullptr;
+    int kmer_k = 0;
 };
 
 namespace sst {
@@ -198,6 +204,8 @@ struct SaParams {
     uint32_t* keys;
     uint32_t* ident;
     int coarse_levels;
+    const uint32_t* kmer;  // k-mer table (or null)
+    int kmer_k;
 };
 
 // Compares suffix(spos) with the pattern from byte `start` on.  Returns lcp (group-uniform) and
@@ -397,8 +405,35 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
         uint32_t l = 0, r = (uint32_t)p.n;  // n < 2^32 - 16: all search state fits 32 bits
         uint32_t lcp_l = 0, lcp_r = 0;
         bool lcp_r_exact = false;  // lcp_r == lcp(q, suffix(r)) exactly (not a conservative bound)
+        // ---- k-mer table: the first k bases select the suffix-array range directly (one load instead of ~2k probes) ----
+        bool have_range = false;
+        if (PHASE != 1 && p.kmer_k) {
+            const int k = p.kmer_k;  // <= 15: the bases sit in p0
+            uint32_t x = 0;
+            bool dna = true;
+#pragma unroll
+            for (int j = 0; j < 15; j++)
+                if (j < k) {
+                    const uint32_t b = (p0.w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                    const bool in = (uint32_t)j < ql;
+                    dna = dna && (!in || b < 4u);
+                    x = x * 4u + (in ? (b & 3u) : 0u);  // a pattern shorter than k is padded with the smallest base
+                }
+            if (dna) {
+                have_range = true;
+                if (ql >= (uint32_t)k) {
+                    l = __ldg(p.kmer + x);
+                    r = __ldg(p.kmer + x + 1);
+                } else {
+                    // every suffix from kmer[x] on is >= q000.. >= q; the only suffixes below it that are >= q are proper
+                    // prefixes of q000.. (the last < k suffixes of the text): search the k positions before it
+                    r = __ldg(p.kmer + x);
+                    l = r > (uint32_t)k ? r - (uint32_t)k : 0u;
+                }
+            }
+        }
         // ---- table levels: one 16-byte load per probe ----
-        {
+        if (!have_range) {
             const uint32_t c = ql < 16u ? ql : 16u;
             // Incremental form of pivot_entry(j, d): the block of triple t rooted at heap node `root`
             // is number root + off_t with off_0 = -1, off_{t+1} = 8 * off_t + 1 (<= 30 levels: 32-bit).
@@ -540,6 +575,8 @@ void launch_search(const SaParams& p, int mode, cudaStream_t st, int device) {
 
 using namespace sst;
 
+static bool build_kmer(sst_sa* s);  // defined after sa_search_launch, which it uses to fill the table
+
 extern "C" {
 
 sst_sa_t* sst_sa_build_device(const uint8_t* d_text, size_t n, int device) {
@@ -556,8 +593,8 @@ sst_sa_t* sst_sa_build_device(const uint8_t* d_text, size_t n, int device) {
     cudaStream_t st = thread_stream(device);
     ok = ok && SST_CUDA_OK(cudaMemsetAsync(s->d_text + n, 0, 64, st)) &&
          SST_CUDA_OK(cudaMemcpyAsync(s->d_text, d_text, n, cudaMemcpyDeviceToDevice, st));
-    ok = ok && build_sa_device(s->d_text, n, s->d_sa, device) && build_pivots(s);
-    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); delete s; return nullptr; }
+    ok = ok && build_sa_device(s->d_text, n, s->d_sa, device) && build_pivots(s) && build_kmer(s);
+    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); delete s; return nullptr; }
     return s;
 }
 
@@ -590,8 +627,8 @@ sst_sa_t* sst_sa_from_parts(const uint8_t* text, size_t n, const uint32_t* sa, i
     bool ok = SST_CUDA_OK(cudaMalloc(&s->d_text, n + 64)) && SST_CUDA_OK(cudaMalloc(&s->d_sa, n * 4)) &&
               SST_CUDA_OK(cudaMemsetAsync(s->d_text + n, 0, 64, st)) && SST_CUDA_OK(cudaMemcpyAsync(s->d_text, text, n, cudaMemcpyHostToDevice, st)) &&
               SST_CUDA_OK(cudaMemcpyAsync(s->d_sa, sa, n * 4, cudaMemcpyHostToDevice, st)) && SST_CUDA_OK(cudaStreamSynchronize(st));
-    ok = ok && build_pivots(s);
-    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); delete s; return nullptr; }
+    ok = ok && build_pivots(s) && build_kmer(s);
+    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); delete s; return nullptr; }
     return s;
 }
 
@@ -601,6 +638,7 @@ void sst_sa_free(sst_sa_t* s) {
     cudaFree(s->d_text);
     cudaFree(s->d_sa);
     cudaFree(s->d_pivots);
+    cudaFree(s->d_kmer);
     delete s;
 }
 
@@ -682,6 +720,8 @@ static int sa_search_launch(const sst_sa_t* s, const uint8_t* d_pats, const uint
     p.pats_bytes = pats_end;  // end offset of the packed patterns (bounds the aligned 16-byte loads)
     p.pivots = s->d_pivots;
     p.pivot_levels = s->d_pivots ? std::min(s->pivot_levels, env_int("SST_SA_USE_LEVELS", 64)) : 0;
+    p.kmer = s->d_kmer;
+    p.kmer_k = s->d_kmer && env_int("SST_SA_USE_KMER", 1) ? s->kmer_k : 0;
     const int lanes = env_int("SST_SA_LANES", 1);
     if (lanes <= 1) {
         const unsigned grid = (unsigned)std::min<unsigned long long>((npat + kThreads - 1) / kThreads, (unsigned long long)sm_count(s->device) * 8);
@@ -725,6 +765,70 @@ static int sa_search_launch(const sst_sa_t* s, const uint8_t* d_pats, const uint
     }
     return SST_CUDA_OK(cudaGetLastError()) ? SST_OK : SST_ERR_CUDA;
 }
+
+}  // extern "C"
+
+// ---- k-mer table builder: kmer[x] = lower bound of the k-base string x, computed by the search kernel itself ----
+namespace sst {
+namespace {
+__global__ void kmer_max_byte_kernel(const uint8_t* __restrict__ t, size_t n, unsigned* __restrict__ out) {
+    unsigned m = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = max(m, (unsigned)t[i]);
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31u) == 0 && m) atomicMax(out, m);
+}
+// patterns x0 .. x0+count-1 as k bytes each (most significant base first), offsets relative to the chunk
+__global__ void kmer_patterns_kernel(unsigned long long x0, unsigned count, int k, uint8_t* __restrict__ pats, unsigned long long* __restrict__ off) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i <= count; i += gridDim.x * blockDim.x) {
+        off[i] = (unsigned long long)i * k;
+        if (i < count) {
+            const unsigned long long x = x0 + i;
+            for (int j = 0; j < k; j++) pats[(size_t)i * k + j] = (uint8_t)((x >> (2 * (k - 1 - j))) & 3ull);
+        }
+    }
+}
+}  // namespace
+}  // namespace sst
+
+static bool build_kmer(sst_sa* s) {
+    if (!env_int("SST_SA_KMER", 1) || s->n < 4096) return true;
+    cudaStream_t st = thread_stream(s->device);
+    unsigned* d_max = nullptr;
+    unsigned h_max = 0;
+    if (!SST_CUDA_OK(cudaMalloc(&d_max, 4)) || !SST_CUDA_OK(cudaMemsetAsync(d_max, 0, 4, st))) { cudaFree(d_max); return false; }
+    kmer_max_byte_kernel<<<sm_count(s->device) * 8, 256, 0, st>>>(s->d_text, s->n, d_max);
+    const bool ok0 = SST_CUDA_OK(cudaMemcpyAsync(&h_max, d_max, 4, cudaMemcpyDeviceToHost, st)) && SST_CUDA_OK(cudaStreamSynchronize(st));
+    cudaFree(d_max);
+    if (!ok0) return false;
+    if (h_max > 3) return true;  // not a 2-bit alphabet: the pivot-prefix table serves every level
+    int k = 1;
+    while (k < 15 && (1ull << (2 * (k + 1))) <= s->n) k++;  // 4^k <= n: about one suffix per table cell
+    k = std::min(k, env_int("SST_SA_KMER_K", 15));
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    while (k > 4 && ((1ull << (2 * k)) + 1) * 4ull > free_b / 4) k--;
+    if (k < 4) return true;
+    const unsigned long long cells = 1ull << (2 * k);
+    const unsigned chunk = 1u << 22;
+    uint8_t* d_p = nullptr;
+    unsigned long long* d_o = nullptr;
+    bool ok = SST_CUDA_OK(cudaMalloc(&s->d_kmer, (cells + 1) * 4)) && SST_CUDA_OK(cudaMalloc(&d_p, (size_t)chunk * k + 64)) &&
+              SST_CUDA_OK(cudaMalloc(&d_o, ((size_t)chunk + 1) * 8));
+    for (unsigned long long x0 = 0; ok && x0 < cells; x0 += chunk) {
+        const unsigned cnt = (unsigned)std::min<unsigned long long>(chunk, cells - x0);
+        kmer_patterns_kernel<<<sm_count(s->device) * 8, 256, 0, st>>>(x0, cnt, k, d_p, d_o);
+        ok = sa_search_launch(s, d_p, (const uint64_t*)d_o, (unsigned long long)cnt * k, cnt, SST_SA_BINARY, s->d_kmer + x0, nullptr, nullptr, st) == SST_OK;
+    }
+    const uint32_t n32 = (uint32_t)s->n;
+    ok = ok && SST_CUDA_OK(cudaMemcpyAsync(s->d_kmer + cells, &n32, 4, cudaMemcpyHostToDevice, st)) && SST_CUDA_OK(cudaStreamSynchronize(st));
+    cudaFree(d_p);
+    cudaFree(d_o);
+    if (!ok) { cudaFree(s->d_kmer); s->d_kmer = nullptr; return false; }
+    s->kmer_k = k;  // set last: the searches above ran without the table
+    return true;
+}
+
+extern "C" {
 
 int sst_sa_search_device(const sst_sa_t* s, const uint8_t* d_pats, const uint64_t* d_pat_off, size_t npat, int mode,
                          uint32_t* d_out_lo, uint32_t* d_out_hi, uint32_t* d_out_pos, void* stream) {

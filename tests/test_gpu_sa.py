@@ -57,6 +57,7 @@ def test_sa_search_parity(gpu, oracle, lanes, pivot_levels, monkeypatch):
     sst = gpu
     monkeypatch.setenv("SST_SA_LANES", lanes)
     monkeypatch.setenv("SST_SA_PIVOT_LEVELS", pivot_levels)
+    monkeypatch.setenv("SST_SA_KMER", "0")  # the pivot-prefix table serves every level (as for texts over a byte alphabet)
     text = random_text(200_000, seed=11)
     s = sst.SaNaive.build(text)
     sa = s.sa
@@ -75,6 +76,7 @@ def test_sa_search_repetitive_text(gpu, oracle, pivot_levels, monkeypatch):
     """Long LCPs: all-equal text and tandem repeats (many occurrences -> hi - lo large)."""
     sst = gpu
     monkeypatch.setenv("SST_SA_PIVOT_LEVELS", pivot_levels)
+    monkeypatch.setenv("SST_SA_KMER", "0" if pivot_levels == "20" else "1")  # once through the pivot table, once through the k-mer table
     for text in (np.zeros(5000, np.uint8), np.tile(random_text(13, seed=5), 700)):
         s = sst.SaNaive.build(text)
         sa = s.sa
@@ -137,6 +139,7 @@ def test_sa_search_sorted_order(gpu, oracle, levels, monkeypatch):
     sst = gpu
     monkeypatch.setenv("SST_SA_SORT_MIN", "1")
     monkeypatch.setenv("SST_SA_SORT_LEVELS", levels)
+    monkeypatch.setenv("SST_SA_KMER", "0")
     text = random_text(300_000, seed=21)
     sa = oracle.sa_build(text)
     s = sst.SaNaive.from_parts(text, sa)
@@ -146,3 +149,27 @@ def test_sa_search_sorted_order(gpu, oracle, levels, monkeypatch):
     pats += pats[:700]  # duplicates
     pats += [bytes([3] * 40), bytes([0]), bytes([3]), text[-5:].tobytes(), text[:50].tobytes()]
     _check_search(sst, oracle, s, text, sa, pats)
+
+
+@pytest.mark.parametrize("n,k", [(200_000, "15"), (200_000, "4"), (5000, "15"), (70_000, "7")])
+def test_sa_search_kmer_table(gpu, oracle, n, k, monkeypatch):
+    """Texts over {0,1,2,3} get a k-mer table (kmer[x] = lower bound of the k-base string x): the search starts in
+    [kmer[x], kmer[x+1]).  Patterns shorter than k, patterns with a byte outside the alphabet (fall back to the pivot table),
+    patterns made of the text's tail (proper prefixes of padded k-mers), absent patterns, the empty pattern."""
+    sst = gpu
+    monkeypatch.setenv("SST_SA_KMER_K", k)
+    text = random_text(n, seed=n + 5)
+    s = sst.SaNaive.build(text)
+    sa = s.sa
+    assert np.array_equal(sa, oracle.sa_build(text))
+    rng = np.random.default_rng(n)
+    tail = text.tobytes()
+    pats = random_patterns(text, 3000, seed=n + 6, lo=1, hi=100)
+    pats += [bytes(rng.integers(0, 4, int(l), dtype=np.uint8)) for l in rng.integers(1, 40, 1500)]      # mostly absent
+    pats += [tail[-j:] for j in range(1, 40)] + [tail[-j:] + b"\x00" * z for j in (1, 3, 9) for z in (1, 2, 7)]
+    pats += [b"", bytes([0]), bytes([3]), bytes([3] * 64), bytes([0] * 64), bytes([4]), bytes([1, 2, 200, 3]), bytes([255] * 3),
+             bytes([3] * 3) + bytes([4]), tail[:150], bytes([0, 1, 2, 3] * 4)]
+    _check_search(sst, oracle, s, text, sa, pats)
+    # the same through the pivot table only
+    monkeypatch.setenv("SST_SA_USE_KMER", "0")
+    _check_search(sst, oracle, s, text, sa, pats[:2000])
