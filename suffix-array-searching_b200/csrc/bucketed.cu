@@ -549,7 +549,7 @@ __device__ __forceinline__ void ldg256(const uint32_t* p, uint32_t (&k)[8]) {
 }
 
 // G = keys per separator: 8 (half node, one 32-byte sector per query) up to 2^29 keys, 16 (whole node, two sectors) above
-template <bool WANT_IDX, int G>
+template <bool WANT_IDX, int G, int PROBE>
 __global__ void __launch_bounds__(1024, 1)
 bk_search_kernel(const BkSearchParams p, const uint32_t* __restrict__ qb, const uint32_t* __restrict__ bstart,
                  const uint2* __restrict__ items, unsigned* __restrict__ ctrl, uint32_t* __restrict__ rb, uint32_t* __restrict__ ib) {
@@ -609,38 +609,73 @@ bk_search_kernel(const BkSearchParams p, const uint32_t* __restrict__ qb, const 
             }
             // rank among the bucket's separators: jump-table cell, then three unconditional probes (independent
             // shared loads for all U queries); a cell with more separators below q continues in a loop (rare)
-            unsigned l[U], h[U];
+            if constexpr (PROBE == 1) {
+                // Predicated probes: jump[x] separators are below q's cell, every separator of a later cell is above q and the
+                // bucket's last separator is >= q, so the scan needs no upper end.  A lane probes again only while its separator
+                // is below q (37 % / 10 % / 2 % of the lanes for uniform keys): idle lanes cost no shared-memory wavefronts.
+                unsigned l[U];
+                uint32_t s0[U];
 #pragma unroll
-            for (int u = 0; u < U; u++) {
-                const unsigned x = (q[u] - lo) >> sh;
-                l[u] = s_jump[x];
-                h[u] = s_jump[x + 1];
-            }
-            uint32_t s0[U], s1[U], s2[U];
+                for (int u = 0; u < U; u++) l[u] = s_jump[(q[u] - lo) >> sh];
 #pragma unroll
-            for (int u = 0; u < U; u++) {
-                s0[u] = s_sep[min(l[u], p.r - 1u)];
-                s1[u] = s_sep[min(l[u] + 1u, p.r - 1u)];
-                s2[u] = s_sep[min(l[u] + 2u, p.r - 1u)];
-            }
+                for (int u = 0; u < U; u++) s0[u] = s_sep[min(l[u], p.r - 1u)];
 #pragma unroll
-            for (int u = 0; u < U; u++) {
-                const bool c0 = l[u] < h[u] && s0[u] < q[u];
-                const bool c1 = c0 && l[u] + 1u < h[u] && s1[u] < q[u];
-                const bool c2 = c1 && l[u] + 2u < h[u] && s2[u] < q[u];
-                unsigned pos = l[u] + (c0 ? 1u : 0u) + (c1 ? 1u : 0u) + (c2 ? 1u : 0u);
-                if (c2) {
-                    unsigned hh = h[u];
-                    if (hh - pos > 8u) {
-                        while (pos < hh) {
-                            const unsigned m = (pos + hh) >> 1;
-                            if (s_sep[m] < q[u]) pos = m + 1; else hh = m;
+                for (int u = 0; u < U; u++) {
+                    unsigned pos = l[u];
+                    if (s0[u] < q[u]) {
+                        pos++;
+                        if (s_sep[min(pos, p.r - 1u)] < q[u]) {
+                            pos++;
+                            if (s_sep[min(pos, p.r - 1u)] < q[u]) {
+                                pos++;
+                                unsigned hh = s_jump[((q[u] - lo) >> sh) + 1u];
+                                if (hh > pos + 8u) {
+                                    while (pos < hh) {
+                                        const unsigned m = (pos + hh) >> 1;
+                                        if (s_sep[m] < q[u]) pos = m + 1; else hh = m;
+                                    }
+                                } else {
+                                    while (pos < hh && s_sep[pos] < q[u]) pos++;
+                                }
+                            }
                         }
-                    } else {
-                        while (pos < hh && s_sep[pos] < q[u]) pos++;
                     }
+                    a[u] = pos;
                 }
-                a[u] = pos;
+            } else {
+                unsigned l[U], h[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const unsigned x = (q[u] - lo) >> sh;
+                    l[u] = s_jump[x];
+                    h[u] = s_jump[x + 1];
+                }
+                uint32_t s0[U], s1[U], s2[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    s0[u] = s_sep[min(l[u], p.r - 1u)];
+                    s1[u] = s_sep[min(l[u] + 1u, p.r - 1u)];
+                    s2[u] = s_sep[min(l[u] + 2u, p.r - 1u)];
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const bool c0 = l[u] < h[u] && s0[u] < q[u];
+                    const bool c1 = c0 && l[u] + 1u < h[u] && s1[u] < q[u];
+                    const bool c2 = c1 && l[u] + 2u < h[u] && s2[u] < q[u];
+                    unsigned pos = l[u] + (c0 ? 1u : 0u) + (c1 ? 1u : 0u) + (c2 ? 1u : 0u);
+                    if (c2) {
+                        unsigned hh = h[u];
+                        if (hh - pos > 8u) {
+                            while (pos < hh) {
+                                const unsigned m = (pos + hh) >> 1;
+                                if (s_sep[m] < q[u]) pos = m + 1; else hh = m;
+                            }
+                        } else {
+                            while (pos < hh && s_sep[pos] < q[u]) pos++;
+                        }
+                    }
+                    a[u] = pos;
+                }
             }
             uint32_t ks[U][G];
             unsigned long long hn[U];
@@ -941,7 +976,9 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
         mark();
         {
             void (*kern)(const BkSearchParams, const uint32_t*, const uint32_t*, const uint2*, unsigned*, uint32_t*, uint32_t*) =
-                a.g == 16 ? (d_idx ? bk_search_kernel<true, 16> : bk_search_kernel<false, 16>) : (d_idx ? bk_search_kernel<true, 8> : bk_search_kernel<false, 8>);
+                env_int("SST_BK_PROBE", 1) == 1
+                    ? (a.g == 16 ? (d_idx ? bk_search_kernel<true, 16, 1> : bk_search_kernel<false, 16, 1>) : (d_idx ? bk_search_kernel<true, 8, 1> : bk_search_kernel<false, 8, 1>))
+                    : (a.g == 16 ? (d_idx ? bk_search_kernel<true, 16, 0> : bk_search_kernel<false, 16, 0>) : (d_idx ? bk_search_kernel<true, 8, 0> : bk_search_kernel<false, 8, 0>));
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_search);
             kern<<<sms * search_ctas, search_threads, smem_search, st>>>(sp, s.qb, s.bstart, s.items, s.ctrl, s.rb, s.ib);
         }

@@ -90,11 +90,12 @@ def c5(n=3_000_000_000, npat=100_000_000):
     hi = torch.empty(npat, dtype=torch.int32, device=dev)
     pos = torch.empty(npat, dtype=torch.int32, device=dev)
     ref_lo = None
-    variants = [("binary", sst.SA_BINARY, None), ("mlr", sst.SA_MLR, None)]
+    variants = [("binary", sst.SA_BINARY, None), ("mlr", sst.SA_MLR, None), ("binary_nokmer", sst.SA_BINARY, "nokmer")]
     for lv in [x for x in os.environ.get("C5_SORT_LEVELS", "").split(",") if x]:  # sorted-order search at these coarse depths
         variants.append((f"binary_sorted{lv}", sst.SA_BINARY, lv))
     for name, mode, sort_lv in variants:
-        if sort_lv is None:
+        os.environ["SST_SA_USE_KMER"] = "0" if sort_lv == "nokmer" else "1"  # pivot-prefix table only: the k-mer path must agree with it
+        if sort_lv is None or sort_lv == "nokmer":
             os.environ["SST_SA_SORT_MIN"] = str(1 << 62)
         else:
             os.environ["SST_SA_SORT_MIN"] = "1"
