@@ -126,6 +126,23 @@ __device__ __forceinline__ unsigned bk_bucket(const uint16_t* __restrict__ bt, c
     return lo + (split[lo + 1] < q ? 1u : 0u);
 }
 
+// The same in ONE shared load per query: pk[c] = next << 12 | flag << 11 | lo with lo = bt[c] & 0x7fff, flag = bit 15 of
+// bt[c] and next = the low 18 key bits of splitter lo + 1 when that splitter lies in cell c, else 0x3ffff (no key of the
+// cell is above it).  Flagged cells (two or more splitters with the same 13-bit prefix: skewed keys) take bk_bucket
+// through the global copies of the tables.
+__device__ __forceinline__ uint32_t bk_pack_cell(const uint16_t* __restrict__ bt, const uint32_t* __restrict__ split, unsigned nb, unsigned c) {
+    const unsigned e = bt[c], lo = e & 0x7fffu;
+    const uint32_t nx = lo + 1u <= nb ? split[lo + 1u] : kMax;
+    const uint32_t thr = (nx >> kBtShift) == c ? (nx & ((1u << kBtShift) - 1u)) : ((1u << kBtShift) - 1u);
+    return (thr << 12) | ((e & 0x8000u) ? 0x800u : 0u) | lo;
+}
+__device__ __forceinline__ unsigned bk_bucket_packed(const uint32_t* __restrict__ s_pk, const uint16_t* __restrict__ g_bt,
+                                                     const uint32_t* __restrict__ g_split, uint32_t q) {
+    const uint32_t e = s_pk[q >> kBtShift];
+    if (e & 0x800u) return bk_bucket(g_bt, g_split, q);
+    return (e & 0x7ffu) + ((q & ((1u << kBtShift) - 1u)) > (e >> 12) ? 1u : 0u);
+}
+
 struct BkView {
     const uint16_t* bt;
     const uint32_t* split;
@@ -159,8 +176,7 @@ __device__ __forceinline__ void ballot_bits(unsigned& peers, unsigned b) {
 // FULL: every tile in [tile_begin, tile_end) holds kTile queries (the partial last tile gets its own launch).
 template <int BITS, bool FULL, int HYBRID>
 __device__ __forceinline__ void rank_tile(const BkView& v, const uint32_t* __restrict__ qs, size_t nq, unsigned tile, uint32_t* __restrict__ counts,
-                                          uint16_t* __restrict__ lpos16, uint16_t* cnt, const uint16_t* s_bt, const uint32_t* s_split,
-                                          unsigned* s_warp) {
+                                          uint16_t* __restrict__ lpos16, uint16_t* cnt, const uint32_t* s_pk, unsigned* s_warp) {
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     uint16_t* cntw = cnt + (size_t)warp * v.nbp;
@@ -180,7 +196,7 @@ __device__ __forceinline__ void rank_tile(const BkView& v, const uint32_t* __res
         for (int r = 0; r < kItems; r++) pk[r] = (FULL || i0 + r * 32 < tile_n) ? __ldcs(tq + r * 32) : 0u;
 #pragma unroll
         for (int r = 0; r < kItems; r++)
-            pk[r] = (FULL || i0 + r * 32 < tile_n) ? bk_bucket(s_bt, s_split, canonical(pk[r])) : 0xffffffffu;
+            pk[r] = (FULL || i0 + r * 32 < tile_n) ? bk_bucket_packed(s_pk, v.bt, v.split, canonical(pk[r])) : 0xffffffffu;
         // rank inside the warp's 1024 queries: lanes with the same bucket find each other by ballots over
         // the bucket bits; the lowest of them bumps the warp's private counter
 #pragma unroll
@@ -312,15 +328,13 @@ bk_rank_kernel(const BkView v, const uint32_t* __restrict__ qs, size_t nq, unsig
     if (blockIdx.x == 0)  // bucket totals accumulated by bk_colsum_kernel, which runs after this kernel
         for (unsigned i = threadIdx.x; i < v.nbp; i += kThreads) tot[i] = 0;
     uint16_t* cnt = reinterpret_cast<uint16_t*>(smem_raw);                       // [kWarps][nbp]
-    uint16_t* s_bt = cnt + (size_t)kWarps * v.nbp;                                // [kBtStride]
-    uint32_t* s_split = reinterpret_cast<uint32_t*>(s_bt + kBtStride);            // [nbp + 1]
+    uint32_t* s_pk = reinterpret_cast<uint32_t*>(cnt + (size_t)kWarps * v.nbp);  // [kBtCells] packed bucket table
     __shared__ unsigned s_warp[kWarps + 1];
     const unsigned tid = threadIdx.x;
-    for (unsigned i = tid; i < (unsigned)kBtStride; i += kThreads) s_bt[i] = i <= (unsigned)kBtCells ? v.bt[i] : 0;
-    for (unsigned i = tid; i <= v.nbp; i += kThreads) s_split[i] = i <= v.nb ? v.split[i] : kMax;
+    for (unsigned i = tid; i < (unsigned)kBtCells; i += kThreads) s_pk[i] = bk_pack_cell(v.bt, v.split, v.nb, i);
     for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        if ((size_t)(tile + 1) * kTile <= nq) rank_tile<BITS, true, HYBRID>(v, qs, nq, tile, counts, lpos16, cnt, s_bt, s_split, s_warp);
-        else rank_tile<BITS, false, HYBRID>(v, qs, nq, tile, counts, lpos16, cnt, s_bt, s_split, s_warp);  // partial last tile
+        if ((size_t)(tile + 1) * kTile <= nq) rank_tile<BITS, true, HYBRID>(v, qs, nq, tile, counts, lpos16, cnt, s_pk, s_warp);
+        else rank_tile<BITS, false, HYBRID>(v, qs, nq, tile, counts, lpos16, cnt, s_pk, s_warp);  // partial last tile
     }
 }
 
@@ -934,7 +948,7 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
     const int sms = sm_count(dev);
     const unsigned bpt = a.nbp / kThreads;
     BkView v{a.d_bt, a.d_split, a.nb, a.nbp, bpt};
-    const size_t smem_rank = (size_t)kWarps * a.nbp * 2 + (size_t)kBtStride * 2 + ((size_t)a.nbp + 1) * 4 + 16;
+    const size_t smem_rank = (size_t)kWarps * a.nbp * 2 + (size_t)kBtCells * 4;
     const size_t smem_move = (size_t)kTile * 4 + (size_t)a.nbp * 4 + (size_t)kTile * 2;
     const size_t smem_search = (size_t)a.r * 4 + ((size_t)a.r + 8) * 2;
     // two CTAs of 512 threads per SM while two buckets fit shared memory, else one CTA of 1024 threads

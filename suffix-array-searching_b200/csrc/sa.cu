@@ -273,7 +273,7 @@ sa_search_kernel(const __grid_constant__ SaParams p) {
             unsigned long long a = lo, b = p.n, step = 1;  // invariant: all of [lo, a) start with q
             while (true) {
                 const unsigned long long pr = a + step - 1;
-                if (pr >= p.n) break;
+                if (pr >= b) break;
                 bool less;
                 const uint32_t lcp = group_compare<PL>(p, __ldg(p.sa + pr), p.pats, po, ql, 0u, sub, gbase, gmask, less);
                 if (lcp >= ql) { a = pr + 1; step <<= 1; } else { b = pr; break; }
@@ -407,12 +407,13 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
         bool lcp_r_exact = false;  // lcp_r == lcp(q, suffix(r)) exactly (not a conservative bound)
         // ---- k-mer table: the first k bases select the suffix-array range directly (one load instead of ~2k probes) ----
         bool have_range = false;
+        uint32_t range_end = (uint32_t)p.n;  // no suffix from here on starts with q (bounds the search for hi)
         if (PHASE != 1 && p.kmer_k) {
-            const int k = p.kmer_k;  // <= 15: the bases sit in p0
+            const int k = p.kmer_k;  // <= 16: the bases sit in p0
             uint32_t x = 0;
             bool dna = true;
 #pragma unroll
-            for (int j = 0; j < 15; j++)
+            for (int j = 0; j < 16; j++)
                 if (j < k) {
                     const uint32_t b = (p0.w[j >> 2] >> (8 * (j & 3))) & 0xffu;
                     const bool in = (uint32_t)j < ql;
@@ -423,7 +424,8 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
                 have_range = true;
                 if (ql >= (uint32_t)k) {
                     l = __ldg(p.kmer + x);
-                    r = __ldg(p.kmer + x + 1);
+                    r = __ldg(p.kmer + (size_t)x + 1);
+                    range_end = r;  // every suffix that starts with q starts with its first k bases
                 } else {
                     // every suffix from kmer[x] on is >= q000.. >= q; the only suffixes below it that are >= q are proper
                     // prefixes of q000.. (the last < k suffixes of the text): search the k positions before it
@@ -482,7 +484,7 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
         if (p.out_pos) p.out_pos[i] = lo < p.n ? __ldg(p.sa + lo) : 0xffffffffu;
         if (p.out_hi) {
             // Suffixes starting with q are contiguous from lo: gallop to bracket the end, then bisect.
-            unsigned long long a = lo, b = p.n, step = 1;
+            unsigned long long a = lo, b = range_end, step = 1;
             // The lower-bound search ended with r == lo; if r moved at all, lcp_r is lcp(q, suffix(lo))
             // and the first probe of the gallop is already answered.
             if (lo < p.n && r == lo && lcp_r_exact) {
@@ -490,7 +492,7 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
             }
             while (step) {
                 const unsigned long long pr = a + step - 1;
-                if (pr >= p.n) break;
+                if (pr >= b) break;
                 bool less;
                 const uint32_t lcp = thread_compare(p, __ldg(p.sa + pr), p0, p1, pat, ql, 0u, less);
                 if (lcp >= ql) { a = pr + 1; step <<= 1; } else { b = pr; break; }
@@ -802,8 +804,9 @@ static bool build_kmer(sst_sa* s) {
     if (!ok0) return false;
     if (h_max > 3) return true;  // not a 2-bit alphabet: the pivot-prefix table serves every level
     int k = 1;
-    while (k < 15 && (1ull << (2 * (k + 1))) <= s->n) k++;  // 4^k <= n: about one suffix per table cell
-    k = std::min(k, env_int("SST_SA_KMER_K", 15));
+    while (k < 16 && (1ull << (2 * k + 1)) <= s->n) k++;  // 4^k nearest to n (in ratio): about one suffix per table cell
+    k = std::min(k, env_int("SST_SA_KMER_K", 16));
+    if (const int force = env_int("SST_SA_KMER_FORCE", 0); force >= 4 && force <= 16) k = force;  // tests: a table deeper than the text needs
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     while (k > 4 && ((1ull << (2 * k)) + 1) * 4ull > free_b / 4) k--;

@@ -151,13 +151,16 @@ def test_sa_search_sorted_order(gpu, oracle, levels, monkeypatch):
     _check_search(sst, oracle, s, text, sa, pats)
 
 
-@pytest.mark.parametrize("n,k", [(200_000, "15"), (200_000, "4"), (5000, "15"), (70_000, "7")])
+@pytest.mark.parametrize("n,k", [(200_000, "15"), (200_000, "4"), (5000, "15"), (70_000, "7"), (120_000, "force12"), (90_000, "force16")])
 def test_sa_search_kmer_table(gpu, oracle, n, k, monkeypatch):
     """Texts over {0,1,2,3} get a k-mer table (kmer[x] = lower bound of the k-base string x): the search starts in
     [kmer[x], kmer[x+1]).  Patterns shorter than k, patterns with a byte outside the alphabet (fall back to the pivot table),
     patterns made of the text's tail (proper prefixes of padded k-mers), absent patterns, the empty pattern."""
     sst = gpu
-    monkeypatch.setenv("SST_SA_KMER_K", k)
+    if k.startswith("force"):  # deeper than one suffix per cell; 16 = the 3 Gbp configuration's depth (2^32 + 1 cells, 64-bit cell index)
+        monkeypatch.setenv("SST_SA_KMER_FORCE", k[5:])
+    else:
+        monkeypatch.setenv("SST_SA_KMER_K", k)
     text = random_text(n, seed=n + 5)
     s = sst.SaNaive.build(text)
     sa = s.sa
