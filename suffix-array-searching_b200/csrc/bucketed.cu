@@ -990,6 +990,9 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
         mark();
         {
             void (*kern)(const BkSearchParams, const uint32_t*, const uint32_t*, const uint2*, unsigned*, uint32_t*, uint32_t*) =
+                // SST_BK_PROBE=0: the earlier form (three unconditional probes bounded by the cell's upper end), kept for A/B runs.
+                // Rejected on measurement: software-pipelining the rounds (leaf loads of round k in flight during the probes of
+                // round k + 1): search 0.675 -> 0.761 ms -- the stage is bound by L1/XBAR throughput, not by latency.
                 env_int("SST_BK_PROBE", 1) == 1
                     ? (a.g == 16 ? (d_idx ? bk_search_kernel<true, 16, 1> : bk_search_kernel<false, 16, 1>) : (d_idx ? bk_search_kernel<true, 8, 1> : bk_search_kernel<false, 8, 1>))
                     : (a.g == 16 ? (d_idx ? bk_search_kernel<true, 16, 0> : bk_search_kernel<false, 16, 0>) : (d_idx ? bk_search_kernel<true, 8, 0> : bk_search_kernel<false, 8, 0>));
