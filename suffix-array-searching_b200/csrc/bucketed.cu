@@ -409,7 +409,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
 }
 
 // THREADS = 512 (two CTAs per SM) or 1024 (one CTA per SM: the same shared memory, i.e. ~120 KB of L1 left for loads in flight)
-template <bool GATHER, typename OutT, int THREADS>
+template <bool GATHER, typename OutT, int THREADS, bool PREFETCH = false>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 bk_move_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offs, const uint16_t* __restrict__ lpos16,
                unsigned nbp, unsigned bpt, unsigned ntiles, size_t nq, int aligned, const uint32_t* __restrict__ src,
@@ -440,6 +440,24 @@ bk_move_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__
         }
     };
     if (blockIdx.x < ntiles) load_row(blockIdx.x);
+    // scatter: the queries and positions of the NEXT tile are loaded into registers right after this tile's have been
+    // placed in shared memory, so that their DRAM latency is hidden behind the copy-out phase (one CTA per SM: nothing else
+    // would overlap it; ncu: long-scoreboard + barrier stalls were 43 % of the samples)
+    [[maybe_unused]] uint4 pq[kVec];
+    [[maybe_unused]] uint2 pl[kVec];
+    [[maybe_unused]] bool have = false;
+    auto prefetch_tile = [&](unsigned tile) {
+        if constexpr (!GATHER) {
+            have = PREFETCH && aligned && tile < ntiles && (size_t)(tile + 1) * kTile <= nq;
+            if (have) {
+                const uint4* q4 = reinterpret_cast<const uint4*>(src + (size_t)tile * kTile);
+                const uint2* l2 = reinterpret_cast<const uint2*>(lpos16 + (size_t)tile * kTile);
+#pragma unroll
+                for (int r = 0; r < kVec; r++) { pq[r] = __ldcs(q4 + r * THREADS + tid); pl[r] = __ldcs(l2 + r * THREADS + tid); }
+            }
+        }
+    };
+    prefetch_tile(blockIdx.x);
     for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const size_t tile_base = (size_t)tile * kTile;
         const unsigned tile_n = (unsigned)min((size_t)kTile, nq - tile_base);
@@ -475,16 +493,18 @@ bk_move_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__
         if (aligned && tile_n == (unsigned)kTile) {
             const uint2* l2 = reinterpret_cast<const uint2*>(lpos16 + tile_base);
             if constexpr (!GATHER) {
-                const uint4* q4 = reinterpret_cast<const uint4*>(src + tile_base);
-                uint4 q[kVec];
-                uint2 l[kVec];
+                if (!have) prefetch_tile(tile);  // (block-uniform) first tile of a CTA without the prefetch
+                if (!have) {
+                    const uint4* q4 = reinterpret_cast<const uint4*>(src + tile_base);
 #pragma unroll
-                for (int r = 0; r < kVec; r++) { q[r] = __ldcs(q4 + r * THREADS + tid); l[r] = __ldcs(l2 + r * THREADS + tid); }
+                    for (int r = 0; r < kVec; r++) { pq[r] = __ldcs(q4 + r * THREADS + tid); pl[r] = __ldcs(l2 + r * THREADS + tid); }
+                }
 #pragma unroll
                 for (int r = 0; r < kVec; r++) {
-                    s_tile[l[r].x & 0xffffu] = canonical(q[r].x); s_tile[l[r].x >> 16] = canonical(q[r].y);
-                    s_tile[l[r].y & 0xffffu] = canonical(q[r].z); s_tile[l[r].y >> 16] = canonical(q[r].w);
+                    s_tile[pl[r].x & 0xffffu] = canonical(pq[r].x); s_tile[pl[r].x >> 16] = canonical(pq[r].y);
+                    s_tile[pl[r].y & 0xffffu] = canonical(pq[r].z); s_tile[pl[r].y >> 16] = canonical(pq[r].w);
                 }
+                prefetch_tile(tile + gridDim.x);
                 __syncthreads();
 #pragma unroll
                 for (int r = 0; r < kIt; r++) {  // runs: consecutive lanes write consecutive words
@@ -867,7 +887,11 @@ void launch_move(int sms, size_t smem, cudaStream_t st, const Scratch& s, unsign
     // allows: one CTA of 1024 threads per SM (gather 0.32 vs 0.37 ms, scatter 0.31); SST_BK_MOVE_THREADS=512 for the old shape.
     const int threads = (nbp % 1024 == 0 && env_int("SST_BK_MOVE_THREADS", 1024) == 1024) ? 1024 : kThreads;
     const unsigned bpt = nbp / threads;
-    if (threads == 1024) {
+    if (threads == 1024 && !GATHER && env_int("SST_BK_PREFETCH", 1)) {
+        auto kern = bk_move_kernel<GATHER, OutT, 1024, true>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<(unsigned)std::min<size_t>(ntiles, (size_t)sms), 1024, smem, st>>>(s.counts, s.offs, s.lpos, nbp, bpt, ntiles, nq, aligned, src, dst);
+    } else if (threads == 1024) {
         auto kern = bk_move_kernel<GATHER, OutT, 1024>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kern<<<(unsigned)std::min<size_t>(ntiles, (size_t)sms), 1024, smem, st>>>(s.counts, s.offs, s.lpos, nbp, bpt, ntiles, nq, aligned, src, dst);

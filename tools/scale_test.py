@@ -16,10 +16,43 @@ import sst_b200 as sst
 
 MAX = sst.MAX
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-outf = open(os.path.join(ROOT, "gpurun_out", "scale.jsonl"), "a")
+# Under torchrun (one process per GPU) the index is replicated and the queries / patterns are sharded: every rank runs its
+# share on its own replica, the time is the max over ranks (NCCL is used for that reduction and the barrier only).
+RANK, WORLD, LOCAL = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+DEV = torch.device("cuda", LOCAL)
+torch.cuda.set_device(DEV)
+if WORLD > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=DEV)
+outf = open(os.path.join(ROOT, "gpurun_out", "scale.jsonl"), "a") if RANK == 0 else None
+
+
+def max_over_ranks(ms):
+    if WORLD == 1:
+        return ms
+    t = torch.tensor([ms], dtype=torch.float64, device=DEV)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def all_ranks(ok):
+    if WORLD == 1:
+        return ok
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=DEV)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item())
+
+
+def barrier():
+    torch.cuda.synchronize()
+    if WORLD > 1:
+        dist.barrier()
 
 
 def emit(**kw):
+    if RANK != 0:
+        return
+    kw["n_gpus"] = WORLD
     line = json.dumps(kw)
     print(line, flush=True)
     outf.write(line + "\n")
@@ -28,12 +61,15 @@ def emit(**kw):
 
 def c4(logn=30, nq=1_000_000_000):
     L = sst.lib()
-    dev = torch.device("cuda", 0)
+    dev = DEV
     g = torch.Generator(device=dev).manual_seed(11)
     n = 1 << logn
     keys = torch.randint(0, MAX, (n,), dtype=torch.int32, device=dev, generator=g)
     keys[0] = MAX
     keys = torch.sort(keys).values.contiguous()
+    nq_total = nq
+    nq = (nq + WORLD - 1) // WORLD  # this rank's contiguous share (chunk = ceil(nq / G), bench.rs:558)
+    g = torch.Generator(device=dev).manual_seed(1100 + RANK)
     qs = torch.randint(0, MAX, (nq,), dtype=torch.int32, device=dev, generator=g)
     out = torch.empty_like(qs)
     for name, build in (("stree16_left_max", lambda: sst.STree16.new_params(keys, True, False, False)),
@@ -42,24 +78,26 @@ def c4(logn=30, nq=1_000_000_000):
         t = build()
         torch.cuda.synchronize()
         bs = time.time() - t0
-        ms = L.sst_time_query_device(t._h, C.c_void_p(qs.data_ptr()), nq, C.c_void_p(out.data_ptr()), None, 0, 1, 3)
+        barrier()
+        ms = max_over_ranks(L.sst_time_query_device(t._h, C.c_void_p(qs.data_ptr()), nq, C.c_void_p(out.data_ptr()), None, 0, 1, 3))
         torch.cuda.synchronize()
         # properties on a 10^8 slice (full-size gathers would need 8 GB more)
-        sl = slice(0, 100_000_000)
+        sl = slice(0, min(nq, 100_000_000))
         v = out[sl]
         ok = bool((v >= qs[sl]).all())
         i = torch.searchsorted(keys, qs[:10_000_000])
         ok = ok and bool((keys[i.clamp(max=n - 1)] == out[:10_000_000]).all())
-        emit(kind="c4", layout=name, logn=logn, nq=nq, layers=t.layers(), size_mb=t.size() / 2**20, build_s=round(bs, 3), ms=ms,
-             gqps=nq / ms / 1e6, ok=ok)
+        emit(kind="c4", layout=name, logn=logn, nq=nq * WORLD, nq_per_gpu=nq, layers=t.layers(), size_mb=t.size() / 2**20, build_s=round(bs, 3), ms=ms,
+             gqps=nq * WORLD / ms / 1e6, ok=all_ranks(ok))
         del t
 
 
 def c5(n=3_000_000_000, npat=100_000_000):
     L = sst.lib()
-    dev = torch.device("cuda", 0)
+    dev = DEV
     g = torch.Generator(device=dev).manual_seed(12)
     text = torch.randint(0, 4, (n,), dtype=torch.uint8, device=dev, generator=g)
+    npat = (npat + WORLD - 1) // WORLD  # this rank's share of the patterns; text + SA replicated
     t0 = time.time()
     sa = sst.SaNaive.build(text)
     torch.cuda.synchronize()
@@ -69,6 +107,7 @@ def c5(n=3_000_000_000, npat=100_000_000):
     viol = sa.check()
     emit(kind="c5_check", violations=viol, check_s=round(time.time() - t0, 2))
     # patterns: substrings, length uniform in [20, 100]
+    g = torch.Generator(device=dev).manual_seed(1200 + RANK)
     lens = torch.randint(20, 101, (npat,), device=dev, generator=g)
     off = torch.zeros(npat + 1, dtype=torch.int64, device=dev)
     torch.cumsum(lens, 0, out=off[1:])
@@ -105,13 +144,13 @@ def c5(n=3_000_000_000, npat=100_000_000):
                                         C.c_void_p(lo.data_ptr()), C.c_void_p(hi.data_ptr()), C.c_void_p(pos.data_ptr()), None)
             assert rc == 0, L.sst_last_error()
         run()
-        torch.cuda.synchronize()
+        barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         run()
         b.record()
         torch.cuda.synchronize()
-        ms = a.elapsed_time(b)
+        ms = max_over_ranks(a.elapsed_time(b))
         # property: the first 20 bytes of the pattern occur at the returned position
         chk = 1_000_000
         p64 = pos[:chk].long() & 0xFFFFFFFF
@@ -121,11 +160,14 @@ def c5(n=3_000_000_000, npat=100_000_000):
         if ref_lo is None:
             ref_lo = lo.clone()
         same = bool((lo == ref_lo).all())
-        emit(kind="c5_search", mode=name, n=n, npat=npat, total_pattern_bytes=total, ms=ms, gpat_per_s=npat / ms / 1e6, ok=ok, same_as_binary=same)
+        emit(kind="c5_search", mode=name, n=n, npat=npat * WORLD, npat_per_gpu=npat, total_pattern_bytes_rank0=total, ms=ms, gpat_per_s=npat * WORLD / ms / 1e6,
+             ok=all_ranks(ok), same_as_binary=all_ranks(same))
 
 
 if __name__ == "__main__":
     what = sys.argv[1]
+    if RANK != 0:
+        sys.stdout = open(os.devnull, "w")
     if what == "c4":
         c4(int(os.environ.get("LOGN", "30")), int(os.environ.get("NQ", "1000000000")))
     elif what == "c5":
