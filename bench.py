@@ -201,6 +201,9 @@ def run_own(args):
         raise RuntimeError("no sm_100 device: sst_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # host side of the e2e path: this rank's thread (and the pinned buffers it allocates) on the CPUs local to its GPU
+    orig_affinity = os.sched_getaffinity(0)
+    affinity_cpus = 0 if os.environ.get("SST_NO_BIND") else sst.bind_thread_to_device(local)
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -341,6 +344,7 @@ def run_own(args):
         e2e = {"value": world * nq * args.e2e_steps / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": 4 * (e - s),
                "d2h_bytes_per_step": 4 * (e - s), "steps": args.e2e_steps}
 
+    os.sched_setaffinity(0, orig_affinity)  # the CPU baselines below use every host core the process was given
     # ---- CPU baseline on the box's host cores (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -406,6 +410,7 @@ def run_own(args):
             "config": {
                 "workload": f"stree16 left_max lower_bound: {n} sorted uniform u32 keys (S+-tree B=16, {len(layer_nodes)} levels), {nq} uniform u32 queries per GPU per step",
                 "n_keys": n, "queries_per_gpu": nq, "global_queries": world * nq, "parallelism": f"replicated index, query-sharded x{world}",
+                "host_affinity_cpus": affinity_cpus,
                 "scheme": scheme_names.get(res_scheme.value, str(res_scheme.value)), "index_build_s": round(build_s, 3),
                 "l2_policy": "inputs larger than L2: 1 GiB leaf level + 0.8 GB query/result streams per step, two alternating query batches",
             },

@@ -85,6 +85,12 @@ int sst_device_count(void);          /* number of usable sm_100 devices, 0 if no
 void* sst_host_alloc(size_t bytes);
 void sst_host_free(void* p);
 const char* sst_version(void);
+/* Binds the calling host thread to the CPUs local to `device` (PCIe/NUMA topology from sysfs), so that the page-locked
+ * buffers it allocates afterwards and its copies stay on the GPU's socket.  The reference pins nothing (rayon workers,
+ * sst/bin/bench.rs:558-573) because its data never leaves host memory; here every query crosses PCIe once each way.
+ * Returns the size of the CPU set, 0 when the topology is not visible (nothing changed), < 0 on a CUDA error.
+ * sst_multi_* workers call it for their device. */
+int sst_bind_thread_to_device(int device);
 
 /* ---- S+-tree: replaces STree::<B,16>::new_params (sst/s_tree.rs:72-176) ------------------- */
 /* `sorted` is a HOST pointer to n ascending keys, all <= SST_MAX.  node_b is B (16, or 15 for

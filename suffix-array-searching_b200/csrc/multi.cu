@@ -13,6 +13,8 @@
 #include <thread>
 #include <vector>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -86,6 +88,7 @@ sst_multi* build_replicas(const int* devices, int n_devices, F build_one) {
     std::vector<int> stats(n_devices, SST_OK);
     for (int i = 0; i < n_devices; i++)
         m->workers[i]->post([&, i] {
+            if (!getenv("SST_NO_BIND")) (void)sst_bind_thread_to_device(devices[i]);  // worker stays on the GPU's socket
             m->replicas[i] = build_one(devices[i]);
             if (!m->replicas[i]) { errs[i] = sst_last_error(); stats[i] = sst_last_status(); }
         });

@@ -3,6 +3,12 @@
 #include <cstdlib>
 #include <mutex>
 
+#include <sched.h>
+
+#include <cctype>
+#include <cstdio>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace sst {
@@ -107,6 +113,46 @@ void* sst_host_alloc(size_t bytes) {
 }
 void sst_host_free(void* p) {
     if (p) (void)cudaFreeHost(p);
+}
+
+// Host-side locality: on a multi-socket box a page-locked buffer that lives on the other socket's memory makes every
+// H2D/D2H cross the socket interconnect (measured: 8 ranks, 0.8 GB per rank and step: 16.8 Gq/s in total, 2.1 per GPU,
+// against 10.5 for one GPU alone).  Binds the calling thread to the CPUs that are local to `device`
+// (/sys/bus/pci/devices/<bus id>/local_cpulist); memory the thread allocates afterwards (first touch, cudaHostAlloc) is
+// then local too.  Returns the number of CPUs in the set, 0 if the topology is not visible (nothing changed), -1 on error.
+int sst_bind_thread_to_device(int device) {
+    sst::clear_error();
+    char bus[32] = {0};
+    if (!SST_CUDA_OK(cudaDeviceGetPCIBusId(bus, sizeof(bus), device))) return -1;
+    for (char* c = bus; *c; c++) *c = (char)tolower(*c);
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return 0;
+    char line[4096] = {0};
+    const bool got = fgets(line, sizeof(line), f) != nullptr;
+    fclose(f);
+    if (!got) return 0;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int count = 0;
+    for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {  // "0-31,64-95"
+        int a = -1, b = -1;
+        if (sscanf(tok, "%d-%d", &a, &b) == 2) {}
+        else if (sscanf(tok, "%d", &a) == 1) b = a;
+        for (int c = a; a >= 0 && c <= b && c < CPU_SETSIZE; c++) { CPU_SET(c, &set); count++; }
+    }
+    if (count == 0) return 0;
+    cpu_set_t cur;
+    if (sched_getaffinity(0, sizeof(cur), &cur) == 0) {  // stay inside the set the process was given (cgroups, taskset)
+        cpu_set_t both;
+        CPU_AND(&both, &set, &cur);
+        if (CPU_COUNT(&both) == 0) return 0;
+        set = both;
+        count = CPU_COUNT(&both);
+    }
+    if (sched_setaffinity(0, sizeof(set), &set) != 0) return 0;
+    return count;
 }
 
 int sst_device_count(void) {

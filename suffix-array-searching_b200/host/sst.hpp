@@ -32,6 +32,9 @@ inline void check(int rc) { if (rc != SST_OK) panic_last(); }
 
 constexpr uint32_t MAX = SST_MAX;  // node.rs:5
 
+/// CPU affinity of the calling thread := the CPUs local to `device` (NUMA); the size of the set, 0 if the topology is hidden.
+inline int bind_thread_to_device(int device) { return sst_bind_thread_to_device(device); }
+
 /// trait SearchIndex (lib.rs:30-48)
 class SearchIndex {
   public:

@@ -29,6 +29,7 @@ extern "C" {
     fn sst_index_layers(idx: *const SstIndex) -> usize;
     fn sst_query(idx: *const SstIndex, qs: *const u32, nq: usize, out_vals: *mut u32, out_idx: *mut u64, scheme: c_int) -> c_int;
     fn sst_eytzinger_build(sorted: *const u32, n: usize, device: c_int) -> *mut SstIndex;
+    fn sst_bind_thread_to_device(device: c_int) -> c_int;
     fn sst_host_alloc(bytes: usize) -> *mut c_void;
     fn sst_host_free(p: *mut c_void);
     fn sst_fasta_encode(fasta: *const c_char, len: usize, out_codes: *mut u8, out_len: *mut usize, device: c_int) -> c_int;
@@ -88,6 +89,11 @@ pub struct GpuEytzinger(pub GpuIndex);
 impl GpuEytzinger {
     pub fn new(vals: &[u32]) -> Self { Self(GpuIndex::from_raw(unsafe { sst_eytzinger_build(vals.as_ptr(), vals.len(), 0) })) }
     pub fn search(&self, q: u32) -> u32 { self.0.query(&[q])[0] }
+}
+
+/// Binds the calling thread to the CPUs local to `device` (NUMA); returns the size of the CPU set, 0 if unknown.
+pub fn bind_thread_to_device(device: i32) -> i32 {
+    unsafe { sst_bind_thread_to_device(device as c_int) as i32 }
 }
 
 /// Page-locked `u32` buffer (`sst_host_alloc`): lets `GpuIndex::query_into` overlap H2D, kernel and D2H.

@@ -56,6 +56,7 @@ def lib() -> C.CDLL:
         "sst_last_status": (i32, []),
         "sst_device_count": (i32, []),
         "sst_version": (C.c_char_p, []),
+        "sst_bind_thread_to_device": (i32, [i32]),
         "sst_host_alloc": (vp, [sz]),
         "sst_host_free": (None, [vp]),
         "sst_stree_build": (vp, [vp, sz, u32, u32, i32]),
@@ -126,6 +127,11 @@ def _check(rc: int):
 
 def device_count() -> int:
     return lib().sst_device_count()
+
+
+def bind_thread_to_device(device: int) -> int:
+    """CPU affinity of the calling thread := the CPUs local to `device` (NUMA); returns the set size, 0 if unknown."""
+    return lib().sst_bind_thread_to_device(device)
 
 
 class PinnedArray:
