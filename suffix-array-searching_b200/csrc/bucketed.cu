@@ -147,6 +147,7 @@ struct BkView {
     const uint16_t* bt;
     const uint32_t* split;
     unsigned nb, nbp, bpt;  // buckets, padded to a multiple of kThreads, buckets per thread
+    unsigned* above;        // Map-partitioned trees: set to 1 when some query is above MAX (null for plain trees)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -194,6 +195,12 @@ __device__ __forceinline__ void rank_tile(const BkView& v, const uint32_t* __res
         uint32_t pk[kItems];  // bucket | rank << 16; 0xffffffff = no query
 #pragma unroll
         for (int r = 0; r < kItems; r++) pk[r] = (FULL || i0 + r * 32 < tile_n) ? __ldcs(tq + r * 32) : 0u;
+        if (v.above) {  // (uniform) the partitioned layouts answer q > MAX with (MAX, n), not with the signed compare: note it
+            uint32_t acc = 0;
+#pragma unroll
+            for (int r = 0; r < kItems; r++) acc |= pk[r];
+            if (__any_sync(kFull, acc > kMax) && lane == 0) atomicOr(v.above, 1u);
+        }
 #pragma unroll
         for (int r = 0; r < kItems; r++)
             pk[r] = (FULL || i0 + r * 32 < tile_n) ? bk_bucket_packed(s_pk, v.bt, v.split, canonical(pk[r])) : 0xffffffffu;
@@ -794,6 +801,19 @@ bk_jump_kernel(const uint32_t* __restrict__ sep, const uint32_t* __restrict__ sp
     }
 }
 
+// Map-partitioned trees: a query above MAX has no part (partitioned_s_tree.rs:844: the prefix map has no such entry) and is
+// answered with (MAX, n) by every kernel of this library; the pipeline canonicalises such queries like the plain tree's
+// signed compare, so they are rewritten here.  Exits at once unless the rank stage saw one.
+__global__ void bk_above_kernel(const unsigned* __restrict__ flag, const uint32_t* __restrict__ qs, size_t nq, uint32_t* __restrict__ vals,
+                                unsigned long long* __restrict__ idx, unsigned long long n) {
+    if (!*flag) return;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += (size_t)gridDim.x * blockDim.x)
+        if (qs[i] > kMax) {
+            vals[i] = kMax;
+            if (idx) idx[i] = n;
+        }
+}
+
 int env_int(const char* name, int dflt) {
     const char* s = getenv(name);
     return (s && *s) ? atoi(s) : dflt;
@@ -913,7 +933,9 @@ void free_bucket_aux(sst_index* idx) {
 // Builds the auxiliary arrays of the reordered-batch pipeline for a plain B=16 tree.  Returns false only
 // on a CUDA error; an index the pipeline does not serve simply has bk.nb == 0.
 bool build_bucket_aux(sst_index* idx) {
-    if (idx->variant != SST_PLAIN || idx->node_b != 16) return true;
+    // plain B=16 trees, and the Map-partitioned layout: its leaf level is the sorted array itself, without per-part gaps
+    // (partitioned_s_tree.rs:503), which is all the pipeline reads of an image
+    if ((idx->variant != SST_PLAIN && idx->variant != SST_MAP) || idx->node_b != 16) return true;
     if (idx->n < (size_t)env_int("SST_BK_MIN_N", 1 << 22)) return true;  // small trees are L2-resident: nothing to gain
     // separators per bucket: 16384 (two search CTAs per SM) up to 2^27 keys, 32768 (one 1024-thread CTA) above, so that the
     // partition has at most 1024 buckets up to 2^28 keys -- fewer buckets = longer runs and fewer ballot bits
@@ -959,7 +981,7 @@ int last_stage_ms(double* out, int n) {
 
 int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx, cudaStream_t st) {
     const BkAux& a = idx->bk;
-    if (!a.nb) { set_error(SST_ERR_UNSUPPORTED, "the reordered-batch pipeline serves plain B=16 trees of 2^22..2^28 keys"); return SST_ERR_UNSUPPORTED; }
+    if (!a.nb) { set_error(SST_ERR_UNSUPPORTED, "the reordered-batch pipeline serves plain and Map-partitioned B=16 trees of 2^22..2^30 keys"); return SST_ERR_UNSUPPORTED; }
     const int dev = idx->device;
     if (dev < 0 || dev >= 64) { set_error(SST_ERR_ARG, "device index out of range"); return SST_ERR_ARG; }
     Scratch& s = g_scratch[dev];
@@ -971,7 +993,9 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
     if (!SST_CUDA_OK(cudaStreamWaitEvent(st, s.done, 0))) return SST_ERR_CUDA;  // scratch reuse across this thread's streams
     const int sms = sm_count(dev);
     const unsigned bpt = a.nbp / kThreads;
-    BkView v{a.d_bt, a.d_split, a.nb, a.nbp, bpt};
+    const bool map_tree = idx->variant == SST_MAP;
+    BkView v{a.d_bt, a.d_split, a.nb, a.nbp, bpt, map_tree ? s.ctrl + 3 : nullptr};
+    if (map_tree && !SST_CUDA_OK(cudaMemsetAsync(s.ctrl + 3, 0, 4, st))) return SST_ERR_CUDA;
     const size_t smem_rank = (size_t)kWarps * a.nbp * 2 + (size_t)kBtCells * 4;
     const size_t smem_move = (size_t)kTile * 4 + (size_t)a.nbp * 4 + (size_t)kTile * 2;
     const size_t smem_search = (size_t)a.r * 4 + ((size_t)a.r + 8) * 2;
@@ -1026,6 +1050,7 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
         mark();
         launch_move<true, uint32_t>(sms, smem_move, st, s, a.nbp, ntiles, cnt, s.rb, d_vals + off);
         if (d_idx) launch_move<true, unsigned long long>(sms, smem_move, st, s, a.nbp, ntiles, cnt, s.ib, d_idx + off);
+        if (map_tree) bk_above_kernel<<<sms * 4, 256, 0, st>>>(s.ctrl + 3, qs, cnt, d_vals + off, d_idx ? d_idx + off : nullptr, (unsigned long long)idx->n);
         mark();
         if (timing && nev == 6 && cudaEventSynchronize(ev[5]) == cudaSuccess) {
             float t[5];

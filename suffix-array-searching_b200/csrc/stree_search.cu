@@ -762,15 +762,15 @@ int launch_fast_top(const sst_index* idx, bool top, const uint32_t* d_qs, size_t
 int resolve_scheme(const sst_index* idx, int scheme, size_t nq) {
     if (scheme != SST_SCHEME_AUTO) return scheme;
     if (idx->variant == SST_EYTZINGER) return SST_SCHEME_GENERIC;
-    if (idx->variant != SST_PLAIN && idx->node_b == 16 && env_int("SST_PGROUP", 1)) return SST_SCHEME_AUTO;  // lane-group kernel
-    if (!fast_eligible(idx)) return SST_SCHEME_GENERIC;
-    if (nq < (size_t)env_int("SST_TABLE_MIN_NQ", 1 << 17)) return env_int("SST_SCHEME", SST_SCHEME_GENERIC);
-    if (bucketed_eligible(idx) && idx->n >= (size_t)env_int("SST_BK_AUTO_MIN_N", 1 << 25)) {
+    if (bucketed_eligible(idx) && idx->n >= (size_t)env_int("SST_BK_AUTO_MIN_N", 1 << 25)) {  // plain and Map-partitioned trees
         // measured crossovers (tools/bucketed_once.py): 2^28 keys ~1.2x10^7 queries, 2^26 keys ~4x10^7, 2^25 keys ~6x10^7;
         // at 2^24 keys and below the tree is L2-resident and the direct kernel always wins (65.7 vs 45.5 Gq/s)
         const size_t min_nq = idx->n >= ((size_t)1 << 27) ? (size_t)1 << 24 : idx->n >= ((size_t)1 << 26) ? (size_t)3 << 24 : (size_t)1 << 26;
         if (nq >= (size_t)env_int("SST_BK_AUTO_MIN_NQ", (int)min_nq)) return env_int("SST_SCHEME", SST_SCHEME_BUCKETED);
     }
+    if (idx->variant != SST_PLAIN && idx->node_b == 16 && env_int("SST_PGROUP", 1)) return SST_SCHEME_AUTO;  // lane-group kernel
+    if (!fast_eligible(idx)) return SST_SCHEME_GENERIC;
+    if (nq < (size_t)env_int("SST_TABLE_MIN_NQ", 1 << 17)) return env_int("SST_SCHEME", SST_SCHEME_GENERIC);
     return env_int("SST_SCHEME", top_eligible(idx) ? SST_SCHEME_TABLE : SST_SCHEME_GROUP2);
 }
 
@@ -781,7 +781,7 @@ int resolve_scheme(const sst_index* idx, int scheme, size_t nq) {
 int query_launch_count(const sst_index* idx, int scheme, size_t nq, bool want_idx) {
     if (nq == 0) return 0;
     if (resolve_scheme(idx, scheme, nq) != SST_SCHEME_BUCKETED) return 1;
-    return (int)(div_ceil(nq, (size_t)1 << 27) * (want_idx ? 8 : 7));
+    return (int)(div_ceil(nq, (size_t)1 << 27) * ((want_idx ? 8 : 7) + (idx->variant == SST_MAP ? 1 : 0)));  // Map: + the q > MAX fix-up
 }
 
 int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx,
@@ -796,14 +796,16 @@ int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t
         eytzinger_search_kernel<<<grid, 256, 0, st>>>(idx->d_tree, idx->eytz_words, idx->eytz_h, d_qs, nq, d_vals, d_idx);
         return SST_CUDA_OK(cudaGetLastError()) ? SST_OK : SST_ERR_CUDA;
     }
-    if (scheme == SST_SCHEME_AUTO && idx->variant != SST_PLAIN && idx->node_b == 16 && env_int("SST_PGROUP", 1)) {
+    auto launch_pgroup = [&]() {  // lane-group kernel of the partitioned layouts
         const int sms = sm_count(idx->device);
         const int T = env_int("SST_PT", 1);  // measured: T=1 27.7 vs T=2 23.9 Gq/s (Simple, 2^28 keys)
         const int grid = (int)std::min<size_t>(div_ceil(nq, (size_t)16 * 32 * T), (size_t)sms * 2);
         if (T == 1) pstree_search_group<1><<<grid, 512, 0, st>>>(idx->view, d_qs, nq, d_vals, d_idx);
         else pstree_search_group<2><<<grid, 512, 0, st>>>(idx->view, d_qs, nq, d_vals, d_idx);
         return SST_CUDA_OK(cudaGetLastError()) ? SST_OK : SST_ERR_CUDA;
-    }
+    };
+    const bool pgroup = idx->variant != SST_PLAIN && idx->node_b == 16 && env_int("SST_PGROUP", 1);
+    if (scheme == SST_SCHEME_AUTO && pgroup && resolve_scheme(idx, scheme, nq) != SST_SCHEME_BUCKETED) return launch_pgroup();
     const bool was_auto = scheme == SST_SCHEME_AUTO;
     scheme = resolve_scheme(idx, scheme, nq);
     if (was_auto && scheme == SST_SCHEME_BUCKETED) {
@@ -811,8 +813,10 @@ int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t
         const int rc = launch_bucketed(idx, d_qs, nq, d_vals, d_idx, st);
         if (rc != SST_ERR_CAPACITY) return rc;
         clear_error();
+        if (idx->variant != SST_PLAIN) return pgroup ? launch_pgroup() : launch_query(idx, d_qs, nq, d_vals, d_idx, SST_SCHEME_GENERIC, st);  // Map tree
         scheme = top_eligible(idx) ? SST_SCHEME_TABLE : SST_SCHEME_GROUP2;
     }
+    if (scheme == SST_SCHEME_BUCKETED && bucketed_eligible(idx)) return launch_bucketed(idx, d_qs, nq, d_vals, d_idx, st);
     if (scheme != SST_SCHEME_GENERIC && !fast_eligible(idx)) {  // (BINSEARCH included: plain B=16 only)
         set_error(SST_ERR_UNSUPPORTED, "the group/table kernels serve the plain B=16 tree; use SST_SCHEME_AUTO or SST_SCHEME_GENERIC");
         return SST_ERR_UNSUPPORTED;

@@ -185,3 +185,49 @@ def test_bucketed_degenerate_batches(gpu, oracle, monkeypatch):
                np.sort(gen_queries(200_000, seed=34, vals=vals)), np.sort(gen_queries(200_000, seed=35, vals=vals))[::-1].copy(),
                (vals[100_000] + (np.arange(150_000) % 7)).astype(np.uint32)):
         _check(sst, oracle, vals, qs, flags=[(1, 0, 0)])
+
+
+@pytest.mark.parametrize("r,n,nq,b", [(64, 5000, 40_000, 4), (64, 1_000_000, 70_000, 8), (256, (1 << 20) + 5, 300_000, 16), (1024, 2_000_003, 150_000, 20),
+                                      (64, 17, 33, 0), (16384, (1 << 22) + 999, 600_000, 20)])
+def test_bucketed_map_partitioned(gpu, oracle, monkeypatch, r, n, nq, b):
+    """The pipeline over a Map-partitioned tree (its leaf level is the sorted array, partitioned_s_tree.rs:503): same values
+    and indices as the oracle and as the layout's own lane-group kernel, including queries above MAX (no part: (MAX, n))."""
+    sst = gpu
+    monkeypatch.setenv("SST_BK_MIN_N", "0")
+    monkeypatch.setenv("SST_BK_R", str(r))
+    vals = gen_vals(n, seed=n + r + 7)
+    t = sst.PartitionedSTree16M.new(vals, b)
+    qs = gen_queries(nq, seed=n + 3, vals=vals)
+    ev, ei = oracle.lower_bound(vals, qs)
+    v, i = t.query(qs, sst.SCHEME_BUCKETED, want_index=True)
+    assert np.array_equal(v, ev) and np.array_equal(i, ei)
+    assert np.array_equal(t.query(qs, sst.SCHEME_BUCKETED), ev)
+    # queries above MAX mixed in: must equal the lane-group kernel (AUTO at this batch size) and the generic kernel
+    qb = qs.copy()
+    qb[:: max(1, nq // 97)] = 0x80000000 + (qb[:: max(1, nq // 97)] >> 1)
+    qb[-1] = 0xFFFFFFFF
+    v1, i1 = t.query(qb, sst.SCHEME_BUCKETED, want_index=True)
+    v2, i2 = t.query(qb, want_index=True)
+    v3, i3 = t.query(qb, sst.SCHEME_GENERIC, want_index=True)
+    assert np.array_equal(v1, v2) and np.array_equal(i1, i2) and np.array_equal(v1, v3) and np.array_equal(i1, i3)
+    assert (v1[qb > MAX] == MAX).all() and (i1[qb > MAX] == n).all()
+    assert np.array_equal(t.query(qb, sst.SCHEME_BUCKETED), v1)
+
+
+def test_bucketed_map_skewed_keys(gpu, oracle, monkeypatch):
+    """Map tree over keys that do not reach 31 bits / with long duplicate runs, MAX not a key."""
+    sst = gpu
+    monkeypatch.setenv("SST_BK_MIN_N", "0")
+    monkeypatch.setenv("SST_BK_R", "64")
+    rng = np.random.default_rng(77)
+    for kind in ("dupes", "clustered"):
+        vals = make_keys(rng, 300_000, kind)
+        qs = make_queries(rng, vals, 100_000)
+        t = sst.PartitionedSTree16M.try_new(vals, 12)
+        if t is None:
+            continue
+        ev, ei = oracle.lower_bound(vals, qs)
+        v, i = t.query(qs, sst.SCHEME_BUCKETED, want_index=True)
+        v2, i2 = t.query(qs, want_index=True)
+        assert np.array_equal(v, v2) and np.array_equal(i, i2)
+        assert np.array_equal(v, ev) and np.array_equal(i, ei)
