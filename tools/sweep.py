@@ -97,7 +97,7 @@ def sizes_mode():
         keys[0] = MAX
         keys = torch.sort(keys).values.contiguous()
         tree = sst.STree16.new_params(keys, True, False, False)
-        for scheme, name in ((0, "auto"), (3, "group2"), (4, "generic")):
+        for scheme, name in ((0, "auto"), (5, "table"), (3, "group2"), (4, "generic")):
             ms = L.sst_time_query_device(tree._h, C.c_void_p(qs.data_ptr()), nq, C.c_void_p(out.data_ptr()), None, scheme, 2, 5)
             emit(kind="size", logn=logn, layout="stree16_left_max", layers=tree.layers(), kernel=name, ms=ms, gqps=nq / ms / 1e6 if ms > 0 else None)
         del tree
@@ -109,7 +109,7 @@ def sizes_mode():
                     emit(kind="size", logn=logn, layout=name, none=True)
                     continue
                 ms = L.sst_time_query_device(t._h, C.c_void_p(qs.data_ptr()), nq, C.c_void_p(out.data_ptr()), None, 0, 1, 3)
-                emit(kind="size", logn=logn, layout=name, layers=t.layers(), size_mb=t.size() / 2**20, params=t.params, kernel="generic",
+                emit(kind="size", logn=logn, layout=name, layers=t.layers(), size_mb=t.size() / 2**20, params=t.params, kernel="auto",
                      ms=ms, gqps=nq / ms / 1e6 if ms > 0 else None)
                 del t
         del keys
