@@ -26,6 +26,8 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace sst {
@@ -678,6 +680,8 @@ int env_int(const char* name, int dflt) {
     return (s && *s) ? atoi(s) : dflt;
 }
 
+thread_local int g_host_grid_cap = 0;  // 0 = no cap (device-resident batches)
+
 bool fast_eligible(const sst_index* idx) { return idx->variant == SST_PLAIN && idx->node_b == 16; }
 bool top_eligible(const sst_index* idx) { return fast_eligible(idx) && idx->d_top_table != nullptr; }
 
@@ -707,6 +711,9 @@ int launch_fast(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t*
     const int sms = sm_count(idx->device);
     const size_t per_cta = (size_t)(threads / 32) * 32 * T;
     int grid = (int)std::min<size_t>(div_ceil(nq, per_cta), (size_t)sms * (size_t)env_int("SST_WAVES", 1));
+    // Host-buffer path: sst_query caps the grid (g_host_grid_cap) so that the kernel runs through a chunk's whole copy period
+    // at low DRAM intensity instead of saturating the random-access rate in bursts next to the copy engines.
+    if (const int cap = env_int("SST_GRID_CAP", g_host_grid_cap); cap > 0 && grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     auto kern = stree_search_fast<G, T, TOP>;
     if (smem_bytes > 48 * 1024 &&
@@ -895,19 +902,20 @@ int sst_query_device(const sst_index_t* idx, const uint32_t* d_qs, size_t nq, ui
 // Per (host thread, device) staging ring for the host-buffer path: allocated once and reused, so
 // that a call costs no cudaMalloc/cudaFree (which synchronise the device).
 namespace {
+constexpr int kRing = 3;  // device-side ring: three chunks in flight (H2D | kernel | D2H)
 struct Staging {
     size_t cap = 0, cap_idx = 0;
-    uint32_t* q[3] = {};
-    uint32_t* v[3] = {};
-    unsigned long long* i[3] = {};
-    cudaEvent_t e_in[3] = {}, e_k[3] = {}, e_out[3] = {};
+    uint32_t* q[kRing] = {};
+    uint32_t* v[kRing] = {};
+    unsigned long long* i[kRing] = {};
+    cudaEvent_t e_in[kRing] = {}, e_k[kRing] = {}, e_out[kRing] = {};
     bool events = false;
     int device = -1;
     ~Staging() {  // host thread exits: give the device memory back (errors at process teardown are ignored)
         if (device < 0 || (!cap && !cap_idx && !events)) return;
         int prev = -1;
         if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) { (void)cudaGetLastError(); return; }
-        for (int b = 0; b < 3; b++) {
+        for (int b = 0; b < kRing; b++) {
             cudaFree(q[b]); cudaFree(v[b]); cudaFree(i[b]);
             if (events) { cudaEventDestroy(e_in[b]); cudaEventDestroy(e_k[b]); cudaEventDestroy(e_out[b]); }
         }
@@ -919,7 +927,7 @@ thread_local Staging g_staging[64];
 
 bool staging_ensure(Staging& s, size_t cap, bool want_idx) {
     if (!s.events) {
-        for (int b = 0; b < 3; b++)
+        for (int b = 0; b < kRing; b++)
             if (!SST_CUDA_OK(cudaEventCreateWithFlags(&s.e_in[b], cudaEventDisableTiming)) ||
                 !SST_CUDA_OK(cudaEventCreateWithFlags(&s.e_k[b], cudaEventDisableTiming)) ||
                 !SST_CUDA_OK(cudaEventCreateWithFlags(&s.e_out[b], cudaEventDisableTiming)))
@@ -927,7 +935,7 @@ bool staging_ensure(Staging& s, size_t cap, bool want_idx) {
         s.events = true;
     }
     if (cap > s.cap) {
-        for (int b = 0; b < 3; b++) {
+        for (int b = 0; b < kRing; b++) {
             cudaFree(s.q[b]); cudaFree(s.v[b]);
             s.q[b] = s.v[b] = nullptr;
             if (!SST_CUDA_OK(cudaMalloc(&s.q[b], cap * 4)) || !SST_CUDA_OK(cudaMalloc(&s.v[b], cap * 4))) { s.cap = 0; return false; }
@@ -935,7 +943,7 @@ bool staging_ensure(Staging& s, size_t cap, bool want_idx) {
         s.cap = cap;
     }
     if (want_idx && cap > s.cap_idx) {
-        for (int b = 0; b < 3; b++) {
+        for (int b = 0; b < kRing; b++) {
             cudaFree(s.i[b]);
             s.i[b] = nullptr;
             if (!SST_CUDA_OK(cudaMalloc(&s.i[b], cap * 8))) { s.cap_idx = 0; return false; }
@@ -961,10 +969,35 @@ int sst_query(const sst_index_t* idx, const uint32_t* qs, size_t nq, uint32_t* o
     if (!s_in || !s_k || !s_out) return SST_ERR_CUDA;
     const size_t chunk = std::max<size_t>((size_t)env_int("SST_CHUNK", 1 << 22), 1024);
     const size_t nchunks = div_ceil(nq, chunk);
-    const int NB = 3;  // device-side ring
+    const int NB = kRing;
     Staging& sg = g_staging[dev];
     sg.device = dev;
     if (!staging_ensure(sg, std::min(chunk, nq), out_idx != nullptr)) return SST_ERR_CUDA;
+    // The kernel next to the copies.  At full width the search kernel saturates the DRAM random-access rate for a third of
+    // every chunk period and the copy engines lose ~40 % of their rate meanwhile (2^28 keys, 10^8 queries: copies alone
+    // 8.4-8.7 ms, with the kernel 9.6-10.1 ms).  A kernel that only just keeps up with PCIe runs through the whole period at
+    // low intensity: on a quarter of the SMs per HBM-resident level (37 CTAs at 2^28 keys, ~0.33 Gq/s each = 12.2 Gq/s, the
+    // PCIe ceiling) the call takes 8.7-9.2 ms on four of five boxes measured, 9.7 on the fifth (profiles/r1_s3_e2e_*.log).
+    // Narrower is kernel-bound (30 CTAs: 10.3 ms), so the rule errs on the wide side: a level counts as HBM-resident as soon
+    // as the levels down to it outgrow L2.  A feedback controller on the kernel stream's utilisation was tried and dropped:
+    // the timing events and the per-chunk host wait it needs cost more (1.0-1.2 ms) than the pacing gains.
+    // SST_HOST_GRID_CAP: 0 = this rule, < 0 = full width, > 0 = CTAs.
+    struct CapGuard { ~CapGuard() { g_host_grid_cap = 0; } } cap_guard;
+    {
+        int cap = env_int("SST_HOST_GRID_CAP", 0);
+        if (cap == 0 && idx->variant == SST_PLAIN && idx->node_b == 16 && nchunks >= 3) {  // (fewer chunks: nothing to overlap with)
+            int l2 = 0;
+            cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev);
+            size_t cum = 0;
+            int hbm_levels = 0;
+            for (int h = 0; h < idx->levels; h++) {
+                cum += (size_t)idx->layer_blocks[h] * 64;
+                if (cum > (size_t)l2) hbm_levels++;
+            }
+            cap = hbm_levels ? sm_count(dev) / 4 * hbm_levels : 0;
+        }
+        g_host_grid_cap = cap > 0 ? cap : 0;
+    }
     int rc = SST_OK;
     for (size_t c = 0; c < nchunks && rc == SST_OK; c++) {
         const int b = (int)(c % NB);
@@ -973,7 +1006,7 @@ int sst_query(const sst_index_t* idx, const uint32_t* qs, size_t nq, uint32_t* o
         if (c >= (size_t)NB && !SST_CUDA_OK(cudaStreamWaitEvent(s_in, sg.e_out[b], 0))) { rc = SST_ERR_CUDA; break; }
         if (!SST_CUDA_OK(cudaMemcpyAsync(sg.q[b], qs + off, cnt * 4, cudaMemcpyHostToDevice, s_in)) ||
             !SST_CUDA_OK(cudaEventRecord(sg.e_in[b], s_in)) || !SST_CUDA_OK(cudaStreamWaitEvent(s_k, sg.e_in[b], 0))) { rc = SST_ERR_CUDA; break; }
-        rc = launch_query(idx, sg.q[b], cnt, sg.v[b], out_idx ? sg.i[b] : nullptr, scheme, s_k);
+        rc = env_int("SST_E2E_NO_KERNEL", 0) ? SST_OK : launch_query(idx, sg.q[b], cnt, sg.v[b], out_idx ? sg.i[b] : nullptr, scheme, s_k);  // (debug: copies only)
         if (rc != SST_OK) break;
         if (!SST_CUDA_OK(cudaEventRecord(sg.e_k[b], s_k)) || !SST_CUDA_OK(cudaStreamWaitEvent(s_out, sg.e_k[b], 0)) ||
             !SST_CUDA_OK(cudaMemcpyAsync(out_vals + off, sg.v[b], cnt * 4, cudaMemcpyDeviceToHost, s_out)) ||

@@ -24,6 +24,6 @@ for var in sys.argv[1:] or ["SST_CHUNK=4194304"]:
     best = 1e9
     for _ in range(5):
         t0 = time.perf_counter(); step(); best = min(best, time.perf_counter() - t0)
-    ok = bool((hv.to(dev) == want).all())
+    ok = bool((hv.to(dev) == want).all()) if "NO_KERNEL" not in var else None
     print(json.dumps({"var": var, "ms": round(best * 1e3, 3), "gqps": round(nq / best / 1e9, 2), "ok": ok}), flush=True)
     for k in kv: os.environ.pop(k)
