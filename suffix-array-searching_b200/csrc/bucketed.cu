@@ -893,8 +893,11 @@ void launch_rank(const BkView& v, int sms, size_t smem, cudaStream_t st, const u
         kern<<<grid, kThreads, smem, st>>>(v, qs, nq, ntiles, counts, lpos, tot);                   \
     }
     // claim : ballot ratio measured at 10 bits (rank stage, ms per 10^8 queries): ballots only 0.494, 1:2 0.472, 1:1 0.452,
-    // 2:1 0.446, 3:1 0.442 -> three claim steps per ballot step
-    if (hyb != 0) SST_BK_LAUNCH_RANK(4)
+    // 2:1 0.446, 3:1 0.442 (before the packed bucket table)
+    // With the packed bucket table (one shared load less per query) the shared-memory pipe has room for more claims: 1:1 0.452,
+    // 3:1 0.431, 7:1 0.419, 31:1 0.412 ms -> claims on every step but the first (SST_BK_HYBRID=4: 3:1, =0: ballots only)
+    if (hyb == 4 && BITS == 10) SST_BK_LAUNCH_RANK(4)
+    else if (hyb != 0) SST_BK_LAUNCH_RANK(32)
     else SST_BK_LAUNCH_RANK(0)
 #undef SST_BK_LAUNCH_RANK
 }
