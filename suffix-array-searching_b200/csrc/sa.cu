@@ -47,6 +47,12 @@ struct sst_sa {
     // string_value (util.rs:76-117).  GPU-only auxiliary.
     uint32_t* d_kmer = nullptr;
     int kmer_k = 0;
+    // Inlined bases (with the k-mer table only): sax[i] = {sa[i], nx[i]}, nx = the 15 bases that follow the first k of
+    // suffix(sa[i]) packed 2 bits each, first base most significant (string_value order, util.rs:76-117), bit 31 set when the
+    // suffix has all of them.  Inside a k-mer cell every suffix shares the first k bases with the pattern, so a probe whose
+    // next 15 bases differ from the pattern's is decided without touching the text: one sector instead of two or three
+    // fills.  The reference has the idea as a TODO ("Inlining values", todo.org:18-19; btree_legacy.rs:4-131).  GPU-only auxiliary.
+    uint2* d_sax = nullptr;
 };
 
 namespace sst {
@@ -206,6 +212,7 @@ struct SaParams {
     int coarse_levels;
     const uint32_t* kmer;  // k-mer table (or null)
     int kmer_k;
+    const uint2* sax;      // {sa, next 15 bases} entries (or null)
 };
 
 // Compares suffix(spos) with the pattern from byte `start` on.  Returns lcp (group-uniform) and
@@ -364,6 +371,12 @@ __device__ __forceinline__ unsigned first_mismatch16(const W4& t, const W4& q, u
     return x ? 4u * wi + (sh >> 3) : 16u;
 }
 
+// Four bases (one per byte, values 0..3, first byte first) -> 8 bits, first base most significant: the four 2-bit fields
+// land in bits 24..31 of the product without overlapping any cross term.
+__device__ __forceinline__ uint32_t pack4(uint32_t w) { return ((w & 0x03030303u) * 0x40100401u) >> 24; }
+// 16 bases of a window -> 32 bits, first base most significant (string_value order, util.rs:76-117)
+__device__ __forceinline__ uint32_t pack16(const W4& w) { return (pack4(w.w[0]) << 24) | (pack4(w.w[1]) << 16) | (pack4(w.w[2]) << 8) | pack4(w.w[3]); }
+
 // suffix(spos) vs pattern from byte `start` (a multiple of 16) on; returns lcp, sets less.
 __device__ __forceinline__ uint32_t thread_compare(const SaParams& p, unsigned long long spos, const W4& p0, const W4& p1,
                                                    const uint8_t* pat, uint32_t ql, uint32_t start, bool& less) {
@@ -434,6 +447,38 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
                 }
             }
         }
+        // ---- inlined bases: inside the k-mer cell a probe reads {sa[m], the 15 bases after the first k} and goes to the text
+        // only when those 15 bases equal the pattern's (the suffix that matches, if any) ----
+        bool inl = false;
+        uint32_t pq = 0;  // the pattern's bases k .. k+14
+        if (have_range && p.sax && ql >= (uint32_t)p.kmer_k + 15u) {
+            uint32_t bad = 0;  // a byte outside the alphabet among the first min(ql, 32) bytes: no inline compare for this pattern
+#pragma unroll
+            for (int wi = 0; wi < 8; wi++) {
+                const uint32_t w = wi < 4 ? p0.w[wi] : p1.w[wi - 4];
+                const uint32_t have = ql >= 4u * wi + 4u ? 0xffffffffu : ql <= 4u * wi ? 0u : (1u << (8u * (ql - 4u * wi))) - 1u;
+                bad |= w & 0xfcfcfcfcu & have;
+            }
+            const unsigned long long code = ((unsigned long long)pack16(p0) << 32) | pack16(p1);  // bases 0..31
+            pq = (uint32_t)(code >> (2 * (32 - p.kmer_k - 15))) & 0x3fffffffu;
+            inl = bad == 0u;
+        }
+        // suffix(sa[m]) vs the pattern: lcp and order, through the inlined bases where they decide
+        auto probe = [&](uint32_t m, uint32_t start, bool& less) -> uint32_t {
+            if (inl) {
+                const uint2 e = __ldg(p.sax + m);
+                const uint32_t code = e.y & 0x3fffffffu;
+                if (e.y >> 31) {  // the suffix has all 15 bases
+                    if (code != pq) {
+                        less = code < pq;
+                        return (uint32_t)p.kmer_k + (((uint32_t)__clz((int)(code ^ pq)) - 2u) >> 1);
+                    }
+                    return thread_compare(p, e.x, p0, p1, pat, ql, start > 16u ? start : 16u, less);  // first k + 15 >= 16 bytes are equal
+                }
+                return thread_compare(p, e.x, p0, p1, pat, ql, start, less);
+            }
+            return thread_compare(p, __ldg(p.sa + m), p0, p1, pat, ql, start, less);
+        };
         // ---- table levels: one 16-byte load per probe ----
         if (!have_range) {
             const uint32_t c = ql < 16u ? ql : 16u;
@@ -476,12 +521,12 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
             const uint32_t m = l + ((r - l) >> 1);
             const uint32_t start = MLR ? ((lcp_l < lcp_r ? lcp_l : lcp_r) & ~15u) : 0u;
             bool less;
-            const uint32_t lcp = thread_compare(p, __ldg(p.sa + m), p0, p1, pat, ql, start, less);
+            const uint32_t lcp = probe(m, start, less);
             if (less) { l = m + 1; lcp_l = lcp; } else { r = m; lcp_r = lcp; lcp_r_exact = true; }
         }
         const unsigned long long lo = l;
         p.out_lo[i] = (uint32_t)lo;
-        if (p.out_pos) p.out_pos[i] = lo < p.n ? __ldg(p.sa + lo) : 0xffffffffu;
+        if (p.out_pos) p.out_pos[i] = lo < p.n ? (inl ? __ldg(p.sax + lo).x : __ldg(p.sa + lo)) : 0xffffffffu;  // (inl: the line the probes read)
         if (p.out_hi) {
             // Suffixes starting with q are contiguous from lo: gallop to bracket the end, then bisect.
             unsigned long long a = lo, b = range_end, step = 1;
@@ -494,13 +539,13 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
                 const unsigned long long pr = a + step - 1;
                 if (pr >= b) break;
                 bool less;
-                const uint32_t lcp = thread_compare(p, __ldg(p.sa + pr), p0, p1, pat, ql, 0u, less);
+                const uint32_t lcp = probe((uint32_t)pr, 0u, less);
                 if (lcp >= ql) { a = pr + 1; step <<= 1; } else { b = pr; break; }
             }
             while (a < b) {
                 const unsigned long long m = (a + b) >> 1;
                 bool less;
-                const uint32_t lcp = thread_compare(p, __ldg(p.sa + m), p0, p1, pat, ql, 0u, less);
+                const uint32_t lcp = probe((uint32_t)m, 0u, less);
                 if (lcp >= ql) a = m + 1; else b = m;
             }
             p.out_hi[i] = (uint32_t)a;
@@ -578,6 +623,7 @@ void launch_search(const SaParams& p, int mode, cudaStream_t st, int device) {
 using namespace sst;
 
 static bool build_kmer(sst_sa* s);  // defined after sa_search_launch, which it uses to fill the table
+static bool build_sax(sst_sa* s);
 
 extern "C" {
 
@@ -595,8 +641,8 @@ sst_sa_t* sst_sa_build_device(const uint8_t* d_text, size_t n, int device) {
     cudaStream_t st = thread_stream(device);
     ok = ok && SST_CUDA_OK(cudaMemsetAsync(s->d_text + n, 0, 64, st)) &&
          SST_CUDA_OK(cudaMemcpyAsync(s->d_text, d_text, n, cudaMemcpyDeviceToDevice, st));
-    ok = ok && build_sa_device(s->d_text, n, s->d_sa, device) && build_pivots(s) && build_kmer(s);
-    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); delete s; return nullptr; }
+    ok = ok && build_sa_device(s->d_text, n, s->d_sa, device) && build_pivots(s) && build_kmer(s) && build_sax(s);
+    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); cudaFree(s->d_sax); delete s; return nullptr; }
     return s;
 }
 
@@ -629,8 +675,8 @@ sst_sa_t* sst_sa_from_parts(const uint8_t* text, size_t n, const uint32_t* sa, i
     bool ok = SST_CUDA_OK(cudaMalloc(&s->d_text, n + 64)) && SST_CUDA_OK(cudaMalloc(&s->d_sa, n * 4)) &&
               SST_CUDA_OK(cudaMemsetAsync(s->d_text + n, 0, 64, st)) && SST_CUDA_OK(cudaMemcpyAsync(s->d_text, text, n, cudaMemcpyHostToDevice, st)) &&
               SST_CUDA_OK(cudaMemcpyAsync(s->d_sa, sa, n * 4, cudaMemcpyHostToDevice, st)) && SST_CUDA_OK(cudaStreamSynchronize(st));
-    ok = ok && build_pivots(s) && build_kmer(s);
-    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); delete s; return nullptr; }
+    ok = ok && build_pivots(s) && build_kmer(s) && build_sax(s);
+    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); cudaFree(s->d_sax); delete s; return nullptr; }
     return s;
 }
 
@@ -641,6 +687,7 @@ void sst_sa_free(sst_sa_t* s) {
     cudaFree(s->d_sa);
     cudaFree(s->d_pivots);
     cudaFree(s->d_kmer);
+    cudaFree(s->d_sax);
     delete s;
 }
 
@@ -724,6 +771,7 @@ static int sa_search_launch(const sst_sa_t* s, const uint8_t* d_pats, const uint
     p.pivot_levels = s->d_pivots ? std::min(s->pivot_levels, env_int("SST_SA_USE_LEVELS", 64)) : 0;
     p.kmer = s->d_kmer;
     p.kmer_k = s->d_kmer && env_int("SST_SA_USE_KMER", 1) ? s->kmer_k : 0;
+    p.sax = p.kmer_k && env_int("SST_SA_USE_INLINE", 1) ? s->d_sax : nullptr;
     const int lanes = env_int("SST_SA_LANES", 1);
     if (lanes <= 1) {
         const unsigned grid = (unsigned)std::min<unsigned long long>((npat + kThreads - 1) / kThreads, (unsigned long long)sm_count(s->device) * 8);
@@ -791,6 +839,36 @@ __global__ void kmer_patterns_kernel(unsigned long long x0, unsigned count, int 
 }
 }  // namespace
 }  // namespace sst
+
+// sax[i] = {sa[i], the 15 bases after the first k of suffix(sa[i]) | complete << 31}
+namespace sst {
+namespace {
+__global__ void sax_kernel(const uint8_t* __restrict__ t, const uint32_t* __restrict__ sa, unsigned long long n, int k, uint2* __restrict__ sax) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t pos = sa[i];
+        const unsigned long long q = (unsigned long long)pos + (unsigned)k;
+        uint32_t nx = 0;
+        if (q + 15ull <= n) {  // (the text is followed by 64 zero bytes: the 16-byte window may run into them)
+            const W4 w = load16_unaligned<false>(t + q, t + n + 64);
+            nx = 0x80000000u | (pack16(w) >> 2);  // 16 bases packed, the last one dropped
+        }
+        sax[i] = make_uint2(pos, nx);
+    }
+}
+}  // namespace
+}  // namespace sst
+
+static bool build_sax(sst_sa* s) {
+    if (!s->kmer_k || !env_int("SST_SA_INLINE", 1)) return true;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (s->n * 8ull > free_b / 3) return true;  // an optional accelerator: never at the cost of the caller's memory
+    if (!SST_CUDA_OK(cudaMalloc(&s->d_sax, s->n * sizeof(uint2)))) { s->d_sax = nullptr; (void)cudaGetLastError(); return true; }
+    cudaStream_t st = thread_stream(s->device);
+    sax_kernel<<<sm_count(s->device) * 16, 256, 0, st>>>(s->d_text, s->d_sa, s->n, s->kmer_k, s->d_sax);
+    if (!SST_CUDA_OK(cudaGetLastError()) || !SST_CUDA_OK(cudaStreamSynchronize(st))) { cudaFree(s->d_sax); s->d_sax = nullptr; return false; }
+    return true;
+}
 
 static bool build_kmer(sst_sa* s) {
     if (!env_int("SST_SA_KMER", 1) || s->n < 4096) return true;

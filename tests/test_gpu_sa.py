@@ -172,7 +172,17 @@ def test_sa_search_kmer_table(gpu, oracle, n, k, monkeypatch):
     pats += [tail[-j:] for j in range(1, 40)] + [tail[-j:] + b"\x00" * z for j in (1, 3, 9) for z in (1, 2, 7)]
     pats += [b"", bytes([0]), bytes([3]), bytes([3] * 64), bytes([0] * 64), bytes([4]), bytes([1, 2, 200, 3]), bytes([255] * 3),
              bytes([3] * 3) + bytes([4]), tail[:150], bytes([0, 1, 2, 3] * 4)]
+    # inlined bases ({sa, the 15 bases after the first k}): patterns with a byte outside the alphabet after the first k
+    # (no inline compare for them), patterns of exactly k + 14 / k + 15 / k + 16 bases, long matches (equal codes -> text)
+    head = text.tobytes()
+    for at in (10, 17, 25, 31, 40):
+        pats += [head[100:100 + at] + bytes([7]) + head[101 + at:160], head[3000:3000 + at] + bytes([4])]
+    for ln in range(16, 36):
+        pats += [head[700:700 + ln], head[701:701 + ln - 1] + bytes([(head[701 + ln - 1] + 1) & 3])]
     _check_search(sst, oracle, s, text, sa, pats)
+    monkeypatch.setenv("SST_SA_USE_INLINE", "0")  # k-mer table, probes on the text
+    _check_search(sst, oracle, s, text, sa, pats[:3000] + pats[-60:])
+    monkeypatch.delenv("SST_SA_USE_INLINE")
     # the same through the pivot table only
     monkeypatch.setenv("SST_SA_USE_KMER", "0")
     _check_search(sst, oracle, s, text, sa, pats[:2000])
