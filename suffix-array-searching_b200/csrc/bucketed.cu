@@ -814,6 +814,25 @@ __global__ void bk_above_kernel(const unsigned* __restrict__ flag, const uint32_
         }
 }
 
+// Simple / L1 / Overlapping: position in the flat leaf level -> index in the sorted array, as the layouts' own kernels
+// report it (stree_search.cu): the keys of part p start at slot part_pos[p] and are part_start[p] .. part_start[p+1] - 1.
+__global__ void bk_flat_index_kernel(const uint32_t* __restrict__ qs, size_t nq, unsigned long long* __restrict__ idx, unsigned shift,
+                                     unsigned long long parts, const uint32_t* __restrict__ part_start,
+                                     const unsigned long long* __restrict__ part_pos, unsigned long long n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t q = qs[i];
+        const unsigned long long part = (unsigned long long)(q >> shift);
+        unsigned long long index = n;
+        if (part < parts) {
+            const unsigned long long pos = idx[i], st = part_start[part], cnt = part_start[part + 1] - st, pp = part_pos[part];
+            const unsigned long long off = pos > pp ? pos - pp : 0;
+            index = st + (off < cnt ? off : cnt);
+            if (index > n) index = n;
+        }
+        idx[i] = index;
+    }
+}
+
 int env_int(const char* name, int dflt) {
     const char* s = getenv(name);
     return (s && *s) ? atoi(s) : dflt;
@@ -938,14 +957,19 @@ void free_bucket_aux(sst_index* idx) {
 bool build_bucket_aux(sst_index* idx) {
     // plain B=16 trees, and the Map-partitioned layout: its leaf level is the sorted array itself, without per-part gaps
     // (partitioned_s_tree.rs:503), which is all the pipeline reads of an image
-    if ((idx->variant != SST_PLAIN && idx->variant != SST_MAP) || idx->node_b != 16) return true;
+    // Simple / L1 / Overlapping: their leaf level is ONE non-decreasing flat array too -- the slots between two parts hold the
+    // first key of the next non-empty part (:502-515), the tail MAX -- so the lower bound in it has the right value; its
+    // position is turned into the sorted-array index afterwards (bk_flat_index_kernel).  Compact interleaves the parts' levels.
+    if (idx->variant == SST_COMPACT || idx->variant == SST_EYTZINGER || idx->node_b != 16) return true;
     if (idx->n < (size_t)env_int("SST_BK_MIN_N", 1 << 22)) return true;  // small trees are L2-resident: nothing to gain
+    const bool flat_parts = idx->variant == SST_SIMPLE || idx->variant == SST_L1 || idx->variant == SST_OVERLAPPING;
+    const size_t n_flat = flat_parts ? (size_t)idx->layer_blocks[idx->levels - 1] * 16 : idx->n;
     // separators per bucket: 16384 (two search CTAs per SM) up to 2^27 keys, 32768 (one 1024-thread CTA) above, so that the
     // partition has at most 1024 buckets up to 2^28 keys -- fewer buckets = longer runs and fewer ballot bits
     // keys per separator: 8 (one leaf sector per query) up to 2^29 keys, 16 (a whole node) up to 2^30
-    unsigned g = (unsigned)env_int("SST_BK_G", div_ceil(idx->n, (size_t)8) > 32768ull * 2048ull ? 16 : 8);
+    unsigned g = (unsigned)env_int("SST_BK_G", div_ceil(n_flat, (size_t)8) > 32768ull * 2048ull ? 16 : 8);
     if (g != 8 && g != 16) g = 8;
-    const unsigned long long m8 = div_ceil(idx->n, (size_t)g);
+    const unsigned long long m8 = div_ceil(n_flat, (size_t)g);
     unsigned r = (unsigned)env_int("SST_BK_R", m8 > 16384ull * 1024ull ? 32768 : 16384);
     if (r < 64 || r > 32768 || (r & (r - 1))) r = 16384;
     const unsigned long long nb64 = div_ceil((size_t)m8, (size_t)r);
@@ -969,7 +993,7 @@ bool build_bucket_aux(sst_index* idx) {
         ok = SST_CUDA_OK(cudaGetLastError()) && SST_CUDA_OK(cudaStreamSynchronize(st));
     }
     if (!ok) { free_bucket_aux(idx); return false; }
-    a.nb = nb; a.nbp = nbp; a.r = r; a.bits = bits; a.m8 = m8; a.g = g;
+    a.nb = nb; a.nbp = nbp; a.r = r; a.bits = bits; a.m8 = m8; a.g = g; a.n_flat = n_flat;
     return true;
 }
 
@@ -996,7 +1020,8 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
     if (!SST_CUDA_OK(cudaStreamWaitEvent(st, s.done, 0))) return SST_ERR_CUDA;  // scratch reuse across this thread's streams
     const int sms = sm_count(dev);
     const unsigned bpt = a.nbp / kThreads;
-    const bool map_tree = idx->variant == SST_MAP;
+    const bool flat_parts = idx->variant == SST_SIMPLE || idx->variant == SST_L1 || idx->variant == SST_OVERLAPPING;
+    const bool map_tree = idx->variant == SST_MAP || flat_parts;  // partitioned: a query above MAX has no part -> (MAX, n)
     BkView v{a.d_bt, a.d_split, a.nb, a.nbp, bpt, map_tree ? s.ctrl + 3 : nullptr};
     if (map_tree && !SST_CUDA_OK(cudaMemsetAsync(s.ctrl + 3, 0, 4, st))) return SST_ERR_CUDA;
     const size_t smem_rank = (size_t)kWarps * a.nbp * 2 + (size_t)kBtCells * 4;
@@ -1007,7 +1032,7 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
     // queries per search work item: every item stages its bucket (r * 6 bytes) again, so larger is cheaper, but a bucket
     // should still split into a few items for load balance
     const unsigned chunk = (unsigned)std::max(env_int("SST_BK_CHUNK", 32768), (int)kMinChunk);
-    BkSearchParams sp{a.d_sep, a.d_jump, a.d_meta, idx->d_tree + idx->offsets[idx->levels - 1] * 16, a.r, a.m8, (unsigned long long)idx->n};
+    BkSearchParams sp{a.d_sep, a.d_jump, a.d_meta, idx->d_tree + idx->offsets[idx->levels - 1] * 16, a.r, a.m8, a.n_flat};
     // SST_BK_TIMING=1 (debug): per-stage CUDA-event times on stderr; synchronises the stream
     const bool timing = env_int("SST_BK_TIMING", 0) != 0;
     cudaEvent_t ev[8] = {};
@@ -1053,6 +1078,9 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
         mark();
         launch_move<true, uint32_t>(sms, smem_move, st, s, a.nbp, ntiles, cnt, s.rb, d_vals + off);
         if (d_idx) launch_move<true, unsigned long long>(sms, smem_move, st, s, a.nbp, ntiles, cnt, s.ib, d_idx + off);
+        if (flat_parts && d_idx)
+            bk_flat_index_kernel<<<sms * 8, 256, 0, st>>>(qs, cnt, d_idx + off, (unsigned)idx->shift, (unsigned long long)idx->parts, idx->d_part_start,
+                                                        idx->d_part_pos, (unsigned long long)idx->n);
         if (map_tree) bk_above_kernel<<<sms * 4, 256, 0, st>>>(s.ctrl + 3, qs, cnt, d_vals + off, d_idx ? d_idx + off : nullptr, (unsigned long long)idx->n);
         mark();
         if (timing && nev == 6 && cudaEventSynchronize(ev[5]) == cudaSuccess) {

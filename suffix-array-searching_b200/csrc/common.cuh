@@ -109,6 +109,7 @@ struct BkAux {
     unsigned nb = 0, nbp = 0, r = 0, bits = 0;
     unsigned g = 8;               // keys per separator: 8 (half node) or 16 (node)
     unsigned long long m8 = 0;    // blocks of g keys that hold keys
+    unsigned long long n_flat = 0;  // slots of the sorted array the pipeline searches: n, or the flat leaf level of Simple / L1 / Overlapping
 };
 
 struct sst_index {

@@ -788,7 +788,8 @@ int resolve_scheme(const sst_index* idx, int scheme, size_t nq) {
 int query_launch_count(const sst_index* idx, int scheme, size_t nq, bool want_idx) {
     if (nq == 0) return 0;
     if (resolve_scheme(idx, scheme, nq) != SST_SCHEME_BUCKETED) return 1;
-    return (int)(div_ceil(nq, (size_t)1 << 27) * ((want_idx ? 8 : 7) + (idx->variant == SST_MAP ? 1 : 0)));  // Map: + the q > MAX fix-up
+    return (int)(div_ceil(nq, (size_t)1 << 27) * ((want_idx ? 8 : 7) + (idx->variant == SST_PLAIN ? 0 : 1) +
+                                                   (want_idx && idx->variant != SST_PLAIN && idx->variant != SST_MAP ? 1 : 0)));  // partitioned: + the q > MAX fix-up (+ flat -> sorted index)
 }
 
 int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx,
