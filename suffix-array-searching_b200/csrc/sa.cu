@@ -450,8 +450,9 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
         // ---- inlined bases: inside the k-mer cell a probe reads {sa[m], the 15 bases after the first k} and goes to the text
         // only when those 15 bases equal the pattern's (the suffix that matches, if any) ----
         bool inl = false;
-        uint32_t pq = 0;  // the pattern's bases k .. k+14
-        if (have_range && p.sax && ql >= (uint32_t)p.kmer_k + 15u) {
+        uint32_t pq = 0, pmask = 0;  // the pattern's bases k .. k+14 (those it has), and the mask of the ones it has
+        bool pat_ends = false;       // the pattern ends within those 15 bases: equal bases = the suffix starts with the pattern
+        if (have_range && p.sax && ql >= (uint32_t)p.kmer_k) {
             uint32_t bad = 0;  // a byte outside the alphabet among the first min(ql, 32) bytes: no inline compare for this pattern
 #pragma unroll
             for (int wi = 0; wi < 8; wi++) {
@@ -460,19 +461,23 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
                 bad |= w & 0xfcfcfcfcu & have;
             }
             const unsigned long long code = ((unsigned long long)pack16(p0) << 32) | pack16(p1);  // bases 0..31
-            pq = (uint32_t)(code >> (2 * (32 - p.kmer_k - 15))) & 0x3fffffffu;
+            const uint32_t nb = ql - (uint32_t)p.kmer_k < 15u ? ql - (uint32_t)p.kmer_k : 15u;  // bases of the pattern after the first k
+            pat_ends = nb < 15u;
+            pmask = nb ? (0x3fffffffu >> (2u * (15u - nb))) << (2u * (15u - nb)) : 0u;
+            pq = (uint32_t)(code >> (2 * (32 - p.kmer_k - 15))) & pmask;
             inl = bad == 0u;
         }
         // suffix(sa[m]) vs the pattern: lcp and order, through the inlined bases where they decide
         auto probe = [&](uint32_t m, uint32_t start, bool& less) -> uint32_t {
             if (inl) {
                 const uint2 e = __ldg(p.sax + m);
-                const uint32_t code = e.y & 0x3fffffffu;
                 if (e.y >> 31) {  // the suffix has all 15 bases
+                    const uint32_t code = e.y & pmask;
                     if (code != pq) {
                         less = code < pq;
                         return (uint32_t)p.kmer_k + (((uint32_t)__clz((int)(code ^ pq)) - 2u) >> 1);
                     }
+                    if (pat_ends) { less = false; return ql; }  // every base of the pattern matched: no text access at all
                     return thread_compare(p, e.x, p0, p1, pat, ql, start > 16u ? start : 16u, less);  // first k + 15 >= 16 bytes are equal
                 }
                 return thread_compare(p, e.x, p0, p1, pat, ql, start, less);

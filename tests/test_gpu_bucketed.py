@@ -228,8 +228,9 @@ def test_bucketed_map_skewed_keys(gpu, oracle, monkeypatch):
     """Map tree over keys that do not reach 31 bits / with long duplicate runs, MAX not a key."""
     sst = gpu
     monkeypatch.setenv("SST_BK_MIN_N", "0")
-    monkeypatch.setenv("SST_BK_R", "64")
+    monkeypatch.setenv("SST_BK_R", "256")
     rng = np.random.default_rng(77)
+    served = 0
     for kind, layout in (("dupes", "PartitionedSTree16M"), ("clustered", "PartitionedSTree16M"), ("dupes", "PartitionedSTree16"),
                          ("clustered", "PartitionedSTree16L"), ("tiny_range", "PartitionedSTree16O"), ("boundary16", "PartitionedSTree16")):
         vals = make_keys(rng, 300_000, kind)
@@ -237,8 +238,15 @@ def test_bucketed_map_skewed_keys(gpu, oracle, monkeypatch):
         t = getattr(sst, layout).try_new(vals, 12)
         if t is None:
             continue
+        try:
+            t.query(qs[:8], sst.SCHEME_BUCKETED)
+        except sst.SstError as e:  # padded flat leaf level too large for 2048 buckets of 64 separators
+            assert "reordered-batch" in str(e) or "group/table" in str(e), str(e)
+            continue
+        served += 1
         ev, ei = oracle.lower_bound(vals, qs)
         v, i = t.query(qs, sst.SCHEME_BUCKETED, want_index=True)
         v2, i2 = t.query(qs, want_index=True)
         assert np.array_equal(v, v2) and np.array_equal(i, i2)
         assert np.array_equal(v, ev) and np.array_equal(i, ei)
+    assert served >= 3
