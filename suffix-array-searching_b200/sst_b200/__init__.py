@@ -30,7 +30,7 @@ SA_BINARY, SA_MLR = 0, 1
 ERR_CUDA, ERR_ARG, ERR_CAPACITY, ERR_UNSUPPORTED = 1, 2, 3, 4
 
 _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG_DIR, "libsst_b200.so")
+LIB_PATH = os.environ.get("SST_B200_LIB") or os.path.join(_PKG_DIR, "libsst_b200.so")  # (SST_B200_LIB: A/B runs of a differently compiled library)
 
 
 class SstError(RuntimeError):
