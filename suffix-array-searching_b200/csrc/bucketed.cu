@@ -5,25 +5,27 @@
 // batches over LARGE trees.  The reference keeps 128 independent queries in flight and lets each one
 // miss the cache once per level (s_tree.rs:303-326); on B200 that design is bound by the number of
 // random DRAM accesses per second (~43 G/s), one per query for the leaf level.
-// Here the batch is first reordered so that all queries that fall into the same 512 KB window of the
+// Here the batch is first reordered so that all queries that fall into the same 0.5-2 MB window of the
 // leaf level are answered together by one CTA:
 //
-//   rank    (bk_rank_kernel)    per 16384-query tile: bucket id per query (table over the top 12 key bits +
-//                               splitter scan), stable rank inside the tile by per-warp counters and
-//                               ballot-matching (no atomics), tile x bucket counts, 16-bit local position
+//   rank    (bk_rank_kernel)    per 16384-query tile: bucket id per query (ONE shared load: a table over the top 13 key bits
+//                               that packs the bucket count, a flag and the next splitter's low bits), rank inside the tile
+//                               by per-warp counters with claim / ballot steps (no atomics), tile x bucket counts, 16-bit
+//                               local position
 //   plan    (bk_colsum/plan/offsets) exclusive scan of the count matrix -> global offset of every
-//                               (tile, bucket) run, bucket starts, work items (bucket, 16384-query chunk)
-//   scatter (bk_move_kernel<0>) tile -> shared memory in bucket order -> coalesced runs in HBM
-//   search  (bk_search_kernel)  per work item: the bucket's separators (last key of every 8-key half
-//                               node, 64 KB) and its jump table (16 KB) are staged into shared memory
-//                               by 1-D TMA bulk copies; a query is ranked among them with 2 + ~2 shared
-//                               loads and finished with ONE 32-byte leaf load (8 keys, LDG.256)
+//                               (tile, bucket) run, bucket starts, work items (bucket, 32768-query chunk)
+//   scatter (bk_move_kernel<0>) tile -> shared memory in bucket order -> coalesced runs in HBM (next tile prefetched)
+//   search  (bk_search_kernel)  per work item: the bucket's separators (last key of every 8-key half node, or of
+//                               every node above 2^29 keys: 64-128 KB) and its jump table (32-64 KB) are staged into
+//                               shared memory by 1-D TMA bulk copies; a query is ranked among them with 2 + ~0.5
+//                               shared loads (predicated probes) and finished with ONE 32-byte leaf load (LDG.256)
 //   gather  (bk_move_kernel<1>) results back into the caller's order through shared memory
 //
 // DRAM traffic per 10^8 queries over 2^28 keys: the leaf level once (1 GiB, instead of 6.4-12.8 GB of
 // random sectors), 128 MB of separators, and ~3 GB of query/result/position streams.  The tree image is
 // untouched: the leaf level is read in place and the separators are a GPU-only auxiliary array like
-// the rank table of stree_search.cu.  Plain B = 16 trees (any new_params flags) up to 2^28 keys.
+// the rank table of stree_search.cu.  Served: plain B = 16 trees (any new_params flags) and the Map, Simple, L1 and
+// Overlapping partitioned layouts (their leaf level is one sorted flat array) of 2^22 .. 2^30 leaf slots.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>

@@ -18,6 +18,12 @@
 //     path is bound by the number of independent miss chains in flight, not by compare width.
 // The `mlr` mode carries lcp(q, suffix(l-1)) and lcp(q, suffix(r)) and starts each comparison at
 // their minimum.
+// Texts over {0,1,2,3} (every BASELINE configuration) get two more GPU-only accelerators, used by the
+// thread kernel: a k-mer table (the suffix-array range of every k-base prefix: SaNaive's `table`,
+// sa_search.rs:59-85, which the reference hard-wires to p = 0) that replaces the first ~2k probes by
+// one load and bounds the search for `hi`, and the next 15 bases of every suffix inlined next to its
+// suffix-array entry ("Inlining values", todo.org:18-19), so that a probe inside a k-mer cell touches
+// the text only for the suffix that matches.  Every path returns the same [lo, hi) and sa[lo].
 //
 // Construction: prefix doubling.  Suffixes are ranked by their first 7 symbols (9 bits each,
 // 0 = past the end, so that a proper prefix sorts first exactly as Rust's slice ordering),
