@@ -221,7 +221,6 @@ __device__ __forceinline__ void rank_tile(const BkView& v, const uint32_t* __res
             //  ballots: lanes with the same bucket find each other by ballots over the bucket bits; the lowest of them
             //           bumps the counter by the group size
             // HYBRID = 0: ballots only; k > 0: claim on every step with r % k != 0 (2: every other step); k < 0: claim on r % -k == 0
-            constexpr bool RECLAIM = HYBRID == 33;  // 33 = claims on every step but the first, losers claim again
             const bool claim_step = HYBRID > 0 ? (r % (HYBRID > 0 ? HYBRID : 1)) != 0 : HYBRID < 0 ? (r % (HYBRID < 0 ? -HYBRID : 1)) == 0 : false;
             if (claim_step) {
                 const unsigned w = valid ? cntw[b] : 0u;
@@ -231,21 +230,8 @@ __device__ __forceinline__ void rank_tile(const BkView& v, const uint32_t* __res
                 const bool lost = valid && (unsigned)(cntw[b] >> 11) != lane;
                 unsigned rank = w & 0x7ffu;
                 unsigned peers = __ballot_sync(kFull, lost);
-                bool still = lost;
-                if (RECLAIM && peers && __popc(peers) <= 3) {
-                    // (warp-uniform; 2 in 5 steps have a loser, nearly always one or two): the losers simply claim again -- a
-                    // round settles at least one of them and costs three shared-memory accesses of a few lanes, where the
-                    // ballots below cost ~50 instructions for the whole warp
-                    do {
-                        const unsigned w2 = still ? cntw[b] : 0u;
-                        __syncwarp();
-                        if (still) cntw[b] = (uint16_t)(((w2 & 0x7ffu) + 1u) | (lane << 11));
-                        __syncwarp();
-                        if (still && (unsigned)(cntw[b] >> 11) == lane) { rank = w2 & 0x7ffu; still = false; }
-                        peers = __ballot_sync(kFull, still);
-                    } while (peers);
-                }
-                if (peers) {  // many lanes on one bucket (skewed batch): settle them by ballots, in bounded time
+                if (peers) {  // (warp-uniform, 2 steps in 5) lanes that share a bucket with a winner: settle them by ballots, in bounded time
+                    // (letting the one or two losers claim again instead was measured slower: rank 0.410 -> 0.431 ms, spills)
                     ballot_bits<0, BITS>(peers, b);
                     const unsigned before = peers & lt_mask;
                     const unsigned old = lost ? (cntw[b] & 0x7ffu) : 0u;  // includes the winner's +1
@@ -933,8 +919,7 @@ void launch_rank(const BkView& v, int sms, size_t smem, cudaStream_t st, const u
     // With the packed bucket table (one shared load less per query) the shared-memory pipe has room for more claims: 1:1 0.452,
     // 3:1 0.431, 7:1 0.419, 31:1 0.412 ms -> claims on every step but the first (SST_BK_HYBRID=4: 3:1, =0: ballots only)
     if (hyb == 4 && BITS == 10) SST_BK_LAUNCH_RANK(4)
-    else if (hyb == 32 && BITS == 10) SST_BK_LAUNCH_RANK(32)
-    else if (hyb != 0) SST_BK_LAUNCH_RANK(33)
+    else if (hyb != 0) SST_BK_LAUNCH_RANK(32)
     else SST_BK_LAUNCH_RANK(0)
 #undef SST_BK_LAUNCH_RANK
 }
