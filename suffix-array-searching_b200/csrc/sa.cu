@@ -35,6 +35,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -59,6 +60,9 @@ struct sst_sa {
     // next 15 bases differ from the pattern's is decided without touching the text: one sector instead of two or three
     // fills.  The reference has the idea as a TODO ("Inlining values", todo.org:18-19; btree_legacy.rs:4-131).  GPU-only auxiliary.
     uint2* d_sax = nullptr;
+    // The same with 32 bases per suffix in 16-byte entries {sa, bases present (32 = all), code hi, code lo}, built instead of
+    // d_sax when memory allows (16 bytes per suffix): a pattern of up to k + 32 bases is then answered without the text.
+    uint4* d_saw = nullptr;
 };
 
 namespace sst {
@@ -219,6 +223,7 @@ struct SaParams {
     const uint32_t* kmer;  // k-mer table (or null)
     int kmer_k;
     const uint2* sax;      // {sa, next 15 bases} entries (or null)
+    const uint4* saw;      // {sa, 32, next 32 bases} entries (or null; the WIDE kernels)
 };
 
 // Compares suffix(spos) with the pattern from byte `start` on.  Returns lcp (group-uniform) and
@@ -410,7 +415,7 @@ __device__ __forceinline__ uint32_t thread_compare(const SaParams& p, unsigned l
 // bound reached (a monotone function of the pattern: the sort key) and the pattern's index.  PHASE 2: patterns in the
 // order of `perm`, i.e. sorted by that key: the lanes of a warp then walk (almost) the same path, so their table and
 // suffix-array loads fall into the same lines instead of 32 different ones.
-template <bool MLR, int PHASE>
+template <bool MLR, int PHASE, bool WIDE = false>
 __global__ void __launch_bounds__(kThreads, SST_SA_MIN_BLOCKS)
 sa_search_thread_kernel(const __grid_constant__ SaParams p) {
     for (unsigned long long slot = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; slot < p.npat;
@@ -456,10 +461,12 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
         // ---- inlined bases: inside the k-mer cell a probe reads {sa[m], the 15 bases after the first k} and goes to the text
         // only when those 15 bases equal the pattern's (the suffix that matches, if any) ----
         bool inl = false;
-        uint32_t pq = 0, pmask = 0;  // the pattern's bases k .. k+14 (those it has), and the mask of the ones it has
-        bool pat_ends = false;       // the pattern ends within those 15 bases: equal bases = the suffix starts with the pattern
-        if (have_range && p.sax && ql >= (uint32_t)p.kmer_k) {
-            uint32_t bad = 0;  // a byte outside the alphabet among the first min(ql, 32) bytes: no inline compare for this pattern
+        using Code = typename std::conditional<WIDE, unsigned long long, uint32_t>::type;
+        constexpr uint32_t NB = WIDE ? 32u : 15u;  // bases inlined per suffix
+        Code pq = 0, pmask = 0;      // the pattern's bases k .. k+NB-1 (those it has), and the mask of the ones it has
+        bool pat_ends = false;       // the pattern ends within those bases: equal bases = the suffix starts with the pattern
+        if (have_range && (WIDE ? (const void*)p.saw : (const void*)p.sax) && ql >= (uint32_t)p.kmer_k) {
+            uint32_t bad = 0;  // a byte outside the alphabet among the first min(ql, 32 or 48) bytes: no inline compare for this pattern
 #pragma unroll
             for (int wi = 0; wi < 8; wi++) {
                 const uint32_t w = wi < 4 ? p0.w[wi] : p1.w[wi - 4];
@@ -467,26 +474,52 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
                 bad |= w & 0xfcfcfcfcu & have;
             }
             const unsigned long long code = ((unsigned long long)pack16(p0) << 32) | pack16(p1);  // bases 0..31
-            const uint32_t nb = ql - (uint32_t)p.kmer_k < 15u ? ql - (uint32_t)p.kmer_k : 15u;  // bases of the pattern after the first k
-            pat_ends = nb < 15u;
-            pmask = nb ? (0x3fffffffu >> (2u * (15u - nb))) << (2u * (15u - nb)) : 0u;
-            pq = (uint32_t)(code >> (2 * (32 - p.kmer_k - 15))) & pmask;
+            const uint32_t nb = ql - (uint32_t)p.kmer_k < NB ? ql - (uint32_t)p.kmer_k : NB;  // bases of the pattern after the first k
+            pat_ends = nb < NB;
+            if constexpr (WIDE) {
+                uint32_t c2 = 0;  // bases 32..47
+                if (ql > 32u) {
+                    const W4 p2 = load16_unaligned<true>(pat + 32, pend);
+#pragma unroll
+                    for (int wi = 0; wi < 4; wi++) {
+                        const uint32_t have = ql >= 36u + 4u * wi ? 0xffffffffu : ql <= 32u + 4u * wi ? 0u : (1u << (8u * (ql - 32u - 4u * wi))) - 1u;
+                        bad |= p2.w[wi] & 0xfcfcfcfcu & have;
+                    }
+                    c2 = pack16(p2);
+                }
+                const unsigned sh = 2u * (unsigned)p.kmer_k;  // <= 32
+                pmask = nb ? ~0ull << (2u * (32u - nb)) : 0ull;
+                pq = ((sh >= 64u ? 0ull : code << sh) | (sh ? (unsigned long long)c2 >> (32u - sh) : 0ull)) & pmask;
+            } else {
+                pmask = nb ? (0x3fffffffu >> (2u * (15u - nb))) << (2u * (15u - nb)) : 0u;
+                pq = (uint32_t)(code >> (2 * (32 - p.kmer_k - 15))) & pmask;
+            }
             inl = bad == 0u;
         }
         // suffix(sa[m]) vs the pattern: lcp and order, through the inlined bases where they decide
         auto probe = [&](uint32_t m, uint32_t start, bool& less) -> uint32_t {
             if (inl) {
-                const uint2 e = __ldg(p.sax + m);
-                if (e.y >> 31) {  // the suffix has all 15 bases
-                    const uint32_t code = e.y & pmask;
+                uint32_t spos;
+                bool complete;
+                Code code;
+                if constexpr (WIDE) {
+                    const uint4 e = __ldg(p.saw + m);
+                    spos = e.x; complete = e.y == 32u; code = (((unsigned long long)e.z << 32) | e.w) & pmask;
+                } else {
+                    const uint2 e = __ldg(p.sax + m);
+                    spos = e.x; complete = (e.y >> 31) != 0u; code = e.y & pmask;
+                }
+                if (complete) {  // the suffix has all the inlined bases
                     if (code != pq) {
                         less = code < pq;
-                        return (uint32_t)p.kmer_k + (((uint32_t)__clz((int)(code ^ pq)) - 2u) >> 1);
+                        if constexpr (WIDE) return (uint32_t)p.kmer_k + ((uint32_t)__clzll((long long)(code ^ pq)) >> 1);
+                        else return (uint32_t)p.kmer_k + (((uint32_t)__clz((int)(code ^ pq)) - 2u) >> 1);
                     }
                     if (pat_ends) { less = false; return ql; }  // every base of the pattern matched: no text access at all
-                    return thread_compare(p, e.x, p0, p1, pat, ql, start > 16u ? start : 16u, less);  // first k + 15 >= 16 bytes are equal
+                    const uint32_t known = ((uint32_t)p.kmer_k + NB) & ~15u;  // bytes known to be equal, rounded down to a window
+                    return thread_compare(p, spos, p0, p1, pat, ql, start > known ? start : known, less);
                 }
-                return thread_compare(p, e.x, p0, p1, pat, ql, start, less);
+                return thread_compare(p, spos, p0, p1, pat, ql, start, less);
             }
             return thread_compare(p, __ldg(p.sa + m), p0, p1, pat, ql, start, less);
         };
@@ -537,7 +570,7 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
         }
         const unsigned long long lo = l;
         p.out_lo[i] = (uint32_t)lo;
-        if (p.out_pos) p.out_pos[i] = lo < p.n ? (inl ? __ldg(p.sax + lo).x : __ldg(p.sa + lo)) : 0xffffffffu;  // (inl: the line the probes read)
+        if (p.out_pos) p.out_pos[i] = lo < p.n ? (inl ? (WIDE ? __ldg(p.saw + lo).x : __ldg(p.sax + lo).x) : __ldg(p.sa + lo)) : 0xffffffffu;  // (inl: the line the probes read)
         if (p.out_hi) {
             // Suffixes starting with q are contiguous from lo: gallop to bracket the end, then bisect.
             unsigned long long a = lo, b = range_end, step = 1;
@@ -653,7 +686,7 @@ sst_sa_t* sst_sa_build_device(const uint8_t* d_text, size_t n, int device) {
     ok = ok && SST_CUDA_OK(cudaMemsetAsync(s->d_text + n, 0, 64, st)) &&
          SST_CUDA_OK(cudaMemcpyAsync(s->d_text, d_text, n, cudaMemcpyDeviceToDevice, st));
     ok = ok && build_sa_device(s->d_text, n, s->d_sa, device) && build_pivots(s) && build_kmer(s) && build_sax(s);
-    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); cudaFree(s->d_sax); delete s; return nullptr; }
+    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); cudaFree(s->d_sax); cudaFree(s->d_saw); delete s; return nullptr; }
     return s;
 }
 
@@ -687,7 +720,7 @@ sst_sa_t* sst_sa_from_parts(const uint8_t* text, size_t n, const uint32_t* sa, i
               SST_CUDA_OK(cudaMemsetAsync(s->d_text + n, 0, 64, st)) && SST_CUDA_OK(cudaMemcpyAsync(s->d_text, text, n, cudaMemcpyHostToDevice, st)) &&
               SST_CUDA_OK(cudaMemcpyAsync(s->d_sa, sa, n * 4, cudaMemcpyHostToDevice, st)) && SST_CUDA_OK(cudaStreamSynchronize(st));
     ok = ok && build_pivots(s) && build_kmer(s) && build_sax(s);
-    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); cudaFree(s->d_sax); delete s; return nullptr; }
+    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); cudaFree(s->d_sax); cudaFree(s->d_saw); delete s; return nullptr; }
     return s;
 }
 
@@ -699,6 +732,7 @@ void sst_sa_free(sst_sa_t* s) {
     cudaFree(s->d_pivots);
     cudaFree(s->d_kmer);
     cudaFree(s->d_sax);
+    cudaFree(s->d_saw);
     delete s;
 }
 
@@ -783,6 +817,7 @@ static int sa_search_launch(const sst_sa_t* s, const uint8_t* d_pats, const uint
     p.kmer = s->d_kmer;
     p.kmer_k = s->d_kmer && env_int("SST_SA_USE_KMER", 1) ? s->kmer_k : 0;
     p.sax = p.kmer_k && env_int("SST_SA_USE_INLINE", 1) ? s->d_sax : nullptr;
+    p.saw = p.kmer_k && env_int("SST_SA_USE_INLINE", 1) ? s->d_saw : nullptr;
     const int lanes = env_int("SST_SA_LANES", 1);
     if (lanes <= 1) {
         const unsigned grid = (unsigned)std::min<unsigned long long>((npat + kThreads - 1) / kThreads, (unsigned long long)sm_count(s->device) * 8);
@@ -813,7 +848,10 @@ static int sa_search_launch(const sst_sa_t* s, const uint8_t* d_pats, const uint
             if (!SST_CUDA_OK(cudaGetLastError()) || !SST_CUDA_OK(cudaEventRecord(sc.done, st))) return SST_ERR_CUDA;
             return SST_OK;
         }
-        if (mode == SST_SA_MLR) sa_search_thread_kernel<true, 0><<<grid, kThreads, 0, st>>>(p);
+        if (p.saw) {
+            if (mode == SST_SA_MLR) sa_search_thread_kernel<true, 0, true><<<grid, kThreads, 0, st>>>(p);
+            else sa_search_thread_kernel<false, 0, true><<<grid, kThreads, 0, st>>>(p);
+        } else if (mode == SST_SA_MLR) sa_search_thread_kernel<true, 0><<<grid, kThreads, 0, st>>>(p);
         else sa_search_thread_kernel<false, 0><<<grid, kThreads, 0, st>>>(p);
         return SST_CUDA_OK(cudaGetLastError()) ? SST_OK : SST_ERR_CUDA;
     }
@@ -866,6 +904,19 @@ __global__ void sax_kernel(const uint8_t* __restrict__ t, const uint32_t* __rest
         sax[i] = make_uint2(pos, nx);
     }
 }
+// saw[i] = {sa[i], bases present (32 = all, else 0), the 32 bases after the first k of suffix(sa[i]) in 64 bits}
+__global__ void saw_kernel(const uint8_t* __restrict__ t, const uint32_t* __restrict__ sa, unsigned long long n, int k, uint4* __restrict__ saw) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t pos = sa[i];
+        const unsigned long long q = (unsigned long long)pos + (unsigned)k;
+        uint4 e = make_uint4(pos, 0u, 0u, 0u);
+        if (q + 32ull <= n) {
+            const W4 w0 = load16_unaligned<false>(t + q, t + n + 64), w1 = load16_unaligned<false>(t + q + 16, t + n + 64);
+            e.y = 32u; e.z = pack16(w0); e.w = pack16(w1);
+        }
+        saw[i] = e;
+    }
+}
 }  // namespace
 }  // namespace sst
 
@@ -873,6 +924,15 @@ static bool build_sax(sst_sa* s) {
     if (!s->kmer_k || !env_int("SST_SA_INLINE", 1)) return true;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
+    cudaStream_t st0 = thread_stream(s->device);
+    // 32 bases per suffix (16-byte entries) when a third of the free memory holds them, else 15 bases (8-byte entries)
+    if (env_int("SST_SA_INLINE", 1) != 15 && s->n * 16ull <= free_b / (size_t)std::max(1, env_int("SST_SA_INLINE_DIV", 3)) && SST_CUDA_OK(cudaMalloc(&s->d_saw, s->n * sizeof(uint4)))) {
+        saw_kernel<<<sm_count(s->device) * 16, 256, 0, st0>>>(s->d_text, s->d_sa, s->n, s->kmer_k, s->d_saw);
+        if (!SST_CUDA_OK(cudaGetLastError()) || !SST_CUDA_OK(cudaStreamSynchronize(st0))) { cudaFree(s->d_saw); s->d_saw = nullptr; return false; }
+        return true;
+    }
+    s->d_saw = nullptr;
+    (void)cudaGetLastError();
     if (s->n * 8ull > free_b / 3) return true;  // an optional accelerator: never at the cost of the caller's memory
     if (!SST_CUDA_OK(cudaMalloc(&s->d_sax, s->n * sizeof(uint2)))) { s->d_sax = nullptr; (void)cudaGetLastError(); return true; }
     cudaStream_t st = thread_stream(s->device);

@@ -151,12 +151,15 @@ def test_sa_search_sorted_order(gpu, oracle, levels, monkeypatch):
     _check_search(sst, oracle, s, text, sa, pats)
 
 
+@pytest.mark.parametrize("inline_bases", ["32", "15"])
 @pytest.mark.parametrize("n,k", [(200_000, "15"), (200_000, "4"), (5000, "15"), (70_000, "7"), (120_000, "force12"), (90_000, "force16")])
-def test_sa_search_kmer_table(gpu, oracle, n, k, monkeypatch):
+def test_sa_search_kmer_table(gpu, oracle, n, k, inline_bases, monkeypatch):
     """Texts over {0,1,2,3} get a k-mer table (kmer[x] = lower bound of the k-base string x): the search starts in
     [kmer[x], kmer[x+1]).  Patterns shorter than k, patterns with a byte outside the alphabet (fall back to the pivot table),
     patterns made of the text's tail (proper prefixes of padded k-mers), absent patterns, the empty pattern."""
     sst = gpu
+    if inline_bases == "15":  # 8-byte {sa, 15 bases} entries (what an index takes when memory is short) instead of 16-byte {sa, 32 bases}
+        monkeypatch.setenv("SST_SA_INLINE", "15")
     if k.startswith("force"):  # deeper than one suffix per cell; 16 = the 3 Gbp configuration's depth (2^32 + 1 cells, 64-bit cell index)
         monkeypatch.setenv("SST_SA_KMER_FORCE", k[5:])
     else:
@@ -177,8 +180,10 @@ def test_sa_search_kmer_table(gpu, oracle, n, k, monkeypatch):
     head = text.tobytes()
     for at in (10, 17, 25, 31, 40):
         pats += [head[100:100 + at] + bytes([7]) + head[101 + at:160], head[3000:3000 + at] + bytes([4])]
-    for ln in range(16, 36):
+    for ln in range(16, 56):
         pats += [head[700:700 + ln], head[701:701 + ln - 1] + bytes([(head[701 + ln - 1] + 1) & 3])]
+    for at in (33, 36, 44, 47, 48, 50):  # a byte outside the alphabet in the third 16-byte window
+        pats += [head[900:900 + at] + bytes([9]) + head[901 + at:970], head[900:900 + at] + bytes([200])]
     _check_search(sst, oracle, s, text, sa, pats)
     monkeypatch.setenv("SST_SA_USE_INLINE", "0")  # k-mer table, probes on the text
     _check_search(sst, oracle, s, text, sa, pats[:3000] + pats[-60:])
