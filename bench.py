@@ -500,11 +500,11 @@ def bench_sa(args, sst, torch, dev):
     out["algorithmic_bytes_per_pattern"] = bpp
     out["roofline_frac_binary"] = out["binary_patterns_per_s"] * bpp / 1e9 / peak
     # The k-mer table (texts over {0,1,2,3}) answers the first ~log4(n) bases with one load, so the probes SURVEY's model
-    # counts are not made and the fraction above can exceed 1.  The floor of THAT path: one sector of the k-mer table, one
-    # suffix-array sector, one unaligned text window (two sectors), the pattern and the two results.
-    kbpp = 32 + 32 + 64 + plen + 8
+    # counts are not made and the fraction above can exceed 1.  The floor of THAT path: one sector of the k-mer table and
+    # the cell's {sa, 32 bases} entries (two sectors; a pattern of up to k + 32 bases needs no text), the pattern and the results.
+    kbpp = 32 + 64 + plen + 8
     out["kmer_path"] = {"bytes_per_pattern": kbpp, "roofline_frac_binary": out["binary_patterns_per_s"] * kbpp / 1e9 / peak,
-                        "note": "floor of the k-mer-table path (4 random sectors + pattern + results); the path is bound by the random-access rate "
+                        "note": "floor of the k-mer-table path (3 random sectors + pattern + results); the path is bound by the random-access rate "
                                 "(~43 G DRAM accesses/s on this part), not by bytes"}
     return out
 
