@@ -415,8 +415,11 @@ __device__ __forceinline__ uint32_t thread_compare(const SaParams& p, unsigned l
 // bound reached (a monotone function of the pattern: the sort key) and the pattern's index.  PHASE 2: patterns in the
 // order of `perm`, i.e. sorted by that key: the lanes of a warp then walk (almost) the same path, so their table and
 // suffix-array loads fall into the same lines instead of 32 different ones.
-template <bool MLR, int PHASE, bool WIDE = false>
-__global__ void __launch_bounds__(kThreads, SST_SA_MIN_BLOCKS)
+// MINB: resident blocks of 256 threads per SM the register budget is set for.  5 (48 registers, a few spills) is best when
+// most patterns go on to the text (more compares in flight: C5 7.7 vs 6.9 Gpat/s), 4 (62 registers, no spills) when the
+// batch is answered from the k-mer cell and the 32-base entries alone (C3 13.0 vs 11.9 Gpat/s).
+template <bool MLR, int PHASE, bool WIDE = false, int MINB = SST_SA_MIN_BLOCKS>
+__global__ void __launch_bounds__(kThreads, MINB)
 sa_search_thread_kernel(const __grid_constant__ SaParams p) {
     for (unsigned long long slot = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; slot < p.npat;
          slot += (unsigned long long)gridDim.x * blockDim.x) {
@@ -849,7 +852,12 @@ static int sa_search_launch(const sst_sa_t* s, const uint8_t* d_pats, const uint
             return SST_OK;
         }
         if (p.saw) {
-            if (mode == SST_SA_MLR) sa_search_thread_kernel<true, 0, true><<<grid, kThreads, 0, st>>>(p);
+            // patterns of up to k + 32 bases never touch the text: a batch of mostly such patterns takes the spill-free build
+            const bool short_pats = env_int("SST_SA_MINB", 0) ? env_int("SST_SA_MINB", 0) == 4 : pats_end <= 48ull * npat;
+            if (short_pats) {
+                if (mode == SST_SA_MLR) sa_search_thread_kernel<true, 0, true, 4><<<grid, kThreads, 0, st>>>(p);
+                else sa_search_thread_kernel<false, 0, true, 4><<<grid, kThreads, 0, st>>>(p);
+            } else if (mode == SST_SA_MLR) sa_search_thread_kernel<true, 0, true><<<grid, kThreads, 0, st>>>(p);
             else sa_search_thread_kernel<false, 0, true><<<grid, kThreads, 0, st>>>(p);
         } else if (mode == SST_SA_MLR) sa_search_thread_kernel<true, 0><<<grid, kThreads, 0, st>>>(p);
         else sa_search_thread_kernel<false, 0><<<grid, kThreads, 0, st>>>(p);
