@@ -290,13 +290,14 @@ def run_own(args):
                            if bucketed else "stree_search_fast"),
                 "kernel_ms": kern_ms, "launches_per_step": res_launches.value}
     if bucketed:  # one extra untimed step with per-stage CUDA events (synchronises between stages, so it is not a bench value)
-        os.environ["SST_BK_TIMING"] = "1"
+        sst.set_option("BK_TIMING", 1)
         step(0)
         torch.cuda.synchronize()
-        os.environ.pop("SST_BK_TIMING", None)
+        sst.set_option("BK_TIMING", 0)
         st_ms = (C.c_double * 5)()
         if L.sst_last_stage_ms(st_ms, 5) == 5:
-            roofline["stage_ms"] = dict(zip(["rank", "plan", "scatter", "search", "gather"], [round(float(x), 4) for x in st_ms]))
+            names = ["rank", "plan", "scatter", "search", "gather"] if sst.get_option("BK_V1") else ["partition", "plan", "-", "search", "unpermute"]
+            roofline["stage_ms"] = {k: round(float(x), 4) for k, x in zip(names, st_ms) if k != "-"}
             tot_st = sum(float(x) for x in st_ms)
             # the dominant kernel of the step and its share (to be compared with the ncu launch list in profiles/)
             roofline["dominant_kernel"] = {"name": "bk_search_kernel", "ms": round(float(st_ms[3]), 4), "share_of_step": round(float(st_ms[3]) / tot_st, 3)}

@@ -65,8 +65,8 @@ enum {
     SST_SCHEME_GENERIC = 4,  /* one thread per query, any layout */
     SST_SCHEME_TABLE = 5,    /* top levels answered by a shared-memory rank table (TMA-staged), rest as GROUP2 */
     SST_SCHEME_BINSEARCH = 6, /* baseline: SortedVec::binary_search (sst/binary_search.rs:36-49) over the leaf level */
-    SST_SCHEME_BUCKETED = 7   /* reordered batch: queries partitioned by key range, each bucket answered from shared memory
-                                 + one leaf sector, results un-permuted (plain B=16 trees of 2^22..2^28 keys, large batches) */
+    SST_SCHEME_BUCKETED = 7   /* reordered batch: every 16384-query tile sorted by key range, each range answered from shared memory
+                                 + one leaf sector per query, in place, answers un-permuted (B=16 trees of 2^22..2^30 keys, large batches) */
 };
 
 /* SA search modes */
@@ -75,6 +75,7 @@ enum { SST_SA_BINARY = 0, SST_SA_MLR = 1 };
 typedef struct sst_index sst_index_t; /* S+-tree / partitioned S+-tree on one device */
 typedef struct sst_sa sst_sa_t;       /* text + suffix array on one device */
 typedef struct sst_multi sst_multi_t; /* replicas of one index on several devices */
+typedef struct sst_multi_sa sst_multi_sa_t; /* replicas of one text + suffix array on several devices */
 
 /* ---- library ------------------------------------------------------------------------------ */
 const char* sst_last_error(void);
@@ -85,6 +86,15 @@ int sst_device_count(void);          /* number of usable sm_100 devices, 0 if no
 void* sst_host_alloc(size_t bytes);
 void sst_host_free(void* p);
 const char* sst_version(void);
+/* Tuning / A-B options (the table in csrc/common.cuh: BK_R, SA_CHUNK, SCHEME, ...).  `name` with or without the SST_
+ * prefix.  Each option starts at its default, or at the value of the environment variable SST_<NAME> read ONCE when the
+ * library is loaded; afterwards only these calls change it (nothing on a query path reads the environment).  A value
+ * outside the option's range is rejected with SST_ERR_ARG.  A change applies to calls and index builds that start after it. */
+int sst_set_option(const char* name, long long value);
+int sst_get_option(const char* name, long long* out_value);
+void sst_reset_options(void);          /* back to the load-time values */
+int sst_option_count(void);
+const char* sst_option_name(int i);    /* NULL when i is out of range */
 /* Binds the calling host thread to the CPUs local to `device` (PCIe/NUMA topology from sysfs), so that the page-locked
  * buffers it allocates afterwards and its copies stay on the GPU's socket.  The reference pins nothing (rayon workers,
  * sst/bin/bench.rs:558-573) because its data never leaves host memory; here every query crosses PCIe once each way.
@@ -141,6 +151,13 @@ int sst_query(const sst_index_t* idx, const uint32_t* qs, size_t nq, uint32_t* o
               int scheme); /* HOST buffers: H2D, kernel, D2H, synchronous */
 int sst_query_device(const sst_index_t* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_out_vals,
                      uint64_t* d_out_idx, int scheme, void* stream); /* DEVICE buffers, asynchronous on `stream` */
+/* Pre-sizes the calling thread's scratch buffers of the reordered-batch pipeline (6-10 bytes per query, at most 2^27 queries'
+ * worth) for batches of up to nq queries on this index, so that later sst_query_device calls from this thread allocate
+ * nothing: they are then asynchronous on `stream` and can be captured into a CUDA graph.  Without it the first large
+ * batch allocates (and synchronises the device) once.  sst_query_release frees the calling thread's scratch on every device
+ * (it is also freed when the thread exits). */
+int sst_query_reserve(const sst_index_t* idx, size_t nq, int want_index);
+void sst_query_release(void);
 /* Number of kernel launches sst_query_device issues for this index/scheme (for launch accounting). */
 int sst_query_launches(const sst_index_t* idx, int scheme);
 /* The kernel SST_SCHEME_AUTO resolves to for a batch of nq queries on this index (*out_scheme; partitioned layouts
@@ -159,6 +176,8 @@ sst_sa_t* sst_sa_from_parts(const uint8_t* text, size_t n, const uint32_t* sa, i
 void sst_sa_free(sst_sa_t* sa);
 size_t sst_sa_len(const sst_sa_t* sa);
 int sst_sa_get(const sst_sa_t* sa, uint32_t* out_sa);                             /* device -> host, n entries */
+/* out_sa[i] = sa[positions[i]] (0xffffffff for a position >= n): e.g. the occurrences sa[lo .. hi) of a pattern. */
+int sst_sa_gather(const sst_sa_t* sa, const uint64_t* positions, size_t count, uint32_t* out_sa);
 /* Number of adjacent suffix pairs violating strict order (sas/sa_search.rs:36-38); 0 == valid. */
 int sst_sa_check(const sst_sa_t* sa, uint64_t* out_violations);
 /* patterns are packed back to back in `pats`; pattern i is pats[pat_off[i] .. pat_off[i+1]).
@@ -169,6 +188,11 @@ int sst_sa_search(const sst_sa_t* sa, const uint8_t* pats, const uint64_t* pat_o
                   uint32_t* out_lo, uint32_t* out_hi, uint32_t* out_pos);
 int sst_sa_search_device(const sst_sa_t* sa, const uint8_t* d_pats, const uint64_t* d_pat_off, size_t npat, int mode,
                          uint32_t* d_out_lo, uint32_t* d_out_hi, uint32_t* d_out_pos, void* stream);
+/* The reference's probe counter (`cnt: &mut usize`, one increment per loop iteration of binary_search, sas/sa_search.rs:98-112,
+ * printed per query by bench, :423-436): runs exactly that loop on the device (plain binary search over [0, n), no table) and
+ * returns out_pos[i] = sa[l] (nullable) and out_probes[i] = its number of iterations.  Host buffers; a tracing aid. */
+int sst_sa_search_probes(const sst_sa_t* sa, const uint8_t* pats, const uint64_t* pat_off, size_t npat, uint32_t* out_pos,
+                         uint32_t* out_probes);
 
 /* ---- input data formats (the callers' side of the path) --------------------------------------
  * sst_fasta_encode: FASTA text -> one byte per base in 0..3, replaces read_fasta_file
@@ -187,15 +211,29 @@ int sst_kmer_keys_device(const uint8_t* d_codes, size_t n, uint32_t k, size_t ma
 
 /* ---- multi-GPU: index replicated per device, query batch sharded contiguously
  *      (chunk = ceil(nq / G), the rule of sst/bin/bench.rs:558-573), one host thread and one
- *      stream per device, no collective. */
+ *      stream per device, no collective.  The host keys are uploaded once; the other replicas receive them
+ *      device to device and run the GPU builder in parallel. */
 sst_multi_t* sst_multi_stree_build(const uint32_t* sorted, size_t n, uint32_t node_b, uint32_t flags,
                                    const int* devices, int n_devices);
 sst_multi_t* sst_multi_pstree_build(const uint32_t* sorted, size_t n, uint32_t b, int variant,
                                     const int* devices, int n_devices);
 int sst_multi_query(const sst_multi_t* m, const uint32_t* qs, size_t nq, uint32_t* out_vals, uint64_t* out_idx,
                     int scheme);
+/* The same with the shards already resident on the replicas' devices: shard i = d_qs[i] (nq[i] queries) with outputs
+ * d_out_vals[i] / d_out_idx[i] (d_out_idx may be NULL) on the device of replica i.  Returns when every shard is done. */
+int sst_multi_query_device(const sst_multi_t* m, const uint32_t* const* d_qs, const size_t* nq, uint32_t* const* d_out_vals,
+                           uint64_t* const* d_out_idx, int scheme);
 int sst_multi_devices(const sst_multi_t* m);
 void sst_multi_free(sst_multi_t* m);
+/* Suffix arrays: text + SA (+ the GPU-only accelerators) replicated per device, the pattern batch sharded contiguously
+ * (chunk = ceil(npat / G)); replaces the serial callers of sas/sa_search.rs:423-451 in the harness shape of
+ * sst/bin/bench.rs:558-573.  The index is built ONCE on devices[0] and copied to the other devices peer to peer. */
+sst_multi_sa_t* sst_multi_sa_build(const uint8_t* text, size_t n, const int* devices, int n_devices);
+sst_multi_sa_t* sst_multi_sa_from_parts(const uint8_t* text, size_t n, const uint32_t* sa, const int* devices, int n_devices);
+int sst_multi_sa_search(const sst_multi_sa_t* m, const uint8_t* pats, const uint64_t* pat_off, size_t npat, int mode,
+                        uint32_t* out_lo, uint32_t* out_hi, uint32_t* out_pos);
+int sst_multi_sa_devices(const sst_multi_sa_t* m);
+void sst_multi_sa_free(sst_multi_sa_t* m);
 
 /* ---- measurement helpers (used by bench.py; not part of the reference surface) ------------ */
 /* Runs sst_query_device `iters` times on an internal stream and returns the mean kernel time in
@@ -205,9 +243,9 @@ double sst_time_query_device(const sst_index_t* idx, const uint32_t* d_qs, size_
 /* Random 64-byte gather probe over `bytes` of device memory: the practical ceiling of the
  * access pattern of one tree level.  Returns GB/s (<0 on error). lanes_per_node in {1,2,4,8,16}. */
 double sst_probe_gather64(int device, size_t bytes, size_t n_gathers, int lanes_per_node, int iters);
-/* With SST_BK_TIMING=1 in the environment the reordered-batch pipeline times its stages with CUDA events (and
- * synchronises the stream); this returns the calling thread's last {rank, plan, scatter, search, gather} times in ms
- * (0 = nothing recorded). */
+/* With the option BK_TIMING = 1 the reordered-batch pipeline times its stages with CUDA events (and synchronises the
+ * stream); this returns the calling thread's last {partition, plan, -, search, un-permute} times in ms (0 = nothing
+ * recorded; with BK_V1 = 1: {rank, plan, scatter, search, gather}). */
 int sst_last_stage_ms(double* out, int n);
 
 #ifdef __cplusplus

@@ -60,6 +60,8 @@ def lib() -> C.CDLL:
         L.orc_tree_search.argtypes = [vp, vp, sz, vp, vp]
         L.orc_stree_batch_final.restype = C.c_double
         L.orc_stree_batch_final.argtypes = [vp, vp, sz, vp, C.c_int]
+        L.orc_stree_batch_interleave.restype = C.c_double
+        L.orc_stree_batch_interleave.argtypes = [vp, vp, sz, vp, C.c_int]
         L.orc_sa_build.restype = None
         L.orc_sa_build.argtypes = [vp, sz, vp]
         L.orc_sa_check.restype = C.c_uint64
@@ -198,6 +200,15 @@ class Tree:
         secs = lib().orc_stree_batch_final(self.h, _p(qs), qs.size, _p(ov), threads)
         if secs < 0:
             raise RuntimeError("batch_final needs a plain B=16 tree")
+        return ov, secs
+
+    def batch_interleave(self, qs, threads=1):
+        """The reference's fastest CPU scheme, batch_interleave_all_128 (s_tree.rs:684-832). Returns (values, seconds)."""
+        qs = _u32(qs)
+        ov = np.empty(qs.size, np.uint32)
+        secs = lib().orc_stree_batch_interleave(self.h, _p(qs), qs.size, _p(ov), threads)
+        if secs < 0:
+            raise RuntimeError("batch_interleave needs a plain B=16 tree of height <= 8")
         return ov, secs
 
 

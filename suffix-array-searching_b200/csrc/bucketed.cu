@@ -176,6 +176,59 @@ __device__ __forceinline__ void ballot_bits(unsigned& peers, unsigned b) {
     }
 }
 
+// Ranks the ITEMS queries every lane of a warp holds (pk[r] = bucket id, 0xffffffff = no query) among the warp's queries of
+// the same bucket, through the warp's private counters cntw[bucket] (count in bits 0..10, claim tag above): on return
+// pk[r] = bucket | rank << 16 and cntw[b] & 0x7ff = the warp's number of queries in bucket b.
+template <int BITS, bool FULL, int HYBRID, int ITEMS>
+__device__ __forceinline__ void rank_items(uint16_t* cntw, uint32_t (&pk)[ITEMS], unsigned lane, unsigned lt_mask) {
+        // rank inside the warp's queries: lanes with the same bucket find each other by ballots over
+            // the bucket bits; the lowest of them bumps the warp's private counter
+    #pragma unroll
+            for (int r = 0; r < ITEMS; r++) {
+                const bool valid = FULL || pk[r] != 0xffffffffu;
+                const unsigned b = valid ? pk[r] : 0u;
+                // Two ways to rank, mixed step by step so that the work is split between the ALU pipe (ballots) and
+                // the shared-memory pipe (claims) -- each alone is bound by its pipe (0.61 / 0.55 ms per 10^8 queries):
+                //  claim:   every lane writes count + 1 tagged with its lane id (5 tag bits above the 11 count bits); the lane
+                //           whose tag sticks takes rank = count; if any lane lost (two queries of one bucket in the same step,
+                //           ~1 step in 5 for uniform queries) the losers are settled by ballots, so the cost stays bounded
+                //           when every query hits the same bucket
+                //  ballots: lanes with the same bucket find each other by ballots over the bucket bits; the lowest of them
+                //           bumps the counter by the group size
+                // HYBRID = 0: ballots only; k > 0: claim on every step with r % k != 0 (2: every other step); k < 0: claim on r % -k == 0
+                const bool claim_step = HYBRID > 0 ? (r % (HYBRID > 0 ? HYBRID : 1)) != 0 : HYBRID < 0 ? (r % (HYBRID < 0 ? -HYBRID : 1)) == 0 : false;
+                if (claim_step) {
+                    const unsigned w = valid ? cntw[b] : 0u;
+                    __syncwarp();
+                    if (valid) cntw[b] = (uint16_t)(((w & 0x7ffu) + 1u) | (lane << 11));
+                    __syncwarp();
+                    const bool lost = valid && (unsigned)(cntw[b] >> 11) != lane;
+                    unsigned rank = w & 0x7ffu;
+                    unsigned peers = __ballot_sync(kFull, lost);
+                    if (peers) {  // (warp-uniform, 2 steps in 5) lanes that share a bucket with a winner: settle them by ballots, in bounded time
+                        // (letting the one or two losers claim again instead was measured slower: rank 0.410 -> 0.431 ms, spills)
+                        ballot_bits<0, BITS>(peers, b);
+                        const unsigned before = peers & lt_mask;
+                        const unsigned old = lost ? (cntw[b] & 0x7ffu) : 0u;  // includes the winner's +1
+                        __syncwarp();
+                        if (lost && before == 0u) cntw[b] = (uint16_t)(old + __popc(peers));
+                        __syncwarp();
+                        if (lost) rank = old + __popc(before);
+                    }
+                    if (valid) pk[r] = b | (rank << 16);
+                } else {
+                    unsigned peers = FULL ? kFull : __ballot_sync(kFull, valid);
+                    ballot_bits<0, BITS>(peers, b);
+                    const unsigned before = peers & lt_mask;
+                    const unsigned old = valid ? (cntw[b] & 0x7ffu) : 0u;
+                    __syncwarp();
+                    if (valid && before == 0u) cntw[b] = (uint16_t)(old + __popc(peers));
+                    __syncwarp();
+                    if (valid) pk[r] = b | ((old + __popc(before)) << 16);
+                }
+            }
+}
+
 // FULL: every tile in [tile_begin, tile_end) holds kTile queries (the partial last tile gets its own launch).
 template <int BITS, bool FULL, int HYBRID>
 __device__ __forceinline__ void rank_tile(const BkView& v, const uint32_t* __restrict__ qs, size_t nq, unsigned tile, uint32_t* __restrict__ counts,
@@ -206,52 +259,7 @@ __device__ __forceinline__ void rank_tile(const BkView& v, const uint32_t* __res
 #pragma unroll
         for (int r = 0; r < kItems; r++)
             pk[r] = (FULL || i0 + r * 32 < tile_n) ? bk_bucket_packed(s_pk, v.bt, v.split, canonical(pk[r])) : 0xffffffffu;
-        // rank inside the warp's 1024 queries: lanes with the same bucket find each other by ballots over
-        // the bucket bits; the lowest of them bumps the warp's private counter
-#pragma unroll
-        for (int r = 0; r < kItems; r++) {
-            const bool valid = FULL || pk[r] != 0xffffffffu;
-            const unsigned b = valid ? pk[r] : 0u;
-            // Two ways to rank, mixed step by step so that the work is split between the ALU pipe (ballots) and
-            // the shared-memory pipe (claims) -- each alone is bound by its pipe (0.61 / 0.55 ms per 10^8 queries):
-            //  claim:   every lane writes count + 1 tagged with its lane id (5 tag bits above the 11 count bits); the lane
-            //           whose tag sticks takes rank = count; if any lane lost (two queries of one bucket in the same step,
-            //           ~1 step in 5 for uniform queries) the losers are settled by ballots, so the cost stays bounded
-            //           when every query hits the same bucket
-            //  ballots: lanes with the same bucket find each other by ballots over the bucket bits; the lowest of them
-            //           bumps the counter by the group size
-            // HYBRID = 0: ballots only; k > 0: claim on every step with r % k != 0 (2: every other step); k < 0: claim on r % -k == 0
-            const bool claim_step = HYBRID > 0 ? (r % (HYBRID > 0 ? HYBRID : 1)) != 0 : HYBRID < 0 ? (r % (HYBRID < 0 ? -HYBRID : 1)) == 0 : false;
-            if (claim_step) {
-                const unsigned w = valid ? cntw[b] : 0u;
-                __syncwarp();
-                if (valid) cntw[b] = (uint16_t)(((w & 0x7ffu) + 1u) | (lane << 11));
-                __syncwarp();
-                const bool lost = valid && (unsigned)(cntw[b] >> 11) != lane;
-                unsigned rank = w & 0x7ffu;
-                unsigned peers = __ballot_sync(kFull, lost);
-                if (peers) {  // (warp-uniform, 2 steps in 5) lanes that share a bucket with a winner: settle them by ballots, in bounded time
-                    // (letting the one or two losers claim again instead was measured slower: rank 0.410 -> 0.431 ms, spills)
-                    ballot_bits<0, BITS>(peers, b);
-                    const unsigned before = peers & lt_mask;
-                    const unsigned old = lost ? (cntw[b] & 0x7ffu) : 0u;  // includes the winner's +1
-                    __syncwarp();
-                    if (lost && before == 0u) cntw[b] = (uint16_t)(old + __popc(peers));
-                    __syncwarp();
-                    if (lost) rank = old + __popc(before);
-                }
-                if (valid) pk[r] = b | (rank << 16);
-            } else {
-                unsigned peers = FULL ? kFull : __ballot_sync(kFull, valid);
-                ballot_bits<0, BITS>(peers, b);
-                const unsigned before = peers & lt_mask;
-                const unsigned old = valid ? (cntw[b] & 0x7ffu) : 0u;
-                __syncwarp();
-                if (valid && before == 0u) cntw[b] = (uint16_t)(old + __popc(peers));
-                __syncwarp();
-                if (valid) pk[r] = b | ((old + __popc(before)) << 16);
-            }
-        }
+        rank_items<BITS, FULL, HYBRID, kItems>(cntw, pk, lane, lt_mask);
         __syncthreads();
         // per bucket: exclusive scan over the warps, total to the count matrix, start inside the tile
         unsigned tot[4] = {0, 0, 0, 0}, sum = 0;
@@ -751,6 +759,531 @@ bk_search_kernel(const BkSearchParams p, const uint32_t* __restrict__ qb, const 
     }
 }
 
+
+// ================================================================================================
+// V2 pipeline: tile-local partition -> plan -> search over runs, in place -> streaming un-permute
+//
+// The round-1 pipeline (above) gathered every bucket into one contiguous array: rank kernel, three plan kernels over the
+// tiles x buckets count matrix, a scatter kernel that read the queries a second time, and a gather kernel that collected
+// ~16-query runs back.  Here a tile is only sorted LOCALLY: the partition kernel reads a tile once (TMA bulk load,
+// prefetched one tile ahead), ranks it, and writes it back as one contiguous 64 KB block in bucket order (TMA bulk store)
+// together with the 16-bit position map and one descriptor {start, count} per (bucket, tile), stored bucket-major.  A
+// bucket is then the list of its ~16-query runs, one per tile, 64 KB apart; the search kernel walks those runs (a warp
+// owns 32 runs at a time: warp scan of the counts, lanes find their run with five shuffles) and overwrites every query
+// with its answer IN PLACE, so the sectors it writes are the ones it has just read.  The last kernel streams each tile's
+// answers back (TMA bulk load, double buffered) and applies the position map in shared memory: all of its global traffic
+// is contiguous.  Per step: the queries are read once, nothing waits on another CTA (no look-back), 5 launches.
+// ================================================================================================
+constexpr int kPThreads = 1024;                // partition / un-permute CTA
+constexpr int kPWarps = kPThreads / 32;
+constexpr int kPItems = kTile / kPThreads;     // 16 queries per thread
+constexpr unsigned kCntPad = 16;               // u16 of padding per counter row of the partition kernel (32 bytes = 8 banks)
+constexpr unsigned kRunShift = 15;             // run descriptor = start | count << 15 (both <= kTile = 2^14: an empty bucket behind the last query starts AT kTile)
+static_assert(kTile < (1 << kRunShift), "run descriptors hold a start of up to kTile in 15 bits");
+
+__device__ __forceinline__ void tma_bulk_s2g(void* dst_gmem, const void* src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+struct PartParams {
+    BkView v;              // bucket lookup tables; v.bpt = buckets per thread of a 1024-thread CTA
+    const uint32_t* qs;    // the caller's queries
+    size_t nq;
+    unsigned ntiles, ntp;  // tiles, and the row pitch of `runs` (tiles rounded up to a multiple of 32)
+    uint32_t* qsort;       // [ntiles * kTile] every tile in bucket order (canonical queries)
+    uint16_t* lpos;        // [nq] position of every query inside its sorted tile
+    uint32_t* runs;        // [nbp][ntp] start | count << 15 of (bucket, tile)
+    uint32_t* tot;         // [nbp] queries per bucket (zeroed before the launch)
+    int tma_ok;            // qs is 16-byte aligned: full tiles move by bulk copies
+};
+
+template <int BITS, int HYBRID>
+__global__ void __launch_bounds__(kPThreads, 1)
+bk_part_kernel(const PartParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t* s_in = reinterpret_cast<uint32_t*>(smem_raw);            // [kTile] landing buffer of the next tile (TMA)
+    uint32_t* s_pk = s_in + kTile;                                      // [kBtCells] packed bucket table
+    uint16_t* cnt = reinterpret_cast<uint16_t*>(s_pk + kBtCells);      // [kPWarps][nbp + 16] per-warp counters (rows padded by 32 bytes) ...
+    uint32_t* s_tile = reinterpret_cast<uint32_t*>(cnt);               // ... reused as the sorted tile [kTile]
+    __shared__ __align__(8) uint64_t bar_in;
+    __shared__ unsigned s_warp[kPWarps + 1];
+    const BkView& v = p.v;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned pitch16 = v.nbp + kCntPad;  // counter row pitch in u16: 32 bytes of padding shift every row by 8 banks (see the scan below)
+    uint16_t* cntw = cnt + (size_t)warp * pitch16;
+    for (unsigned i = tid; i < (unsigned)kBtCells; i += kPThreads) s_pk[i] = bk_pack_cell(v.bt, v.split, v.nb, i);
+    if (tid == 0) {
+        mbar_init(&bar_in, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto full_tile = [&](unsigned t) { return t < p.ntiles && (size_t)(t + 1) * kTile <= p.nq; };
+    auto issue_load = [&](unsigned t) {  // (thread 0) next tile -> s_in
+        if (p.tma_ok && full_tile(t)) {
+            mbar_expect_tx(&bar_in, kTile * 4u);
+            const char* src = reinterpret_cast<const char*>(p.qs + (size_t)t * kTile);
+            tma_bulk_g2s(s_in, src, 32768u, &bar_in);
+            tma_bulk_g2s(reinterpret_cast<char*>(s_in) + 32768, src + 32768, 32768u, &bar_in);
+        }
+    };
+    if (tid == 0) issue_load(blockIdx.x);
+    unsigned phase = 0;
+    unsigned acc_tot[2] = {0, 0};  // this CTA's queries in buckets tid and tid + 1024, over all of its tiles
+    const unsigned i0 = warp * (kPItems * 32) + lane;  // this thread's queries: i0 + 32 r
+    for (unsigned tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const size_t tile_base = (size_t)tile * kTile;
+        const bool full = (size_t)(tile + 1) * kTile <= p.nq;
+        const unsigned tile_n = full ? (unsigned)kTile : (unsigned)(p.nq - tile_base);
+        const bool via_tma = p.tma_ok && full;  // (block-uniform)
+        uint32_t q[kPItems], pk[kPItems];
+        if (via_tma) {
+            mbar_wait(&bar_in, phase);
+            phase ^= 1u;
+#pragma unroll
+            for (int r = 0; r < kPItems; r++) q[r] = s_in[i0 + r * 32];
+        } else {
+#pragma unroll
+            for (int r = 0; r < kPItems; r++) q[r] = i0 + r * 32 < tile_n ? __ldcs(p.qs + tile_base + i0 + r * 32) : 0u;
+        }
+        __syncthreads();  // s_in has been read by everyone
+        if (tid == 0) {
+            issue_load(tile + gridDim.x);  // lands during the ranking below
+            tma_store_wait_read();         // the previous tile's bulk store has read s_tile (= the counters zeroed next)
+        }
+        if (v.above) {  // (uniform) the partitioned layouts answer q > MAX with (MAX, n), not with the signed compare: note it
+            uint32_t acc = 0;
+#pragma unroll
+            for (int r = 0; r < kPItems; r++) acc |= q[r];
+            if (__any_sync(kFull, acc > kMax) && lane == 0) atomicOr(v.above, 1u);
+        }
+#pragma unroll
+        for (int r = 0; r < kPItems; r++) {
+            q[r] = canonical(q[r]);
+            pk[r] = (full || i0 + r * 32 < tile_n) ? bk_bucket_packed(s_pk, v.bt, v.split, q[r]) : 0xffffffffu;
+        }
+        __syncthreads();  // thread 0 has seen the store's reads complete
+        {   // zero the per-warp counters
+            uint4* c4 = reinterpret_cast<uint4*>(cnt);
+            const unsigned n16 = kPWarps * pitch16 / 8;
+            for (unsigned i = tid; i < n16; i += kPThreads) c4[i] = make_uint4(0, 0, 0, 0);
+        }
+        __syncthreads();
+        if (full) rank_items<BITS, true, HYBRID, kPItems>(cntw, pk, lane, lt_mask);
+        else rank_items<BITS, false, HYBRID, kPItems>(cntw, pk, lane, lt_mask);
+        __syncthreads();
+        // Per bucket: exclusive scan of the counters over the warps, the bucket's run {start, count} of this tile, and the
+        // bucket's start folded into the per-warp bases.  Four adjacent lanes share a group of four adjacent buckets (one
+        // 8-byte access = the four 16-bit counters of one warp) and take eight warps each (lane j: warps j, j + 4, ...), so
+        // the 64 KB counter matrix is read twice and written once in 8-byte accesses (it was 4 x 32 two-byte accesses per
+        // thread).  Rows are padded by 32 bytes: the four lanes of a group then hit banks 8 apart and a half-warp's sixteen
+        // 8-byte accesses cover all 32 banks once (unpadded rows put the four lanes on the same banks: measured +7 %).
+        {
+            const unsigned j = tid & 3u, pitch = pitch16 / 4;  // quarter of the warps; row pitch in uint2
+            unsigned tot_k[2] = {0, 0}, st_k[2] = {0, 0};
+            unsigned ex_k[2][2], add_k[2][2];  // [k][x/y]: packed 16-bit pairs
+            unsigned gtot[2] = {0, 0};
+#pragma unroll
+            for (unsigned k = 0; k < 2; k++)
+                if (k < v.bpt) {
+                    const uint2* c2 = reinterpret_cast<const uint2*>(cnt) + (tid >> 2) + k * (kPThreads / 4) + (size_t)j * pitch;
+                    unsigned rx = 0, ry = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const uint2 c = c2[(size_t)(4 * i) * pitch];
+                        rx += c.x & 0x07ff07ffu;  // (claim tags masked off; 16-bit halves cannot carry: every sum is <= kTile)
+                        ry += c.y & 0x07ff07ffu;
+                    }
+                    unsigned px = rx, py = ry;  // inclusive scan over the four quarters
+                    unsigned yx = __shfl_up_sync(kFull, px, 1), yy = __shfl_up_sync(kFull, py, 1);
+                    if (j >= 1) { px += yx; py += yy; }
+                    yx = __shfl_up_sync(kFull, px, 2); yy = __shfl_up_sync(kFull, py, 2);
+                    if (j >= 2) { px += yx; py += yy; }
+                    ex_k[k][0] = px - rx; ex_k[k][1] = py - ry;
+                    const unsigned tx = __shfl_sync(kFull, px, lane | 3u), ty = __shfl_sync(kFull, py, lane | 3u);  // the group's four totals
+                    add_k[k][0] = tx; add_k[k][1] = ty;  // (turned into the starts below)
+                    gtot[k] = (tx & 0xffffu) + (tx >> 16) + (ty & 0xffffu) + (ty >> 16);
+                }
+            // buckets are laid out in the order b = tid (k = 0), then b = tid + 1024 (k = 1): two scans keep bucket order
+            unsigned total0, total1 = 0;
+            unsigned base[2];
+            base[0] = block_excl_scan(j == 0 ? gtot[0] : 0u, s_warp, &total0);
+            base[1] = 0;
+            if (v.bpt > 1) {
+                __syncthreads();
+                base[1] = total0 + block_excl_scan(j == 0 ? gtot[1] : 0u, s_warp, &total1);
+            }
+#pragma unroll
+            for (unsigned k = 0; k < 2; k++)
+                if (k < v.bpt) {
+                    const unsigned g0 = __shfl_sync(kFull, base[k], lane & ~3u);  // start of the group's first bucket
+                    const unsigned tx = add_k[k][0], ty = add_k[k][1];
+                    const unsigned s0 = g0, s1 = s0 + (tx & 0xffffu), s2 = s1 + (tx >> 16), s3 = s2 + (ty & 0xffffu);
+                    add_k[k][0] = (s0 | (s1 << 16)) + ex_k[k][0];
+                    add_k[k][1] = (s2 | (s3 << 16)) + ex_k[k][1];
+                    st_k[k] = j == 0 ? s0 : j == 1 ? s1 : j == 2 ? s2 : s3;  // this thread's bucket: tid + 1024 k
+                    tot_k[k] = j == 0 ? (tx & 0xffffu) : j == 1 ? (tx >> 16) : j == 2 ? (ty & 0xffffu) : (ty >> 16);
+                    p.runs[(size_t)(tid + k * kPThreads) * p.ntp + tile] = st_k[k] | (tot_k[k] << kRunShift);
+                    acc_tot[k] += tot_k[k];
+                    uint2* c2 = reinterpret_cast<uint2*>(cnt) + (tid >> 2) + k * (kPThreads / 4) + (size_t)j * pitch;
+                    unsigned rx = add_k[k][0], ry = add_k[k][1];  // bucket start + queries of the bucket in earlier warps
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const uint2 c = c2[(size_t)(4 * i) * pitch];
+                        c2[(size_t)(4 * i) * pitch] = make_uint2(rx, ry);
+                        rx += c.x & 0x07ff07ffu;
+                        ry += c.y & 0x07ff07ffu;
+                    }
+                }
+        }
+        __syncthreads();
+        // final position of every query inside the sorted tile; the position map goes out as it is computed
+        uint16_t* tl = p.lpos + tile_base + i0;
+#pragma unroll
+        for (int r = 0; r < kPItems; r++) {
+            const bool valid = full || i0 + r * 32 < tile_n;
+            const unsigned pos = valid ? (unsigned)cntw[pk[r] & 0xffffu] + (pk[r] >> 16) : 0u;
+            pk[r] = pos;
+            if (valid) tl[r * 32] = (uint16_t)pos;
+        }
+        __syncthreads();  // every counter has been read: the sorted tile may overwrite them
+#pragma unroll
+        for (int r = 0; r < kPItems; r++)
+            if (full || i0 + r * 32 < tile_n) s_tile[pk[r]] = q[r];
+        if (via_tma) {
+            fence_proxy_async();  // generic-proxy writes to shared memory -> visible to the bulk-copy engine
+            __syncthreads();
+            if (tid == 0) {
+                char* dst = reinterpret_cast<char*>(p.qsort + tile_base);
+                tma_bulk_s2g(dst, s_tile, 32768u);
+                tma_bulk_s2g(dst + 32768, reinterpret_cast<char*>(s_tile) + 32768, 32768u);
+                tma_store_commit();
+            }
+        } else {
+            __syncthreads();
+            for (unsigned i = tid; i < tile_n; i += kPThreads) p.qsort[tile_base + i] = s_tile[i];
+        }
+    }
+#pragma unroll
+    for (unsigned k = 0; k < 2; k++)
+        if (k < v.bpt && acc_tot[k]) atomicAdd(p.tot + tid + k * kPThreads, acc_tot[k]);
+    if (tid == 0) tma_store_wait_all();  // shared memory must outlive the last bulk store
+}
+
+// ---- plan: the work items of the search kernel ------------------------------------------------------
+// Work items {bucket, first tile, end tile, 0}: the tiles of a bucket whose exclusive query prefix falls into the same
+// multiple of `chunk` form one item (a run holds at most kTile <= chunk queries, so no multiple is skipped); a bucket of
+// tot queries owns tot / chunk + 1 consecutive item slots (0 when empty), a slot no tile maps to stays empty.
+// ctrl[0] = work counter, ctrl[1] = number of items.  One CTA per bucket: thread i owns a contiguous span of the bucket's
+// tiles (all of its descriptor loads are in flight at once), a block scan gives the span's query prefix.
+constexpr int kPlanThreads = 256;
+__global__ void __launch_bounds__(kPlanThreads)
+bk_items_kernel(const uint32_t* __restrict__ runs, const uint32_t* __restrict__ tot, unsigned ntiles, unsigned ntp, unsigned nb,
+                unsigned chunk_log2, uint4* __restrict__ items, unsigned* __restrict__ ctrl) {
+    __shared__ unsigned s_warp[kPlanThreads / 32 + 1];
+    const unsigned b = blockIdx.x, tid = threadIdx.x;
+    // first item slot of this bucket: the slots of the buckets before it
+    unsigned before = 0;
+    for (unsigned j = tid; j < b; j += kPlanThreads) { const unsigned t = __ldg(tot + j); before += t ? (t >> chunk_log2) + 1u : 0u; }
+    unsigned ibase_total;
+    (void)block_excl_scan(before, s_warp, &ibase_total);
+    const unsigned ibase = ibase_total;
+    const unsigned mine = __ldg(tot + b), nmine = mine ? (mine >> chunk_log2) + 1u : 0u;
+    if (b == nb - 1 && tid == 0) { ctrl[0] = 0; ctrl[1] = ibase + nmine; }
+    if (!nmine) return;
+    for (unsigned k = tid; k < nmine; k += kPlanThreads) items[ibase + k] = make_uint4(b, 0, 0, 0);
+    __syncthreads();  // (also: s_warp may be reused)
+    const uint32_t* row = runs + (size_t)b * ntp;
+    constexpr unsigned kSpanMax = 40;  // tiles per thread: 2^27 / kTile / kPlanThreads = 32, rounded up generously
+    const unsigned span = (ntiles + kPlanThreads - 1) / kPlanThreads;  // <= kSpanMax
+    const unsigned t_begin = min(ntiles, tid * span), t_end = min(ntiles, t_begin + span);
+    unsigned c[kSpanMax];
+    unsigned sum = 0;
+#pragma unroll
+    for (unsigned j = 0; j < kSpanMax; j++) {
+        c[j] = t_begin + j < t_end ? __ldg(row + t_begin + j) >> kRunShift : 0u;
+        sum += c[j];
+    }
+    unsigned total;
+    unsigned e = block_excl_scan(sum, s_warp, &total);  // queries of the bucket in earlier tiles
+    // the item of the tile before this span (0xffffffff at the very start): the last tile of the previous span with the same rule
+    unsigned prev = t_begin == 0 ? 0xffffffffu : 0u;
+    if (t_begin > 0 && t_begin < ntiles) {
+        // exclusive prefix of tile t_begin - 1 = e - count(t_begin - 1)
+        prev = (e - (__ldg(row + t_begin - 1) >> kRunShift)) >> chunk_log2;
+    }
+#pragma unroll
+    for (unsigned j = 0; j < kSpanMax; j++)
+        if (t_begin + j < t_end) {
+            const unsigned item = e >> chunk_log2;
+            if (item != prev) {
+                items[ibase + item].y = t_begin + j;
+                if (prev != 0xffffffffu) items[ibase + prev].z = t_begin + j;
+            }
+            prev = item;
+            e += c[j];
+            if (t_begin + j == ntiles - 1) items[ibase + item].z = ntiles;
+        }
+}
+
+// ---- search over runs, in place --------------------------------------------------------------------
+// One work item = (bucket, tile range).  The bucket's separators and jump table are staged as in the V1 kernel; a warp
+// then takes 32 tiles at a time: lane i holds run i's {start, count}, a warp scan gives every run its offset in the
+// group's flattened query sequence, and the lane that handles flattened query k finds its run with a five-step search
+// over those offsets by shuffles.  Each answer overwrites its query.
+template <bool WANT_IDX, int G>
+__global__ void __launch_bounds__(1024, 1)
+bk_search2_kernel(const BkSearchParams p, uint32_t* __restrict__ qsort, uint32_t* __restrict__ isort, const uint32_t* __restrict__ runs,
+                  unsigned ntp, const uint4* __restrict__ items, unsigned* __restrict__ ctrl, int pol) {
+    constexpr int U = G == 8 ? 4 : 2;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t* s_sep = reinterpret_cast<uint32_t*>(smem_raw);                 // [r]
+    uint16_t* s_jump = reinterpret_cast<uint16_t*>(s_sep + p.r);              // [r + 8]
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ unsigned s_item, s_next;
+    uint64_t keep;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+    auto ldleaf = [&](const uint32_t* a, uint32_t (&k)[8]) {  // the bucket's leaf window is read ~3 times per sector: keep it in L2
+        if (pol & 2)
+            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.L2::128B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                         : "=r"(k[0]), "=r"(k[1]), "=r"(k[2]), "=r"(k[3]), "=r"(k[4]), "=r"(k[5]), "=r"(k[6]), "=r"(k[7])
+                         : "l"(a), "l"(keep));
+        else ldg256(a, k);
+    };
+    pol &= 1;
+    auto ldq = [&](const uint32_t* a) -> uint32_t { return pol ? *reinterpret_cast<const volatile uint32_t*>(a) : __ldcs(a); };
+    auto stq = [&](uint32_t* a, uint32_t v) { if (pol) *a = v; else __stcs(a, v); };
+    const unsigned tid = threadIdx.x, lane = tid & 31u;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    unsigned phase = 0, cur_b = 0xffffffffu;
+    const unsigned nitems = ctrl[1];
+    while (true) {
+        __syncthreads();  // previous item finished: s_item, s_next, s_sep, s_jump may be overwritten
+        if (tid == 0) { s_item = atomicAdd(&ctrl[0], 1u); s_next = 0; }
+        __syncthreads();
+        const unsigned item = s_item;
+        if (item >= nitems) break;
+        const uint4 it = items[item];
+        const unsigned b = it.x, t0 = it.y, t1 = it.z;
+        if (t0 >= t1) continue;  // (block-uniform) an item slot no tile mapped to
+        if (b != cur_b) {  // stage the bucket: 1-D TMA bulk copies (SASS UBLKCP), completion on the mbarrier
+            if (tid == 0) {
+                const unsigned sep_bytes = p.r * 4u, jump_bytes = (p.r + 8u) * 2u;
+                mbar_expect_tx(&bar, sep_bytes + jump_bytes);
+                for (unsigned off = 0; off < sep_bytes; off += 32768u)
+                    tma_bulk_g2s((char*)s_sep + off, (const char*)(p.sep + (size_t)b * p.r) + off, min(32768u, sep_bytes - off), &bar);
+                for (unsigned off = 0; off < jump_bytes; off += 32768u)
+                    tma_bulk_g2s((char*)s_jump + off, (const char*)(p.jump + (size_t)b * (p.r + 8u)) + off, min(32768u, jump_bytes - off), &bar);
+            }
+            mbar_wait(&bar, phase);
+            phase ^= 1u;
+            cur_b = b;
+        }
+        const uint2 mt = p.meta[b];
+        const uint32_t lo = mt.x;
+        const unsigned sh = mt.y;
+        const unsigned long long hbase = (unsigned long long)b * p.r;
+        const uint32_t* row = runs + (size_t)b * ntp;
+        const unsigned ngroups = (t1 - t0 + 31u) >> 5;
+        while (true) {
+            unsigned g = 0;
+            if (lane == 0) g = atomicAdd(&s_next, 1u);
+            g = __shfl_sync(kFull, g, 0);
+            if (g >= ngroups) break;
+            const unsigned t = t0 + g * 32u + lane;
+            const uint32_t d = t < t1 ? __ldg(row + t) : 0u;
+            const unsigned c = d >> kRunShift;
+            unsigned incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(kFull, incl, o); if (lane >= (unsigned)o) incl += y; }
+            const unsigned excl = incl - c;
+            const unsigned T = __shfl_sync(kFull, incl, 31);  // queries of these 32 runs
+            if (T == 0) continue;
+            const uint32_t dlt = t * (unsigned)kTile + (d & ((1u << kRunShift) - 1u)) - excl;  // address of flattened query k of run `lane` = dlt + k
+            // Address of flattened query k (k < T): the last run whose offset is <= k holds it (empty runs tie with their
+            // successor).  Slots are visited in order, so the run of a slot's first query is carried along (`rcur`, warp-uniform)
+            // and a slot of 32 queries usually crosses at most three run boundaries: the offsets of the next four runs come
+            // from four INDEPENDENT broadcast shuffles (uniform source lane) instead of a five-deep chain of per-lane ones;
+            // a slot that crosses more (short runs) takes the general five-step search.
+            unsigned rcur = 0;  // last run with excl <= (first query of the next slot to locate); runs before it are exhausted
+            auto locate = [&](unsigned kbase) -> uint32_t {  // kbase = the slot's first query (warp-uniform); this lane's is kbase + lane
+                const unsigned k = min(kbase + lane, T - 1u), klast = min(kbase + 31u, T - 1u);
+                const unsigned e1 = __shfl_sync(kFull, excl, min(rcur + 1u, 31u)), e2 = __shfl_sync(kFull, excl, min(rcur + 2u, 31u));
+                const unsigned e3 = __shfl_sync(kFull, excl, min(rcur + 3u, 31u)), e4 = __shfl_sync(kFull, excl, min(rcur + 4u, 31u));
+                unsigned r;
+                if (rcur + 4u > 31u || e4 > klast) {  // (warp-uniform) at most three boundaries inside the slot
+                    const bool h1 = rcur + 1u <= 31u, h2 = rcur + 2u <= 31u, h3 = rcur + 3u <= 31u;
+                    r = rcur + ((h1 && e1 <= k) ? 1u : 0u) + ((h2 && e2 <= k) ? 1u : 0u) + ((h3 && e3 <= k) ? 1u : 0u);
+                    rcur += ((h1 && e1 <= klast) ? 1u : 0u) + ((h2 && e2 <= klast) ? 1u : 0u) + ((h3 && e3 <= klast) ? 1u : 0u);
+                } else {
+                    r = 0;
+#pragma unroll
+                    for (unsigned s = 16; s; s >>= 1) {
+                        const unsigned e = __shfl_sync(kFull, excl, r + s);
+                        if (e <= k) r += s;
+                    }
+                    rcur = __shfl_sync(kFull, r, 31);
+                }
+                return __shfl_sync(kFull, dlt, r) + k;
+            };
+            uint32_t an[U], qn[U];  // next round: addresses and queries (their loads stay in flight while this round is answered)
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const unsigned kb = u * 32u;
+                an[u] = kb < T ? locate(kb) : 0u;
+                qn[u] = kb + lane < T ? ldq(qsort + an[u]) : lo;
+            }
+            for (unsigned k0 = 0; k0 < T; k0 += 32u * U) {
+                uint32_t q[U], ad[U];
+                unsigned a[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    q[u] = qn[u];
+                    ad[u] = an[u];
+                    const unsigned kb = k0 + (U + u) * 32u;
+                    an[u] = kb < T ? locate(kb) : 0u;
+                    qn[u] = kb + lane < T ? ldq(qsort + an[u]) : lo;
+                }
+                // rank among the bucket's separators (predicated probes, see bk_search_kernel)
+                unsigned l[U];
+                uint32_t s0[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) l[u] = s_jump[(q[u] - lo) >> sh];
+#pragma unroll
+                for (int u = 0; u < U; u++) s0[u] = s_sep[min(l[u], p.r - 1u)];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    unsigned pos = l[u];
+                    if (s0[u] < q[u]) {
+                        pos++;
+                        if (s_sep[min(pos, p.r - 1u)] < q[u]) {
+                            pos++;
+                            if (s_sep[min(pos, p.r - 1u)] < q[u]) {
+                                pos++;
+                                unsigned hh = s_jump[((q[u] - lo) >> sh) + 1u];
+                                if (hh > pos + 8u) {
+                                    while (pos < hh) {
+                                        const unsigned m = (pos + hh) >> 1;
+                                        if (s_sep[m] < q[u]) pos = m + 1; else hh = m;
+                                    }
+                                } else {
+                                    while (pos < hh && s_sep[pos] < q[u]) pos++;
+                                }
+                            }
+                        }
+                    }
+                    a[u] = pos;
+                }
+                uint32_t ks[U][G];
+                unsigned long long hn[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {  // the half node that holds the answer: one 32-byte sector
+                    hn[u] = hbase + a[u];
+                    const unsigned long long hc = hn[u] < p.m8 ? hn[u] : p.m8 - 1;
+                    ldleaf(p.leaf + hc * (unsigned long long)G, reinterpret_cast<uint32_t(&)[8]>(ks[u][0]));
+                    if constexpr (G == 16) ldleaf(p.leaf + hc * 16ull + 8ull, reinterpret_cast<uint32_t(&)[8]>(ks[u][8]));
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    unsigned cc = 0;
+#pragma unroll
+                    for (int e = 0; e < G; e++) cc += ks[u][e] < q[u] ? 1u : 0u;
+                    uint32_t val = ks[u][0];
+#pragma unroll
+                    for (int e = 1; e < G; e++) val = cc == (unsigned)e ? ks[u][e] : val;
+                    unsigned long long pos = hn[u] * (unsigned long long)G + cc;
+                    if (hn[u] >= p.m8 || cc == (unsigned)G) { val = kMax; pos = p.n; }  // above every key (cc == G cannot happen below m8)
+                    if (pos > p.n) pos = p.n;
+                    if (k0 + u * 32u + lane < T) {
+                        stq(qsort + ad[u], val);
+                        if constexpr (WANT_IDX) stq(isort + ad[u], (uint32_t)pos);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- un-permute: answers of a tile (bucket order) -> the caller's order ------------------------------
+// Every global access is contiguous: the tile's 64 KB of answers arrive by TMA bulk copies (two buffers: the next tile
+// lands while this one is permuted), the position map is read with 8-byte loads one tile ahead, the output leaves in
+// 16-byte stores; the permutation itself is a random read of shared memory.
+template <typename OutT>
+__global__ void __launch_bounds__(kPThreads, 1)
+bk_unperm_kernel(const uint32_t* __restrict__ res, const uint16_t* __restrict__ lpos, size_t nq, unsigned ntiles, int tma_ok,
+                 OutT* __restrict__ dst) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t* s_buf = reinterpret_cast<uint32_t*>(smem_raw);  // [2][kTile]
+    __shared__ __align__(8) uint64_t bars[2];
+    const unsigned tid = threadIdx.x;
+    constexpr int kVec = kPItems / 4;  // groups of 4 consecutive outputs per thread
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto full_tile = [&](unsigned t) { return t < ntiles && (size_t)(t + 1) * kTile <= nq; };
+    auto issue_load = [&](unsigned t, unsigned buf) {  // (thread 0)
+        if (tma_ok && full_tile(t)) {
+            mbar_expect_tx(&bars[buf], kTile * 4u);
+            const char* src = reinterpret_cast<const char*>(res + (size_t)t * kTile);
+            char* d = reinterpret_cast<char*>(s_buf + (size_t)buf * kTile);
+            tma_bulk_g2s(d, src, 32768u, &bars[buf]);
+            tma_bulk_g2s(d + 32768, src + 32768, 32768u, &bars[buf]);
+        }
+    };
+    uint2 ln[kVec];
+    auto load_map = [&](unsigned t) {
+        if (tma_ok && full_tile(t)) {
+            const uint2* l2 = reinterpret_cast<const uint2*>(lpos + (size_t)t * kTile);
+#pragma unroll
+            for (int r = 0; r < kVec; r++) ln[r] = __ldcs(l2 + r * kPThreads + tid);
+        }
+    };
+    if (tid == 0) issue_load(blockIdx.x, 0);
+    load_map(blockIdx.x);
+    unsigned ph[2] = {0, 0}, buf = 0;
+    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1u) {
+        const size_t tile_base = (size_t)tile * kTile;
+        const bool full = (size_t)(tile + 1) * kTile <= nq;
+        uint32_t* sb = s_buf + (size_t)buf * kTile;
+        if (tid == 0) issue_load(tile + gridDim.x, buf ^ 1u);  // that buffer was released by the barrier that ended the previous tile
+        if (tma_ok && full) {
+            uint2 l[kVec];
+#pragma unroll
+            for (int r = 0; r < kVec; r++) l[r] = ln[r];
+            load_map(tile + gridDim.x);
+            mbar_wait(&bars[buf], ph[buf]);
+            ph[buf] ^= 1u;
+#pragma unroll
+            for (int r = 0; r < kVec; r++) {
+                const uint32_t v0 = sb[l[r].x & 0xffffu], v1 = sb[l[r].x >> 16], v2 = sb[l[r].y & 0xffffu], v3 = sb[l[r].y >> 16];
+                OutT* d = dst + tile_base + (size_t)(r * kPThreads + tid) * 4;
+                if constexpr (sizeof(OutT) == 4) {
+                    __stcs(reinterpret_cast<uint4*>(d), make_uint4(v0, v1, v2, v3));
+                } else {
+                    __stcs(reinterpret_cast<ulonglong2*>(d), make_ulonglong2(v0, v1));
+                    __stcs(reinterpret_cast<ulonglong2*>(d) + 1, make_ulonglong2(v2, v3));
+                }
+            }
+        } else {  // partial last tile, or buffers that are not 16-byte aligned
+            const unsigned tile_n = (unsigned)min((size_t)kTile, nq - tile_base);
+            for (unsigned i = tid; i < tile_n; i += kPThreads) sb[i] = __ldcs(res + tile_base + i);
+            __syncthreads();
+            for (unsigned i = tid; i < tile_n; i += kPThreads) __stcs(dst + tile_base + i, (OutT)sb[lpos[tile_base + i]]);
+        }
+        __syncthreads();  // sb is free for the bulk load of tile + 2 * gridDim.x
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // auxiliary arrays (index build time)
 // ------------------------------------------------------------------------------------------------
@@ -836,11 +1369,6 @@ __global__ void bk_flat_index_kernel(const uint32_t* __restrict__ qs, size_t nq,
     }
 }
 
-int env_int(const char* name, int dflt) {
-    const char* s = getenv(name);
-    return (s && *s) ? atoi(s) : dflt;
-}
-
 // ------------------------------------------------------------------------------------------------
 // scratch buffers: one set per (host thread, device), grown on demand, released when the thread exits
 // ------------------------------------------------------------------------------------------------
@@ -907,7 +1435,7 @@ template <int BITS>
 void launch_rank(const BkView& v, int sms, size_t smem, cudaStream_t st, const uint32_t* qs, size_t nq, unsigned ntiles, uint32_t* counts,
                  uint16_t* lpos, uint32_t* tot) {
     const unsigned grid = (unsigned)std::min<size_t>(ntiles, (size_t)sms * 2);
-    const int hyb = BITS > 0 ? env_int("SST_BK_HYBRID", 1) : 0;
+    const int hyb = BITS > 0 ? (int)opt(OPT_BK_HYBRID) : 0;
 #define SST_BK_LAUNCH_RANK(H)                                                                       \
     {                                                                                               \
         auto kern = bk_rank_kernel<BITS, H>;                                                        \
@@ -926,13 +1454,13 @@ void launch_rank(const BkView& v, int sms, size_t smem, cudaStream_t st, const u
 
 template <bool GATHER, typename OutT>
 void launch_move(int sms, size_t smem, cudaStream_t st, const Scratch& s, unsigned nbp, unsigned ntiles, size_t nq, const uint32_t* src, OutT* dst) {
-    const int aligned = (((uintptr_t)src | (uintptr_t)dst) & 15u) == 0 && env_int("SST_BK_VEC", 1);
+    const int aligned = (((uintptr_t)src | (uintptr_t)dst) & 15u) == 0 && opt(OPT_BK_VEC);
     // Two 104 KB tiles per SM leave ~20 KB of L1, too little for the loads in flight (ncu: LG-throttle stalls): with 512
     // threads the scatter is faster on ONE CTA per SM (0.32 vs 0.36 ms per 10^8 queries).  Default where the bucket count
     // allows: one CTA of 1024 threads per SM (gather 0.32 vs 0.37 ms, scatter 0.31); SST_BK_MOVE_THREADS=512 for the old shape.
-    const int threads = (nbp % 1024 == 0 && env_int("SST_BK_MOVE_THREADS", 1024) == 1024) ? 1024 : kThreads;
+    const int threads = (nbp % 1024 == 0 && opt(OPT_BK_MOVE_THREADS) == 1024) ? 1024 : kThreads;
     const unsigned bpt = nbp / threads;
-    if (threads == 1024 && !GATHER && env_int("SST_BK_PREFETCH", 1)) {
+    if (threads == 1024 && !GATHER && opt(OPT_BK_PREFETCH)) {
         auto kern = bk_move_kernel<GATHER, OutT, 1024, true>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kern<<<(unsigned)std::min<size_t>(ntiles, (size_t)sms), 1024, smem, st>>>(s.counts, s.offs, s.lpos, nbp, bpt, ntiles, nq, aligned, src, dst);
@@ -943,7 +1471,7 @@ void launch_move(int sms, size_t smem, cudaStream_t st, const Scratch& s, unsign
     } else {
         auto kern = bk_move_kernel<GATHER, OutT, kThreads>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<(unsigned)std::min<size_t>(ntiles, (size_t)sms * env_int("SST_BK_MOVE_CTAS", GATHER ? 2 : 1)), kThreads, smem, st>>>(
+        kern<<<(unsigned)std::min<size_t>(ntiles, (size_t)sms * (opt(OPT_BK_MOVE_CTAS) > 0 ? (size_t)opt(OPT_BK_MOVE_CTAS) : (GATHER ? 2 : 1))), kThreads, smem, st>>>(
             s.counts, s.offs, s.lpos, nbp, bpt, ntiles, nq, aligned, src, dst);
     }
 }
@@ -964,16 +1492,16 @@ bool build_bucket_aux(sst_index* idx) {
     // first key of the next non-empty part (:502-515), the tail MAX -- so the lower bound in it has the right value; its
     // position is turned into the sorted-array index afterwards (bk_flat_index_kernel).  Compact interleaves the parts' levels.
     if (idx->variant == SST_COMPACT || idx->variant == SST_EYTZINGER || idx->node_b != 16) return true;
-    if (idx->n < (size_t)env_int("SST_BK_MIN_N", 1 << 22)) return true;  // small trees are L2-resident: nothing to gain
+    if (idx->n < (size_t)opt(OPT_BK_MIN_N)) return true;  // small trees are L2-resident: nothing to gain
     const bool flat_parts = idx->variant == SST_SIMPLE || idx->variant == SST_L1 || idx->variant == SST_OVERLAPPING;
     const size_t n_flat = flat_parts ? (size_t)idx->layer_blocks[idx->levels - 1] * 16 : idx->n;
     // separators per bucket: 16384 (two search CTAs per SM) up to 2^27 keys, 32768 (one 1024-thread CTA) above, so that the
     // partition has at most 1024 buckets up to 2^28 keys -- fewer buckets = longer runs and fewer ballot bits
     // keys per separator: 8 (one leaf sector per query) up to 2^29 keys, 16 (a whole node) up to 2^30
-    unsigned g = (unsigned)env_int("SST_BK_G", div_ceil(n_flat, (size_t)8) > 32768ull * 2048ull ? 16 : 8);
+    unsigned g = opt(OPT_BK_G) > 0 ? (unsigned)opt(OPT_BK_G) : (div_ceil(n_flat, (size_t)8) > 32768ull * 2048ull ? 16u : 8u);
     if (g != 8 && g != 16) g = 8;
     const unsigned long long m8 = div_ceil(n_flat, (size_t)g);
-    unsigned r = (unsigned)env_int("SST_BK_R", m8 > 16384ull * 1024ull ? 32768 : 16384);
+    unsigned r = opt(OPT_BK_R) > 0 ? (unsigned)opt(OPT_BK_R) : (m8 > 16384ull * 1024ull ? 32768u : 16384u);
     if (r < 64 || r > 32768 || (r & (r - 1))) r = 16384;
     const unsigned long long nb64 = div_ceil((size_t)m8, (size_t)r);
     if (nb64 > 2048) return true;  // > 2^30 keys: served by the rank-table kernel
@@ -989,7 +1517,7 @@ bool build_bucket_aux(sst_index* idx) {
               SST_CUDA_OK(cudaMalloc(&a.d_bt, (size_t)kBtStride * 2)) && SST_CUDA_OK(cudaMalloc(&a.d_jump, (size_t)nb * (r + 8) * 2)) &&
               SST_CUDA_OK(cudaMalloc(&a.d_meta, (size_t)nb * sizeof(uint2)));
     if (ok) {
-        bk_sep_kernel<<<(unsigned)std::min<size_t>(div_ceil((size_t)total, (size_t)256), 148 * 16), 256, 0, st>>>(leaf, m8, total, g, a.d_sep);
+        bk_sep_kernel<<<(unsigned)std::min<size_t>(div_ceil((size_t)total, (size_t)256), (size_t)cur_sms() * 16), 256, 0, st>>>(leaf, m8, total, g, a.d_sep);
         bk_split_kernel<<<(unsigned)div_ceil((size_t)nb + 1, (size_t)256), 256, 0, st>>>(a.d_sep, nb, r, a.d_split);
         bk_bt_kernel<<<(unsigned)div_ceil((size_t)kBtStride, (size_t)256), 256, 0, st>>>(a.d_split, nb, a.d_bt);
         bk_jump_kernel<<<nb, 256, 0, st>>>(a.d_sep, a.d_split, r, m8, a.d_jump, a.d_meta);
@@ -1009,7 +1537,202 @@ int last_stage_ms(double* out, int n) {
     return g_stage_ms[0] < 0 ? 0 : k;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// V2 scratch: one set per (host thread, device); sized by sst_query_reserve or grown on first use
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Scratch2 {
+    int device = -1;
+    size_t cap_q = 0, cap_idx = 0, cap_runs = 0, cap_items = 0;
+    uint32_t *qsort = nullptr, *isort = nullptr, *runs = nullptr, *tot = nullptr;
+    uint16_t* lpos = nullptr;
+    uint4* items = nullptr;
+    unsigned* ctrl = nullptr;
+    cudaEvent_t done = nullptr;
+    void release() {
+        if (device < 0) return;
+        int prev = -1;
+        if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) { (void)cudaGetLastError(); return; }
+        cudaFree(qsort); cudaFree(isort); cudaFree(runs); cudaFree(tot); cudaFree(lpos); cudaFree(items); cudaFree(ctrl);
+        if (done) cudaEventDestroy(done);
+        (void)cudaGetLastError();
+        if (prev >= 0) cudaSetDevice(prev);
+        *this = Scratch2{};
+    }
+    ~Scratch2() { release(); }
+};
+thread_local Scratch2 g_scratch2[64];
+
+struct Shape2 { size_t sub; unsigned ntiles, ntp, nbp2; size_t runs, items; };
+Shape2 shape2(const BkAux& a, size_t nq) {
+    Shape2 h;
+    h.sub = std::min(nq, kSubBatch);
+    h.ntiles = (unsigned)div_ceil(h.sub, (size_t)kTile);
+    h.ntp = (h.ntiles + 31u) & ~31u;
+    h.nbp2 = (unsigned)(div_ceil((size_t)a.nb, (size_t)kPThreads) * kPThreads);
+    h.runs = (size_t)h.nbp2 * h.ntp;
+    h.items = h.sub / kMinChunk + a.nb + 2;
+    return h;
+}
+
+// (needs_alloc != nullptr: only report whether anything would have to be allocated)
+bool scratch2_ensure(Scratch2& s, int device, const Shape2& h, bool want_idx, bool* needs_alloc = nullptr) {
+    const size_t nslots = (size_t)h.ntiles * kTile;
+    const bool grow = !s.ctrl || nslots > s.cap_q || (want_idx && nslots > s.cap_idx) || h.runs > s.cap_runs || h.items > s.cap_items;
+    if (needs_alloc) { *needs_alloc = grow; return true; }
+    if (!grow) return true;
+    s.device = device;
+    if (!s.done && !SST_CUDA_OK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming))) return false;
+    if (!s.ctrl && (!regrow(s.ctrl, 8) || !regrow(s.tot, 4096))) return false;
+    if (nslots > s.cap_q) {
+        s.cap_q = 0;
+        if (!regrow(s.qsort, nslots) || !regrow(s.lpos, nslots)) return false;
+        s.cap_q = nslots;
+    }
+    if (want_idx && nslots > s.cap_idx) {
+        s.cap_idx = 0;
+        if (!regrow(s.isort, nslots)) return false;
+        s.cap_idx = nslots;
+    }
+    if (h.runs > s.cap_runs) {
+        s.cap_runs = 0;
+        if (!regrow(s.runs, h.runs)) return false;
+        s.cap_runs = h.runs;
+    }
+    if (h.items > s.cap_items) {
+        s.cap_items = 0;
+        if (!regrow(s.items, h.items)) return false;
+        s.cap_items = h.items;
+    }
+    return true;
+}
+
+template <int BITS>
+void launch_part(const PartParams& pp, int sms, size_t smem, cudaStream_t st) {
+    const unsigned grid = (unsigned)std::min<size_t>(pp.ntiles, (size_t)sms);
+    if (BITS > 0 && opt(OPT_BK_HYBRID) != 0) {
+        auto kern = bk_part_kernel<BITS, 32>;  // claims on every step but the first (see launch_rank)
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, kPThreads, smem, st>>>(pp);
+    } else {
+        auto kern = bk_part_kernel<BITS, 0>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, kPThreads, smem, st>>>(pp);
+    }
+}
+
+template <typename OutT>
+void launch_unperm(int sms, cudaStream_t st, const uint32_t* res, const uint16_t* lpos, size_t nq, unsigned ntiles, OutT* dst) {
+    const int tma_ok = ((uintptr_t)dst & 15u) == 0;
+    auto kern = bk_unperm_kernel<OutT>;
+    const size_t smem = (size_t)2 * kTile * 4;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<(unsigned)std::min<size_t>(ntiles, (size_t)sms), kPThreads, smem, st>>>(res, lpos, nq, ntiles, tma_ok, dst);
+}
+}  // namespace
+
+// Pre-sizes the calling thread's pipeline scratch for batches of up to nq queries on this index, so that later
+// sst_query_device calls allocate nothing (asynchronous, graph-capturable).  No-op for an index the pipeline does not serve.
+int reserve_bucketed(const sst_index* idx, size_t nq, bool want_idx) {
+    const BkAux& a = idx->bk;
+    if (!a.nb || nq == 0) return SST_OK;
+    const int dev = idx->device;
+    if (dev < 0 || dev >= 64) { set_error(SST_ERR_ARG, "device index out of range"); return SST_ERR_ARG; }
+    if (!scratch2_ensure(g_scratch2[dev], dev, shape2(a, nq), want_idx)) {
+        set_error(SST_ERR_CAPACITY, "not enough device memory for the reordered-batch scratch buffers (6-10 bytes per query)");
+        return SST_ERR_CAPACITY;
+    }
+    return SST_OK;
+}
+void release_bucketed_scratch() {
+    for (auto& s : g_scratch2) s.release();
+}
+
+static int launch_bucketed_v1(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx, cudaStream_t st);
+
+static int launch_bucketed_v2(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx, cudaStream_t st) {
+    const BkAux& a = idx->bk;
+    const int dev = idx->device;
+    if (dev < 0 || dev >= 64) { set_error(SST_ERR_ARG, "device index out of range"); return SST_ERR_ARG; }
+    Scratch2& s = g_scratch2[dev];
+    const Shape2 h = shape2(a, nq);
+    if (!scratch2_ensure(s, dev, h, d_idx != nullptr)) {  // out of device memory for the scratch buffers
+        set_error(SST_ERR_CAPACITY, "not enough device memory for the reordered-batch scratch buffers (6-10 bytes per query)");
+        return SST_ERR_CAPACITY;
+    }
+    if (!SST_CUDA_OK(cudaStreamWaitEvent(st, s.done, 0))) return SST_ERR_CUDA;  // scratch reuse across this thread's streams
+    const int sms = sm_count(dev);
+    const bool flat_parts = idx->variant == SST_SIMPLE || idx->variant == SST_L1 || idx->variant == SST_OVERLAPPING;
+    const bool map_tree = idx->variant == SST_MAP || flat_parts;  // partitioned: a query above MAX has no part -> (MAX, n)
+    if (map_tree && !SST_CUDA_OK(cudaMemsetAsync(s.ctrl + 3, 0, 4, st))) return SST_ERR_CUDA;
+    const size_t smem_part = (size_t)kTile * 4 + (size_t)kBtCells * 4 + std::max((size_t)kTile * 4, (size_t)kPWarps * (h.nbp2 + kCntPad) * 2);
+    const size_t smem_search = (size_t)a.r * 4 + ((size_t)a.r + 8) * 2;
+    const unsigned chunk_log2 = (unsigned)opt(OPT_BK_CHUNK2_LOG2);
+    BkSearchParams sp{a.d_sep, a.d_jump, a.d_meta, idx->d_tree + idx->offsets[idx->levels - 1] * 16, a.r, a.m8, a.n_flat};
+    const bool timing = opt(OPT_BK_TIMING) != 0;
+    cudaEvent_t ev[8] = {};
+    int nev = 0;
+    auto mark = [&]() {
+        if (!timing || nev >= 8) return;
+        cudaEventCreate(&ev[nev]);
+        cudaEventRecord(ev[nev++], st);
+    };
+    for (size_t off = 0; off < nq; off += h.sub) {
+        const size_t cnt = std::min(h.sub, nq - off);
+        const unsigned ntiles = (unsigned)div_ceil(cnt, (size_t)kTile);
+        const uint32_t* qs = d_qs + off;
+        PartParams pp{};
+        pp.v = BkView{a.d_bt, a.d_split, a.nb, h.nbp2, h.nbp2 / kPThreads, map_tree ? s.ctrl + 3 : nullptr};
+        pp.qs = qs; pp.nq = cnt; pp.ntiles = ntiles; pp.ntp = h.ntp;
+        pp.qsort = s.qsort; pp.lpos = s.lpos; pp.runs = s.runs; pp.tot = s.tot;
+        if (!SST_CUDA_OK(cudaMemsetAsync(s.tot, 0, (size_t)h.nbp2 * 4, st))) return SST_ERR_CUDA;
+        pp.tma_ok = ((uintptr_t)qs & 15u) == 0;
+        nev = 0;
+        mark();
+        switch (a.bits) {
+#define SST_BK_PART(B) case B: launch_part<B>(pp, sms, smem_part, st); break;
+            SST_BK_PART(0) SST_BK_PART(1) SST_BK_PART(2) SST_BK_PART(3) SST_BK_PART(4) SST_BK_PART(5)
+            SST_BK_PART(6) SST_BK_PART(7) SST_BK_PART(8) SST_BK_PART(9) SST_BK_PART(10) SST_BK_PART(11)
+#undef SST_BK_PART
+            default: set_error(SST_ERR_UNSUPPORTED, "too many buckets"); return SST_ERR_UNSUPPORTED;
+        }
+        mark();
+        bk_items_kernel<<<a.nb, kPlanThreads, 0, st>>>(s.runs, s.tot, ntiles, h.ntp, a.nb, chunk_log2, s.items, s.ctrl);
+        mark();
+        mark();  // (no scatter stage: kept so that the five stage times line up with the V1 report)
+        {
+            void (*kern)(const BkSearchParams, uint32_t*, uint32_t*, const uint32_t*, unsigned, const uint4*, unsigned*, int) =
+                a.g == 16 ? (d_idx ? bk_search2_kernel<true, 16> : bk_search2_kernel<false, 16>) : (d_idx ? bk_search2_kernel<true, 8> : bk_search2_kernel<false, 8>);
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_search);
+            kern<<<sms, 1024, smem_search, st>>>(sp, s.qsort, s.isort, s.runs, h.ntp, s.items, s.ctrl, (int)(opt(OPT_BK_POL) | (opt(OPT_BK_LEAF_KEEP) << 1)));
+        }
+        mark();
+        launch_unperm<uint32_t>(sms, st, s.qsort, s.lpos, cnt, ntiles, d_vals + off);
+        if (d_idx) launch_unperm<unsigned long long>(sms, st, s.isort, s.lpos, cnt, ntiles, d_idx + off);
+        if (flat_parts && d_idx)
+            bk_flat_index_kernel<<<sms * 8, 256, 0, st>>>(qs, cnt, d_idx + off, (unsigned)idx->shift, (unsigned long long)idx->parts, idx->d_part_start,
+                                                        idx->d_part_pos, (unsigned long long)idx->n);
+        if (map_tree) bk_above_kernel<<<sms * 4, 256, 0, st>>>(s.ctrl + 3, qs, cnt, d_vals + off, d_idx ? d_idx + off : nullptr, (unsigned long long)idx->n);
+        mark();
+        if (timing && nev == 6 && cudaEventSynchronize(ev[5]) == cudaSuccess) {
+            float t[5];
+            for (int i = 0; i < 5; i++) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
+            for (int i = 0; i < 5; i++) g_stage_ms[i] = t[i];
+            if (opt(OPT_BK_TIMING) > 1) fprintf(stderr, "[sst] bucketed v2 nq=%zu nb=%u: partition %.3f plan %.3f - search %.3f unpermute %.3f ms\n", cnt, a.nb, t[0], t[1], t[3], t[4]);
+        }
+        for (int i = 0; i < nev; i++) cudaEventDestroy(ev[i]);
+    }
+    if (!SST_CUDA_OK(cudaGetLastError()) || !SST_CUDA_OK(cudaEventRecord(s.done, st))) return SST_ERR_CUDA;
+    return SST_OK;
+}
+
 int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx, cudaStream_t st) {
+    if (!idx->bk.nb) { set_error(SST_ERR_UNSUPPORTED, "the reordered-batch pipeline serves plain and Map-partitioned B=16 trees of 2^22..2^30 keys"); return SST_ERR_UNSUPPORTED; }
+    return opt(OPT_BK_V1) ? launch_bucketed_v1(idx, d_qs, nq, d_vals, d_idx, st) : launch_bucketed_v2(idx, d_qs, nq, d_vals, d_idx, st);
+}
+
+static int launch_bucketed_v1(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx, cudaStream_t st) {
     const BkAux& a = idx->bk;
     if (!a.nb) { set_error(SST_ERR_UNSUPPORTED, "the reordered-batch pipeline serves plain and Map-partitioned B=16 trees of 2^22..2^30 keys"); return SST_ERR_UNSUPPORTED; }
     const int dev = idx->device;
@@ -1034,10 +1757,10 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
     const int search_threads = smem_search * 2 + 4096 <= max_smem_optin(dev) ? kThreads : 1024, search_ctas = search_threads == kThreads ? 2 : 1;
     // queries per search work item: every item stages its bucket (r * 6 bytes) again, so larger is cheaper, but a bucket
     // should still split into a few items for load balance
-    const unsigned chunk = (unsigned)std::max(env_int("SST_BK_CHUNK", 32768), (int)kMinChunk);
+    const unsigned chunk = (unsigned)std::max<long long>(opt(OPT_BK_CHUNK), (long long)kMinChunk);
     BkSearchParams sp{a.d_sep, a.d_jump, a.d_meta, idx->d_tree + idx->offsets[idx->levels - 1] * 16, a.r, a.m8, a.n_flat};
     // SST_BK_TIMING=1 (debug): per-stage CUDA-event times on stderr; synchronises the stream
-    const bool timing = env_int("SST_BK_TIMING", 0) != 0;
+    const bool timing = opt(OPT_BK_TIMING) != 0;
     cudaEvent_t ev[8] = {};
     int nev = 0;
     auto mark = [&]() {
@@ -1072,7 +1795,7 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
                 // SST_BK_PROBE=0: the earlier form (three unconditional probes bounded by the cell's upper end), kept for A/B runs.
                 // Rejected on measurement: software-pipelining the rounds (leaf loads of round k in flight during the probes of
                 // round k + 1): search 0.675 -> 0.761 ms -- the stage is bound by L1/XBAR throughput, not by latency.
-                env_int("SST_BK_PROBE", 1) == 1
+                opt(OPT_BK_PROBE) == 1
                     ? (a.g == 16 ? (d_idx ? bk_search_kernel<true, 16, 1> : bk_search_kernel<false, 16, 1>) : (d_idx ? bk_search_kernel<true, 8, 1> : bk_search_kernel<false, 8, 1>))
                     : (a.g == 16 ? (d_idx ? bk_search_kernel<true, 16, 0> : bk_search_kernel<false, 16, 0>) : (d_idx ? bk_search_kernel<true, 8, 0> : bk_search_kernel<false, 8, 0>));
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_search);
@@ -1090,7 +1813,7 @@ int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint3
             float t[5];
             for (int i = 0; i < 5; i++) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
             for (int i = 0; i < 5; i++) g_stage_ms[i] = t[i];
-            if (env_int("SST_BK_TIMING", 0) > 1) fprintf(stderr, "[sst] bucketed nq=%zu nb=%u: rank %.3f plan %.3f scatter %.3f search %.3f gather %.3f ms\n", cnt, a.nb, t[0], t[1],
+            if (opt(OPT_BK_TIMING) > 1) fprintf(stderr, "[sst] bucketed nq=%zu nb=%u: rank %.3f plan %.3f scatter %.3f search %.3f gather %.3f ms\n", cnt, a.nb, t[0], t[1],
                     t[2], t[3], t[4]);
         }
         for (int i = 0; i < nev; i++) cudaEventDestroy(ev[i]);

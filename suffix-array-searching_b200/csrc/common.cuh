@@ -36,7 +36,81 @@ cudaStream_t thread_stream(int device);
 cudaStream_t thread_copy_stream(int device, int which);
 
 void configure_l2_fetch(int device);  // must run with `device` current
-int sm_count(int device);
+int sm_count(int device);             // cached per device
+unsigned cur_sms();                   // sm_count of the calling thread's current device (launch sites run under a DeviceGuard)
+
+// ---- library options -------------------------------------------------------------------------
+// Every tuning / A-B switch of the library lives in ONE table: a default, overridden ONCE when the library is loaded by
+// the environment variable SST_<NAME> (so a tool can still be started as `SST_BK_R=256 python tool.py`), and afterwards
+// only through sst_set_option() (tests, bench).  Nothing on a launch path calls getenv: the table is an array of
+// atomics, so sst_query* stay re-entrant while another thread changes an option.  -1 means "auto" where noted.
+//   X(name, default, min, max)
+#define SST_OPTION_LIST(X)                                                                                                   \
+    X(DEBUG, 0, 0, 9)                                                                                                        \
+    X(L2_FETCH, 64, 0, 128)              /* cudaLimitMaxL2FetchGranularity set at first use; 0 = leave */                    \
+    X(NO_BIND, 0, 0, 1)                  /* sst_multi_* workers do not pin themselves to the GPU's CPUs */                   \
+    /* direct kernels (stree_search.cu) */                                                                                    \
+    X(SCHEME, -1, -1, 8)                 /* what SST_SCHEME_AUTO resolves to for plain trees; -1 = the measured rule */       \
+    X(HINTS, 3, 0, 3)                                                                                                        \
+    X(L1_LEVEL_KB, 256, 0, 1 << 20)                                                                                          \
+    X(USE_C5, 1, 0, 1)                                                                                                       \
+    X(C5, 0, 0, 1)                       /* build the 16-bit copy of the last inner level (measured slower: off) */          \
+    X(THREADS, 1024, 32, 1024)           /* CTA size of stree_search_fast; rounded down to a multiple of 32 */                \
+    X(WAVES, 1, 1, 64)                                                                                                       \
+    X(GRID_CAP, 0, 0, 1 << 20)                                                                                               \
+    X(PERSIST, 0, 0, 300)                                                                                                    \
+    X(PERSIST_MB, -1, -1, 1 << 20)                                                                                           \
+    X(PGROUP, 1, 0, 1)                                                                                                       \
+    X(PT, 1, 1, 2)                                                                                                           \
+    X(T, 2, 1, 2)                                                                                                            \
+    X(TABLE_G, 2, 2, 4)                                                                                                      \
+    X(TABLE_MIN_NQ, 1 << 17, 0, 1ll << 40)                                                                                   \
+    X(CHUNK, 1 << 22, 1024, 1ll << 32)   /* queries per chunk of the host-buffer path */                                     \
+    X(HOST_GRID_CAP, 0, -1, 1 << 20)                                                                                         \
+    /* reordered-batch pipeline (bucketed.cu) */                                                                              \
+    X(BK_AUTO_MIN_N, 1 << 25, 0, 1ll << 40)                                                                                  \
+    X(BK_AUTO_MIN_NQ, -1, -1, 1ll << 40) /* -1 = measured crossover by tree size */                                           \
+    X(BK_MIN_N, 1 << 22, 0, 1ll << 40)   /* smaller trees get no pipeline arrays */                                          \
+    X(BK_G, -1, -1, 16)                  /* keys per separator: 8 / 16; -1 = by size */                                       \
+    X(BK_R, -1, -1, 32768)               /* separators per bucket (power of two >= 64); -1 = by size */                       \
+    X(BK_CHUNK, 32768, 16384, 1 << 24)   /* queries per search work item */                                                   \
+    X(BK_TIMING, 0, 0, 2)                /* per-stage CUDA-event times (synchronises; bench/tools only) */                    \
+    X(BK_V1, 0, 0, 1)                    /* 1 = the round-1 seven-launch pipeline (A/B runs) */                               \
+    X(BK_CHUNK2_LOG2, 15, 14, 24)        /* log2 of the queries per search work item of the V2 pipeline */                    \
+    X(BK_LEAF_KEEP, 1, 0, 1)             /* V2 search: leaf sectors carry an L2 evict_last hint */                             \
+    X(BK_POL, 1, 0, 1)                   /* V2 search: 0 = streaming (evict-first) run loads/stores, 1 = default policy */       \
+    X(BK_HYBRID, 1, 0, 4)                                                                                                    \
+    X(BK_VEC, 1, 0, 1)                                                                                                       \
+    X(BK_MOVE_THREADS, 1024, 512, 1024)                                                                                      \
+    X(BK_PREFETCH, 1, 0, 1)                                                                                                  \
+    X(BK_MOVE_CTAS, -1, -1, 8)                                                                                               \
+    X(BK_PROBE, 1, 0, 1)                                                                                                     \
+    /* suffix arrays (sa.cu) */                                                                                               \
+    X(SA_PIVOT_LEVELS, -1, -1, 33)       /* -1 = all but the last ~3 levels */                                                \
+    X(SA_TABLE_GB, -1, -1, 1 << 10)      /* pivot-table budget; -1 = min(half of free memory, 64 GB) */                       \
+    X(SA_USE_LEVELS, 64, 0, 64)                                                                                              \
+    X(SA_USE_KMER, 1, 0, 1)                                                                                                  \
+    X(SA_USE_INLINE, 1, 0, 1)                                                                                                \
+    X(SA_LANES, 1, 1, 32)                                                                                                    \
+    X(SA_SORT_LEVELS, 12, 0, 30)                                                                                             \
+    X(SA_SORT_MIN, -1, -1, 1ll << 62)    /* batches of at least this many patterns search in sorted order; -1 = never */      \
+    X(SA_MINB, 0, 0, 5)                                                                                                      \
+    X(SA_INLINE, 1, 0, 15)               /* 0 = no inlined bases, 15 = 8-byte entries, 1 = widest that fits */                \
+    X(SA_INLINE_DIV, 2, 1, 64)                                                                                               \
+    X(SA_KMER, 1, 0, 1)                                                                                                      \
+    X(SA_KMER_K, 16, 1, 16)                                                                                                  \
+    X(SA_KMER_FORCE, 0, 0, 16)                                                                                               \
+    X(SA_CHUNK, 1 << 20, 16, 1ll << 32)  /* patterns per chunk of the host-buffer path */                                     \
+    X(SA_L2_64B, 1, 0, 2)                /* random loads of the SA search ask L2 for 64-byte fills (0 = plain __ldg) */        \
+    X(SA_VALIDATE, 1, 0, 1)              /* sst_sa_from_parts checks the caller's suffix array (sa_search.rs:36-38) */
+
+enum Opt : int {
+#define SST_OPT_ENUM(name, dflt, lo, hi) OPT_##name,
+    SST_OPTION_LIST(SST_OPT_ENUM)
+#undef SST_OPT_ENUM
+    OPT_COUNT
+};
+long long opt(Opt o);
 size_t max_smem_optin(int device);
 bool device_usable(int device);
 
@@ -168,4 +242,8 @@ bool bucketed_eligible(const sst_index* idx);
 int last_stage_ms(double* out, int n);  // stage times of this thread's last pipeline run under SST_BK_TIMING=1
 int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx,
                     cudaStream_t stream);
+int reserve_bucketed(const sst_index* idx, size_t nq, bool want_idx);  // pre-size the calling thread's scratch
+void release_bucketed_scratch();                                       // free the calling thread's scratch on every device
+// suffix arrays (sa.cu): replica of a finished index on another device, copied device to device
+struct sst_sa* clone_sa(const struct sst_sa* src, int device);
 }  // namespace sst

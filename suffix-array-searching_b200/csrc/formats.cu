@@ -23,7 +23,7 @@ namespace sst {
 namespace {
 
 constexpr int kThreads = 256;
-inline unsigned grid_for(size_t work) { return (unsigned)std::min<size_t>(div_ceil(work, (size_t)kThreads), 148 * 32); }
+inline unsigned grid_for(size_t work) { return (unsigned)std::min<size_t>(div_ceil(work, (size_t)kThreads), (size_t)cur_sms() * 32); }
 
 // start-of-line marker: position i if byte i starts a line, else 0 (a running max gives the line start)
 __global__ void fasta_line_starts(const char* __restrict__ s, size_t n, unsigned long long* __restrict__ start) {

@@ -1,13 +1,12 @@
 // runtime.cu -- error state, device selection and per-thread streams.
+#include <atomic>
+#include <cctype>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include <sched.h>
-
-#include <cctype>
-#include <cstdio>
-#include <cstring>
 
 #include "common.cuh"
 
@@ -18,7 +17,40 @@ thread_local std::string g_err;
 thread_local int g_status = SST_OK;
 constexpr int kMaxDevices = 64;
 thread_local cudaStream_t g_streams[kMaxDevices][3] = {};
+
+// ---- options table (see SST_OPTION_LIST in common.cuh) ----
+struct OptDesc { const char* name; long long dflt, lo, hi; };
+const OptDesc kOptDesc[OPT_COUNT] = {
+#define SST_OPT_DESC(name, dflt, lo, hi) {#name, (long long)(dflt), (long long)(lo), (long long)(hi)},
+    SST_OPTION_LIST(SST_OPT_DESC)
+#undef SST_OPT_DESC
+};
+std::atomic<long long> g_opt[OPT_COUNT];
+long long g_opt_initial[OPT_COUNT];  // default or the environment's value at load time (what sst_reset_options restores)
+long long clamp_opt(int o, long long v) { return v < kOptDesc[o].lo ? kOptDesc[o].lo : v > kOptDesc[o].hi ? kOptDesc[o].hi : v; }
+// Runs once when the library is loaded (single-threaded): the only getenv calls of the library.
+struct OptInit {
+    OptInit() {
+        for (int o = 0; o < OPT_COUNT; o++) {
+            long long v = kOptDesc[o].dflt;
+            char env[64];
+            snprintf(env, sizeof env, "SST_%s", kOptDesc[o].name);
+            if (const char* e = getenv(env); e && *e) v = clamp_opt(o, strtoll(e, nullptr, 10));
+            g_opt_initial[o] = v;
+            g_opt[o].store(v, std::memory_order_relaxed);
+        }
+    }
+} g_opt_init;
+int find_opt(const char* name) {
+    if (!name) return -1;
+    if (!strncmp(name, "SST_", 4)) name += 4;
+    for (int o = 0; o < OPT_COUNT; o++)
+        if (!strcmp(name, kOptDesc[o].name)) return o;
+    return -1;
+}
 }  // namespace
+
+long long opt(Opt o) { return g_opt[o].load(std::memory_order_relaxed); }
 
 void set_error(int status, const std::string& msg) {
     g_status = status;
@@ -66,21 +98,30 @@ void configure_l2_fetch(int device) {
     static thread_local bool done[kMaxDevices] = {};
     if (device < 0 || device >= kMaxDevices || done[device]) return;
     done[device] = true;
-    const char* e = getenv("SST_L2_FETCH");
-    const int want = e && *e ? atoi(e) : 64;
+    const int want = (int)opt(OPT_L2_FETCH);
     if (want <= 0) return;
     size_t before = 0, after = 0;
     cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
     const cudaError_t rc = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)want);
     cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
     if (rc != cudaSuccess) (void)cudaGetLastError();
-    if (getenv("SST_DEBUG")) fprintf(stderr, "[sst] L2 fetch granularity: before=%zu want=%d rc=%d after=%zu\n", before, want, (int)rc, after);
+    if (opt(OPT_DEBUG)) fprintf(stderr, "[sst] L2 fetch granularity: before=%zu want=%d rc=%d after=%zu\n", before, want, (int)rc, after);
 }
 
 int sm_count(int device) {
+    static std::atomic<int> cache[kMaxDevices];
+    if (device >= 0 && device < kMaxDevices)
+        if (const int c = cache[device].load(std::memory_order_relaxed)) return c;
     int v = 0;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    if (device >= 0 && device < kMaxDevices) cache[device].store(v, std::memory_order_relaxed);
     return v;
+}
+unsigned cur_sms() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) { (void)cudaGetLastError(); return 1; }
+    const int v = sm_count(d);
+    return v > 0 ? (unsigned)v : 1u;
 }
 size_t max_smem_optin(int device) {
     int v = 0;
@@ -102,7 +143,34 @@ extern "C" {
 
 const char* sst_last_error(void) { return sst::g_err.c_str(); }
 int sst_last_status(void) { return sst::g_status; }
-const char* sst_version(void) { return "sst_b200 0.1 (sm_100a)"; }
+const char* sst_version(void) { return "sst_b200 0.2 (sm_100a)"; }
+
+// Options: `name` with or without the SST_ prefix.  Values outside the option's range are rejected (SST_ERR_ARG), so a
+// typo cannot turn every launch into a failure.  Takes effect for calls (and index builds) that start afterwards.
+int sst_set_option(const char* name, long long value) {
+    sst::clear_error();
+    const int o = sst::find_opt(name);
+    if (o < 0) { sst::set_error(SST_ERR_ARG, std::string("unknown option ") + (name ? name : "(null)")); return SST_ERR_ARG; }
+    if (value < sst::kOptDesc[o].lo || value > sst::kOptDesc[o].hi) {
+        sst::set_error(SST_ERR_ARG, std::string("option ") + sst::kOptDesc[o].name + " out of range [" + std::to_string(sst::kOptDesc[o].lo) + ", " +
+                                        std::to_string(sst::kOptDesc[o].hi) + "]");
+        return SST_ERR_ARG;
+    }
+    sst::g_opt[o].store(value, std::memory_order_relaxed);
+    return SST_OK;
+}
+int sst_get_option(const char* name, long long* out_value) {
+    sst::clear_error();
+    const int o = sst::find_opt(name);
+    if (o < 0 || !out_value) { sst::set_error(SST_ERR_ARG, "unknown option or null output"); return SST_ERR_ARG; }
+    *out_value = sst::g_opt[o].load(std::memory_order_relaxed);
+    return SST_OK;
+}
+void sst_reset_options(void) {
+    for (int o = 0; o < sst::OPT_COUNT; o++) sst::g_opt[o].store(sst::g_opt_initial[o], std::memory_order_relaxed);
+}
+int sst_option_count(void) { return sst::OPT_COUNT; }
+const char* sst_option_name(int i) { return i >= 0 && i < sst::OPT_COUNT ? sst::kOptDesc[i].name : nullptr; }
 
 // Page-locked host buffers for full-speed sst_query / sst_sa_search (PCIe DMA without a staging copy).
 void* sst_host_alloc(size_t bytes) {

@@ -73,7 +73,7 @@ constexpr int kThreads = 256;
 #define SST_SA_MIN_BLOCKS 5
 #endif
 
-inline unsigned grid_for(size_t work) { return (unsigned)std::min<size_t>(div_ceil(work, (size_t)kThreads), 148 * 32); }
+inline unsigned grid_for(size_t work) { return (unsigned)std::min<size_t>(div_ceil(work, (size_t)kThreads), (size_t)cur_sms() * 32); }
 
 // ---- construction --------------------------------------------------------------------------
 __global__ void sa_init_keys(const uint8_t* __restrict__ t, size_t n, unsigned long long* __restrict__ keys,
@@ -192,12 +192,14 @@ __global__ void sa_check_kernel(const uint8_t* __restrict__ t, size_t n, const u
 // or beyond `end` read as zero, so nothing outside [base_aligned, end) is touched.
 __device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t* __restrict__ base, unsigned long long pos,
                                                        unsigned long long end) {
-    const unsigned long long a = pos & ~3ull;
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(base + a);
-    const uint32_t w0 = a < end ? __ldg(w) : 0u;
-    const unsigned sh = (unsigned)(pos & 3ull);
+    // the ADDRESS is aligned down (a chunk of the host-buffer path starts at an arbitrary byte of the packed patterns)
+    const uint8_t* addr = base + pos;
+    const uint8_t* lim = base + end;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(addr) & ~(uintptr_t)3);
+    const uint32_t w0 = reinterpret_cast<const uint8_t*>(w) < lim ? __ldg(w) : 0u;
+    const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(addr) & 3u);
     if (sh == 0) return w0;
-    const uint32_t w1 = a + 4 < end ? __ldg(w + 1) : 0u;
+    const uint32_t w1 = reinterpret_cast<const uint8_t*>(w + 1) < lim ? __ldg(w + 1) : 0u;
     return __funnelshift_r(w0, w1, sh * 8);
 }
 
@@ -224,6 +226,7 @@ struct SaParams {
     int kmer_k;
     const uint2* sax;      // {sa, next 15 bases} entries (or null)
     const uint4* saw;      // {sa, 32, next 32 bases} entries (or null; the WIDE kernels)
+    uint32_t* out_probes;  // sa_search_kernel only: iterations of the reference's loop (its `cnt`, sa_search.rs:98-112), or null
 };
 
 // Compares suffix(spos) with the pattern from byte `start` on.  Returns lcp (group-uniform) and
@@ -274,8 +277,9 @@ sa_search_kernel(const __grid_constant__ SaParams p) {
         const uint32_t ql = (uint32_t)(p.pat_off[i + 1] - po);
         // ---- lower bound: sa_search.rs:98-112 ----
         unsigned long long l = 0, r = p.n;
-        uint32_t lcp_l = 0, lcp_r = 0;
+        uint32_t lcp_l = 0, lcp_r = 0, probes = 0;
         while (l < r) {
+            probes++;  // the reference's `*cnt += 1` (sa_search.rs:104)
             const unsigned long long m = (l + r) >> 1;
             const unsigned long long spos = __ldg(p.sa + m);
             bool less;
@@ -306,6 +310,7 @@ sa_search_kernel(const __grid_constant__ SaParams p) {
             hi = a;
         }
         if (sub == 0) {
+            if (p.out_probes) p.out_probes[i] = probes;
             p.out_lo[i] = (uint32_t)lo;
             if (p.out_hi) p.out_hi[i] = (uint32_t)hi;
             if (p.out_pos) p.out_pos[i] = lo < p.n ? __ldg(p.sa + lo) : 0xffffffffu;
@@ -342,17 +347,51 @@ __host__ __device__ __forceinline__ unsigned long long pivot_table_entries(int l
     return (((1ull << levels) - 1ull) / 7ull) * 8ull;
 }
 
+// Random loads of the search (k-mer cells, {sa, bases} entries, sa[m], text windows) carry the L2::64B prefetch-size
+// qualifier: by default B200 fills L2 from HBM in 128-byte units, so every isolated 16-32-byte read dragged 128 bytes
+// in (ncu, round 1: 299 B of DRAM reads per C3 pattern for ~2.3 fills).  -DSST_SA_PF64=0 builds the plain __ldg form (A/B).
+#ifndef SST_SA_PF64
+#define SST_SA_PF64 1
+#endif
+__device__ __forceinline__ uint32_t ldr(const uint32_t* p) {
+#if SST_SA_PF64
+    uint32_t v;
+    asm("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ uint2 ldr(const uint2* p) {
+#if SST_SA_PF64
+    uint2 v;
+    asm("ld.global.nc.L2::64B.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ uint4 ldr(const uint4* p) {
+#if SST_SA_PF64
+    uint4 v;
+    asm("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
 struct W4 { uint32_t w[4]; };
 
 // 16 bytes starting at byte address `addr` (little endian words); aligned 16-byte chunks starting
 // at or beyond `end` read as zero.
-template <bool GUARD>
+template <bool GUARD, bool RANDOM = false>
 __device__ __forceinline__ W4 load16_unaligned(const uint8_t* addr, const uint8_t* end) {
     const uintptr_t a = reinterpret_cast<uintptr_t>(addr) & ~(uintptr_t)15;
     const uint4* c = reinterpret_cast<const uint4*>(a);
     uint4 A = make_uint4(0, 0, 0, 0), B = make_uint4(0, 0, 0, 0);
-    if (!GUARD || reinterpret_cast<const uint8_t*>(c) < end) A = __ldg(c);
-    if (!GUARD || reinterpret_cast<const uint8_t*>(c + 1) < end) B = __ldg(c + 1);
+    if (!GUARD || reinterpret_cast<const uint8_t*>(c) < end) A = RANDOM ? ldr(c) : __ldg(c);
+    if (!GUARD || reinterpret_cast<const uint8_t*>(c + 1) < end) B = RANDOM ? ldr(c + 1) : __ldg(c + 1);
     const unsigned s = (unsigned)(reinterpret_cast<uintptr_t>(addr) & 15u);
     const bool s2 = (s & 8u) != 0, s1 = (s & 4u) != 0;
     const unsigned bs = (s & 3u) * 8u;
@@ -399,7 +438,7 @@ __device__ __forceinline__ uint32_t thread_compare(const SaParams& p, unsigned l
     const uint8_t* pend = p.pats + p.pats_bytes;
     for (uint32_t off = start;; off += 16u) {
         if (off >= lim) { less = sl < ql; return lim; }
-        const W4 tw = load16_unaligned<false>(tbase + off, tend);  // the text has 64 bytes of zero padding
+        const W4 tw = load16_unaligned<false, true>(tbase + off, tend);  // the text has 64 bytes of zero padding
         W4 pw;
         if (off == 0u) pw = p0;
         else if (off == 16u) pw = p1;
@@ -450,13 +489,13 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
             if (dna) {
                 have_range = true;
                 if (ql >= (uint32_t)k) {
-                    l = __ldg(p.kmer + x);
-                    r = __ldg(p.kmer + (size_t)x + 1);
+                    l = ldr(p.kmer + x);
+                    r = ldr(p.kmer + (size_t)x + 1);
                     range_end = r;  // every suffix that starts with q starts with its first k bases
                 } else {
                     // every suffix from kmer[x] on is >= q000.. >= q; the only suffixes below it that are >= q are proper
                     // prefixes of q000.. (the last < k suffixes of the text): search the k positions before it
-                    r = __ldg(p.kmer + x);
+                    r = ldr(p.kmer + x);
                     l = r > (uint32_t)k ? r - (uint32_t)k : 0u;
                 }
             }
@@ -506,10 +545,10 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
                 bool complete;
                 Code code;
                 if constexpr (WIDE) {
-                    const uint4 e = __ldg(p.saw + m);
+                    const uint4 e = ldr(p.saw + m);
                     spos = e.x; complete = e.y == 32u; code = (((unsigned long long)e.z << 32) | e.w) & pmask;
                 } else {
-                    const uint2 e = __ldg(p.sax + m);
+                    const uint2 e = ldr(p.sax + m);
                     spos = e.x; complete = (e.y >> 31) != 0u; code = e.y & pmask;
                 }
                 if (complete) {  // the suffix has all the inlined bases
@@ -524,7 +563,7 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
                 }
                 return thread_compare(p, spos, p0, p1, pat, ql, start, less);
             }
-            return thread_compare(p, __ldg(p.sa + m), p0, p1, pat, ql, start, less);
+            return thread_compare(p, ldr(p.sa + m), p0, p1, pat, ql, start, less);
         };
         // ---- table levels: one 16-byte load per probe ----
         if (!have_range) {
@@ -553,7 +592,7 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
                     lcp = exact ? mp : 0u;
                 } else {  // tie on the stored prefix: decide on the text
                     const uint32_t start = MLR ? ((lcp_l < lcp_r ? lcp_l : lcp_r) & ~15u) : 0u;
-                    lcp = thread_compare(p, __ldg(p.sa + m), p0, p1, pat, ql, start, less);
+                    lcp = thread_compare(p, ldr(p.sa + m), p0, p1, pat, ql, start, less);
                     exact = true;
                 }
                 if (less) { l = m + 1; lcp_l = lcp; j = 2 * j + 1; } else { r = m; lcp_r = lcp; lcp_r_exact = exact; j = 2 * j; }
@@ -573,7 +612,7 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
         }
         const unsigned long long lo = l;
         p.out_lo[i] = (uint32_t)lo;
-        if (p.out_pos) p.out_pos[i] = lo < p.n ? (inl ? (WIDE ? __ldg(p.saw + lo).x : __ldg(p.sax + lo).x) : __ldg(p.sa + lo)) : 0xffffffffu;  // (inl: the line the probes read)
+        if (p.out_pos) p.out_pos[i] = lo < p.n ? (inl ? (WIDE ? ldr(p.saw + lo).x : ldr(p.sax + lo).x) : ldr(p.sa + lo)) : 0xffffffffu;  // (inl: the line the probes read)
         if (p.out_hi) {
             // Suffixes starting with q are contiguous from lo: gallop to bracket the end, then bisect.
             unsigned long long a = lo, b = range_end, step = 1;
@@ -624,20 +663,18 @@ __global__ void sa_pivot_kernel(const uint8_t* __restrict__ t, const uint32_t* _
 }
 
 bool build_pivots(sst_sa* s) {
-    const char* e = getenv("SST_SA_PIVOT_LEVELS");
     int need = 1;
     while ((1ull << need) < s->n + 1) need++;
     // Default: all but the last ~3 levels of the search (measured on a 10^8 text: 24 levels 4.16,
     // 27 = full depth 3.74, 21 levels 3.97 Gpat/s: at the bottom every pattern ties with its own
     // suffix and needs sa[lo] anyway), within the memory budget (16 B per heap slot * 8/7).  The
     // levels below the table are plain probes (sa[m], then the text: two fills each).
-    int levels = e && *e ? atoi(e) : 3 * ((need - 2) / 3);  // 10^8 text: 24 of 27; 3x10^9 text: 30 of 32 (1.98 vs 1.76 Gpat/s at 27)
+    int levels = opt(OPT_SA_PIVOT_LEVELS) >= 0 ? (int)opt(OPT_SA_PIVOT_LEVELS) : 3 * ((need - 2) / 3);  // 10^8 text: 24 of 27; 3x10^9 text: 30 of 32 (1.98 vs 1.76 Gpat/s at 27)
     levels = 3 * (levels / 3);
     if (levels > 3 * ((need + 2) / 3)) levels = 3 * ((need + 2) / 3);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    const char* ge = getenv("SST_SA_TABLE_GB");
-    const double budget = ge && *ge ? atof(ge) * 1e9 : std::min(0.5 * (double)free_b, 64e9);
+    const double budget = opt(OPT_SA_TABLE_GB) >= 0 ? (double)opt(OPT_SA_TABLE_GB) * 1e9 : std::min(0.5 * (double)free_b, 64e9);
     if (levels > 30) levels = 30;  // the search kernel keeps heap indices and table offsets in 32 bits
     while (levels >= 3 && (double)pivot_table_entries(levels) * 16.0 > budget) levels -= 3;
     if (levels < 3) { s->pivot_levels = 0; return true; }
@@ -649,11 +686,6 @@ bool build_pivots(sst_sa* s) {
     if (!SST_CUDA_OK(cudaGetLastError()) || !SST_CUDA_OK(cudaStreamSynchronize(st))) return false;
     s->pivot_levels = levels;
     return true;
-}
-
-int env_int(const char* name, int dflt) {
-    const char* s = getenv(name);
-    return (s && *s) ? atoi(s) : dflt;
 }
 
 template <int PL>
@@ -722,6 +754,17 @@ sst_sa_t* sst_sa_from_parts(const uint8_t* text, size_t n, const uint32_t* sa, i
     bool ok = SST_CUDA_OK(cudaMalloc(&s->d_text, n + 64)) && SST_CUDA_OK(cudaMalloc(&s->d_sa, n * 4)) &&
               SST_CUDA_OK(cudaMemsetAsync(s->d_text + n, 0, 64, st)) && SST_CUDA_OK(cudaMemcpyAsync(s->d_text, text, n, cudaMemcpyHostToDevice, st)) &&
               SST_CUDA_OK(cudaMemcpyAsync(s->d_sa, sa, n * 4, cudaMemcpyHostToDevice, st)) && SST_CUDA_OK(cudaStreamSynchronize(st));
+    // The reference asserts strict suffix order when it builds (sa_search.rs:36-38); an entry >= n would make the search
+    // kernels read the text out of bounds and an unsorted array silently returns wrong bounds, so a caller's array is checked
+    // the same way (strictly increasing suffixes with every entry < n are a permutation).  SA_VALIDATE=0: trusted callers.
+    if (ok && opt(OPT_SA_VALIDATE)) {
+        uint64_t bad = 0;
+        ok = sst_sa_check(s, &bad) == SST_OK;
+        if (ok && bad) {
+            set_error(SST_ERR_ARG, "not a suffix array of the text: " + std::to_string(bad) + " adjacent pairs out of order or entries >= n (sa_search.rs:36-38)");
+            ok = false;
+        }
+    }
     ok = ok && build_pivots(s) && build_kmer(s) && build_sax(s);
     if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); cudaFree(s->d_sax); cudaFree(s->d_saw); delete s; return nullptr; }
     return s;
@@ -747,6 +790,35 @@ int sst_sa_get(const sst_sa_t* s, uint32_t* out_sa) {
     DeviceGuard g(s->device);
     if (!g.ok) return SST_ERR_CUDA;
     return SST_CUDA_OK(cudaMemcpy(out_sa, s->d_sa, s->n * 4, cudaMemcpyDeviceToHost)) ? SST_OK : SST_ERR_CUDA;
+}
+
+// out_sa[i] = sa[positions[i]] (0xffffffff for a position >= n): the occurrences sa[lo .. hi) of a pattern, or the few
+// entries a host-side check needs, without copying the whole array (12 GB at 3x10^9).  Host buffers.
+namespace sst { namespace {
+__global__ void sa_gather_kernel(const uint32_t* __restrict__ sa, unsigned long long n, const unsigned long long* __restrict__ pos, size_t count,
+                                 uint32_t* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = pos[i] < n ? sa[pos[i]] : 0xffffffffu;
+}
+} }
+int sst_sa_gather(const sst_sa_t* s, const uint64_t* positions, size_t count, uint32_t* out_sa) {
+    clear_error();
+    if (!s || (count && (!positions || !out_sa))) { set_error(SST_ERR_ARG, "null argument"); return SST_ERR_ARG; }
+    if (count == 0) return SST_OK;
+    DeviceGuard g(s->device);
+    if (!g.ok) return SST_ERR_CUDA;
+    cudaStream_t st = thread_stream(s->device);
+    unsigned long long* d_p = nullptr;
+    uint32_t* d_o = nullptr;
+    bool ok = SST_CUDA_OK(cudaMalloc(&d_p, count * 8)) && SST_CUDA_OK(cudaMalloc(&d_o, count * 4)) &&
+              SST_CUDA_OK(cudaMemcpyAsync(d_p, positions, count * 8, cudaMemcpyHostToDevice, st));
+    if (ok) {
+        sa_gather_kernel<<<grid_for(count), kThreads, 0, st>>>(s->d_sa, s->n, d_p, count, d_o);
+        ok = SST_CUDA_OK(cudaGetLastError()) && SST_CUDA_OK(cudaMemcpyAsync(out_sa, d_o, count * 4, cudaMemcpyDeviceToHost, st)) &&
+             SST_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    cudaFree(d_p); cudaFree(d_o);
+    return ok ? SST_OK : SST_ERR_CUDA;
 }
 
 int sst_sa_check(const sst_sa_t* s, uint64_t* out_violations) {
@@ -816,12 +888,12 @@ static int sa_search_launch(const sst_sa_t* s, const uint8_t* d_pats, const uint
     p.out_lo = d_out_lo; p.out_hi = d_out_hi; p.out_pos = d_out_pos;
     p.pats_bytes = pats_end;  // end offset of the packed patterns (bounds the aligned 16-byte loads)
     p.pivots = s->d_pivots;
-    p.pivot_levels = s->d_pivots ? std::min(s->pivot_levels, env_int("SST_SA_USE_LEVELS", 64)) : 0;
+    p.pivot_levels = s->d_pivots ? std::min(s->pivot_levels, (int)opt(OPT_SA_USE_LEVELS)) : 0;
     p.kmer = s->d_kmer;
-    p.kmer_k = s->d_kmer && env_int("SST_SA_USE_KMER", 1) ? s->kmer_k : 0;
-    p.sax = p.kmer_k && env_int("SST_SA_USE_INLINE", 1) ? s->d_sax : nullptr;
-    p.saw = p.kmer_k && env_int("SST_SA_USE_INLINE", 1) ? s->d_saw : nullptr;
-    const int lanes = env_int("SST_SA_LANES", 1);
+    p.kmer_k = s->d_kmer && opt(OPT_SA_USE_KMER) ? s->kmer_k : 0;
+    p.sax = p.kmer_k && opt(OPT_SA_USE_INLINE) ? s->d_sax : nullptr;
+    p.saw = p.kmer_k && opt(OPT_SA_USE_INLINE) ? s->d_saw : nullptr;
+    const int lanes = (int)opt(OPT_SA_LANES);
     if (lanes <= 1) {
         const unsigned grid = (unsigned)std::min<unsigned long long>((npat + kThreads - 1) / kThreads, (unsigned long long)sm_count(s->device) * 8);
         // Opt-in (SST_SA_SORT_MIN=<patterns>): search in sorted order (see PHASE above): coarse pass over the cache-resident
@@ -829,9 +901,8 @@ static int sa_search_launch(const sst_sa_t* s, const uint8_t* d_pats, const uint
         // through perm.  Measured: C3 3.28 vs 4.61 Gpat/s (a loss), C5 2.12 vs 2.03 Gpat/s at 12 coarse levels, worse with
         // more levels -- the DRAM fills are the text/SA probes of the last levels and of `hi` (777 B per pattern with or
         // without the sort, ncu), not the table, so reordering cannot pay for its two extra passes; off by default.
-        const int coarse = std::min(p.pivot_levels, 3 * (env_int("SST_SA_SORT_LEVELS", 12) / 3));
-        const char* smin = getenv("SST_SA_SORT_MIN");
-        const unsigned long long sort_min = smin && *smin ? strtoull(smin, nullptr, 10) : ~0ull;
+        const int coarse = std::min(p.pivot_levels, 3 * ((int)opt(OPT_SA_SORT_LEVELS) / 3));
+        const unsigned long long sort_min = opt(OPT_SA_SORT_MIN) >= 0 ? (unsigned long long)opt(OPT_SA_SORT_MIN) : ~0ull;
         if (coarse >= 3 && npat >= sort_min && s->device >= 0 && s->device < 64) {
             SaSortScratch& sc = g_sa_sort[s->device];
             int nbits = 1;
@@ -853,7 +924,7 @@ static int sa_search_launch(const sst_sa_t* s, const uint8_t* d_pats, const uint
         }
         if (p.saw) {
             // patterns of up to k + 32 bases never touch the text: a batch of mostly such patterns takes the spill-free build
-            const bool short_pats = env_int("SST_SA_MINB", 0) ? env_int("SST_SA_MINB", 0) == 4 : pats_end <= 48ull * npat;
+            const bool short_pats = opt(OPT_SA_MINB) ? opt(OPT_SA_MINB) == 4 : pats_end <= 48ull * npat;
             if (short_pats) {
                 if (mode == SST_SA_MLR) sa_search_thread_kernel<true, 0, true, 4><<<grid, kThreads, 0, st>>>(p);
                 else sa_search_thread_kernel<false, 0, true, 4><<<grid, kThreads, 0, st>>>(p);
@@ -929,13 +1000,13 @@ __global__ void saw_kernel(const uint8_t* __restrict__ t, const uint32_t* __rest
 }  // namespace sst
 
 static bool build_sax(sst_sa* s) {
-    if (!s->kmer_k || !env_int("SST_SA_INLINE", 1)) return true;
+    if (!s->kmer_k || !opt(OPT_SA_INLINE)) return true;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     cudaStream_t st0 = thread_stream(s->device);
     // 32 bases per suffix (16-byte entries) when half of the free memory holds them (3x10^9 text: 48 GB of the ~130 GB left
     // on a 180 GB part: 7.7 vs 6.3 Gpat/s), else 15 bases (8-byte entries) within a third of it
-    if (env_int("SST_SA_INLINE", 1) != 15 && s->n * 16ull <= free_b / (size_t)std::max(1, env_int("SST_SA_INLINE_DIV", 2)) && SST_CUDA_OK(cudaMalloc(&s->d_saw, s->n * sizeof(uint4)))) {
+    if (opt(OPT_SA_INLINE) != 15 && s->n * 16ull <= free_b / (size_t)opt(OPT_SA_INLINE_DIV) && SST_CUDA_OK(cudaMalloc(&s->d_saw, s->n * sizeof(uint4)))) {
         saw_kernel<<<sm_count(s->device) * 16, 256, 0, st0>>>(s->d_text, s->d_sa, s->n, s->kmer_k, s->d_saw);
         if (!SST_CUDA_OK(cudaGetLastError()) || !SST_CUDA_OK(cudaStreamSynchronize(st0))) { cudaFree(s->d_saw); s->d_saw = nullptr; return false; }
         return true;
@@ -951,7 +1022,7 @@ static bool build_sax(sst_sa* s) {
 }
 
 static bool build_kmer(sst_sa* s) {
-    if (!env_int("SST_SA_KMER", 1) || s->n < 4096) return true;
+    if (!opt(OPT_SA_KMER) || s->n < 4096) return true;
     cudaStream_t st = thread_stream(s->device);
     unsigned* d_max = nullptr;
     unsigned h_max = 0;
@@ -963,8 +1034,8 @@ static bool build_kmer(sst_sa* s) {
     if (h_max > 3) return true;  // not a 2-bit alphabet: the pivot-prefix table serves every level
     int k = 1;
     while (k < 16 && (1ull << (2 * k + 1)) <= s->n) k++;  // 4^k nearest to n (in ratio): about one suffix per table cell
-    k = std::min(k, env_int("SST_SA_KMER_K", 16));
-    if (const int force = env_int("SST_SA_KMER_FORCE", 0); force >= 4 && force <= 16) k = force;  // tests: a table deeper than the text needs
+    k = std::min(k, (int)opt(OPT_SA_KMER_K));
+    if (const int force = (int)opt(OPT_SA_KMER_FORCE); force >= 4 && force <= 16) k = force;  // tests: a table deeper than the text needs
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     while (k > 4 && ((1ull << (2 * k)) + 1) * 4ull > free_b / 4) k--;
@@ -989,6 +1060,46 @@ static bool build_kmer(sst_sa* s) {
     return true;
 }
 
+
+// ---- replica of a finished index on another device (sst_multi_sa_*): device-to-device copies, no rebuild ----
+namespace sst {
+sst_sa* clone_sa(const sst_sa* src, int device) {
+    clear_error();
+    if (!src) { set_error(SST_ERR_ARG, "null argument"); return nullptr; }
+    if (!device_usable(device)) { set_error(SST_ERR_CUDA, "device is not an sm_100 GPU (no CPU fallback)"); return nullptr; }
+    DeviceGuard g(device);
+    if (!g.ok) return nullptr;
+    if (device != src->device) {  // direct NVLink path when the devices can reach each other (otherwise the copy is staged)
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, device, src->device) == cudaSuccess && can) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+            (void)cudaGetLastError();
+        }
+    }
+    auto* s = new sst_sa();
+    s->device = device;
+    s->n = src->n;
+    s->pivot_levels = src->pivot_levels;
+    s->kmer_k = src->kmer_k;
+    cudaStream_t st = thread_stream(device);
+    bool ok = true;
+    auto copy = [&](auto*& dst, const auto* from, size_t bytes) {
+        if (!ok || !from || !bytes) return;
+        ok = SST_CUDA_OK(cudaMalloc(&dst, bytes)) && SST_CUDA_OK(cudaMemcpyPeerAsync(dst, device, from, src->device, bytes, st));
+    };
+    copy(s->d_text, src->d_text, s->n + 64);
+    copy(s->d_sa, src->d_sa, s->n * 4);
+    if (src->pivot_levels) copy(s->d_pivots, src->d_pivots, pivot_table_entries(src->pivot_levels) * sizeof(uint4));
+    if (src->kmer_k) copy(s->d_kmer, src->d_kmer, ((1ull << (2 * src->kmer_k)) + 1) * 4);
+    copy(s->d_sax, src->d_sax, s->n * sizeof(uint2));
+    copy(s->d_saw, src->d_saw, s->n * sizeof(uint4));
+    ok = ok && SST_CUDA_OK(cudaStreamSynchronize(st));
+    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); cudaFree(s->d_sax); cudaFree(s->d_saw); delete s; return nullptr; }
+    return s;
+}
+}  // namespace sst
+
 extern "C" {
 
 int sst_sa_search_device(const sst_sa_t* s, const uint8_t* d_pats, const uint64_t* d_pat_off, size_t npat, int mode,
@@ -1005,6 +1116,38 @@ int sst_sa_search_device(const sst_sa_t* s, const uint8_t* d_pats, const uint64_
     if (!SST_CUDA_OK(cudaMemcpyAsync(&total, d_pat_off + npat, 8, cudaMemcpyDeviceToHost, st)) || !SST_CUDA_OK(cudaStreamSynchronize(st)))
         return SST_ERR_CUDA;
     return sa_search_launch(s, d_pats, d_pat_off, total, npat, mode, d_out_lo, d_out_hi, d_out_pos, st);
+}
+
+// The reference threads a probe counter through every search function (`cnt: &mut usize`, sa_search.rs:98-112,423-436: one
+// increment per loop iteration).  This entry point runs exactly that loop -- the plain binary search over [0, n), no table,
+// on the sub-warp kernel -- and returns sa[l] and the number of iterations per pattern.  A tracing aid, not the fast path.
+int sst_sa_search_probes(const sst_sa_t* s, const uint8_t* pats, const uint64_t* pat_off, size_t npat, uint32_t* out_pos,
+                         uint32_t* out_probes) {
+    clear_error();
+    if (!s || (npat && (!pat_off || !out_probes))) { set_error(SST_ERR_ARG, "null argument"); return SST_ERR_ARG; }
+    if (npat == 0) return SST_OK;
+    DeviceGuard g(s->device);
+    if (!g.ok) return SST_ERR_CUDA;
+    cudaStream_t st = thread_stream(s->device);
+    const size_t byte0 = pat_off[0], bytes = pat_off[npat] - byte0;
+    uint8_t* d_p = nullptr;
+    uint64_t* d_o = nullptr;
+    uint32_t *d_lo = nullptr, *d_pos = nullptr, *d_pr = nullptr;
+    bool ok = SST_CUDA_OK(cudaMalloc(&d_p, bytes + 64)) && SST_CUDA_OK(cudaMalloc(&d_o, (npat + 1) * 8)) && SST_CUDA_OK(cudaMalloc(&d_lo, npat * 4)) &&
+              SST_CUDA_OK(cudaMalloc(&d_pos, npat * 4)) && SST_CUDA_OK(cudaMalloc(&d_pr, npat * 4)) &&
+              (!bytes || SST_CUDA_OK(cudaMemcpyAsync(d_p, pats + byte0, bytes, cudaMemcpyHostToDevice, st))) &&
+              SST_CUDA_OK(cudaMemcpyAsync(d_o, pat_off, (npat + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (ok) {
+        SaParams p{};
+        p.text = s->d_text; p.sa = s->d_sa; p.n = s->n;
+        p.pats = d_p - byte0; p.pat_off = (const unsigned long long*)d_o; p.npat = npat; p.pats_bytes = pat_off[npat];
+        p.out_lo = d_lo; p.out_pos = d_pos; p.out_probes = d_pr;
+        launch_search<8>(p, SST_SA_BINARY, st, s->device);
+        ok = SST_CUDA_OK(cudaGetLastError()) && (!out_pos || SST_CUDA_OK(cudaMemcpyAsync(out_pos, d_pos, npat * 4, cudaMemcpyDeviceToHost, st))) &&
+             SST_CUDA_OK(cudaMemcpyAsync(out_probes, d_pr, npat * 4, cudaMemcpyDeviceToHost, st)) && SST_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    cudaFree(d_p); cudaFree(d_o); cudaFree(d_lo); cudaFree(d_pos); cudaFree(d_pr);
+    return ok ? SST_OK : SST_ERR_CUDA;
 }
 
 // Per (host thread, device) staging ring for the host-buffer SA path (see Staging in stree_search.cu).
@@ -1075,7 +1218,7 @@ int sst_sa_search(const sst_sa_t* s, const uint8_t* pats, const uint64_t* pat_of
     if (!g.ok) return SST_ERR_CUDA;
     cudaStream_t s_in = thread_copy_stream(dev, 0), s_k = thread_stream(dev), s_out = thread_copy_stream(dev, 1);
     if (!s_in || !s_k || !s_out) return SST_ERR_CUDA;
-    const size_t chunk = std::max<size_t>((size_t)env_int("SST_SA_CHUNK", 1 << 20), 16);
+    const size_t chunk = (size_t)opt(OPT_SA_CHUNK);
     const size_t nchunks = div_ceil(npat, chunk);
     size_t max_bytes = 0;
     for (size_t c = 0; c < nchunks; c++) {

@@ -150,7 +150,7 @@ bool validate_keys(const uint32_t* d_sorted, size_t n, int device) {
     bool ok = SST_CUDA_OK(cudaMemsetAsync(d_flags, 0, sizeof(unsigned), st));
     unsigned flags = 0;
     if (ok) {
-        check_keys_kernel<<<std::min<unsigned>(grid_for(n), 148 * 16), kBuildThreads, 0, st>>>(d_sorted, n, d_flags);
+        check_keys_kernel<<<std::min<unsigned>(grid_for(n), cur_sms() * 16), kBuildThreads, 0, st>>>(d_sorted, n, d_flags);
         ok = SST_CUDA_OK(cudaGetLastError()) &&
              SST_CUDA_OK(cudaMemcpyAsync(&flags, d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, st)) &&
              SST_CUDA_OK(cudaStreamSynchronize(st));
@@ -165,17 +165,15 @@ bool validate_keys(const uint32_t* d_sorted, size_t n, int device) {
 // Optional persisting-L2 carve-out (SST_PERSIST != 0): lets a per-launch access-policy window pin
 // the last internal level.  Device-wide limit, so only touched when asked for.
 void configure_persisting_l2(sst_index* idx) {
-    const char* e = getenv("SST_PERSIST");
-    if (!e || atoi(e) == 0) return;
+    if (opt(OPT_PERSIST) == 0) return;
     int max_persist = 0, max_window = 0;
     cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, idx->device);
     cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, idx->device);
     if (max_persist <= 0 || max_window <= 0) return;
-    const char* mb = getenv("SST_PERSIST_MB");
     size_t want = (size_t)max_persist;
-    if (mb && *mb) want = std::min<size_t>((size_t)atoi(mb) << 20, (size_t)max_persist);
+    if (const long long mb = opt(OPT_PERSIST_MB); mb >= 0) want = std::min<size_t>((size_t)mb << 20, (size_t)max_persist);
     const cudaError_t rc = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-    if (getenv("SST_DEBUG")) {
+    if (opt(OPT_DEBUG)) {
         size_t got = 0;
         cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize);
         fprintf(stderr, "[sst] persisting L2: max=%d window_max=%d set rc=%d limit now=%zu\n", max_persist, max_window, (int)rc, got);
@@ -242,10 +240,10 @@ sst_index* build_plain(const uint32_t* d_sorted, bool, size_t n, uint32_t node_b
         if (h + 1 < H) inner_slots += sh.level_slots[h];
     }
     cudaStream_t st = thread_stream(device);
-    plain_leaf_kernel<<<std::min<unsigned>(grid_for(sh.level_slots[H - 1]), 148 * 32), kBuildThreads, 0, st>>>(
+    plain_leaf_kernel<<<std::min<unsigned>(grid_for(sh.level_slots[H - 1]), cur_sms() * 32), kBuildThreads, 0, st>>>(
         d_sorted, idx->d_tree, sh, 1);
     if (inner_slots)
-        plain_inner_kernel<<<std::min<unsigned>(grid_for(inner_slots), 148 * 32), kBuildThreads, 0, st>>>(
+        plain_inner_kernel<<<std::min<unsigned>(grid_for(inner_slots), cur_sms() * 32), kBuildThreads, 0, st>>>(
             d_sorted, idx->d_tree, sh, inner_slots);
     fill_kernel<<<1, 16, 0, st>>>(idx->d_tree + n_blocks * 16, 16, kMax);  // guard node
     if (!SST_CUDA_OK(cudaGetLastError()) || !SST_CUDA_OK(cudaStreamSynchronize(st))) {
@@ -509,15 +507,14 @@ bool build_compressed_level(sst_index* idx) {
     if (idx->variant != SST_PLAIN || idx->node_b != 16 || idx->levels < 3) return true;
     // Opt-in experiment (SST_C5=1): measured at 2^28 keys it cuts DRAM reads by 15 % (7.99 -> 6.77 GB per
     // 10^8 queries, L2 hit 47 -> 54 %) but the extra load and instructions cost 8 % of run time.
-    const char* e = getenv("SST_C5");
-    if (!e || atoi(e) == 0) return true;
+    if (!opt(OPT_C5)) return true;
     const int h = idx->levels - 2;
     const size_t nodes = idx->layer_sizes[h];
     if (idx->top_level > h) return true;
     cudaStream_t st = thread_stream(idx->device);
     bool ok = SST_CUDA_OK(cudaMalloc(&idx->d_c5, nodes * 32)) && SST_CUDA_OK(cudaMalloc(&idx->d_h5, nodes * 4));
     if (ok) {
-        compress_level_kernel<<<std::min<unsigned>(grid_for(nodes), 148 * 16), kBuildThreads, 0, st>>>(
+        compress_level_kernel<<<std::min<unsigned>(grid_for(nodes), cur_sms() * 16), kBuildThreads, 0, st>>>(
             idx->d_tree + idx->offsets[h] * 16, nodes, idx->d_c5, idx->d_h5);
         ok = SST_CUDA_OK(cudaGetLastError()) && SST_CUDA_OK(cudaStreamSynchronize(st));
     }
@@ -551,9 +548,9 @@ bool build_top_table(sst_index* idx, const uint32_t* d_sorted) {
               SST_CUDA_OK(cudaMalloc(&idx->d_top_low, low_bytes)) && SST_CUDA_OK(cudaMemsetAsync(idx->d_top_table, 0, table_bytes, st)) &&
               SST_CUDA_OK(cudaMemsetAsync(idx->d_top_low, 0, low_bytes, st));
     if (ok) {
-        top_bounds_kernel<<<std::min<unsigned>(grid_for(nb), 148 * 8), kBuildThreads, 0, st>>>(
+        top_bounds_kernel<<<std::min<unsigned>(grid_for(nb), cur_sms() * 8), kBuildThreads, 0, st>>>(
             d_sorted, (unsigned)nb, ipow(17, H - 1 - t), (idx->flags & SST_LEFT_MAX) ? 1 : 0, d_bkeys, idx->d_top_low);
-        top_table_kernel<<<std::min<unsigned>(grid_for((1u << 15) + 1), 148 * 8), kBuildThreads, 0, st>>>(d_bkeys, (unsigned)nb, idx->d_top_table);
+        top_table_kernel<<<std::min<unsigned>(grid_for((1u << 15) + 1), cur_sms() * 8), kBuildThreads, 0, st>>>(d_bkeys, (unsigned)nb, idx->d_top_table);
         ok = SST_CUDA_OK(cudaGetLastError()) && SST_CUDA_OK(cudaStreamSynchronize(st));
     }
     cudaFree(d_bkeys);
@@ -594,7 +591,7 @@ sst_index* build_partitioned(const uint32_t* d_sorted, size_t n, uint32_t b, int
     {
         uint32_t* d_ps = nullptr;
         if (!SST_CUDA_OK(cudaMalloc(&d_ps, (parts + 1) * 4))) return nullptr;
-        part_start_kernel<<<std::min<unsigned>(grid_for(parts + 1), 148 * 32), kBuildThreads, 0, st>>>(d_sorted, n, (unsigned)shift, parts, d_ps);
+        part_start_kernel<<<std::min<unsigned>(grid_for(parts + 1), cur_sms() * 32), kBuildThreads, 0, st>>>(d_sorted, n, (unsigned)shift, parts, d_ps);
         bool ok = SST_CUDA_OK(cudaGetLastError()) &&
                   SST_CUDA_OK(cudaMemcpyAsync(fine.data(), d_ps, (parts + 1) * 4, cudaMemcpyDeviceToHost, st)) &&
                   SST_CUDA_OK(cudaStreamSynchronize(st));
@@ -736,7 +733,7 @@ sst_index* build_partitioned(const uint32_t* d_sorted, size_t n, uint32_t b, int
     unsigned long long* d_ne_pos = nullptr;
     uint32_t *d_ne_start = nullptr, *d_ne_cnt = nullptr;
     ok = ok && upload(&idx->d_part_start, ps, st) && upload(&idx->d_part_pos, part_pos, st);
-    const unsigned maxgrid = 148 * 32;
+    const unsigned maxgrid = cur_sms() * 32;
     const int H = (int)height;
     if (ok) {
         if (COMPACT) {
@@ -809,7 +806,7 @@ sst_index* build_eytzinger(const uint32_t* d_sorted, size_t n, int device) {
     unsigned flags = 0;
     bool ok = SST_CUDA_OK(cudaMalloc(&d_flags, 4)) && SST_CUDA_OK(cudaMemsetAsync(d_flags, 0, 4, st));
     if (ok) {
-        check_sorted_kernel<<<std::min<unsigned>(grid_for(n), 148 * 16), kBuildThreads, 0, st>>>(d_sorted, n, d_flags);
+        check_sorted_kernel<<<std::min<unsigned>(grid_for(n), cur_sms() * 16), kBuildThreads, 0, st>>>(d_sorted, n, d_flags);
         ok = SST_CUDA_OK(cudaMemcpyAsync(&flags, d_flags, 4, cudaMemcpyDeviceToHost, st)) && SST_CUDA_OK(cudaStreamSynchronize(st));
     }
     cudaFree(d_flags);
@@ -825,7 +822,7 @@ sst_index* build_eytzinger(const uint32_t* d_sorted, size_t n, int device) {
     idx->n_blocks = div_ceil(n + 1, 16);
     idx->eytz_words = n + 1;
     if (!SST_CUDA_OK(cudaMalloc(&idx->d_tree, (idx->n_blocks + 1) * 64))) { delete idx; return nullptr; }
-    eytzinger_build_kernel<<<std::min<unsigned>(grid_for(n + 1), 148 * 32), kBuildThreads, 0, st>>>(d_sorted, n, H, idx->d_tree);
+    eytzinger_build_kernel<<<std::min<unsigned>(grid_for(n + 1), cur_sms() * 32), kBuildThreads, 0, st>>>(d_sorted, n, H, idx->d_tree);
     if (!SST_CUDA_OK(cudaGetLastError()) || !SST_CUDA_OK(cudaStreamSynchronize(st))) { cudaFree(idx->d_tree); delete idx; return nullptr; }
     idx->eytz_h = H;
     finalize_view(idx);

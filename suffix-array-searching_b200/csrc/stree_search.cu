@@ -675,11 +675,6 @@ gather_probe_kernel(const uint32_t* __restrict__ buf, unsigned long long nodes, 
 // ------------------------------------------------------------------------------------------------
 // Launch planning
 // ------------------------------------------------------------------------------------------------
-int env_int(const char* name, int dflt) {
-    const char* s = getenv(name);
-    return (s && *s) ? atoi(s) : dflt;
-}
-
 thread_local int g_host_grid_cap = 0;  // 0 = no cap (device-resident batches)
 
 bool fast_eligible(const sst_index* idx) { return idx->variant == SST_PLAIN && idx->node_b == 16; }
@@ -693,12 +688,12 @@ int launch_fast(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t*
     fp.levels = idx->levels;
     fp.leaf_slots = (unsigned long long)idx->layer_sizes[idx->levels - 1] * 16;
     fp.n = idx->n;
-    fp.hints = env_int("SST_HINTS", 3);
+    fp.hints = (int)opt(OPT_HINTS);
     for (int h = 0; h < idx->levels; h++) {
         fp.level_slot[h] = (unsigned long long)idx->offsets[h] * 16;
-        if (idx->layer_sizes[h] * 64 <= (size_t)env_int("SST_L1_LEVEL_KB", 256) * 1024) fp.l1_levels |= 1u << h;
+        if (idx->layer_sizes[h] * 64 <= (size_t)opt(OPT_L1_LEVEL_KB) * 1024) fp.l1_levels |= 1u << h;
     }
-    if (G == 2 && TOP && idx->d_c5 && env_int("SST_USE_C5", 1)) { fp.c5 = idx->d_c5; fp.h5 = idx->d_h5; }
+    if (G == 2 && TOP && idx->d_c5 && opt(OPT_USE_C5)) { fp.c5 = idx->d_c5; fp.h5 = idx->d_h5; }
     size_t smem_bytes = 0;
     if (TOP) {
         fp.top_level = idx->top_level;
@@ -707,13 +702,13 @@ int launch_fast(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t*
         fp.top_nbound = (unsigned)idx->top_nbound;
         smem_bytes = kTopTableBytes + ((idx->top_nbound * 2 + 15) & ~(size_t)15);
     }
-    const int threads = env_int("SST_THREADS", 1024);
+    const int threads = std::max(32, (int)opt(OPT_THREADS) & ~31);
     const int sms = sm_count(idx->device);
     const size_t per_cta = (size_t)(threads / 32) * 32 * T;
-    int grid = (int)std::min<size_t>(div_ceil(nq, per_cta), (size_t)sms * (size_t)env_int("SST_WAVES", 1));
+    int grid = (int)std::min<size_t>(div_ceil(nq, per_cta), (size_t)sms * (size_t)opt(OPT_WAVES));
     // Host-buffer path: sst_query caps the grid (g_host_grid_cap) so that the kernel runs through a chunk's whole copy period
     // at low DRAM intensity instead of saturating the random-access rate in bursts next to the copy engines.
-    if (const int cap = env_int("SST_GRID_CAP", g_host_grid_cap); cap > 0 && grid > cap) grid = cap;
+    if (const int cap = opt(OPT_GRID_CAP) > 0 ? (int)opt(OPT_GRID_CAP) : g_host_grid_cap; cap > 0 && grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     auto kern = stree_search_fast<G, T, TOP>;
     if (smem_bytes > 48 * 1024 &&
@@ -728,7 +723,7 @@ int launch_fast(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t*
     int nattr = 0;
     // Optional: pin the last internal level (the one that just fits L2) with a persisting
     // access-policy window for this launch only; the leaf level streams through.
-    const int persist = env_int("SST_PERSIST", 0);
+    const int persist = (int)opt(OPT_PERSIST);
     if (persist && idx->levels >= 2 && idx->persist_ok) {
         const int h = idx->levels - 2;
         attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
@@ -745,7 +740,7 @@ int launch_fast(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t*
             if (!SST_CUDA_OK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &sv))) return SST_ERR_CUDA;
             nattr = 0;
         }
-        if (getenv("SST_DEBUG"))
+        if (opt(OPT_DEBUG))
             fprintf(stderr, "[sst] access window base=%p bytes=%zu hit=%.2f mode=%s\n", attr[0].val.accessPolicyWindow.base_ptr,
                     (size_t)attr[0].val.accessPolicyWindow.num_bytes, attr[0].val.accessPolicyWindow.hitRatio, nattr ? "launch" : "stream");
     }
@@ -769,26 +764,29 @@ int launch_fast_top(const sst_index* idx, bool top, const uint32_t* d_qs, size_t
 int resolve_scheme(const sst_index* idx, int scheme, size_t nq) {
     if (scheme != SST_SCHEME_AUTO) return scheme;
     if (idx->variant == SST_EYTZINGER) return SST_SCHEME_GENERIC;
-    if (bucketed_eligible(idx) && idx->n >= (size_t)env_int("SST_BK_AUTO_MIN_N", 1 << 25)) {  // plain and Map-partitioned trees
+    const int forced = (int)opt(OPT_SCHEME);  // A/B runs: what AUTO resolves to (-1 = the measured rule below)
+    if (bucketed_eligible(idx) && idx->n >= (size_t)opt(OPT_BK_AUTO_MIN_N)) {  // plain and Map-partitioned trees
         // measured crossovers (tools/bucketed_once.py): 2^28 keys ~1.2x10^7 queries, 2^26 keys ~4x10^7, 2^25 keys ~6x10^7;
         // at 2^24 keys and below the tree is L2-resident and the direct kernel always wins (65.7 vs 45.5 Gq/s)
         const size_t min_nq = idx->n >= ((size_t)1 << 27) ? (size_t)1 << 24 : idx->n >= ((size_t)1 << 26) ? (size_t)3 << 24 : (size_t)1 << 26;
-        if (nq >= (size_t)env_int("SST_BK_AUTO_MIN_NQ", (int)min_nq)) return env_int("SST_SCHEME", SST_SCHEME_BUCKETED);
+        if (nq >= (opt(OPT_BK_AUTO_MIN_NQ) >= 0 ? (size_t)opt(OPT_BK_AUTO_MIN_NQ) : min_nq)) return forced >= 0 ? forced : SST_SCHEME_BUCKETED;
     }
-    if (idx->variant != SST_PLAIN && idx->node_b == 16 && env_int("SST_PGROUP", 1)) return SST_SCHEME_AUTO;  // lane-group kernel
+    if (idx->variant != SST_PLAIN && idx->node_b == 16 && opt(OPT_PGROUP)) return SST_SCHEME_AUTO;  // lane-group kernel
     if (!fast_eligible(idx)) return SST_SCHEME_GENERIC;
-    if (nq < (size_t)env_int("SST_TABLE_MIN_NQ", 1 << 17)) return env_int("SST_SCHEME", SST_SCHEME_GENERIC);
-    return env_int("SST_SCHEME", top_eligible(idx) ? SST_SCHEME_TABLE : SST_SCHEME_GROUP2);
+    if (nq < (size_t)opt(OPT_TABLE_MIN_NQ)) return forced >= 0 ? forced : SST_SCHEME_GENERIC;
+    return forced >= 0 ? forced : (top_eligible(idx) ? SST_SCHEME_TABLE : SST_SCHEME_GROUP2);
 }
 
 }  // namespace
 
-// Kernel launches of one sst_query_device call.  The reordered-batch pipeline runs 7 kernels per 2^27-query
-// sub-batch (rank, column sums, plan, offsets, scatter, search, gather) and one more gather for the index output.
+// Kernel launches of one sst_query_device call.  The reordered-batch pipeline runs 4 kernels per 2^27-query sub-batch
+// (partition, work items, search, un-permute) and one more un-permute for the index output; the round-1
+// pipeline (BK_V1) ran 7 (rank, column sums, plan, offsets, scatter, search, gather).
 int query_launch_count(const sst_index* idx, int scheme, size_t nq, bool want_idx) {
     if (nq == 0) return 0;
     if (resolve_scheme(idx, scheme, nq) != SST_SCHEME_BUCKETED) return 1;
-    return (int)(div_ceil(nq, (size_t)1 << 27) * ((want_idx ? 8 : 7) + (idx->variant == SST_PLAIN ? 0 : 1) +
+    const int base = opt(OPT_BK_V1) ? 7 : 4;
+    return (int)(div_ceil(nq, (size_t)1 << 27) * (base + (want_idx ? 1 : 0) + (idx->variant == SST_PLAIN ? 0 : 1) +
                                                    (want_idx && idx->variant != SST_PLAIN && idx->variant != SST_MAP ? 1 : 0)));  // partitioned: + the q > MAX fix-up (+ flat -> sorted index)
 }
 
@@ -806,13 +804,13 @@ int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t
     }
     auto launch_pgroup = [&]() {  // lane-group kernel of the partitioned layouts
         const int sms = sm_count(idx->device);
-        const int T = env_int("SST_PT", 1);  // measured: T=1 27.7 vs T=2 23.9 Gq/s (Simple, 2^28 keys)
+        const int T = (int)opt(OPT_PT);  // measured: T=1 27.7 vs T=2 23.9 Gq/s (Simple, 2^28 keys)
         const int grid = (int)std::min<size_t>(div_ceil(nq, (size_t)16 * 32 * T), (size_t)sms * 2);
         if (T == 1) pstree_search_group<1><<<grid, 512, 0, st>>>(idx->view, d_qs, nq, d_vals, d_idx);
         else pstree_search_group<2><<<grid, 512, 0, st>>>(idx->view, d_qs, nq, d_vals, d_idx);
         return SST_CUDA_OK(cudaGetLastError()) ? SST_OK : SST_ERR_CUDA;
     };
-    const bool pgroup = idx->variant != SST_PLAIN && idx->node_b == 16 && env_int("SST_PGROUP", 1);
+    const bool pgroup = idx->variant != SST_PLAIN && idx->node_b == 16 && opt(OPT_PGROUP);
     if (scheme == SST_SCHEME_AUTO && pgroup && resolve_scheme(idx, scheme, nq) != SST_SCHEME_BUCKETED) return launch_pgroup();
     const bool was_auto = scheme == SST_SCHEME_AUTO;
     scheme = resolve_scheme(idx, scheme, nq);
@@ -829,13 +827,13 @@ int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t
         set_error(SST_ERR_UNSUPPORTED, "the group/table kernels serve the plain B=16 tree; use SST_SCHEME_AUTO or SST_SCHEME_GENERIC");
         return SST_ERR_UNSUPPORTED;
     }
-    const int T = env_int("SST_T", 2);
+    const int T = (int)opt(OPT_T);
     switch (scheme) {
         case SST_SCHEME_BUCKETED:
             return launch_bucketed(idx, d_qs, nq, d_vals, d_idx, st);
         case SST_SCHEME_TABLE: {
             const bool top = top_eligible(idx);  // trees of height 1 have nothing above the leaf
-            if (env_int("SST_TABLE_G", 2) == 4) {
+            if (opt(OPT_TABLE_G) == 4) {
                 if (T == 1) return launch_fast_top<4, 1>(idx, top, d_qs, nq, d_vals, d_idx, st);
                 return launch_fast_top<4, 2>(idx, top, d_qs, nq, d_vals, d_idx, st);
             }
@@ -889,6 +887,15 @@ int sst_query_plan(const sst_index_t* idx, size_t nq, int scheme, int want_index
 }
 
 int sst_last_stage_ms(double* out, int n) { return last_stage_ms(out, n); }
+
+int sst_query_reserve(const sst_index_t* idx, size_t nq, int want_index) {
+    clear_error();
+    if (!idx) { set_error(SST_ERR_ARG, "null argument"); return SST_ERR_ARG; }
+    DeviceGuard g(idx->device);
+    if (!g.ok) return SST_ERR_CUDA;
+    return reserve_bucketed(idx, nq, want_index != 0);
+}
+void sst_query_release(void) { release_bucketed_scratch(); }
 
 int sst_query_device(const sst_index_t* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_out_vals, uint64_t* d_out_idx,
                      int scheme, void* stream) {
@@ -968,7 +975,7 @@ int sst_query(const sst_index_t* idx, const uint32_t* qs, size_t nq, uint32_t* o
     if (dev < 0 || dev >= 64) { set_error(SST_ERR_ARG, "device index out of range"); return SST_ERR_ARG; }
     cudaStream_t s_in = thread_copy_stream(dev, 0), s_k = thread_stream(dev), s_out = thread_copy_stream(dev, 1);
     if (!s_in || !s_k || !s_out) return SST_ERR_CUDA;
-    const size_t chunk = std::max<size_t>((size_t)env_int("SST_CHUNK", 1 << 22), 1024);
+    const size_t chunk = (size_t)opt(OPT_CHUNK);
     const size_t nchunks = div_ceil(nq, chunk);
     const int NB = kRing;
     Staging& sg = g_staging[dev];
@@ -985,7 +992,7 @@ int sst_query(const sst_index_t* idx, const uint32_t* qs, size_t nq, uint32_t* o
     // SST_HOST_GRID_CAP: 0 = this rule, < 0 = full width, > 0 = CTAs.
     struct CapGuard { ~CapGuard() { g_host_grid_cap = 0; } } cap_guard;
     {
-        int cap = env_int("SST_HOST_GRID_CAP", 0);
+        int cap = (int)opt(OPT_HOST_GRID_CAP);
         if (cap == 0 && idx->variant == SST_PLAIN && idx->node_b == 16 && nchunks >= 3) {  // (fewer chunks: nothing to overlap with)
             int l2 = 0;
             cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev);
@@ -1007,7 +1014,7 @@ int sst_query(const sst_index_t* idx, const uint32_t* qs, size_t nq, uint32_t* o
         if (c >= (size_t)NB && !SST_CUDA_OK(cudaStreamWaitEvent(s_in, sg.e_out[b], 0))) { rc = SST_ERR_CUDA; break; }
         if (!SST_CUDA_OK(cudaMemcpyAsync(sg.q[b], qs + off, cnt * 4, cudaMemcpyHostToDevice, s_in)) ||
             !SST_CUDA_OK(cudaEventRecord(sg.e_in[b], s_in)) || !SST_CUDA_OK(cudaStreamWaitEvent(s_k, sg.e_in[b], 0))) { rc = SST_ERR_CUDA; break; }
-        rc = env_int("SST_E2E_NO_KERNEL", 0) ? SST_OK : launch_query(idx, sg.q[b], cnt, sg.v[b], out_idx ? sg.i[b] : nullptr, scheme, s_k);  // (debug: copies only)
+        rc = launch_query(idx, sg.q[b], cnt, sg.v[b], out_idx ? sg.i[b] : nullptr, scheme, s_k);
         if (rc != SST_OK) break;
         if (!SST_CUDA_OK(cudaEventRecord(sg.e_k[b], s_k)) || !SST_CUDA_OK(cudaStreamWaitEvent(s_out, sg.e_k[b], 0)) ||
             !SST_CUDA_OK(cudaMemcpyAsync(out_vals + off, sg.v[b], cnt * 4, cudaMemcpyDeviceToHost, s_out)) ||

@@ -14,10 +14,22 @@ fn main() {
               "-Xcompiler", "-fPIC", "-shared", "-o"])
         .arg(&lib)
         .arg(format!("-I{}", include.display()));
-    for f in ["runtime.cu", "stree_build.cu", "stree_search.cu", "sa.cu", "multi.cu", "formats.cu"] {
-        cmd.arg(csrc.join(f));
-        println!("cargo:rerun-if-changed={}", csrc.join(f).display());
+    // every csrc/*.cu, in a stable order (the same set csrc/Makefile builds with $(wildcard *.cu);
+    // tests/test_abi.py::test_build_rs_compiles_every_source checks that no file list is hard-coded here)
+    let mut sources: Vec<PathBuf> = std::fs::read_dir(&csrc)
+        .expect("csrc/ not found")
+        .filter_map(|e| e.ok().map(|e| e.path()))
+        .filter(|p| p.extension().map_or(false, |x| x == "cu"))
+        .collect();
+    sources.sort();
+    assert!(!sources.is_empty(), "no CUDA sources under {}", csrc.display());
+    for f in &sources {
+        cmd.arg(f);
+        println!("cargo:rerun-if-changed={}", f.display());
     }
+    println!("cargo:rerun-if-changed={}", csrc.join("common.cuh").display());
+    println!("cargo:rerun-if-changed={}", include.join("sst_b200.h").display());
+    cmd.arg("-lpthread");
     let status = cmd.status().expect("failed to run nvcc");
     assert!(status.success(), "nvcc failed");
     println!("cargo:rustc-link-search=native={}", out.display());

@@ -40,6 +40,8 @@ extern "C" {
     fn sst_sa_check(sa: *const SstSa, out_violations: *mut u64) -> c_int;
     fn sst_sa_search(sa: *const SstSa, pats: *const u8, pat_off: *const u64, npat: usize, mode: c_int,
                      out_lo: *mut u32, out_hi: *mut u32, out_pos: *mut u32) -> c_int;
+    fn sst_sa_search_probes(sa: *const SstSa, pats: *const u8, pat_off: *const u64, npat: usize,
+                            out_pos: *mut u32, out_probes: *mut u32) -> c_int;
 }
 
 fn last_error() -> String { unsafe { CStr::from_ptr(sst_last_error()).to_string_lossy().into_owned() } }
@@ -193,8 +195,13 @@ impl<'t> GpuSa<'t> {
         pos.into_iter().map(|p| p as usize).collect()
     }
 }
-/// `fn(&SaNaive, &[u8], &mut usize) -> usize` (type F1, sa_search.rs:453).
+/// `fn(&SaNaive, &[u8], &mut usize) -> usize` (type F1, sa_search.rs:453).  `cnt` advances by the number of probes the
+/// reference's loop makes for this pattern (sa_search.rs:98-112: one per iteration), counted on the device by the plain
+/// binary-search kernel (`sst_sa_search_probes`); use `GpuSa::binary_search_batch` when the counter is not needed.
 pub fn binary_search(sa: &GpuSa, q: &[u8], cnt: &mut usize) -> usize {
-    *cnt += (usize::BITS - 1) as usize;  // probes are not counted on the device
-    sa.binary_search_batch(&[q], false)[0]
+    let off = [0u64, q.len() as u64];
+    let (mut pos, mut probes) = (0u32, 0u32);
+    check(unsafe { sst_sa_search_probes(sa.h, q.as_ptr(), off.as_ptr(), 1, &mut pos, &mut probes) });
+    *cnt += probes as usize;
+    pos as usize
 }

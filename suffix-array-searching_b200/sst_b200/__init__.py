@@ -56,6 +56,13 @@ def lib() -> C.CDLL:
         "sst_last_status": (i32, []),
         "sst_device_count": (i32, []),
         "sst_version": (C.c_char_p, []),
+        "sst_set_option": (i32, [C.c_char_p, C.c_longlong]),
+        "sst_get_option": (i32, [C.c_char_p, vp]),
+        "sst_reset_options": (None, []),
+        "sst_option_count": (i32, []),
+        "sst_option_name": (C.c_char_p, [i32]),
+        "sst_query_reserve": (i32, [vp, sz, i32]),
+        "sst_query_release": (None, []),
         "sst_bind_thread_to_device": (i32, [i32]),
         "sst_host_alloc": (vp, [sz]),
         "sst_host_free": (None, [vp]),
@@ -90,8 +97,16 @@ def lib() -> C.CDLL:
         "sst_sa_len": (sz, [vp]),
         "sst_sa_get": (i32, [vp, vp]),
         "sst_sa_check": (i32, [vp, vp]),
+        "sst_sa_gather": (i32, [vp, vp, sz, vp]),
         "sst_sa_search": (i32, [vp, vp, vp, sz, i32, vp, vp, vp]),
         "sst_sa_search_device": (i32, [vp, vp, vp, sz, i32, vp, vp, vp, vp]),
+        "sst_sa_search_probes": (i32, [vp, vp, vp, sz, vp, vp]),
+        "sst_multi_query_device": (i32, [vp, vp, vp, vp, vp, i32]),
+        "sst_multi_sa_build": (vp, [vp, sz, vp, i32]),
+        "sst_multi_sa_from_parts": (vp, [vp, sz, vp, vp, i32]),
+        "sst_multi_sa_search": (i32, [vp, vp, vp, sz, i32, vp, vp, vp]),
+        "sst_multi_sa_devices": (i32, [vp]),
+        "sst_multi_sa_free": (None, [vp]),
         "sst_fasta_encode": (i32, [vp, sz, vp, vp, i32]),
         "sst_fasta_encode_device": (i32, [vp, sz, vp, vp, i32]),
         "sst_kmer_keys": (i32, [vp, sz, u32, sz, vp, vp, i32, i32]),
@@ -127,6 +142,45 @@ def _check(rc: int):
 
 def device_count() -> int:
     return lib().sst_device_count()
+
+
+def set_option(name: str, value: int) -> None:
+    """Tuning / A-B option of the library (csrc/common.cuh: SST_OPTION_LIST); `name` with or without the SST_ prefix."""
+    _check(lib().sst_set_option(name.encode(), int(value)))
+
+
+def get_option(name: str) -> int:
+    v = C.c_longlong(0)
+    _check(lib().sst_get_option(name.encode(), C.byref(v)))
+    return v.value
+
+
+def reset_options() -> None:
+    lib().sst_reset_options()
+
+
+def option_names():
+    L = lib()
+    return [L.sst_option_name(i).decode() for i in range(L.sst_option_count())]
+
+
+class options:
+    """Context manager: `with sst.options(BK_MIN_N=0, BK_R=256): ...` sets options and restores the previous values."""
+
+    def __init__(self, **kw):
+        self.kw = kw
+        self.old = {}
+
+    def __enter__(self):
+        for k, v in self.kw.items():
+            self.old[k] = get_option(k)
+            set_option(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self.old.items():
+            set_option(k, v)
+        return False
 
 
 def bind_thread_to_device(device: int) -> int:
@@ -259,6 +313,10 @@ class SearchIndex:
         idx = np.empty(q.size, np.uint64) if want_index else None
         _check(L.sst_query(self._h, _ptr(q), q.size, _ptr(vals), _ptr(idx), scheme))
         return (vals, idx) if want_index else vals
+
+    def reserve(self, nq: int, want_index: bool = False) -> None:
+        """Pre-size the calling thread's pipeline scratch so that device-side queries of up to nq allocate nothing."""
+        _check(lib().sst_query_reserve(self._h, int(nq), int(want_index)))
 
     def query_one(self, q: int, scheme: int = SCHEME_AUTO) -> int:
         """SearchScheme::query_one (lib.rs:52-54)."""
@@ -428,6 +486,68 @@ class MultiIndex:
         return (vals, idx) if want_index else vals
 
 
+    def query_device(self, shards, scheme=SCHEME_AUTO, want_index=False):
+        """Device-resident shards: shards[i] is a contiguous int32/uint32 CUDA tensor on the device of replica i.
+        Returns the per-shard value tensors (and index tensors)."""
+        import torch
+
+        G = self.n_devices
+        assert len(shards) == G
+        vals = [torch.empty_like(q) for q in shards]
+        idx = [torch.empty(q.numel(), dtype=torch.int64, device=q.device) for q in shards] if want_index else None
+        for q in shards:
+            torch.cuda.synchronize(q.device)  # the shards may come from other streams
+        PP = C.c_void_p * G
+        qp = PP(*[q.data_ptr() for q in shards])
+        vp_ = PP(*[v.data_ptr() for v in vals])
+        ip = PP(*[i.data_ptr() for i in idx]) if want_index else None
+        nq = (C.c_size_t * G)(*[q.numel() for q in shards])
+        _check(lib().sst_multi_query_device(self._h, qp, nq, vp_, ip, scheme))
+        return (vals, idx) if want_index else vals
+
+
+class MultiSa:
+    """Text + suffix array replicated on several GPUs (built once, copied peer to peer), patterns sharded contiguously."""
+
+    def __init__(self, handle):
+        if not handle:
+            _raise()
+        self._h = C.c_void_p(handle)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h and _lib is not None:
+            _lib.sst_multi_sa_free(h)
+            self._h = None
+
+    @classmethod
+    def build(cls, text, devices):
+        t = np.ascontiguousarray(text, np.uint8)
+        d = np.ascontiguousarray(devices, np.int32)
+        return cls(lib().sst_multi_sa_build(_ptr(t), t.size, _ptr(d), d.size))
+
+    @classmethod
+    def from_parts(cls, text, sa, devices):
+        t = np.ascontiguousarray(text, np.uint8)
+        s = _host_u32(sa)
+        d = np.ascontiguousarray(devices, np.int32)
+        return cls(lib().sst_multi_sa_from_parts(_ptr(t), t.size, _ptr(s), _ptr(d), d.size))
+
+    @property
+    def n_devices(self) -> int:
+        return lib().sst_multi_sa_devices(self._h)
+
+    def search(self, flat, off, mode=SA_BINARY, want_hi=True):
+        flat = np.ascontiguousarray(flat, np.uint8)
+        off = np.ascontiguousarray(off, np.uint64)
+        npat = off.size - 1
+        lo = np.empty(npat, np.uint32)
+        hi = np.empty(npat, np.uint32) if want_hi else None
+        pos = np.empty(npat, np.uint32)
+        _check(lib().sst_multi_sa_search(self._h, _ptr(flat), _ptr(off), npat, mode, _ptr(lo), _ptr(hi), _ptr(pos)))
+        return lo, hi, pos
+
+
 # ----------------------------------------------------------------------------------------------
 # suffix arrays (suffix-array-searching/src/sa_search.rs)
 # ----------------------------------------------------------------------------------------------
@@ -481,6 +601,13 @@ class SaNaive:
         _check(lib().sst_sa_get(self._h, _ptr(out)))
         return out
 
+    def gather(self, positions) -> np.ndarray:
+        """sa[positions] (0xffffffff beyond the end) without copying the whole array."""
+        p = np.ascontiguousarray(positions, np.uint64)
+        out = np.empty(p.size, np.uint32)
+        _check(lib().sst_sa_gather(self._h, _ptr(p), p.size, _ptr(out)))
+        return out
+
     def check(self) -> int:
         """Adjacent-suffix strict order (sa_search.rs:36-38): number of violations."""
         v = C.c_uint64(0)
@@ -497,6 +624,17 @@ class SaNaive:
         pos = np.empty(npat, np.uint32)
         _check(lib().sst_sa_search(self._h, _ptr(flat), _ptr(off), npat, mode, _ptr(lo), _ptr(hi), _ptr(pos)))
         return lo, hi, pos
+
+    def search_probes(self, flat, off):
+        """The reference's loop itself (plain binary search over [0, n)) with its probe counter `cnt`
+        (sa_search.rs:98-112): returns (sa[l], iterations) per pattern."""
+        flat = np.ascontiguousarray(flat, np.uint8)
+        off = np.ascontiguousarray(off, np.uint64)
+        npat = off.size - 1
+        pos = np.empty(npat, np.uint32)
+        probes = np.empty(npat, np.uint32)
+        _check(lib().sst_sa_search_probes(self._h, _ptr(flat), _ptr(off), npat, _ptr(pos), _ptr(probes)))
+        return pos, probes
 
     def binary_search(self, q: bytes) -> int:
         """binary_search(sa, q, cnt) -> sa[l] (sa_search.rs:98-112)."""

@@ -36,3 +36,12 @@ def gpu(sst):
     if sst.device_count() < 1:
         pytest.fail("GPU test selected but no sm_100 device is usable (no CPU fallback exists)")
     return sst
+
+
+@pytest.fixture(autouse=True)
+def _restore_library_options():
+    """Tests change library options with sst.set_option(); every test starts from the load-time values."""
+    yield
+    mod = sys.modules.get("sst_b200")
+    if mod is not None and getattr(mod, "_lib", None) is not None:
+        mod.reset_options()

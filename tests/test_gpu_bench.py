@@ -35,12 +35,12 @@ def test_bench_line_contract(gpu):
 
 @pytest.mark.gpu
 def test_bench_line_bucketed(gpu):
-    """A configuration large enough for SCHEME_AUTO to take the reordered-batch pipeline: 7 launches per step, stage times."""
+    """A configuration large enough for SCHEME_AUTO to take the reordered-batch pipeline: 4 launches per step, stage times."""
     out = subprocess.run(
         [sys.executable, os.path.join(ROOT, "bench.py"), "--n-keys", str(1 << 27), "--queries", str(1 << 24), "--steps", "2", "--warmup", "3",
          "--no-cpu", "--sa-text", "0", "--e2e-steps", "1"],
         capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-3000:]
     d = json.loads([l for l in out.stdout.splitlines() if l.strip()][-1])
-    assert d["config"]["scheme"] == "bucketed" and d["gpu_launches"] == 2 * 7 and d["results_ok"] is True
-    assert set(d["roofline"]["stage_ms"]) == {"rank", "plan", "scatter", "search", "gather"}
+    assert d["config"]["scheme"] == "bucketed" and d["gpu_launches"] == 2 * 4 and d["results_ok"] is True
+    assert set(d["roofline"]["stage_ms"]) == {"partition", "plan", "search", "unpermute"}

@@ -25,8 +25,8 @@ def _check(sst, oracle, vals, qs, flags=FLAG_SETS):
 @pytest.mark.parametrize("r,n,nq", [(64, 5000, 40_000), (64, 100_000, 100_001), (64, 1_000_000, 70_000), (256, 1 << 20, 300_000),
                                     (1024, 2_000_003, 50_000), (16384, (1 << 22) + 12345, 1_000_003), (32768, 3_000_000, 500_000), (64, 17, 33), (64, 600, 1)])
 def test_bucketed_uniform(gpu, oracle, monkeypatch, r, n, nq):
-    monkeypatch.setenv("SST_BK_MIN_N", "0")
-    monkeypatch.setenv("SST_BK_R", str(r))
+    gpu.set_option("BK_MIN_N", 0)
+    gpu.set_option("BK_R", int(str(r)))
     vals = gen_vals(n, seed=n + r)
     _check(gpu, oracle, vals, gen_queries(nq, seed=n + 1, vals=vals))
 
@@ -35,9 +35,9 @@ def test_bucketed_uniform(gpu, oracle, monkeypatch, r, n, nq):
                                     (64, 17, 5)])
 def test_bucketed_node_granularity(gpu, oracle, monkeypatch, r, n, nq):
     """SST_BK_G=16: one separator per 16-key node (the layout used above 2^29 keys), two leaf sectors per query."""
-    monkeypatch.setenv("SST_BK_MIN_N", "0")
-    monkeypatch.setenv("SST_BK_R", str(r))
-    monkeypatch.setenv("SST_BK_G", "16")
+    gpu.set_option("BK_MIN_N", 0)
+    gpu.set_option("BK_R", int(str(r)))
+    gpu.set_option("BK_G", 16)
     vals = gen_vals(n, seed=n + r + 1)
     _check(gpu, oracle, vals, gen_queries(nq, seed=n + 2, vals=vals))
     rng = np.random.default_rng(n)
@@ -50,8 +50,8 @@ def test_bucketed_fuzz(gpu, oracle, monkeypatch, seed):
     """Adversarial key distributions (clusters, duplicate runs longer than a bucket, tiny ranges): crowded bucket-table
     cells, empty buckets, all queries in one bucket, jump-table cells with many separators."""
     rng = np.random.default_rng(5000 + seed)
-    monkeypatch.setenv("SST_BK_MIN_N", "0")
-    monkeypatch.setenv("SST_BK_R", str(int(rng.choice([64, 128, 1024]))))
+    gpu.set_option("BK_MIN_N", 0)
+    gpu.set_option("BK_R", int(str(int(rng.choice([64, 128, 1024])))))
     n = int(rng.integers(1, 900_000))
     vals = make_keys(rng, n, KINDS[seed % len(KINDS)])
     nq = int(rng.integers(1, 200_000))
@@ -63,8 +63,8 @@ def test_bucketed_fuzz(gpu, oracle, monkeypatch, seed):
 
 def test_bucketed_edges(gpu, oracle, monkeypatch):
     sst = gpu
-    monkeypatch.setenv("SST_BK_MIN_N", "0")
-    monkeypatch.setenv("SST_BK_R", "64")
+    gpu.set_option("BK_MIN_N", 0)
+    gpu.set_option("BK_R", 64)
     vals = np.sort(np.random.default_rng(3).integers(0, 1 << 20, 50_000).astype(np.uint32))  # MAX is not a key
     for nq in (1, 31, 33, 16383, 16384, 16385, 32768 + 7):
         _check(sst, oracle, vals, gen_queries(nq, seed=nq, vals=vals), flags=[(1, 0, 0)])
@@ -87,8 +87,8 @@ def test_bucketed_unsupported_is_loud(gpu, monkeypatch):
     t = sst.STree16.new_params(vals, True, False, False)  # default: trees below 2^22 keys have no bucket index
     with pytest.raises(sst.SstError):
         t.query(qs, sst.SCHEME_BUCKETED)
-    monkeypatch.setenv("SST_BK_MIN_N", "0")
-    monkeypatch.setenv("SST_BK_R", "64")
+    gpu.set_option("BK_MIN_N", 0)
+    gpu.set_option("BK_R", 64)
     big = gen_vals(64 * 8 * 2048 + 9, seed=10)  # one bucket too many for the 2048-bucket partition
     with pytest.raises(sst.SstError):
         sst.STree16.new_params(big, True, False, False).query(qs, sst.SCHEME_BUCKETED)
@@ -103,8 +103,8 @@ def test_bucketed_streams_and_repeats(gpu, oracle, monkeypatch):
     import torch
 
     sst = gpu
-    monkeypatch.setenv("SST_BK_MIN_N", "0")
-    monkeypatch.setenv("SST_BK_R", "256")
+    gpu.set_option("BK_MIN_N", 0)
+    gpu.set_option("BK_R", 256)
     vals = gen_vals(1 << 19, seed=5)
     t = sst.STree16.new_params(vals, True, False, False)
     qa = gen_queries(400_000, seed=6, vals=vals)
@@ -131,8 +131,8 @@ def test_bucketed_unaligned_device_buffers(gpu, oracle, monkeypatch):
     import torch
 
     sst = gpu
-    monkeypatch.setenv("SST_BK_MIN_N", "0")
-    monkeypatch.setenv("SST_BK_R", "128")
+    gpu.set_option("BK_MIN_N", 0)
+    gpu.set_option("BK_R", 128)
     vals = gen_vals(300_000, seed=15)
     t = sst.STree16.new_params(vals, True, False, False)
     qs = gen_queries(100_000, seed=16, vals=vals)
@@ -160,9 +160,9 @@ def test_auto_picks_the_pipeline_for_large_batches(gpu, oracle):
     sch, launches = C.c_int(0), C.c_int(0)
     L = sst.lib()
     assert L.sst_query_plan(t._h, 1 << 26, 0, 0, C.byref(sch), C.byref(launches)) == 0
-    assert sch.value == sst.SCHEME_BUCKETED and launches.value == 7
-    assert L.sst_query_plan(t._h, 1 << 26, 0, 1, C.byref(sch), C.byref(launches)) == 0 and launches.value == 8
-    assert L.sst_query_plan(t._h, (1 << 28) + 1, 0, 0, C.byref(sch), C.byref(launches)) == 0 and launches.value == 21  # three sub-batches
+    assert sch.value == sst.SCHEME_BUCKETED and launches.value == 4  # partition, work items, search, un-permute
+    assert L.sst_query_plan(t._h, 1 << 26, 0, 1, C.byref(sch), C.byref(launches)) == 0 and launches.value == 5
+    assert L.sst_query_plan(t._h, (1 << 28) + 1, 0, 0, C.byref(sch), C.byref(launches)) == 0 and launches.value == 12  # three sub-batches
     assert L.sst_query_plan(t._h, 1 << 24, 0, 0, C.byref(sch), C.byref(launches)) == 0 and sch.value == sst.SCHEME_TABLE
     assert L.sst_query_plan(t._h, 1 << 20, 0, 0, C.byref(sch), C.byref(launches)) == 0
     assert sch.value == sst.SCHEME_TABLE and launches.value == 1
@@ -178,8 +178,8 @@ def test_auto_picks_the_pipeline_for_large_batches(gpu, oracle):
 def test_bucketed_degenerate_batches(gpu, oracle, monkeypatch):
     """Every query in one bucket / one key (all lanes of a warp collide in the ranking step), sorted and reverse-sorted batches."""
     sst = gpu
-    monkeypatch.setenv("SST_BK_MIN_N", "0")
-    monkeypatch.setenv("SST_BK_R", "256")
+    gpu.set_option("BK_MIN_N", 0)
+    gpu.set_option("BK_R", 256)
     vals = gen_vals(700_000, seed=33)
     for qs in (np.full(300_001, vals[123_456], np.uint32), np.full(50_000, 0, np.uint32), np.full(50_000, MAX, np.uint32),
                np.sort(gen_queries(200_000, seed=34, vals=vals)), np.sort(gen_queries(200_000, seed=35, vals=vals))[::-1].copy(),
@@ -196,8 +196,8 @@ def test_bucketed_map_partitioned(gpu, oracle, monkeypatch, r, n, nq, b, layout)
     sorted-array indices): same values and indices as the oracle and as the layout's own lane-group kernel, including
     queries above MAX (no part: (MAX, n))."""
     sst = gpu
-    monkeypatch.setenv("SST_BK_MIN_N", "0")
-    monkeypatch.setenv("SST_BK_R", str(r))
+    gpu.set_option("BK_MIN_N", 0)
+    gpu.set_option("BK_R", int(str(r)))
     vals = gen_vals(n, seed=n + r + 7)
     t = getattr(sst, layout).try_new(vals, b)
     if t is None:
@@ -227,8 +227,8 @@ def test_bucketed_map_partitioned(gpu, oracle, monkeypatch, r, n, nq, b, layout)
 def test_bucketed_map_skewed_keys(gpu, oracle, monkeypatch):
     """Map tree over keys that do not reach 31 bits / with long duplicate runs, MAX not a key."""
     sst = gpu
-    monkeypatch.setenv("SST_BK_MIN_N", "0")
-    monkeypatch.setenv("SST_BK_R", "256")
+    gpu.set_option("BK_MIN_N", 0)
+    gpu.set_option("BK_R", 256)
     rng = np.random.default_rng(77)
     served = 0
     for kind, layout in (("dupes", "PartitionedSTree16M"), ("clustered", "PartitionedSTree16M"), ("dupes", "PartitionedSTree16"),

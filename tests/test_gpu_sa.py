@@ -55,9 +55,9 @@ def test_sa_search_parity(gpu, oracle, lanes, pivot_levels, monkeypatch):
     """lanes=1: thread-per-pattern kernel with the pivot-prefix table (all / some / no levels from the table);
     lanes>1: sub-warp kernels (32 = warp per pattern)."""
     sst = gpu
-    monkeypatch.setenv("SST_SA_LANES", lanes)
-    monkeypatch.setenv("SST_SA_PIVOT_LEVELS", pivot_levels)
-    monkeypatch.setenv("SST_SA_KMER", "0")  # the pivot-prefix table serves every level (as for texts over a byte alphabet)
+    gpu.set_option("SA_LANES", int(lanes))
+    gpu.set_option("SA_PIVOT_LEVELS", int(pivot_levels))
+    gpu.set_option("SA_KMER", 0)  # the pivot-prefix table serves every level (as for texts over a byte alphabet)
     text = random_text(200_000, seed=11)
     s = sst.SaNaive.build(text)
     sa = s.sa
@@ -75,8 +75,8 @@ def test_sa_search_parity(gpu, oracle, lanes, pivot_levels, monkeypatch):
 def test_sa_search_repetitive_text(gpu, oracle, pivot_levels, monkeypatch):
     """Long LCPs: all-equal text and tandem repeats (many occurrences -> hi - lo large)."""
     sst = gpu
-    monkeypatch.setenv("SST_SA_PIVOT_LEVELS", pivot_levels)
-    monkeypatch.setenv("SST_SA_KMER", "0" if pivot_levels == "20" else "1")  # once through the pivot table, once through the k-mer table
+    gpu.set_option("SA_PIVOT_LEVELS", int(pivot_levels))
+    gpu.set_option("SA_KMER", int("0" if pivot_levels == "20" else "1"))  # once through the pivot table, once through the k-mer table
     for text in (np.zeros(5000, np.uint8), np.tile(random_text(13, seed=5), 700)):
         s = sst.SaNaive.build(text)
         sa = s.sa
@@ -105,12 +105,12 @@ def test_sa_zero_bytes_and_short_suffixes(gpu, oracle):
 def test_sa_host_pipeline_chunks(gpu, oracle, monkeypatch):
     """Host path in many small chunks (ring of three staging buffers, shifted pattern base per chunk)."""
     sst = gpu
-    monkeypatch.setenv("SST_SA_CHUNK", "37")
+    gpu.set_option("SA_CHUNK", 37)
     text = random_text(80_000, seed=41)
     s = sst.SaNaive.build(text)
     pats = random_patterns(text, 1000, seed=42, lo=1, hi=90) + [b"", b"", text[-3:].tobytes()]
     _check_search(sst, oracle, s, text, s.sa, pats)
-    monkeypatch.setenv("SST_SA_CHUNK", "1000000")
+    gpu.set_option("SA_CHUNK", 1000000)
     _check_search(sst, oracle, s, text, s.sa, pats)
 
 
@@ -137,9 +137,9 @@ def test_sa_search_sorted_order(gpu, oracle, levels, monkeypatch):
     """Opt-in reordered batch (SST_SA_SORT_MIN): coarse pass -> radix sort -> search in sorted order; identical outputs,
     including duplicate patterns, absent patterns and patterns of very different lengths."""
     sst = gpu
-    monkeypatch.setenv("SST_SA_SORT_MIN", "1")
-    monkeypatch.setenv("SST_SA_SORT_LEVELS", levels)
-    monkeypatch.setenv("SST_SA_KMER", "0")
+    gpu.set_option("SA_SORT_MIN", 1)
+    gpu.set_option("SA_SORT_LEVELS", int(levels))
+    gpu.set_option("SA_KMER", 0)
     text = random_text(300_000, seed=21)
     sa = oracle.sa_build(text)
     s = sst.SaNaive.from_parts(text, sa)
@@ -159,11 +159,11 @@ def test_sa_search_kmer_table(gpu, oracle, n, k, inline_bases, monkeypatch):
     patterns made of the text's tail (proper prefixes of padded k-mers), absent patterns, the empty pattern."""
     sst = gpu
     if inline_bases == "15":  # 8-byte {sa, 15 bases} entries (what an index takes when memory is short) instead of 16-byte {sa, 32 bases}
-        monkeypatch.setenv("SST_SA_INLINE", "15")
+        gpu.set_option("SA_INLINE", 15)
     if k.startswith("force"):  # deeper than one suffix per cell; 16 = the 3 Gbp configuration's depth (2^32 + 1 cells, 64-bit cell index)
-        monkeypatch.setenv("SST_SA_KMER_FORCE", k[5:])
+        gpu.set_option("SA_KMER_FORCE", int(k[5:]))
     else:
-        monkeypatch.setenv("SST_SA_KMER_K", k)
+        gpu.set_option("SA_KMER_K", int(k))
     text = random_text(n, seed=n + 5)
     s = sst.SaNaive.build(text)
     sa = s.sa
@@ -185,9 +185,9 @@ def test_sa_search_kmer_table(gpu, oracle, n, k, inline_bases, monkeypatch):
     for at in (33, 36, 44, 47, 48, 50):  # a byte outside the alphabet in the third 16-byte window
         pats += [head[900:900 + at] + bytes([9]) + head[901 + at:970], head[900:900 + at] + bytes([200])]
     _check_search(sst, oracle, s, text, sa, pats)
-    monkeypatch.setenv("SST_SA_USE_INLINE", "0")  # k-mer table, probes on the text
+    gpu.set_option("SA_USE_INLINE", 0)  # k-mer table, probes on the text
     _check_search(sst, oracle, s, text, sa, pats[:3000] + pats[-60:])
     monkeypatch.delenv("SST_SA_USE_INLINE")
     # the same through the pivot table only
-    monkeypatch.setenv("SST_SA_USE_KMER", "0")
+    gpu.set_option("SA_USE_KMER", 0)
     _check_search(sst, oracle, s, text, sa, pats[:2000])

@@ -149,17 +149,16 @@ def test_table_kernel_skewed_keys(gpu, oracle):
     for lm, rev, full in FLAG_SETS:
         t = sst.STree16.new_params(vals, bool(lm), bool(rev), bool(full))
         for g in ("2", "4"):
-            os.environ["SST_TABLE_G"] = g
+            sst.set_option("TABLE_G", int(g))
             v, i = t.query(qs, sst.SCHEME_TABLE, want_index=True)
             assert np.array_equal(v, ev) and np.array_equal(i, ei), (lm, rev, full, g)
-    os.environ.pop("SST_TABLE_G", None)
 
 
 def test_compressed_last_level(gpu, oracle, monkeypatch):
     """16-bit copy of the last internal level (forced on for a small tree): dense keys (compressed path),
     sparse keys (every node falls back to the exact node) and a mix, all flag combinations."""
     sst = gpu
-    monkeypatch.setenv("SST_C5", "1")  # build it regardless of the level's size
+    gpu.set_option("C5", 1)  # build it regardless of the level's size
     rng = np.random.default_rng(91)
     dense = np.sort(rng.integers(1 << 20, (1 << 20) + (1 << 22), 600_000).astype(np.uint32))
     sparse = gen_vals(300_000, seed=92)
@@ -251,7 +250,7 @@ def test_device_buffers_and_streams(gpu, oracle):
 
 def test_host_pipeline_chunks(gpu, oracle, monkeypatch):
     sst = gpu
-    monkeypatch.setenv("SST_CHUNK", "4096")
+    gpu.set_option("CHUNK", 4096)
     vals = gen_vals(1 << 16, seed=1)
     qs = gen_queries(4096 * 7 + 123, seed=2, vals=vals)
     ev, ei = oracle.lower_bound(vals, qs)

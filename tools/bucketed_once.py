@@ -1,5 +1,5 @@
 """Reordered-batch pipeline (SCHEME_BUCKETED) vs the rank-table kernel at LOGN keys / NQ queries: equality of
-results and CUDA-event times; SST_BK_TIMING=2 prints the per-stage split."""
+results and CUDA-event times; the option BK_TIMING=2 prints the per-stage split."""
 import ctypes as C, os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "suffix-array-searching_b200"))
@@ -25,7 +25,6 @@ torch.cuda.synchronize()
 print(json.dumps({"values_equal": bool((v1 == v2).all()), "indices_equal": bool((i1 == i2).all())}), flush=True)
 del i1, i2, v2
 out = torch.empty_like(qs)
-os.environ.pop("SST_BK_TIMING", None)
 for name, scheme in (("table", 5), ("bucketed", 7)):
     ms = L.sst_time_query_device(t._h, C.c_void_p(qs.data_ptr()), nq, C.c_void_p(out.data_ptr()), None, scheme, 2, 5)
     print(json.dumps({"scheme": name, "ms": round(ms, 3), "gqps": round(nq / ms / 1e6, 2), "ok": bool((out == v1).all())}), flush=True)

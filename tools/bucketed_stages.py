@@ -1,4 +1,4 @@
-"""Warm per-stage times of the reordered-batch pipeline (mean of 5 runs under SST_BK_TIMING=1) at LOGN keys / NQ queries."""
+"""Warm per-stage times of the reordered-batch pipeline (mean of 5 runs with the option BK_TIMING=1) at LOGN keys / NQ queries."""
 import os, sys, ctypes as C, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "suffix-array-searching_b200"))
@@ -14,7 +14,7 @@ out = torch.empty_like(qs)
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 for _ in range(3): L.sst_query_device(t._h, C.c_void_p(qs.data_ptr()), nq, C.c_void_p(out.data_ptr()), None, 7, st)
 ms_all = L.sst_time_query_device(t._h, C.c_void_p(qs.data_ptr()), nq, C.c_void_p(out.data_ptr()), None, 7, 1, 5)
-os.environ["SST_BK_TIMING"] = "1"
+sst.set_option("BK_TIMING", 1)
 acc = [0.0] * 5
 for _ in range(5):
     L.sst_query_device(t._h, C.c_void_p(qs.data_ptr()), nq, C.c_void_p(out.data_ptr()), None, 7, st)
@@ -22,4 +22,4 @@ for _ in range(5):
     ms = (C.c_double * 5)(); L.sst_last_stage_ms(ms, 5)
     acc = [a + b for a, b in zip(acc, ms)]
 print(json.dumps({"tag": os.environ.get("TAG", ""), "ms": round(ms_all, 3), "gqps": round(nq / ms_all / 1e6, 2),
-                  "stages_ms": dict(zip(["rank", "plan", "scatter", "search", "gather"], [round(a / 5, 3) for a in acc]))}))
+                  "stages_ms": dict(zip((["rank", "plan", "scatter", "search", "gather"] if sst.get_option("BK_V1") else ["partition", "plan", "-", "search", "unpermute"]), [round(a / 5, 3) for a in acc]))}))

@@ -39,10 +39,10 @@ ev, ei = O.lower_bound(vals, qs)
 t = sst.STree16.new_params(vals, True, False, False)
 v, i = t.query(qs, sst.SCHEME_TABLE, want_index=True)
 assert (v == ev).all() and (i == ei).all()
-# the reordered-batch pipeline (rank / plan / scatter / search / gather), forced onto a small tree; full and partial tiles,
+# the reordered-batch pipeline (partition / plan / search / un-permute), forced onto a small tree; full and partial tiles,
 # skewed batches (one bucket, one key) and the index output
-os.environ["SST_BK_MIN_N"] = "0"
-os.environ["SST_BK_R"] = "256"
+sst.set_option("BK_MIN_N", 0)
+sst.set_option("BK_R", 256)
 vals = np.sort(rng.integers(0, MAX, 600_000, dtype=np.uint32)); vals[-1] = MAX
 tb = sst.STree16.new_params(vals, True, False, False)
 for qs in (rng.integers(0, MAX, 3 * 16384 + 77, dtype=np.uint32), np.full(40_000, vals[1234], np.uint32),
@@ -51,7 +51,7 @@ for qs in (rng.integers(0, MAX, 3 * 16384 + 77, dtype=np.uint32), np.full(40_000
     v, i = tb.query(qs, sst.SCHEME_BUCKETED, want_index=True)
     assert (v == ev).all() and (i == ei).all()
     assert (tb.query(qs, sst.SCHEME_BUCKETED) == ev).all()
-os.environ.pop("SST_BK_MIN_N"); os.environ.pop("SST_BK_R")
+sst.reset_options()
 # suffix arrays
 for n, sigma in ((1, 4), (50, 2), (30_000, 4), (20_000, 256)):
     text = rng.integers(0, sigma, n, dtype=np.uint8)
@@ -62,7 +62,7 @@ for n, sigma in ((1, 4), (50, 2), (30_000, 4), (20_000, 256)):
     of, oo = O.pack_patterns(pats)
     elo, ehi, epos, _ = O.sa_search(text, sa.sa, of, oo)
     for lanes in ("1", "8", "32"):
-        os.environ["SST_SA_LANES"] = lanes
+        sst.set_option("SA_LANES", int(lanes))
         for mode in (0, 1):
             lo, hi, pos = sa.search(flat, off, mode)
             assert (lo == elo).all() and (hi == ehi).all() and (pos == epos).all(), (n, sigma, lanes, mode)

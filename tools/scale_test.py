@@ -133,12 +133,12 @@ def c5(n=3_000_000_000, npat=100_000_000):
     for lv in [x for x in os.environ.get("C5_SORT_LEVELS", "").split(",") if x]:  # sorted-order search at these coarse depths
         variants.append((f"binary_sorted{lv}", sst.SA_BINARY, lv))
     for name, mode, sort_lv in variants:
-        os.environ["SST_SA_USE_KMER"] = "0" if sort_lv == "nokmer" else "1"  # pivot-prefix table only: the k-mer path must agree with it
+        sst.set_option("SA_USE_KMER", 0 if sort_lv == "nokmer" else 1)  # pivot-prefix table only: the k-mer path must agree with it
         if sort_lv is None or sort_lv == "nokmer":
-            os.environ["SST_SA_SORT_MIN"] = str(1 << 62)
+            sst.set_option("SA_SORT_MIN", -1)
         else:
-            os.environ["SST_SA_SORT_MIN"] = "1"
-            os.environ["SST_SA_SORT_LEVELS"] = sort_lv
+            sst.set_option("SA_SORT_MIN", 1)
+            sst.set_option("SA_SORT_LEVELS", int(sort_lv))
         def run():
             rc = L.sst_sa_search_device(sa._h, C.c_void_p(pats.data_ptr()), C.c_void_p(off.data_ptr()), npat, mode,
                                         C.c_void_p(lo.data_ptr()), C.c_void_p(hi.data_ptr()), C.c_void_p(pos.data_ptr()), None)
