@@ -62,6 +62,11 @@ def layer_nodes_for(n, B=16):
     return [-(-s // B) for s in reversed(sizes)]
 
 
+def workload_name(n, nq):
+    """The same string in both arms (own / reference): the configuration the metric is quoted on."""
+    return f"stree16 left_max lower_bound: {n} sorted uniform u32 keys (S+-tree B=16), {nq} uniform u32 queries per GPU per step"
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -127,6 +132,82 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+# exact host-side parity samples (plain numpy / Python on host copies; no GPU search path involved)
+# ------------------------------------------------------------------------------------------------
+def check_lower_bound_sample(q, val, idx, key_prev, key_at, n):
+    """SortedVec::binary_search's contract (static-search-tree/src/binary_search.rs:36-49) for sampled queries:
+    idx is the lower bound of q in the sorted keys iff keys[idx-1] < q <= keys[idx]; val = keys[idx] (MAX at idx == n).
+    key_prev / key_at are keys[max(idx-1, 0)] / keys[min(idx, n-1)] read from the sorted array itself.
+    A query above MAX compares like 0 on the plain tree (signed compare, node.rs:91-108).  Returns the number of violations."""
+    q = np.asarray(q, np.uint32).astype(np.int64)
+    val, idx = np.asarray(val, np.uint32).astype(np.int64), np.asarray(idx, np.uint64).astype(np.int64)
+    key_prev, key_at = np.asarray(key_prev, np.uint32).astype(np.int64), np.asarray(key_at, np.uint32).astype(np.int64)
+    cq = np.where(q > MAX, 0, q)
+    bad = (idx < 0) | (idx > n)
+    bad |= (idx < n) & ~(key_at >= cq)
+    bad |= (idx > 0) & ~(key_prev < cq)
+    bad |= val != np.where(idx < n, key_at, MAX)
+    return int(bad.sum())
+
+
+def check_sa_sample(pats, lo, hi, pos, n, sa_at, win):
+    """binary_search's contract (suffix-array-searching/src/sa_search.rs:98-112) for sampled patterns, in plain Python:
+    lo is the first l with suffix(sa[l]) >= q, i.e. suffix(sa[lo-1]) < q <= suffix(sa[lo]) (the suffix array is sorted:
+    sst_sa_check == 0); pos = sa[lo]; hi is the first index >= lo whose suffix does not start with q.
+    pats[i] = bytes; sa_at[j][i] = sa[x] and win[j][i] = text[sa[x] : sa[x] + len(q)] (bytes, cut at the text's end) for
+    x = lo-1, lo, hi-1, hi (j = 0..3; entries for x outside [0, n) are ignored).  Returns the number of violations."""
+    bad = 0
+    for i, q in enumerate(pats):
+        l, h = int(lo[i]), int(hi[i])
+        ok = 0 <= l <= h <= n
+        if ok and l > 0:
+            ok = win[0][i] < q                       # bytes compare == the reference's slice compare (a proper prefix sorts first)
+        if ok and l < n:
+            ok = win[1][i] >= q and int(pos[i]) == int(sa_at[1][i])
+        if ok and l == n:
+            ok = int(pos[i]) == 0xFFFFFFFF
+        if ok and h > l:
+            ok = win[2][i] == q                      # the last suffix of [lo, hi) starts with q
+        if ok and h < n:
+            ok = win[3][i] != q                      # and the next one does not
+        bad += 0 if ok else 1
+    return bad
+
+
+class Ranks:
+    """torch.distributed plumbing of the own arm: barrier, max / min over ranks (NCCL; no data-path collective exists)."""
+
+    def __init__(self, torch, dev, dist):
+        self.torch, self.dev, self.dist = torch, dev, dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max(self, x):
+        if self.dist is None:
+            return float(x)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ok(self, ok):
+        if self.dist is None:
+            return bool(ok)
+        t = self.torch.tensor([1 if ok else 0], dtype=self.torch.int32, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def sum(self, x):
+        if self.dist is None:
+            return float(x)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+
+# ------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU implementation of the path (oracle restatement of
 # batched(STree16::batch_final::<128>) on new_params(vals, true, false, false), bench_binsearch.rs:239-252)
 # ------------------------------------------------------------------------------------------------
@@ -158,25 +239,38 @@ def run_reference(args):
     keys = gen_keys_host(n, args.seed)
     tree = O.Tree.stree(keys, left_max=True)
     build_s = time.time() - t0
-    sample = args.ref_sample
+    sample = args.ref_sample if args.ref_sample > 0 else args.queries  # the own arm's step by default: same config
     rng = np.random.default_rng(args.seed + 1)
     batches = [rng.integers(0, MAX, sample, dtype=np.uint32) for _ in range(2)]
-    for w in range(max(args.warmup, 1)):
-        tree.batch_final(batches[w % 2], threads)
-    secs = []
-    for k in range(args.steps):
-        _, s = tree.batch_final(batches[k % 2], threads)
-        secs.append(s)
-    total = sum(secs)
-    value = sample * args.steps / total
+    # both CPU schemes of the reference's headline (bench_binsearch.rs:239-252): batch_final<128> (s_tree.rs:303-326) and its
+    # fastest, batch_interleave_all_128 (s_tree.rs:684-832); the line's value is the faster one
+    schemes = {"batch_final_128": tree.batch_final}
+    if len(tree.offsets) <= 8:
+        schemes["batch_interleave_all_128"] = tree.batch_interleave
+    per = {}
+    expect = None
+    for sname, fn in schemes.items():
+        for w in range(max(args.warmup, 1)):
+            fn(batches[w % 2], threads)
+        secs = []
+        for k in range(args.steps):
+            v, t = fn(batches[k % 2], threads)
+            secs.append(t)
+        if expect is None:
+            expect = v
+        per[sname] = {"value": sample * args.steps / sum(secs), "ms_per_step": 1e3 * sum(secs) / args.steps,
+                      "equals_batch_final": bool((v == expect).all())}
+    best = max(per, key=lambda k: per[k]["value"])
+    value, ms_step = per[best]["value"], per[best]["ms_per_step"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": f"stree16 left_max lower_bound, {n} sorted uniform u32 keys; CPU batch_final<128> (s_tree.rs:303-326)",
-                   "n_keys": n, "queries_per_step": sample, "host_build_s": round(build_s, 2)},
+        "config": {"workload": workload_name(n, sample),
+                   "n_keys": n, "queries_per_gpu": sample, "global_queries": sample, "queries_per_step": sample, "cpu_scheme": best,
+                   "host_build_s": round(build_s, 2), "cpu_schemes": per},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} uniform queries per step over the full {n}-key tree, {threads} host threads, AVX2={bool(O.lib().orc_has_avx2())}"},
+                         "sample": f"{sample} uniform queries per step over the full {n}-key tree, {threads} host threads, AVX2={bool(O.lib().orc_has_avx2())}, scheme {best}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -361,8 +455,15 @@ def run_own(args):
         cv, secs = ot.batch_final(hs, threads)
         gv = tree.query(batches[0][:sample]).cpu().numpy().view(np.uint32)
         ok = ok and bool((cv == gv).all())
-        cpu = {"value": sample / secs, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"first {sample} queries of the step's batch over the full {n}-key tree; oracle batch_final<128> (AVX2={bool(O.lib().orc_has_avx2())}) on {threads} threads; results equal the GPU's"}
+        schemes = {"batch_final_128": sample / secs}
+        if len(ot.offsets) <= 8:  # the reference's fastest CPU scheme (s_tree.rs:684-832; heights 1..8 like its dispatch table)
+            ot.batch_interleave(hs[: min(sample, 1 << 20)], threads)
+            cv2, secs2 = ot.batch_interleave(hs, threads)
+            ok = ok and bool((cv2 == gv).all())
+            schemes["batch_interleave_all_128"] = sample / secs2
+        best = max(schemes, key=schemes.get)
+        cpu = {"value": schemes[best], "unit": UNIT, "cores": threads, "kind": "port", "scheme": best, "schemes": schemes,
+               "sample": f"first {sample} queries of the step's batch over the full {n}-key tree; oracle {best} (AVX2={bool(O.lib().orc_has_avx2())}) on {threads} threads; results equal the GPU's"}
         del ot
 
     # ---- GPU baseline the reference's headline is about: plain binary search on the same device ----
@@ -395,13 +496,32 @@ def run_own(args):
         except Exception as ex:
             baselines["gpu_eytzinger_error"] = repr(ex)
 
-    # ---- optional secondary metric: suffix-array patterns/s (config C3) ----
-    sa_info = None
-    if rank == 0 and world == 1 and args.sa_text > 0:
+    # ---- the other BASELINE configs, at every N (index replicated per GPU, batch sharded contiguously) ----
+    del tree, keys, batches, out_v
+    torch.cuda.empty_cache()
+    R = Ranks(torch, dev, dist)
+    extra = {}
+
+    def run_block(key, fn):
         try:
-            sa_info = bench_sa(args, sst, torch, dev)
-        except Exception as ex:  # the headline line must still print
-            sa_info = {"error": repr(ex)}
+            extra[key] = fn()
+        except Exception as ex:  # the headline line must still print; the failure is reported and fails the run
+            import traceback
+            traceback.print_exc()
+            extra[key] = {"error": repr(ex), "ok": False}
+        torch.cuda.empty_cache()
+
+    if args.sa_text > 0:  # C3: 10^8 random DNA text, 10^7 32-mers, plain vs LCP-accelerated
+        run_block("sa", lambda: bench_sa_config(args, sst, torch, dev, R, rank, world, "C3", args.sa_text, args.sa_patterns, 32, 32,
+                                                3, args.c_e2e_reps, args.sa_cpu_sample))
+    if args.c4_log2_keys > 0:
+        run_block("c4", lambda: bench_c4(args, sst, torch, dev, R, rank, world))
+    if args.c5_text > 0:  # C5: 3x10^9 text, 10^8 patterns of 20..100 bytes
+        run_block("c5", lambda: bench_sa_config(args, sst, torch, dev, R, rank, world, "C5", args.c5_text, args.c5_patterns, 20, 100,
+                                                args.c_reps, args.c_e2e_reps, 0))
+    for blk in extra.values():
+        ok = ok and bool(blk.get("ok", False))
+    ok = R.all_ok(ok)
 
     if rank == 0:
         line = {
@@ -409,7 +529,7 @@ def run_own(args):
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {
-                "workload": f"stree16 left_max lower_bound: {n} sorted uniform u32 keys (S+-tree B=16, {len(layer_nodes)} levels), {nq} uniform u32 queries per GPU per step",
+                "workload": workload_name(n, nq), "levels": len(layer_nodes),
                 "n_keys": n, "queries_per_gpu": nq, "global_queries": world * nq, "parallelism": f"replicated index, query-sharded x{world}",
                 "host_affinity_cpus": affinity_cpus,
                 "scheme": scheme_names.get(res_scheme.value, str(res_scheme.value)), "index_build_s": round(build_s, 3),
@@ -420,93 +540,287 @@ def run_own(args):
         }
         if baselines is not None:
             line["baselines"] = baselines
-        if sa_info is not None:
-            line["sa"] = sa_info
+        line.update(extra)
         emit_line(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0 if ok else 1
 
 
-def bench_sa(args, sst, torch, dev):
-    """Config C3: random DNA text, 32-mer patterns, plain vs LCP-accelerated binary search."""
+def _sa_exact_sample(sst, torch, dev, sa, text, pats, off, lo, hi, pos, nsample, seed):
+    """Pulls `nsample` random patterns of this rank with their results to the host and checks them with check_sa_sample."""
+    n, npat = text.numel(), lo.numel()
+    if npat == 0:
+        return 0, 0
+    rng = np.random.default_rng(seed)
+    sel = np.unique(rng.integers(0, npat, min(nsample, npat)))
+    tsel = torch.from_numpy(sel).to(dev)
+    h_lo = lo[tsel].cpu().numpy().view(np.uint32).astype(np.int64)
+    h_hi = hi[tsel].cpu().numpy().view(np.uint32).astype(np.int64)
+    h_pos = pos[tsel].cpu().numpy().view(np.uint32)
+    o0, o1 = off[tsel].cpu().numpy(), off[tsel + 1].cpu().numpy()
+    plen = (o1 - o0).astype(np.int64)
+    maxlen = int(plen.max())
+    ar = torch.arange(maxlen, device=dev)[None, :]
+    pm = pats[(off[tsel][:, None] + ar).clamp(max=pats.numel() - 1)].cpu().numpy()
+    h_pats = [pm[i, : plen[i]].tobytes() for i in range(sel.size)]
+    want = np.stack([h_lo - 1, h_lo, h_hi - 1, h_hi])                      # positions in the suffix array
+    valid = (want >= 0) & (want < n)
+    sa_at = sa.gather(np.where(valid, want, 0).astype(np.uint64).reshape(-1)).reshape(4, -1).astype(np.int64)
+    win = []
+    for j in range(4):                                                     # text windows of those suffixes, cut at the text's end
+        st = torch.from_numpy(sa_at[j]).to(dev)
+        w = text[(st[:, None] + ar).clamp(max=n - 1)].cpu().numpy()
+        wl = np.minimum(plen, n - sa_at[j])
+        win.append([w[i, : wl[i]].tobytes() if valid[j, i] else b"" for i in range(sel.size)])
+    return check_sa_sample(h_pats, h_lo, h_hi, h_pos, n, sa_at, win), int(sel.size)
+
+
+def _make_patterns(torch, dev, text, npat, len_lo, len_hi, gen):
+    """Substrings of the text, length uniform in [len_lo, len_hi], packed back to back (+64 bytes of slack)."""
+    n = text.numel()
+    lens = torch.randint(len_lo, len_hi + 1, (npat,), device=dev, generator=gen)
+    off = torch.zeros(npat + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(lens, 0, out=off[1:])
+    total = int(off[-1])
+    starts = torch.randint(0, max(1, n - len_hi - 1), (npat,), device=dev, generator=gen)
+    pats = torch.zeros(total + 64, dtype=torch.uint8, device=dev)
+    CH = 5_000_000                                                         # in chunks: bounds the index temporaries
+    for a in range(0, npat, CH):
+        b = min(npat, a + CH)
+        tot = int(off[b] - off[a])
+        owner = torch.repeat_interleave(torch.arange(b - a, device=dev), lens[a:b])
+        within = torch.arange(tot, device=dev) - (off[a:b] - off[a])[owner]
+        pats[int(off[a]): int(off[b])] = text[starts[a:b][owner] + within]
+        del owner, within
+    return pats, off, total
+
+
+def bench_sa_config(args, sst, torch, dev, R, rank, world, name, n, npat_total, len_lo, len_hi, reps, e2e_reps, cpu_sample):
+    """One suffix-array config (C3: 10^8 text / 10^7 32-mers; C5: 3x10^9 text / 10^8 patterns of 20..100 bytes): text + SA
+    replicated per GPU, the pattern batch sharded contiguously (chunk = ceil(npat / N)), binary and LCP-accelerated search,
+    device-resident and through the host-buffer call, with an exact host-side sample check of [lo, hi) and pos."""
     import ctypes as C
+    import math
 
     L = sst.lib()
-    n, npat, plen = args.sa_text, args.sa_patterns, 32
-    g = torch.Generator(device=dev).manual_seed(args.seed + 5)
+    g = torch.Generator(device=dev).manual_seed(args.seed + 5)              # the same text on every rank
     text = torch.randint(0, 4, (n,), dtype=torch.uint8, device=dev, generator=g)
     t0 = time.time()
     sa = sst.SaNaive.build(text)
     torch.cuda.synchronize()
     build_s = time.time() - t0
-    starts = torch.randint(0, n - 200, (npat,), device=dev, generator=g)
-    pats = text[(starts[:, None] + torch.arange(plen, device=dev)[None, :]).reshape(-1)].contiguous()
-    off = (torch.arange(npat + 1, device=dev, dtype=torch.int64) * plen).contiguous()
+    s, e = shard_range(npat_total, rank, world)
+    npat = e - s
+    gp = torch.Generator(device=dev).manual_seed(args.seed + 700 + rank)
+    pats, off, total = _make_patterns(torch, dev, text, npat, len_lo, len_hi, gp)
     lo = torch.empty(npat, dtype=torch.int32, device=dev)
     hi = torch.empty(npat, dtype=torch.int32, device=dev)
     pos = torch.empty(npat, dtype=torch.int32, device=dev)
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    out = {"text_bytes": n, "patterns": npat, "pattern_len": plen, "sa_build_s": round(build_s, 3), "unit": "patterns/s"}
-    ref_lo = None
-    for name, mode in (("binary", sst.SA_BINARY), ("mlr", sst.SA_MLR)):
+    out = {"config": name, "text_bytes": n, "patterns": npat_total, "patterns_per_gpu": npat, "pattern_len": [len_lo, len_hi],
+           "sa_build_s": round(build_s, 3), "unit": "patterns/s", "n_gpus": world, "scaling": "strong", "timed_reps": reps}
+    ok = True
+    ref_lo = ref_hi = None
+    for mname, mode in (("binary", sst.SA_BINARY), ("mlr", sst.SA_MLR)):
         def run():
             rc = L.sst_sa_search_device(sa._h, C.c_void_p(pats.data_ptr()), C.c_void_p(off.data_ptr()), npat, mode,
                                         C.c_void_p(lo.data_ptr()), C.c_void_p(hi.data_ptr()), C.c_void_p(pos.data_ptr()), stream)
             if rc != 0:
                 raise RuntimeError(L.sst_last_error().decode())
         run()
-        torch.cuda.synchronize()
+        R.barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(3):
+        for _ in range(reps):
             run()
         b.record()
-        torch.cuda.synchronize()
-        ms = a.elapsed_time(b) / 3
-        out[name + "_patterns_per_s"] = npat / (ms * 1e-3)
-        # property: the pattern occurs at the returned position
-        got = text[(pos.long()[:100000, None] + torch.arange(plen, device=dev)[None, :])]
-        out[name + "_ok"] = bool((got == pats.view(npat, plen)[:100000]).all()) and bool((hi > lo).all())
+        R.barrier()
+        ms = R.max(a.elapsed_time(b)) / reps
+        out[mname + "_patterns_per_s"] = npat_total / (ms * 1e-3)
+        out[mname + "_ms"] = ms
+        bad, checked = _sa_exact_sample(sst, torch, dev, sa, text, pats, off, lo, hi, pos, args.parity_sample, args.seed + 31 * rank)
+        out[mname + "_ok"] = R.all_ok(bad == 0)
+        ok = ok and out[mname + "_ok"]
         if ref_lo is None:
-            ref_lo = lo.clone()
+            ref_lo, ref_hi = lo.clone(), hi.clone()
+            out["parity_sample"] = (f"{checked} random patterns per rank checked on the host in plain Python: suffix(sa[lo-1]) < q <= suffix(sa[lo]), "
+                                    "pos == sa[lo], suffix(sa[hi-1]) starts with q, suffix(sa[hi]) does not (sa_search.rs:98-112)")
         else:
-            out["mlr_equals_binary"] = bool((lo == ref_lo).all())
+            out["mlr_equals_binary"] = R.all_ok(bool((lo == ref_lo).all()) and bool((hi == ref_hi).all()))
+            ok = ok and out["mlr_equals_binary"]
     out["sa_check_violations"] = sa.check()
-    # CPU baseline for the same path on this box: oracle port of binary_search_batch::<32> (sa_search.rs:157-196)
-    # on all host threads over a bounded sample of the same patterns; results must equal the GPU's.
-    if not args.no_cpu:
+    ok = ok and out["sa_check_violations"] == 0
+    # ---- through the host-buffer call: pinned host patterns -> H2D -> search -> D2H of lo / hi / pos ----
+    if e2e_reps > 0 and npat > 0:
+        hp = torch.empty(total + 64, dtype=torch.uint8).pin_memory()
+        ho = torch.empty(npat + 1, dtype=torch.int64).pin_memory()
+        hl = [torch.empty(npat, dtype=torch.int32).pin_memory() for _ in range(3)]
+        hp.copy_(pats); ho.copy_(off)
+        torch.cuda.synchronize()
+
+        def e2e_run():
+            rc = L.sst_sa_search(sa._h, C.c_void_p(hp.data_ptr()), C.c_void_p(ho.data_ptr()), npat, sst.SA_BINARY,
+                                 C.c_void_p(hl[0].data_ptr()), C.c_void_p(hl[1].data_ptr()), C.c_void_p(hl[2].data_ptr()))
+            if rc != 0:
+                raise RuntimeError(L.sst_last_error().decode())
+        e2e_run()
+        R.barrier()
+        t1 = time.perf_counter()
+        for _ in range(e2e_reps):
+            e2e_run()
+        torch.cuda.synchronize()
+        dt = R.max(time.perf_counter() - t1)
+        same = bool((hl[0].to(dev) == ref_lo).all()) and bool((hl[1].to(dev) == ref_hi).all())
+        out["e2e"] = {"value": npat_total * e2e_reps / dt, "unit": "patterns/s", "h2d_bytes_per_step": int(total + 8 * (npat + 1)),
+                      "d2h_bytes_per_step": 12 * npat, "steps": e2e_reps, "equals_device_path": R.all_ok(same)}
+        ok = ok and out["e2e"]["equals_device_path"]
+        del hp, ho, hl
+    # ---- CPU baseline for the same path on this box (N = 1 only): oracle port of binary_search_batch::<32>
+    # (sa_search.rs:157-196) on all host threads over a bounded sample of the same patterns; results must equal the GPU's.
+    if cpu_sample > 0 and world == 1 and not args.no_cpu:
         try:
             from oracle import oracle as O
 
             threads = host_threads()
-            sample = min(npat, args.sa_cpu_sample)
+            sample = min(npat, cpu_sample)
             h_text = text.cpu().numpy()
             h_sa = sa.sa
-            h_pats = np.concatenate([pats[: sample * plen].cpu().numpy(), np.zeros(64, np.uint8)])
-            h_off = (np.arange(sample + 1, dtype=np.uint64) * plen)
+            nbytes = int(off[sample])
+            h_pats = np.concatenate([pats[:nbytes].cpu().numpy(), np.zeros(64, np.uint8)])
+            h_off = off[: sample + 1].cpu().numpy().astype(np.uint64)
             O.sa_search_batch32(h_text, h_sa, h_pats, h_off[: min(sample, 1 << 14) + 1], threads)  # warm-up
             clo, cpos, secs = O.sa_search_batch32(h_text, h_sa, h_pats, h_off, threads)
+            eq = bool((clo == ref_lo[:sample].cpu().numpy().view(np.uint32)).all())
             out["cpu_baseline"] = {"value": sample / secs, "unit": "patterns/s", "cores": threads, "kind": "port",
-                                   "sample": f"first {sample} patterns; oracle binary_search_batch<32> on {threads} threads",
-                                   "equals_gpu": bool((clo == ref_lo[:sample].cpu().numpy().view(np.uint32)).all())}
+                                   "sample": f"first {sample} patterns; oracle binary_search_batch<32> on {threads} threads", "equals_gpu": eq}
+            ok = ok and eq
+            del h_text, h_sa
         except Exception as ex:
             out["cpu_baseline"] = {"error": repr(ex)}
+            ok = False
     # SURVEY 8(d): bytes/pattern = 96*max(0, I-T) + 96 + |q| + 8 with I = ceil(log2(n+1)), T = floor(log2(L2/96))
-    import math
     I = math.ceil(math.log2(n + 1))
     T = math.floor(math.log2(torch.cuda.get_device_properties(dev).L2_cache_size / 96))
-    bpp = 96 * max(0, I - T) + 96 + plen + 8
+    mean_len = (len_lo + len_hi) / 2
+    bpp = 96 * max(0, I - T) + 96 + mean_len + 8
     peak, _ = measured_peak()
     out["algorithmic_bytes_per_pattern"] = bpp
-    out["roofline_frac_binary"] = out["binary_patterns_per_s"] * bpp / 1e9 / peak
+    out["roofline_frac_binary"] = out["binary_patterns_per_s"] / world * bpp / 1e9 / peak
     # The k-mer table (texts over {0,1,2,3}) answers the first ~log4(n) bases with one load, so the probes SURVEY's model
     # counts are not made and the fraction above can exceed 1.  The floor of THAT path: one sector of the k-mer table and
     # the cell's {sa, 32 bases} entries (two sectors; a pattern of up to k + 32 bases needs no text), the pattern and the results.
-    kbpp = 32 + 64 + plen + 8
-    out["kmer_path"] = {"bytes_per_pattern": kbpp, "roofline_frac_binary": out["binary_patterns_per_s"] * kbpp / 1e9 / peak,
-                        "note": "floor of the k-mer-table path (3 random sectors + pattern + results); the path is bound by the random-access rate "
-                                "(~43 G DRAM accesses/s on this part), not by bytes"}
+    kbpp = 32 + 64 + mean_len + 8
+    out["kmer_path"] = {"bytes_per_pattern": kbpp, "roofline_frac_binary": out["binary_patterns_per_s"] / world * kbpp / 1e9 / peak,
+                        "note": "floor of the k-mer-table path (3 random sectors + pattern + results): the honest fraction; the path is bound by "
+                                "the random-access rate (~43 G DRAM accesses/s on this part), not by bytes"}
+    out["ok"] = bool(ok)
+    del sa, text, pats, off, lo, hi, pos
+    torch.cuda.empty_cache()
+    return out
+
+
+def bench_c4(args, sst, torch, dev, R, rank, world):
+    """BASELINE config C4: 2^30 keys, 10^9 queries sharded over the N GPUs (chunk = ceil(nq / N), bench.rs:558-573), through the
+    plain S+-tree and the Map-partitioned layout (b = 20); device-resident and through the host-buffer call; an exact
+    host-side sample check of the lower bound per rank."""
+    import ctypes as C
+
+    L = sst.lib()
+    n, nq_total = 1 << args.c4_log2_keys, args.c4_queries
+    g = torch.Generator(device=dev).manual_seed(args.seed + 11)
+    keys = torch.randint(0, MAX, (n,), dtype=torch.int32, device=dev, generator=g)
+    keys[0] = MAX
+    keys = torch.sort(keys).values.contiguous()
+    torch.cuda.empty_cache()
+    s, e = shard_range(nq_total, rank, world)
+    nq = e - s
+    gq = torch.Generator(device=dev).manual_seed(args.seed + 1100 + rank)
+    qs = torch.randint(0, MAX, (nq,), dtype=torch.int32, device=dev, generator=gq)
+    out_v = torch.empty_like(qs)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    reps = args.c_reps
+    out = {"config": "C4", "n_keys": n, "queries": nq_total, "queries_per_gpu": nq, "n_gpus": world, "scaling": "strong", "unit": UNIT,
+           "timed_reps": reps, "layouts": {}}
+    ok_all = True
+    hq = hv = None
+    for name, build in (("stree16_left_max", lambda: sst.STree16.new_params(keys, True, False, False)),
+                        ("map_b20", lambda: sst.PartitionedSTree16M.new(keys, min(20, args.c4_log2_keys - 4)))):
+        t0 = time.time()
+        tree = build()
+        torch.cuda.synchronize()
+        bs = time.time() - t0
+
+        def run(idx_ptr=None):
+            rc = L.sst_query_device(tree._h, C.c_void_p(qs.data_ptr()), nq, C.c_void_p(out_v.data_ptr()), idx_ptr, args.scheme, stream)
+            if rc != 0:
+                raise RuntimeError(L.sst_last_error().decode())
+        run()
+        R.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            run()
+        b.record()
+        R.barrier()
+        ms = R.max(a.elapsed_time(b)) / reps
+        timed_v = out_v.clone()
+        # exact sample check on the host: one more (untimed) pass that also returns the index, a random sample per rank
+        idx = torch.empty(nq, dtype=torch.int64, device=dev)
+        run(C.c_void_p(idx.data_ptr()))
+        torch.cuda.synchronize()
+        ok = bool((timed_v == out_v).all())                                 # the timed pass returned the same values
+        rng = np.random.default_rng(args.seed + 77 + rank)
+        sel = torch.from_numpy(rng.integers(0, max(nq, 1), min(args.parity_sample, nq))).to(dev)
+        si = idx[sel]
+        bad = check_lower_bound_sample(qs[sel].cpu().numpy().view(np.uint32), out_v[sel].cpu().numpy().view(np.uint32),
+                                       si.cpu().numpy().astype(np.uint64), keys[(si - 1).clamp(min=0)].cpu().numpy().view(np.uint32),
+                                       keys[si.clamp(max=n - 1)].cpu().numpy().view(np.uint32), n)
+        ok = R.all_ok(ok and bad == 0)
+        del idx, timed_v
+        res_scheme, res_launches = C.c_int(0), C.c_int(0)
+        L.sst_query_plan(tree._h, nq, args.scheme, 0, C.byref(res_scheme), C.byref(res_launches))
+        lay = {"queries_per_s": nq_total / (ms * 1e-3), "ms": ms, "build_s": round(bs, 3), "levels": tree.layers(), "image_mb": round(tree.size() / 2**20, 1),
+               "scheme": res_scheme.value, "launches_per_pass": res_launches.value, "ok": ok}
+        # ---- through the host-buffer call (pinned host -> H2D -> kernels -> D2H) ----
+        if args.c_e2e_reps > 0 and nq > 0:
+            if hq is None:
+                hq = torch.empty(nq, dtype=torch.int32).pin_memory()
+                hv = torch.empty(nq, dtype=torch.int32).pin_memory()
+                hq.copy_(qs)
+                torch.cuda.synchronize()
+
+            def e2e_run():
+                rc = L.sst_query(tree._h, C.c_void_p(hq.data_ptr()), nq, C.c_void_p(hv.data_ptr()), None, args.scheme)
+                if rc != 0:
+                    raise RuntimeError(L.sst_last_error().decode())
+            e2e_run()
+            R.barrier()
+            t1 = time.perf_counter()
+            for _ in range(args.c_e2e_reps):
+                e2e_run()
+            torch.cuda.synchronize()
+            dt = R.max(time.perf_counter() - t1)
+            same = R.all_ok(bool((hv.to(dev) == out_v).all()))
+            lay["e2e"] = {"value": nq_total * args.c_e2e_reps / dt, "unit": UNIT, "h2d_bytes_per_step": 4 * nq, "d2h_bytes_per_step": 4 * nq,
+                          "steps": args.c_e2e_reps, "equals_device_path": same}
+            lay["ok"] = lay["ok"] and same
+        ok_all = ok_all and lay["ok"]
+        out["layouts"][name] = lay
+        del tree
+        torch.cuda.empty_cache()
+    out["parity_sample"] = (f"{min(args.parity_sample, nq)} random queries per rank and layout checked on the host with numpy: keys[idx-1] < q <= keys[idx], "
+                            "value == keys[idx] (binary_search.rs:36-49); the timed pass's values equal the checked pass's")
+    # SURVEY 8(d): 64 bytes per HBM-resident level + query in + value out
+    layer_nodes = layer_nodes_for(n)
+    H_hbm = hbm_levels(layer_nodes, torch.cuda.get_device_properties(dev).L2_cache_size)
+    bpq = 64 * H_hbm + 8
+    peak, _ = measured_peak()
+    out["algorithmic_bytes_per_query"] = bpq
+    out["roofline_frac"] = out["layouts"]["stree16_left_max"]["queries_per_s"] / world * bpq / 1e9 / peak
+    out["ok"] = bool(ok_all)
+    del keys, qs, out_v, hq, hv
+    torch.cuda.empty_cache()
     return out
 
 
@@ -555,10 +869,17 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=100_000_000)
-    ap.add_argument("--ref-sample", type=int, default=20_000_000, help="queries per step of the reference arm")
+    ap.add_argument("--ref-sample", type=int, default=0, help="queries per step of the reference arm (0 = --queries, the own arm's step)")
     ap.add_argument("--sa-text", type=int, default=100_000_000, help="0 disables the secondary SA metric")
     ap.add_argument("--sa-patterns", type=int, default=10_000_000)
     ap.add_argument("--sa-cpu-sample", type=int, default=2_000_000, help="patterns of the CPU SA baseline sample")
+    ap.add_argument("--c4-log2-keys", type=int, default=30, help="config C4: log2 of the key count (0 disables the block)")
+    ap.add_argument("--c4-queries", type=int, default=1_000_000_000, help="config C4: queries in total, sharded over the GPUs")
+    ap.add_argument("--c5-text", type=int, default=3_000_000_000, help="config C5: text length (0 disables the block)")
+    ap.add_argument("--c5-patterns", type=int, default=100_000_000, help="config C5: patterns in total, sharded over the GPUs")
+    ap.add_argument("--c-reps", type=int, default=5, help="timed repetitions of the C4 / C5 blocks")
+    ap.add_argument("--c-e2e-reps", type=int, default=2, help="host-buffer repetitions of the C3 / C4 / C5 blocks (0 = skip)")
+    ap.add_argument("--parity-sample", type=int, default=10_000, help="queries / patterns per rank checked exactly on the host")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "own":
         args.warmup = 3  # timing rule: W >= 3

@@ -71,6 +71,20 @@ def test_batch_final_cpu_baseline(oracle):
         assert (v == ev).all() and secs >= 0
 
 
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 300, 5000, 100_000, 1_200_000])
+def test_batch_interleave_cpu_baseline(oracle, n):
+    """batch_interleave_all_128 (s_tree.rs:684-832), the reference's fastest CPU scheme, restated as a rotating pipeline:
+    every tree height of the dispatch table that fits a test, batch sizes around P * L, several threads."""
+    vals = gen_vals(n, seed=n)
+    t = oracle.Tree.stree(vals, left_max=True)
+    for nq in (0, 1, 127, 128 * 7 + 5, 20_011):
+        qs = gen_queries(nq, seed=nq + 1, vals=vals)
+        ev, _ = oracle.lower_bound(vals, qs)
+        for threads in (1, 3):
+            v, secs = t.batch_interleave(qs, threads)
+            assert (v == ev).all() and secs >= 0, (n, nq, threads)
+
+
 def test_duplicates_and_tiny(oracle):
     for vals in ([MAX], [0, MAX], [5] * 40 + [MAX], list(range(16)), list(range(17)), [7] * 16 + [9] * 16 + [MAX] * 3):
         vals = np.array(vals, np.uint32)
