@@ -1038,7 +1038,7 @@ bk_items_kernel(const uint32_t* __restrict__ runs, const uint32_t* __restrict__ 
 template <bool WANT_IDX, int G>
 __global__ void __launch_bounds__(1024, 1)
 bk_search2_kernel(const BkSearchParams p, uint32_t* __restrict__ qsort, uint32_t* __restrict__ isort, const uint32_t* __restrict__ runs,
-                  unsigned ntp, const uint4* __restrict__ items, unsigned* __restrict__ ctrl, int pol) {
+                  unsigned ntp, const uint4* __restrict__ items, unsigned* __restrict__ ctrl) {
     constexpr int U = G == 8 ? 4 : 2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t* s_sep = reinterpret_cast<uint32_t*>(smem_raw);                 // [r]
@@ -1047,16 +1047,16 @@ bk_search2_kernel(const BkSearchParams p, uint32_t* __restrict__ qsort, uint32_t
     __shared__ unsigned s_item, s_next;
     uint64_t keep;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
-    auto ldleaf = [&](const uint32_t* a, uint32_t (&k)[8]) {  // the bucket's leaf window is read ~3 times per sector: keep it in L2
-        if (pol & 2)
-            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.L2::128B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
-                         : "=r"(k[0]), "=r"(k[1]), "=r"(k[2]), "=r"(k[3]), "=r"(k[4]), "=r"(k[5]), "=r"(k[6]), "=r"(k[7])
-                         : "l"(a), "l"(keep));
-        else ldg256(a, k);
+    // The bucket's leaf window is read ~3 times per sector (by this and the neighbouring work items): keep it in L2.  Measured
+    // (profiles/r2_search2_policy_ab.log): evict_last on the leaf 0.927 -> 0.910 ms; evict-first run loads/stores 0.959 vs 0.910.
+    auto ldleaf = [&](const uint32_t* a, uint32_t (&k)[8]) {
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.L2::128B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                     : "=r"(k[0]), "=r"(k[1]), "=r"(k[2]), "=r"(k[3]), "=r"(k[4]), "=r"(k[5]), "=r"(k[6]), "=r"(k[7])
+                     : "l"(a), "l"(keep));
     };
-    pol &= 1;
-    auto ldq = [&](const uint32_t* a) -> uint32_t { return pol ? *reinterpret_cast<const volatile uint32_t*>(a) : __ldcs(a); };
-    auto stq = [&](uint32_t* a, uint32_t v) { if (pol) *a = v; else __stcs(a, v); };
+    // (a query is read once, before its own lane overwrites it with the answer: plain weak accesses are enough)
+    auto ldq = [&](const uint32_t* a) -> uint32_t { uint32_t v; asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(a)); return v; };
+    auto stq = [&](uint32_t* a, uint32_t v) { *a = v; };
     const unsigned tid = threadIdx.x, lane = tid & 31u;
     if (tid == 0) {
         mbar_init(&bar, 1);
@@ -1089,7 +1089,7 @@ bk_search2_kernel(const BkSearchParams p, uint32_t* __restrict__ qsort, uint32_t
         const uint2 mt = p.meta[b];
         const uint32_t lo = mt.x;
         const unsigned sh = mt.y;
-        const unsigned long long hbase = (unsigned long long)b * p.r;
+        const unsigned hbase32 = b * p.r, m8m1 = (unsigned)(p.m8 - 1);  // block numbers fit 32 bits: at most 2^30 / 8 blocks
         const uint32_t* row = runs + (size_t)b * ntp;
         const unsigned ngroups = (t1 - t0 + 31u) >> 5;
         while (true) {
@@ -1181,29 +1181,39 @@ bk_search2_kernel(const BkSearchParams p, uint32_t* __restrict__ qsort, uint32_t
                     }
                     a[u] = pos;
                 }
+                // the block of G keys that holds the answer: one 32-byte sector (two for G = 16).  Block numbers fit 32 bits
+                // (at most 2^30 / 8 blocks), so the address is one 32 x 32 -> 64 multiply-add.
                 uint32_t ks[U][G];
-                unsigned long long hn[U];
+                unsigned hn[U];
 #pragma unroll
-                for (int u = 0; u < U; u++) {  // the half node that holds the answer: one 32-byte sector
-                    hn[u] = hbase + a[u];
-                    const unsigned long long hc = hn[u] < p.m8 ? hn[u] : p.m8 - 1;
-                    ldleaf(p.leaf + hc * (unsigned long long)G, reinterpret_cast<uint32_t(&)[8]>(ks[u][0]));
-                    if constexpr (G == 16) ldleaf(p.leaf + hc * 16ull + 8ull, reinterpret_cast<uint32_t(&)[8]>(ks[u][8]));
+                for (int u = 0; u < U; u++) {
+                    hn[u] = hbase32 + a[u];
+                    const unsigned hc = min(hn[u], m8m1);
+                    const uint32_t* src = p.leaf + (size_t)hc * (unsigned)G;
+                    ldleaf(src, reinterpret_cast<uint32_t(&)[8]>(ks[u][0]));
+                    if constexpr (G == 16) ldleaf(src + 8, reinterpret_cast<uint32_t(&)[8]>(ks[u][8]));
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
-                    unsigned cc = 0;
+                    // The keys are sorted and at most MAX = 2^31 - 1, the query is canonical (<= MAX): the first key >= q is the
+                    // one with the smallest difference key - q among the non-negative ones, and a negative difference wraps to
+                    // >= 2^31 + 1.  One subtract and one unsigned min per key (it was a compare, a conditional increment and a
+                    // compare + select per key: 45 -> 17 instructions per query).
+                    uint32_t md = ks[u][0] - q[u];
 #pragma unroll
-                    for (int e = 0; e < G; e++) cc += ks[u][e] < q[u] ? 1u : 0u;
-                    uint32_t val = ks[u][0];
-#pragma unroll
-                    for (int e = 1; e < G; e++) val = cc == (unsigned)e ? ks[u][e] : val;
-                    unsigned long long pos = hn[u] * (unsigned long long)G + cc;
-                    if (hn[u] >= p.m8 || cc == (unsigned)G) { val = kMax; pos = p.n; }  // above every key (cc == G cannot happen below m8)
-                    if (pos > p.n) pos = p.n;
+                    for (int e = 1; e < G; e++) md = min(md, ks[u][e] - q[u]);
+                    const bool none = md > 0x7fffffffu || hn[u] > m8m1;  // above every key of the block (only past the last key) / past the end
+                    const uint32_t val = none ? kMax : q[u] + md;
                     if (k0 + u * 32u + lane < T) {
                         stq(qsort + ad[u], val);
-                        if constexpr (WANT_IDX) stq(isort + ad[u], (uint32_t)pos);
+                        if constexpr (WANT_IDX) {
+                            unsigned cc = 0;
+#pragma unroll
+                            for (int e = 0; e < G; e++) cc += ks[u][e] < q[u] ? 1u : 0u;
+                            unsigned long long pos = (unsigned long long)hn[u] * (unsigned)G + cc;
+                            if (none || pos > p.n) pos = p.n;
+                            stq(isort + ad[u], (uint32_t)pos);
+                        }
                     }
                 }
             }
@@ -1702,10 +1712,10 @@ static int launch_bucketed_v2(const sst_index* idx, const uint32_t* d_qs, size_t
         mark();
         mark();  // (no scatter stage: kept so that the five stage times line up with the V1 report)
         {
-            void (*kern)(const BkSearchParams, uint32_t*, uint32_t*, const uint32_t*, unsigned, const uint4*, unsigned*, int) =
+            void (*kern)(const BkSearchParams, uint32_t*, uint32_t*, const uint32_t*, unsigned, const uint4*, unsigned*) =
                 a.g == 16 ? (d_idx ? bk_search2_kernel<true, 16> : bk_search2_kernel<false, 16>) : (d_idx ? bk_search2_kernel<true, 8> : bk_search2_kernel<false, 8>);
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_search);
-            kern<<<sms, 1024, smem_search, st>>>(sp, s.qsort, s.isort, s.runs, h.ntp, s.items, s.ctrl, (int)(opt(OPT_BK_POL) | (opt(OPT_BK_LEAF_KEEP) << 1)));
+            kern<<<sms, 1024, smem_search, st>>>(sp, s.qsort, s.isort, s.runs, h.ntp, s.items, s.ctrl);
         }
         mark();
         launch_unperm<uint32_t>(sms, st, s.qsort, s.lpos, cnt, ntiles, d_vals + off);

@@ -77,8 +77,6 @@ unsigned cur_sms();                   // sm_count of the calling thread's curren
     X(BK_TIMING, 0, 0, 2)                /* per-stage CUDA-event times (synchronises; bench/tools only) */                    \
     X(BK_V1, 0, 0, 1)                    /* 1 = the round-1 seven-launch pipeline (A/B runs) */                               \
     X(BK_CHUNK2_LOG2, 15, 14, 24)        /* log2 of the queries per search work item of the V2 pipeline */                    \
-    X(BK_LEAF_KEEP, 1, 0, 1)             /* V2 search: leaf sectors carry an L2 evict_last hint */                             \
-    X(BK_POL, 1, 0, 1)                   /* V2 search: 0 = streaming (evict-first) run loads/stores, 1 = default policy */       \
     X(BK_HYBRID, 1, 0, 4)                                                                                                    \
     X(BK_VEC, 1, 0, 1)                                                                                                       \
     X(BK_MOVE_THREADS, 1024, 512, 1024)                                                                                      \
