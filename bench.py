@@ -390,7 +390,7 @@ def run_own(args):
         sst.set_option("BK_TIMING", 0)
         st_ms = (C.c_double * 5)()
         if L.sst_last_stage_ms(st_ms, 5) == 5:
-            names = ["rank", "plan", "scatter", "search", "gather"] if sst.get_option("BK_V1") else ["partition", "plan", "-", "search", "unpermute"]
+            names = ["partition", "plan", "-", "search", "unpermute"]
             roofline["stage_ms"] = {k: round(float(x), 4) for k, x in zip(names, st_ms) if k != "-"}
             tot_st = sum(float(x) for x in st_ms)
             # the dominant kernel of the step and its share (to be compared with the ncu launch list in profiles/)

@@ -38,15 +38,11 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kTile = 16384;                 // queries per partition tile (64 KB of shared memory)
 constexpr int kThreads = 512;
-constexpr int kWarps = kThreads / 32;
-constexpr int kItems = kTile / kThreads;     // 32 queries per thread
 // jump table: one cell per separator of a bucket (cells = r), r + 8 u16 entries per bucket (a multiple of 16 bytes)
 constexpr int kBtShift = 18;                 // bucket table over the top 13 bits of a 31-bit key
 constexpr int kBtCells = 1 << (31 - kBtShift);
 constexpr int kBtStride = kBtCells + 8;
 constexpr unsigned kMinChunk = 16384;        // queries per search work item: at least this many (scratch sizing)
-constexpr int kTilesPerGroup = 64;
-constexpr unsigned kLongRun = 128;           // map runs longer than this are filled cooperatively
 constexpr size_t kSubBatch = (size_t)1 << 27;  // queries per pipeline run (bounds the scratch buffers)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -230,357 +226,6 @@ __device__ __forceinline__ void rank_items(uint16_t* cntw, uint32_t (&pk)[ITEMS]
 }
 
 // FULL: every tile in [tile_begin, tile_end) holds kTile queries (the partial last tile gets its own launch).
-template <int BITS, bool FULL, int HYBRID>
-__device__ __forceinline__ void rank_tile(const BkView& v, const uint32_t* __restrict__ qs, size_t nq, unsigned tile, uint32_t* __restrict__ counts,
-                                          uint16_t* __restrict__ lpos16, uint16_t* cnt, const uint32_t* s_pk, unsigned* s_warp) {
-    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    uint16_t* cntw = cnt + (size_t)warp * v.nbp;
-    {
-        {   // zero the per-warp counters
-            uint4* c4 = reinterpret_cast<uint4*>(cnt);
-            const unsigned n16 = kWarps * v.nbp / 8;
-            for (unsigned i = tid; i < n16; i += kThreads) c4[i] = make_uint4(0, 0, 0, 0);
-        }
-        const size_t tile_base = (size_t)tile * kTile;
-        const unsigned tile_n = FULL ? (unsigned)kTile : (unsigned)min((size_t)kTile, nq - tile_base);
-        const uint32_t* tq = qs + tile_base + warp * (kItems * 32) + lane;
-        const unsigned i0 = warp * (kItems * 32) + lane;
-        __syncthreads();  // tables + zeroed counters visible
-        uint32_t pk[kItems];  // bucket | rank << 16; 0xffffffff = no query
-#pragma unroll
-        for (int r = 0; r < kItems; r++) pk[r] = (FULL || i0 + r * 32 < tile_n) ? __ldcs(tq + r * 32) : 0u;
-        if (v.above) {  // (uniform) the partitioned layouts answer q > MAX with (MAX, n), not with the signed compare: note it
-            uint32_t acc = 0;
-#pragma unroll
-            for (int r = 0; r < kItems; r++) acc |= pk[r];
-            if (__any_sync(kFull, acc > kMax) && lane == 0) atomicOr(v.above, 1u);
-        }
-#pragma unroll
-        for (int r = 0; r < kItems; r++)
-            pk[r] = (FULL || i0 + r * 32 < tile_n) ? bk_bucket_packed(s_pk, v.bt, v.split, canonical(pk[r])) : 0xffffffffu;
-        rank_items<BITS, FULL, HYBRID, kItems>(cntw, pk, lane, lt_mask);
-        __syncthreads();
-        // per bucket: exclusive scan over the warps, total to the count matrix, start inside the tile
-        unsigned tot[4] = {0, 0, 0, 0}, sum = 0;
-        if (v.bpt == 4) {  // 2048 buckets: four consecutive 16-bit counters per thread and warp in one 8-byte access
-            uint2* c2 = reinterpret_cast<uint2*>(cnt) + tid;
-#pragma unroll
-            for (int w = 0; w < kWarps; w++) {
-                const uint2 c = c2[(size_t)w * (v.nbp / 4)];
-                c2[(size_t)w * (v.nbp / 4)] = make_uint2(tot[0] | (tot[1] << 16), tot[2] | (tot[3] << 16));
-                tot[0] += c.x & 0x7ffu; tot[1] += (c.x >> 16) & 0x7ffu; tot[2] += c.y & 0x7ffu; tot[3] += (c.y >> 16) & 0x7ffu;  // (claim tags masked off)
-            }
-            sum = tot[0] + tot[1] + tot[2] + tot[3];
-            *reinterpret_cast<uint4*>(counts + (size_t)tile * v.nbp + tid * 4) = make_uint4(tot[0], tot[1], tot[2], tot[3]);
-        } else if (v.bpt == 2) {  // 1024 buckets: two counters per 4-byte access
-            uint32_t* c1 = reinterpret_cast<uint32_t*>(cnt) + tid;
-#pragma unroll
-            for (int w = 0; w < kWarps; w++) {
-                const uint32_t c = c1[(size_t)w * (v.nbp / 2)];
-                c1[(size_t)w * (v.nbp / 2)] = tot[0] | (tot[1] << 16);
-                tot[0] += c & 0x7ffu; tot[1] += (c >> 16) & 0x7ffu;
-            }
-            sum = tot[0] + tot[1];
-            *reinterpret_cast<uint2*>(counts + (size_t)tile * v.nbp + tid * 2) = make_uint2(tot[0], tot[1]);
-        } else {
-#pragma unroll
-            for (unsigned k = 0; k < 4; k++)
-                if (k < v.bpt) {
-                    const unsigned b = tid * v.bpt + k;
-                    unsigned run = 0;
-#pragma unroll
-                    for (int w = 0; w < kWarps; w++) {
-                        const unsigned c = cnt[(size_t)w * v.nbp + b] & 0x7ffu;
-                        cnt[(size_t)w * v.nbp + b] = (uint16_t)run;
-                        run += c;
-                    }
-                    tot[k] = run;
-                    sum += run;
-                    counts[(size_t)tile * v.nbp + b] = run;
-                }
-        }
-        unsigned total;
-        const unsigned base = block_excl_scan(sum, s_warp, &total);
-        // fold the bucket's start inside the tile into the per-warp bases
-        if (v.bpt == 4) {
-            const unsigned s0 = base, s1 = s0 + tot[0], s2 = s1 + tot[1], s3 = s2 + tot[2];
-            const uint2 add = make_uint2(s0 | (s1 << 16), s2 | (s3 << 16));
-            uint2* c2 = reinterpret_cast<uint2*>(cnt) + tid;
-#pragma unroll
-            for (int w = 0; w < kWarps; w++) {
-                uint2 c = c2[(size_t)w * (v.nbp / 4)];
-                c.x += add.x; c.y += add.y;  // 16-bit lanes cannot carry: every sum is < kTile
-                c2[(size_t)w * (v.nbp / 4)] = c;
-            }
-        } else if (v.bpt == 2) {
-            const uint32_t add = base | ((base + tot[0]) << 16);
-            uint32_t* c1 = reinterpret_cast<uint32_t*>(cnt) + tid;
-#pragma unroll
-            for (int w = 0; w < kWarps; w++) c1[(size_t)w * (v.nbp / 2)] += add;
-        } else {
-            unsigned st = base;
-#pragma unroll
-            for (unsigned k = 0; k < 4; k++)
-                if (k < v.bpt) {
-                    const unsigned b = tid * v.bpt + k;
-#pragma unroll
-                    for (int w = 0; w < kWarps; w++) cnt[(size_t)w * v.nbp + b] += (uint16_t)st;
-                    st += tot[k];
-                }
-        }
-        __syncthreads();
-        uint16_t* tl = lpos16 + tile_base + warp * (kItems * 32) + lane;
-#pragma unroll
-        for (int r = 0; r < kItems; r++)
-            if (FULL || i0 + r * 32 < tile_n) tl[r * 32] = (uint16_t)(cntw[pk[r] & 0xffffu] + (pk[r] >> 16));
-        __syncthreads();  // counters are zeroed again at the top
-    }
-}
-
-template <int BITS, int HYBRID>
-__global__ void __launch_bounds__(kThreads, 2)
-bk_rank_kernel(const BkView v, const uint32_t* __restrict__ qs, size_t nq, unsigned ntiles, uint32_t* __restrict__ counts,
-               uint16_t* __restrict__ lpos16, uint32_t* __restrict__ tot) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    if (blockIdx.x == 0)  // bucket totals accumulated by bk_colsum_kernel, which runs after this kernel
-        for (unsigned i = threadIdx.x; i < v.nbp; i += kThreads) tot[i] = 0;
-    uint16_t* cnt = reinterpret_cast<uint16_t*>(smem_raw);                       // [kWarps][nbp]
-    uint32_t* s_pk = reinterpret_cast<uint32_t*>(cnt + (size_t)kWarps * v.nbp);  // [kBtCells] packed bucket table
-    __shared__ unsigned s_warp[kWarps + 1];
-    const unsigned tid = threadIdx.x;
-    for (unsigned i = tid; i < (unsigned)kBtCells; i += kThreads) s_pk[i] = bk_pack_cell(v.bt, v.split, v.nb, i);
-    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        if ((size_t)(tile + 1) * kTile <= nq) rank_tile<BITS, true, HYBRID>(v, qs, nq, tile, counts, lpos16, cnt, s_pk, s_warp);
-        else rank_tile<BITS, false, HYBRID>(v, qs, nq, tile, counts, lpos16, cnt, s_pk, s_warp);  // partial last tile
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// plan: scan of the count matrix (tiles x buckets) and the work-item list of the search kernel
-// ------------------------------------------------------------------------------------------------
-// gsum[g][b] = queries of bucket b in the tiles of group g; tot[b] += the same (zeroed by the rank kernel)
-__global__ void __launch_bounds__(256)
-bk_colsum_kernel(const uint32_t* __restrict__ counts, unsigned ntiles, unsigned nbp, uint32_t* __restrict__ gsum, uint32_t* __restrict__ tot) {
-    const unsigned b = blockIdx.x * 256 + threadIdx.x, g = blockIdx.y;
-    const unsigned t0 = g * kTilesPerGroup, t1 = min(t0 + kTilesPerGroup, ntiles);
-    unsigned s = 0;
-    for (unsigned t = t0; t < t1; t++) s += counts[(size_t)t * nbp + b];
-    gsum[(size_t)g * nbp + b] = s;
-    if (s) atomicAdd(tot + b, s);
-}
-
-// bucket starts, work items of the search kernel; ctrl[0] = work counter, ctrl[1] = number of work items
-__global__ void __launch_bounds__(1024)
-bk_plan_kernel(const uint32_t* __restrict__ tot_in, unsigned nbp, unsigned chunk, uint32_t* __restrict__ bstart, uint2* __restrict__ items,
-               unsigned* __restrict__ ctrl) {
-    __shared__ unsigned s_warp[33];
-    const unsigned tid = threadIdx.x;
-    unsigned tot[2] = {0, 0};
-    if (tid * 2 < nbp) { const uint2 t2 = *reinterpret_cast<const uint2*>(tot_in + tid * 2); tot[0] = t2.x; tot[1] = t2.y; }
-    unsigned total;
-    unsigned base = block_excl_scan(tot[0] + tot[1], s_warp, &total);
-    if (tid * 2 < nbp) bstart[tid * 2] = base;
-    if (tid * 2 + 1 < nbp) bstart[tid * 2 + 1] = base + tot[0];
-    if (tid == 0) bstart[nbp] = total;
-    __syncthreads();
-    const unsigned ni0 = (tot[0] + chunk - 1) / chunk, ni1 = (tot[1] + chunk - 1) / chunk;
-    unsigned nitems;
-    unsigned ib = block_excl_scan(ni0 + ni1, s_warp, &nitems);
-    for (unsigned c = 0; c < ni0; c++) items[ib + c] = make_uint2(tid * 2, c);
-    for (unsigned c = 0; c < ni1; c++) items[ib + ni0 + c] = make_uint2(tid * 2 + 1, c);
-    if (tid == 0) { ctrl[0] = 0; ctrl[1] = nitems; ctrl[2] = chunk; }
-}
-
-// offs[t][b] = position in the bucketed array of the first query of (tile t, bucket b)
-__global__ void __launch_bounds__(256)
-bk_offsets_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ gsum, const uint32_t* __restrict__ bstart,
-                  unsigned ntiles, unsigned nbp, uint32_t* __restrict__ offs) {
-    const unsigned b = blockIdx.x * 256 + threadIdx.x, g = blockIdx.y;
-    const unsigned t0 = g * kTilesPerGroup, t1 = min(t0 + kTilesPerGroup, ntiles);
-    unsigned run = bstart[b];
-    for (unsigned g0 = 0; g0 < g; g0 += 16) {  // queries of the bucket in earlier tile groups (16 loads in flight)
-        unsigned c[16];
-#pragma unroll
-        for (unsigned j = 0; j < 16; j++) c[j] = g0 + j < g ? gsum[(size_t)(g0 + j) * nbp + b] : 0u;
-#pragma unroll
-        for (unsigned j = 0; j < 16; j++) run += c[j];
-    }
-    for (unsigned t = t0; t < t1; t++) {
-        const unsigned c = counts[(size_t)t * nbp + b];
-        offs[(size_t)t * nbp + b] = run;
-        run += c;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// scatter (GATHER = false): queries of a tile -> bucket order; gather (GATHER = true): results back.
-// A full tile with 16-byte aligned buffers takes the vector path: four queries per load (LDG.128 + LDG.64 of the
-// positions), run elements fetched by 4-byte cp.async (LDGSTS) straight into shared memory so that all 32 per
-// thread are in flight at once; a partial last tile or an odd pointer takes the checked scalar path.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src_gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-
-// THREADS = 512 (two CTAs per SM) or 1024 (one CTA per SM: the same shared memory, i.e. ~120 KB of L1 left for loads in flight)
-template <bool GATHER, typename OutT, int THREADS, bool PREFETCH = false>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
-bk_move_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offs, const uint16_t* __restrict__ lpos16,
-               unsigned nbp, unsigned bpt, unsigned ntiles, size_t nq, int aligned, const uint32_t* __restrict__ src,
-               OutT* __restrict__ dst) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint32_t* s_tile = reinterpret_cast<uint32_t*>(smem_raw);        // [kTile] in bucket order
-    uint32_t* s_delta = s_tile + kTile;                                // [nbp] global offset - local start
-    uint16_t* s_map = reinterpret_cast<uint16_t*>(s_delta + nbp);      // [kTile] bucket of each local position
-    __shared__ unsigned s_warp[THREADS / 32 + 1];
-    __shared__ uint4 s_long[kTile / kLongRun];  // runs longer than kLongRun: {begin, end, bucket}
-    __shared__ unsigned s_nlong;
-    const unsigned tid = threadIdx.x;
-    if (tid == 0) s_nlong = 0;
-    __syncthreads();
-    constexpr int kIt = kTile / THREADS;  // queries per thread
-    constexpr int kVec = kIt / 4;         // groups of 4 consecutive queries per thread
-    unsigned c[4] = {0, 0, 0, 0}, o[4] = {0, 0, 0, 0};
-    auto load_row = [&](unsigned tile) {  // this thread's buckets of the count / offset rows of `tile`
-        if (bpt == 4) {
-            const uint4 c4 = *reinterpret_cast<const uint4*>(counts + (size_t)tile * nbp + tid * 4);
-            const uint4 o4 = *reinterpret_cast<const uint4*>(offs + (size_t)tile * nbp + tid * 4);
-            c[0] = c4.x; c[1] = c4.y; c[2] = c4.z; c[3] = c4.w;
-            o[0] = o4.x; o[1] = o4.y; o[2] = o4.z; o[3] = o4.w;
-        } else {
-#pragma unroll
-            for (unsigned k = 0; k < 4; k++)
-                if (k < bpt) { c[k] = counts[(size_t)tile * nbp + tid * bpt + k]; o[k] = offs[(size_t)tile * nbp + tid * bpt + k]; }
-        }
-    };
-    if (blockIdx.x < ntiles) load_row(blockIdx.x);
-    // scatter: the queries and positions of the NEXT tile are loaded into registers right after this tile's have been
-    // placed in shared memory, so that their DRAM latency is hidden behind the copy-out phase (one CTA per SM: nothing else
-    // would overlap it; ncu: long-scoreboard + barrier stalls were 43 % of the samples)
-    [[maybe_unused]] uint4 pq[kVec];
-    [[maybe_unused]] uint2 pl[kVec];
-    [[maybe_unused]] bool have = false;
-    auto prefetch_tile = [&](unsigned tile) {
-        if constexpr (!GATHER) {
-            have = PREFETCH && aligned && tile < ntiles && (size_t)(tile + 1) * kTile <= nq;
-            if (have) {
-                const uint4* q4 = reinterpret_cast<const uint4*>(src + (size_t)tile * kTile);
-                const uint2* l2 = reinterpret_cast<const uint2*>(lpos16 + (size_t)tile * kTile);
-#pragma unroll
-                for (int r = 0; r < kVec; r++) { pq[r] = __ldcs(q4 + r * THREADS + tid); pl[r] = __ldcs(l2 + r * THREADS + tid); }
-            }
-        }
-    };
-    prefetch_tile(blockIdx.x);
-    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const size_t tile_base = (size_t)tile * kTile;
-        const unsigned tile_n = (unsigned)min((size_t)kTile, nq - tile_base);
-        unsigned total;
-        unsigned base = block_excl_scan(c[0] + c[1] + c[2] + c[3], s_warp, &total);
-#pragma unroll
-        for (unsigned k = 0; k < 4; k++)
-            if (k < bpt) {
-                const unsigned b = tid * bpt + k;
-                s_delta[b] = o[k] - base;
-                unsigned j = base, e = base + c[k];  // fill [j, e) with b: 32-bit stores over the aligned middle
-                if (c[k] > kLongRun) {  // skewed batch: a long run is filled by the whole CTA below, not by one thread
-                    const unsigned slot = atomicAdd(&s_nlong, 1u);
-                    s_long[slot] = make_uint4(j, e, b, 0);
-                } else {
-                    if (j < e && (j & 1u)) s_map[j++] = (uint16_t)b;
-                    for (; j + 2 <= e; j += 2) *reinterpret_cast<uint32_t*>(s_map + j) = b | (b << 16);
-                    if (j < e) s_map[j] = (uint16_t)b;
-                }
-                base = e;
-            }
-        if (tile + gridDim.x < ntiles) load_row(tile + gridDim.x);  // next tile's rows: in flight during this tile
-        __syncthreads();
-        if (s_nlong) {  // (block-uniform)
-            const unsigned nl = s_nlong;
-            for (unsigned q = 0; q < nl; q++) {
-                const uint4 lr = s_long[q];
-                for (unsigned j = lr.x + tid; j < lr.y; j += THREADS) s_map[j] = (uint16_t)lr.z;
-            }
-            __syncthreads();
-            if (tid == 0) s_nlong = 0;
-        }
-        if (aligned && tile_n == (unsigned)kTile) {
-            const uint2* l2 = reinterpret_cast<const uint2*>(lpos16 + tile_base);
-            if constexpr (!GATHER) {
-                if (!have) prefetch_tile(tile);  // (block-uniform) first tile of a CTA without the prefetch
-                if (!have) {
-                    const uint4* q4 = reinterpret_cast<const uint4*>(src + tile_base);
-#pragma unroll
-                    for (int r = 0; r < kVec; r++) { pq[r] = __ldcs(q4 + r * THREADS + tid); pl[r] = __ldcs(l2 + r * THREADS + tid); }
-                }
-#pragma unroll
-                for (int r = 0; r < kVec; r++) {
-                    s_tile[pl[r].x & 0xffffu] = canonical(pq[r].x); s_tile[pl[r].x >> 16] = canonical(pq[r].y);
-                    s_tile[pl[r].y & 0xffffu] = canonical(pq[r].z); s_tile[pl[r].y >> 16] = canonical(pq[r].w);
-                }
-                prefetch_tile(tile + gridDim.x);
-                __syncthreads();
-#pragma unroll
-                for (int r = 0; r < kIt; r++) {  // runs: consecutive lanes write consecutive words
-                    const unsigned i = r * THREADS + tid;
-                    dst[s_delta[s_map[i]] + i] = (OutT)s_tile[i];
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < kIt; r++) {
-                    const unsigned i = r * THREADS + tid;
-                    cp_async4(s_tile + i, src + (s_delta[s_map[i]] + i));
-                }
-                uint2 l[kVec];
-#pragma unroll
-                for (int r = 0; r < kVec; r++) l[r] = __ldcs(l2 + r * THREADS + tid);
-                cp_async_wait_all();
-                __syncthreads();
-#pragma unroll
-                for (int r = 0; r < kVec; r++) {
-                    const uint32_t v0 = s_tile[l[r].x & 0xffffu], v1 = s_tile[l[r].x >> 16], v2 = s_tile[l[r].y & 0xffffu], v3 = s_tile[l[r].y >> 16];
-                    OutT* d = dst + tile_base + (size_t)(r * THREADS + tid) * 4;
-                    if constexpr (sizeof(OutT) == 4) {
-                        __stcs(reinterpret_cast<uint4*>(d), make_uint4(v0, v1, v2, v3));
-                    } else {
-                        __stcs(reinterpret_cast<ulonglong2*>(d), make_ulonglong2(v0, v1));
-                        __stcs(reinterpret_cast<ulonglong2*>(d) + 1, make_ulonglong2(v2, v3));
-                    }
-                }
-            }
-        } else if constexpr (!GATHER) {
-#pragma unroll 8
-            for (int r = 0; r < kIt; r++) {
-                const unsigned i = r * THREADS + tid;
-                if (i < tile_n) s_tile[lpos16[tile_base + i]] = canonical(__ldcs(src + tile_base + i));
-            }
-            __syncthreads();
-#pragma unroll 8
-            for (int r = 0; r < kIt; r++) {
-                const unsigned i = r * THREADS + tid;
-                if (i < tile_n) dst[s_delta[s_map[i]] + i] = (OutT)s_tile[i];
-            }
-        } else {
-#pragma unroll 8
-            for (int r = 0; r < kIt; r++) {
-                const unsigned i = r * THREADS + tid;
-                if (i < tile_n) s_tile[i] = __ldcs(src + (s_delta[s_map[i]] + i));
-            }
-            __syncthreads();
-#pragma unroll 8
-            for (int r = 0; r < kIt; r++) {
-                const unsigned i = r * THREADS + tid;
-                if (i < tile_n) __stcs(dst + tile_base + i, (OutT)s_tile[lpos16[tile_base + i]]);
-            }
-        }
-        __syncthreads();
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // search: one work item = (bucket, chunk of its queries)
 // ------------------------------------------------------------------------------------------------
@@ -594,172 +239,8 @@ struct BkSearchParams {
     unsigned long long n;
 };
 
-__device__ __forceinline__ void ldg256(const uint32_t* p, uint32_t (&k)[8]) {
-    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(k[0]), "=r"(k[1]), "=r"(k[2]), "=r"(k[3]), "=r"(k[4]), "=r"(k[5]), "=r"(k[6]), "=r"(k[7])
-                 : "l"(p));
-}
 
 // G = keys per separator: 8 (half node, one 32-byte sector per query) up to 2^29 keys, 16 (whole node, two sectors) above
-template <bool WANT_IDX, int G, int PROBE>
-__global__ void __launch_bounds__(1024, 1)
-bk_search_kernel(const BkSearchParams p, const uint32_t* __restrict__ qb, const uint32_t* __restrict__ bstart,
-                 const uint2* __restrict__ items, unsigned* __restrict__ ctrl, uint32_t* __restrict__ rb, uint32_t* __restrict__ ib) {
-    constexpr int U = G == 8 ? 4 : 2;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint32_t* s_sep = reinterpret_cast<uint32_t*>(smem_raw);                 // [r]
-    uint16_t* s_jump = reinterpret_cast<uint16_t*>(s_sep + p.r);              // [r + 8]
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ unsigned s_item;
-    const unsigned tid = threadIdx.x, nthr = blockDim.x;
-    if (tid == 0) {
-        mbar_init(&bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    unsigned phase = 0, cur_b = 0xffffffffu;
-    const unsigned nitems = ctrl[1], chunk = ctrl[2];
-    while (true) {
-        __syncthreads();  // previous item finished: s_item, s_sep, s_jump may be overwritten
-        if (tid == 0) s_item = atomicAdd(&ctrl[0], 1u);
-        __syncthreads();
-        const unsigned item = s_item;
-        if (item >= nitems) break;
-        const uint2 it = items[item];
-        const unsigned b = it.x;
-        if (b != cur_b) {  // stage the bucket: 1-D TMA bulk copies (SASS UBLKCP), completion on the mbarrier
-            if (tid == 0) {
-                const unsigned sep_bytes = p.r * 4u, jump_bytes = (p.r + 8u) * 2u;
-                mbar_expect_tx(&bar, sep_bytes + jump_bytes);
-                for (unsigned off = 0; off < sep_bytes; off += 32768u)
-                    tma_bulk_g2s((char*)s_sep + off, (const char*)(p.sep + (size_t)b * p.r) + off, min(32768u, sep_bytes - off), &bar);
-                for (unsigned off = 0; off < jump_bytes; off += 32768u)
-                    tma_bulk_g2s((char*)s_jump + off, (const char*)(p.jump + (size_t)b * (p.r + 8u)) + off, min(32768u, jump_bytes - off), &bar);
-            }
-            mbar_wait(&bar, phase);
-            phase ^= 1u;
-            cur_b = b;
-        }
-        const uint2 mt = p.meta[b];
-        const uint32_t lo = mt.x;
-        const unsigned sh = mt.y;
-        const unsigned qbeg = bstart[b] + it.y * chunk, qend = min(qbeg + chunk, bstart[b + 1]);
-        const unsigned long long hbase = (unsigned long long)b * p.r;
-        uint32_t qn[U];  // queries of the next round: their loads stay in flight while this round is answered
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const unsigned i = qbeg + tid + u * nthr;
-            qn[u] = i < qend ? __ldcs(qb + i) : lo;
-        }
-        for (unsigned i0 = qbeg + tid; i0 < qend; i0 += nthr * U) {
-            uint32_t q[U];
-            unsigned a[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                q[u] = qn[u];
-                const unsigned i = i0 + (U + u) * nthr;
-                qn[u] = i < qend ? __ldcs(qb + i) : lo;
-            }
-            // rank among the bucket's separators: jump-table cell, then three unconditional probes (independent
-            // shared loads for all U queries); a cell with more separators below q continues in a loop (rare)
-            if constexpr (PROBE == 1) {
-                // Predicated probes: jump[x] separators are below q's cell, every separator of a later cell is above q and the
-                // bucket's last separator is >= q, so the scan needs no upper end.  A lane probes again only while its separator
-                // is below q (37 % / 10 % / 2 % of the lanes for uniform keys): idle lanes cost no shared-memory wavefronts.
-                unsigned l[U];
-                uint32_t s0[U];
-#pragma unroll
-                for (int u = 0; u < U; u++) l[u] = s_jump[(q[u] - lo) >> sh];
-#pragma unroll
-                for (int u = 0; u < U; u++) s0[u] = s_sep[min(l[u], p.r - 1u)];
-#pragma unroll
-                for (int u = 0; u < U; u++) {
-                    unsigned pos = l[u];
-                    if (s0[u] < q[u]) {
-                        pos++;
-                        if (s_sep[min(pos, p.r - 1u)] < q[u]) {
-                            pos++;
-                            if (s_sep[min(pos, p.r - 1u)] < q[u]) {
-                                pos++;
-                                unsigned hh = s_jump[((q[u] - lo) >> sh) + 1u];
-                                if (hh > pos + 8u) {
-                                    while (pos < hh) {
-                                        const unsigned m = (pos + hh) >> 1;
-                                        if (s_sep[m] < q[u]) pos = m + 1; else hh = m;
-                                    }
-                                } else {
-                                    while (pos < hh && s_sep[pos] < q[u]) pos++;
-                                }
-                            }
-                        }
-                    }
-                    a[u] = pos;
-                }
-            } else {
-                unsigned l[U], h[U];
-#pragma unroll
-                for (int u = 0; u < U; u++) {
-                    const unsigned x = (q[u] - lo) >> sh;
-                    l[u] = s_jump[x];
-                    h[u] = s_jump[x + 1];
-                }
-                uint32_t s0[U], s1[U], s2[U];
-#pragma unroll
-                for (int u = 0; u < U; u++) {
-                    s0[u] = s_sep[min(l[u], p.r - 1u)];
-                    s1[u] = s_sep[min(l[u] + 1u, p.r - 1u)];
-                    s2[u] = s_sep[min(l[u] + 2u, p.r - 1u)];
-                }
-#pragma unroll
-                for (int u = 0; u < U; u++) {
-                    const bool c0 = l[u] < h[u] && s0[u] < q[u];
-                    const bool c1 = c0 && l[u] + 1u < h[u] && s1[u] < q[u];
-                    const bool c2 = c1 && l[u] + 2u < h[u] && s2[u] < q[u];
-                    unsigned pos = l[u] + (c0 ? 1u : 0u) + (c1 ? 1u : 0u) + (c2 ? 1u : 0u);
-                    if (c2) {
-                        unsigned hh = h[u];
-                        if (hh - pos > 8u) {
-                            while (pos < hh) {
-                                const unsigned m = (pos + hh) >> 1;
-                                if (s_sep[m] < q[u]) pos = m + 1; else hh = m;
-                            }
-                        } else {
-                            while (pos < hh && s_sep[pos] < q[u]) pos++;
-                        }
-                    }
-                    a[u] = pos;
-                }
-            }
-            uint32_t ks[U][G];
-            unsigned long long hn[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) {  // the half node that holds the answer: one 32-byte sector
-                hn[u] = hbase + a[u];
-                const unsigned long long hc = hn[u] < p.m8 ? hn[u] : p.m8 - 1;
-                ldg256(p.leaf + hc * (unsigned long long)G, reinterpret_cast<uint32_t(&)[8]>(ks[u][0]));
-                if constexpr (G == 16) ldg256(p.leaf + hc * 16ull + 8ull, reinterpret_cast<uint32_t(&)[8]>(ks[u][8]));
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const unsigned i = i0 + u * nthr;
-                unsigned c = 0;
-#pragma unroll
-                for (int e = 0; e < G; e++) c += ks[u][e] < q[u] ? 1u : 0u;
-                uint32_t val = ks[u][0];
-#pragma unroll
-                for (int e = 1; e < G; e++) val = c == (unsigned)e ? ks[u][e] : val;
-                unsigned long long pos = hn[u] * (unsigned long long)G + c;
-                if (hn[u] >= p.m8 || c == (unsigned)G) { val = kMax; pos = p.n; }  // above every key (c == G cannot happen below m8)
-                if (pos > p.n) pos = p.n;
-                if (i < qend) {
-                    __stcs(rb + i, val);
-                    if constexpr (WANT_IDX) __stcs(ib + i, (uint32_t)pos);
-                }
-            }
-        }
-    }
-}
-
-
 // ================================================================================================
 // V2 pipeline: tile-local partition -> plan -> search over runs, in place -> streaming un-permute
 //
@@ -775,6 +256,10 @@ bk_search_kernel(const BkSearchParams p, const uint32_t* __restrict__ qb, const 
 // is contiguous.  Per step: the queries are read once, nothing waits on another CTA (no look-back), 5 launches.
 // ================================================================================================
 constexpr int kPThreads = 1024;                // partition / un-permute CTA
+#ifndef SST_BK_STHREADS
+#define SST_BK_STHREADS 1024
+#endif
+constexpr int kSThreads = SST_BK_STHREADS;     // search CTA
 constexpr int kPWarps = kPThreads / 32;
 constexpr int kPItems = kTile / kPThreads;     // 16 queries per thread
 constexpr unsigned kCntPad = 16;               // u16 of padding per counter row of the partition kernel (32 bytes = 8 banks)
@@ -1031,50 +516,75 @@ bk_items_kernel(const uint32_t* __restrict__ runs, const uint32_t* __restrict__ 
 }
 
 // ---- search over runs, in place --------------------------------------------------------------------
-// One work item = (bucket, tile range).  The bucket's separators and jump table are staged as in the V1 kernel; a warp
-// then takes 32 tiles at a time: lane i holds run i's {start, count}, a warp scan gives every run its offset in the
-// group's flattened query sequence, and the lane that handles flattened query k finds its run with a five-step search
-// over those offsets by shuffles.  Each answer overwrites its query.
+// One work item = (bucket, tile range).  The bucket's separators and jump table are staged in shared memory by 1-D TMA bulk
+// copies; the item's tiles are taken 32 at a time (a "group": lane i holds run i's {start, count}, a warp scan gives every
+// run its offset in the group's flattened query sequence, the lane that handles flattened query k finds its run among the
+// next few offsets by broadcast shuffles), warp w takes groups w, w + 32, ...  Each answer overwrites its query.
+//
+// Everything that does not need the staged tables runs ahead of them, because nothing else hides a DRAM round trip with
+// 32 warps per SM (ncu before: 10 % of the warp samples sat in the group set-up, 12 % at the item boundary):
+//   * the queries of round k + 1 are loaded while round k is answered -- also across a group boundary: the last round of a
+//     group sets up the warp's next group (its descriptors were loaded one group earlier) and loads its first queries;
+//   * the first warp that finishes an item fetches the next work item (atomic counter, item record, bucket record) into
+//     shared memory, so that after the barrier the bulk copies start at once, and every warp sets up its first group and
+//     loads its first queries of the new item BEFORE it waits for the copies.
 template <bool WANT_IDX, int G>
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(kSThreads, 1)
 bk_search2_kernel(const BkSearchParams p, uint32_t* __restrict__ qsort, uint32_t* __restrict__ isort, const uint32_t* __restrict__ runs,
                   unsigned ntp, const uint4* __restrict__ items, unsigned* __restrict__ ctrl) {
-    constexpr int U = G == 8 ? 4 : 2;
+    constexpr int U = (G == 8 ? 4 : 2) * (1024 / kSThreads);
+    constexpr unsigned kSWarps = kSThreads / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t* s_sep = reinterpret_cast<uint32_t*>(smem_raw);                 // [r]
     uint16_t* s_jump = reinterpret_cast<uint16_t*>(s_sep + p.r);              // [r + 8]
     __shared__ __align__(8) uint64_t bar;
-    __shared__ unsigned s_item, s_next;
+    __shared__ uint4 s_it[2];      // the work item of this / the next iteration: {bucket, first tile, end tile, item number}
+    __shared__ uint2 s_meta[2];    // its bucket record {lo, shift}
+    __shared__ unsigned s_done;    // warps that have finished the current item
     uint64_t keep;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
-    // The bucket's leaf window is read ~3 times per sector (by this and the neighbouring work items): keep it in L2.  Measured
-    // (profiles/r2_search2_policy_ab.log): evict_last on the leaf 0.927 -> 0.910 ms; evict-first run loads/stores 0.959 vs 0.910.
+    // The bucket's leaf window is read ~3 times per sector (by this and the neighbouring work items): keep it in L2.  Measured:
+    // evict_last on the leaf 0.927 -> 0.910 ms; evict-first run loads/stores 0.959 vs 0.910; a bulk L2 prefetch of the window at
+    // the start of an item changes nothing (profiles/r2_search2_leaf_l2_prefetch_ab.log).
     auto ldleaf = [&](const uint32_t* a, uint32_t (&k)[8]) {
-        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.L2::128B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.L2::256B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
                      : "=r"(k[0]), "=r"(k[1]), "=r"(k[2]), "=r"(k[3]), "=r"(k[4]), "=r"(k[5]), "=r"(k[6]), "=r"(k[7])
                      : "l"(a), "l"(keep));
     };
     // (a query is read once, before its own lane overwrites it with the answer: plain weak accesses are enough)
     auto ldq = [&](const uint32_t* a) -> uint32_t { uint32_t v; asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(a)); return v; };
     auto stq = [&](uint32_t* a, uint32_t v) { *a = v; };
-    const unsigned tid = threadIdx.x, lane = tid & 31u;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const unsigned nitems = ctrl[1];
+    // (one thread) the next work item that holds tiles -> s_it[slot], s_meta[slot]; item number >= nitems: none left
+    auto fetch_item = [&](unsigned slot) {
+        uint4 it = make_uint4(0, 0, 0, 0xffffffffu);
+        while (true) {
+            const unsigned item = atomicAdd(&ctrl[0], 1u);
+            if (item >= nitems) { it.w = 0xffffffffu; break; }
+            it = __ldg(items + item);
+            it.w = item;
+            if (it.y < it.z) break;  // (an item slot no tile mapped to is skipped)
+        }
+        s_it[slot] = it;
+        if (it.w != 0xffffffffu) s_meta[slot] = __ldg(p.meta + it.x);
+    };
     if (tid == 0) {
         mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_done = 0;
+        fetch_item(0);
     }
-    unsigned phase = 0, cur_b = 0xffffffffu;
-    const unsigned nitems = ctrl[1];
+    unsigned phase = 0, cur_b = 0xffffffffu, slot = 0;
     while (true) {
-        __syncthreads();  // previous item finished: s_item, s_next, s_sep, s_jump may be overwritten
-        if (tid == 0) { s_item = atomicAdd(&ctrl[0], 1u); s_next = 0; }
-        __syncthreads();
-        const unsigned item = s_item;
-        if (item >= nitems) break;
-        const uint4 it = items[item];
+        __syncthreads();  // the previous item is finished (s_sep, s_jump may be overwritten) and s_it[slot] is published
+        const uint4 it = s_it[slot];
+        if (it.w == 0xffffffffu) break;
         const unsigned b = it.x, t0 = it.y, t1 = it.z;
-        if (t0 >= t1) continue;  // (block-uniform) an item slot no tile mapped to
-        if (b != cur_b) {  // stage the bucket: 1-D TMA bulk copies (SASS UBLKCP), completion on the mbarrier
-            if (tid == 0) {
+        const bool stage = b != cur_b;  // (block-uniform)
+        if (tid == 0) {
+            s_done = 0;  // (every warp passes the barrier above before it can finish this item)
+            if (stage) {  // 1-D TMA bulk copies (SASS UBLKCP), completion on the mbarrier
                 const unsigned sep_bytes = p.r * 4u, jump_bytes = (p.r + 8u) * 2u;
                 mbar_expect_tx(&bar, sep_bytes + jump_bytes);
                 for (unsigned off = 0; off < sep_bytes; off += 32768u)
@@ -1082,142 +592,170 @@ bk_search2_kernel(const BkSearchParams p, uint32_t* __restrict__ qsort, uint32_t
                 for (unsigned off = 0; off < jump_bytes; off += 32768u)
                     tma_bulk_g2s((char*)s_jump + off, (const char*)(p.jump + (size_t)b * (p.r + 8u)) + off, min(32768u, jump_bytes - off), &bar);
             }
-            mbar_wait(&bar, phase);
-            phase ^= 1u;
-            cur_b = b;
         }
-        const uint2 mt = p.meta[b];
+        const uint2 mt = s_meta[slot];
         const uint32_t lo = mt.x;
         const unsigned sh = mt.y;
         const unsigned hbase32 = b * p.r, m8m1 = (unsigned)(p.m8 - 1);  // block numbers fit 32 bits: at most 2^30 / 8 blocks
         const uint32_t* row = runs + (size_t)b * ntp;
         const unsigned ngroups = (t1 - t0 + 31u) >> 5;
-        while (true) {
-            unsigned g = 0;
-            if (lane == 0) g = atomicAdd(&s_next, 1u);
-            g = __shfl_sync(kFull, g, 0);
-            if (g >= ngroups) break;
+        // ---- this warp's groups: g_next = the next one to set up, d_next = this lane's descriptor of it (already loaded) ----
+        auto load_desc = [&](unsigned g) -> uint32_t {
             const unsigned t = t0 + g * 32u + lane;
-            const uint32_t d = t < t1 ? __ldg(row + t) : 0u;
-            const unsigned c = d >> kRunShift;
-            unsigned incl = c;
+            return g < ngroups && t < t1 ? __ldg(row + t) : 0u;
+        };
+        unsigned g_next = warp;
+        uint32_t d_next = load_desc(g_next);
+        // state of the current group
+        unsigned excl = 0, T = 0, rcur = 0;  // this lane's run starts at flattened query excl; T queries in the group's 32 runs
+        uint32_t dlt = 0;                    // address of flattened query k of this lane's run = dlt + k
+        // Sets up the warp's next non-empty group; false when it has none left.  (warp-uniform)
+        auto advance = [&]() -> bool {
+            while (g_next < ngroups) {
+                const uint32_t d = d_next;
+                const unsigned t = t0 + g_next * 32u + lane;
+                g_next += kSWarps;
+                d_next = load_desc(g_next);  // consumed one group later
+                const unsigned c = d >> kRunShift;
+                unsigned incl = c;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(kFull, incl, o); if (lane >= (unsigned)o) incl += y; }
-            const unsigned excl = incl - c;
-            const unsigned T = __shfl_sync(kFull, incl, 31);  // queries of these 32 runs
-            if (T == 0) continue;
-            const uint32_t dlt = t * (unsigned)kTile + (d & ((1u << kRunShift) - 1u)) - excl;  // address of flattened query k of run `lane` = dlt + k
-            // Address of flattened query k (k < T): the last run whose offset is <= k holds it (empty runs tie with their
-            // successor).  Slots are visited in order, so the run of a slot's first query is carried along (`rcur`, warp-uniform)
-            // and a slot of 32 queries usually crosses at most three run boundaries: the offsets of the next four runs come
-            // from four INDEPENDENT broadcast shuffles (uniform source lane) instead of a five-deep chain of per-lane ones;
-            // a slot that crosses more (short runs) takes the general five-step search.
-            unsigned rcur = 0;  // last run with excl <= (first query of the next slot to locate); runs before it are exhausted
-            auto locate = [&](unsigned kbase) -> uint32_t {  // kbase = the slot's first query (warp-uniform); this lane's is kbase + lane
-                const unsigned k = min(kbase + lane, T - 1u), klast = min(kbase + 31u, T - 1u);
-                const unsigned e1 = __shfl_sync(kFull, excl, min(rcur + 1u, 31u)), e2 = __shfl_sync(kFull, excl, min(rcur + 2u, 31u));
-                const unsigned e3 = __shfl_sync(kFull, excl, min(rcur + 3u, 31u)), e4 = __shfl_sync(kFull, excl, min(rcur + 4u, 31u));
-                unsigned r;
-                if (rcur + 4u > 31u || e4 > klast) {  // (warp-uniform) at most three boundaries inside the slot
-                    const bool h1 = rcur + 1u <= 31u, h2 = rcur + 2u <= 31u, h3 = rcur + 3u <= 31u;
-                    r = rcur + ((h1 && e1 <= k) ? 1u : 0u) + ((h2 && e2 <= k) ? 1u : 0u) + ((h3 && e3 <= k) ? 1u : 0u);
-                    rcur += ((h1 && e1 <= klast) ? 1u : 0u) + ((h2 && e2 <= klast) ? 1u : 0u) + ((h3 && e3 <= klast) ? 1u : 0u);
-                } else {
-                    r = 0;
+                for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(kFull, incl, o); if (lane >= (unsigned)o) incl += y; }
+                T = __shfl_sync(kFull, incl, 31);
+                if (T == 0) continue;
+                excl = incl - c;
+                dlt = t * (unsigned)kTile + (d & ((1u << kRunShift) - 1u)) - excl;
+                rcur = 0;
+                return true;
+            }
+            return false;
+        };
+        // Address of flattened query k (k < T): the last run whose offset is <= k holds it (empty runs tie with their
+        // successor).  Slots are visited in order, so the run of a slot's first query is carried along (`rcur`, warp-uniform)
+        // and a slot of 32 queries usually crosses at most three run boundaries: the offsets of the next four runs come
+        // from four INDEPENDENT broadcast shuffles (uniform source lane) instead of a five-deep chain of per-lane ones;
+        // a slot that crosses more (short runs) takes the general five-step search.  (One REDUX.OR over "my run starts at
+        // lane j of this slot" + popc + a shared-memory table of the non-empty runs was measured slower: 0.943 vs 0.883 ms.)
+        auto locate = [&](unsigned kbase) -> uint32_t {  // kbase = the slot's first query (warp-uniform); this lane's is kbase + lane
+            const unsigned k = min(kbase + lane, T - 1u), klast = min(kbase + 31u, T - 1u);
+            const unsigned e1 = __shfl_sync(kFull, excl, min(rcur + 1u, 31u)), e2 = __shfl_sync(kFull, excl, min(rcur + 2u, 31u));
+            const unsigned e3 = __shfl_sync(kFull, excl, min(rcur + 3u, 31u)), e4 = __shfl_sync(kFull, excl, min(rcur + 4u, 31u));
+            unsigned r;
+            if (rcur + 4u > 31u || e4 > klast) {  // (warp-uniform) at most three boundaries inside the slot
+                const bool h1 = rcur + 1u <= 31u, h2 = rcur + 2u <= 31u, h3 = rcur + 3u <= 31u;
+                r = rcur + ((h1 && e1 <= k) ? 1u : 0u) + ((h2 && e2 <= k) ? 1u : 0u) + ((h3 && e3 <= k) ? 1u : 0u);
+                rcur += ((h1 && e1 <= klast) ? 1u : 0u) + ((h2 && e2 <= klast) ? 1u : 0u) + ((h3 && e3 <= klast) ? 1u : 0u);
+            } else {
+                r = 0;
 #pragma unroll
-                    for (unsigned s = 16; s; s >>= 1) {
-                        const unsigned e = __shfl_sync(kFull, excl, r + s);
-                        if (e <= k) r += s;
-                    }
-                    rcur = __shfl_sync(kFull, r, 31);
+                for (unsigned s = 16; s; s >>= 1) {
+                    const unsigned e = __shfl_sync(kFull, excl, r + s);
+                    if (e <= k) r += s;
                 }
-                return __shfl_sync(kFull, dlt, r) + k;
-            };
-            uint32_t an[U], qn[U];  // next round: addresses and queries (their loads stay in flight while this round is answered)
+                rcur = __shfl_sync(kFull, r, 31);
+            }
+            return __shfl_sync(kFull, dlt, r) + k;
+        };
+        uint32_t an[U], qn[U];  // next round: addresses and queries (their loads stay in flight while this round is answered)
+        auto prefetch = [&](unsigned k0) {  // the round that starts at flattened query k0 of the current group
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                const unsigned kb = u * 32u;
+                const unsigned kb = k0 + u * 32u;
                 an[u] = kb < T ? locate(kb) : 0u;
                 qn[u] = kb + lane < T ? ldq(qsort + an[u]) : lo;
             }
-            for (unsigned k0 = 0; k0 < T; k0 += 32u * U) {
-                uint32_t q[U], ad[U];
-                unsigned a[U];
+        };
+        bool more = advance();
+        if (more) prefetch(0);  // (before the wait below: the first queries of the item travel while the tables are staged)
+        if (stage) {
+            mbar_wait(&bar, phase);
+            phase ^= 1u;
+            cur_b = b;
+        }
+        unsigned k0 = 0;
+        while (more) {
+            uint32_t q[U], ad[U];
+            unsigned a[U], vm = 0;  // vm: bit u = slot u of this round holds a query for this lane
 #pragma unroll
-                for (int u = 0; u < U; u++) {
-                    q[u] = qn[u];
-                    ad[u] = an[u];
-                    const unsigned kb = k0 + (U + u) * 32u;
-                    an[u] = kb < T ? locate(kb) : 0u;
-                    qn[u] = kb + lane < T ? ldq(qsort + an[u]) : lo;
-                }
-                // rank among the bucket's separators (predicated probes, see bk_search_kernel)
-                unsigned l[U];
-                uint32_t s0[U];
+            for (int u = 0; u < U; u++) {
+                q[u] = qn[u];
+                ad[u] = an[u];
+                vm |= (k0 + u * 32u + lane < T ? 1u : 0u) << u;
+            }
+            // next round: of this group, or the first one of the warp's next group
+            k0 += 32u * U;
+            if (k0 >= T) { more = advance(); k0 = 0; }
+            if (more) prefetch(k0);
+            // rank among the bucket's separators: the jump cell gives the first candidate; later separators are probed only
+            // while they are below the query (37 % / 10 % / 2 % of the lanes for uniform keys).  No upper end is needed:
+            // every separator of a later cell is above q and the bucket's last separator is >= q.
+            unsigned l[U];
+            uint32_t s0[U];
 #pragma unroll
-                for (int u = 0; u < U; u++) l[u] = s_jump[(q[u] - lo) >> sh];
+            for (int u = 0; u < U; u++) l[u] = s_jump[(q[u] - lo) >> sh];
 #pragma unroll
-                for (int u = 0; u < U; u++) s0[u] = s_sep[min(l[u], p.r - 1u)];
+            for (int u = 0; u < U; u++) s0[u] = s_sep[min(l[u], p.r - 1u)];
 #pragma unroll
-                for (int u = 0; u < U; u++) {
-                    unsigned pos = l[u];
-                    if (s0[u] < q[u]) {
+            for (int u = 0; u < U; u++) {
+                unsigned pos = l[u];
+                if (s0[u] < q[u]) {
+                    pos++;
+                    if (s_sep[min(pos, p.r - 1u)] < q[u]) {
                         pos++;
                         if (s_sep[min(pos, p.r - 1u)] < q[u]) {
                             pos++;
-                            if (s_sep[min(pos, p.r - 1u)] < q[u]) {
-                                pos++;
-                                unsigned hh = s_jump[((q[u] - lo) >> sh) + 1u];
-                                if (hh > pos + 8u) {
-                                    while (pos < hh) {
-                                        const unsigned m = (pos + hh) >> 1;
-                                        if (s_sep[m] < q[u]) pos = m + 1; else hh = m;
-                                    }
-                                } else {
-                                    while (pos < hh && s_sep[pos] < q[u]) pos++;
+                            unsigned hh = s_jump[((q[u] - lo) >> sh) + 1u];
+                            if (hh > pos + 8u) {
+                                while (pos < hh) {
+                                    const unsigned m = (pos + hh) >> 1;
+                                    if (s_sep[m] < q[u]) pos = m + 1; else hh = m;
                                 }
+                            } else {
+                                while (pos < hh && s_sep[pos] < q[u]) pos++;
                             }
                         }
                     }
-                    a[u] = pos;
                 }
-                // the block of G keys that holds the answer: one 32-byte sector (two for G = 16).  Block numbers fit 32 bits
-                // (at most 2^30 / 8 blocks), so the address is one 32 x 32 -> 64 multiply-add.
-                uint32_t ks[U][G];
-                unsigned hn[U];
+                a[u] = pos;
+            }
+            // the block of G keys that holds the answer: one 32-byte sector (two for G = 16).  Block numbers fit 32 bits
+            // (at most 2^30 / 8 blocks), so the address is one 32 x 32 -> 64 multiply-add.
+            uint32_t ks[U][G];
+            unsigned hn[U];
 #pragma unroll
-                for (int u = 0; u < U; u++) {
-                    hn[u] = hbase32 + a[u];
-                    const unsigned hc = min(hn[u], m8m1);
-                    const uint32_t* src = p.leaf + (size_t)hc * (unsigned)G;
-                    ldleaf(src, reinterpret_cast<uint32_t(&)[8]>(ks[u][0]));
-                    if constexpr (G == 16) ldleaf(src + 8, reinterpret_cast<uint32_t(&)[8]>(ks[u][8]));
-                }
+            for (int u = 0; u < U; u++) {
+                hn[u] = hbase32 + a[u];
+                const unsigned hc = min(hn[u], m8m1);
+                const uint32_t* src = p.leaf + (size_t)hc * (unsigned)G;
+                ldleaf(src, reinterpret_cast<uint32_t(&)[8]>(ks[u][0]));
+                if constexpr (G == 16) ldleaf(src + 8, reinterpret_cast<uint32_t(&)[8]>(ks[u][8]));
+            }
 #pragma unroll
-                for (int u = 0; u < U; u++) {
-                    // The keys are sorted and at most MAX = 2^31 - 1, the query is canonical (<= MAX): the first key >= q is the
-                    // one with the smallest difference key - q among the non-negative ones, and a negative difference wraps to
-                    // >= 2^31 + 1.  One subtract and one unsigned min per key (it was a compare, a conditional increment and a
-                    // compare + select per key: 45 -> 17 instructions per query).
-                    uint32_t md = ks[u][0] - q[u];
+            for (int u = 0; u < U; u++) {
+                // The keys are sorted and at most MAX = 2^31 - 1, the query is canonical (<= MAX): the first key >= q is the
+                // one with the smallest difference key - q among the non-negative ones, and a negative difference wraps to
+                // >= 2^31 + 1.  One subtract and one unsigned min per key (it was a compare, a conditional increment and a
+                // compare + select per key: 45 -> 17 instructions per query).
+                uint32_t md = ks[u][0] - q[u];
 #pragma unroll
-                    for (int e = 1; e < G; e++) md = min(md, ks[u][e] - q[u]);
-                    const bool none = md > 0x7fffffffu || hn[u] > m8m1;  // above every key of the block (only past the last key) / past the end
-                    const uint32_t val = none ? kMax : q[u] + md;
-                    if (k0 + u * 32u + lane < T) {
-                        stq(qsort + ad[u], val);
-                        if constexpr (WANT_IDX) {
-                            unsigned cc = 0;
+                for (int e = 1; e < G; e++) md = min(md, ks[u][e] - q[u]);
+                const bool none = md > 0x7fffffffu || hn[u] > m8m1;  // above every key of the block (only past the last key) / past the end
+                const uint32_t val = none ? kMax : q[u] + md;
+                if (vm >> u & 1u) {
+                    stq(qsort + ad[u], val);
+                    if constexpr (WANT_IDX) {
+                        unsigned cc = 0;
 #pragma unroll
-                            for (int e = 0; e < G; e++) cc += ks[u][e] < q[u] ? 1u : 0u;
-                            unsigned long long pos = (unsigned long long)hn[u] * (unsigned)G + cc;
-                            if (none || pos > p.n) pos = p.n;
-                            stq(isort + ad[u], (uint32_t)pos);
-                        }
+                        for (int e = 0; e < G; e++) cc += ks[u][e] < q[u] ? 1u : 0u;
+                        unsigned long long pos = (unsigned long long)hn[u] * (unsigned)G + cc;
+                        if (none || pos > p.n) pos = p.n;
+                        stq(isort + ad[u], (uint32_t)pos);
                     }
                 }
             }
         }
+        // the first warp to get here has time to spare: it fetches the next work item for everybody
+        if (lane == 0 && atomicAdd(&s_done, 1u) == 0u) fetch_item(slot ^ 1u);
+        slot ^= 1u;
     }
 }
 
@@ -1382,26 +920,6 @@ __global__ void bk_flat_index_kernel(const uint32_t* __restrict__ qs, size_t nq,
 // ------------------------------------------------------------------------------------------------
 // scratch buffers: one set per (host thread, device), grown on demand, released when the thread exits
 // ------------------------------------------------------------------------------------------------
-struct Scratch {
-    int device = -1;
-    size_t cap_q = 0, cap_idx = 0, cap_mat = 0, cap_items = 0;
-    uint32_t *qb = nullptr, *rb = nullptr, *ib = nullptr, *counts = nullptr, *offs = nullptr, *gsum = nullptr, *bstart = nullptr, *tot = nullptr;
-    uint16_t* lpos = nullptr;
-    uint2* items = nullptr;
-    unsigned* ctrl = nullptr;
-    cudaEvent_t done = nullptr;  // last pipeline run (another stream of this thread must wait for it)
-    ~Scratch() {
-        if (device < 0) return;
-        int prev = -1;
-        if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) { (void)cudaGetLastError(); return; }
-        cudaFree(qb); cudaFree(rb); cudaFree(ib); cudaFree(counts); cudaFree(offs); cudaFree(gsum); cudaFree(bstart); cudaFree(tot);
-        cudaFree(lpos); cudaFree(items); cudaFree(ctrl);
-        if (done) cudaEventDestroy(done);
-        (void)cudaGetLastError();
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
-thread_local Scratch g_scratch[64];
 thread_local double g_stage_ms[5] = {-1, -1, -1, -1, -1};
 
 template <typename T>
@@ -1409,81 +927,6 @@ bool regrow(T*& p, size_t count) {
     cudaFree(p);
     p = nullptr;
     return SST_CUDA_OK(cudaMalloc(&p, count * sizeof(T)));
-}
-
-bool scratch_ensure(Scratch& s, int device, size_t nq, bool want_idx, unsigned nbp) {
-    s.device = device;
-    if (!s.done && !SST_CUDA_OK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming))) return false;
-    if (!s.ctrl && (!regrow(s.ctrl, 4) || !regrow(s.bstart, 2048 + 8) || !regrow(s.tot, 2048))) return false;
-    if (nq > s.cap_q) {
-        s.cap_q = 0;
-        if (!regrow(s.qb, nq) || !regrow(s.rb, nq) || !regrow(s.lpos, nq)) return false;
-        s.cap_q = nq;
-    }
-    if (want_idx && nq > s.cap_idx) {
-        s.cap_idx = 0;
-        if (!regrow(s.ib, nq)) return false;
-        s.cap_idx = nq;
-    }
-    const size_t ntiles = div_ceil(nq, (size_t)kTile);
-    const size_t mat = ntiles * nbp;
-    if (mat > s.cap_mat) {
-        s.cap_mat = 0;
-        if (!regrow(s.counts, mat) || !regrow(s.offs, mat) || !regrow(s.gsum, mat / kTilesPerGroup + 4096)) return false;
-        s.cap_mat = mat;
-    }
-    const size_t items = 2048 + nq / kMinChunk + 2;
-    if (items > s.cap_items) {
-        s.cap_items = 0;
-        if (!regrow(s.items, items)) return false;
-        s.cap_items = items;
-    }
-    return true;
-}
-
-template <int BITS>
-void launch_rank(const BkView& v, int sms, size_t smem, cudaStream_t st, const uint32_t* qs, size_t nq, unsigned ntiles, uint32_t* counts,
-                 uint16_t* lpos, uint32_t* tot) {
-    const unsigned grid = (unsigned)std::min<size_t>(ntiles, (size_t)sms * 2);
-    const int hyb = BITS > 0 ? (int)opt(OPT_BK_HYBRID) : 0;
-#define SST_BK_LAUNCH_RANK(H)                                                                       \
-    {                                                                                               \
-        auto kern = bk_rank_kernel<BITS, H>;                                                        \
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
-        kern<<<grid, kThreads, smem, st>>>(v, qs, nq, ntiles, counts, lpos, tot);                   \
-    }
-    // claim : ballot ratio measured at 10 bits (rank stage, ms per 10^8 queries): ballots only 0.494, 1:2 0.472, 1:1 0.452,
-    // 2:1 0.446, 3:1 0.442 (before the packed bucket table)
-    // With the packed bucket table (one shared load less per query) the shared-memory pipe has room for more claims: 1:1 0.452,
-    // 3:1 0.431, 7:1 0.419, 31:1 0.412 ms -> claims on every step but the first (SST_BK_HYBRID=4: 3:1, =0: ballots only)
-    if (hyb == 4 && BITS == 10) SST_BK_LAUNCH_RANK(4)
-    else if (hyb != 0) SST_BK_LAUNCH_RANK(32)
-    else SST_BK_LAUNCH_RANK(0)
-#undef SST_BK_LAUNCH_RANK
-}
-
-template <bool GATHER, typename OutT>
-void launch_move(int sms, size_t smem, cudaStream_t st, const Scratch& s, unsigned nbp, unsigned ntiles, size_t nq, const uint32_t* src, OutT* dst) {
-    const int aligned = (((uintptr_t)src | (uintptr_t)dst) & 15u) == 0 && opt(OPT_BK_VEC);
-    // Two 104 KB tiles per SM leave ~20 KB of L1, too little for the loads in flight (ncu: LG-throttle stalls): with 512
-    // threads the scatter is faster on ONE CTA per SM (0.32 vs 0.36 ms per 10^8 queries).  Default where the bucket count
-    // allows: one CTA of 1024 threads per SM (gather 0.32 vs 0.37 ms, scatter 0.31); SST_BK_MOVE_THREADS=512 for the old shape.
-    const int threads = (nbp % 1024 == 0 && opt(OPT_BK_MOVE_THREADS) == 1024) ? 1024 : kThreads;
-    const unsigned bpt = nbp / threads;
-    if (threads == 1024 && !GATHER && opt(OPT_BK_PREFETCH)) {
-        auto kern = bk_move_kernel<GATHER, OutT, 1024, true>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<(unsigned)std::min<size_t>(ntiles, (size_t)sms), 1024, smem, st>>>(s.counts, s.offs, s.lpos, nbp, bpt, ntiles, nq, aligned, src, dst);
-    } else if (threads == 1024) {
-        auto kern = bk_move_kernel<GATHER, OutT, 1024>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<(unsigned)std::min<size_t>(ntiles, (size_t)sms), 1024, smem, st>>>(s.counts, s.offs, s.lpos, nbp, bpt, ntiles, nq, aligned, src, dst);
-    } else {
-        auto kern = bk_move_kernel<GATHER, OutT, kThreads>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<(unsigned)std::min<size_t>(ntiles, (size_t)sms * (opt(OPT_BK_MOVE_CTAS) > 0 ? (size_t)opt(OPT_BK_MOVE_CTAS) : (GATHER ? 2 : 1))), kThreads, smem, st>>>(
-            s.counts, s.offs, s.lpos, nbp, bpt, ntiles, nq, aligned, src, dst);
-    }
 }
 
 }  // namespace
@@ -1659,8 +1102,6 @@ void release_bucketed_scratch() {
     for (auto& s : g_scratch2) s.release();
 }
 
-static int launch_bucketed_v1(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx, cudaStream_t st);
-
 static int launch_bucketed_v2(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx, cudaStream_t st) {
     const BkAux& a = idx->bk;
     const int dev = idx->device;
@@ -1715,7 +1156,7 @@ static int launch_bucketed_v2(const sst_index* idx, const uint32_t* d_qs, size_t
             void (*kern)(const BkSearchParams, uint32_t*, uint32_t*, const uint32_t*, unsigned, const uint4*, unsigned*) =
                 a.g == 16 ? (d_idx ? bk_search2_kernel<true, 16> : bk_search2_kernel<false, 16>) : (d_idx ? bk_search2_kernel<true, 8> : bk_search2_kernel<false, 8>);
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_search);
-            kern<<<sms, 1024, smem_search, st>>>(sp, s.qsort, s.isort, s.runs, h.ntp, s.items, s.ctrl);
+            kern<<<sms, kSThreads, smem_search, st>>>(sp, s.qsort, s.isort, s.runs, h.ntp, s.items, s.ctrl);
         }
         mark();
         launch_unperm<uint32_t>(sms, st, s.qsort, s.lpos, cnt, ntiles, d_vals + off);
@@ -1739,97 +1180,7 @@ static int launch_bucketed_v2(const sst_index* idx, const uint32_t* d_qs, size_t
 
 int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx, cudaStream_t st) {
     if (!idx->bk.nb) { set_error(SST_ERR_UNSUPPORTED, "the reordered-batch pipeline serves plain and Map-partitioned B=16 trees of 2^22..2^30 keys"); return SST_ERR_UNSUPPORTED; }
-    return opt(OPT_BK_V1) ? launch_bucketed_v1(idx, d_qs, nq, d_vals, d_idx, st) : launch_bucketed_v2(idx, d_qs, nq, d_vals, d_idx, st);
-}
-
-static int launch_bucketed_v1(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx, cudaStream_t st) {
-    const BkAux& a = idx->bk;
-    if (!a.nb) { set_error(SST_ERR_UNSUPPORTED, "the reordered-batch pipeline serves plain and Map-partitioned B=16 trees of 2^22..2^30 keys"); return SST_ERR_UNSUPPORTED; }
-    const int dev = idx->device;
-    if (dev < 0 || dev >= 64) { set_error(SST_ERR_ARG, "device index out of range"); return SST_ERR_ARG; }
-    Scratch& s = g_scratch[dev];
-    const size_t sub = std::min(nq, kSubBatch);
-    if (!scratch_ensure(s, dev, sub, d_idx != nullptr, a.nbp)) {  // out of device memory for the scratch buffers
-        set_error(SST_ERR_CAPACITY, "not enough device memory for the reordered-batch scratch buffers (10-14 bytes per query)");
-        return SST_ERR_CAPACITY;
-    }
-    if (!SST_CUDA_OK(cudaStreamWaitEvent(st, s.done, 0))) return SST_ERR_CUDA;  // scratch reuse across this thread's streams
-    const int sms = sm_count(dev);
-    const unsigned bpt = a.nbp / kThreads;
-    const bool flat_parts = idx->variant == SST_SIMPLE || idx->variant == SST_L1 || idx->variant == SST_OVERLAPPING;
-    const bool map_tree = idx->variant == SST_MAP || flat_parts;  // partitioned: a query above MAX has no part -> (MAX, n)
-    BkView v{a.d_bt, a.d_split, a.nb, a.nbp, bpt, map_tree ? s.ctrl + 3 : nullptr};
-    if (map_tree && !SST_CUDA_OK(cudaMemsetAsync(s.ctrl + 3, 0, 4, st))) return SST_ERR_CUDA;
-    const size_t smem_rank = (size_t)kWarps * a.nbp * 2 + (size_t)kBtCells * 4;
-    const size_t smem_move = (size_t)kTile * 4 + (size_t)a.nbp * 4 + (size_t)kTile * 2;
-    const size_t smem_search = (size_t)a.r * 4 + ((size_t)a.r + 8) * 2;
-    // two CTAs of 512 threads per SM while two buckets fit shared memory, else one CTA of 1024 threads
-    const int search_threads = smem_search * 2 + 4096 <= max_smem_optin(dev) ? kThreads : 1024, search_ctas = search_threads == kThreads ? 2 : 1;
-    // queries per search work item: every item stages its bucket (r * 6 bytes) again, so larger is cheaper, but a bucket
-    // should still split into a few items for load balance
-    const unsigned chunk = (unsigned)std::max<long long>(opt(OPT_BK_CHUNK), (long long)kMinChunk);
-    BkSearchParams sp{a.d_sep, a.d_jump, a.d_meta, idx->d_tree + idx->offsets[idx->levels - 1] * 16, a.r, a.m8, a.n_flat};
-    // SST_BK_TIMING=1 (debug): per-stage CUDA-event times on stderr; synchronises the stream
-    const bool timing = opt(OPT_BK_TIMING) != 0;
-    cudaEvent_t ev[8] = {};
-    int nev = 0;
-    auto mark = [&]() {
-        if (!timing || nev >= 8) return;
-        cudaEventCreate(&ev[nev]);
-        cudaEventRecord(ev[nev++], st);
-    };
-    for (size_t off = 0; off < nq; off += sub) {
-        const size_t cnt = std::min(sub, nq - off);
-        const unsigned ntiles = (unsigned)div_ceil(cnt, (size_t)kTile), ngroups = (unsigned)div_ceil((size_t)ntiles, (size_t)kTilesPerGroup);
-        const int grid = (int)std::min<size_t>(ntiles, (size_t)sms * 2);
-        const uint32_t* qs = d_qs + off;
-        nev = 0;
-        mark();
-        switch (a.bits) {
-#define SST_BK_RANK(B) case B: launch_rank<B>(v, sms, smem_rank, st, qs, cnt, ntiles, s.counts, s.lpos, s.tot); break;
-            SST_BK_RANK(0) SST_BK_RANK(1) SST_BK_RANK(2) SST_BK_RANK(3) SST_BK_RANK(4) SST_BK_RANK(5)
-            SST_BK_RANK(6) SST_BK_RANK(7) SST_BK_RANK(8) SST_BK_RANK(9) SST_BK_RANK(10) SST_BK_RANK(11)
-#undef SST_BK_RANK
-            default: set_error(SST_ERR_UNSUPPORTED, "too many buckets"); return SST_ERR_UNSUPPORTED;
-        }
-        mark();
-        const dim3 mgrid(a.nbp / 256, ngroups);
-        bk_colsum_kernel<<<mgrid, 256, 0, st>>>(s.counts, ntiles, a.nbp, s.gsum, s.tot);
-        bk_plan_kernel<<<1, 1024, 0, st>>>(s.tot, a.nbp, chunk, s.bstart, s.items, s.ctrl);
-        bk_offsets_kernel<<<mgrid, 256, 0, st>>>(s.counts, s.gsum, s.bstart, ntiles, a.nbp, s.offs);
-        mark();
-        launch_move<false, uint32_t>(sms, smem_move, st, s, a.nbp, ntiles, cnt, qs, s.qb);
-        mark();
-        {
-            void (*kern)(const BkSearchParams, const uint32_t*, const uint32_t*, const uint2*, unsigned*, uint32_t*, uint32_t*) =
-                // SST_BK_PROBE=0: the earlier form (three unconditional probes bounded by the cell's upper end), kept for A/B runs.
-                // Rejected on measurement: software-pipelining the rounds (leaf loads of round k in flight during the probes of
-                // round k + 1): search 0.675 -> 0.761 ms -- the stage is bound by L1/XBAR throughput, not by latency.
-                opt(OPT_BK_PROBE) == 1
-                    ? (a.g == 16 ? (d_idx ? bk_search_kernel<true, 16, 1> : bk_search_kernel<false, 16, 1>) : (d_idx ? bk_search_kernel<true, 8, 1> : bk_search_kernel<false, 8, 1>))
-                    : (a.g == 16 ? (d_idx ? bk_search_kernel<true, 16, 0> : bk_search_kernel<false, 16, 0>) : (d_idx ? bk_search_kernel<true, 8, 0> : bk_search_kernel<false, 8, 0>));
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_search);
-            kern<<<sms * search_ctas, search_threads, smem_search, st>>>(sp, s.qb, s.bstart, s.items, s.ctrl, s.rb, s.ib);
-        }
-        mark();
-        launch_move<true, uint32_t>(sms, smem_move, st, s, a.nbp, ntiles, cnt, s.rb, d_vals + off);
-        if (d_idx) launch_move<true, unsigned long long>(sms, smem_move, st, s, a.nbp, ntiles, cnt, s.ib, d_idx + off);
-        if (flat_parts && d_idx)
-            bk_flat_index_kernel<<<sms * 8, 256, 0, st>>>(qs, cnt, d_idx + off, (unsigned)idx->shift, (unsigned long long)idx->parts, idx->d_part_start,
-                                                        idx->d_part_pos, (unsigned long long)idx->n);
-        if (map_tree) bk_above_kernel<<<sms * 4, 256, 0, st>>>(s.ctrl + 3, qs, cnt, d_vals + off, d_idx ? d_idx + off : nullptr, (unsigned long long)idx->n);
-        mark();
-        if (timing && nev == 6 && cudaEventSynchronize(ev[5]) == cudaSuccess) {
-            float t[5];
-            for (int i = 0; i < 5; i++) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
-            for (int i = 0; i < 5; i++) g_stage_ms[i] = t[i];
-            if (opt(OPT_BK_TIMING) > 1) fprintf(stderr, "[sst] bucketed nq=%zu nb=%u: rank %.3f plan %.3f scatter %.3f search %.3f gather %.3f ms\n", cnt, a.nb, t[0], t[1],
-                    t[2], t[3], t[4]);
-        }
-        for (int i = 0; i < nev; i++) cudaEventDestroy(ev[i]);
-    }
-    if (!SST_CUDA_OK(cudaGetLastError()) || !SST_CUDA_OK(cudaEventRecord(s.done, st))) return SST_ERR_CUDA;
-    return SST_OK;
+    return launch_bucketed_v2(idx, d_qs, nq, d_vals, d_idx, st);
 }
 
 }  // namespace sst

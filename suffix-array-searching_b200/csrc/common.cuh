@@ -75,7 +75,6 @@ unsigned cur_sms();                   // sm_count of the calling thread's curren
     X(BK_R, -1, -1, 32768)               /* separators per bucket (power of two >= 64); -1 = by size */                       \
     X(BK_CHUNK, 32768, 16384, 1 << 24)   /* queries per search work item */                                                   \
     X(BK_TIMING, 0, 0, 2)                /* per-stage CUDA-event times (synchronises; bench/tools only) */                    \
-    X(BK_V1, 0, 0, 1)                    /* 1 = the round-1 seven-launch pipeline (A/B runs) */                               \
     X(BK_CHUNK2_LOG2, 15, 14, 24)        /* log2 of the queries per search work item of the V2 pipeline */                    \
     X(BK_HYBRID, 1, 0, 4)                                                                                                    \
     X(BK_VEC, 1, 0, 1)                                                                                                       \

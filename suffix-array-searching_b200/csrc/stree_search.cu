@@ -781,11 +781,11 @@ int resolve_scheme(const sst_index* idx, int scheme, size_t nq) {
 
 // Kernel launches of one sst_query_device call.  The reordered-batch pipeline runs 4 kernels per 2^27-query sub-batch
 // (partition, work items, search, un-permute) and one more un-permute for the index output; the round-1
-// pipeline (BK_V1) ran 7 (rank, column sums, plan, offsets, scatter, search, gather).
+// pipeline ran 7 (rank, column sums, plan, offsets, scatter, search, gather).
 int query_launch_count(const sst_index* idx, int scheme, size_t nq, bool want_idx) {
     if (nq == 0) return 0;
     if (resolve_scheme(idx, scheme, nq) != SST_SCHEME_BUCKETED) return 1;
-    const int base = opt(OPT_BK_V1) ? 7 : 4;
+    const int base = 4;
     return (int)(div_ceil(nq, (size_t)1 << 27) * (base + (want_idx ? 1 : 0) + (idx->variant == SST_PLAIN ? 0 : 1) +
                                                    (want_idx && idx->variant != SST_PLAIN && idx->variant != SST_MAP ? 1 : 0)));  // partitioned: + the q > MAX fix-up (+ flat -> sorted index)
 }

@@ -22,4 +22,4 @@ for _ in range(5):
     ms = (C.c_double * 5)(); L.sst_last_stage_ms(ms, 5)
     acc = [a + b for a, b in zip(acc, ms)]
 print(json.dumps({"tag": os.environ.get("TAG", ""), "ms": round(ms_all, 3), "gqps": round(nq / ms_all / 1e6, 2),
-                  "stages_ms": dict(zip((["rank", "plan", "scatter", "search", "gather"] if sst.get_option("BK_V1") else ["partition", "plan", "-", "search", "unpermute"]), [round(a / 5, 3) for a in acc]))}))
+                  "stages_ms": dict(zip(["partition", "plan", "-", "search", "unpermute"], [round(a / 5, 3) for a in acc]))}))
