@@ -346,10 +346,27 @@ bk_part_kernel(const PartParams p) {
             for (int r = 0; r < kPItems; r++) acc |= q[r];
             if (__any_sync(kFull, acc > kMax) && lane == 0) atomicOr(v.above, 1u);
         }
+        {   // bucket of every query: ONE shared load and a compare (bk_pack_cell); a cell that two or more splitters share (skewed
+            // keys) is flagged and settled afterwards through the global tables, outside the straight-line path (the branchy
+            // form cost 30 instructions per query, a quarter of the kernel)
+            uint32_t flags = 0;
 #pragma unroll
-        for (int r = 0; r < kPItems; r++) {
-            q[r] = canonical(q[r]);
-            pk[r] = (full || i0 + r * 32 < tile_n) ? bk_bucket_packed(s_pk, v.bt, v.split, q[r]) : 0xffffffffu;
+            for (int r = 0; r < kPItems; r++) {
+                q[r] = canonical(q[r]);
+                const uint32_t e = s_pk[q[r] >> kBtShift];
+                flags |= e;
+                pk[r] = (e & 0x7ffu) + ((q[r] & ((1u << kBtShift) - 1u)) > (e >> 12) ? 1u : 0u);
+            }
+            if (flags & 0x800u) {  // (unrolled: a rolled loop would index q[] and pk[] dynamically and push both into local memory)
+#pragma unroll
+                for (int r = 0; r < kPItems; r++)
+                    if (s_pk[q[r] >> kBtShift] & 0x800u) pk[r] = bk_bucket(v.bt, v.split, q[r]);
+            }
+            if (!full) {
+#pragma unroll
+                for (int r = 0; r < kPItems; r++)
+                    if (i0 + r * 32 >= tile_n) pk[r] = 0xffffffffu;
+            }
         }
         __syncthreads();  // thread 0 has seen the store's reads complete
         {   // zero the per-warp counters
