@@ -200,16 +200,37 @@ __device__ __forceinline__ void rank_items(uint16_t* cntw, uint32_t (&pk)[ITEMS]
                     __syncwarp();
                     const bool lost = valid && (unsigned)(cntw[b] >> 11) != lane;
                     unsigned rank = w & 0x7ffu;
-                    unsigned peers = __ballot_sync(kFull, lost);
-                    if (peers) {  // (warp-uniform, 2 steps in 5) lanes that share a bucket with a winner: settle them by ballots, in bounded time
-                        // (letting the one or two losers claim again instead was measured slower: rank 0.410 -> 0.431 ms, spills)
-                        ballot_bits<0, BITS>(peers, b);
-                        const unsigned before = peers & lt_mask;
-                        const unsigned old = lost ? (cntw[b] & 0x7ffu) : 0u;  // includes the winner's +1
+                    unsigned lostm = __ballot_sync(kFull, lost);
+                    if (lostm) {  // (warp-uniform, 2 steps in 5) lanes that share a bucket with a winner
+                        // Usually ONE bucket is contested (a pair of lanes; or every lane when the queries are all alike): the
+                        // losers of the lowest contested lane's bucket find each other with one shuffle and one ballot and are
+                        // settled together; twice over, then whatever is left takes the ballots over the bucket bits, so the
+                        // cost stays bounded for any input (the ballots alone cost 45 instructions whenever a step had a loser;
+                        // letting the losers claim again instead was measured slower: rank 0.410 -> 0.431 ms).
+                        bool mine = lost;
+#pragma unroll
+                        for (int it = 0; it < 2; it++) {
+                            if (lostm) {
+                                const unsigned bl = __shfl_sync(kFull, b, __ffs(lostm) - 1);
+                                const bool hit = mine && b == bl;
+                                const unsigned same = __ballot_sync(kFull, hit);
+                                const unsigned old = hit ? (cntw[b] & 0x7ffu) : 0u;  // includes the winner's +1
+                                __syncwarp();
+                                if (hit && (same & lt_mask) == 0u) cntw[b] = (uint16_t)(old + __popc(same));
+                                if (hit) { rank = old + __popc(same & lt_mask); mine = false; }
+                                lostm &= ~same;
+                            }
+                        }
+                        if (lostm) {
+                            unsigned peers = lostm;
+                            ballot_bits<0, BITS>(peers, b);
+                            const unsigned before = peers & lt_mask;
+                            const unsigned old = mine ? (cntw[b] & 0x7ffu) : 0u;
+                            __syncwarp();
+                            if (mine && before == 0u) cntw[b] = (uint16_t)(old + __popc(peers));
+                            if (mine) rank = old + __popc(before);
+                        }
                         __syncwarp();
-                        if (lost && before == 0u) cntw[b] = (uint16_t)(old + __popc(peers));
-                        __syncwarp();
-                        if (lost) rank = old + __popc(before);
                     }
                     if (valid) pk[r] = b | (rank << 16);
                 } else {
