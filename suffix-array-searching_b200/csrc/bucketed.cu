@@ -27,6 +27,7 @@
 // the rank table of stree_search.cu.  Served: plain B = 16 trees (any new_params flags) and the Map, Simple, L1 and
 // Overlapping partitioned layouts (their leaf level is one sorted flat array) of 2^22 .. 2^30 leaf slots.
 #include <algorithm>
+#include <type_traits>
 #include <cstdio>
 #include <cstdlib>
 
@@ -307,6 +308,173 @@ struct PartParams {
     int tma_ok;            // qs is 16-byte aligned: full tiles move by bulk copies
 };
 
+struct PartCtx {
+    uint32_t *s_in, *s_pk;
+    uint16_t *cnt, *cntw;
+    uint32_t* s_tile;
+    uint64_t* bar_in;
+    unsigned* s_warp;
+    unsigned tid, lane, lt_mask, pitch16, i0;
+};
+
+// (thread 0) tile t of a 16-byte aligned batch -> the landing buffer, by two bulk copies
+__device__ __forceinline__ void part_issue_load(const PartParams& p, uint32_t* s_in, uint64_t* bar_in, unsigned t) {
+    if (p.tma_ok && t < p.ntiles && (size_t)(t + 1) * kTile <= p.nq) {
+        mbar_expect_tx(bar_in, kTile * 4u);
+        const char* src = reinterpret_cast<const char*>(p.qs + (size_t)t * kTile);
+        tma_bulk_g2s(s_in, src, 32768u, bar_in);
+        tma_bulk_g2s(reinterpret_cast<char*>(s_in) + 32768, src + 32768, 32768u, bar_in);
+    }
+}
+
+// One tile of the partition kernel.  Compiled twice, for full tiles and for the partial last one: with `full` a compile-time
+// constant the per-query validity tests vanish from the full-tile code (they were 11 of the 19 instructions per query of the
+// position phase).
+template <int BITS, int HYBRID, bool full>
+__device__ __forceinline__ void part_tile(const PartParams& p, const PartCtx& c, const unsigned tile, unsigned& phase, unsigned (&acc_tot)[2]) {
+    const BkView& v = p.v;
+    uint32_t* const s_in = c.s_in;
+    uint32_t* const s_pk = c.s_pk;
+    uint16_t* const cnt = c.cnt;
+    uint16_t* const cntw = c.cntw;
+    uint32_t* const s_tile = c.s_tile;
+    unsigned* const s_warp = c.s_warp;
+    const unsigned tid = c.tid, lane = c.lane, lt_mask = c.lt_mask, pitch16 = c.pitch16, i0 = c.i0;
+    const size_t tile_base = (size_t)tile * kTile;
+    const unsigned tile_n = full ? (unsigned)kTile : (unsigned)(p.nq - tile_base);
+    const bool via_tma = p.tma_ok && full;  // (block-uniform)
+    uint32_t q[kPItems], pk[kPItems];
+    if (via_tma) {
+        mbar_wait(c.bar_in, phase);
+        phase ^= 1u;
+#pragma unroll
+        for (int r = 0; r < kPItems; r++) q[r] = s_in[i0 + r * 32];
+    } else {
+#pragma unroll
+        for (int r = 0; r < kPItems; r++) q[r] = i0 + r * 32 < tile_n ? __ldcs(p.qs + tile_base + i0 + r * 32) : 0u;
+    }
+    __syncthreads();  // s_in has been read by everyone
+    if (tid == 0) {
+        part_issue_load(p, c.s_in, c.bar_in, tile + gridDim.x);  // lands during the ranking below
+        tma_store_wait_read();         // the previous tile's bulk store has read s_tile (= the counters zeroed next)
+    }
+    if (v.above) {  // (uniform) the partitioned layouts answer q > MAX with (MAX, n), not with the signed compare: note it
+        uint32_t acc = 0;
+#pragma unroll
+        for (int r = 0; r < kPItems; r++) acc |= q[r];
+        if (__any_sync(kFull, acc > kMax) && lane == 0) atomicOr(v.above, 1u);
+    }
+    {   // bucket of every query: ONE shared load and a compare (bk_pack_cell); a cell that two or more splitters share (skewed
+        // keys) is flagged and settled afterwards through the global tables, outside the straight-line path (the branchy
+        // form cost 30 instructions per query, a quarter of the kernel)
+        uint32_t flags = 0;
+#pragma unroll
+        for (int r = 0; r < kPItems; r++) {
+            q[r] = canonical(q[r]);
+            const uint32_t e = s_pk[q[r] >> kBtShift];
+            flags |= e;
+            pk[r] = (e & 0x7ffu) + ((q[r] & ((1u << kBtShift) - 1u)) > (e >> 12) ? 1u : 0u);
+        }
+        if (flags & 0x800u) {  // (unrolled: a rolled loop would index q[] and pk[] dynamically and push both into local memory)
+#pragma unroll
+            for (int r = 0; r < kPItems; r++)
+                if (s_pk[q[r] >> kBtShift] & 0x800u) pk[r] = bk_bucket(v.bt, v.split, q[r]);
+        }
+        if (!full) {
+#pragma unroll
+            for (int r = 0; r < kPItems; r++)
+                if (i0 + r * 32 >= tile_n) pk[r] = 0xffffffffu;
+        }
+    }
+    __syncthreads();  // thread 0 has seen the store's reads complete
+    {   // zero the per-warp counters
+        uint4* c4 = reinterpret_cast<uint4*>(cnt);
+        const unsigned n16 = kPWarps * pitch16 / 8;
+        for (unsigned i = tid; i < n16; i += kPThreads) c4[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    rank_items<BITS, full, HYBRID, kPItems>(cntw, pk, lane, lt_mask);
+    __syncthreads();
+    // Per bucket: exclusive scan of the counters over the warps, the bucket's run {start, count} of this tile, and the
+    // bucket's start folded into the per-warp bases.  Four adjacent lanes share a group of four adjacent buckets (one
+    // 8-byte access = the four 16-bit counters of one warp) and take eight warps each (lane j: warps j, j + 4, ...), so
+    // the 64 KB counter matrix is read twice and written once in 8-byte accesses (it was 4 x 32 two-byte accesses per
+    // thread).  Rows are padded by 32 bytes: the four lanes of a group then hit banks 8 apart and a half-warp's sixteen
+    // 8-byte accesses cover all 32 banks once (unpadded rows put the four lanes on the same banks: measured +7 %).
+    {
+        const unsigned j = tid & 3u, pitch = pitch16 / 4;  // quarter of the warps; row pitch in uint2
+        // buckets are laid out in the order b = tid (k = 0), then b = tid + 1024 (k = 1): one k after the other, each with its
+        // own block scan, so that only one set of partial sums is live next to the 32 query / bucket registers
+        unsigned run_total = 0;
+#pragma unroll
+        for (unsigned k = 0; k < 2; k++)
+            if (k < v.bpt) {
+                uint2* c2 = reinterpret_cast<uint2*>(cnt) + (tid >> 2) + k * (kPThreads / 4) + (size_t)j * pitch;
+                unsigned rx = 0, ry = 0;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const uint2 c = c2[(size_t)(4 * i) * pitch];
+                    rx += c.x & 0x07ff07ffu;  // (claim tags masked off; 16-bit halves cannot carry: every sum is <= kTile)
+                    ry += c.y & 0x07ff07ffu;
+                }
+                unsigned px = rx, py = ry;  // inclusive scan over the four quarters
+                unsigned yx = __shfl_up_sync(kFull, px, 1), yy = __shfl_up_sync(kFull, py, 1);
+                if (j >= 1) { px += yx; py += yy; }
+                yx = __shfl_up_sync(kFull, px, 2); yy = __shfl_up_sync(kFull, py, 2);
+                if (j >= 2) { px += yx; py += yy; }
+                const unsigned ex_x = px - rx, ex_y = py - ry;
+                const unsigned tx = __shfl_sync(kFull, px, lane | 3u), ty = __shfl_sync(kFull, py, lane | 3u);  // the group's four totals
+                const unsigned gtot = (tx & 0xffffu) + (tx >> 16) + (ty & 0xffffu) + (ty >> 16);
+                unsigned total;
+                if (k) __syncthreads();  // s_warp of the previous scan has been read
+                const unsigned base = run_total + block_excl_scan(j == 0 ? gtot : 0u, s_warp, &total);
+                run_total += total;
+                const unsigned s0 = __shfl_sync(kFull, base, lane & ~3u);  // start of the group's first bucket
+                const unsigned s1 = s0 + (tx & 0xffffu), s2 = s1 + (tx >> 16), s3 = s2 + (ty & 0xffffu);
+                const unsigned st = j == 0 ? s0 : j == 1 ? s1 : j == 2 ? s2 : s3;  // this thread's bucket: tid + 1024 k
+                const unsigned tt = j == 0 ? (tx & 0xffffu) : j == 1 ? (tx >> 16) : j == 2 ? (ty & 0xffffu) : (ty >> 16);
+                p.runs[(size_t)(tid + k * kPThreads) * p.ntp + tile] = st | (tt << kRunShift);
+                acc_tot[k] += tt;
+                rx = (s0 | (s1 << 16)) + ex_x;  // bucket start + queries of the bucket in earlier warps
+                ry = (s2 | (s3 << 16)) + ex_y;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const uint2 c = c2[(size_t)(4 * i) * pitch];
+                    c2[(size_t)(4 * i) * pitch] = make_uint2(rx, ry);
+                    rx += c.x & 0x07ff07ffu;
+                    ry += c.y & 0x07ff07ffu;
+                }
+            }
+    }
+    __syncthreads();
+    // final position of every query inside the sorted tile; the position map goes out as it is computed
+    uint16_t* tl = p.lpos + tile_base + i0;
+#pragma unroll
+    for (int r = 0; r < kPItems; r++) {
+        const bool valid = full || i0 + r * 32 < tile_n;
+        const unsigned pos = valid ? (unsigned)cntw[pk[r] & 0xffffu] + (pk[r] >> 16) : 0u;
+        pk[r] = pos;
+        if (valid) tl[r * 32] = (uint16_t)pos;
+    }
+    __syncthreads();  // every counter has been read: the sorted tile may overwrite them
+#pragma unroll
+    for (int r = 0; r < kPItems; r++)
+        if (full || i0 + r * 32 < tile_n) s_tile[pk[r]] = q[r];
+    if (via_tma) {
+        fence_proxy_async();  // generic-proxy writes to shared memory -> visible to the bulk-copy engine
+        __syncthreads();
+        if (tid == 0) {
+            char* dst = reinterpret_cast<char*>(p.qsort + tile_base);
+            tma_bulk_s2g(dst, s_tile, 32768u);
+            tma_bulk_s2g(dst + 32768, reinterpret_cast<char*>(s_tile) + 32768, 32768u);
+            tma_store_commit();
+        }
+    } else {
+        __syncthreads();
+        for (unsigned i = tid; i < tile_n; i += kPThreads) p.qsort[tile_base + i] = s_tile[i];
+    }
+}
+
 template <int BITS, int HYBRID>
 __global__ void __launch_bounds__(kPThreads, 1)
 bk_part_kernel(const PartParams p) {
@@ -328,168 +496,14 @@ bk_part_kernel(const PartParams p) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto full_tile = [&](unsigned t) { return t < p.ntiles && (size_t)(t + 1) * kTile <= p.nq; };
-    auto issue_load = [&](unsigned t) {  // (thread 0) next tile -> s_in
-        if (p.tma_ok && full_tile(t)) {
-            mbar_expect_tx(&bar_in, kTile * 4u);
-            const char* src = reinterpret_cast<const char*>(p.qs + (size_t)t * kTile);
-            tma_bulk_g2s(s_in, src, 32768u, &bar_in);
-            tma_bulk_g2s(reinterpret_cast<char*>(s_in) + 32768, src + 32768, 32768u, &bar_in);
-        }
-    };
-    if (tid == 0) issue_load(blockIdx.x);
+    if (tid == 0) part_issue_load(p, s_in, &bar_in, blockIdx.x);
     unsigned phase = 0;
     unsigned acc_tot[2] = {0, 0};  // this CTA's queries in buckets tid and tid + 1024, over all of its tiles
     const unsigned i0 = warp * (kPItems * 32) + lane;  // this thread's queries: i0 + 32 r
+    const PartCtx ctx{s_in, s_pk, cnt, cntw, s_tile, &bar_in, s_warp, tid, lane, lt_mask, pitch16, i0};
     for (unsigned tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        const size_t tile_base = (size_t)tile * kTile;
-        const bool full = (size_t)(tile + 1) * kTile <= p.nq;
-        const unsigned tile_n = full ? (unsigned)kTile : (unsigned)(p.nq - tile_base);
-        const bool via_tma = p.tma_ok && full;  // (block-uniform)
-        uint32_t q[kPItems], pk[kPItems];
-        if (via_tma) {
-            mbar_wait(&bar_in, phase);
-            phase ^= 1u;
-#pragma unroll
-            for (int r = 0; r < kPItems; r++) q[r] = s_in[i0 + r * 32];
-        } else {
-#pragma unroll
-            for (int r = 0; r < kPItems; r++) q[r] = i0 + r * 32 < tile_n ? __ldcs(p.qs + tile_base + i0 + r * 32) : 0u;
-        }
-        __syncthreads();  // s_in has been read by everyone
-        if (tid == 0) {
-            issue_load(tile + gridDim.x);  // lands during the ranking below
-            tma_store_wait_read();         // the previous tile's bulk store has read s_tile (= the counters zeroed next)
-        }
-        if (v.above) {  // (uniform) the partitioned layouts answer q > MAX with (MAX, n), not with the signed compare: note it
-            uint32_t acc = 0;
-#pragma unroll
-            for (int r = 0; r < kPItems; r++) acc |= q[r];
-            if (__any_sync(kFull, acc > kMax) && lane == 0) atomicOr(v.above, 1u);
-        }
-        {   // bucket of every query: ONE shared load and a compare (bk_pack_cell); a cell that two or more splitters share (skewed
-            // keys) is flagged and settled afterwards through the global tables, outside the straight-line path (the branchy
-            // form cost 30 instructions per query, a quarter of the kernel)
-            uint32_t flags = 0;
-#pragma unroll
-            for (int r = 0; r < kPItems; r++) {
-                q[r] = canonical(q[r]);
-                const uint32_t e = s_pk[q[r] >> kBtShift];
-                flags |= e;
-                pk[r] = (e & 0x7ffu) + ((q[r] & ((1u << kBtShift) - 1u)) > (e >> 12) ? 1u : 0u);
-            }
-            if (flags & 0x800u) {  // (unrolled: a rolled loop would index q[] and pk[] dynamically and push both into local memory)
-#pragma unroll
-                for (int r = 0; r < kPItems; r++)
-                    if (s_pk[q[r] >> kBtShift] & 0x800u) pk[r] = bk_bucket(v.bt, v.split, q[r]);
-            }
-            if (!full) {
-#pragma unroll
-                for (int r = 0; r < kPItems; r++)
-                    if (i0 + r * 32 >= tile_n) pk[r] = 0xffffffffu;
-            }
-        }
-        __syncthreads();  // thread 0 has seen the store's reads complete
-        {   // zero the per-warp counters
-            uint4* c4 = reinterpret_cast<uint4*>(cnt);
-            const unsigned n16 = kPWarps * pitch16 / 8;
-            for (unsigned i = tid; i < n16; i += kPThreads) c4[i] = make_uint4(0, 0, 0, 0);
-        }
-        __syncthreads();
-        if (full) rank_items<BITS, true, HYBRID, kPItems>(cntw, pk, lane, lt_mask);
-        else rank_items<BITS, false, HYBRID, kPItems>(cntw, pk, lane, lt_mask);
-        __syncthreads();
-        // Per bucket: exclusive scan of the counters over the warps, the bucket's run {start, count} of this tile, and the
-        // bucket's start folded into the per-warp bases.  Four adjacent lanes share a group of four adjacent buckets (one
-        // 8-byte access = the four 16-bit counters of one warp) and take eight warps each (lane j: warps j, j + 4, ...), so
-        // the 64 KB counter matrix is read twice and written once in 8-byte accesses (it was 4 x 32 two-byte accesses per
-        // thread).  Rows are padded by 32 bytes: the four lanes of a group then hit banks 8 apart and a half-warp's sixteen
-        // 8-byte accesses cover all 32 banks once (unpadded rows put the four lanes on the same banks: measured +7 %).
-        {
-            const unsigned j = tid & 3u, pitch = pitch16 / 4;  // quarter of the warps; row pitch in uint2
-            unsigned tot_k[2] = {0, 0}, st_k[2] = {0, 0};
-            unsigned ex_k[2][2], add_k[2][2];  // [k][x/y]: packed 16-bit pairs
-            unsigned gtot[2] = {0, 0};
-#pragma unroll
-            for (unsigned k = 0; k < 2; k++)
-                if (k < v.bpt) {
-                    const uint2* c2 = reinterpret_cast<const uint2*>(cnt) + (tid >> 2) + k * (kPThreads / 4) + (size_t)j * pitch;
-                    unsigned rx = 0, ry = 0;
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const uint2 c = c2[(size_t)(4 * i) * pitch];
-                        rx += c.x & 0x07ff07ffu;  // (claim tags masked off; 16-bit halves cannot carry: every sum is <= kTile)
-                        ry += c.y & 0x07ff07ffu;
-                    }
-                    unsigned px = rx, py = ry;  // inclusive scan over the four quarters
-                    unsigned yx = __shfl_up_sync(kFull, px, 1), yy = __shfl_up_sync(kFull, py, 1);
-                    if (j >= 1) { px += yx; py += yy; }
-                    yx = __shfl_up_sync(kFull, px, 2); yy = __shfl_up_sync(kFull, py, 2);
-                    if (j >= 2) { px += yx; py += yy; }
-                    ex_k[k][0] = px - rx; ex_k[k][1] = py - ry;
-                    const unsigned tx = __shfl_sync(kFull, px, lane | 3u), ty = __shfl_sync(kFull, py, lane | 3u);  // the group's four totals
-                    add_k[k][0] = tx; add_k[k][1] = ty;  // (turned into the starts below)
-                    gtot[k] = (tx & 0xffffu) + (tx >> 16) + (ty & 0xffffu) + (ty >> 16);
-                }
-            // buckets are laid out in the order b = tid (k = 0), then b = tid + 1024 (k = 1): two scans keep bucket order
-            unsigned total0, total1 = 0;
-            unsigned base[2];
-            base[0] = block_excl_scan(j == 0 ? gtot[0] : 0u, s_warp, &total0);
-            base[1] = 0;
-            if (v.bpt > 1) {
-                __syncthreads();
-                base[1] = total0 + block_excl_scan(j == 0 ? gtot[1] : 0u, s_warp, &total1);
-            }
-#pragma unroll
-            for (unsigned k = 0; k < 2; k++)
-                if (k < v.bpt) {
-                    const unsigned g0 = __shfl_sync(kFull, base[k], lane & ~3u);  // start of the group's first bucket
-                    const unsigned tx = add_k[k][0], ty = add_k[k][1];
-                    const unsigned s0 = g0, s1 = s0 + (tx & 0xffffu), s2 = s1 + (tx >> 16), s3 = s2 + (ty & 0xffffu);
-                    add_k[k][0] = (s0 | (s1 << 16)) + ex_k[k][0];
-                    add_k[k][1] = (s2 | (s3 << 16)) + ex_k[k][1];
-                    st_k[k] = j == 0 ? s0 : j == 1 ? s1 : j == 2 ? s2 : s3;  // this thread's bucket: tid + 1024 k
-                    tot_k[k] = j == 0 ? (tx & 0xffffu) : j == 1 ? (tx >> 16) : j == 2 ? (ty & 0xffffu) : (ty >> 16);
-                    p.runs[(size_t)(tid + k * kPThreads) * p.ntp + tile] = st_k[k] | (tot_k[k] << kRunShift);
-                    acc_tot[k] += tot_k[k];
-                    uint2* c2 = reinterpret_cast<uint2*>(cnt) + (tid >> 2) + k * (kPThreads / 4) + (size_t)j * pitch;
-                    unsigned rx = add_k[k][0], ry = add_k[k][1];  // bucket start + queries of the bucket in earlier warps
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const uint2 c = c2[(size_t)(4 * i) * pitch];
-                        c2[(size_t)(4 * i) * pitch] = make_uint2(rx, ry);
-                        rx += c.x & 0x07ff07ffu;
-                        ry += c.y & 0x07ff07ffu;
-                    }
-                }
-        }
-        __syncthreads();
-        // final position of every query inside the sorted tile; the position map goes out as it is computed
-        uint16_t* tl = p.lpos + tile_base + i0;
-#pragma unroll
-        for (int r = 0; r < kPItems; r++) {
-            const bool valid = full || i0 + r * 32 < tile_n;
-            const unsigned pos = valid ? (unsigned)cntw[pk[r] & 0xffffu] + (pk[r] >> 16) : 0u;
-            pk[r] = pos;
-            if (valid) tl[r * 32] = (uint16_t)pos;
-        }
-        __syncthreads();  // every counter has been read: the sorted tile may overwrite them
-#pragma unroll
-        for (int r = 0; r < kPItems; r++)
-            if (full || i0 + r * 32 < tile_n) s_tile[pk[r]] = q[r];
-        if (via_tma) {
-            fence_proxy_async();  // generic-proxy writes to shared memory -> visible to the bulk-copy engine
-            __syncthreads();
-            if (tid == 0) {
-                char* dst = reinterpret_cast<char*>(p.qsort + tile_base);
-                tma_bulk_s2g(dst, s_tile, 32768u);
-                tma_bulk_s2g(dst + 32768, reinterpret_cast<char*>(s_tile) + 32768, 32768u);
-                tma_store_commit();
-            }
-        } else {
-            __syncthreads();
-            for (unsigned i = tid; i < tile_n; i += kPThreads) p.qsort[tile_base + i] = s_tile[i];
-        }
+        if ((size_t)(tile + 1) * kTile <= p.nq) part_tile<BITS, HYBRID, true>(p, ctx, tile, phase, acc_tot);
+        else part_tile<BITS, HYBRID, false>(p, ctx, tile, phase, acc_tot);
     }
 #pragma unroll
     for (unsigned k = 0; k < 2; k++)
