@@ -741,30 +741,30 @@ bk_search2_kernel(const BkSearchParams p, uint32_t* __restrict__ qsort, uint32_t
             // while they are below the query (37 % / 10 % / 2 % of the lanes for uniform keys).  No upper end is needed:
             // every separator of a later cell is above q and the bucket's last separator is >= q.
             unsigned l[U];
-            uint32_t s0[U];
+            uint32_t s0[U], s1[U], s2[U];
 #pragma unroll
             for (int u = 0; u < U; u++) l[u] = s_jump[(q[u] - lo) >> sh];
+            // three separators from the jump cell on, loaded for every query at once (3 x U independent loads in flight; with
+            // one branch per probe the U chains ran one after the other); a fourth is needed by ~1 % of the queries
 #pragma unroll
             for (int u = 0; u < U; u++) s0[u] = s_sep[min(l[u], p.r - 1u)];
 #pragma unroll
+            for (int u = 0; u < U; u++) s1[u] = s_sep[min(l[u] + 1u, p.r - 1u)];
+#pragma unroll
+            for (int u = 0; u < U; u++) s2[u] = s_sep[min(l[u] + 2u, p.r - 1u)];
+#pragma unroll
             for (int u = 0; u < U; u++) {
-                unsigned pos = l[u];
-                if (s0[u] < q[u]) {
-                    pos++;
-                    if (s_sep[min(pos, p.r - 1u)] < q[u]) {
-                        pos++;
-                        if (s_sep[min(pos, p.r - 1u)] < q[u]) {
-                            pos++;
-                            unsigned hh = s_jump[((q[u] - lo) >> sh) + 1u];
-                            if (hh > pos + 8u) {
-                                while (pos < hh) {
-                                    const unsigned m = (pos + hh) >> 1;
-                                    if (s_sep[m] < q[u]) pos = m + 1; else hh = m;
-                                }
-                            } else {
-                                while (pos < hh && s_sep[pos] < q[u]) pos++;
-                            }
+                const bool c0 = s0[u] < q[u], c1 = c0 && s1[u] < q[u], c2 = c1 && s2[u] < q[u];
+                unsigned pos = l[u] + (c0 ? 1u : 0u) + (c1 ? 1u : 0u) + (c2 ? 1u : 0u);
+                if (c2) {
+                    unsigned hh = s_jump[((q[u] - lo) >> sh) + 1u];
+                    if (hh > pos + 8u) {
+                        while (pos < hh) {
+                            const unsigned m = (pos + hh) >> 1;
+                            if (s_sep[m] < q[u]) pos = m + 1; else hh = m;
                         }
+                    } else {
+                        while (pos < hh && s_sep[pos] < q[u]) pos++;
                     }
                 }
                 a[u] = pos;
