@@ -1164,7 +1164,13 @@ static int launch_bucketed_v2(const sst_index* idx, const uint32_t* d_qs, size_t
         set_error(SST_ERR_CAPACITY, "not enough device memory for the reordered-batch scratch buffers (6-10 bytes per query)");
         return SST_ERR_CAPACITY;
     }
-    if (!SST_CUDA_OK(cudaStreamWaitEvent(st, s.done, 0))) return SST_ERR_CUDA;  // scratch reuse across this thread's streams
+    // scratch reuse across this thread's streams: a call waits for the previous one.  Not while `st` is being captured into a
+    // CUDA graph: an event recorded outside the capture cannot be waited on there, and one recorded inside it would tie later
+    // calls to the capture; the graph's own launches are ordered by the stream, replays are the caller's to order.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (!SST_CUDA_OK(cudaStreamIsCapturing(st, &cap))) return SST_ERR_CUDA;
+    const bool capturing = cap != cudaStreamCaptureStatusNone;
+    if (!capturing && !SST_CUDA_OK(cudaStreamWaitEvent(st, s.done, 0))) return SST_ERR_CUDA;
     const int sms = sm_count(dev);
     const bool flat_parts = idx->variant == SST_SIMPLE || idx->variant == SST_L1 || idx->variant == SST_OVERLAPPING;
     const bool map_tree = idx->variant == SST_MAP || flat_parts;  // partitioned: a query above MAX has no part -> (MAX, n)
@@ -1226,7 +1232,7 @@ static int launch_bucketed_v2(const sst_index* idx, const uint32_t* d_qs, size_t
         }
         for (int i = 0; i < nev; i++) cudaEventDestroy(ev[i]);
     }
-    if (!SST_CUDA_OK(cudaGetLastError()) || !SST_CUDA_OK(cudaEventRecord(s.done, st))) return SST_ERR_CUDA;
+    if (!SST_CUDA_OK(cudaGetLastError()) || (!capturing && !SST_CUDA_OK(cudaEventRecord(s.done, st)))) return SST_ERR_CUDA;
     return SST_OK;
 }
 

@@ -47,6 +47,9 @@ def test_sa_check_detects_corruption(gpu, oracle):
     bad = sa.copy()
     bad[[100, 101]] = bad[[101, 100]]
     assert sst.SaNaive.from_parts(text, sa).check() == 0
+    with pytest.raises(sst.SstError):  # an uploaded array is validated like the reference's build asserts (sa_search.rs:36-38)
+        sst.SaNaive.from_parts(text, bad)
+    sst.set_option("SA_VALIDATE", 0)   # trusted caller: no check at upload, the handle's own check still reports it
     assert sst.SaNaive.from_parts(text, bad).check() > 0
 
 
@@ -187,7 +190,7 @@ def test_sa_search_kmer_table(gpu, oracle, n, k, inline_bases, monkeypatch):
     _check_search(sst, oracle, s, text, sa, pats)
     gpu.set_option("SA_USE_INLINE", 0)  # k-mer table, probes on the text
     _check_search(sst, oracle, s, text, sa, pats[:3000] + pats[-60:])
-    monkeypatch.delenv("SST_SA_USE_INLINE")
+    gpu.set_option("SA_USE_INLINE", 1)
     # the same through the pivot table only
     gpu.set_option("SA_USE_KMER", 0)
     _check_search(sst, oracle, s, text, sa, pats[:2000])
