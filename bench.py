@@ -366,7 +366,7 @@ def run_own(args):
     ok = ok and bool((keys[i2.clamp(max=n - 1)] == out_v[:1_000_000]).all())
 
     # ---- roofline of the step's kernels: algorithmic bytes per step / mean step time ----
-    # (one kernel for the direct schemes; the reordered-batch pipeline is 7 dependent kernels, timed as a whole)
+    # (one kernel for the direct schemes; the reordered-batch pipeline is 4 dependent kernels, timed as a whole)
     layer_nodes = layer_nodes_for(n)
     l2_bytes = torch.cuda.get_device_properties(dev).L2_cache_size
     H_hbm = hbm_levels(layer_nodes, l2_bytes)
@@ -380,7 +380,7 @@ def run_own(args):
     bucketed = res_scheme.value == sst.SCHEME_BUCKETED
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "bytes_per_query": bytes_per_query, "hbm_levels": H_hbm,
-                "kernel": ("reordered-batch pipeline: bk_rank + bk_colsum + bk_plan + bk_offsets + bk_move<scatter> + bk_search + bk_move<gather>"
+                "kernel": ("reordered-batch pipeline: bk_part_kernel + bk_items_kernel + bk_search2_kernel + bk_unperm_kernel"
                            if bucketed else "stree_search_fast"),
                 "kernel_ms": kern_ms, "launches_per_step": res_launches.value}
     if bucketed:  # one extra untimed step with per-stage CUDA events (synchronises between stages, so it is not a bench value)
@@ -394,7 +394,7 @@ def run_own(args):
             roofline["stage_ms"] = {k: round(float(x), 4) for k, x in zip(names, st_ms) if k != "-"}
             tot_st = sum(float(x) for x in st_ms)
             # the dominant kernel of the step and its share (to be compared with the ncu launch list in profiles/)
-            roofline["dominant_kernel"] = {"name": "bk_search_kernel", "ms": round(float(st_ms[3]), 4), "share_of_step": round(float(st_ms[3]) / tot_st, 3)}
+            roofline["dominant_kernel"] = {"name": "bk_search2_kernel", "ms": round(float(st_ms[3]), 4), "share_of_step": round(float(st_ms[3]) / tot_st, 3)}
     tf = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tf) and n == (1 << 28) and (e - s) == 100_000_000:  # the capture is of exactly this step shape
         try:

@@ -21,7 +21,8 @@ for r in rows:
     elif unit in ("Kbyte", "Mbyte", "Gbyte", "byte"):
         val *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
     per[k][metric] += val
-bk = {k: v for k, v in per.items() if re.match(r"bk_(rank|colsum|plan|offsets|move|search)", k) and "unsigned long" not in k}  # (the index-output gather belongs to verification calls)
+# the pipeline's kernels: round 1 = rank/colsum/plan/offsets/move/search, round 2 = part/items/search2/unperm
+bk = {k: v for k, v in per.items() if re.match(r"bk_(rank|colsum|plan|offsets|move|search|part|items|unperm)", k) and "unsigned long" not in k}  # (the index-output pass belongs to verification calls)
 steps = max([len(count[k]) for k in bk if k.startswith("bk_search")] or [1])  # one search launch per pipeline run
 out = {"per_kernel": {}, "pipeline_runs_in_capture": steps}
 step_us = sum(v["gpu__time_duration.sum"] for v in bk.values()) / steps
