@@ -514,6 +514,9 @@ def run_own(args):
     if args.sa_text > 0:  # C3: 10^8 random DNA text, 10^7 32-mers, plain vs LCP-accelerated
         run_block("sa", lambda: bench_sa_config(args, sst, torch, dev, R, rank, world, "C3", args.sa_text, args.sa_patterns, 32, 32,
                                                 3, args.c_e2e_reps, args.sa_cpu_sample))
+    if args.sa_rep_text > 0:  # the same path where LCP skipping can pay: repetitive text, long patterns (north_star (3): "report both")
+        run_block("sa_repetitive", lambda: bench_sa_config(args, sst, torch, dev, R, rank, world, "C3-repetitive", args.sa_rep_text, args.sa_rep_patterns,
+                                                           200, 2000, 3, 0, 0, tandem=50_000))
     if args.c4_log2_keys > 0:
         run_block("c4", lambda: bench_c4(args, sst, torch, dev, R, rank, world))
     if args.c5_text > 0:  # C5: 3x10^9 text, 10^8 patterns of 20..100 bytes
@@ -596,7 +599,7 @@ def _make_patterns(torch, dev, text, npat, len_lo, len_hi, gen):
     return pats, off, total
 
 
-def bench_sa_config(args, sst, torch, dev, R, rank, world, name, n, npat_total, len_lo, len_hi, reps, e2e_reps, cpu_sample):
+def bench_sa_config(args, sst, torch, dev, R, rank, world, name, n, npat_total, len_lo, len_hi, reps, e2e_reps, cpu_sample, tandem=0):
     """One suffix-array config (C3: 10^8 text / 10^7 32-mers; C5: 3x10^9 text / 10^8 patterns of 20..100 bytes): text + SA
     replicated per GPU, the pattern batch sharded contiguously (chunk = ceil(npat / N)), binary and LCP-accelerated search,
     device-resident and through the host-buffer call, with an exact host-side sample check of [lo, hi) and pos."""
@@ -605,7 +608,14 @@ def bench_sa_config(args, sst, torch, dev, R, rank, world, name, n, npat_total, 
 
     L = sst.lib()
     g = torch.Generator(device=dev).manual_seed(args.seed + 5)              # the same text on every rank
-    text = torch.randint(0, 4, (n,), dtype=torch.uint8, device=dev, generator=g)
+    if tandem:  # a random unit of `tandem` bases repeated over the whole text, one base in 1000 mutated: long common prefixes
+        unit = torch.randint(0, 4, (tandem,), dtype=torch.uint8, device=dev, generator=g)
+        text = unit.repeat(-(-n // tandem))[:n].contiguous()
+        nmut = n // 1000
+        text[torch.randint(0, n, (nmut,), device=dev, generator=g)] = torch.randint(0, 4, (nmut,), dtype=torch.uint8, device=dev, generator=g)
+        del unit
+    else:
+        text = torch.randint(0, 4, (n,), dtype=torch.uint8, device=dev, generator=g)
     t0 = time.time()
     sa = sst.SaNaive.build(text)
     torch.cuda.synchronize()
@@ -618,7 +628,8 @@ def bench_sa_config(args, sst, torch, dev, R, rank, world, name, n, npat_total, 
     hi = torch.empty(npat, dtype=torch.int32, device=dev)
     pos = torch.empty(npat, dtype=torch.int32, device=dev)
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    out = {"config": name, "text_bytes": n, "patterns": npat_total, "patterns_per_gpu": npat, "pattern_len": [len_lo, len_hi],
+    out = {"config": name, "text": (f"tandem repeats of a {tandem}-base unit, 0.1 % point mutations" if tandem else "uniform random over {0,1,2,3}"),
+           "text_bytes": n, "patterns": npat_total, "patterns_per_gpu": npat, "pattern_len": [len_lo, len_hi],
            "sa_build_s": round(build_s, 3), "unit": "patterns/s", "n_gpus": world, "scaling": "strong", "timed_reps": reps}
     ok = True
     ref_lo = ref_hi = None
@@ -639,7 +650,8 @@ def bench_sa_config(args, sst, torch, dev, R, rank, world, name, n, npat_total, 
         ms = R.max(a.elapsed_time(b)) / reps
         out[mname + "_patterns_per_s"] = npat_total / (ms * 1e-3)
         out[mname + "_ms"] = ms
-        bad, checked = _sa_exact_sample(sst, torch, dev, sa, text, pats, off, lo, hi, pos, args.parity_sample, args.seed + 31 * rank)
+        bad, checked = _sa_exact_sample(sst, torch, dev, sa, text, pats, off, lo, hi, pos, min(args.parity_sample, 1000) if tandem else args.parity_sample,
+                                        args.seed + 31 * rank)
         out[mname + "_ok"] = R.all_ok(bad == 0)
         ok = ok and out[mname + "_ok"]
         if ref_lo is None:
@@ -873,6 +885,8 @@ def main():
     ap.add_argument("--sa-text", type=int, default=100_000_000, help="0 disables the secondary SA metric")
     ap.add_argument("--sa-patterns", type=int, default=10_000_000)
     ap.add_argument("--sa-cpu-sample", type=int, default=2_000_000, help="patterns of the CPU SA baseline sample")
+    ap.add_argument("--sa-rep-text", type=int, default=100_000_000, help="repetitive-text SA block: text length (0 disables it)")
+    ap.add_argument("--sa-rep-patterns", type=int, default=200_000, help="repetitive-text SA block: patterns (length 200..2000) in total")
     ap.add_argument("--c4-log2-keys", type=int, default=30, help="config C4: log2 of the key count (0 disables the block)")
     ap.add_argument("--c4-queries", type=int, default=1_000_000_000, help="config C4: queries in total, sharded over the GPUs")
     ap.add_argument("--c5-text", type=int, default=3_000_000_000, help="config C5: text length (0 disables the block)")

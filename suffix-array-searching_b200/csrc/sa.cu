@@ -436,6 +436,7 @@ __device__ __forceinline__ uint32_t thread_compare(const SaParams& p, unsigned l
     const uint8_t* tbase = p.text + spos;
     const uint8_t* tend = p.text + p.n + 64;   // the text is followed by 64 zero bytes
     const uint8_t* pend = p.pats + p.pats_bytes;
+    if (sl < start) start = 0u;  // (a suffix shorter than the prefix the caller assumes equal: see the k-mer cell's LCP seed)
     for (uint32_t off = start;; off += 16u) {
         if (off >= lim) { less = sl < ql; return lim; }
         const W4 tw = load16_unaligned<false, true>(tbase + off, tend);  // the text has 64 bytes of zero padding
@@ -492,6 +493,11 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
                     l = ldr(p.kmer + x);
                     r = ldr(p.kmer + (size_t)x + 1);
                     range_end = r;  // every suffix that starts with q starts with its first k bases
+                    // every suffix of the cell that has k bases shares them with the pattern: both LCP bounds start at k instead of
+                    // 0 (lower bounds, not exact values: lcp_r_exact stays false).  One of the text's last < k suffixes can sit in
+                    // the cell without sharing them (AAC lies between AAAT and AACA); thread_compare starts such a suffix,
+                    // which is shorter than the assumed common prefix, at byte 0.
+                    if (MLR) lcp_l = lcp_r = (uint32_t)k;
                 } else {
                     // every suffix from kmer[x] on is >= q000.. >= q; the only suffixes below it that are >= q are proper
                     // prefixes of q000.. (the last < k suffixes of the text): search the k positions before it
@@ -621,18 +627,22 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
             if (lo < p.n && r == lo && lcp_r_exact) {
                 if (lcp_r >= ql) { a = lo + 1; step = 2; } else { b = lo; step = 0; }
             }
+            // LCP-accelerated form: every suffix of [a, b) lies between one that starts with q (lcp = |q|) and suffix(b), so it
+            // shares at least lcp(q, suffix(b)) bytes with q: once a probe has failed, later probes start there (rounded to 16).
+            uint32_t lcp_b = 0;  // lcp(q, suffix(b)) once b comes from a failed probe
+            if (MLR && step == 0) lcp_b = lcp_r;
             while (step) {
                 const unsigned long long pr = a + step - 1;
                 if (pr >= b) break;
                 bool less;
                 const uint32_t lcp = probe((uint32_t)pr, 0u, less);
-                if (lcp >= ql) { a = pr + 1; step <<= 1; } else { b = pr; break; }
+                if (lcp >= ql) { a = pr + 1; step <<= 1; } else { b = pr; lcp_b = lcp; break; }
             }
             while (a < b) {
                 const unsigned long long m = (a + b) >> 1;
                 bool less;
-                const uint32_t lcp = probe((uint32_t)m, 0u, less);
-                if (lcp >= ql) a = m + 1; else b = m;
+                const uint32_t lcp = probe((uint32_t)m, MLR ? (lcp_b & ~15u) : 0u, less);
+                if (lcp >= ql) a = m + 1; else { b = m; lcp_b = lcp; }
             }
             p.out_hi[i] = (uint32_t)a;
         }
