@@ -158,6 +158,12 @@ int sst_query_device(const sst_index_t* idx, const uint32_t* d_qs, size_t nq, ui
  * (it is also freed when the thread exits). */
 int sst_query_reserve(const sst_index_t* idx, size_t nq, int want_index);
 void sst_query_release(void);
+/* Measures on this index, on its own device, from which batch size on the reordered-batch pipeline beats the direct kernel
+ * (synthetic queries that follow the key distribution, batches of 2^20 .. max_nq), and makes SST_SCHEME_AUTO use that
+ * crossover for this index instead of the default rule.  A few tens of milliseconds; 12 bytes of device memory per query of
+ * the largest batch while it runs.  *out_min_nq (nullable): the crossover, SIZE_MAX if the pipeline never won, 0 for an
+ * index the pipeline does not serve (nothing to calibrate). */
+int sst_query_calibrate(sst_index_t* idx, size_t max_nq, size_t* out_min_nq);
 /* Number of kernel launches sst_query_device issues for this index/scheme (for launch accounting). */
 int sst_query_launches(const sst_index_t* idx, int scheme);
 /* The kernel SST_SCHEME_AUTO resolves to for a batch of nq queries on this index (*out_scheme; partitioned layouts

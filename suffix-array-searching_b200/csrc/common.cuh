@@ -215,6 +215,7 @@ struct sst_index {
     uint16_t* d_c5 = nullptr;                     // [nodes * 16] separators minus the node's base
     uint32_t* d_h5 = nullptr;                     // [nodes] base (first separator), 0xffffffff = use the exact node
     BkAux bk;                                     // reordered-batch pipeline (plain B=16 trees, 2^22..2^28 keys)
+    size_t auto_min_nq = 0;                       // SCHEME_AUTO takes the pipeline from this batch size on; 0 = the rule of resolve_scheme, set by sst_query_calibrate
     bool persist_ok = false;                      // persisting-L2 carve-out configured on this device
     size_t persist_window_max = 0;
     SstTreeView view{};

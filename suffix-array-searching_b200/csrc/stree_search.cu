@@ -761,14 +761,29 @@ int launch_fast_top(const sst_index* idx, bool top, const uint32_t* d_qs, size_t
 // the thread-per-query kernel has the shortest latency (6-10 us up to 2^16 queries), the rank-table kernel wins from 2^17
 // queries, and for large batches over >= 2^25 keys the reordered-batch pipeline does (59.7 vs 52.8 Gq/s at 2^25 keys,
 // 55 vs 34 Gq/s at 2^28 keys for 10^8 queries); the table-less group kernel never wins.
+// Synthetic queries for sst_query_calibrate: a uniformly chosen bucket of the pipeline's splitters, a uniform value inside it
+// (so they follow the key distribution the index was built on); counter-based hash, no state.
+__global__ void calib_queries_kernel(const uint32_t* __restrict__ split, unsigned nb, uint32_t* __restrict__ q, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned long long x = (i + 1) * 0x9E3779B97F4A7C15ull;
+        x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+        const unsigned b = (unsigned)((x >> 40) % nb);
+        const uint32_t lo = split[b], hi = split[b + 1];
+        q[i] = lo + (uint32_t)((x & 0xffffffffull) % ((unsigned long long)(hi - lo) + 1ull));
+    }
+}
+
 int resolve_scheme(const sst_index* idx, int scheme, size_t nq) {
     if (scheme != SST_SCHEME_AUTO) return scheme;
     if (idx->variant == SST_EYTZINGER) return SST_SCHEME_GENERIC;
     const int forced = (int)opt(OPT_SCHEME);  // A/B runs: what AUTO resolves to (-1 = the measured rule below)
     if (bucketed_eligible(idx) && idx->n >= (size_t)opt(OPT_BK_AUTO_MIN_N)) {  // plain and Map-partitioned trees
-        // measured crossovers (tools/bucketed_once.py): 2^28 keys ~1.2x10^7 queries, 2^26 keys ~4x10^7, 2^25 keys ~6x10^7;
-        // at 2^24 keys and below the tree is L2-resident and the direct kernel always wins (65.7 vs 45.5 Gq/s)
-        const size_t min_nq = idx->n >= ((size_t)1 << 27) ? (size_t)1 << 24 : idx->n >= ((size_t)1 << 26) ? (size_t)3 << 24 : (size_t)1 << 26;
+        // Crossover between the rank-table kernel and the pipeline, in queries per batch.  Default rule from the size x batch sweep
+        // of profiles/r2_s3_size_batch_sweep.jsonl (one B200: the pipeline wins from 2^24 queries on at 2^25..2^29 keys and from
+        // 2^23 on at 2^30; at 2^24 keys and below the tree is L2-resident and the direct kernel always wins); an index that
+        // was calibrated on its own device and key distribution (sst_query_calibrate) carries its measured value instead.
+        const size_t rule = idx->n >= ((size_t)1 << 30) ? (size_t)1 << 23 : (size_t)1 << 24;
+        const size_t min_nq = idx->auto_min_nq ? idx->auto_min_nq : rule;
         if (nq >= (opt(OPT_BK_AUTO_MIN_NQ) >= 0 ? (size_t)opt(OPT_BK_AUTO_MIN_NQ) : min_nq)) return forced >= 0 ? forced : SST_SCHEME_BUCKETED;
     }
     if (idx->variant != SST_PLAIN && idx->node_b == 16 && opt(OPT_PGROUP)) return SST_SCHEME_AUTO;  // lane-group kernel
@@ -1048,6 +1063,61 @@ double sst_time_query_device(const sst_index_t* idx, const uint32_t* d_qs, size_
     cudaEventDestroy(a);
     cudaEventDestroy(b);
     return ok ? (double)ms / iters : -1.0;
+}
+
+// Measures, on this index and this device, from which batch size on the reordered-batch pipeline beats the direct kernel, and
+// makes SST_SCHEME_AUTO use that crossover for this index (instead of the rule taken from one B200).  Synthetic queries that
+// follow the key distribution (a uniformly chosen bucket of the pipeline's splitters, a uniform value inside it), batches of
+// 2^20 .. max_nq queries (max_nq is rounded down to a power of two, at most 2^26).  Costs a few tens of milliseconds and
+// 12 bytes of device memory per query of the largest batch while it runs.  *out_min_nq (nullable) receives the crossover
+// (SIZE_MAX: the pipeline never won).  No-op (SST_OK, *out_min_nq = 0) for an index the pipeline does not serve.
+int sst_query_calibrate(sst_index_t* idx, size_t max_nq, size_t* out_min_nq) {
+    clear_error();
+    if (!idx) { set_error(SST_ERR_ARG, "null argument"); return SST_ERR_ARG; }
+    if (out_min_nq) *out_min_nq = 0;
+    if (!bucketed_eligible(idx)) return SST_OK;
+    DeviceGuard g(idx->device);
+    if (!g.ok) return SST_ERR_CUDA;
+    int top = 20;
+    while (top < 26 && ((size_t)2 << top) <= max_nq) top++;
+    const size_t cap = (size_t)1 << top;
+    if (cap > max_nq) { set_error(SST_ERR_ARG, "max_nq must be at least 2^20"); return SST_ERR_ARG; }
+    uint32_t *d_q = nullptr, *d_v = nullptr;
+    if (!SST_CUDA_OK(cudaMalloc(&d_q, cap * 4)) || !SST_CUDA_OK(cudaMalloc(&d_v, cap * 4))) { cudaFree(d_q); return SST_ERR_CUDA; }
+    cudaStream_t st = thread_stream(idx->device);
+    calib_queries_kernel<<<cur_sms() * 8, 256, 0, st>>>(idx->bk.d_split, idx->bk.nb, d_q, cap);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    const int direct = idx->variant != SST_PLAIN ? SST_SCHEME_AUTO : top_eligible(idx) ? SST_SCHEME_TABLE : SST_SCHEME_GROUP2;
+    const size_t saved = idx->auto_min_nq;
+    idx->auto_min_nq = ~(size_t)0;  // AUTO = the direct kernel while the partitioned layouts are timed through it
+    auto time_ms = [&](int scheme, size_t nq) -> double {
+        for (int it = 0; it < 4; it++) {
+            if (it == 1) cudaEventRecord(a, st);
+            if (launch_query(idx, d_q, nq, d_v, nullptr, scheme, st) != SST_OK) return -1.0;
+        }
+        cudaEventRecord(b, st);
+        float ms = 0;
+        if (!SST_CUDA_OK(cudaEventSynchronize(b)) || !SST_CUDA_OK(cudaEventElapsedTime(&ms, a, b))) return -1.0;
+        return ms / 3.0;
+    };
+    size_t found = ~(size_t)0;
+    bool ok = true;
+    for (int lg = top; lg >= 20; lg--) {  // from the largest batch down: the crossover is the smallest size of the winning run
+        const size_t nq = (size_t)1 << lg;
+        const double td = time_ms(direct, nq), tb = time_ms(SST_SCHEME_BUCKETED, nq);
+        if (td < 0 || tb < 0) { ok = false; break; }
+        if (tb <= td) found = nq; else break;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d_q);
+    cudaFree(d_v);
+    if (!ok) { idx->auto_min_nq = saved; return sst_last_status() != SST_OK ? sst_last_status() : SST_ERR_CUDA; }
+    idx->auto_min_nq = found;
+    if (out_min_nq) *out_min_nq = found;
+    return SST_OK;
 }
 
 double sst_probe_gather64(int device, size_t bytes, size_t n_gathers, int lanes_per_node, int iters) {

@@ -57,6 +57,10 @@ class SearchIndex {
     uint32_t query_one(uint32_t q) const { return query({q})[0]; }
     uint32_t search(uint32_t q) const { return query_one(q); }  // s_tree.rs:196
     const sst_index_t* raw() const { return h_.get(); }
+    /// Pre-sizes the calling thread's pipeline scratch: later device-side queries of up to nq allocate nothing.
+    void reserve(size_t nq, bool want_index = false) const { check(sst_query_reserve(h_.get(), nq, want_index ? 1 : 0)); }
+    /// Measures on this device from which batch size on the reordered-batch pipeline wins and makes SST_SCHEME_AUTO use it.
+    size_t calibrate(size_t max_nq = (size_t)1 << 25) { size_t v = 0; check(sst_query_calibrate(h_.get(), max_nq, &v)); return v; }
 
   protected:
     explicit SearchIndex(sst_index_t* h) : h_(h, sst_index_free) { if (!h) panic_last(); }
@@ -209,7 +213,46 @@ class SaNaive {
     std::shared_ptr<sst_sa_t> h_;
     size_t n_;
 };
-/// binary_search(sa, q, cnt) -> sa[l]  (sa_search.rs:98-112); cnt is not tracked on the GPU
+/// binary_search(sa, q, cnt) -> sa[l]  (sa_search.rs:98-112)
 inline size_t binary_search(const SaNaive& sa, const std::vector<uint8_t>& q) { return sa.search({q})[0].pos; }
+/// the same with the reference's probe counter: *cnt advances by the iterations of `while l < r` (sa_search.rs:101-110)
+inline size_t binary_search(const SaNaive& sa, const std::vector<uint8_t>& q, size_t* cnt) {
+    const uint64_t off[2] = {0, q.size()};
+    uint32_t pos = 0, probes = 0;
+    check(sst_sa_search_probes(sa.raw(), q.data(), off, 1, &pos, &probes));
+    if (cnt) *cnt += probes;
+    return pos;
+}
+
+/// Text + suffix array replicated on several GPUs, the pattern batch sharded contiguously (chunk = ceil(npat / G)): the
+/// serial callers of sa_search.rs:423-451 in the harness shape of bench.rs:558-573.
+class MultiSa {
+  public:
+    static MultiSa build(const std::vector<uint8_t>& t, const std::vector<int>& devices) {
+        return MultiSa(sst_multi_sa_build(t.data(), t.size(), devices.data(), (int)devices.size()));
+    }
+    static MultiSa from_parts(const std::vector<uint8_t>& t, const std::vector<uint32_t>& sa, const std::vector<int>& devices) {
+        return MultiSa(sst_multi_sa_from_parts(t.data(), t.size(), sa.data(), devices.data(), (int)devices.size()));
+    }
+    int devices() const { return sst_multi_sa_devices(h_.get()); }
+    std::vector<SaNaive::Hit> search(const std::vector<std::vector<uint8_t>>& pats, int mode = SST_SA_BINARY) const {
+        std::vector<uint8_t> flat;
+        std::vector<uint64_t> off{0};
+        for (auto& p : pats) { flat.insert(flat.end(), p.begin(), p.end()); off.push_back(flat.size()); }
+        std::vector<uint32_t> lo(pats.size()), hi(pats.size()), pos(pats.size());
+        check(sst_multi_sa_search(h_.get(), flat.data(), off.data(), pats.size(), mode, lo.data(), hi.data(), pos.data()));
+        std::vector<SaNaive::Hit> out(pats.size());
+        for (size_t i = 0; i < pats.size(); i++) out[i] = {lo[i], hi[i], pos[i]};
+        return out;
+    }
+
+  private:
+    explicit MultiSa(sst_multi_sa_t* h) : h_(h, sst_multi_sa_free) { if (!h) panic_last(); }
+    std::shared_ptr<sst_multi_sa_t> h_;
+};
+
+/// Library options (the table of csrc/common.cuh; read from SST_<NAME> once at load time, then only through these)
+inline void set_option(const std::string& name, long long v) { check(sst_set_option(name.c_str(), v)); }
+inline long long get_option(const std::string& name) { long long v = 0; check(sst_get_option(name.c_str(), &v)); return v; }
 
 }  // namespace sst

@@ -114,6 +114,24 @@ int main() {
         EXPECT(std::equal(q.begin(), q.end(), t.begin() + pos));
         auto hits = sa.search({q}, SST_SA_MLR);
         EXPECT(hits[0].pos == pos && hits[0].hi > hits[0].lo);
+        // the reference's probe counter: iterations of `while l < r` over [0, n) = floor(log2 n) or one more (sa_search.rs:98-112)
+        size_t cnt = 0;
+        EXPECT(binary_search(sa, q, &cnt) == pos && cnt >= 16 && cnt <= 17);
+        // replicas (one device listed three times), patterns sharded by chunk = ceil(npat / G)
+        auto msa = MultiSa::build(t, {0, 0, 0});
+        std::vector<std::vector<uint8_t>> pats;
+        for (int k = 0; k < 50; k++) pats.emplace_back(t.begin() + 1000 * k, t.begin() + 1000 * k + 20 + k);
+        auto one = sa.search(pats), many = msa.search(pats, SST_SA_MLR);
+        EXPECT(msa.devices() == 3 && one.size() == many.size());
+        for (size_t k = 0; k < one.size(); k++) EXPECT(one[k].lo == many[k].lo && one[k].hi == many[k].hi && one[k].pos == many[k].pos);
+    }
+    {   // options are validated; calibrate is a no-op on an index the pipeline does not serve
+        bool threw = false;
+        try { set_option("SA_LANES", 0); } catch (const Panic&) { threw = true; }
+        EXPECT(threw && get_option("SA_LANES") == 1);
+        auto small = STree16::new_({1, 5, 9, MAX});
+        EXPECT(small.calibrate() == 0);
+        small.reserve(1000);
     }
     if (failures) { fprintf(stderr, "%d failure(s)\n", failures); return 1; }
     printf("host mirror OK\n");

@@ -13,6 +13,7 @@ use std::marker::PhantomData;
 
 #[repr(C)] pub struct SstIndex { _p: [u8; 0] }
 #[repr(C)] pub struct SstSa { _p: [u8; 0] }
+#[repr(C)] pub struct SstMultiSa { _p: [u8; 0] }
 
 pub const SST_LEFT_MAX: u32 = 1;
 pub const SST_REVERSE_STORAGE: u32 = 2;
@@ -42,6 +43,14 @@ extern "C" {
                      out_lo: *mut u32, out_hi: *mut u32, out_pos: *mut u32) -> c_int;
     fn sst_sa_search_probes(sa: *const SstSa, pats: *const u8, pat_off: *const u64, npat: usize,
                             out_pos: *mut u32, out_probes: *mut u32) -> c_int;
+    fn sst_multi_sa_build(text: *const u8, n: usize, devices: *const c_int, n_devices: c_int) -> *mut SstMultiSa;
+    fn sst_multi_sa_search(m: *const SstMultiSa, pats: *const u8, pat_off: *const u64, npat: usize, mode: c_int,
+                           out_lo: *mut u32, out_hi: *mut u32, out_pos: *mut u32) -> c_int;
+    fn sst_multi_sa_devices(m: *const SstMultiSa) -> c_int;
+    fn sst_multi_sa_free(m: *mut SstMultiSa);
+    fn sst_query_reserve(idx: *const SstIndex, nq: usize, want_index: c_int) -> c_int;
+    fn sst_query_calibrate(idx: *mut SstIndex, max_nq: usize, out_min_nq: *mut usize) -> c_int;
+    fn sst_set_option(name: *const c_char, value: i64) -> c_int;
 }
 
 fn last_error() -> String { unsafe { CStr::from_ptr(sst_last_error()).to_string_lossy().into_owned() } }
@@ -57,6 +66,14 @@ impl GpuIndex {
     fn from_raw(h: *mut SstIndex) -> Self { if h.is_null() { panic!("sst_b200: {}", last_error()); } Self { h } }
     pub fn size(&self) -> usize { unsafe { sst_index_size_bytes(self.h) } }
     pub fn layers(&self) -> usize { unsafe { sst_index_layers(self.h) } }
+    /// Pre-sizes the calling thread's pipeline scratch: later device-side queries of up to `nq` allocate nothing.
+    pub fn reserve(&self, nq: usize, want_index: bool) { check(unsafe { sst_query_reserve(self.h, nq, want_index as c_int) }) }
+    /// Measures on this device from which batch size on the reordered-batch pipeline wins; `SST_SCHEME_AUTO` then uses it.
+    pub fn calibrate(&mut self, max_nq: usize) -> usize {
+        let mut v = 0usize;
+        check(unsafe { sst_query_calibrate(self.h, max_nq, &mut v) });
+        v
+    }
     /// `SearchScheme::query`: values of the first key >= q, same length and order as `qs`.
     pub fn query(&self, qs: &[u32]) -> Vec<u32> {
         let mut out = vec![0u32; qs.len()];
@@ -204,4 +221,35 @@ pub fn binary_search(sa: &GpuSa, q: &[u8], cnt: &mut usize) -> usize {
     check(unsafe { sst_sa_search_probes(sa.h, q.as_ptr(), off.as_ptr(), 1, &mut pos, &mut probes) });
     *cnt += probes as usize;
     pos as usize
+}
+
+/// Text + suffix array replicated on several GPUs, the pattern batch sharded contiguously (chunk = ceil(npat / G)): the serial
+/// callers of sa_search.rs:423-451 in the harness shape of static-search-tree/src/bin/bench.rs:558-573.
+pub struct GpuMultiSa { h: *mut SstMultiSa }
+unsafe impl Send for GpuMultiSa {}
+unsafe impl Sync for GpuMultiSa {}
+impl Drop for GpuMultiSa { fn drop(&mut self) { unsafe { sst_multi_sa_free(self.h) } } }
+impl GpuMultiSa {
+    pub fn build(t: &[u8], devices: &[i32]) -> Self {
+        let h = unsafe { sst_multi_sa_build(t.as_ptr(), t.len(), devices.as_ptr(), devices.len() as c_int) };
+        if h.is_null() { panic!("sst_b200: {}", last_error()); }
+        Self { h }
+    }
+    pub fn devices(&self) -> usize { unsafe { sst_multi_sa_devices(self.h) as usize } }
+    /// Batched `binary_search`: `sa[l]` per pattern, in pattern order.
+    pub fn binary_search_batch(&self, qs: &[&[u8]], mlr: bool) -> Vec<usize> {
+        let mut flat = Vec::new();
+        let mut off = vec![0u64];
+        for q in qs { flat.extend_from_slice(q); off.push(flat.len() as u64); }
+        let (mut lo, mut pos) = (vec![0u32; qs.len()], vec![0u32; qs.len()]);
+        check(unsafe { sst_multi_sa_search(self.h, flat.as_ptr(), off.as_ptr(), qs.len(), mlr as c_int, lo.as_mut_ptr(),
+                                           std::ptr::null_mut(), pos.as_mut_ptr()) });
+        pos.into_iter().map(|p| p as usize).collect()
+    }
+}
+
+/// Library option by name (the table of csrc/common.cuh), e.g. `set_option("SA_CHUNK", 1 << 22)`.
+pub fn set_option(name: &str, value: i64) {
+    let c = std::ffi::CString::new(name).unwrap();
+    check(unsafe { sst_set_option(c.as_ptr(), value) });
 }

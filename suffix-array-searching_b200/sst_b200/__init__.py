@@ -63,6 +63,7 @@ def lib() -> C.CDLL:
         "sst_option_name": (C.c_char_p, [i32]),
         "sst_query_reserve": (i32, [vp, sz, i32]),
         "sst_query_release": (None, []),
+        "sst_query_calibrate": (i32, [vp, sz, vp]),
         "sst_bind_thread_to_device": (i32, [i32]),
         "sst_host_alloc": (vp, [sz]),
         "sst_host_free": (None, [vp]),
@@ -317,6 +318,13 @@ class SearchIndex:
     def reserve(self, nq: int, want_index: bool = False) -> None:
         """Pre-size the calling thread's pipeline scratch so that device-side queries of up to nq allocate nothing."""
         _check(lib().sst_query_reserve(self._h, int(nq), int(want_index)))
+
+    def calibrate(self, max_nq: int = 1 << 25) -> int:
+        """Measure on this device from which batch size on the reordered-batch pipeline beats the direct kernel and make
+        SCHEME_AUTO use it for this index.  Returns the crossover (0: nothing to calibrate; 2**64 - 1: the pipeline never won)."""
+        out = C.c_size_t(0)
+        _check(lib().sst_query_calibrate(self._h, int(max_nq), C.byref(out)))
+        return out.value
 
     def query_one(self, q: int, scheme: int = SCHEME_AUTO) -> int:
         """SearchScheme::query_one (lib.rs:52-54)."""

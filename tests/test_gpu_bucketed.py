@@ -144,8 +144,8 @@ def test_bucketed_unaligned_device_buffers(gpu, oracle, monkeypatch):
 
 
 def test_auto_picks_the_pipeline_for_large_batches(gpu, oracle):
-    """SCHEME_AUTO: reordered-batch pipeline for large batches over >= 2^25 keys (from 2^26 queries at 2^25 keys, from 2^24 at
-    2^27 keys and up), the rank-table kernel below; sst_query_plan reports the choice and the launch count."""
+    """SCHEME_AUTO: reordered-batch pipeline for large batches over >= 2^25 keys (from 2^24 queries on, the crossover of
+    profiles/r2_s3_size_batch_sweep.jsonl), the rank-table kernel below; sst_query_plan reports the choice and the launch count."""
     import ctypes as C
 
     import torch
@@ -163,7 +163,8 @@ def test_auto_picks_the_pipeline_for_large_batches(gpu, oracle):
     assert sch.value == sst.SCHEME_BUCKETED and launches.value == 4  # partition, work items, search, un-permute
     assert L.sst_query_plan(t._h, 1 << 26, 0, 1, C.byref(sch), C.byref(launches)) == 0 and launches.value == 5
     assert L.sst_query_plan(t._h, (1 << 28) + 1, 0, 0, C.byref(sch), C.byref(launches)) == 0 and launches.value == 12  # three sub-batches
-    assert L.sst_query_plan(t._h, 1 << 24, 0, 0, C.byref(sch), C.byref(launches)) == 0 and sch.value == sst.SCHEME_TABLE
+    assert L.sst_query_plan(t._h, 1 << 24, 0, 0, C.byref(sch), C.byref(launches)) == 0 and sch.value == sst.SCHEME_BUCKETED
+    assert L.sst_query_plan(t._h, (1 << 24) - 1, 0, 0, C.byref(sch), C.byref(launches)) == 0 and sch.value == sst.SCHEME_TABLE
     assert L.sst_query_plan(t._h, 1 << 20, 0, 0, C.byref(sch), C.byref(launches)) == 0
     assert sch.value == sst.SCHEME_TABLE and launches.value == 1
     qs = torch.randint(0, MAX, ((1 << 26) + 5,), dtype=torch.int32, device="cuda", generator=g)
@@ -250,3 +251,37 @@ def test_bucketed_map_skewed_keys(gpu, oracle, monkeypatch):
         assert np.array_equal(v, v2) and np.array_equal(i, i2)
         assert np.array_equal(v, ev) and np.array_equal(i, ei)
     assert served >= 3
+
+
+def test_calibrate_sets_the_auto_crossover(gpu, oracle):
+    """sst_query_calibrate times the direct kernel against the pipeline on the index's own device and SCHEME_AUTO follows the
+    measured crossover: below it the direct kernel, from it on the pipeline; results do not change."""
+    import ctypes as C
+
+    sst = gpu
+    sst.set_option("BK_MIN_N", 0)
+    sst.set_option("BK_AUTO_MIN_N", 0)
+    sst.set_option("BK_R", 1024)
+    vals = gen_vals(1 << 21, seed=51)
+    t = sst.STree16.new_params(vals, True, False, False)
+    L = sst.lib()
+
+    def auto_scheme(nq):
+        sch, ln = C.c_int(0), C.c_int(0)
+        L.sst_query_plan(t._h, nq, sst.SCHEME_AUTO, 0, C.byref(sch), C.byref(ln))
+        return sch.value
+
+    assert auto_scheme(1 << 22) != sst.SCHEME_BUCKETED and auto_scheme(1 << 24) == sst.SCHEME_BUCKETED  # the default rule
+    cross = t.calibrate(1 << 22)
+    assert cross == 2**64 - 1 or (1 << 20) <= cross <= (1 << 22)
+    if cross != 2**64 - 1:
+        assert auto_scheme(cross) == sst.SCHEME_BUCKETED and (cross == 1 << 20 or auto_scheme(cross // 2) != sst.SCHEME_BUCKETED)
+    else:
+        assert auto_scheme(1 << 24) != sst.SCHEME_BUCKETED
+    qs = gen_queries(300_000, seed=52, vals=vals)
+    ev, ei = oracle.lower_bound(vals, qs)
+    v, i = t.query(qs, want_index=True)
+    assert np.array_equal(v, ev) and np.array_equal(i, ei)
+    small = sst.STree16.new_params(gen_vals(1000, seed=53), True, False, False)
+    sst.reset_options()
+    assert sst.STree16.new_params(gen_vals(1000, seed=53), True, False, False).calibrate() == 0  # nothing to calibrate
