@@ -302,15 +302,17 @@ def sa_search_batch32(text, sa, flat, off, threads=1):
 # input formats (pure Python / numpy restatements)
 # ----------------------------------------------------------------------------------------------
 def read_fasta(data: bytes) -> np.ndarray:
-    """suffix-array-searching/src/util.rs:144-169 read_fasta_file: needletail FASTA records (a header line
-    starts with '>', sequence lines are concatenated with line ends stripped); map[] sends A/C/G/T in either
-    case to 0..3 and every other byte to 0."""
+    """suffix-array-searching/src/util.rs:144-169 read_fasta_file: needletail::parse_fastx_file records.  The format is
+    picked from the first byte (needletail 0.5.1, pinned at Cargo.lock:686-687; not vendored): '>' = FASTA (a header line starts with '>', sequence
+    lines are concatenated with line ends stripped), '@' = FASTQ (four-line records: header, sequence, '+', qualities;
+    only the second line is sequence).  map[] sends A/C/G/T in either case to 0..3 and every other byte to 0."""
     m = np.zeros(256, np.uint8)
     for ch, v in ((b"A", 0), (b"C", 1), (b"G", 2), (b"T", 3), (b"a", 0), (b"c", 1), (b"g", 2), (b"t", 3)):
         m[ch[0]] = v
     out = []
-    for line in data.split(b"\n"):
-        if line.startswith(b">"):
+    fastq = data[:1] == b"@"
+    for ln, line in enumerate(data.split(b"\n")):
+        if (ln % 4 != 1) if fastq else line.startswith(b">"):
             continue
         line = line.replace(b"\r", b"")
         if line:

@@ -2,8 +2,10 @@
 //
 // Replaces (reference paths):
 //   read_fasta_file                      suffix-array-searching/src/util.rs:144-169
-//     (needletail FASTA records: header lines start with '>', sequence lines are concatenated with
-//      line ends stripped; A/C/G/T in either case map to 0..3, every other byte to 0)
+//     (needletail::parse_fastx_file picks the format from the first byte.  FASTA ('>'): header lines start with '>',
+//      sequence lines are concatenated with line ends stripped.  FASTQ ('@'): four-line records -- header, sequence,
+//      '+' line, qualities -- of which only the second line is sequence.  A/C/G/T in either case map to 0..3, every
+//      other byte to 0)
 //   k-mer key generation of `--human`    static-search-tree/src/bin/bench.rs:60-76
 //     (rolling 2-bit pack of k = 16 bases, masked to 31 bits; vals[0] = MAX)
 //   the key sort before every build      static-search-tree/src/bin/bench.rs:89 (rdst radix sort)
@@ -54,6 +56,19 @@ __global__ void fasta_classify(const char* __restrict__ s, size_t n, const unsig
     }
 }
 
+// FASTQ: number of line ends before byte i (an exclusive sum gives every byte its line number; line % 4 == 1 is sequence)
+__global__ void fastq_line_ends(const char* __restrict__ s, size_t n, unsigned long long* __restrict__ flag) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) flag[i] = s[i] == '\n' ? 1ull : 0ull;
+}
+__global__ void fastq_classify(const char* __restrict__ s, size_t n, const unsigned long long* __restrict__ line_no, uint8_t* __restrict__ code,
+                               uint8_t* __restrict__ keep) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const char c = s[i];
+        keep[i] = ((line_no[i] & 3ull) == 1ull && c != '\n' && c != '\r') ? 1 : 0;
+        code[i] = base_code(c);
+    }
+}
+
 // bench.rs:64-73: key_i = (2-bit pack of codes[i .. i+k), first base most significant) & (2^(2k) - 1) & MAX
 __global__ void kmer_keys_kernel(const uint8_t* __restrict__ codes, size_t count, unsigned k, uint32_t* __restrict__ keys) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
@@ -93,7 +108,24 @@ int sst_fasta_encode_device(const char* d_fasta, size_t len, uint8_t* d_out_code
          SST_CUDA_OK(cub::DeviceSelect::Flagged(nullptr, tb2, d_code, d_keep, d_out_codes, d_count, (unsigned long long)len, st));
     ok = ok && SST_CUDA_OK(cudaMalloc(&tmp, std::max(tb1, tb2)));
     unsigned long long count = 0;
-    if (ok) {
+    char first = 0;
+    ok = ok && SST_CUDA_OK(cudaMemcpyAsync(&first, d_fasta, 1, cudaMemcpyDeviceToHost, st)) && SST_CUDA_OK(cudaStreamSynchronize(st));
+    if (ok && first == '@') {  // FASTQ (needletail decides by the first byte): line number of every byte, line % 4 == 1 is sequence
+        size_t tb3 = 0;
+        ok = SST_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tb3, d_start, d_start, (unsigned long long)len, st));
+        if (ok && tb3 > std::max(tb1, tb2)) { cudaFree(tmp); tmp = nullptr; ok = SST_CUDA_OK(cudaMalloc(&tmp, tb3)); }
+        if (ok) {
+            fastq_line_ends<<<grid_for(len), kThreads, 0, st>>>(d_fasta, len, d_start);
+            ok = SST_CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp, tb3, d_start, d_start, (unsigned long long)len, st));
+        }
+        if (ok) {
+            fastq_classify<<<grid_for(len), kThreads, 0, st>>>(d_fasta, len, d_start, d_code, d_keep);
+            size_t tb = std::max(tb2, tb3);
+            ok = SST_CUDA_OK(cub::DeviceSelect::Flagged(tmp, tb, d_code, d_keep, d_out_codes, d_count, (unsigned long long)len, st)) &&
+                 SST_CUDA_OK(cudaMemcpyAsync(&count, d_count, 8, cudaMemcpyDeviceToHost, st)) && SST_CUDA_OK(cudaStreamSynchronize(st)) &&
+                 SST_CUDA_OK(cudaGetLastError());
+        }
+    } else if (ok) {
         fasta_line_starts<<<grid_for(len), kThreads, 0, st>>>(d_fasta, len, d_start);
         size_t tb = tb1;
         ok = SST_CUDA_OK(cub::DeviceScan::InclusiveScan(tmp, tb, d_start, d_start, MaxOp(), (unsigned long long)len, st));

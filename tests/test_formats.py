@@ -25,6 +25,22 @@ def test_oracle_fasta_known_answers(oracle):
     assert oracle.read_fasta(CASES[6]).tolist() == [0, 1, 2, 3, 2, 2]
 
 
+FASTQ_CASES = [
+    b"@r1\nACGT\n+\nIIII\n",
+    b"@r1 desc\nACGT\n+r1\n@III\n@r2\nggta\n+\n>>>>\n",     # '@' and '>' inside quality lines, lower case
+    b"@r1\r\nACNT\r\n+\r\nIIII\r\n@r2\r\nTT\r\n+\r\nII",    # CRLF, N -> 0, no trailing newline
+    b"@empty\n\n+\n\n@r\nCC\n+\nII\n",                      # an empty read
+]
+
+
+def test_oracle_fastq_known_answers(oracle):
+    """needletail::parse_fastx_file (util.rs:161) also reads FASTQ: four-line records, the second line is the sequence."""
+    assert oracle.read_fasta(FASTQ_CASES[0]).tolist() == [0, 1, 2, 3]
+    assert oracle.read_fasta(FASTQ_CASES[1]).tolist() == [0, 1, 2, 3, 2, 2, 3, 0]
+    assert oracle.read_fasta(FASTQ_CASES[2]).tolist() == [0, 1, 0, 3, 3, 3]
+    assert oracle.read_fasta(FASTQ_CASES[3]).tolist() == [1, 1]
+
+
 def test_oracle_kmer_keys_known_answers(oracle):
     codes = np.array([0, 1, 2, 3, 3, 2, 1, 0], np.uint8)
     k3 = oracle.kmer_keys(codes, k=3, sort=False)
@@ -44,7 +60,9 @@ def test_gpu_fasta_matches_oracle(gpu, oracle):
     rng = np.random.default_rng(5)
     big = b"".join(b">rec%d some text\n" % i + b"\n".join(bytes(rng.choice(list(b"ACGTacgtN"), 61).tolist()) for _ in range(int(rng.integers(1, 40)))) + b"\n"
                    for i in range(200))
-    for data in CASES + [big]:
+    bigq = b"".join(b"@read%d\n" % i + bytes(rng.choice(list(b"ACGTacgtN"), n).tolist()) + b"\n+\n" + bytes(rng.choice(list(b"@>+IJ#"), n).tolist()) + b"\n"
+                    for i, n in enumerate(rng.integers(1, 300, 500)))
+    for data in CASES + [big] + FASTQ_CASES + [bigq]:
         got = sst.read_fasta(data)
         assert np.array_equal(got, oracle.read_fasta(data)), data[:40]
 
