@@ -887,6 +887,10 @@ bk_unperm_kernel(const uint32_t* __restrict__ res, const uint16_t* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // auxiliary arrays (index build time)
 // ------------------------------------------------------------------------------------------------
+__global__ void bk_pad_kernel(uint32_t* __restrict__ a, size_t from, size_t to) {
+    for (size_t i = from + threadIdx.x; i < to; i += blockDim.x) a[i] = kMax;
+}
+
 // sep[m] = last key of block m of g keys (leaf slot g*m + g - 1) for m < m8, 0xffffffff beyond
 __global__ void bk_sep_kernel(const uint32_t* __restrict__ leaf, unsigned long long m8, unsigned long long total, unsigned g,
                               uint32_t* __restrict__ sep) {
@@ -984,19 +988,24 @@ bool regrow(T*& p, size_t count) {
 }  // namespace
 
 void free_bucket_aux(sst_index* idx) {
-    cudaFree(idx->bk.d_sep); cudaFree(idx->bk.d_split); cudaFree(idx->bk.d_bt); cudaFree(idx->bk.d_jump); cudaFree(idx->bk.d_meta);
+    cudaFree(idx->bk.d_dense); cudaFree(idx->bk.d_sep); cudaFree(idx->bk.d_split); cudaFree(idx->bk.d_bt); cudaFree(idx->bk.d_jump); cudaFree(idx->bk.d_meta);
     idx->bk = BkAux{};
 }
 
 // Builds the auxiliary arrays of the reordered-batch pipeline for a plain B=16 tree.  Returns false only
 // on a CUDA error; an index the pipeline does not serve simply has bk.nb == 0.
-bool build_bucket_aux(sst_index* idx) {
+bool build_bucket_aux(sst_index* idx, const uint32_t* d_sorted) {
     // plain B=16 trees, and the Map-partitioned layout: its leaf level is the sorted array itself, without per-part gaps
     // (partitioned_s_tree.rs:503), which is all the pipeline reads of an image
     // Simple / L1 / Overlapping: their leaf level is ONE non-decreasing flat array too -- the slots between two parts hold the
     // first key of the next non-empty part (:502-515), the tail MAX -- so the lower bound in it has the right value; its
-    // position is turned into the sorted-array index afterwards (bk_flat_index_kernel).  Compact interleaves the parts' levels.
-    if (idx->variant == SST_COMPACT || idx->variant == SST_EYTZINGER || idx->node_b != 16) return true;
+    // position is turned into the sorted-array index afterwards (bk_flat_index_kernel).
+    // Compact interleaves the levels of every part and pads each part's leaves with MAX (:283-307), so its image holds no flat
+    // sorted leaf level: the pipeline reads a dense GPU-only copy of the keys instead (4 bytes per key on top of the image, next
+    // to the dense copy of the upper levels the lane-group kernel already uses); when memory is short the layout simply stays on
+    // the lane-group kernel.
+    if (idx->variant == SST_EYTZINGER || idx->node_b != 16) return true;
+    if (idx->variant == SST_COMPACT && (!d_sorted || !opt(OPT_BK_COMPACT))) return true;
     if (idx->n < (size_t)opt(OPT_BK_MIN_N)) return true;  // small trees are L2-resident: nothing to gain
     const bool flat_parts = idx->variant == SST_SIMPLE || idx->variant == SST_L1 || idx->variant == SST_OVERLAPPING;
     const size_t n_flat = flat_parts ? (size_t)idx->layer_blocks[idx->levels - 1] * 16 : idx->n;
@@ -1017,6 +1026,14 @@ bool build_bucket_aux(sst_index* idx) {
     while ((1u << bits) < nb) bits++;
     cudaStream_t st = thread_stream(idx->device);
     const uint32_t* leaf = idx->d_tree + idx->offsets[idx->levels - 1] * 16;
+    if (idx->variant == SST_COMPACT) {
+        // room for whole blocks of g keys: the tail reads as MAX like the padded leaf level of the other layouts
+        const size_t words = (size_t)m8 * g;
+        if (cudaMalloc(&a.d_dense, words * 4) != cudaSuccess) { (void)cudaGetLastError(); a.d_dense = nullptr; return true; }  // no room: lane-group kernel
+        bk_pad_kernel<<<1, 32, 0, st>>>(a.d_dense, idx->n, words);  // the tail of the last block reads as MAX, like a padded leaf level
+        if (!SST_CUDA_OK(cudaMemcpyAsync(a.d_dense, d_sorted, idx->n * 4, cudaMemcpyDeviceToDevice, st))) { free_bucket_aux(idx); return false; }
+        leaf = a.d_dense;
+    }
     const unsigned long long total = (unsigned long long)nb * r;
     bool ok = SST_CUDA_OK(cudaMalloc(&a.d_sep, total * 4)) && SST_CUDA_OK(cudaMalloc(&a.d_split, ((size_t)nb + 1) * 4)) &&
               SST_CUDA_OK(cudaMalloc(&a.d_bt, (size_t)kBtStride * 2)) && SST_CUDA_OK(cudaMalloc(&a.d_jump, (size_t)nb * (r + 8) * 2)) &&
@@ -1173,12 +1190,12 @@ static int launch_bucketed_v2(const sst_index* idx, const uint32_t* d_qs, size_t
     if (!capturing && !SST_CUDA_OK(cudaStreamWaitEvent(st, s.done, 0))) return SST_ERR_CUDA;
     const int sms = sm_count(dev);
     const bool flat_parts = idx->variant == SST_SIMPLE || idx->variant == SST_L1 || idx->variant == SST_OVERLAPPING;
-    const bool map_tree = idx->variant == SST_MAP || flat_parts;  // partitioned: a query above MAX has no part -> (MAX, n)
+    const bool map_tree = idx->variant == SST_MAP || idx->variant == SST_COMPACT || flat_parts;  // partitioned: a query above MAX has no part -> (MAX, n)
     if (map_tree && !SST_CUDA_OK(cudaMemsetAsync(s.ctrl + 3, 0, 4, st))) return SST_ERR_CUDA;
     const size_t smem_part = (size_t)kTile * 4 + (size_t)kBtCells * 4 + std::max((size_t)kTile * 4, (size_t)kPWarps * (h.nbp2 + kCntPad) * 2);
     const size_t smem_search = (size_t)a.r * 4 + ((size_t)a.r + 8) * 2;
     const unsigned chunk_log2 = (unsigned)opt(OPT_BK_CHUNK2_LOG2);
-    BkSearchParams sp{a.d_sep, a.d_jump, a.d_meta, idx->d_tree + idx->offsets[idx->levels - 1] * 16, a.r, a.m8, a.n_flat};
+    BkSearchParams sp{a.d_sep, a.d_jump, a.d_meta, a.d_dense ? a.d_dense : idx->d_tree + idx->offsets[idx->levels - 1] * 16, a.r, a.m8, a.n_flat};
     const bool timing = opt(OPT_BK_TIMING) != 0;
     cudaEvent_t ev[8] = {};
     int nev = 0;

@@ -76,6 +76,7 @@ unsigned cur_sms();                   // sm_count of the calling thread's curren
     X(BK_CHUNK, 32768, 16384, 1 << 24)   /* queries per search work item */                                                   \
     X(BK_TIMING, 0, 0, 2)                /* per-stage CUDA-event times (synchronises; bench/tools only) */                    \
     X(BK_CHUNK2_LOG2, 15, 14, 24)        /* log2 of the queries per search work item of the V2 pipeline */                    \
+    X(BK_COMPACT, 1, 0, 1)               /* Compact layout: keep a dense copy of the keys so that large batches take the pipeline */ \
     X(BK_HYBRID, 1, 0, 4)                                                                                                    \
     X(BK_VEC, 1, 0, 1)                                                                                                       \
     X(BK_MOVE_THREADS, 1024, 512, 1024)                                                                                      \
@@ -172,6 +173,7 @@ struct SstTreeView {
 
 // Auxiliary arrays of the reordered-batch pipeline (bucketed.cu); nb == 0: not built for this index.
 struct BkAux {
+    uint32_t* d_dense = nullptr;  // COMPACT only: dense copy of the sorted keys, the "leaf level" the pipeline reads (the image interleaves the parts' levels)
     uint32_t* d_sep = nullptr;    // [nb * r] last key of every g-key block of the leaf level, 0xffffffff beyond the keys
     uint32_t* d_split = nullptr;  // [nb + 1] split[0] = 0, split[b] = last key before bucket b, split[nb] = MAX
     uint16_t* d_bt = nullptr;     // bucket table over the top 12 key bits
@@ -234,7 +236,7 @@ int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t
                  int scheme, cudaStream_t stream);
 int query_launch_count(const sst_index* idx, int scheme, size_t nq, bool want_idx);
 // reordered-batch pipeline (bucketed.cu)
-bool build_bucket_aux(sst_index* idx);
+bool build_bucket_aux(sst_index* idx, const uint32_t* d_sorted = nullptr);  // d_sorted: the builder's input (COMPACT keeps a copy)
 void free_bucket_aux(sst_index* idx);
 bool bucketed_eligible(const sst_index* idx);
 int last_stage_ms(double* out, int n);  // stage times of this thread's last pipeline run under SST_BK_TIMING=1

@@ -772,7 +772,7 @@ sst_index* build_partitioned(const uint32_t* d_sorted, size_t n, uint32_t b, int
         ok = ok && SST_CUDA_OK(cudaGetLastError()) && SST_CUDA_OK(cudaStreamSynchronize(st));
     }
     cudaFree(d_ne_pos); cudaFree(d_ne_start); cudaFree(d_ne_cnt);
-    if (ok && !COMPACT) ok = build_bucket_aux(idx);  // large batches take the reordered-batch pipeline over the (flat, sorted) leaf level
+    if (ok) ok = build_bucket_aux(idx, d_sorted);  // large batches take the reordered-batch pipeline over the (flat, sorted) leaf level; Compact: over a dense copy of the keys
     if (!ok) { free_index(idx); return nullptr; }
     finalize_view(idx);
     return idx;

@@ -802,7 +802,7 @@ int query_launch_count(const sst_index* idx, int scheme, size_t nq, bool want_id
     if (resolve_scheme(idx, scheme, nq) != SST_SCHEME_BUCKETED) return 1;
     const int base = 4;
     return (int)(div_ceil(nq, (size_t)1 << 27) * (base + (want_idx ? 1 : 0) + (idx->variant == SST_PLAIN ? 0 : 1) +
-                                                   (want_idx && idx->variant != SST_PLAIN && idx->variant != SST_MAP ? 1 : 0)));  // partitioned: + the q > MAX fix-up (+ flat -> sorted index)
+                                                   (want_idx && idx->variant != SST_PLAIN && idx->variant != SST_MAP && idx->variant != SST_COMPACT ? 1 : 0)));  // partitioned: + the q > MAX fix-up (+ flat -> sorted index)
 }
 
 int launch_query(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx,

@@ -94,8 +94,9 @@ def test_bucketed_unsupported_is_loud(gpu, monkeypatch):
         sst.STree16.new_params(big, True, False, False).query(qs, sst.SCHEME_BUCKETED)
     with pytest.raises(sst.SstError):
         sst.STree15.new_params(vals, True, False, False).query(qs, sst.SCHEME_BUCKETED)
+    gpu.set_option("BK_COMPACT", 0)  # Compact without its dense key copy: the image holds no flat leaf level
     with pytest.raises(sst.SstError):
-        sst.PartitionedSTree16C.new(vals, 4).query(qs, sst.SCHEME_BUCKETED)  # Compact interleaves the parts' levels: no flat leaf level
+        sst.PartitionedSTree16C.new(vals, 4).query(qs, sst.SCHEME_BUCKETED)
 
 
 def test_bucketed_streams_and_repeats(gpu, oracle, monkeypatch):
@@ -190,12 +191,13 @@ def test_bucketed_degenerate_batches(gpu, oracle, monkeypatch):
 
 @pytest.mark.parametrize("r,n,nq,b", [(64, 5000, 40_000, 4), (64, 1_000_000, 70_000, 8), (256, (1 << 20) + 5, 300_000, 16), (1024, 2_000_003, 150_000, 20),
                                       (64, 17, 33, 0), (16384, (1 << 22) + 999, 600_000, 20)])
-@pytest.mark.parametrize("layout", ["PartitionedSTree16M", "PartitionedSTree16", "PartitionedSTree16L", "PartitionedSTree16O"])
+@pytest.mark.parametrize("layout", ["PartitionedSTree16M", "PartitionedSTree16", "PartitionedSTree16L", "PartitionedSTree16O", "PartitionedSTree16C"])
 def test_bucketed_map_partitioned(gpu, oracle, monkeypatch, r, n, nq, b, layout):
     """The pipeline over a Map-partitioned tree (its leaf level is the sorted array, partitioned_s_tree.rs:503) and over the
     flat leaf level of Simple / L1 / Overlapping (gaps hold the next part's first key, :502-515; positions converted to
-    sorted-array indices): same values and indices as the oracle and as the layout's own lane-group kernel, including
-    queries above MAX (no part: (MAX, n))."""
+    sorted-array indices), and for Compact (whose image interleaves the parts' levels) over a dense GPU-only copy of the keys:
+    same values and indices as the oracle and as the layout's own lane-group kernel, including queries above MAX (no part:
+    (MAX, n))."""
     sst = gpu
     gpu.set_option("BK_MIN_N", 0)
     gpu.set_option("BK_R", int(str(r)))
@@ -233,7 +235,8 @@ def test_bucketed_map_skewed_keys(gpu, oracle, monkeypatch):
     rng = np.random.default_rng(77)
     served = 0
     for kind, layout in (("dupes", "PartitionedSTree16M"), ("clustered", "PartitionedSTree16M"), ("dupes", "PartitionedSTree16"),
-                         ("clustered", "PartitionedSTree16L"), ("tiny_range", "PartitionedSTree16O"), ("boundary16", "PartitionedSTree16")):
+                         ("clustered", "PartitionedSTree16L"), ("tiny_range", "PartitionedSTree16O"), ("boundary16", "PartitionedSTree16"),
+                         ("dupes", "PartitionedSTree16C"), ("clustered", "PartitionedSTree16C")):
         vals = make_keys(rng, 300_000, kind)
         qs = make_queries(rng, vals, 100_000)
         t = getattr(sst, layout).try_new(vals, 12)
