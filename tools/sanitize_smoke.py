@@ -51,7 +51,19 @@ for qs in (rng.integers(0, MAX, 3 * 16384 + 77, dtype=np.uint32), np.full(40_000
     v, i = tb.query(qs, sst.SCHEME_BUCKETED, want_index=True)
     assert (v == ev).all() and (i == ei).all()
     assert (tb.query(qs, sst.SCHEME_BUCKETED) == ev).all()
+# the same over the partitioned layouts (Compact reads a dense copy of the keys), queries above MAX mixed in
+for cls in (sst.PartitionedSTree16M, sst.PartitionedSTree16, sst.PartitionedSTree16C):
+    tp = cls.new(vals, 8)
+    qs = rng.integers(0, MAX, 2 * 16384 + 5, dtype=np.uint32)
+    qs[::97] |= 0x80000000
+    v1, i1 = tp.query(qs, sst.SCHEME_BUCKETED, want_index=True)
+    v2, i2 = tp.query(qs, sst.SCHEME_GENERIC, want_index=True)
+    assert (v1 == v2).all() and (i1 == i2).all(), cls.__name__
 sst.reset_options()
+# replicas on "several" devices (device 0 listed twice) and the probe counter
+ms = sst.MultiSa.build(rng.integers(0, 4, 20_000, dtype=np.uint8), [0, 0])
+flat, off = sst.pack_patterns([bytes(rng.integers(0, 4, 12, dtype=np.uint8)) for _ in range(100)])
+assert ms.search(flat, off)[0].size == 100
 # suffix arrays
 for n, sigma in ((1, 4), (50, 2), (30_000, 4), (20_000, 256)):
     text = rng.integers(0, sigma, n, dtype=np.uint8)
