@@ -518,7 +518,7 @@ bk_part_kernel(const PartParams p) {
 // ctrl[0] = work counter, ctrl[1] = number of items.  One CTA per bucket: thread i owns a contiguous span of the bucket's
 // tiles (all of its descriptor loads are in flight at once), a block scan gives the span's query prefix.
 constexpr int kPlanThreads = 256;
-__global__ void __launch_bounds__(kPlanThreads)
+__global__ void __launch_bounds__(kPlanThreads, 8)
 bk_items_kernel(const uint32_t* __restrict__ runs, const uint32_t* __restrict__ tot, unsigned ntiles, unsigned ntp, unsigned nb,
                 unsigned chunk_log2, uint4* __restrict__ items, unsigned* __restrict__ ctrl) {
     __shared__ unsigned s_warp[kPlanThreads / 32 + 1];
@@ -538,13 +538,12 @@ bk_items_kernel(const uint32_t* __restrict__ runs, const uint32_t* __restrict__ 
     constexpr unsigned kSpanMax = 40;  // tiles per thread: 2^27 / kTile / kPlanThreads = 32, rounded up generously
     const unsigned span = (ntiles + kPlanThreads - 1) / kPlanThreads;  // <= kSpanMax
     const unsigned t_begin = min(ntiles, tid * span), t_end = min(ntiles, t_begin + span);
-    unsigned c[kSpanMax];
+    // (two passes over the span: the counts are read again after the scan -- L1 / L2 hits -- instead of being held in 40
+    // registers, which had limited the kernel to two CTAs per SM: 3.5 waves of CTAs, 27 us; now one wave)
     unsigned sum = 0;
-#pragma unroll
-    for (unsigned j = 0; j < kSpanMax; j++) {
-        c[j] = t_begin + j < t_end ? __ldg(row + t_begin + j) >> kRunShift : 0u;
-        sum += c[j];
-    }
+#pragma unroll 8
+    for (unsigned j = 0; j < kSpanMax; j++)
+        if (t_begin + j < t_end) sum += __ldg(row + t_begin + j) >> kRunShift;
     unsigned total;
     unsigned e = block_excl_scan(sum, s_warp, &total);  // queries of the bucket in earlier tiles
     // the item of the tile before this span (0xffffffff at the very start): the last tile of the previous span with the same rule
@@ -553,7 +552,7 @@ bk_items_kernel(const uint32_t* __restrict__ runs, const uint32_t* __restrict__ 
         // exclusive prefix of tile t_begin - 1 = e - count(t_begin - 1)
         prev = (e - (__ldg(row + t_begin - 1) >> kRunShift)) >> chunk_log2;
     }
-#pragma unroll
+#pragma unroll 4
     for (unsigned j = 0; j < kSpanMax; j++)
         if (t_begin + j < t_end) {
             const unsigned item = e >> chunk_log2;
@@ -562,7 +561,7 @@ bk_items_kernel(const uint32_t* __restrict__ runs, const uint32_t* __restrict__ 
                 if (prev != 0xffffffffu) items[ibase + prev].z = t_begin + j;
             }
             prev = item;
-            e += c[j];
+            e += __ldg(row + t_begin + j) >> kRunShift;
             if (t_begin + j == ntiles - 1) items[ibase + item].z = ntiles;
         }
 }
