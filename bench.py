@@ -466,6 +466,34 @@ def run_own(args):
                "sample": f"first {sample} queries of the step's batch over the full {n}-key tree; oracle {best} (AVX2={bool(O.lib().orc_has_avx2())}) on {threads} threads; results equal the GPU's"}
         del ot
 
+    # ---- configs C1 / C2: the size sweep 2^10 .. 2^26 keys (2^20 = C1, the reference's own CPU-runnable case) at the step's
+    # batch size, SCHEME_AUTO, one GPU (rank 0 at N = 1); 2^28 is the headline above and 2^30 the c4 block below.  Every size is
+    # checked exactly on the host on a sample (keys[idx-1] < q <= keys[idx], value == keys[idx]).
+    c2 = None
+    if rank == 0 and world == 1 and args.c2_sizes:
+        c2 = {"config": "C2 (2^20 = C1)", "queries": e - s, "unit": UNIT, "scheme": "auto", "sizes": {}, "ok": True}
+        rng = np.random.default_rng(args.seed + 9)
+        for lg in [int(x) for x in args.c2_sizes.split(",") if x]:
+            m = 1 << lg
+            gk = torch.Generator(device=dev).manual_seed(args.seed + lg)
+            k2 = torch.randint(0, MAX, (m,), dtype=torch.int32, device=dev, generator=gk)
+            k2[0] = MAX
+            k2 = torch.sort(k2).values.contiguous()
+            t2 = sst.STree16.new_params(k2, True, False, False)
+            ms2 = L.sst_time_query_device(t2._h, C.c_void_p(batches[0].data_ptr()), e - s, C.c_void_p(out_v.data_ptr()), None, args.scheme, 2, 5)
+            sel = torch.from_numpy(rng.integers(0, e - s, min(args.parity_sample, e - s))).to(dev)
+            v2, i2s = t2.query(batches[0][sel].contiguous(), want_index=True)
+            bad = check_lower_bound_sample(batches[0][sel].cpu().numpy().view(np.uint32), v2.cpu().numpy().view(np.uint32), i2s.cpu().numpy().astype(np.uint64),
+                                           k2[(i2s - 1).clamp(min=0)].cpu().numpy().view(np.uint32), k2[i2s.clamp(max=m - 1)].cpu().numpy().view(np.uint32), m)
+            same = bool((out_v[sel] == v2).all())  # the timed pass (large batch) returned the sampled pass's values
+            sch2 = C.c_int(0)
+            L.sst_query_plan(t2._h, e - s, args.scheme, 0, C.byref(sch2), None)
+            c2["sizes"][f"2^{lg}"] = {"queries_per_s": (e - s) / (ms2 * 1e-3), "ms": ms2, "levels": t2.layers(), "kernel": scheme_names.get(sch2.value, str(sch2.value)),
+                                     "ok": bad == 0 and same}
+            c2["ok"] = c2["ok"] and bad == 0 and same
+            del t2, k2
+        ok = ok and c2["ok"]
+
     # ---- GPU baseline the reference's headline is about: plain binary search on the same device ----
     baselines = None
     if rank == 0:
@@ -543,6 +571,8 @@ def run_own(args):
         }
         if baselines is not None:
             line["baselines"] = baselines
+        if c2 is not None:
+            line["c2"] = c2
         line.update(extra)
         emit_line(line)
     if dist is not None:
@@ -885,6 +915,7 @@ def main():
     ap.add_argument("--sa-text", type=int, default=100_000_000, help="0 disables the secondary SA metric")
     ap.add_argument("--sa-patterns", type=int, default=10_000_000)
     ap.add_argument("--sa-cpu-sample", type=int, default=2_000_000, help="patterns of the CPU SA baseline sample")
+    ap.add_argument("--c2-sizes", default="10,14,18,20,22,24,26", help="log2 key counts of the C1 / C2 size sweep (N = 1 only; empty disables it)")
     ap.add_argument("--sa-rep-text", type=int, default=100_000_000, help="repetitive-text SA block: text length (0 disables it)")
     ap.add_argument("--sa-rep-patterns", type=int, default=200_000, help="repetitive-text SA block: patterns (length 200..2000) in total")
     ap.add_argument("--c4-log2-keys", type=int, default=30, help="config C4: log2 of the key count (0 disables the block)")

@@ -14,7 +14,7 @@ def test_bench_line_contract(gpu):
     out = subprocess.run(
         [sys.executable, os.path.join(ROOT, "bench.py"), "--n-keys", str(1 << 22), "--queries", str(1 << 22), "--steps", "3", "--warmup", "3",
          "--cpu-sample", str(1 << 20), "--sa-text", "400000", "--sa-patterns", "20000", "--e2e-steps", "2",
-         "--sa-rep-text", "2000000", "--sa-rep-patterns", "3000", "--c4-log2-keys", "23", "--c4-queries", "5000000", "--c5-text", "3000000", "--c5-patterns", "200000", "--c-reps", "2", "--parity-sample", "2000"],
+         "--c2-sizes", "10,16", "--sa-rep-text", "2000000", "--sa-rep-patterns", "3000", "--c4-log2-keys", "23", "--c4-queries", "5000000", "--c5-text", "3000000", "--c5-patterns", "200000", "--c-reps", "2", "--parity-sample", "2000"],
         capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-3000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
@@ -33,6 +33,7 @@ def test_bench_line_contract(gpu):
     assert d["sa"]["binary_ok"] and d["sa"]["mlr_ok"] and d["sa"]["mlr_equals_binary"] and d["sa"]["sa_check_violations"] == 0
     assert d["sa"]["cpu_baseline"]["equals_gpu"] and d["sa"]["ok"] and d["sa"]["e2e"]["equals_device_path"]
     assert "workload" in d["config"]
+    assert d["c2"]["ok"] and set(d["c2"]["sizes"]) == {"2^10", "2^16"} and all(v["queries_per_s"] > 0 for v in d["c2"]["sizes"].values())
     rep = d["sa_repetitive"]
     assert rep["ok"] and rep["binary_ok"] and rep["mlr_ok"] and rep["mlr_equals_binary"] and rep["pattern_len"] == [200, 2000]
     # BASELINE configs C4 / C5 ride in the same line, each with an exact host-side parity sample that gates the exit code
@@ -49,7 +50,7 @@ def test_bench_line_bucketed(gpu):
     """A configuration large enough for SCHEME_AUTO to take the reordered-batch pipeline: 4 launches per step, stage times."""
     out = subprocess.run(
         [sys.executable, os.path.join(ROOT, "bench.py"), "--n-keys", str(1 << 27), "--queries", str(1 << 24), "--steps", "2", "--warmup", "3",
-         "--no-cpu", "--sa-text", "0", "--e2e-steps", "1", "--c4-log2-keys", "0", "--c5-text", "0", "--sa-rep-text", "0"],
+         "--no-cpu", "--sa-text", "0", "--e2e-steps", "1", "--c4-log2-keys", "0", "--c5-text", "0", "--sa-rep-text", "0", "--c2-sizes", ""],
         capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-3000:]
     d = json.loads([l for l in out.stdout.splitlines() if l.strip()][-1])
