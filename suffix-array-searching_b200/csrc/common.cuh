@@ -89,6 +89,8 @@ unsigned cur_sms();                   // sm_count of the calling thread's curren
     X(SA_USE_LEVELS, 64, 0, 64)                                                                                              \
     X(SA_USE_KMER, 1, 0, 1)                                                                                                  \
     X(SA_USE_INLINE, 1, 0, 1)                                                                                                \
+    X(SA_CELLS, 1, 0, 1)                 /* build the packed 64-byte k-mer cells (range + first five entries in one line) */ \
+    X(SA_USE_CELLS, 1, 0, 1)             /* use them */ \
     X(SA_LANES, 1, 1, 32)                                                                                                    \
     X(SA_SORT_LEVELS, 12, 0, 30)                                                                                             \
     X(SA_SORT_MIN, -1, -1, 1ll << 62)    /* batches of at least this many patterns search in sorted order; -1 = never */      \

@@ -63,6 +63,13 @@ struct sst_sa {
     // The same with 32 bases per suffix in 16-byte entries {sa, bases present (32 = all), code hi, code lo}, built instead of
     // d_sax when memory allows (16 bytes per suffix): a pattern of up to k + 32 bases is then answered without the text.
     uint4* d_saw = nullptr;
+    // Packed k-mer cells (with d_saw, k <= 14, n < 2^31, memory permitting): 128 bytes per cell = {start | overflow << 31, entries
+    // 0..4} {-, entries 5..9}, an entry = {sa, code hi, code lo} -- the cell's suffix-array range AND its first ten {sa, 32 bases}
+    // entries in ONE line, so that a pattern of k .. k + 31 bases is answered by a single random DRAM access instead of two (k-mer
+    // cell, then the entries); the second half is read (an L2 hit) only when the first five entries do not decide.  Unused
+    // entries have sa = 0xffffffff; a cell with more than ten suffixes, or with a suffix too close to the text's end to have
+    // all 32 bases, is flagged and takes the ordinary path.  GPU-only auxiliary; no result depends on it.
+    uint4* d_cells = nullptr;
 };
 
 namespace sst {
@@ -226,6 +233,7 @@ struct SaParams {
     int kmer_k;
     const uint2* sax;      // {sa, next 15 bases} entries (or null)
     const uint4* saw;      // {sa, 32, next 32 bases} entries (or null; the WIDE kernels)
+    const uint4* cells;    // packed k-mer cells, 4 x uint4 each (or null)
     uint32_t* out_probes;  // sa_search_kernel only: iterations of the reference's loop (its `cnt`, sa_search.rs:98-112), or null
 };
 
@@ -381,6 +389,13 @@ __device__ __forceinline__ uint4 ldr(const uint4* p) {
 #endif
 }
 
+// (the packed k-mer cells are 128 bytes: ask L2 for the whole line, the second half is read only by crowded cells)
+__device__ __forceinline__ uint4 ldc128(const uint4* p) {
+    uint4 v;
+    asm("ld.global.nc.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 struct W4 { uint32_t w[4]; };
 
 // 16 bytes starting at byte address `addr` (little endian words); aligned 16-byte chunks starting
@@ -469,12 +484,10 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
         const uint8_t* pat = p.pats + po;
         const uint8_t* pend = p.pats + p.pats_bytes;
         const W4 p0 = load16_unaligned<true>(pat, pend), p1 = load16_unaligned<true>(pat + 16, pend);
-        uint32_t l = 0, r = (uint32_t)p.n;  // n < 2^32 - 16: all search state fits 32 bits
-        uint32_t lcp_l = 0, lcp_r = 0;
-        bool lcp_r_exact = false;  // lcp_r == lcp(q, suffix(r)) exactly (not a conservative bound)
         // ---- k-mer table: the first k bases select the suffix-array range directly (one load instead of ~2k probes) ----
         bool have_range = false;
         uint32_t range_end = (uint32_t)p.n;  // no suffix from here on starts with q (bounds the search for hi)
+        uint32_t kx = 0;                     // 2-bit code of the pattern's first k bases (padded with the smallest base)
         if (PHASE != 1 && p.kmer_k) {
             const int k = p.kmer_k;  // <= 16: the bases sit in p0
             uint32_t x = 0;
@@ -487,24 +500,8 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
                     dna = dna && (!in || b < 4u);
                     x = x * 4u + (in ? (b & 3u) : 0u);  // a pattern shorter than k is padded with the smallest base
                 }
-            if (dna) {
-                have_range = true;
-                if (ql >= (uint32_t)k) {
-                    l = ldr(p.kmer + x);
-                    r = ldr(p.kmer + (size_t)x + 1);
-                    range_end = r;  // every suffix that starts with q starts with its first k bases
-                    // every suffix of the cell that has k bases shares them with the pattern: both LCP bounds start at k instead of
-                    // 0 (lower bounds, not exact values: lcp_r_exact stays false).  One of the text's last < k suffixes can sit in
-                    // the cell without sharing them (AAC lies between AAAT and AACA); thread_compare starts such a suffix,
-                    // which is shorter than the assumed common prefix, at byte 0.
-                    if (MLR) lcp_l = lcp_r = (uint32_t)k;
-                } else {
-                    // every suffix from kmer[x] on is >= q000.. >= q; the only suffixes below it that are >= q are proper
-                    // prefixes of q000.. (the last < k suffixes of the text): search the k positions before it
-                    r = ldr(p.kmer + x);
-                    l = r > (uint32_t)k ? r - (uint32_t)k : 0u;
-                }
-            }
+            have_range = dna;
+            kx = x;
         }
         // ---- inlined bases: inside the k-mer cell a probe reads {sa[m], the 15 bases after the first k} and goes to the text
         // only when those 15 bases equal the pattern's (the suffix that matches, if any) ----
@@ -543,6 +540,72 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
                 pq = (uint32_t)(code >> (2 * (32 - p.kmer_k - 15))) & pmask;
             }
             inl = bad == 0u;
+        }
+        // ---- packed cell: range and entries of the pattern's k-mer in one 64-byte line; a pattern that ends within the inlined
+        // bases is answered from it alone when the cell is not flagged (one random DRAM access per pattern instead of two) ----
+        if constexpr (WIDE && PHASE == 0) {
+            if (p.cells && inl && pat_ends) {
+                const uint4* c = p.cells + (size_t)kx * 8;
+                uint4 c0 = ldc128(c), c1 = ldc128(c + 1), c2 = ldc128(c + 2), c3 = ldc128(c + 3);  // first half: start + entries 0..4
+                if (!(c0.x & 0x80000000u)) {
+                    const uint32_t start = c0.x;
+                    unsigned below = 0, equal = 0, cnt = 0;
+                    uint32_t sp = 0xffffffffu;  // sa of entry number `below` (the lower bound), once seen
+                    // five entries {sa, code hi, code lo} in words 1..15 of a half; an entry with sa = 0xffffffff is unused
+                    auto half = [&](unsigned base) {
+                        const uint32_t es[5] = {c0.y, c1.x, c1.w, c2.z, c3.y};
+                        const unsigned long long ec[5] = {((unsigned long long)c0.z << 32) | c0.w, ((unsigned long long)c1.y << 32) | c1.z,
+                                                          ((unsigned long long)c2.x << 32) | c2.y, ((unsigned long long)c2.w << 32) | c3.x,
+                                                          ((unsigned long long)c3.z << 32) | c3.w};
+                        const unsigned below0 = below;
+#pragma unroll
+                        for (int e = 0; e < 5; e++) {
+                            const bool valid = es[e] != 0xffffffffu;
+                            const unsigned long long cm = ec[e] & pmask;
+                            cnt += valid ? 1u : 0u;
+                            below += valid && cm < pq ? 1u : 0u;   // shares the first k bases, the next ones are smaller: suffix < q
+                            equal += valid && cm == pq ? 1u : 0u;  // every base of the pattern matches: the suffix starts with q
+                        }
+#pragma unroll
+                        for (int e = 0; e < 5; e++)  // (entries are sorted: `below` only grows while it equals the entries seen)
+                            if (below == base + (unsigned)e && below0 <= base + (unsigned)e) sp = es[e];
+                    };
+                    half(0u);
+                    if (cnt == 5u && below + equal == 5u) {  // all five are < q or start with q: the cell may hold more of either kind
+                        c0 = ldc128(c + 4); c1 = ldc128(c + 5); c2 = ldc128(c + 6); c3 = ldc128(c + 7);  // entries 5..9 (word 0 of this half is unused)
+                        half(5u);
+                    }
+                    const uint32_t lo = start + below;
+                    p.out_lo[i] = lo;
+                    if (p.out_hi) p.out_hi[i] = lo + equal;
+                    if (p.out_pos) {
+                        if (below >= cnt) sp = lo < p.n ? ldr(p.sa + lo) : 0xffffffffu;  // first suffix of a later cell
+                        p.out_pos[i] = sp;
+                    }
+                    continue;
+                }
+            }
+        }
+        uint32_t l = 0, r = (uint32_t)p.n;  // n < 2^32 - 16: all search state fits 32 bits
+        uint32_t lcp_l = 0, lcp_r = 0;
+        bool lcp_r_exact = false;  // lcp_r == lcp(q, suffix(r)) exactly (not a conservative bound)
+        if (have_range) {
+            const int k = p.kmer_k;
+            if (ql >= (uint32_t)k) {
+                l = ldr(p.kmer + kx);
+                r = ldr(p.kmer + (size_t)kx + 1);
+                range_end = r;  // every suffix that starts with q starts with its first k bases
+                // every suffix of the cell that has k bases shares them with the pattern: both LCP bounds start at k instead of
+                // 0 (lower bounds, not exact values: lcp_r_exact stays false).  One of the text's last < k suffixes can sit in
+                // the cell without sharing them (AAC lies between AAAT and AACA); thread_compare starts such a suffix,
+                // which is shorter than the assumed common prefix, at byte 0.
+                if (MLR) lcp_l = lcp_r = (uint32_t)k;
+            } else {
+                // every suffix from kmer[x] on is >= q000.. >= q; the only suffixes below it that are >= q are proper
+                // prefixes of q000.. (the last < k suffixes of the text): search the k positions before it
+                r = ldr(p.kmer + kx);
+                l = r > (uint32_t)k ? r - (uint32_t)k : 0u;
+            }
         }
         // suffix(sa[m]) vs the pattern: lcp and order, through the inlined bases where they decide
         auto probe = [&](uint32_t m, uint32_t start, bool& less) -> uint32_t {
@@ -713,6 +776,7 @@ using namespace sst;
 
 static bool build_kmer(sst_sa* s);  // defined after sa_search_launch, which it uses to fill the table
 static bool build_sax(sst_sa* s);
+static bool build_cells(sst_sa* s);
 
 extern "C" {
 
@@ -730,8 +794,8 @@ sst_sa_t* sst_sa_build_device(const uint8_t* d_text, size_t n, int device) {
     cudaStream_t st = thread_stream(device);
     ok = ok && SST_CUDA_OK(cudaMemsetAsync(s->d_text + n, 0, 64, st)) &&
          SST_CUDA_OK(cudaMemcpyAsync(s->d_text, d_text, n, cudaMemcpyDeviceToDevice, st));
-    ok = ok && build_sa_device(s->d_text, n, s->d_sa, device) && build_pivots(s) && build_kmer(s) && build_sax(s);
-    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); cudaFree(s->d_sax); cudaFree(s->d_saw); delete s; return nullptr; }
+    ok = ok && build_sa_device(s->d_text, n, s->d_sa, device) && build_pivots(s) && build_kmer(s) && build_sax(s) && build_cells(s);
+    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); cudaFree(s->d_sax); cudaFree(s->d_saw); cudaFree(s->d_cells); delete s; return nullptr; }
     return s;
 }
 
@@ -775,8 +839,8 @@ sst_sa_t* sst_sa_from_parts(const uint8_t* text, size_t n, const uint32_t* sa, i
             ok = false;
         }
     }
-    ok = ok && build_pivots(s) && build_kmer(s) && build_sax(s);
-    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); cudaFree(s->d_sax); cudaFree(s->d_saw); delete s; return nullptr; }
+    ok = ok && build_pivots(s) && build_kmer(s) && build_sax(s) && build_cells(s);
+    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); cudaFree(s->d_sax); cudaFree(s->d_saw); cudaFree(s->d_cells); delete s; return nullptr; }
     return s;
 }
 
@@ -789,6 +853,7 @@ void sst_sa_free(sst_sa_t* s) {
     cudaFree(s->d_kmer);
     cudaFree(s->d_sax);
     cudaFree(s->d_saw);
+    cudaFree(s->d_cells);
     delete s;
 }
 
@@ -903,6 +968,7 @@ static int sa_search_launch(const sst_sa_t* s, const uint8_t* d_pats, const uint
     p.kmer_k = s->d_kmer && opt(OPT_SA_USE_KMER) ? s->kmer_k : 0;
     p.sax = p.kmer_k && opt(OPT_SA_USE_INLINE) ? s->d_sax : nullptr;
     p.saw = p.kmer_k && opt(OPT_SA_USE_INLINE) ? s->d_saw : nullptr;
+    p.cells = p.saw && opt(OPT_SA_USE_CELLS) ? s->d_cells : nullptr;
     const int lanes = (int)opt(OPT_SA_LANES);
     if (lanes <= 1) {
         const unsigned grid = (unsigned)std::min<unsigned long long>((npat + kThreads - 1) / kThreads, (unsigned long long)sm_count(s->device) * 8);
@@ -1009,6 +1075,51 @@ __global__ void saw_kernel(const uint8_t* __restrict__ t, const uint32_t* __rest
 }  // namespace
 }  // namespace sst
 
+namespace sst {
+namespace {
+// cells[x] (128 bytes) = {start | overflow << 31, entries 0..4} {unused word, entries 5..9}, an entry = {sa, code hi, code lo},
+// from the k-mer table and the 32-base entries (see sst_sa::d_cells)
+__global__ void cells_kernel(const uint32_t* __restrict__ kmer, const uint4* __restrict__ saw, unsigned long long ncells, uint4* __restrict__ cells) {
+    for (unsigned long long x = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; x < ncells; x += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t start = kmer[x], cnt = kmer[x + 1] - start;
+        bool overflow = cnt > 10u;
+        uint4* c = cells + x * 8;
+        for (uint32_t h = 0; h < 2u; h++) {
+            uint32_t w[16];
+            for (int i = 0; i < 16; i++) w[i] = 0xffffffffu;
+            for (uint32_t i = 0; i < 5u && 5u * h + i < cnt; i++) {
+                const uint4 e = saw[(size_t)start + 5u * h + i];
+                overflow = overflow || e.y != 32u;  // a suffix without all 32 bases (the text's last k + 31): ordinary path
+                w[1 + 3 * i] = e.x; w[2 + 3 * i] = e.z; w[3 + 3 * i] = e.w;
+            }
+            if (h == 0) w[0] = start;
+            c[4 * h + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+            c[4 * h + 2] = make_uint4(w[8], w[9], w[10], w[11]);
+            c[4 * h + 3] = make_uint4(w[12], w[13], w[14], w[15]);
+            if (h == 1) c[4] = make_uint4(w[0], w[1], w[2], w[3]);
+            else c[0] = make_uint4(w[0], w[1], w[2], w[3]);  // (the flag is added below, once the second half has been seen)
+        }
+        if (overflow) reinterpret_cast<uint32_t*>(c)[0] = start | 0x80000000u;
+    }
+}
+}  // namespace
+}  // namespace sst
+
+// Packed k-mer cells: only next to the 32-base entries, for k <= 14 (128 bytes x 4^k: 8.6 GB at k = 13), texts below 2^31 bytes
+// (bit 31 of the start is the flag) and within a quarter of the free memory; an optional accelerator like the others.
+static bool build_cells(sst_sa* s) {
+    if (!s->d_saw || !s->kmer_k || s->kmer_k > 14 || s->n >= (1ull << 31) || !opt(OPT_SA_CELLS)) return true;
+    const unsigned long long ncells = 1ull << (2 * s->kmer_k);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (ncells * 128ull > free_b / 4) return true;
+    if (cudaMalloc(&s->d_cells, ncells * 128ull) != cudaSuccess) { s->d_cells = nullptr; (void)cudaGetLastError(); return true; }
+    cudaStream_t st = thread_stream(s->device);
+    cells_kernel<<<sm_count(s->device) * 16, 256, 0, st>>>(s->d_kmer, s->d_saw, ncells, s->d_cells);
+    if (!SST_CUDA_OK(cudaGetLastError()) || !SST_CUDA_OK(cudaStreamSynchronize(st))) { cudaFree(s->d_cells); s->d_cells = nullptr; return false; }
+    return true;
+}
+
 static bool build_sax(sst_sa* s) {
     if (!s->kmer_k || !opt(OPT_SA_INLINE)) return true;
     size_t free_b = 0, total_b = 0;
@@ -1104,8 +1215,9 @@ sst_sa* clone_sa(const sst_sa* src, int device) {
     if (src->kmer_k) copy(s->d_kmer, src->d_kmer, ((1ull << (2 * src->kmer_k)) + 1) * 4);
     copy(s->d_sax, src->d_sax, s->n * sizeof(uint2));
     copy(s->d_saw, src->d_saw, s->n * sizeof(uint4));
+    if (src->d_cells) copy(s->d_cells, src->d_cells, (1ull << (2 * src->kmer_k)) * 128ull);
     ok = ok && SST_CUDA_OK(cudaStreamSynchronize(st));
-    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); cudaFree(s->d_sax); cudaFree(s->d_saw); delete s; return nullptr; }
+    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); cudaFree(s->d_sax); cudaFree(s->d_saw); cudaFree(s->d_cells); delete s; return nullptr; }
     return s;
 }
 }  // namespace sst

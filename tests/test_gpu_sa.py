@@ -188,9 +188,39 @@ def test_sa_search_kmer_table(gpu, oracle, n, k, inline_bases, monkeypatch):
     for at in (33, 36, 44, 47, 48, 50):  # a byte outside the alphabet in the third 16-byte window
         pats += [head[900:900 + at] + bytes([9]) + head[901 + at:970], head[900:900 + at] + bytes([200])]
     _check_search(sst, oracle, s, text, sa, pats)
+    gpu.set_option("SA_USE_CELLS", 0)   # without the packed 64-byte cells (range + first five entries in one line)
+    _check_search(sst, oracle, s, text, sa, pats[:3000] + pats[-200:])
+    gpu.set_option("SA_USE_CELLS", 1)
     gpu.set_option("SA_USE_INLINE", 0)  # k-mer table, probes on the text
     _check_search(sst, oracle, s, text, sa, pats[:3000] + pats[-60:])
     gpu.set_option("SA_USE_INLINE", 1)
     # the same through the pivot table only
     gpu.set_option("SA_USE_KMER", 0)
     _check_search(sst, oracle, s, text, sa, pats[:2000])
+
+
+@pytest.mark.parametrize("n,k", [(300_000, 7), (300_000, 9), (50_000, 8), (2_000_000, 10)])
+def test_sa_packed_cells(gpu, oracle, n, k):
+    """Packed k-mer cells: patterns of k .. k + 31 bases are answered from one 64-byte line {start, 5 x {sa, 32 bases}}.  Shallow
+    tables (many suffixes per cell: most cells flagged), deep ones (most cells with 0..5 suffixes), repeats (cells with many
+    equal entries: hi - lo up to 5), absent patterns that fall behind every entry of their cell, the text's tail."""
+    sst = gpu
+    gpu.set_option("SA_KMER_K", k)
+    rng = np.random.default_rng(n + k)
+    text = random_text(n, seed=n + k)
+    text[1000:1200] = np.tile(text[1000:1050], 4)  # a few repeated 50-mers
+    s = sst.SaNaive.build(text)
+    sa = s.sa
+    head = text.tobytes()
+    pats = [head[i:i + int(l)] for i, l in zip(rng.integers(0, n - 100, 4000), rng.integers(k, k + 34, 4000))]          # occur
+    pats += [bytes(rng.integers(0, 4, int(l), dtype=np.uint8)) for l in rng.integers(k, k + 33, 3000)]                     # mostly absent
+    pats += [head[i:i + k] + bytes([3] * int(l)) for i, l in zip(rng.integers(0, n - 100, 500), rng.integers(0, 30, 500))]  # behind their cell's entries
+    pats += [head[i:i + k] + bytes([0] * int(l)) for i, l in zip(rng.integers(0, n - 100, 500), rng.integers(0, 30, 500))]  # before them
+    pats += [head[1000:1000 + l] for l in range(k, 50)] + [head[-j:] for j in range(k, k + 40)]
+    _check_search(sst, oracle, s, text, sa, pats)
+    gpu.set_option("SA_USE_CELLS", 0)
+    flat, off = sst.pack_patterns(pats)
+    a = s.search(flat, off)
+    gpu.set_option("SA_USE_CELLS", 1)
+    b = s.search(flat, off)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))

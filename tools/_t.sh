@@ -1,5 +1,4 @@
 cd $GRAFT_REPO_ROOT
-python -m pytest tests/test_gpu_bench.py -x -q -m gpu 2>&1 | tail -5
-python bench.py --no-cpu --c4-log2-keys 0 --c5-text 0 --no-e2e --steps 3 --sa-text 0 --sa-rep-text 0 2>/dev/null | python -c "
-import sys, json
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(json.dumps(d['c2'])[:1500])"
+python -m pytest tests/test_gpu_sa.py tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -8
+TAG=cells python tools/sa_bench.py 2>&1 | tail -2
+SST_SA_USE_CELLS=0 TAG=nocells python tools/sa_bench.py 2>&1 | tail -2
