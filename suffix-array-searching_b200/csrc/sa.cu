@@ -1000,7 +1000,9 @@ static int sa_search_launch(const sst_sa_t* s, const uint8_t* d_pats, const uint
         }
         if (p.saw) {
             // patterns of up to k + 32 bases never touch the text: a batch of mostly such patterns takes the spill-free build
-            const bool short_pats = opt(OPT_SA_MINB) ? opt(OPT_SA_MINB) == 4 : pats_end <= 48ull * npat;
+            // ... unless the packed cells answer them with one access: then more resident blocks win again (C3 with the cells: 4 blocks
+            // of 256 threads per SM 15.5, 5: 16.7-17.2, 6: 17.0, 8: 13.6 Gpat/s)
+            const bool short_pats = opt(OPT_SA_MINB) ? opt(OPT_SA_MINB) == 4 : (pats_end <= 48ull * npat && !p.cells);
             if (short_pats) {
                 if (mode == SST_SA_MLR) sa_search_thread_kernel<true, 0, true, 4><<<grid, kThreads, 0, st>>>(p);
                 else sa_search_thread_kernel<false, 0, true, 4><<<grid, kThreads, 0, st>>>(p);

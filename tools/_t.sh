@@ -1,4 +1,2 @@
 cd $GRAFT_REPO_ROOT
-python -m pytest tests/test_gpu_sa.py tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -8
-TAG=cells python tools/sa_bench.py 2>&1 | tail -2
-SST_SA_USE_CELLS=0 TAG=nocells python tools/sa_bench.py 2>&1 | tail -2
+for mb in 0 4 5 0 5; do SST_SA_MINB=$mb TAG=minb$mb python tools/sa_bench.py 2>&1 | tail -2 | head -1 | cut -c1-160; done
