@@ -44,7 +44,6 @@ constexpr int kBtShift = 18;                 // bucket table over the top 13 bit
 constexpr int kBtCells = 1 << (31 - kBtShift);
 constexpr int kBtStride = kBtCells + 8;
 constexpr unsigned kMinChunk = 16384;        // queries per search work item: at least this many (scratch sizing)
-constexpr size_t kSubBatch = (size_t)1 << 27;  // queries per pipeline run (bounds the scratch buffers)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
@@ -257,6 +256,8 @@ struct BkSearchParams {
     const uint2* meta;       // [nb] {lo, shift}
     const uint32_t* leaf;    // sorted keys (leaf level of the image, MAX-padded)
     unsigned r;              // half nodes (separators) per bucket
+    const uint16_t* sep16;   // 16-bit mode: [nb * r] offsets of the separators inside their jump cells (sep is unused then)
+    unsigned cells;          // jump cells per bucket (r, or r / 2 in 16-bit mode): jump has cells + 8 entries per bucket
     unsigned long long m8;   // blocks of G keys (half nodes / nodes) that hold keys
     unsigned long long n;
 };
@@ -535,15 +536,13 @@ bk_items_kernel(const uint32_t* __restrict__ runs, const uint32_t* __restrict__ 
     for (unsigned k = tid; k < nmine; k += kPlanThreads) items[ibase + k] = make_uint4(b, 0, 0, 0);
     __syncthreads();  // (also: s_warp may be reused)
     const uint32_t* row = runs + (size_t)b * ntp;
-    constexpr unsigned kSpanMax = 40;  // tiles per thread: 2^27 / kTile / kPlanThreads = 32, rounded up generously
-    const unsigned span = (ntiles + kPlanThreads - 1) / kPlanThreads;  // <= kSpanMax
+    const unsigned span = (ntiles + kPlanThreads - 1) / kPlanThreads;  // tiles per thread: 24 at 10^8 queries, 256 at 2^30
     const unsigned t_begin = min(ntiles, tid * span), t_end = min(ntiles, t_begin + span);
-    // (two passes over the span: the counts are read again after the scan -- L1 / L2 hits -- instead of being held in 40
+    // (two passes over the span: the counts are read again after the scan -- L1 / L2 hits -- instead of being held in
     // registers, which had limited the kernel to two CTAs per SM: 3.5 waves of CTAs, 27 us; now one wave)
     unsigned sum = 0;
 #pragma unroll 8
-    for (unsigned j = 0; j < kSpanMax; j++)
-        if (t_begin + j < t_end) sum += __ldg(row + t_begin + j) >> kRunShift;
+    for (unsigned t = t_begin; t < t_end; t++) sum += __ldg(row + t) >> kRunShift;
     unsigned total;
     unsigned e = block_excl_scan(sum, s_warp, &total);  // queries of the bucket in earlier tiles
     // the item of the tile before this span (0xffffffff at the very start): the last tile of the previous span with the same rule
@@ -553,17 +552,16 @@ bk_items_kernel(const uint32_t* __restrict__ runs, const uint32_t* __restrict__ 
         prev = (e - (__ldg(row + t_begin - 1) >> kRunShift)) >> chunk_log2;
     }
 #pragma unroll 4
-    for (unsigned j = 0; j < kSpanMax; j++)
-        if (t_begin + j < t_end) {
-            const unsigned item = e >> chunk_log2;
-            if (item != prev) {
-                items[ibase + item].y = t_begin + j;
-                if (prev != 0xffffffffu) items[ibase + prev].z = t_begin + j;
-            }
-            prev = item;
-            e += __ldg(row + t_begin + j) >> kRunShift;
-            if (t_begin + j == ntiles - 1) items[ibase + item].z = ntiles;
+    for (unsigned t = t_begin; t < t_end; t++) {
+        const unsigned item = e >> chunk_log2;
+        if (item != prev) {
+            items[ibase + item].y = t;
+            if (prev != 0xffffffffu) items[ibase + prev].z = t;
         }
+        prev = item;
+        e += __ldg(row + t) >> kRunShift;
+        if (t == ntiles - 1) items[ibase + item].z = ntiles;
+    }
 }
 
 // ---- search over runs, in place --------------------------------------------------------------------
@@ -579,15 +577,16 @@ bk_items_kernel(const uint32_t* __restrict__ runs, const uint32_t* __restrict__ 
 //   * the first warp that finishes an item fetches the next work item (atomic counter, item record, bucket record) into
 //     shared memory, so that after the barrier the bulk copies start at once, and every warp sets up its first group and
 //     loads its first queries of the new item BEFORE it waits for the copies.
-template <bool WANT_IDX, int G>
+template <bool WANT_IDX, int G, bool S16>
 __global__ void __launch_bounds__(kSThreads, 1)
 bk_search2_kernel(const BkSearchParams p, uint32_t* __restrict__ qsort, uint32_t* __restrict__ isort, const uint32_t* __restrict__ runs,
                   unsigned ntp, const uint4* __restrict__ items, unsigned* __restrict__ ctrl) {
     constexpr int U = (G == 8 ? 4 : 2) * (1024 / kSThreads);
     constexpr unsigned kSWarps = kSThreads / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint32_t* s_sep = reinterpret_cast<uint32_t*>(smem_raw);                 // [r]
-    uint16_t* s_jump = reinterpret_cast<uint16_t*>(s_sep + p.r);              // [r + 8]
+    // separators: [r] u32, or in 16-bit mode [r] u16 (read as pairs); then the jump table [cells + 8] u16
+    uint32_t* s_sep = reinterpret_cast<uint32_t*>(smem_raw);
+    uint16_t* s_jump = reinterpret_cast<uint16_t*>(smem_raw + (size_t)p.r * (S16 ? 2u : 4u));
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint4 s_it[2];      // the work item of this / the next iteration: {bucket, first tile, end tile, item number}
     __shared__ uint2 s_meta[2];    // its bucket record {lo, shift}
@@ -636,12 +635,13 @@ bk_search2_kernel(const BkSearchParams p, uint32_t* __restrict__ qsort, uint32_t
         if (tid == 0) {
             s_done = 0;  // (every warp passes the barrier above before it can finish this item)
             if (stage) {  // 1-D TMA bulk copies (SASS UBLKCP), completion on the mbarrier
-                const unsigned sep_bytes = p.r * 4u, jump_bytes = (p.r + 8u) * 2u;
+                const unsigned sep_bytes = p.r * (S16 ? 2u : 4u), jump_bytes = (p.cells + 8u) * 2u;
+                const char* sep_src = S16 ? (const char*)(p.sep16 + (size_t)b * p.r) : (const char*)(p.sep + (size_t)b * p.r);
                 mbar_expect_tx(&bar, sep_bytes + jump_bytes);
                 for (unsigned off = 0; off < sep_bytes; off += 32768u)
-                    tma_bulk_g2s((char*)s_sep + off, (const char*)(p.sep + (size_t)b * p.r) + off, min(32768u, sep_bytes - off), &bar);
+                    tma_bulk_g2s((char*)s_sep + off, sep_src + off, min(32768u, sep_bytes - off), &bar);
                 for (unsigned off = 0; off < jump_bytes; off += 32768u)
-                    tma_bulk_g2s((char*)s_jump + off, (const char*)(p.jump + (size_t)b * (p.r + 8u)) + off, min(32768u, jump_bytes - off), &bar);
+                    tma_bulk_g2s((char*)s_jump + off, (const char*)(p.jump + (size_t)b * (p.cells + 8u)) + off, min(32768u, jump_bytes - off), &bar);
             }
         }
         const uint2 mt = s_meta[slot];
@@ -688,13 +688,23 @@ bk_search2_kernel(const BkSearchParams p, uint32_t* __restrict__ qsort, uint32_t
         // lane j of this slot" + popc + a shared-memory table of the non-empty runs was measured slower: 0.943 vs 0.883 ms.)
         auto locate = [&](unsigned kbase) -> uint32_t {  // kbase = the slot's first query (warp-uniform); this lane's is kbase + lane
             const unsigned k = min(kbase + lane, T - 1u), klast = min(kbase + 31u, T - 1u);
-            const unsigned e1 = __shfl_sync(kFull, excl, min(rcur + 1u, 31u)), e2 = __shfl_sync(kFull, excl, min(rcur + 2u, 31u));
-            const unsigned e3 = __shfl_sync(kFull, excl, min(rcur + 3u, 31u)), e4 = __shfl_sync(kFull, excl, min(rcur + 4u, 31u));
+            // (LB = boundaries the fast path handles; 7 instead of 3 for the ~8-query runs of 2048 buckets was measured: search 1.768
+            // vs 1.735 ms at 2^30 keys, no gain)
+            constexpr int LB = 3;
+            unsigned e[LB + 1];
+#pragma unroll
+            for (int i = 0; i <= LB; i++) e[i] = __shfl_sync(kFull, excl, min(rcur + 1u + (unsigned)i, 31u));
             unsigned r;
-            if (rcur + 4u > 31u || e4 > klast) {  // (warp-uniform) at most three boundaries inside the slot
-                const bool h1 = rcur + 1u <= 31u, h2 = rcur + 2u <= 31u, h3 = rcur + 3u <= 31u;
-                r = rcur + ((h1 && e1 <= k) ? 1u : 0u) + ((h2 && e2 <= k) ? 1u : 0u) + ((h3 && e3 <= k) ? 1u : 0u);
-                rcur += ((h1 && e1 <= klast) ? 1u : 0u) + ((h2 && e2 <= klast) ? 1u : 0u) + ((h3 && e3 <= klast) ? 1u : 0u);
+            if (rcur + (unsigned)LB + 1u > 31u || e[LB] > klast) {  // (warp-uniform) at most LB boundaries inside the slot
+                r = rcur;
+                unsigned adv = 0;
+#pragma unroll
+                for (int i = 0; i < LB; i++) {
+                    const bool have = rcur + 1u + (unsigned)i <= 31u;
+                    r += (have && e[i] <= k) ? 1u : 0u;
+                    adv += (have && e[i] <= klast) ? 1u : 0u;
+                }
+                rcur += adv;
             } else {
                 r = 0;
 #pragma unroll
@@ -739,6 +749,50 @@ bk_search2_kernel(const BkSearchParams p, uint32_t* __restrict__ qsort, uint32_t
             // rank among the bucket's separators: the jump cell gives the first candidate; later separators are probed only
             // while they are below the query (37 % / 10 % / 2 % of the lanes for uniform keys).  No upper end is needed:
             // every separator of a later cell is above q and the bucket's last separator is >= q.
+            if constexpr (S16) {
+                // 16-bit mode (leaf levels above 2^28 slots): 65536 separators per bucket as 16-bit offsets inside their jump cell
+                // (a cell is at most 2^16 keys wide: 32768 cells over a range below 2^31), two per cell on average.  A cell's
+                // separators are the only ones whose offsets compare with the query's, so both ends of the cell are read; six
+                // offsets from the cell's start on come in three aligned 32-bit loads, more are needed by ~0.4 % of the queries.
+                const uint32_t* s_sep32 = s_sep;  // (pairs of u16)
+                const uint16_t* s_sep16 = reinterpret_cast<const uint16_t*>(s_sep);
+                const unsigned rw = p.r / 2u - 1u;
+                unsigned l[U], h[U];
+                uint32_t qr[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const uint32_t d = q[u] - lo;
+                    const unsigned x = d >> sh;
+                    qr[u] = d & ((1u << sh) - 1u);
+                    l[u] = s_jump[x];
+                    h[u] = s_jump[x + 1u];
+                }
+                uint32_t w0[U], w1[U], w2[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const unsigned wl = l[u] >> 1;
+                    w0[u] = s_sep32[min(wl, rw)];
+                    w1[u] = s_sep32[min(wl + 1u, rw)];
+                    w2[u] = s_sep32[min(wl + 2u, rw)];
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const unsigned base = l[u] & ~1u;
+                    const uint32_t v[6] = {w0[u] & 0xffffu, w0[u] >> 16, w1[u] & 0xffffu, w1[u] >> 16, w2[u] & 0xffffu, w2[u] >> 16};
+                    unsigned pos = l[u];
+#pragma unroll
+                    for (unsigned j = 0; j < 6u; j++)  // (offsets are sorted inside a cell: the ones below the query's come first)
+                        pos += (base + j >= l[u] && base + j < h[u] && v[j] < qr[u]) ? 1u : 0u;
+                    if (pos == base + 6u && pos < h[u]) {  // rare: more than five separators of the cell below the query
+                        unsigned hh = h[u];
+                        while (pos < hh) {
+                            const unsigned m = (pos + hh) >> 1;
+                            if (s_sep16[m] < qr[u]) pos = m + 1; else hh = m;
+                        }
+                    }
+                    a[u] = pos;
+                }
+            } else {
             unsigned l[U];
             uint32_t s0[U], s1[U], s2[U];
 #pragma unroll
@@ -767,6 +821,7 @@ bk_search2_kernel(const BkSearchParams p, uint32_t* __restrict__ qsort, uint32_t
                     }
                 }
                 a[u] = pos;
+            }
             }
             // the block of G keys that holds the answer: one 32-byte sector (two for G = 16).  Block numbers fit 32 bits
             // (at most 2^30 / 8 blocks), so the address is one 32 x 32 -> 64 multiply-add.
@@ -940,6 +995,32 @@ bk_jump_kernel(const uint32_t* __restrict__ sep, const uint32_t* __restrict__ sp
     }
 }
 
+// 16-bit mode.  Per bucket: lo = split[b], shift = smallest s with (split[b+1] - lo) >> s < cells (<= 16, since cells = 32768 and
+// the range is below 2^31), jump[x] = number of the bucket's separators with (sep - lo) >> s < x for x in [0, cells], saturated
+// at 65535 (a query's own cell always starts below that: the bucket's last separator is >= every query of the bucket); and
+// sep16[m] = the low s bits of sep[m] - lo, the separator's offset inside its cell.
+__global__ void __launch_bounds__(256)
+bk_jump16_kernel(const uint32_t* __restrict__ sep, const uint32_t* __restrict__ split, unsigned r, unsigned cells, unsigned long long m8,
+                 uint16_t* __restrict__ jump, uint2* __restrict__ meta, uint16_t* __restrict__ sep16) {
+    const unsigned b = blockIdx.x;
+    const uint32_t lo = split[b], hi = split[b + 1];
+    unsigned s = 0;
+    while (((hi - lo) >> s) >= cells) s++;
+    if (threadIdx.x == 0) meta[b] = make_uint2(lo, s);
+    const uint32_t* sb = sep + (size_t)b * r;
+    const unsigned long long first = (unsigned long long)b * r;
+    const unsigned valid = (unsigned)min((unsigned long long)r, m8 > first ? m8 - first : 0ull);
+    for (unsigned x = threadIdx.x; x < cells + 8u; x += blockDim.x) {
+        unsigned l = 0, h = valid;
+        while (l < h) {
+            const unsigned m = (l + h) >> 1;
+            if (((sb[m] - lo) >> s) < x) l = m + 1; else h = m;
+        }
+        jump[(size_t)b * (cells + 8u) + x] = x <= cells ? (uint16_t)min(l, 65535u) : 0;
+    }
+    for (unsigned m = threadIdx.x; m < r; m += blockDim.x) sep16[(size_t)b * r + m] = m < valid ? (uint16_t)((sb[m] - lo) & ((1u << s) - 1u)) : 0xffffu;
+}
+
 // Map-partitioned trees: a query above MAX has no part (partitioned_s_tree.rs:844: the prefix map has no such entry) and is
 // answered with (MAX, n) by every kernel of this library; the pipeline canonicalises such queries like the plain tree's
 // signed compare, so they are rewritten here.  Exits at once unless the rank stage saw one.
@@ -987,7 +1068,7 @@ bool regrow(T*& p, size_t count) {
 }  // namespace
 
 void free_bucket_aux(sst_index* idx) {
-    cudaFree(idx->bk.d_dense); cudaFree(idx->bk.d_sep); cudaFree(idx->bk.d_split); cudaFree(idx->bk.d_bt); cudaFree(idx->bk.d_jump); cudaFree(idx->bk.d_meta);
+    cudaFree(idx->bk.d_dense); cudaFree(idx->bk.d_sep16); cudaFree(idx->bk.d_sep); cudaFree(idx->bk.d_split); cudaFree(idx->bk.d_bt); cudaFree(idx->bk.d_jump); cudaFree(idx->bk.d_meta);
     idx->bk = BkAux{};
 }
 
@@ -1011,11 +1092,18 @@ bool build_bucket_aux(sst_index* idx, const uint32_t* d_sorted) {
     // separators per bucket: 16384 (two search CTAs per SM) up to 2^27 keys, 32768 (one 1024-thread CTA) above, so that the
     // partition has at most 1024 buckets up to 2^28 keys -- fewer buckets = longer runs and fewer ballot bits
     // keys per separator: 8 (one leaf sector per query) up to 2^29 keys, 16 (a whole node) up to 2^30
-    unsigned g = opt(OPT_BK_G) > 0 ? (unsigned)opt(OPT_BK_G) : (div_ceil(n_flat, (size_t)8) > 32768ull * 2048ull ? 16u : 8u);
+    // Above 2^28 slots 32768 32-bit separators per bucket would need more than 1024 buckets (8-query runs: partition and search
+    // both suffer) or 16 keys per separator (two leaf sectors per query, half as many queries in flight per thread: the search took
+    // 2.04 ms per 2^27 queries at 2^30 keys against 1.28 at 2^29).  The 16-bit mode keeps 8 keys per separator with 65536
+    // separators per bucket in the same 192 KB: the separators are stored as 16-bit offsets inside their jump cell (bk_jump16_kernel).
+    const bool s16 = (opt(OPT_BK_SEP16) == 1 && opt(OPT_BK_G) <= 0) || (opt(OPT_BK_SEP16) < 0 && opt(OPT_BK_G) <= 0 && opt(OPT_BK_R) <= 0 && div_ceil(n_flat, (size_t)8) > 32768ull * 1024ull);
+    unsigned g = s16 ? 8u : opt(OPT_BK_G) > 0 ? (unsigned)opt(OPT_BK_G) : (div_ceil(n_flat, (size_t)8) > 32768ull * 2048ull ? 16u : 8u);
     if (g != 8 && g != 16) g = 8;
     const unsigned long long m8 = div_ceil(n_flat, (size_t)g);
     unsigned r = opt(OPT_BK_R) > 0 ? (unsigned)opt(OPT_BK_R) : (m8 > 16384ull * 1024ull ? 32768u : 16384u);
     if (r < 64 || r > 32768 || (r & (r - 1))) r = 16384;
+    if (s16) r = 65536u;  // (fixed: 16-bit offsets need cells = r / 2 >= 2^31 / 2^16 whatever the bucket's key range)
+    const unsigned cells = s16 ? r / 2u : r;
     const unsigned long long nb64 = div_ceil((size_t)m8, (size_t)r);
     if (nb64 > 2048) return true;  // > 2^30 keys: served by the rank-table kernel
     BkAux& a = idx->bk;
@@ -1035,16 +1123,19 @@ bool build_bucket_aux(sst_index* idx, const uint32_t* d_sorted) {
     }
     const unsigned long long total = (unsigned long long)nb * r;
     bool ok = SST_CUDA_OK(cudaMalloc(&a.d_sep, total * 4)) && SST_CUDA_OK(cudaMalloc(&a.d_split, ((size_t)nb + 1) * 4)) &&
-              SST_CUDA_OK(cudaMalloc(&a.d_bt, (size_t)kBtStride * 2)) && SST_CUDA_OK(cudaMalloc(&a.d_jump, (size_t)nb * (r + 8) * 2)) &&
-              SST_CUDA_OK(cudaMalloc(&a.d_meta, (size_t)nb * sizeof(uint2)));
+              SST_CUDA_OK(cudaMalloc(&a.d_bt, (size_t)kBtStride * 2)) && SST_CUDA_OK(cudaMalloc(&a.d_jump, (size_t)nb * (cells + 8) * 2)) &&
+              SST_CUDA_OK(cudaMalloc(&a.d_meta, (size_t)nb * sizeof(uint2))) && (!s16 || SST_CUDA_OK(cudaMalloc(&a.d_sep16, total * 2)));
     if (ok) {
         bk_sep_kernel<<<(unsigned)std::min<size_t>(div_ceil((size_t)total, (size_t)256), (size_t)cur_sms() * 16), 256, 0, st>>>(leaf, m8, total, g, a.d_sep);
         bk_split_kernel<<<(unsigned)div_ceil((size_t)nb + 1, (size_t)256), 256, 0, st>>>(a.d_sep, nb, r, a.d_split);
         bk_bt_kernel<<<(unsigned)div_ceil((size_t)kBtStride, (size_t)256), 256, 0, st>>>(a.d_split, nb, a.d_bt);
-        bk_jump_kernel<<<nb, 256, 0, st>>>(a.d_sep, a.d_split, r, m8, a.d_jump, a.d_meta);
+        if (s16) bk_jump16_kernel<<<nb, 256, 0, st>>>(a.d_sep, a.d_split, r, cells, m8, a.d_jump, a.d_meta, a.d_sep16);
+        else bk_jump_kernel<<<nb, 256, 0, st>>>(a.d_sep, a.d_split, r, m8, a.d_jump, a.d_meta);
         ok = SST_CUDA_OK(cudaGetLastError()) && SST_CUDA_OK(cudaStreamSynchronize(st));
     }
     if (!ok) { free_bucket_aux(idx); return false; }
+    if (s16) { cudaFree(a.d_sep); a.d_sep = nullptr; }  // (the 32-bit separators were only needed to build the 16-bit form)
+    a.cells = cells;
     a.nb = nb; a.nbp = nbp; a.r = r; a.bits = bits; a.m8 = m8; a.g = g; a.n_flat = n_flat;
     return true;
 }
@@ -1086,9 +1177,13 @@ struct Scratch2 {
 thread_local Scratch2 g_scratch2[64];
 
 struct Shape2 { size_t sub; unsigned ntiles, ntp, nbp2; size_t runs, items; };
-Shape2 shape2(const BkAux& a, size_t nq) {
+// Queries per pipeline run.  A larger run puts more queries on every leaf sector (at 2^30 keys a run of 2^27 queries touches every
+// sector once: the whole 4 GB leaf level per run) but needs 6-10 bytes of scratch per query: up to 2^30 (BK_SUB_LOG2) when the
+// scratch can be had, halved down to 2^27 when it cannot.
+size_t sub_batch_max() { return (size_t)1 << opt(OPT_BK_SUB_LOG2); }
+Shape2 shape2(const BkAux& a, size_t nq, size_t sub_max) {
     Shape2 h;
-    h.sub = std::min(nq, kSubBatch);
+    h.sub = std::min(nq, sub_max);
     h.ntiles = (unsigned)div_ceil(h.sub, (size_t)kTile);
     h.ntp = (h.ntiles + 31u) & ~31u;
     h.nbp2 = (unsigned)(div_ceil((size_t)a.nb, (size_t)kPThreads) * kPThreads);
@@ -1160,12 +1255,13 @@ int reserve_bucketed(const sst_index* idx, size_t nq, bool want_idx) {
     if (!a.nb || nq == 0) return SST_OK;
     const int dev = idx->device;
     if (dev < 0 || dev >= 64) { set_error(SST_ERR_ARG, "device index out of range"); return SST_ERR_ARG; }
-    if (!scratch2_ensure(g_scratch2[dev], dev, shape2(a, nq), want_idx)) {
+    if (!scratch2_ensure(g_scratch2[dev], dev, shape2(a, nq, sub_batch_max()), want_idx)) {
         set_error(SST_ERR_CAPACITY, "not enough device memory for the reordered-batch scratch buffers (6-10 bytes per query)");
         return SST_ERR_CAPACITY;
     }
     return SST_OK;
 }
+size_t bucketed_sub_batch() { return sub_batch_max(); }
 void release_bucketed_scratch() {
     for (auto& s : g_scratch2) s.release();
 }
@@ -1175,10 +1271,15 @@ static int launch_bucketed_v2(const sst_index* idx, const uint32_t* d_qs, size_t
     const int dev = idx->device;
     if (dev < 0 || dev >= 64) { set_error(SST_ERR_ARG, "device index out of range"); return SST_ERR_ARG; }
     Scratch2& s = g_scratch2[dev];
-    const Shape2 h = shape2(a, nq);
-    if (!scratch2_ensure(s, dev, h, d_idx != nullptr)) {  // out of device memory for the scratch buffers
-        set_error(SST_ERR_CAPACITY, "not enough device memory for the reordered-batch scratch buffers (6-10 bytes per query)");
-        return SST_ERR_CAPACITY;
+    Shape2 h = shape2(a, nq, sub_batch_max());
+    while (!scratch2_ensure(s, dev, h, d_idx != nullptr)) {  // out of device memory for the scratch buffers: smaller runs, down to 2^27 queries
+        (void)cudaGetLastError();
+        if (h.sub <= ((size_t)1 << 27)) {
+            set_error(SST_ERR_CAPACITY, "not enough device memory for the reordered-batch scratch buffers (6-10 bytes per query)");
+            return SST_ERR_CAPACITY;
+        }
+        clear_error();
+        h = shape2(a, nq, h.sub / 2);
     }
     // scratch reuse across this thread's streams: a call waits for the previous one.  Not while `st` is being captured into a
     // CUDA graph: an event recorded outside the capture cannot be waited on there, and one recorded inside it would tie later
@@ -1192,9 +1293,9 @@ static int launch_bucketed_v2(const sst_index* idx, const uint32_t* d_qs, size_t
     const bool map_tree = idx->variant == SST_MAP || idx->variant == SST_COMPACT || flat_parts;  // partitioned: a query above MAX has no part -> (MAX, n)
     if (map_tree && !SST_CUDA_OK(cudaMemsetAsync(s.ctrl + 3, 0, 4, st))) return SST_ERR_CUDA;
     const size_t smem_part = (size_t)kTile * 4 + (size_t)kBtCells * 4 + std::max((size_t)kTile * 4, (size_t)kPWarps * (h.nbp2 + kCntPad) * 2);
-    const size_t smem_search = (size_t)a.r * 4 + ((size_t)a.r + 8) * 2;
+    const size_t smem_search = (size_t)a.r * (a.d_sep16 ? 2 : 4) + ((size_t)a.cells + 8) * 2;
     const unsigned chunk_log2 = (unsigned)opt(OPT_BK_CHUNK2_LOG2);
-    BkSearchParams sp{a.d_sep, a.d_jump, a.d_meta, a.d_dense ? a.d_dense : idx->d_tree + idx->offsets[idx->levels - 1] * 16, a.r, a.m8, a.n_flat};
+    BkSearchParams sp{a.d_sep, a.d_jump, a.d_meta, a.d_dense ? a.d_dense : idx->d_tree + idx->offsets[idx->levels - 1] * 16, a.r, a.d_sep16, a.cells, a.m8, a.n_flat};
     const bool timing = opt(OPT_BK_TIMING) != 0;
     cudaEvent_t ev[8] = {};
     int nev = 0;
@@ -1228,7 +1329,8 @@ static int launch_bucketed_v2(const sst_index* idx, const uint32_t* d_qs, size_t
         mark();  // (no scatter stage: kept so that the five stage times line up with the V1 report)
         {
             void (*kern)(const BkSearchParams, uint32_t*, uint32_t*, const uint32_t*, unsigned, const uint4*, unsigned*) =
-                a.g == 16 ? (d_idx ? bk_search2_kernel<true, 16> : bk_search2_kernel<false, 16>) : (d_idx ? bk_search2_kernel<true, 8> : bk_search2_kernel<false, 8>);
+                a.d_sep16 ? (d_idx ? bk_search2_kernel<true, 8, true> : bk_search2_kernel<false, 8, true>)
+                : a.g == 16 ? (d_idx ? bk_search2_kernel<true, 16, false> : bk_search2_kernel<false, 16, false>) : (d_idx ? bk_search2_kernel<true, 8, false> : bk_search2_kernel<false, 8, false>);
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_search);
             kern<<<sms, kSThreads, smem_search, st>>>(sp, s.qsort, s.isort, s.runs, h.ntp, s.items, s.ctrl);
         }

@@ -77,6 +77,8 @@ unsigned cur_sms();                   // sm_count of the calling thread's curren
     X(BK_TIMING, 0, 0, 2)                /* per-stage CUDA-event times (synchronises; bench/tools only) */                    \
     X(BK_CHUNK2_LOG2, 15, 14, 24)        /* log2 of the queries per search work item of the V2 pipeline */                    \
     X(BK_COMPACT, 1, 0, 1)               /* Compact layout: keep a dense copy of the keys so that large batches take the pipeline */ \
+    X(BK_SEP16, -1, -1, 1)               /* 16-bit separators (65536 per bucket, 8 keys each): -1 = above 2^28 slots, 0 = never, 1 = always */ \
+    X(BK_SUB_LOG2, 30, 20, 30)           /* log2 of the queries per pipeline run (sub-batch); halved when the scratch does not fit */ \
     X(BK_HYBRID, 1, 0, 4)                                                                                                    \
     X(BK_VEC, 1, 0, 1)                                                                                                       \
     X(BK_MOVE_THREADS, 1024, 512, 1024)                                                                                      \
@@ -181,6 +183,8 @@ struct BkAux {
     uint16_t* d_bt = nullptr;     // bucket table over the top 12 key bits
     uint16_t* d_jump = nullptr;   // [nb][8200] per-bucket jump table into its separators
     uint2* d_meta = nullptr;      // [nb] {lo, shift} of the jump table
+    uint16_t* d_sep16 = nullptr;  // 16-bit mode (above 2^28 slots): [nb * r] low `shift` bits of sep - lo, i.e. the separator's offset inside its jump cell
+    unsigned cells = 0;           // jump cells per bucket: r (32-bit separators) or r / 2 (16-bit mode)
     unsigned nb = 0, nbp = 0, r = 0, bits = 0;
     unsigned g = 8;               // keys per separator: 8 (half node) or 16 (node)
     unsigned long long m8 = 0;    // blocks of g keys that hold keys
@@ -245,7 +249,8 @@ int last_stage_ms(double* out, int n);  // stage times of this thread's last pip
 int launch_bucketed(const sst_index* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_vals, unsigned long long* d_idx,
                     cudaStream_t stream);
 int reserve_bucketed(const sst_index* idx, size_t nq, bool want_idx);  // pre-size the calling thread's scratch
-void release_bucketed_scratch();                                       // free the calling thread's scratch on every device
+void release_bucketed_scratch();
+size_t bucketed_sub_batch();                                           // queries per pipeline run (larger batches run in several)                                       // free the calling thread's scratch on every device
 // suffix arrays (sa.cu): replica of a finished index on another device, copied device to device
 struct sst_sa* clone_sa(const struct sst_sa* src, int device);
 }  // namespace sst

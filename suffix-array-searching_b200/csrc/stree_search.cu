@@ -801,7 +801,7 @@ int query_launch_count(const sst_index* idx, int scheme, size_t nq, bool want_id
     if (nq == 0) return 0;
     if (resolve_scheme(idx, scheme, nq) != SST_SCHEME_BUCKETED) return 1;
     const int base = 4;
-    return (int)(div_ceil(nq, (size_t)1 << 27) * (base + (want_idx ? 1 : 0) + (idx->variant == SST_PLAIN ? 0 : 1) +
+    return (int)(div_ceil(nq, bucketed_sub_batch()) * (base + (want_idx ? 1 : 0) + (idx->variant == SST_PLAIN ? 0 : 1) +
                                                    (want_idx && idx->variant != SST_PLAIN && idx->variant != SST_MAP && idx->variant != SST_COMPACT ? 1 : 0)));  // partitioned: + the q > MAX fix-up (+ flat -> sorted index)
 }
 

@@ -163,7 +163,10 @@ def test_auto_picks_the_pipeline_for_large_batches(gpu, oracle):
     assert L.sst_query_plan(t._h, 1 << 26, 0, 0, C.byref(sch), C.byref(launches)) == 0
     assert sch.value == sst.SCHEME_BUCKETED and launches.value == 4  # partition, work items, search, un-permute
     assert L.sst_query_plan(t._h, 1 << 26, 0, 1, C.byref(sch), C.byref(launches)) == 0 and launches.value == 5
-    assert L.sst_query_plan(t._h, (1 << 28) + 1, 0, 0, C.byref(sch), C.byref(launches)) == 0 and launches.value == 12  # three sub-batches
+    assert L.sst_query_plan(t._h, (1 << 28) + 1, 0, 0, C.byref(sch), C.byref(launches)) == 0 and launches.value == 4  # one run of up to 2^30 queries
+    sst.set_option("BK_SUB_LOG2", 27)
+    assert L.sst_query_plan(t._h, (1 << 28) + 1, 0, 0, C.byref(sch), C.byref(launches)) == 0 and launches.value == 12  # three runs of 2^27
+    sst.set_option("BK_SUB_LOG2", 30)
     assert L.sst_query_plan(t._h, 1 << 24, 0, 0, C.byref(sch), C.byref(launches)) == 0 and sch.value == sst.SCHEME_BUCKETED
     assert L.sst_query_plan(t._h, (1 << 24) - 1, 0, 0, C.byref(sch), C.byref(launches)) == 0 and sch.value == sst.SCHEME_TABLE
     assert L.sst_query_plan(t._h, 1 << 20, 0, 0, C.byref(sch), C.byref(launches)) == 0
@@ -288,3 +291,38 @@ def test_calibrate_sets_the_auto_crossover(gpu, oracle):
     small = sst.STree16.new_params(gen_vals(1000, seed=53), True, False, False)
     sst.reset_options()
     assert sst.STree16.new_params(gen_vals(1000, seed=53), True, False, False).calibrate() == 0  # nothing to calibrate
+
+
+@pytest.mark.parametrize("kind,n,nq", [("uniform", 3_000_000, 400_000), ("uniform", 600_001, 100_000), ("clustered", 1_500_000, 200_000),
+                                       ("dupes", 2_000_000, 200_000), ("tiny_range", 700_000, 100_000), ("uniform", 1000, 5000)])
+def test_bucketed_sep16(gpu, oracle, kind, n, nq):
+    """16-bit separator mode (what leaf levels above 2^28 slots take): 65536 separators per bucket stored as offsets inside their
+    jump cell, both ends of the cell read, up to six offsets per query from three 32-bit loads, more by bisection.  Forced onto
+    small trees: uniform keys (two separators per cell), clustered / duplicate keys (crowded cells: the bisection path, empty
+    cells), plain and Map / Compact layouts, with the index output."""
+    sst = gpu
+    gpu.set_option("BK_MIN_N", 0)
+    gpu.set_option("BK_SEP16", 1)
+    rng = np.random.default_rng(n + nq)
+    vals = gen_vals(n, seed=n) if kind == "uniform" else make_keys(rng, n, kind)
+    qs = make_queries(rng, vals, nq)
+    _check(sst, oracle, vals, qs, flags=[(1, 0, 0), (0, 1, 0)])
+    ev, ei = oracle.lower_bound(vals, qs)
+    for layout in ("PartitionedSTree16M", "PartitionedSTree16C"):
+        t = getattr(sst, layout).try_new(vals, 8)
+        if t is None:
+            continue
+        v, i = t.query(qs, sst.SCHEME_BUCKETED, want_index=True)
+        assert np.array_equal(v, ev) and np.array_equal(i, ei), layout
+
+
+def test_bucketed_several_runs(gpu, oracle):
+    """A batch larger than the pipeline's run size (BK_SUB_LOG2; 2^30 by default, halved when the scratch does not fit) is
+    answered run by run: full runs, a partial last run, the index output."""
+    sst = gpu
+    gpu.set_option("BK_MIN_N", 0)
+    gpu.set_option("BK_R", 256)
+    gpu.set_option("BK_SUB_LOG2", 20)
+    vals = gen_vals(700_000, seed=61)
+    qs = gen_queries((3 << 20) + 12_345, seed=62, vals=vals)
+    _check(sst, oracle, vals, qs, flags=[(1, 0, 0)])
