@@ -151,7 +151,7 @@ int sst_query(const sst_index_t* idx, const uint32_t* qs, size_t nq, uint32_t* o
               int scheme); /* HOST buffers: H2D, kernel, D2H, synchronous */
 int sst_query_device(const sst_index_t* idx, const uint32_t* d_qs, size_t nq, uint32_t* d_out_vals,
                      uint64_t* d_out_idx, int scheme, void* stream); /* DEVICE buffers, asynchronous on `stream` */
-/* Pre-sizes the calling thread's scratch buffers of the reordered-batch pipeline (6-10 bytes per query, at most 2^27 queries'
+/* Pre-sizes the calling thread's scratch buffers of the reordered-batch pipeline (6-10 bytes per query, at most 2^30 queries'
  * worth) for batches of up to nq queries on this index, so that later sst_query_device calls from this thread allocate
  * nothing: they are then asynchronous on `stream` and can be captured into a CUDA graph.  Without it the first large
  * batch allocates (and synchronises the device) once.  sst_query_release frees the calling thread's scratch on every device

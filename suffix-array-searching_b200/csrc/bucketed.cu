@@ -1,31 +1,33 @@
-// bucketed.cu -- reordered-batch lower_bound: partition the query batch by key range, answer each bucket
-// from shared memory + one leaf sector, un-permute the results.  Same results as every other scheme.
+// bucketed.cu -- reordered-batch lower_bound: sort every tile of the query batch by key range, answer each range
+// from shared memory + one leaf sector per query, put the answers back in the caller's order.  Same results as every other scheme.
 //
 // Replaces (static-search-tree/src): the batched/interleaved searches of s_tree.rs:208-832 for LARGE
 // batches over LARGE trees.  The reference keeps 128 independent queries in flight and lets each one
 // miss the cache once per level (s_tree.rs:303-326); on B200 that design is bound by the number of
 // random DRAM accesses per second (~43 G/s), one per query for the leaf level.
-// Here the batch is first reordered so that all queries that fall into the same 0.5-2 MB window of the
-// leaf level are answered together by one CTA:
+// Here the batch is first reordered so that all queries that fall into the same 1-2 MB window of the
+// leaf level are answered together by one CTA (4 launches per run of up to 2^30 queries):
 //
-//   rank    (bk_rank_kernel)    per 16384-query tile: bucket id per query (ONE shared load: a table over the top 13 key bits
-//                               that packs the bucket count, a flag and the next splitter's low bits), rank inside the tile
-//                               by per-warp counters with claim / ballot steps (no atomics), tile x bucket counts, 16-bit
-//                               local position
-//   plan    (bk_colsum/plan/offsets) exclusive scan of the count matrix -> global offset of every
-//                               (tile, bucket) run, bucket starts, work items (bucket, 32768-query chunk)
-//   scatter (bk_move_kernel<0>) tile -> shared memory in bucket order -> coalesced runs in HBM (next tile prefetched)
-//   search  (bk_search_kernel)  per work item: the bucket's separators (last key of every 8-key half node, or of
-//                               every node above 2^29 keys: 64-128 KB) and its jump table (32-64 KB) are staged into
-//                               shared memory by 1-D TMA bulk copies; a query is ranked among them with 2 + ~0.5
-//                               shared loads (predicated probes) and finished with ONE 32-byte leaf load (LDG.256)
-//   gather  (bk_move_kernel<1>) results back into the caller's order through shared memory
+//   partition  (bk_part_kernel)     per 16384-query tile: TMA bulk load (next tile prefetched) -> bucket id per query (ONE shared
+//                                   load: a table over the top 13 key bits that packs the bucket count, a flag and the next
+//                                   splitter's low bits) -> rank inside the tile by per-warp counters with claim / ballot steps
+//                                   (no atomics) -> scan -> sorted tile in shared memory -> TMA bulk store; plus the 16-bit
+//                                   position map and one run descriptor {start, count} per (bucket, tile), bucket-major
+//   plan       (bk_items_kernel)    work items (bucket, tile range) of at most 32768 queries
+//   search     (bk_search2_kernel)  per work item: the bucket's separators (last key of every 8-key half node: 32768 x 32 bits, or
+//                                   above 2^28 slots 65536 x 16-bit offsets inside their jump cell) and its jump table (192 KB in
+//                                   all) are staged by 1-D TMA bulk copies; a warp walks 32 runs at a time, a query is ranked
+//                                   among the separators with the jump cell + three separator loads and finished with ONE
+//                                   32-byte leaf load (LDG.256); the answer overwrites the query IN PLACE
+//   un-permute (bk_unperm_kernel)   tile of answers by TMA bulk load (double buffered) -> caller's order through the position
+//                                   map in shared memory -> 16-byte stores
 //
 // DRAM traffic per 10^8 queries over 2^28 keys: the leaf level once (1 GiB, instead of 6.4-12.8 GB of
-// random sectors), 128 MB of separators, and ~3 GB of query/result/position streams.  The tree image is
+// random sectors), 128 MB of separators, and ~3 GB of query/result/position streams (4.26 GB in all, ncu).  The tree image is
 // untouched: the leaf level is read in place and the separators are a GPU-only auxiliary array like
 // the rank table of stree_search.cu.  Served: plain B = 16 trees (any new_params flags) and the Map, Simple, L1 and
-// Overlapping partitioned layouts (their leaf level is one sorted flat array) of 2^22 .. 2^30 leaf slots.
+// Overlapping partitioned layouts (their leaf level is one sorted flat array) of 2^22 .. 2^30 leaf slots; Compact through a
+// dense copy of its keys.
 #include <algorithm>
 #include <type_traits>
 #include <cstdio>
@@ -246,7 +248,6 @@ __device__ __forceinline__ void rank_items(uint16_t* cntw, uint32_t (&pk)[ITEMS]
             }
 }
 
-// FULL: every tile in [tile_begin, tile_end) holds kTile queries (the partial last tile gets its own launch).
 // ------------------------------------------------------------------------------------------------
 // search: one work item = (bucket, chunk of its queries)
 // ------------------------------------------------------------------------------------------------
@@ -263,11 +264,10 @@ struct BkSearchParams {
 };
 
 
-// G = keys per separator: 8 (half node, one 32-byte sector per query) up to 2^29 keys, 16 (whole node, two sectors) above
 // ================================================================================================
-// V2 pipeline: tile-local partition -> plan -> search over runs, in place -> streaming un-permute
+// The pipeline: tile-local partition -> plan -> search over runs, in place -> streaming un-permute
 //
-// The round-1 pipeline (above) gathered every bucket into one contiguous array: rank kernel, three plan kernels over the
+// The round-1 pipeline (git history) gathered every bucket into one contiguous array: rank kernel, three plan kernels over the
 // tiles x buckets count matrix, a scatter kernel that read the queries a second time, and a gather kernel that collected
 // ~16-query runs back.  Here a tile is only sorted LOCALLY: the partition kernel reads a tile once (TMA bulk load,
 // prefetched one tile ahead), ranks it, and writes it back as one contiguous 64 KB block in bucket order (TMA bulk store)

@@ -794,7 +794,7 @@ int resolve_scheme(const sst_index* idx, int scheme, size_t nq) {
 
 }  // namespace
 
-// Kernel launches of one sst_query_device call.  The reordered-batch pipeline runs 4 kernels per 2^27-query sub-batch
+// Kernel launches of one sst_query_device call.  The reordered-batch pipeline runs 4 kernels per run of up to 2^30 queries (BK_SUB_LOG2)
 // (partition, work items, search, un-permute) and one more un-permute for the index output; the round-1
 // pipeline ran 7 (rank, column sums, plan, offsets, scatter, search, gather).
 int query_launch_count(const sst_index* idx, int scheme, size_t nq, bool want_idx) {
