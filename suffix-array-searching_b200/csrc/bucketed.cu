@@ -717,12 +717,17 @@ bk_search2_kernel(const BkSearchParams p, uint32_t* __restrict__ qsort, uint32_t
             return __shfl_sync(kFull, dlt, r) + k;
         };
         uint32_t an[U], qn[U];  // next round: addresses and queries (their loads stay in flight while this round is answered)
+        unsigned vn = 0;        // bit u = slot u of the next round holds a query for this lane (carried along with the round: recomputing
+                                // it from k0 and T at the top of the round cost 0.03 ms of the stage, profiles/r2_search2_units_ab.log)
         auto prefetch = [&](unsigned k0) {  // the round that starts at flattened query k0 of the current group
+            vn = 0;
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 const unsigned kb = k0 + u * 32u;
                 an[u] = kb < T ? locate(kb) : 0u;
-                qn[u] = kb + lane < T ? ldq(qsort + an[u]) : lo;
+                const bool v = kb + lane < T;
+                qn[u] = v ? ldq(qsort + an[u]) : lo;
+                vn |= (v ? 1u : 0u) << u;
             }
         };
         bool more = advance();
@@ -735,12 +740,12 @@ bk_search2_kernel(const BkSearchParams p, uint32_t* __restrict__ qsort, uint32_t
         unsigned k0 = 0;
         while (more) {
             uint32_t q[U], ad[U];
-            unsigned a[U], vm = 0;  // vm: bit u = slot u of this round holds a query for this lane
+            unsigned a[U];
+            const unsigned vm = vn;  // bit u = slot u of this round holds a query for this lane
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 q[u] = qn[u];
                 ad[u] = an[u];
-                vm |= (k0 + u * 32u + lane < T ? 1u : 0u) << u;
             }
             // next round: of this group, or the first one of the warp's next group
             k0 += 32u * U;
