@@ -97,7 +97,10 @@ unsigned cur_sms();                   // sm_count of the calling thread's curren
     X(SA_SORT_LEVELS, 12, 0, 30)                                                                                             \
     X(SA_SORT_MIN, -1, -1, 1ll << 62)    /* batches of at least this many patterns search in sorted order; -1 = never */      \
     X(SA_MINB, 0, 0, 5)                                                                                                      \
-    X(SA_INLINE, 1, 0, 15)               /* 0 = no inlined bases, 15 = 8-byte entries, 1 = widest that fits */                \
+    X(SA_INLINE, 1, 0, 32)               /* 0 = no inlined bases, 15 / 32 = 8- / 16-byte entries, 1 = widest that fits */     \
+    X(SA_GRID, 0, 0, 1 << 20)            /* cap on the blocks per SM of the search kernel's grid; 0 = one block per 256 patterns */ \
+    X(SA_PACKED_TEXT, 1, 0, 1)           /* build the 2-bit packed text next to the inlined bases */                          \
+    X(SA_USE_PACKED_TEXT, 1, 0, 1)       /* compare behind the inlined bases through it */                                    \
     X(SA_INLINE_DIV, 2, 1, 64)                                                                                               \
     X(SA_KMER, 1, 0, 1)                                                                                                      \
     X(SA_KMER_K, 16, 1, 16)                                                                                                  \

@@ -63,6 +63,11 @@ struct sst_sa {
     // The same with 32 bases per suffix in 16-byte entries {sa, bases present (32 = all), code hi, code lo}, built instead of
     // d_sax when memory allows (16 bytes per suffix): a pattern of up to k + 32 bases is then answered without the text.
     uint4* d_saw = nullptr;
+    // The text at 2 bits per base (with the k-mer table, i.e. for texts over {0,1,2,3}): word w = bases 16 w .. 16 w + 15, first base
+    // most significant, zero padded.  When the inlined bases of an entry equal the pattern's and the pattern goes on, the rest
+    // is compared here instead of in the byte text: the 52 bytes a 100-base pattern still needs shrink to 13, i.e. one 64-byte
+    // fill instead of (usually) two.  n / 4 bytes; GPU-only auxiliary.
+    uint32_t* d_text2 = nullptr;
     // Packed k-mer cells (with d_saw, k <= 14, n < 2^31, memory permitting): 128 bytes per cell = {start | overflow << 31, entries
     // 0..4} {-, entries 5..9}, an entry = {sa, code hi, code lo} -- the cell's suffix-array range AND its first ten {sa, 32 bases}
     // entries in ONE line, so that a pattern of k .. k + 31 bases is answered by a single random DRAM access instead of two (k-mer
@@ -76,6 +81,10 @@ namespace sst {
 namespace {
 
 constexpr int kThreads = 256;
+#ifndef SST_SA_SEARCH_THREADS
+#define SST_SA_SEARCH_THREADS 128   // (one pattern per thread: smaller blocks retire sooner; C5 256 / 128 / 64 threads 8.78 / 8.97 / 9.02 Gpat/s, C3 19.1 / 19.0 / 18.8)
+#endif
+constexpr int kSearchThreads = SST_SA_SEARCH_THREADS;  // block of sa_search_thread_kernel (MINB counts blocks of 256 threads' worth)
 #ifndef SST_SA_MIN_BLOCKS
 #define SST_SA_MIN_BLOCKS 5
 #endif
@@ -234,6 +243,7 @@ struct SaParams {
     const uint2* sax;      // {sa, next 15 bases} entries (or null)
     const uint4* saw;      // {sa, 32, next 32 bases} entries (or null; the WIDE kernels)
     const uint4* cells;    // packed k-mer cells, 4 x uint4 each (or null)
+    const uint32_t* text2; // the text at 2 bits per base (or null)
     uint32_t* out_probes;  // sa_search_kernel only: iterations of the reference's loop (its `cnt`, sa_search.rs:98-112), or null
 };
 
@@ -466,15 +476,49 @@ __device__ __forceinline__ uint32_t thread_compare(const SaParams& p, unsigned l
     }
 }
 
+// suffix(spos) vs the pattern from base `from` (a multiple of 16) on, through the 2-bit packed text; the caller knows that the
+// bases before `from` are equal.  Same contract as thread_compare (returns lcp, sets less); a pattern byte outside the alphabet
+// or a suffix shorter than `from` hands over to it.
+__device__ __forceinline__ uint32_t packed_compare(const SaParams& p, uint32_t spos, const W4& p0, const W4& p1, const uint8_t* pat, uint32_t ql,
+                                                   uint32_t from, bool& less) {
+    const unsigned long long sl64 = p.n - spos;
+    const uint32_t sl = sl64 > 0xffffffffull ? 0xffffffffu : (uint32_t)sl64;
+    if (sl < from) return thread_compare(p, spos, p0, p1, pat, ql, from, less);
+    const uint32_t lim = sl < ql ? sl : ql;
+    const uint8_t* pend = p.pats + p.pats_bytes;
+    const unsigned long long b0 = (unsigned long long)spos + from;  // first base to compare
+    const uint32_t* tw = p.text2 + (b0 >> 4);
+    const unsigned sh = (unsigned)(b0 & 15ull) * 2u;
+    uint32_t hi = ldr(tw);
+    for (uint32_t off = from;; off += 16u) {
+        if (off >= lim) { less = sl < ql; return lim; }
+        const uint32_t lo = ldr(++tw);
+        const uint32_t t16 = __funnelshift_l(lo, hi, sh);  // text bases spos + off .. + 15
+        hi = lo;
+        const W4 pw = load16_unaligned<true>(pat + off, pend);
+        const uint32_t valid = lim - off;  // >= 1
+        uint32_t bad = 0;
+#pragma unroll
+        for (int wi = 0; wi < 4; wi++) {
+            const uint32_t have = valid >= 4u * wi + 4u ? 0xffffffffu : valid <= 4u * wi ? 0u : (1u << (8u * (valid - 4u * wi))) - 1u;
+            bad |= pw.w[wi] & 0xfcfcfcfcu & have;
+        }
+        if (bad) return thread_compare(p, spos, p0, p1, pat, ql, off, less);
+        const uint32_t mask = valid >= 16u ? 0xffffffffu : 0xffffffffu << (2u * (16u - valid));
+        const uint32_t a = t16 & mask, b = pack16(pw) & mask;
+        if (a != b) { less = a < b; return off + ((uint32_t)__clz((int)(a ^ b)) >> 1); }
+    }
+}
+
 // PHASE 0: patterns in the caller's order.  PHASE 1 (coarse): only the first coarse_levels table levels; writes the lower
 // bound reached (a monotone function of the pattern: the sort key) and the pattern's index.  PHASE 2: patterns in the
 // order of `perm`, i.e. sorted by that key: the lanes of a warp then walk (almost) the same path, so their table and
 // suffix-array loads fall into the same lines instead of 32 different ones.
-// MINB: resident blocks of 256 threads per SM the register budget is set for.  5 (48 registers, a few spills) is best when
-// most patterns go on to the text (more compares in flight: C5 7.7 vs 6.9 Gpat/s), 4 (62 registers, no spills) when the
-// batch is answered from the k-mer cell and the 32-base entries alone (C3 13.0 vs 11.9 Gpat/s).
-template <bool MLR, int PHASE, bool WIDE = false, int MINB = SST_SA_MIN_BLOCKS>
-__global__ void __launch_bounds__(kThreads, MINB)
+// MINB: resident blocks of 256 threads' worth per SM the register budget is set for: 4 (62 registers, no spills) for the 32-base
+// entries, 5 (48 registers) for the other paths.  One pattern per thread: the launch makes one block per kSearchThreads patterns.
+// WIDE: the inlined entries the index holds: 0 = {sa, 15 bases} (8 bytes), 1 = {sa, 32 bases} (16 bytes).
+template <bool MLR, int PHASE, int WIDE = 0, int MINB = SST_SA_MIN_BLOCKS>
+__global__ void __launch_bounds__(kSearchThreads, MINB * (256 / kSearchThreads))
 sa_search_thread_kernel(const __grid_constant__ SaParams p) {
     for (unsigned long long slot = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; slot < p.npat;
          slot += (unsigned long long)gridDim.x * blockDim.x) {
@@ -506,11 +550,11 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
         // ---- inlined bases: inside the k-mer cell a probe reads {sa[m], the 15 bases after the first k} and goes to the text
         // only when those 15 bases equal the pattern's (the suffix that matches, if any) ----
         bool inl = false;
-        using Code = typename std::conditional<WIDE, unsigned long long, uint32_t>::type;
-        constexpr uint32_t NB = WIDE ? 32u : 15u;  // bases inlined per suffix
+        using Code = typename std::conditional<WIDE != 0, unsigned long long, uint32_t>::type;
+        constexpr uint32_t NB = WIDE == 1 ? 32u : 15u;  // bases inlined per suffix
         Code pq = 0, pmask = 0;      // the pattern's bases k .. k+NB-1 (those it has), and the mask of the ones it has
         bool pat_ends = false;       // the pattern ends within those bases: equal bases = the suffix starts with the pattern
-        if (have_range && (WIDE ? (const void*)p.saw : (const void*)p.sax) && ql >= (uint32_t)p.kmer_k) {
+        if (have_range && (WIDE == 1 ? (const void*)p.saw : (const void*)p.sax) && ql >= (uint32_t)p.kmer_k) {
             uint32_t bad = 0;  // a byte outside the alphabet among the first min(ql, 32 or 48) bytes: no inline compare for this pattern
 #pragma unroll
             for (int wi = 0; wi < 8; wi++) {
@@ -521,7 +565,7 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
             const unsigned long long code = ((unsigned long long)pack16(p0) << 32) | pack16(p1);  // bases 0..31
             const uint32_t nb = ql - (uint32_t)p.kmer_k < NB ? ql - (uint32_t)p.kmer_k : NB;  // bases of the pattern after the first k
             pat_ends = nb < NB;
-            if constexpr (WIDE) {
+            if constexpr (WIDE == 1) {
                 uint32_t c2 = 0;  // bases 32..47
                 if (ql > 32u) {
                     const W4 p2 = load16_unaligned<true>(pat + 32, pend);
@@ -543,7 +587,7 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
         }
         // ---- packed cell: range and entries of the pattern's k-mer in one 64-byte line; a pattern that ends within the inlined
         // bases is answered from it alone when the cell is not flagged (one random DRAM access per pattern instead of two) ----
-        if constexpr (WIDE && PHASE == 0) {
+        if constexpr (WIDE == 1 && PHASE == 0) {
             if (p.cells && inl && pat_ends) {
                 const uint4* c = p.cells + (size_t)kx * 8;
                 uint4 c0 = ldc128(c), c1 = ldc128(c + 1), c2 = ldc128(c + 2), c3 = ldc128(c + 3);  // first half: start + entries 0..4
@@ -613,7 +657,7 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
                 uint32_t spos;
                 bool complete;
                 Code code;
-                if constexpr (WIDE) {
+                if constexpr (WIDE == 1) {
                     const uint4 e = ldr(p.saw + m);
                     spos = e.x; complete = e.y == 32u; code = (((unsigned long long)e.z << 32) | e.w) & pmask;
                 } else {
@@ -623,11 +667,12 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
                 if (complete) {  // the suffix has all the inlined bases
                     if (code != pq) {
                         less = code < pq;
-                        if constexpr (WIDE) return (uint32_t)p.kmer_k + ((uint32_t)__clzll((long long)(code ^ pq)) >> 1);
+                        if constexpr (WIDE == 1) return (uint32_t)p.kmer_k + ((uint32_t)__clzll((long long)(code ^ pq)) >> 1);
                         else return (uint32_t)p.kmer_k + (((uint32_t)__clz((int)(code ^ pq)) - 2u) >> 1);
                     }
                     if (pat_ends) { less = false; return ql; }  // every base of the pattern matched: no text access at all
                     const uint32_t known = ((uint32_t)p.kmer_k + NB) & ~15u;  // bytes known to be equal, rounded down to a window
+                    if (p.text2) return packed_compare(p, spos, p0, p1, pat, ql, start > known ? start : known, less);
                     return thread_compare(p, spos, p0, p1, pat, ql, start > known ? start : known, less);
                 }
                 return thread_compare(p, spos, p0, p1, pat, ql, start, less);
@@ -681,7 +726,7 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
         }
         const unsigned long long lo = l;
         p.out_lo[i] = (uint32_t)lo;
-        if (p.out_pos) p.out_pos[i] = lo < p.n ? (inl ? (WIDE ? ldr(p.saw + lo).x : ldr(p.sax + lo).x) : ldr(p.sa + lo)) : 0xffffffffu;  // (inl: the line the probes read)
+        if (p.out_pos) p.out_pos[i] = lo < p.n ? (inl ? (WIDE == 1 ? ldr(p.saw + lo).x : ldr(p.sax + lo).x) : ldr(p.sa + lo)) : 0xffffffffu;  // (inl: the line the probes read)
         if (p.out_hi) {
             // Suffixes starting with q are contiguous from lo: gallop to bracket the end, then bisect.
             unsigned long long a = lo, b = range_end, step = 1;
@@ -795,7 +840,7 @@ sst_sa_t* sst_sa_build_device(const uint8_t* d_text, size_t n, int device) {
     ok = ok && SST_CUDA_OK(cudaMemsetAsync(s->d_text + n, 0, 64, st)) &&
          SST_CUDA_OK(cudaMemcpyAsync(s->d_text, d_text, n, cudaMemcpyDeviceToDevice, st));
     ok = ok && build_sa_device(s->d_text, n, s->d_sa, device) && build_pivots(s) && build_kmer(s) && build_sax(s) && build_cells(s);
-    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); cudaFree(s->d_sax); cudaFree(s->d_saw); cudaFree(s->d_cells); delete s; return nullptr; }
+    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); cudaFree(s->d_sax); cudaFree(s->d_saw); cudaFree(s->d_text2); cudaFree(s->d_cells); delete s; return nullptr; }
     return s;
 }
 
@@ -840,7 +885,7 @@ sst_sa_t* sst_sa_from_parts(const uint8_t* text, size_t n, const uint32_t* sa, i
         }
     }
     ok = ok && build_pivots(s) && build_kmer(s) && build_sax(s) && build_cells(s);
-    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); cudaFree(s->d_sax); cudaFree(s->d_saw); cudaFree(s->d_cells); delete s; return nullptr; }
+    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); cudaFree(s->d_sax); cudaFree(s->d_saw); cudaFree(s->d_text2); cudaFree(s->d_cells); delete s; return nullptr; }
     return s;
 }
 
@@ -853,6 +898,7 @@ void sst_sa_free(sst_sa_t* s) {
     cudaFree(s->d_kmer);
     cudaFree(s->d_sax);
     cudaFree(s->d_saw);
+    cudaFree(s->d_text2);
     cudaFree(s->d_cells);
     delete s;
 }
@@ -969,9 +1015,10 @@ static int sa_search_launch(const sst_sa_t* s, const uint8_t* d_pats, const uint
     p.sax = p.kmer_k && opt(OPT_SA_USE_INLINE) ? s->d_sax : nullptr;
     p.saw = p.kmer_k && opt(OPT_SA_USE_INLINE) ? s->d_saw : nullptr;
     p.cells = p.saw && opt(OPT_SA_USE_CELLS) ? s->d_cells : nullptr;
+    p.text2 = p.kmer_k && opt(OPT_SA_USE_PACKED_TEXT) ? s->d_text2 : nullptr;
     const int lanes = (int)opt(OPT_SA_LANES);
     if (lanes <= 1) {
-        const unsigned grid = (unsigned)std::min<unsigned long long>((npat + kThreads - 1) / kThreads, (unsigned long long)sm_count(s->device) * 8);
+        const unsigned grid = (unsigned)std::min<unsigned long long>((npat + kSearchThreads - 1) / kSearchThreads, (unsigned long long)sm_count(s->device) * 8);
         // Opt-in (SST_SA_SORT_MIN=<patterns>): search in sorted order (see PHASE above): coarse pass over the cache-resident
         // top of the table, radix sort of (lower bound so far, index) on the bits the coarse pass has decided, main pass
         // through perm.  Measured: C3 3.28 vs 4.61 Gpat/s (a loss), C5 2.12 vs 2.03 Gpat/s at 12 coarse levels, worse with
@@ -987,29 +1034,37 @@ static int sa_search_launch(const sst_sa_t* s, const uint8_t* d_pats, const uint
             if (!sc.ensure(s->device, npat, begin_bit, nbits)) return SST_ERR_CUDA;
             if (!SST_CUDA_OK(cudaStreamWaitEvent(st, sc.done, 0))) return SST_ERR_CUDA;
             p.keys = sc.k0; p.ident = sc.v0; p.coarse_levels = coarse;
-            if (mode == SST_SA_MLR) sa_search_thread_kernel<true, 1><<<grid, kThreads, 0, st>>>(p);
-            else sa_search_thread_kernel<false, 1><<<grid, kThreads, 0, st>>>(p);
+            if (mode == SST_SA_MLR) sa_search_thread_kernel<true, 1><<<grid, kSearchThreads, 0, st>>>(p);
+            else sa_search_thread_kernel<false, 1><<<grid, kSearchThreads, 0, st>>>(p);
             cub::DoubleBuffer<uint32_t> dk(sc.k0, sc.k1), dv(sc.v0, sc.v1);
             size_t tb = sc.tmp_bytes;
             if (!SST_CUDA_OK(cub::DeviceRadixSort::SortPairs(sc.tmp, tb, dk, dv, (unsigned long long)npat, begin_bit, nbits, st))) return SST_ERR_CUDA;
             p.perm = dv.Current();
-            if (mode == SST_SA_MLR) sa_search_thread_kernel<true, 2><<<grid, kThreads, 0, st>>>(p);
-            else sa_search_thread_kernel<false, 2><<<grid, kThreads, 0, st>>>(p);
+            if (mode == SST_SA_MLR) sa_search_thread_kernel<true, 2><<<grid, kSearchThreads, 0, st>>>(p);
+            else sa_search_thread_kernel<false, 2><<<grid, kSearchThreads, 0, st>>>(p);
             if (!SST_CUDA_OK(cudaGetLastError()) || !SST_CUDA_OK(cudaEventRecord(sc.done, st))) return SST_ERR_CUDA;
             return SST_OK;
         }
+        // One block of 256 threads per 256 patterns, however many that makes (the hardware block scheduler back-fills an SM as soon
+        // as a block retires).  The grid used to be capped at 8 blocks per SM with a grid-stride loop: every resident thread then
+        // walked the batch in lockstep (all of them at their k-mer load, then all at their entry) and the rate depended on how the
+        // cap divided by the residency -- 5 or 10 blocks per SM on 5 resident ones were the slowest.  C3 16.3 -> 18.8 Gpat/s, C5
+        // 6.96 -> 8.4 (profiles/r2_sa_grid_sweep.log; option SA_GRID = blocks per SM restores a cap).
+        auto go = [&](auto kern) {
+            unsigned long long blocks = (npat + kSearchThreads - 1) / kSearchThreads;
+            if (opt(OPT_SA_GRID) > 0) blocks = std::min<unsigned long long>(blocks, (unsigned long long)sm_count(s->device) * (unsigned long long)opt(OPT_SA_GRID));
+            kern<<<(unsigned)std::min<unsigned long long>(blocks, 0x7fffffffull), kSearchThreads, 0, st>>>(p);
+        };
+        const bool mlr = mode == SST_SA_MLR;
         if (p.saw) {
-            // patterns of up to k + 32 bases never touch the text: a batch of mostly such patterns takes the spill-free build
-            // ... unless the packed cells answer them with one access: then more resident blocks win again (C3 with the cells: 4 blocks
-            // of 256 threads per SM 15.5, 5: 16.7-17.2, 6: 17.0, 8: 13.6 Gpat/s)
-            const bool short_pats = opt(OPT_SA_MINB) ? opt(OPT_SA_MINB) == 4 : (pats_end <= 48ull * npat && !p.cells);
-            if (short_pats) {
-                if (mode == SST_SA_MLR) sa_search_thread_kernel<true, 0, true, 4><<<grid, kThreads, 0, st>>>(p);
-                else sa_search_thread_kernel<false, 0, true, 4><<<grid, kThreads, 0, st>>>(p);
-            } else if (mode == SST_SA_MLR) sa_search_thread_kernel<true, 0, true><<<grid, kThreads, 0, st>>>(p);
-            else sa_search_thread_kernel<false, 0, true><<<grid, kThreads, 0, st>>>(p);
-        } else if (mode == SST_SA_MLR) sa_search_thread_kernel<true, 0><<<grid, kThreads, 0, st>>>(p);
-        else sa_search_thread_kernel<false, 0><<<grid, kThreads, 0, st>>>(p);
+            // Register budget of four resident blocks of 256 threads' worth (62 registers, no spills) unless the option asks for five
+            // (48 registers, a few spills).  With the capped grid five had looked better for long patterns (C5 7.7 vs 6.9) and for
+            // the packed cells; with one pattern per thread the spill-free build wins everywhere: C3 19.3 vs 18.8, C5 8.7 vs 8.3 Gpat/s.
+            if (opt(OPT_SA_MINB) == 5) { if (mlr) go(sa_search_thread_kernel<true, 0, 1, 5>); else go(sa_search_thread_kernel<false, 0, 1, 5>); }
+            else if (mlr) go(sa_search_thread_kernel<true, 0, 1, 4>);
+            else go(sa_search_thread_kernel<false, 0, 1, 4>);
+        } else if (mlr) go(sa_search_thread_kernel<true, 0>);
+        else go(sa_search_thread_kernel<false, 0>);
         return SST_CUDA_OK(cudaGetLastError()) ? SST_OK : SST_ERR_CUDA;
     }
     switch (lanes) {
@@ -1059,6 +1114,19 @@ __global__ void sax_kernel(const uint8_t* __restrict__ t, const uint32_t* __rest
             nx = 0x80000000u | (pack16(w) >> 2);  // 16 bases packed, the last one dropped
         }
         sax[i] = make_uint2(pos, nx);
+    }
+}
+// out[w] = bases 16 w .. 16 w + 15 of the text at 2 bits each, first base most significant (the text is followed by 64 zero bytes)
+__global__ void pack_text_kernel(const uint8_t* __restrict__ t, unsigned long long n, unsigned long long words, uint32_t* __restrict__ out) {
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t v = 0;
+        if (16ull * w < n) {
+            const uint4 x = *reinterpret_cast<const uint4*>(t + 16ull * w);
+            W4 b;
+            b.w[0] = x.x; b.w[1] = x.y; b.w[2] = x.z; b.w[3] = x.w;
+            v = pack16(b);
+        }
+        out[w] = v;
     }
 }
 // saw[i] = {sa[i], bases present (32 = all, else 0), the 32 bases after the first k of suffix(sa[i]) in 64 bits}
@@ -1127,6 +1195,14 @@ static bool build_sax(sst_sa* s) {
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     cudaStream_t st0 = thread_stream(s->device);
+    // the 2-bit packed text (n / 4 bytes) for the compares behind the inlined bases
+    if (opt(OPT_SA_PACKED_TEXT) && s->n / 4 <= free_b / 8) {
+        const unsigned long long words = s->n / 16 + 16;
+        if (cudaMalloc(&s->d_text2, words * 4) == cudaSuccess) {
+            pack_text_kernel<<<sm_count(s->device) * 16, 256, 0, st0>>>(s->d_text, s->n, words, s->d_text2);
+            if (!SST_CUDA_OK(cudaGetLastError()) || !SST_CUDA_OK(cudaStreamSynchronize(st0))) { cudaFree(s->d_text2); s->d_text2 = nullptr; return false; }
+        } else { s->d_text2 = nullptr; (void)cudaGetLastError(); }
+    }
     // 32 bases per suffix (16-byte entries) when half of the free memory holds them (3x10^9 text: 48 GB of the ~130 GB left
     // on a 180 GB part: 7.7 vs 6.3 Gpat/s), else 15 bases (8-byte entries) within a third of it
     if (opt(OPT_SA_INLINE) != 15 && s->n * 16ull <= free_b / (size_t)opt(OPT_SA_INLINE_DIV) && SST_CUDA_OK(cudaMalloc(&s->d_saw, s->n * sizeof(uint4)))) {
@@ -1217,9 +1293,10 @@ sst_sa* clone_sa(const sst_sa* src, int device) {
     if (src->kmer_k) copy(s->d_kmer, src->d_kmer, ((1ull << (2 * src->kmer_k)) + 1) * 4);
     copy(s->d_sax, src->d_sax, s->n * sizeof(uint2));
     copy(s->d_saw, src->d_saw, s->n * sizeof(uint4));
+    if (src->d_text2) copy(s->d_text2, src->d_text2, (s->n / 16 + 16) * 4);
     if (src->d_cells) copy(s->d_cells, src->d_cells, (1ull << (2 * src->kmer_k)) * 128ull);
     ok = ok && SST_CUDA_OK(cudaStreamSynchronize(st));
-    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); cudaFree(s->d_sax); cudaFree(s->d_saw); cudaFree(s->d_cells); delete s; return nullptr; }
+    if (!ok) { cudaFree(s->d_text); cudaFree(s->d_sa); cudaFree(s->d_pivots); cudaFree(s->d_kmer); cudaFree(s->d_sax); cudaFree(s->d_saw); cudaFree(s->d_text2); cudaFree(s->d_cells); delete s; return nullptr; }
     return s;
 }
 }  // namespace sst

@@ -161,8 +161,8 @@ def test_sa_search_kmer_table(gpu, oracle, n, k, inline_bases, monkeypatch):
     [kmer[x], kmer[x+1]).  Patterns shorter than k, patterns with a byte outside the alphabet (fall back to the pivot table),
     patterns made of the text's tail (proper prefixes of padded k-mers), absent patterns, the empty pattern."""
     sst = gpu
-    if inline_bases == "15":  # 8-byte {sa, 15 bases} entries (what an index takes when memory is short) instead of 16-byte {sa, 32 bases}
-        gpu.set_option("SA_INLINE", 15)
+    # 8-byte {sa, 15 bases} entries (what an index takes when memory is short) or 16-byte {sa, 32 bases}
+    gpu.set_option("SA_INLINE", int(inline_bases))
     if k.startswith("force"):  # deeper than one suffix per cell; 16 = the 3 Gbp configuration's depth (2^32 + 1 cells, 64-bit cell index)
         gpu.set_option("SA_KMER_FORCE", int(k[5:]))
     else:
@@ -187,7 +187,19 @@ def test_sa_search_kmer_table(gpu, oracle, n, k, inline_bases, monkeypatch):
         pats += [head[700:700 + ln], head[701:701 + ln - 1] + bytes([(head[701 + ln - 1] + 1) & 3])]
     for at in (33, 36, 44, 47, 48, 50):  # a byte outside the alphabet in the third 16-byte window
         pats += [head[900:900 + at] + bytes([9]) + head[901 + at:970], head[900:900 + at] + bytes([200])]
+    # long patterns (the text compare behind the inlined bases): matches and near-misses of 60 .. 130 bases, a byte outside the
+    # alphabet in the fourth .. eighth 16-byte window, patterns that run into the text's end
+    for ln in list(range(60, 131, 3)) + [kk + d for kk in (4, 7, 12, 15, 16) for d in (94, 95, 96, 97)]:
+        if ln + 1200 < n:
+            pats += [head[1200:1200 + ln], head[1201:1201 + ln - 1] + bytes([(head[1201 + ln - 1] + 1) & 3]),
+                     head[1202:1202 + ln // 2] + bytes([(head[1202 + ln // 2] + 2) & 3]) + head[1203 + ln // 2:1202 + ln]]
+    for at in (52, 63, 64, 79, 95, 96, 100, 111, 112, 120):
+        pats += [head[1500:1500 + at] + bytes([9]) + head[1501 + at:1640], head[1500:1500 + at] + bytes([200])]
+    pats += [tail[-j:] for j in range(90, 135, 4)] + [tail[-j:-3] for j in range(90, 135, 7)]
     _check_search(sst, oracle, s, text, sa, pats)
+    gpu.set_option("SA_USE_PACKED_TEXT", 0)  # compares behind the inlined bases on the byte text instead of the 2-bit packed one
+    _check_search(sst, oracle, s, text, sa, pats)
+    gpu.set_option("SA_USE_PACKED_TEXT", 1)
     gpu.set_option("SA_USE_CELLS", 0)   # without the packed 64-byte cells (range + first five entries in one line)
     _check_search(sst, oracle, s, text, sa, pats[:3000] + pats[-200:])
     gpu.set_option("SA_USE_CELLS", 1)
