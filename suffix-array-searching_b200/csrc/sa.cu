@@ -406,6 +406,12 @@ __device__ __forceinline__ uint4 ldc128(const uint4* p) {
     return v;
 }
 
+// (32 bytes of a cell in one request: sm_100 has 256-bit global loads)
+__device__ __forceinline__ void ldc256(const uint4* p, uint4& a, uint4& b) {
+    asm("ld.global.nc.L2::128B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+
 struct W4 { uint32_t w[4]; };
 
 // 16 bytes starting at byte address `addr` (little endian words); aligned 16-byte chunks starting
@@ -590,7 +596,8 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
         if constexpr (WIDE == 1 && PHASE == 0) {
             if (p.cells && inl && pat_ends) {
                 const uint4* c = p.cells + (size_t)kx * 8;
-                uint4 c0 = ldc128(c), c1 = ldc128(c + 1), c2 = ldc128(c + 2), c3 = ldc128(c + 3);  // first half: start + entries 0..4
+                uint4 c0, c1, c2, c3;  // first half: start + entries 0..4
+                ldc256(c, c0, c1); ldc256(c + 2, c2, c3);
                 if (!(c0.x & 0x80000000u)) {
                     const uint32_t start = c0.x;
                     unsigned below = 0, equal = 0, cnt = 0;
@@ -616,7 +623,7 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
                     };
                     half(0u);
                     if (cnt == 5u && below + equal == 5u) {  // all five are < q or start with q: the cell may hold more of either kind
-                        c0 = ldc128(c + 4); c1 = ldc128(c + 5); c2 = ldc128(c + 6); c3 = ldc128(c + 7);  // entries 5..9 (word 0 of this half is unused)
+                        ldc256(c + 4, c0, c1); ldc256(c + 6, c2, c3);  // entries 5..9 (word 0 of this half is unused)
                         half(5u);
                     }
                     const uint32_t lo = start + below;
