@@ -1101,8 +1101,11 @@ bool build_bucket_aux(sst_index* idx, const uint32_t* d_sorted) {
     // both suffer) or 16 keys per separator (two leaf sectors per query, half as many queries in flight per thread: the search took
     // 2.04 ms per 2^27 queries at 2^30 keys against 1.28 at 2^29).  The 16-bit mode keeps 8 keys per separator with 65536
     // separators per bucket in the same 192 KB: the separators are stored as 16-bit offsets inside their jump cell (bk_jump16_kernel).
-    const bool s16 = (opt(OPT_BK_SEP16) == 1 && opt(OPT_BK_G) <= 0) || (opt(OPT_BK_SEP16) < 0 && opt(OPT_BK_G) <= 0 && opt(OPT_BK_R) <= 0 && div_ceil(n_flat, (size_t)8) > 32768ull * 1024ull);
-    unsigned g = s16 ? 8u : opt(OPT_BK_G) > 0 ? (unsigned)opt(OPT_BK_G) : (div_ceil(n_flat, (size_t)8) > 32768ull * 2048ull ? 16u : 8u);
+    // Above 2^30 slots the 16-bit mode takes 16 keys per separator (two leaf sectors per query): 2048 buckets of 65536 separators
+    // then cover 2^31 slots, which is every u32 tree this library can hold (n < 2^32 and keys <= MAX).
+    const bool s16 = opt(OPT_BK_SEP16) == 1 || (opt(OPT_BK_SEP16) < 0 && opt(OPT_BK_G) <= 0 && opt(OPT_BK_R) <= 0 && div_ceil(n_flat, (size_t)8) > 32768ull * 1024ull);
+    unsigned g = s16 ? ((opt(OPT_BK_G) == 16 || div_ceil(n_flat, (size_t)8) > 65536ull * 2048ull) ? 16u : 8u)
+                     : opt(OPT_BK_G) > 0 ? (unsigned)opt(OPT_BK_G) : (div_ceil(n_flat, (size_t)8) > 32768ull * 2048ull ? 16u : 8u);
     if (g != 8 && g != 16) g = 8;
     const unsigned long long m8 = div_ceil(n_flat, (size_t)g);
     unsigned r = opt(OPT_BK_R) > 0 ? (unsigned)opt(OPT_BK_R) : (m8 > 16384ull * 1024ull ? 32768u : 16384u);
@@ -1110,7 +1113,7 @@ bool build_bucket_aux(sst_index* idx, const uint32_t* d_sorted) {
     if (s16) r = 65536u;  // (fixed: 16-bit offsets need cells = r / 2 >= 2^31 / 2^16 whatever the bucket's key range)
     const unsigned cells = s16 ? r / 2u : r;
     const unsigned long long nb64 = div_ceil((size_t)m8, (size_t)r);
-    if (nb64 > 2048) return true;  // > 2^30 keys: served by the rank-table kernel
+    if (nb64 > 2048) return true;  // (more than 2^31 slots: served by the rank-table kernel)
     BkAux& a = idx->bk;
     const unsigned nb = (unsigned)nb64;
     const unsigned nbp = (unsigned)(div_ceil((size_t)nb, (size_t)kThreads) * kThreads);
@@ -1334,7 +1337,8 @@ static int launch_bucketed_v2(const sst_index* idx, const uint32_t* d_qs, size_t
         mark();  // (no scatter stage: kept so that the five stage times line up with the V1 report)
         {
             void (*kern)(const BkSearchParams, uint32_t*, uint32_t*, const uint32_t*, unsigned, const uint4*, unsigned*) =
-                a.d_sep16 ? (d_idx ? bk_search2_kernel<true, 8, true> : bk_search2_kernel<false, 8, true>)
+                a.d_sep16 ? (a.g == 16 ? (d_idx ? bk_search2_kernel<true, 16, true> : bk_search2_kernel<false, 16, true>)
+                                       : (d_idx ? bk_search2_kernel<true, 8, true> : bk_search2_kernel<false, 8, true>))
                 : a.g == 16 ? (d_idx ? bk_search2_kernel<true, 16, false> : bk_search2_kernel<false, 16, false>) : (d_idx ? bk_search2_kernel<true, 8, false> : bk_search2_kernel<false, 8, false>);
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_search);
             kern<<<sms, kSThreads, smem_search, st>>>(sp, s.qsort, s.isort, s.runs, h.ntp, s.items, s.ctrl);

@@ -1,8 +1,13 @@
 """GPU parity tests (-m gpu) of the reordered-batch pipeline (SCHEME_BUCKETED, csrc/bucketed.cu): partition ->
 search from shared memory -> un-permute must give exactly the oracle's values and indices.  Small separator
 windows (SST_BK_R) force many buckets on small trees; the full-size run is in test_gpu_stree.py."""
+import os
+import sys
+
 import numpy as np
 import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 from test_fuzz import KINDS, make_keys, make_queries
 from util import MAX, gen_queries, gen_vals
@@ -293,16 +298,20 @@ def test_calibrate_sets_the_auto_crossover(gpu, oracle):
     assert sst.STree16.new_params(gen_vals(1000, seed=53), True, False, False).calibrate() == 0  # nothing to calibrate
 
 
+@pytest.mark.parametrize("g", [8, 16])
 @pytest.mark.parametrize("kind,n,nq", [("uniform", 3_000_000, 400_000), ("uniform", 600_001, 100_000), ("clustered", 1_500_000, 200_000),
                                        ("dupes", 2_000_000, 200_000), ("tiny_range", 700_000, 100_000), ("uniform", 1000, 5000)])
-def test_bucketed_sep16(gpu, oracle, kind, n, nq):
+def test_bucketed_sep16(gpu, oracle, kind, n, nq, g):
     """16-bit separator mode (what leaf levels above 2^28 slots take): 65536 separators per bucket stored as offsets inside their
     jump cell, both ends of the cell read, up to six offsets per query from three 32-bit loads, more by bisection.  Forced onto
     small trees: uniform keys (two separators per cell), clustered / duplicate keys (crowded cells: the bisection path, empty
-    cells), plain and Map / Compact layouts, with the index output."""
+    cells), plain and Map / Compact layouts, with the index output.  g = 16 keys per separator (two leaf sectors per query) is
+    what a leaf level above 2^30 slots takes."""
     sst = gpu
     gpu.set_option("BK_MIN_N", 0)
     gpu.set_option("BK_SEP16", 1)
+    if g == 16:
+        gpu.set_option("BK_G", 16)
     rng = np.random.default_rng(n + nq)
     vals = gen_vals(n, seed=n) if kind == "uniform" else make_keys(rng, n, kind)
     qs = make_queries(rng, vals, nq)
@@ -326,3 +335,16 @@ def test_bucketed_several_runs(gpu, oracle):
     vals = gen_vals(700_000, seed=61)
     qs = gen_queries((3 << 20) + 12_345, seed=62, vals=vals)
     _check(sst, oracle, vals, qs, flags=[(1, 0, 0)])
+
+
+@pytest.mark.gpu
+def test_bucketed_two_to_the_31_keys():
+    """The largest tree a u32 index can hold (2^31 slots: 2048 buckets of 65536 16-bit separators, 16 keys each) takes the pipeline:
+    a sample of values and indices equals torch.searchsorted, the whole batch equals the direct kernel (tools/big_tree.py)."""
+    import json
+    import subprocess
+    env = dict(os.environ, N=str(1 << 31), NQ=str(1 << 24), TAG="test")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "big_tree.py")], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["auto_scheme"] == 7 and r["values_ok"] and r["index_ok"] and r["pipeline_equals_direct"], r

@@ -11,10 +11,10 @@ PROF = os.path.join(ROOT, "profiles")
 
 
 def test_launch_summary_matches_bench_line():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "launch_summary.py"), os.path.join(PROF, "r2_s2_launches.csv")],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "launch_summary.py"), os.path.join(PROF, "r2_s6_launches.csv")],
                          capture_output=True, text=True, check=True).stdout
     summ = json.loads(out)
-    bench = json.loads(open(os.path.join(PROF, "r2_s2_bench_launchlist_cmd.json")).read().strip().splitlines()[-1])
+    bench = json.loads(open(os.path.join(PROF, "r2_s6_bench_launchlist_cmd.json")).read().strip().splitlines()[-1])
     traffic = json.load(open(os.path.join(PROF, "traffic.json")))
     shares = {k: v["share_of_step"] for k, v in summ["per_kernel"].items() if v["share_of_step"]}
     assert abs(sum(shares.values()) - 1.0) < 1e-6

@@ -7,7 +7,7 @@ tag=$1
 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1; tail -2 gpurun_out/${tag}_pytest.log
 ( time python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err ) 2> gpurun_out/${tag}_time.log; echo "bench rc=$?"; tail -3 gpurun_out/${tag}_time.log
 python bench.py --impl reference > gpurun_out/${tag}_bench_reference_arm.json 2>> gpurun_out/${tag}_bench.err; echo "ref rc=$?"
-LL="--steps 3 --warmup 3 --no-cpu --sa-text 0 --no-e2e --c4-log2-keys 0 --c5-text 0"
+LL="--steps 3 --warmup 3 --no-cpu --sa-text 0 --no-e2e --c4-log2-keys 0 --c5-text 0 --sa-rep-text 0 --c2-sizes="
 python bench.py $LL > gpurun_out/${tag}_bench_launchlist_cmd.json 2>> gpurun_out/${tag}_bench.err && \
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 800 --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py $LL > gpurun_out/${tag}_ncu_launchlist.log 2>&1
