@@ -751,7 +751,7 @@ def bench_sa_config(args, sst, torch, dev, R, rank, world, name, n, npat_total, 
     out["roofline_frac_binary"] = out["binary_patterns_per_s"] / world * bpp / 1e9 / peak
     # The k-mer table (texts over {0,1,2,3}) answers the first ~log4(n) bases with one load, so the probes SURVEY's model
     # counts are not made and the fraction above can exceed 1.  The floor of THAT path: one sector of the k-mer table and
-    # the cell's {sa, 32 bases} entries (two sectors; a pattern of up to k + 32 bases needs no text), the pattern and the results.
+    # the cell's {sa, 48 bases} entries (two sectors; a pattern of up to k + 48 bases needs no text), the pattern and the results.
     kbpp = 32 + 64 + mean_len + 8
     out["kmer_path"] = {"bytes_per_pattern": kbpp, "roofline_frac_binary": out["binary_patterns_per_s"] / world * kbpp / 1e9 / peak,
                         "note": "floor of the k-mer-table path (3 random sectors + pattern + results): the honest fraction; the path is bound by "

@@ -174,7 +174,7 @@ int sst_query_plan(const sst_index_t* idx, size_t nq, int scheme, int want_index
  *      sas/experiments.rs:19-38; the libsais call at sa_search.rs:33) and binary_search
  *      (sas/sa_search.rs:98-112, sas/experiments.rs:51-64).  A handle also carries GPU-only accelerators that do not
  *      change any result: a pivot-prefix table and, for texts over {0,1,2,3}, a k-mer table (SaNaive's prefix `table`,
- *      sa_search.rs:59-85), the next 15 or 32 bases of every suffix inlined next to its entry ("Inlining values",
+ *      sa_search.rs:59-85), the next 15 or 48 bases of every suffix inlined next to its entry ("Inlining values",
  *      todo.org:18-19) and the text at 2 bits per base for the compares behind them; each is skipped when device memory
  *      is short. */
 sst_sa_t* sst_sa_build(const uint8_t* text, size_t n, int device);               /* GPU SA construction */

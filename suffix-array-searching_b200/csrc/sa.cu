@@ -60,8 +60,10 @@ struct sst_sa {
     // next 15 bases differ from the pattern's is decided without touching the text: one sector instead of two or three
     // fills.  The reference has the idea as a TODO ("Inlining values", todo.org:18-19; btree_legacy.rs:4-131).  GPU-only auxiliary.
     uint2* d_sax = nullptr;
-    // The same with 32 bases per suffix in 16-byte entries {sa, bases present (32 = all), code hi, code lo}, built instead of
-    // d_sax when memory allows (16 bytes per suffix): a pattern of up to k + 32 bases is then answered without the text.
+    // The same with 48 bases per suffix in 16-byte entries {sa, three words of 16 bases}, built instead of d_sax when memory
+    // allows (16 bytes per suffix): a pattern of up to k + 48 bases is then answered without the text.  A suffix with fewer
+    // than k + 48 bases has zero words; the reader tells from sa itself (the entries held 32 bases and a "32 present" word
+    // until the third session of round 2: C5 9.66 -> 10.0 Gpat/s).
     uint4* d_saw = nullptr;
     // The text at 2 bits per base (with the k-mer table, i.e. for texts over {0,1,2,3}): word w = bases 16 w .. 16 w + 15, first base
     // most significant, zero padded.  When the inlined bases of an entry equal the pattern's and the pattern goes on, the rest
@@ -241,7 +243,7 @@ struct SaParams {
     const uint32_t* kmer;  // k-mer table (or null)
     int kmer_k;
     const uint2* sax;      // {sa, next 15 bases} entries (or null)
-    const uint4* saw;      // {sa, 32, next 32 bases} entries (or null; the WIDE kernels)
+    const uint4* saw;      // {sa, next 48 bases in three words} entries (or null; the WIDE kernels)
     const uint4* cells;    // packed k-mer cells, 4 x uint4 each (or null)
     const uint32_t* text2; // the text at 2 bits per base (or null)
     uint32_t* out_probes;  // sa_search_kernel only: iterations of the reference's loop (its `cnt`, sa_search.rs:98-112), or null
@@ -399,14 +401,8 @@ __device__ __forceinline__ uint4 ldr(const uint4* p) {
 #endif
 }
 
-// (the packed k-mer cells are 128 bytes: ask L2 for the whole line, the second half is read only by crowded cells)
-__device__ __forceinline__ uint4 ldc128(const uint4* p) {
-    uint4 v;
-    asm("ld.global.nc.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-}
-
-// (32 bytes of a cell in one request: sm_100 has 256-bit global loads)
+// (the packed k-mer cells are 128 bytes: ask L2 for the whole line, the second half is read only by crowded cells;
+// 32 bytes of a cell in one request: sm_100 has 256-bit global loads)
 __device__ __forceinline__ void ldc256(const uint4* p, uint4& a, uint4& b) {
     asm("ld.global.nc.L2::128B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
@@ -482,6 +478,13 @@ __device__ __forceinline__ uint32_t thread_compare(const SaParams& p, unsigned l
     }
 }
 
+// Mask of the bases a pattern has among bases 16 j .. 16 j + 15 after the first k, when it has nb of them in all (2 bits per
+// base, first base most significant).
+__device__ __forceinline__ uint32_t mask16(uint32_t nb, int j) {
+    const uint32_t from = 16u * (uint32_t)j;
+    return nb >= from + 16u ? 0xffffffffu : nb <= from ? 0u : 0xffffffffu << (2u * (16u - (nb - from)));
+}
+
 // suffix(spos) vs the pattern from base `from` (a multiple of 16) on, through the 2-bit packed text; the caller knows that the
 // bases before `from` are equal.  Same contract as thread_compare (returns lcp, sets less); a pattern byte outside the alphabet
 // or a suffix shorter than `from` hands over to it.
@@ -520,9 +523,9 @@ __device__ __forceinline__ uint32_t packed_compare(const SaParams& p, uint32_t s
 // bound reached (a monotone function of the pattern: the sort key) and the pattern's index.  PHASE 2: patterns in the
 // order of `perm`, i.e. sorted by that key: the lanes of a warp then walk (almost) the same path, so their table and
 // suffix-array loads fall into the same lines instead of 32 different ones.
-// MINB: resident blocks of 256 threads' worth per SM the register budget is set for: 4 (62 registers, no spills) for the 32-base
+// MINB: resident blocks of 256 threads' worth per SM the register budget is set for: 4 (62 registers, no spills) for the 48-base
 // entries, 5 (48 registers) for the other paths.  One pattern per thread: the launch makes one block per kSearchThreads patterns.
-// WIDE: the inlined entries the index holds: 0 = {sa, 15 bases} (8 bytes), 1 = {sa, 32 bases} (16 bytes).
+// WIDE: the inlined entries the index holds: 0 = {sa, 15 bases} (8 bytes), 1 = {sa, 48 bases} (16 bytes).
 template <bool MLR, int PHASE, int WIDE = 0, int MINB = SST_SA_MIN_BLOCKS>
 __global__ void __launch_bounds__(kSearchThreads, MINB * (256 / kSearchThreads))
 sa_search_thread_kernel(const __grid_constant__ SaParams p) {
@@ -557,8 +560,10 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
         // only when those 15 bases equal the pattern's (the suffix that matches, if any) ----
         bool inl = false;
         using Code = typename std::conditional<WIDE != 0, unsigned long long, uint32_t>::type;
-        constexpr uint32_t NB = WIDE == 1 ? 32u : 15u;  // bases inlined per suffix
-        Code pq = 0, pmask = 0;      // the pattern's bases k .. k+NB-1 (those it has), and the mask of the ones it has
+        constexpr uint32_t NB = WIDE == 1 ? 48u : 15u;  // bases inlined per suffix
+        Code pq = 0, pmask = 0;      // the pattern's bases k .. k+14 (k+31 for the packed cells), those it has, and the mask of the ones it has
+        uint32_t pq3[WIDE == 1 ? 3 : 1] = {};  // WIDE: the pattern's bases k .. k+47 in three words of 16 (masked to the nbp it has)
+        uint32_t nbp = 0;
         bool pat_ends = false;       // the pattern ends within those bases: equal bases = the suffix starts with the pattern
         if (have_range && (WIDE == 1 ? (const void*)p.saw : (const void*)p.sax) && ql >= (uint32_t)p.kmer_k) {
             uint32_t bad = 0;  // a byte outside the alphabet among the first min(ql, 32 or 48) bytes: no inline compare for this pattern
@@ -572,19 +577,26 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
             const uint32_t nb = ql - (uint32_t)p.kmer_k < NB ? ql - (uint32_t)p.kmer_k : NB;  // bases of the pattern after the first k
             pat_ends = nb < NB;
             if constexpr (WIDE == 1) {
-                uint32_t c2 = 0;  // bases 32..47
-                if (ql > 32u) {
-                    const W4 p2 = load16_unaligned<true>(pat + 32, pend);
+                uint32_t cw[4] = {(uint32_t)(code >> 32), (uint32_t)code, 0u, 0u};  // bases 0..15, 16..31, 32..47, 48..63
 #pragma unroll
-                    for (int wi = 0; wi < 4; wi++) {
-                        const uint32_t have = ql >= 36u + 4u * wi ? 0xffffffffu : ql <= 32u + 4u * wi ? 0u : (1u << (8u * (ql - 32u - 4u * wi))) - 1u;
-                        bad |= p2.w[wi] & 0xfcfcfcfcu & have;
+                for (int j = 2; j < 4; j++)
+                    if (ql > 16u * j) {
+                        const W4 pj = load16_unaligned<true>(pat + 16 * j, pend);
+#pragma unroll
+                        for (int wi = 0; wi < 4; wi++) {
+                            const uint32_t at = 16u * j + 4u * wi;
+                            const uint32_t have = ql >= at + 4u ? 0xffffffffu : ql <= at ? 0u : (1u << (8u * (ql - at))) - 1u;
+                            bad |= pj.w[wi] & 0xfcfcfcfcu & have;
+                        }
+                        cw[j] = pack16(pj);
                     }
-                    c2 = pack16(p2);
-                }
-                const unsigned sh = 2u * (unsigned)p.kmer_k;  // <= 32
-                pmask = nb ? ~0ull << (2u * (32u - nb)) : 0ull;
-                pq = ((sh >= 64u ? 0ull : code << sh) | (sh ? (unsigned long long)c2 >> (32u - sh) : 0ull)) & pmask;
+                const unsigned sh = 2u * (unsigned)p.kmer_k;  // 2 .. 32: the k bases the cell fixes are shifted out
+                nbp = nb;
+#pragma unroll
+                for (int j = 0; j < 3; j++) pq3[j] = (sh >= 32u ? cw[j + 1] : ((cw[j] << sh) | (cw[j + 1] >> (32u - sh)))) & mask16(nb, j);
+                // (the packed cells hold 32 bases per entry: they answer a pattern that ends within those)
+                pmask = nb >= 32u ? ~0ull : nb ? ~0ull << (2u * (32u - nb)) : 0ull;
+                pq = ((unsigned long long)pq3[0] << 32) | pq3[1];
             } else {
                 pmask = nb ? (0x3fffffffu >> (2u * (15u - nb))) << (2u * (15u - nb)) : 0u;
                 pq = (uint32_t)(code >> (2 * (32 - p.kmer_k - 15))) & pmask;
@@ -594,7 +606,7 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
         // ---- packed cell: range and entries of the pattern's k-mer in one 64-byte line; a pattern that ends within the inlined
         // bases is answered from it alone when the cell is not flagged (one random DRAM access per pattern instead of two) ----
         if constexpr (WIDE == 1 && PHASE == 0) {
-            if (p.cells && inl && pat_ends) {
+            if (p.cells && inl && nbp < 32u) {
                 const uint4* c = p.cells + (size_t)kx * 8;
                 uint4 c0, c1, c2, c3;  // first half: start + entries 0..4
                 ldc256(c, c0, c1); ldc256(c + 2, c2, c3);
@@ -661,28 +673,41 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
         // suffix(sa[m]) vs the pattern: lcp and order, through the inlined bases where they decide
         auto probe = [&](uint32_t m, uint32_t start, bool& less) -> uint32_t {
             if (inl) {
-                uint32_t spos;
-                bool complete;
-                Code code;
                 if constexpr (WIDE == 1) {
-                    const uint4 e = ldr(p.saw + m);
-                    spos = e.x; complete = e.y == 32u; code = (((unsigned long long)e.z << 32) | e.w) & pmask;
+                    const uint4 e = ldr(p.saw + m);  // {sa, bases k .. k+15, k+16 .. k+31, k+32 .. k+47}
+                    if ((unsigned long long)e.x + (unsigned)p.kmer_k + 48ull <= p.n) {  // the suffix has all 48 bases
+                        const uint32_t ew[3] = {e.y, e.z, e.w};
+                        uint32_t x = 0, ev = 0, pv = 0, at = 0;  // first word (16 bases) that differs among the pattern's bases
+#pragma unroll
+                        for (int j = 2; j >= 0; j--) {
+                            const uint32_t a = ew[j] & mask16(nbp, j), d = a ^ pq3[j];
+                            if (d) { x = d; ev = a; pv = pq3[j]; at = 16u * (uint32_t)j; }
+                        }
+                        if (x) {
+                            less = ev < pv;
+                            return (uint32_t)p.kmer_k + at + ((uint32_t)__clz((int)x) >> 1);
+                        }
+                        if (pat_ends) { less = false; return ql; }  // every base of the pattern matched: no text access at all
+                        const uint32_t known = ((uint32_t)p.kmer_k + NB) & ~15u;  // bytes known to be equal, rounded down to a window
+                        if (p.text2) return packed_compare(p, e.x, p0, p1, pat, ql, start > known ? start : known, less);
+                        return thread_compare(p, e.x, p0, p1, pat, ql, start > known ? start : known, less);
+                    }
+                    return thread_compare(p, e.x, p0, p1, pat, ql, start, less);
                 } else {
                     const uint2 e = ldr(p.sax + m);
-                    spos = e.x; complete = (e.y >> 31) != 0u; code = e.y & pmask;
-                }
-                if (complete) {  // the suffix has all the inlined bases
-                    if (code != pq) {
-                        less = code < pq;
-                        if constexpr (WIDE == 1) return (uint32_t)p.kmer_k + ((uint32_t)__clzll((long long)(code ^ pq)) >> 1);
-                        else return (uint32_t)p.kmer_k + (((uint32_t)__clz((int)(code ^ pq)) - 2u) >> 1);
+                    const uint32_t spos = e.x, code = e.y & pmask;
+                    if ((e.y >> 31) != 0u) {  // the suffix has all the inlined bases
+                        if (code != pq) {
+                            less = code < pq;
+                            return (uint32_t)p.kmer_k + (((uint32_t)__clz((int)(code ^ pq)) - 2u) >> 1);
+                        }
+                        if (pat_ends) { less = false; return ql; }  // every base of the pattern matched: no text access at all
+                        const uint32_t known = ((uint32_t)p.kmer_k + NB) & ~15u;  // bytes known to be equal, rounded down to a window
+                        if (p.text2) return packed_compare(p, spos, p0, p1, pat, ql, start > known ? start : known, less);
+                        return thread_compare(p, spos, p0, p1, pat, ql, start > known ? start : known, less);
                     }
-                    if (pat_ends) { less = false; return ql; }  // every base of the pattern matched: no text access at all
-                    const uint32_t known = ((uint32_t)p.kmer_k + NB) & ~15u;  // bytes known to be equal, rounded down to a window
-                    if (p.text2) return packed_compare(p, spos, p0, p1, pat, ql, start > known ? start : known, less);
-                    return thread_compare(p, spos, p0, p1, pat, ql, start > known ? start : known, less);
+                    return thread_compare(p, spos, p0, p1, pat, ql, start, less);
                 }
-                return thread_compare(p, spos, p0, p1, pat, ql, start, less);
             }
             return thread_compare(p, ldr(p.sa + m), p0, p1, pat, ql, start, less);
         };
@@ -1136,15 +1161,17 @@ __global__ void pack_text_kernel(const uint8_t* __restrict__ t, unsigned long lo
         out[w] = v;
     }
 }
-// saw[i] = {sa[i], bases present (32 = all, else 0), the 32 bases after the first k of suffix(sa[i]) in 64 bits}
+// saw[i] = {sa[i], the 48 bases after the first k of suffix(sa[i]) in three words of 16, first base most significant}; zero words
+// when the suffix has fewer (sa[i] + k + 48 > n: the reader derives that from sa[i])
 __global__ void saw_kernel(const uint8_t* __restrict__ t, const uint32_t* __restrict__ sa, unsigned long long n, int k, uint4* __restrict__ saw) {
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
         const uint32_t pos = sa[i];
         const unsigned long long q = (unsigned long long)pos + (unsigned)k;
         uint4 e = make_uint4(pos, 0u, 0u, 0u);
-        if (q + 32ull <= n) {
-            const W4 w0 = load16_unaligned<false>(t + q, t + n + 64), w1 = load16_unaligned<false>(t + q + 16, t + n + 64);
-            e.y = 32u; e.z = pack16(w0); e.w = pack16(w1);
+        if (q + 48ull <= n) {
+            e.y = pack16(load16_unaligned<false>(t + q, t + n + 64));
+            e.z = pack16(load16_unaligned<false>(t + q + 16, t + n + 64));
+            e.w = pack16(load16_unaligned<false>(t + q + 32, t + n + 64));
         }
         saw[i] = e;
     }
@@ -1155,8 +1182,9 @@ __global__ void saw_kernel(const uint8_t* __restrict__ t, const uint32_t* __rest
 namespace sst {
 namespace {
 // cells[x] (128 bytes) = {start | overflow << 31, entries 0..4} {unused word, entries 5..9}, an entry = {sa, code hi, code lo},
-// from the k-mer table and the 32-base entries (see sst_sa::d_cells)
-__global__ void cells_kernel(const uint32_t* __restrict__ kmer, const uint4* __restrict__ saw, unsigned long long ncells, uint4* __restrict__ cells) {
+// from the k-mer table and the first 32 bases of the 48-base entries (see sst_sa::d_cells)
+__global__ void cells_kernel(const uint32_t* __restrict__ kmer, const uint4* __restrict__ saw, unsigned long long ncells, unsigned long long n, int k,
+                             uint4* __restrict__ cells) {
     for (unsigned long long x = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; x < ncells; x += (unsigned long long)gridDim.x * blockDim.x) {
         const uint32_t start = kmer[x], cnt = kmer[x + 1] - start;
         bool overflow = cnt > 10u;
@@ -1166,8 +1194,8 @@ __global__ void cells_kernel(const uint32_t* __restrict__ kmer, const uint4* __r
             for (int i = 0; i < 16; i++) w[i] = 0xffffffffu;
             for (uint32_t i = 0; i < 5u && 5u * h + i < cnt; i++) {
                 const uint4 e = saw[(size_t)start + 5u * h + i];
-                overflow = overflow || e.y != 32u;  // a suffix without all 32 bases (the text's last k + 31): ordinary path
-                w[1 + 3 * i] = e.x; w[2 + 3 * i] = e.z; w[3 + 3 * i] = e.w;
+                overflow = overflow || (unsigned long long)e.x + (unsigned)k + 48ull > n;  // a suffix without its inlined bases (the text's last k + 47): ordinary path
+                w[1 + 3 * i] = e.x; w[2 + 3 * i] = e.y; w[3 + 3 * i] = e.z;  // (the first 32 of the entry's 48 bases)
             }
             if (h == 0) w[0] = start;
             c[4 * h + 1] = make_uint4(w[4], w[5], w[6], w[7]);
@@ -1182,7 +1210,7 @@ __global__ void cells_kernel(const uint32_t* __restrict__ kmer, const uint4* __r
 }  // namespace
 }  // namespace sst
 
-// Packed k-mer cells: only next to the 32-base entries, for k <= 14 (128 bytes x 4^k: 8.6 GB at k = 13), texts below 2^31 bytes
+// Packed k-mer cells: only next to the 16-byte entries, for k <= 14 (128 bytes x 4^k: 8.6 GB at k = 13), texts below 2^31 bytes
 // (bit 31 of the start is the flag) and within a quarter of the free memory; an optional accelerator like the others.
 static bool build_cells(sst_sa* s) {
     if (!s->d_saw || !s->kmer_k || s->kmer_k > 14 || s->n >= (1ull << 31) || !opt(OPT_SA_CELLS)) return true;
@@ -1192,7 +1220,7 @@ static bool build_cells(sst_sa* s) {
     if (ncells * 128ull > free_b / 4) return true;
     if (cudaMalloc(&s->d_cells, ncells * 128ull) != cudaSuccess) { s->d_cells = nullptr; (void)cudaGetLastError(); return true; }
     cudaStream_t st = thread_stream(s->device);
-    cells_kernel<<<sm_count(s->device) * 16, 256, 0, st>>>(s->d_kmer, s->d_saw, ncells, s->d_cells);
+    cells_kernel<<<sm_count(s->device) * 16, 256, 0, st>>>(s->d_kmer, s->d_saw, ncells, s->n, s->kmer_k, s->d_cells);
     if (!SST_CUDA_OK(cudaGetLastError()) || !SST_CUDA_OK(cudaStreamSynchronize(st))) { cudaFree(s->d_cells); s->d_cells = nullptr; return false; }
     return true;
 }
@@ -1210,7 +1238,7 @@ static bool build_sax(sst_sa* s) {
             if (!SST_CUDA_OK(cudaGetLastError()) || !SST_CUDA_OK(cudaStreamSynchronize(st0))) { cudaFree(s->d_text2); s->d_text2 = nullptr; return false; }
         } else { s->d_text2 = nullptr; (void)cudaGetLastError(); }
     }
-    // 32 bases per suffix (16-byte entries) when half of the free memory holds them (3x10^9 text: 48 GB of the ~130 GB left
+    // 48 bases per suffix (16-byte entries) when half of the free memory holds them (3x10^9 text: 48 GB of the ~130 GB left
     // on a 180 GB part: 7.7 vs 6.3 Gpat/s), else 15 bases (8-byte entries) within a third of it
     if (opt(OPT_SA_INLINE) != 15 && s->n * 16ull <= free_b / (size_t)opt(OPT_SA_INLINE_DIV) && SST_CUDA_OK(cudaMalloc(&s->d_saw, s->n * sizeof(uint4)))) {
         saw_kernel<<<sm_count(s->device) * 16, 256, 0, st0>>>(s->d_text, s->d_sa, s->n, s->kmer_k, s->d_saw);

@@ -161,7 +161,7 @@ def test_sa_search_kmer_table(gpu, oracle, n, k, inline_bases, monkeypatch):
     [kmer[x], kmer[x+1]).  Patterns shorter than k, patterns with a byte outside the alphabet (fall back to the pivot table),
     patterns made of the text's tail (proper prefixes of padded k-mers), absent patterns, the empty pattern."""
     sst = gpu
-    # 8-byte {sa, 15 bases} entries (what an index takes when memory is short) or 16-byte {sa, 32 bases}
+    # 8-byte {sa, 15 bases} entries (what an index takes when memory is short) or 16-byte {sa, 48 bases}
     gpu.set_option("SA_INLINE", int(inline_bases))
     if k.startswith("force"):  # deeper than one suffix per cell; 16 = the 3 Gbp configuration's depth (2^32 + 1 cells, 64-bit cell index)
         gpu.set_option("SA_KMER_FORCE", int(k[5:]))
