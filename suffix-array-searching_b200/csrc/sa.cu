@@ -404,7 +404,7 @@ __device__ __forceinline__ uint4 ldr(const uint4* p) {
 // (the packed k-mer cells are 128 bytes: ask L2 for the whole line, the second half is read only by crowded cells;
 // 32 bytes of a cell in one request: sm_100 has 256-bit global loads)
 __device__ __forceinline__ void ldc256(const uint4* p, uint4& a, uint4& b) {
-    asm("ld.global.nc.L2::128B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm("ld.global.nc.L2::64B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
 }
 
