@@ -129,20 +129,13 @@ __device__ __forceinline__ unsigned bk_bucket(const uint16_t* __restrict__ bt, c
 // The same in ONE shared load per query: pk[c] = next << 12 | flag << 11 | lo with lo = bt[c] & 0x7fff, flag = bit 15 of
 // bt[c] and next = the low 18 key bits of splitter lo + 1 when that splitter lies in cell c, else 0x3ffff (no key of the
 // cell is above it).  Flagged cells (two or more splitters with the same 13-bit prefix: skewed keys) take bk_bucket
-// through the global copies of the tables.
+// through the global copies of the tables (the lookup itself is written out in part_tile).
 __device__ __forceinline__ uint32_t bk_pack_cell(const uint16_t* __restrict__ bt, const uint32_t* __restrict__ split, unsigned nb, unsigned c) {
     const unsigned e = bt[c], lo = e & 0x7fffu;
     const uint32_t nx = lo + 1u <= nb ? split[lo + 1u] : kMax;
     const uint32_t thr = (nx >> kBtShift) == c ? (nx & ((1u << kBtShift) - 1u)) : ((1u << kBtShift) - 1u);
     return (thr << 12) | ((e & 0x8000u) ? 0x800u : 0u) | lo;
 }
-__device__ __forceinline__ unsigned bk_bucket_packed(const uint32_t* __restrict__ s_pk, const uint16_t* __restrict__ g_bt,
-                                                     const uint32_t* __restrict__ g_split, uint32_t q) {
-    const uint32_t e = s_pk[q >> kBtShift];
-    if (e & 0x800u) return bk_bucket(g_bt, g_split, q);
-    return (e & 0x7ffu) + ((q & ((1u << kBtShift) - 1u)) > (e >> 12) ? 1u : 0u);
-}
-
 struct BkView {
     const uint16_t* bt;
     const uint32_t* split;
