@@ -236,3 +236,24 @@ def test_sa_packed_cells(gpu, oracle, n, k):
     gpu.set_option("SA_USE_CELLS", 1)
     b = s.search(flat, off)
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_sa_search_capped_grid(gpu, oracle):
+    """The search kernel makes one block per 128 patterns by default; with a capped grid (option SA_GRID = blocks per SM) every
+    thread walks several patterns with a grid stride.  Same results either way, with and without the packed cells."""
+    sst = gpu
+    text = random_text(150_000, seed=91)
+    s = sst.SaNaive.build(text)
+    pats = random_patterns(text, 40_000, seed=92, lo=1, hi=110)
+    rng = np.random.default_rng(93)
+    pats += [bytes(rng.integers(0, 4, int(l), dtype=np.uint8)) for l in rng.integers(1, 60, 5000)]
+    flat, off = sst.pack_patterns(pats)
+    want = s.search(flat, off)
+    _check_search(sst, oracle, s, text, s.sa, pats[:3000])
+    for cap in (1, 3):
+        gpu.set_option("SA_GRID", cap)
+        got = s.search(flat, off)
+        assert all(np.array_equal(a, b) for a, b in zip(want, got)), cap
+        got = s.search(flat, off, sst.SA_MLR)
+        assert all(np.array_equal(a, b) for a, b in zip(want, got)), cap
+    gpu.set_option("SA_GRID", 0)
