@@ -383,9 +383,11 @@ def run_own(args):
                 "kernel": ("reordered-batch pipeline: bk_part_kernel + bk_items_kernel + bk_search2_kernel + bk_unperm_kernel"
                            if bucketed else "stree_search_fast"),
                 "kernel_ms": kern_ms, "launches_per_step": res_launches.value}
-    if bucketed:  # one extra untimed step with per-stage CUDA events (synchronises between stages, so it is not a bench value)
+    if bucketed:  # extra untimed steps with per-stage CUDA events (they synchronise at the end of a call, so they are not a bench value);
+        # the last of three is reported: the first kernel after an idle gap (the partition) reads ~4 % slow
         sst.set_option("BK_TIMING", 1)
-        step(0)
+        for k in range(3):
+            step(k)
         torch.cuda.synchronize()
         sst.set_option("BK_TIMING", 0)
         st_ms = (C.c_double * 5)()
