@@ -519,6 +519,38 @@ __device__ __forceinline__ uint32_t packed_compare(const SaParams& p, uint32_t s
     }
 }
 
+// The same for a pattern whose bases 48 .. 111 are already packed (cw[c] = bases 48 + 16 c .. 63 + 16 c, checked to lie in the
+// alphabet): the 48-base entries leave exactly these chunks to compare for patterns of up to 112 bases, and a pattern is probed more
+// than once (lower bound, then hi), so packing them once per pattern instead of once per probe and chunk removes ~90 of the ~105
+// instructions of a chunk.  Bases 0 .. 47 are known equal; a longer pattern goes on in packed_compare.
+__device__ __forceinline__ uint32_t packed_compare48(const SaParams& p, uint32_t spos, const W4& p0, const W4& p1, const uint8_t* pat, uint32_t ql,
+                                                     uint32_t from, const uint32_t (&cw)[4], bool& less) {
+    const unsigned long long sl64 = p.n - spos;
+    const uint32_t sl = sl64 > 0xffffffffull ? 0xffffffffu : (uint32_t)sl64;
+    if (sl < from) return thread_compare(p, spos, p0, p1, pat, ql, from, less);
+    const uint32_t lim = sl < ql ? sl : ql;
+    const unsigned long long b0 = (unsigned long long)spos + 48ull;
+    const uint32_t* tw = p.text2 + (b0 >> 4);
+    const unsigned sh = (unsigned)(b0 & 15ull) * 2u;
+    const uint32_t c0 = from >= 64u ? 1u : 0u;  // (k = 16: the entry covers bases 16 .. 63, the first chunk is known equal too)
+    uint32_t hi = ldr(tw + c0);
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const uint32_t off = 48u + 16u * (uint32_t)c;
+        if ((uint32_t)c < c0) continue;
+        if (off >= lim) { less = sl < ql; return lim; }
+        const uint32_t lo = ldr(tw + c + 1);
+        const uint32_t t16 = __funnelshift_l(lo, hi, sh);  // text bases spos + off .. + 15
+        hi = lo;
+        const uint32_t valid = lim - off;  // >= 1
+        const uint32_t mask = valid >= 16u ? 0xffffffffu : 0xffffffffu << (2u * (16u - valid));
+        const uint32_t a = t16 & mask, b = cw[c] & mask;
+        if (a != b) { less = a < b; return off + ((uint32_t)__clz((int)(a ^ b)) >> 1); }
+    }
+    if (112u >= lim) { less = sl < ql; return lim; }
+    return packed_compare(p, spos, p0, p1, pat, ql, from > 112u ? from : 112u, less);
+}
+
 // PHASE 0: patterns in the caller's order.  PHASE 1 (coarse): only the first coarse_levels table levels; writes the lower
 // bound reached (a monotone function of the pattern: the sort key) and the pattern's index.  PHASE 2: patterns in the
 // order of `perm`, i.e. sorted by that key: the lanes of a warp then walk (almost) the same path, so their table and
@@ -542,19 +574,19 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
         uint32_t range_end = (uint32_t)p.n;  // no suffix from here on starts with q (bounds the search for hi)
         uint32_t kx = 0;                     // 2-bit code of the pattern's first k bases (padded with the smallest base)
         if (PHASE != 1 && p.kmer_k) {
-            const int k = p.kmer_k;  // <= 16: the bases sit in p0
-            uint32_t x = 0;
-            bool dna = true;
+            const uint32_t k = (uint32_t)p.kmer_k;  // <= 16: the bases sit in p0
+            const uint32_t nk = ql < k ? ql : k;     // bases of the pattern among the first k
+            uint32_t bad_k = 0;
 #pragma unroll
-            for (int j = 0; j < 16; j++)
-                if (j < k) {
-                    const uint32_t b = (p0.w[j >> 2] >> (8 * (j & 3))) & 0xffu;
-                    const bool in = (uint32_t)j < ql;
-                    dna = dna && (!in || b < 4u);
-                    x = x * 4u + (in ? (b & 3u) : 0u);  // a pattern shorter than k is padded with the smallest base
-                }
-            have_range = dna;
-            kx = x;
+            for (int wi = 0; wi < 4; wi++) {
+                const uint32_t have = nk >= 4u * wi + 4u ? 0xffffffffu : nk <= 4u * wi ? 0u : (1u << (8u * (nk - 4u * wi))) - 1u;
+                bad_k |= p0.w[wi] & 0xfcfcfcfcu & have;
+            }
+            // the first 16 bases at 2 bits each, first base most significant; the ones the pattern lacks read as the smallest base
+            // (the loop over the k bytes this replaces cost ~100 of the kernel's ~1800 instructions per pattern)
+            const uint32_t c16 = pack16(p0) & (nk >= 16u ? 0xffffffffu : nk ? 0xffffffffu << (2u * (16u - nk)) : 0u);
+            have_range = bad_k == 0u;
+            kx = c16 >> (32u - 2u * k);
         }
         // ---- inlined bases: inside the k-mer cell a probe reads {sa[m], the 15 bases after the first k} and goes to the text
         // only when those 15 bases equal the pattern's (the suffix that matches, if any) ----
@@ -563,10 +595,11 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
         constexpr uint32_t NB = WIDE == 1 ? 48u : 15u;  // bases inlined per suffix
         Code pq = 0, pmask = 0;      // the pattern's bases k .. k+14 (k+31 for the packed cells), those it has, and the mask of the ones it has
         uint32_t pq3[WIDE == 1 ? 3 : 1] = {};  // WIDE: the pattern's bases k .. k+47 in three words of 16 (masked to the nbp it has)
+        uint32_t cwk[4] = {};                  // WIDE: the pattern's bases 48 .. 111 in four words of 16 (for packed_compare48)
         uint32_t nbp = 0;
         bool pat_ends = false;       // the pattern ends within those bases: equal bases = the suffix starts with the pattern
         if (have_range && (WIDE == 1 ? (const void*)p.saw : (const void*)p.sax) && ql >= (uint32_t)p.kmer_k) {
-            uint32_t bad = 0;  // a byte outside the alphabet among the first min(ql, 32 or 48) bytes: no inline compare for this pattern
+            uint32_t bad = 0;  // a byte outside the alphabet among the first min(ql, 32 or 112) bytes: no inline compare for this pattern
 #pragma unroll
             for (int wi = 0; wi < 8; wi++) {
                 const uint32_t w = wi < 4 ? p0.w[wi] : p1.w[wi - 4];
@@ -577,9 +610,9 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
             const uint32_t nb = ql - (uint32_t)p.kmer_k < NB ? ql - (uint32_t)p.kmer_k : NB;  // bases of the pattern after the first k
             pat_ends = nb < NB;
             if constexpr (WIDE == 1) {
-                uint32_t cw[4] = {(uint32_t)(code >> 32), (uint32_t)code, 0u, 0u};  // bases 0..15, 16..31, 32..47, 48..63
+                uint32_t cw[7] = {(uint32_t)(code >> 32), (uint32_t)code, 0u, 0u, 0u, 0u, 0u};  // bases 0..15, 16..31, .. 96..111
 #pragma unroll
-                for (int j = 2; j < 4; j++)
+                for (int j = 2; j < 7; j++)
                     if (ql > 16u * j) {
                         const W4 pj = load16_unaligned<true>(pat + 16 * j, pend);
 #pragma unroll
@@ -594,6 +627,8 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
                 nbp = nb;
 #pragma unroll
                 for (int j = 0; j < 3; j++) pq3[j] = (sh >= 32u ? cw[j + 1] : ((cw[j] << sh) | (cw[j + 1] >> (32u - sh)))) & mask16(nb, j);
+#pragma unroll
+                for (int j = 0; j < 4; j++) cwk[j] = cw[3 + j];
                 // (the packed cells hold 32 bases per entry: they answer a pattern that ends within those)
                 pmask = nb >= 32u ? ~0ull : nb ? ~0ull << (2u * (32u - nb)) : 0ull;
                 pq = ((unsigned long long)pq3[0] << 32) | pq3[1];
@@ -689,7 +724,7 @@ sa_search_thread_kernel(const __grid_constant__ SaParams p) {
                         }
                         if (pat_ends) { less = false; return ql; }  // every base of the pattern matched: no text access at all
                         const uint32_t known = ((uint32_t)p.kmer_k + NB) & ~15u;  // bytes known to be equal, rounded down to a window
-                        if (p.text2) return packed_compare(p, e.x, p0, p1, pat, ql, start > known ? start : known, less);
+                        if (p.text2) return packed_compare48(p, e.x, p0, p1, pat, ql, start > known ? start : known, cwk, less);  // (known = 48)
                         return thread_compare(p, e.x, p0, p1, pat, ql, start > known ? start : known, less);
                     }
                     return thread_compare(p, e.x, p0, p1, pat, ql, start, less);
