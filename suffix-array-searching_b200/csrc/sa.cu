@@ -528,6 +528,7 @@ __device__ __forceinline__ uint32_t packed_compare48(const SaParams& p, uint32_t
     const unsigned long long sl64 = p.n - spos;
     const uint32_t sl = sl64 > 0xffffffffull ? 0xffffffffu : (uint32_t)sl64;
     if (sl < from) return thread_compare(p, spos, p0, p1, pat, ql, from, less);
+    if (from >= 112u) return packed_compare(p, spos, p0, p1, pat, ql, from, less);  // (mlr on long patterns: the packed chunks are known equal)
     const uint32_t lim = sl < ql ? sl : ql;
     const unsigned long long b0 = (unsigned long long)spos + 48ull;
     const uint32_t* tw = p.text2 + (b0 >> 4);
